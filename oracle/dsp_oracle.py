@@ -1,0 +1,576 @@
+"""CPU oracle for the basic_dsp FFT-centred vector hot path.  TEST INFRASTRUCTURE ONLY.
+
+This module restates, in NumPy, the *semantics* of the reference (liebharc/basic_dsp v0.10.0)
+for the hot path named in BASELINE.json.  It is the checker for the CUDA kernels; it is never
+imported by the product (`basic_dsp_b200/`).  Only `tests/`, `__graft_entry__.smoke()` and
+`bench.py`'s cpu_baseline / `--impl reference` legs may import it.
+
+Parity status: PINNED.  `tests/test_oracle_golden.py` checks every function below against the
+known-answer vectors the reference's own tests hold (tests/golden/reference_kats.json, extracted by
+tests/golden/extract_goldens.py from the reference sources).
+
+The FFT arithmetic of the reference lives in the un-vendored third-party crate `rustfft ^6.0.0`
+(vector/Cargo.toml:40; no Cargo.lock).  rustfft computes the plain unnormalised DFT
+X[k] = sum_n x[n] exp(-+2 pi i n k / N); this oracle evaluates that definition with NumPy's
+pocketfft in complex128, which is exact to ~1e-15 relative and therefore a valid stand-in at the
+tolerances of BASELINE.json (rel-L2 <= 1e-5*log2 N for f32, 1e-12*log2 N for f64).
+
+All file:line citations are relative to the reference tree (/root/reference in the build container).
+Conventions: vectors are complex NumPy arrays (one element per point) or real arrays; `dtype`
+(np.float32 / np.float64) is the precision `T` in which the reference evaluates taps and indices.
+Accumulations are carried out in float64/complex128 so that the oracle is the mathematically exact
+answer the reference approximates in precision T.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+# --------------------------------------------------------------------------------------------
+# Error codes of the C ABI (interop/src/lib.rs:125-151)
+# --------------------------------------------------------------------------------------------
+ERR_OK = 0
+ERR_VECTOR_INVALID = -1
+ERR_SAME_SIZE = 1
+ERR_META_DATA = 2
+ERR_MUST_BE_COMPLEX = 3
+ERR_MUST_BE_REAL = 4
+ERR_MUST_BE_TIME = 5
+ERR_MUST_BE_FREQ = 6
+ERR_INVALID_ARG_LEN = 7
+CONVERT_VOID_OK = 9  # interop/src/lib.rs:100-105 (quirk Q8)
+
+
+# --------------------------------------------------------------------------------------------
+# Impulse / frequency responses, evaluated in precision T  (conv_types.rs:391-518)
+# --------------------------------------------------------------------------------------------
+def _T(dtype):
+    return np.dtype(dtype).type
+
+
+def raised_cosine_impulse(x, rolloff, dtype=np.float64):
+    """RaisedCosineFunction as RealImpulseResponse::calc, conv_types.rs:406-423."""
+    T = _T(dtype)
+    x = T(x)
+    rolloff = T(rolloff)
+    if x == T(0):
+        return T(1)
+    one, two = T(1), T(2)
+    pi = T(math.pi)
+    four = two * two
+    if abs(x) == one / (two * rolloff):
+        arg = pi / two / rolloff
+        return T(np.sin(arg) / arg * pi / four)
+    pi_x = pi * x
+    arg = two * rolloff * x
+    return T(np.sin(pi_x) * np.cos(pi_x * rolloff) / pi_x / (one - (arg * arg)))
+
+
+def raised_cosine_freq(x, rolloff, dtype=np.float64):
+    """RaisedCosineFunction as RealFrequencyResponse::calc, conv_types.rs:434-449."""
+    T = _T(dtype)
+    x = T(x)
+    rolloff = T(rolloff)
+    one, two = T(1), T(2)
+    pi = T(math.pi)
+    ax = abs(x)
+    if ax <= (one - rolloff):
+        return one
+    if (one - rolloff) < ax <= (one + rolloff):
+        return T(one / two * (one + np.cos(pi / rolloff * (ax - (one - rolloff)) / two)))
+    return T(0)
+
+
+def sinc_impulse(x, dtype=np.float64):
+    """SincFunction as RealImpulseResponse::calc, conv_types.rs:479-487."""
+    T = _T(dtype)
+    x = T(x)
+    if x == T(0):
+        return T(1)
+    pi_x = T(math.pi) * x
+    return T(np.sin(pi_x) / pi_x)
+
+
+def sinc_freq(x, dtype=np.float64):
+    """SincFunction as RealFrequencyResponse::calc, conv_types.rs:498-505."""
+    T = _T(dtype)
+    return T(1) if abs(T(x)) <= T(1) else T(0)
+
+
+def make_impulse_response(kind, rolloff, dtype):
+    """interop translate_to_real_convolution_function (interop/src/lib.rs:166-178): 0 = Sinc, else RC."""
+    if kind == 0:
+        return lambda x: sinc_impulse(x, dtype)
+    return lambda x: raised_cosine_impulse(x, rolloff, dtype)
+
+
+def make_frequency_response(kind, rolloff, dtype):
+    """interop translate_to_real_frequency_response (interop/src/lib.rs:180-192)."""
+    if kind == 0:
+        return lambda x: sinc_freq(x, dtype)
+    return lambda x: raised_cosine_freq(x, rolloff, dtype)
+
+
+# --------------------------------------------------------------------------------------------
+# Half swaps  (vector_types/mod.rs:171-191, freq.rs:85-91)
+# --------------------------------------------------------------------------------------------
+def swap_array_halves_literal(data, forward):
+    """Literal restatement of swap_array_halves (vector_types/mod.rs:171-191); small inputs only."""
+    data = list(data)
+    n = len(data)
+    if n == 0:
+        return data
+    if n % 2 == 0:
+        h = n // 2
+        return data[h:] + data[:h]
+    step = n // 2 if forward else n // 2 + 1
+    temp = data[0]
+    pos = step
+    for _ in range(n):
+        pos_new = (pos + step) % n
+        temp, data[pos] = data[pos], temp
+        pos = pos_new
+    return data
+
+
+def fft_shift(x):
+    """FrequencyDomainOperations::fft_shift (freq.rs:85-87) == numpy.fft.fftshift."""
+    x = np.asarray(x)
+    return np.roll(x, len(x) // 2)
+
+
+def ifft_shift(x):
+    """FrequencyDomainOperations::ifft_shift (freq.rs:89-91) == numpy.fft.ifftshift."""
+    x = np.asarray(x)
+    return np.roll(x, -(len(x) // 2))
+
+
+def swap_halves(x):
+    """ReorganizeDataOps::swap_halves (data_reorganization.rs:247-252) -> swap_halves_priv(true)."""
+    return fft_shift(x)
+
+
+# --------------------------------------------------------------------------------------------
+# Transforms  (time_freq/mod.rs:32-63, time_to_freq.rs:136-165, freq_to_time.rs:138-168)
+# --------------------------------------------------------------------------------------------
+def plain_fft(x):
+    """Unnormalised forward DFT, DC at index 0.  Real input is first zero-interleaved to complex
+    (time_to_freq.rs:147-150).  delta <- points*delta (time_freq/mod.rs:54-55) is handled by the
+    caller (see `delta_after_fft`)."""
+    return np.fft.fft(np.asarray(x).astype(np.complex128))
+
+
+def fft(x):
+    """plain_fft followed by fft_shift (time_to_freq.rs:158-165)."""
+    return fft_shift(plain_fft(x))
+
+
+def plain_ifft(X):
+    """Unnormalised inverse DFT (rustfft Inverse direction, no 1/N)."""
+    X = np.asarray(X).astype(np.complex128)
+    return np.fft.ifft(X) * len(X)
+
+
+def ifft(X):
+    """scale(1/points) -> ifft_shift -> plain_ifft (freq_to_time.rs:160-168)."""
+    X = np.asarray(X).astype(np.complex128)
+    return plain_ifft(ifft_shift(X / len(X)))
+
+
+def delta_after_fft(delta, points, dtype):
+    """Q1: delta <- T(points)*delta for both directions (time_freq/mod.rs:54-55)."""
+    T = _T(dtype)
+    return T(T(points) * T(delta))
+
+
+# --------------------------------------------------------------------------------------------
+# convolve_signal: centred circular convolution
+#   (convolution.rs:477-542, time_freq/mod.rs:275-361,456-473,788-848)
+# --------------------------------------------------------------------------------------------
+def conv_len_of(h_points):
+    """conv_len = L - L/2 (time_freq/mod.rs:297-303); (L+1)/2 in overlap_discard (convolution.rs:381)."""
+    return h_points - h_points // 2
+
+
+def convolve_signal_direct(x, h):
+    """Literal definition: y[i] = sum_k x[(i + cl - 1 - k) mod N] * h[k]
+    (convolve_iteration + ReverseWrappingIterator, time_freq/mod.rs:456-473,788-848).
+    O(N*L): small/medium inputs."""
+    x = np.asarray(x)
+    h = np.asarray(h)
+    N, L = len(x), len(h)
+    assert N >= L
+    cl = conv_len_of(L)
+    out_dtype = np.complex128 if (np.iscomplexobj(x) or np.iscomplexobj(h)) else np.float64
+    xx = x.astype(out_dtype)
+    y = np.zeros(N, dtype=out_dtype)
+    idx = np.arange(N)
+    for k in range(L):
+        y += xx[(idx + cl - 1 - k) % N] * out_dtype(h[k])
+    return y
+
+
+def convolve_signal(x, h):
+    """Same result via its FFT identity y = IFFT(FFT(x) * FFT(roll(pad(h, N), -(cl-1)))) in
+    complex128 (error ~1e-15, far below the parity tolerance).  Use for large N."""
+    x = np.asarray(x)
+    h = np.asarray(h)
+    N, L = len(x), len(h)
+    assert N >= L
+    cl = conv_len_of(L)
+    hp = np.zeros(N, dtype=np.complex128)
+    hp[:L] = h
+    hp = np.roll(hp, -(cl - 1))
+    y = np.fft.ifft(np.fft.fft(x.astype(np.complex128)) * np.fft.fft(hp))
+    if not (np.iscomplexobj(x) or np.iscomplexobj(h)):
+        return y.real.copy()
+    return y
+
+
+def check_convolve_signal_args(x_points, x_complex, x_domain, x_delta, h_points, h_complex, h_domain,
+                               h_delta):
+    """Error behaviour of convolve_signal (convolution.rs:485-492 + assert_meta_data! :257-268).
+    Returns the C-ABI result code."""
+    ratio = x_delta / h_delta
+    if x_complex != h_complex or x_domain != h_domain or ratio > 1.1 or ratio < 0.9:
+        return ERR_META_DATA
+    if x_domain != 0:
+        return ERR_MUST_BE_TIME
+    if x_points < h_points:
+        return ERR_INVALID_ARG_LEN
+    return ERR_OK
+
+
+# --------------------------------------------------------------------------------------------
+# convolve with a function-defined impulse response
+#   (convolution.rs:126-255, time_freq/mod.rs:174-213)
+# --------------------------------------------------------------------------------------------
+def would_benefit_from_simd(vec_len, imp_len, ratio, dtype):
+    """convolution.rs:104-110."""
+    T = _T(dtype)
+    ratio = T(ratio)
+    ratio_inv = T(1) / ratio
+    return bool(imp_len <= 202 and vec_len > 2000
+                and abs(np.round(ratio_inv) - ratio_inv) < T(1e-6) and ratio > T(0.5))
+
+
+def function_taps(f, ratio, conv_len, dtype):
+    """Tap table of convolve_function_priv (time_freq/mod.rs:199-209): for window offsets
+    m = -L..L the tap is f(-j*ratio) with j = m counted up in precision T."""
+    T = _T(dtype)
+    ratio = T(ratio)
+    taps = np.empty(2 * conv_len + 1, dtype=dtype)
+    j = -T(conv_len)
+    for q in range(2 * conv_len + 1):
+        taps[q] = f(-j * ratio)
+        j = j + T(1)
+    return taps
+
+
+def function_taps_simd_branch(f, ratio, conv_len, dtype):
+    """Tap table of the `would_benefit_from_simd` branch (convolution.rs:151-167): f(j/ratio),
+    j = -L..L, materialised and handed to convolve_signal."""
+    T = _T(dtype)
+    ratio_inv = T(1) / T(ratio)
+    taps = np.empty(2 * conv_len + 1, dtype=dtype)
+    j = -T(conv_len)
+    for q in range(2 * conv_len + 1):
+        taps[q] = f(j * ratio_inv)
+        j = j + T(1)
+    return taps
+
+
+def convolve_function(x, f, ratio, conv_len, dtype, len_in_T=None):
+    """Convolution::convolve for &dyn RealImpulseResponse (convolution.rs:136-192).
+
+    Non-SIMD branch: y[i] = sum_{m=-L..L} x[(i+m) mod N] * f(-m*ratio), L = min(len, N)
+    (time_freq/mod.rs:174-213; the WrappingIterator pre-increments, :745-763).
+    SIMD branch (ratio == 1 in practice): the taps f(j/ratio) are materialised and routed through
+    convolve_signal, i.e. y[i] = sum_k x[(i + cl - 1 - k) mod N] * t[k] with 2L+1 taps.
+
+    Deliberate deviation: for REAL vectors the reference's SIMD branch fills only every
+    second tap (`i += 2`, convolution.rs:160-167); the oracle and the product implement the evident
+    intent (all taps)."""
+    x = np.asarray(x)
+    N = len(x)
+    if len_in_T is None:
+        len_in_T = 2 * N if np.iscomplexobj(x) else N
+    if would_benefit_from_simd(len_in_T, conv_len, ratio, dtype):
+        taps = function_taps_simd_branch(f, ratio, conv_len, dtype)
+        if len(taps) <= N:
+            return convolve_signal_direct(x, taps.astype(np.float64)) if N * len(taps) < 5e7 else \
+                convolve_signal(x, taps.astype(np.float64))
+        # falls through in the reference to an InvalidArgumentLength panic (.expect); not reachable
+        # for vec_len > 2000 and len <= 202.
+    L = min(conv_len, N)
+    taps = function_taps(f, ratio, L, dtype).astype(np.float64)
+    out_dtype = np.complex128 if np.iscomplexobj(x) else np.float64
+    xx = x.astype(out_dtype)
+    y = np.zeros(N, dtype=out_dtype)
+    idx = np.arange(N)
+    for q in range(2 * L + 1):
+        m = q - L
+        y += xx[(idx + m) % N] * taps[q]
+    return y
+
+
+# --------------------------------------------------------------------------------------------
+# multiply_frequency_response  (convolution.rs:545-610, time_freq/mod.rs:612-723)
+# --------------------------------------------------------------------------------------------
+def multiply_frequency_response(X, f, ratio, dtype):
+    """X[i] <- X[i] * ratio * f(x_i * ratio), x_i = (i - c)/c with c = (points - points%2)/2
+    (is_fft_shifted == false, time_freq/mod.rs:637-648 and fft_swap_x :67-78)."""
+    T = _T(dtype)
+    X = np.asarray(X)
+    n = len(X)
+    offset = n % 2
+    mx = T(n - offset) / T(2)
+    ratio = T(ratio)
+    out = np.array(X, dtype=np.complex128 if np.iscomplexobj(X) else np.float64)
+    j = -T(n - offset) / T(2)
+    for i in range(n):
+        out[i] = out[i] * float(ratio) * float(f(j / mx * ratio))
+        j = j + T(1)
+    return out
+
+
+def fft_swap_x(is_fft_shifted, x_value, x_max):
+    """time_freq/mod.rs:67-78."""
+    if not is_fft_shifted:
+        return x_value / x_max
+    if x_value <= 0.0:
+        return 1.0 + x_value / x_max
+    return -(x_max - x_value + 1.0) / x_max
+
+
+# --------------------------------------------------------------------------------------------
+# interpolatef  (interpolation.rs:92-181,191-315,387-482)
+# --------------------------------------------------------------------------------------------
+def interpolatef_new_len(len_T, factor, dtype):
+    """new_len = round(len*F) rounded up to even (interpolation.rs:406-410), evaluated in T."""
+    T = _T(dtype)
+    n = int(np.round(T(len_T) * T(factor)))
+    return n + n % 2
+
+
+def interpolatef_uses_fast_path(conv_len, new_len, factor, dtype):
+    """interpolation.rs:411-414."""
+    T = _T(dtype)
+    factor = T(factor)
+    return bool(conv_len <= 202 and new_len >= 2000 and abs(np.round(factor) - factor) < T(1e-6))
+
+
+def interpolatef_tap_vectors(f, conv_len, factor_int, delay, dtype):
+    """function_to_vectors (interpolation.rs:133-181): v_s[k] = f(j_k - s/F),
+    j_0 = -(L-1) + delay, j_{k+1} = j_k + 1, all in precision T."""
+    T = _T(dtype)
+    vs = np.empty((factor_int, 2 * conv_len + 1), dtype=dtype)
+    for s in range(factor_int):
+        offset = T(s) / T(factor_int)
+        j = -(T(conv_len) - T(1)) + T(delay)
+        for k in range(2 * conv_len + 1):
+            vs[s, k] = f(j - offset)
+            j = j + T(1)
+    return vs
+
+
+def interpolatef(x, f, factor, delay, conv_len, dtype, delta=1.0):
+    """InterpolationOps::interpolatef (interpolation.rs:387-482).
+
+    * delay <- delay/delta (:397); L = min(conv_len, points/2) (:399-404).
+    * integer-F fast path (interpolate_priv_simd :191-290): interior outputs use
+      rc = ceil(i/F), s = (F - i%F)%F, y[i] = sum_q x[rc+L-1-q] * v_s[q]   (taps reversed, Q6);
+      edge outputs (first/last (2L+1)*F) use interpolate_priv_simd_step :293-315:
+      r = i//F, s = i%F, y[i] = sum_k x[(r-L+1+k) mod N] * v_s[k].
+    * otherwise interpolate_priv_scalar :92-131: center = T(i)/F, r = floor(center),
+      y[i] = sum_{k=0..2L} x[(r-L+k) mod N] * f(-L - (center-r) + delay + k).
+    Output points: new_len (complex: new_len/2)."""
+    T = _T(dtype)
+    x = np.asarray(x)
+    is_complex = np.iscomplexobj(x)
+    N = len(x)
+    len_T = 2 * N if is_complex else N
+    delay = T(delay) / T(delta)
+    L = min(conv_len, N // 2)
+    new_len = interpolatef_new_len(len_T, factor, dtype)
+    new_points = new_len // 2 if is_complex else new_len
+    out_dtype = np.complex128 if is_complex else np.float64
+    xx = x.astype(out_dtype)
+    y = np.zeros(new_points, dtype=out_dtype)
+    if interpolatef_uses_fast_path(L, new_len, factor, dtype):
+        F = int(np.round(T(factor)))
+        vs = interpolatef_tap_vectors(f, L, F, delay, dtype).astype(np.float64)
+        scalar_len = (2 * L + 1) * F
+        i = np.arange(new_points)
+        interior = (i >= scalar_len) & (i < new_points - scalar_len)
+        # interior
+        ii = i[interior]
+        rc = (ii + F - 1) // F
+        s = (F - ii % F) % F
+        acc = np.zeros(len(ii), dtype=out_dtype)
+        for q in range(2 * L + 1):
+            acc += xx[rc + L - 1 - q] * vs[s, q]
+        y[interior] = acc
+        # edges
+        ie = i[~interior]
+        r = ie // F
+        s = ie % F
+        acc = np.zeros(len(ie), dtype=out_dtype)
+        for k in range(2 * L + 1):
+            acc += xx[(r - L + 1 + k) % N] * vs[s, k]
+        y[~interior] = acc
+        return y
+    factor = T(factor)
+    for i in range(new_points):
+        center = T(i) / factor
+        rounded = np.floor(center)
+        r = int(rounded)
+        j = -T(L) - (center - rounded) + delay
+        acc = 0.0
+        for k in range(2 * L + 1):
+            acc = acc + xx[(r - L + k) % N] * float(f(j))
+            j = j + T(1)
+        y[i] = acc
+    return y
+
+
+# --------------------------------------------------------------------------------------------
+# interpolate_lin  (real_interpolation.rs:33-71)
+# --------------------------------------------------------------------------------------------
+def interpolate_lin_dest_len(data_len, factor, dtype):
+    T = _T(dtype)
+    return int(np.round(T(data_len - 1) * T(factor))) + 1
+
+
+def interpolate_lin(x, factor, delay, dtype, replicate_counter_saturation=False):
+    """dest_len = round((len-1)*F)+1; for i < dest_len-1: p = T(i)/F + delay (in T), b = floor(p),
+    y[i] = x[b] + (x[b+1]-x[b])*(p-b) evaluated in T without FMA; last = x[len-1].
+
+    The position p is computed in precision T exactly as the reference does, so the result is
+    bit-reproducible.  Deliberate deviation: the reference counts `i` in T by repeated
+    `+ 1.0` (:53,65), which stops advancing at 2^24 in f32; the product converts the integer index
+    to T (round-to-nearest) instead.  `replicate_counter_saturation=True` reproduces the reference."""
+    T = _T(dtype)
+    x = np.asarray(x, dtype=dtype)
+    n = len(x)
+    dest_len = interpolate_lin_dest_len(n, factor, dtype)
+    F = T(factor)
+    d = T(delay)
+    idx = np.arange(dest_len - 1, dtype=np.int64)
+    i_T = idx.astype(dtype)
+    if replicate_counter_saturation and dtype == np.float32:
+        i_T = np.minimum(i_T, T(2 ** 24))
+    p = (i_T / F + d).astype(dtype)
+    bf = np.floor(p)
+    b = bf.astype(np.int64)
+    y0 = x[b]
+    y1 = x[b + 1]
+    out = np.empty(dest_len, dtype=dtype)
+    out[:-1] = (y0 + ((y1 - y0).astype(dtype) * (p - bf).astype(dtype)).astype(dtype)).astype(dtype)
+    out[-1] = x[n - 1]
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# Elementwise chain  (elementary.rs:327-360,420-455,558-572; complex_to_real.rs:374-405,635-712;
+#                     simd_extensions/fallback.rs:195-231)
+# --------------------------------------------------------------------------------------------
+def real_scale(x, c, dtype):
+    """ScaleOps<T>::scale: every T scalar times c (elementary.rs:334-341)."""
+    x = np.asarray(x)
+    if np.iscomplexobj(x):
+        ct = np.complex64 if dtype == np.float32 else np.complex128
+        x = x.astype(ct)
+        return (x.view(dtype) * _T(dtype)(c)).view(ct)
+    return (x.astype(dtype) * _T(dtype)(c)).astype(dtype)
+
+
+def _cmul_T(a_re, a_im, b_re, b_im, dtype):
+    """(ac - bd, ad + bc) with every product and sum rounded to T, no FMA
+    (num-complex Mul; simd_extensions/fallback.rs:195-203)."""
+    a_re, a_im, b_re, b_im = (np.asarray(v, dtype=dtype) for v in (a_re, a_im, b_re, b_im))
+    re = ((a_re * b_re).astype(dtype) - (a_im * b_im).astype(dtype)).astype(dtype)
+    im = ((a_re * b_im).astype(dtype) + (a_im * b_re).astype(dtype)).astype(dtype)
+    return re, im
+
+
+def complex_scale(x, c, dtype):
+    """ScaleOps<Complex<T>>::scale (elementary.rs:351-359)."""
+    ct = np.complex64 if dtype == np.float32 else np.complex128
+    x = np.asarray(x).astype(ct)
+    re, im = _cmul_T(x.real, x.imag, np.real(c), np.imag(c), dtype)
+    return (re + 1j * im).astype(ct)
+
+
+def mul(x, w, dtype):
+    """ElementaryOps::mul (elementary.rs:558-572): complex (ac-bd, ad+bc) or real product, in T."""
+    x = np.asarray(x)
+    w = np.asarray(w)
+    if np.iscomplexobj(x):
+        ct = np.complex64 if dtype == np.float32 else np.complex128
+        x = x.astype(ct)
+        w = w.astype(ct)
+        re, im = _cmul_T(x.real, x.imag, w.real, w.imag, dtype)
+        return (re + 1j * im).astype(ct)
+    return (x.astype(dtype) * w.astype(dtype)).astype(dtype)
+
+
+def add(x, w, dtype):
+    ct = (np.complex64 if dtype == np.float32 else np.complex128) if np.iscomplexobj(x) else dtype
+    return (np.asarray(x).astype(ct) + np.asarray(w).astype(ct)).astype(ct)
+
+
+def sub(x, w, dtype):
+    ct = (np.complex64 if dtype == np.float32 else np.complex128) if np.iscomplexobj(x) else dtype
+    return (np.asarray(x).astype(ct) - np.asarray(w).astype(ct)).astype(ct)
+
+
+def div(x, w, dtype):
+    """ElementaryOps::div; complex division evaluated in float64 then rounded (<= 1 ulp of the
+    reference's num-complex Div, inside the 4-ulp budget)."""
+    x = np.asarray(x)
+    if np.iscomplexobj(x):
+        ct = np.complex64 if dtype == np.float32 else np.complex128
+        return (x.astype(np.complex128) / np.asarray(w).astype(np.complex128)).astype(ct)
+    return (x.astype(dtype) / np.asarray(w).astype(dtype)).astype(dtype)
+
+
+def magnitude(x, dtype):
+    """|x|: hypot (complex_to_real.rs:376) / sqrt(re^2+im^2) (fallback.rs:223-231); both are within
+    1 ulp of the float64-evaluated value returned here."""
+    x = np.asarray(x).astype(np.complex128)
+    return np.hypot(x.real, x.imag).astype(dtype)
+
+
+def magnitude_squared(x, dtype):
+    x = np.asarray(x)
+    re = x.real.astype(dtype)
+    im = x.imag.astype(dtype)
+    return ((re * re).astype(dtype) + (im * im).astype(dtype)).astype(dtype)
+
+
+def phase(x, dtype):
+    """atan2(im, re) (x.arg(), complex_to_real.rs:402)."""
+    x = np.asarray(x).astype(np.complex128)
+    return np.arctan2(x.imag, x.real).astype(dtype)
+
+
+def ulp_diff(a, b, dtype):
+    """Distance in units in the last place of `dtype` between two real arrays."""
+    a = np.asarray(a, dtype=dtype)
+    b = np.asarray(b, dtype=dtype)
+    it = np.int32 if dtype == np.float32 else np.int64
+    ai = a.view(it).astype(np.int64)
+    bi = b.view(it).astype(np.int64)
+    mask = np.int64(0x7FFFFFFF) if dtype == np.float32 else np.iinfo(np.int64).max
+    ai = np.where(ai < 0, -(ai & mask), ai)  # sign-magnitude -> monotone integer line
+    bi = np.where(bi < 0, -(bi & mask), bi)
+    return np.abs(ai - bi)
+
+
+def rel_l2(a, b):
+    a = np.asarray(a).astype(np.complex128).ravel()
+    b = np.asarray(b).astype(np.complex128).ravel()
+    den = np.linalg.norm(b)
+    return float(np.linalg.norm(a - b) / den) if den > 0 else float(np.linalg.norm(a - b))
