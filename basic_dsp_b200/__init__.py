@@ -1,0 +1,457 @@
+"""basic_dsp_b200 - Python (ctypes) host binding of the B200-native basic_dsp hot path.
+
+The product is `libbasic_dsp_b200.so` (hand-written sm_100a CUDA kernels behind the reference's
+`interop` C ABI, see include/basic_dsp_b200.h).  This module is the thin host side used by the tests
+and the benchmark, in the same style as the reference's own ctypes examples
+(examples/basic_dsp_example.py): it declares the prototypes and wraps a handle in `DspVec`, whose
+methods carry the names of the reference's vector traits (TimeToFrequencyDomainOperations::fft,
+ConvolutionOps::convolve_signal, InterpolationOps::interpolatef, ...).
+
+There is no CPU fallback: importing works everywhere (so that the symbol table can be checked on a
+machine without a GPU), but every compute call needs a CUDA device and raises `DspError` otherwise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int32, c_size_t, c_uint8, c_uint64, c_void_p
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbasic_dsp_b200.so")
+
+F_INVERSE, F_SHIFT, F_MAGNITUDE, F_REAL_INPUT = 1, 2, 4, 8
+TIME, FREQ = 0, 1
+SINC, RAISED_COSINE = 0, 1
+
+
+class DspError(RuntimeError):
+    """A C-ABI call returned a non-zero result code (see the table in include/basic_dsp_b200.h)."""
+
+    def __init__(self, code, what):
+        self.code = int(code)
+        super().__init__("%s failed with result code %d%s" % (what, self.code, _last_error_suffix()))
+
+
+class _VecResult(Structure):
+    _fields_ = [("result_code", c_int32), ("vector", c_void_p)]
+
+
+class _Complex32(Structure):
+    _fields_ = [("re", c_float), ("im", c_float)]
+
+
+class _Complex64(Structure):
+    _fields_ = [("re", c_double), ("im", c_double)]
+
+
+_lib = None
+
+
+def _last_error_suffix():
+    if _lib is None:
+        return ""
+    msg = _lib.bdsp_last_error()
+    return " (%s)" % msg.decode() if msg else ""
+
+
+def _declare(lib):
+    H = c_void_p
+    for s, T, CT in (("32", c_float, _Complex32), ("64", c_double, _Complex64)):
+        RFN = ctypes.CFUNCTYPE(T, c_void_p, T)
+        # ctypes cannot return structs from callbacks.  A {float, float} struct comes back in the low
+        # 64 bits of xmm0 on SysV x86-64, i.e. exactly like a double with that bit pattern; the f64
+        # variant ({double, double} in xmm0:xmm1) needs a native function pointer.
+        CFN = ctypes.CFUNCTYPE(c_double, c_void_p, T) if s == "32" else c_void_p
+        setattr(lib, "RealFn" + s, RFN)
+        setattr(lib, "ComplexFn" + s, CFN)
+        protos = {
+            "new": (H, [c_int32, c_int32, T, c_size_t, T]),
+            "new_with_performance_options": (H, [c_int32, c_int32, T, c_size_t, T, c_size_t]),
+            "new_with_detailed_performance_options": (H, [c_int32, c_int32, T, c_size_t, T] + [c_size_t] * 5),
+            "delete_vector": (None, [H]),
+            "clone": (H, [H]),
+            "get_value": (T, [H, c_size_t]),
+            "set_value": (None, [H, c_size_t, T]),
+            "is_complex": (c_int32, [H]),
+            "get_domain": (c_int32, [H]),
+            "get_len": (c_size_t, [H]),
+            "set_len": (None, [H, c_size_t]),
+            "get_points": (c_size_t, [H]),
+            "get_delta": (T, [H]),
+            "data": (POINTER(T), [H]),
+            "complex_data": (POINTER(CT), [H]),
+            "get_allocated_len": (c_size_t, [H]),
+            "overwrite_data": (_VecResult, [H, POINTER(T), c_size_t]),
+            "real_offset": (_VecResult, [H, T]),
+            "real_scale": (_VecResult, [H, T]),
+            "complex_offset": (_VecResult, [H, T, T]),
+            "complex_scale": (_VecResult, [H, T, T]),
+            "complex_divide": (_VecResult, [H, T, T]),
+            "zero_pad": (_VecResult, [H, c_size_t, c_int32]),
+            "zero_interleave": (_VecResult, [H, c_int32]),
+            "convolve_signal": (_VecResult, [H, H]),
+            "convolve": (_VecResult, [H, c_int32, T, T, c_size_t]),
+            "convolve_real": (_VecResult, [H, RFN, c_void_p, c_uint8, T, c_size_t]),
+            "convolve_complex": (_VecResult, [H, CFN, c_void_p, c_uint8, T, c_size_t]),
+            "multiply_frequency_response": (_VecResult, [H, c_int32, T, T]),
+            "multiply_frequency_response_real": (_VecResult, [H, RFN, c_void_p, c_uint8, T]),
+            "multiply_frequency_response_complex": (_VecResult, [H, CFN, c_void_p, c_uint8, T]),
+            "interpolatef": (_VecResult, [H, c_int32, T, T, T, c_size_t]),
+            "interpolatef_custom": (_VecResult, [H, RFN, c_void_p, c_uint8, T, T, c_size_t]),
+            "interpolate_lin": (_VecResult, [H, T, T]),
+            "get_mag_phase": (c_int32, [H, H, H]),
+        }
+        for name in ("add", "sub", "div", "mul", "add_vector", "sub_vector", "div_vector", "mul_vector"):
+            protos[name] = (_VecResult, [H, H])
+        for name in ("conj", "to_complex", "magnitude", "magnitude_squared", "phase", "to_real", "to_imag",
+                     "plain_fft", "plain_ifft", "fft", "ifft", "swap_halves", "fft_shift", "ifft_shift"):
+            protos[name] = (_VecResult, [H])
+        for name in ("get_magnitude", "get_magnitude_squared", "get_phase", "get_real", "get_imag"):
+            protos[name] = (c_int32, [H, H])
+        for name, (res, args) in protos.items():
+            fn = getattr(lib, name + s)
+            fn.restype, fn.argtypes = res, args
+        ext = {
+            "bdsp_upload": (c_int32, [H, POINTER(T), c_size_t]),
+            "bdsp_download": (c_int32, [H, POINTER(T), c_size_t]),
+            "bdsp_device_ptr": (c_void_p, [H]),
+            "bdsp_scale_mul_mag_phase": (c_int32, [H, T, T, H, H, H, c_int32]),
+            "bdsp_fft_magnitude": (_VecResult, [H]),
+        }
+        for name, (res, args) in ext.items():
+            fn = getattr(lib, name + s)
+            fn.restype, fn.argtypes = res, args
+        for name in ("bdsp_fft_rows_c", "bdsp_convolve_signal_rows_c", "bdsp_conv_plan_create_c"):
+            pass
+    lib.bdsp_version.restype, lib.bdsp_version.argtypes = c_char_p, []
+    lib.bdsp_last_error.restype, lib.bdsp_last_error.argtypes = c_char_p, []
+    lib.bdsp_device_count.restype, lib.bdsp_device_count.argtypes = c_int32, []
+    lib.bdsp_set_device.restype, lib.bdsp_set_device.argtypes = c_int32, [c_int32]
+    lib.bdsp_sync.restype, lib.bdsp_sync.argtypes = c_int32, []
+    lib.bdsp_set_stream.restype, lib.bdsp_set_stream.argtypes = None, [c_void_p]
+    for s in ("32", "64"):
+        f = getattr(lib, "bdsp_fft_rows_c" + s)
+        f.restype, f.argtypes = c_int32, [c_void_p, c_void_p, c_size_t, c_size_t, c_int32]
+        f = getattr(lib, "bdsp_conv_plan_create_c" + s)
+        f.restype, f.argtypes = c_void_p, [c_void_p, c_size_t]
+        f = getattr(lib, "bdsp_convolve_signal_rows_c" + s)
+        f.restype, f.argtypes = c_int32, [c_void_p, c_void_p, c_size_t, c_size_t, c_void_p]
+    lib.bdsp_conv_plan_destroy.restype, lib.bdsp_conv_plan_destroy.argtypes = None, [c_void_p]
+    lib.bdsp_malloc.restype, lib.bdsp_malloc.argtypes = c_void_p, [c_size_t]
+    lib.bdsp_free.restype, lib.bdsp_free.argtypes = None, [c_void_p]
+    lib.bdsp_malloc_host.restype, lib.bdsp_malloc_host.argtypes = c_void_p, [c_size_t]
+    lib.bdsp_free_host.restype, lib.bdsp_free_host.argtypes = None, [c_void_p]
+    lib.bdsp_memcpy_h2d.restype, lib.bdsp_memcpy_h2d.argtypes = c_int32, [c_void_p, c_void_p, c_size_t]
+    lib.bdsp_memcpy_d2h.restype, lib.bdsp_memcpy_d2h.argtypes = c_int32, [c_void_p, c_void_p, c_size_t]
+    lib.bdsp_memset.restype, lib.bdsp_memset.argtypes = c_int32, [c_void_p, c_int32, c_size_t]
+    lib.bdsp_event_create.restype, lib.bdsp_event_create.argtypes = c_void_p, []
+    lib.bdsp_event_destroy.restype, lib.bdsp_event_destroy.argtypes = None, [c_void_p]
+    lib.bdsp_event_record.restype, lib.bdsp_event_record.argtypes = c_int32, [c_void_p]
+    lib.bdsp_event_elapsed_ms.restype, lib.bdsp_event_elapsed_ms.argtypes = c_float, [c_void_p, c_void_p]
+    lib.bdsp_kernel_launch_count.restype, lib.bdsp_kernel_launch_count.argtypes = c_uint64, []
+
+
+def lib():
+    """The loaded C-ABI library.  Raises if libbasic_dsp_b200.so has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "basic_dsp_b200: %s is missing - build it with `python -m basic_dsp_b200.build` "
+                "(there is no CPU fallback)" % LIB_PATH)
+        loaded = ctypes.CDLL(LIB_PATH)
+        _declare(loaded)
+        _lib = loaded
+    return _lib
+
+
+def device_count():
+    return int(lib().bdsp_device_count())
+
+
+def require_device():
+    if device_count() < 1:
+        raise DspError(-1000, "basic_dsp_b200: no CUDA device available (no CPU fallback)")
+
+
+def synchronize():
+    rc = lib().bdsp_sync()
+    if rc:
+        raise DspError(rc, "bdsp_sync")
+
+
+def kernel_launch_count():
+    return int(lib().bdsp_kernel_launch_count())
+
+
+def _check(res, what):
+    if res.result_code != 0:
+        raise DspError(res.result_code, what)
+    return res.vector
+
+
+class DspVec:
+    """A device-resident vector behind an `InteropVec` handle (GenDspVec semantics: real/complex and
+    time/frequency are run-time properties).  Methods mirror the reference's trait methods; the ones
+    that consume `self` in Rust (fft, magnitude, ...) mutate this object in place and return it."""
+
+    def __init__(self, data=None, *, is_complex=None, domain=TIME, delta=1.0, dtype=None, _handle=None, _suffix=None):
+        L = lib()
+        if _handle is not None:
+            self._s = _suffix
+            self._h = _handle
+            return
+        require_device()
+        arr = np.asarray(data)
+        if is_complex is None:
+            is_complex = np.iscomplexobj(arr)
+        if dtype is None:
+            dtype = np.float64 if arr.dtype in (np.float64, np.complex128) else np.float32
+        self._s = "64" if np.dtype(dtype) == np.float64 else "32"
+        flat = self._flatten(arr, is_complex)
+        self._h = getattr(L, "new" + self._s)(1 if is_complex else 0, domain, 0.0, flat.size, delta)
+        self.upload(flat)
+
+    # -- plumbing ---------------------------------------------------------------------------------
+    @property
+    def _T(self):
+        return np.float64 if self._s == "64" else np.float32
+
+    @property
+    def _cT(self):
+        return c_double if self._s == "64" else c_float
+
+    def _fn(self, name):
+        return getattr(lib(), name + self._s)
+
+    def _flatten(self, arr, is_complex):
+        T = self._T
+        if np.iscomplexobj(arr):
+            ct = np.complex128 if T == np.float64 else np.complex64
+            return np.ascontiguousarray(arr.astype(ct)).view(T).ravel()
+        return np.ascontiguousarray(arr.astype(T)).ravel()
+
+    def _call(self, name, *args):
+        res = self._fn(name)(self._h, *args)
+        self._h = res.vector  # callers continue with the returned pointer (interop/src/lib.rs:203-212)
+        if res.result_code != 0:
+            raise DspError(res.result_code, name + self._s)
+        return self
+
+    def result_code_of(self, name, *args):
+        """Runs a mutating C-ABI call and returns its result code instead of raising."""
+        args = [a._h if isinstance(a, DspVec) else a for a in args]
+        res = self._fn(name)(self._h, *args)
+        self._h = res.vector
+        return int(res.result_code)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._fn("delete_vector")(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # -- host access -------------------------------------------------------------------------------
+    def upload(self, flat):
+        flat = np.ascontiguousarray(flat, dtype=self._T)
+        rc = self._fn("bdsp_upload")(self._h, flat.ctypes.data_as(POINTER(self._cT)), flat.size)
+        if rc:
+            raise DspError(rc, "bdsp_upload" + self._s)
+        return self
+
+    def to_numpy(self):
+        """Copy of the data: complex array (one element per point) or real array."""
+        n = self.len()
+        out = np.empty(n, dtype=self._T)
+        rc = self._fn("bdsp_download")(self._h, out.ctypes.data_as(POINTER(self._cT)), n)
+        if rc:
+            raise DspError(rc, "bdsp_download" + self._s)
+        if self.is_complex():
+            return out.view(np.complex128 if self._s == "64" else np.complex64)
+        return out
+
+    def data_via_host_mirror(self):
+        """data32()/data64(): pointer into the synchronised host mirror, copied out."""
+        n = self.len()
+        p = self._fn("data")(self._h)
+        return np.ctypeslib.as_array(p, shape=(max(n, 1),))[:n].copy()
+
+    # -- meta data (Vector<T>, MetaData) --------------------------------------------------------------
+    def len(self):
+        return int(self._fn("get_len")(self._h))
+
+    def points(self):
+        return int(self._fn("get_points")(self._h))
+
+    def is_complex(self):
+        return bool(self._fn("is_complex")(self._h))
+
+    def domain(self):
+        return int(self._fn("get_domain")(self._h))
+
+    def delta(self):
+        return float(self._fn("get_delta")(self._h))
+
+    def alloc_len(self):
+        return int(self._fn("get_allocated_len")(self._h))
+
+    def set_len(self, n):
+        self._fn("set_len")(self._h, n)
+
+    def get_value(self, i):
+        return float(self._fn("get_value")(self._h, i))
+
+    def set_value(self, i, v):
+        self._fn("set_value")(self._h, i, v)
+
+    def clone(self):
+        return DspVec(_handle=self._fn("clone")(self._h), _suffix=self._s)
+
+    @classmethod
+    def zeros(cls, length, *, is_complex=False, domain=TIME, delta=1.0, dtype=np.float32, init=0.0):
+        require_device()
+        s = "64" if np.dtype(dtype) == np.float64 else "32"
+        h = getattr(lib(), "new" + s)(1 if is_complex else 0, domain, init, length, delta)
+        return cls(_handle=h, _suffix=s)
+
+    # -- TimeToFrequencyDomainOperations / FrequencyToTimeDomainOperations ------------------------------
+    def plain_fft(self):
+        return self._call("plain_fft")
+
+    def fft(self):
+        return self._call("fft")
+
+    def plain_ifft(self):
+        return self._call("plain_ifft")
+
+    def ifft(self):
+        return self._call("ifft")
+
+    def fft_magnitude(self):
+        """fft(&mut buffer).magnitude() in one kernel."""
+        return self._call("bdsp_fft_magnitude")
+
+    # -- FrequencyDomainOperations / ReorganizeDataOps ----------------------------------------------------
+    def fft_shift(self):
+        return self._call("fft_shift")
+
+    def ifft_shift(self):
+        return self._call("ifft_shift")
+
+    def swap_halves(self):
+        return self._call("swap_halves")
+
+    def zero_pad(self, points, option=0):
+        return self._call("zero_pad", points, option)
+
+    def zero_interleave(self, factor):
+        return self._call("zero_interleave", factor)
+
+    def to_complex(self):
+        return self._call("to_complex")
+
+    # -- ConvolutionOps / Convolution / FrequencyMultiplication ---------------------------------------------
+    def convolve_signal(self, impulse_response):
+        return self._call("convolve_signal", impulse_response._h)
+
+    def convolve(self, impulse_response, rolloff, ratio, length):
+        """Built-in responses (SINC / RAISED_COSINE) or a Python callable x -> float."""
+        if callable(impulse_response):
+            cb = getattr(lib(), "RealFn" + self._s)(lambda _d, x: float(impulse_response(x)))
+            return self._call("convolve_real", cb, None, 1, ratio, length)
+        return self._call("convolve", impulse_response, rolloff, ratio, length)
+
+    def convolve_complex(self, fn, ratio, length):
+        """`fn`: Python callable x -> complex (f32 vectors only, see _declare) or a native function
+        pointer (int / c_void_p) of type BdspComplexFn32/64."""
+        if callable(fn):
+            if self._s != "32":
+                raise TypeError("Python complex callbacks are only supported for f32 vectors")
+
+            pyfn = fn
+
+            def _cb(_d, x):
+                c = complex(pyfn(x))
+                return float(np.array([c.real, c.imag], dtype=np.float32).view(np.float64)[0])
+            native = getattr(lib(), "ComplexFn32")(_cb)
+            return self._call("convolve_complex", native, None, 0, ratio, length)
+        return self._call("convolve_complex", fn, None, 0, ratio, length)
+
+    def multiply_frequency_response(self, frequency_response, rolloff, ratio):
+        if callable(frequency_response):
+            cb = getattr(lib(), "RealFn" + self._s)(lambda _d, x: float(frequency_response(x)))
+            return self._call("multiply_frequency_response_real", cb, None, 1, ratio)
+        return self._call("multiply_frequency_response", frequency_response, rolloff, ratio)
+
+    # -- InterpolationOps / RealInterpolationOps --------------------------------------------------------------
+    def interpolatef(self, impulse_response, rolloff, factor, delay, length):
+        if callable(impulse_response):
+            cb = getattr(lib(), "RealFn" + self._s)(lambda _d, x: float(impulse_response(x)))
+            return self._call("interpolatef_custom", cb, None, 1, factor, delay, length)
+        return self._call("interpolatef", impulse_response, rolloff, factor, delay, length)
+
+    def interpolate_lin(self, factor, delay):
+        return self._call("interpolate_lin", factor, delay)
+
+    # -- ScaleOps / OffsetOps / ElementaryOps -----------------------------------------------------------------
+    def scale(self, c):
+        if isinstance(c, complex):
+            return self._call("complex_scale", c.real, c.imag)
+        return self._call("real_scale", c)
+
+    def offset(self, c):
+        if isinstance(c, complex):
+            return self._call("complex_offset", c.real, c.imag)
+        return self._call("real_offset", c)
+
+    def add(self, other):
+        return self._call("add", other._h)
+
+    def sub(self, other):
+        return self._call("sub", other._h)
+
+    def mul(self, other):
+        return self._call("mul", other._h)
+
+    def div(self, other):
+        return self._call("div", other._h)
+
+    def conj(self):
+        return self._call("conj")
+
+    # -- ComplexToRealTransformsOps / ComplexToRealGetterOps ----------------------------------------------------
+    def magnitude(self):
+        return self._call("magnitude")
+
+    def magnitude_squared(self):
+        return self._call("magnitude_squared")
+
+    def phase(self):
+        return self._call("phase")
+
+    def to_real(self):
+        return self._call("to_real")
+
+    def to_imag(self):
+        return self._call("to_imag")
+
+    def get_magnitude(self, dest):
+        return int(self._fn("get_magnitude")(self._h, dest._h))
+
+    def get_phase(self, dest):
+        return int(self._fn("get_phase")(self._h, dest._h))
+
+    def get_mag_phase(self, mag, phase):
+        return int(self._fn("get_mag_phase")(self._h, mag._h, phase._h))
+
+    def scale_mul_mag_phase(self, c, w, mag, phase, write_back=False):
+        """Fused scale(c) -> mul(&w) -> get_mag_phase in one pass over memory."""
+        c = complex(c)
+        rc = self._fn("bdsp_scale_mul_mag_phase")(self._h, c.real, c.imag, w._h, mag._h, phase._h, 1 if write_back else 0)
+        if rc:
+            raise DspError(rc, "bdsp_scale_mul_mag_phase" + self._s)
+        return mag, phase

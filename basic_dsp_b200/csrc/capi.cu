@@ -1,0 +1,872 @@
+// C ABI of basic_dsp_b200 (include/basic_dsp_b200.h): device-resident vector handles behind the
+// reference's interop function names (interop/src/facade32.rs / facade64.rs), plus the batched
+// raw-pointer kernels.  Host logic only; all arithmetic runs in the CUDA kernels of this directory.
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/basic_dsp_b200.h"
+#include "common.cuh"
+#include "conv.cuh"
+#include "elementwise.cuh"
+#include "fft.cuh"
+#include "interp.cuh"
+
+using namespace bdsp;
+
+namespace {
+
+thread_local cudaStream_t g_stream = 0;
+
+enum {
+    E_OK = 0, E_INVALID = -1, E_SAME_SIZE = 1, E_META = 2, E_COMPLEX = 3, E_REAL = 4, E_TIME = 5, E_FREQ = 6,
+    E_ARG_LEN = 7, E_EVEN_LEN = 13, E_RESIZE = 14, VOID_OK = 9
+};
+
+// InteropVec<T> analogue: device storage + device scratch ("SingleBuffer": never shrinks, results are
+// produced in the scratch and swapped in = `trade`, vector/src/vector_types/support_std.rs:79-81)
+template <typename T> struct Vec {
+    T* d = nullptr;        size_t cap = 0;    // storage, capacity in T scalars
+    T* scratch = nullptr;  size_t scap = 0;
+    size_t len = 0;                           // valid_len in T scalars
+    T delta = 1;
+    int is_complex = 0;
+    int domain = 0;                           // 0 time, 1 frequency
+    unsigned long long version = 0;           // bumped by every mutation (invalidates caches)
+    // cache: spectrum of this vector used as overlap-save impulse response
+    T* Hs = nullptr; size_t Hs_M = 0; unsigned long long Hs_version = ~0ull;
+    // host mirror for data32()
+    std::vector<T> host;
+};
+
+template <typename T> struct Res { int32_t result_code; Vec<T>* vector; };
+
+template <typename T> bool erroneous(const Vec<T>* v) { return v->len == 0 && isnan((double)v->delta); }
+template <typename T> void mark_invalid(Vec<T>* v) { v->len = 0; v->delta = (T)NAN; v->version++; }
+template <typename T> Res<T> done(Vec<T>* v, int code) {
+    v->version++;
+    Res<T> r;
+    r.result_code = code != 0 ? code : (erroneous(v) ? E_INVALID : E_OK);
+    r.vector = v;
+    return r;
+}
+template <typename T> size_t points_of(const Vec<T>* v) { return v->is_complex ? v->len / 2 : v->len; }
+
+template <typename T> int reserve(T** p, size_t* cap, size_t want, bool keep, size_t keep_n) {
+    if (*cap >= want) return 0;
+    T* n = nullptr;
+    BDSP_CUDA_OK(cudaMalloc(&n, (want ? want : 1) * sizeof(T)));
+    if (keep && *p && keep_n) BDSP_CUDA_OK(cudaMemcpyAsync(n, *p, keep_n * sizeof(T), cudaMemcpyDeviceToDevice, g_stream));
+    if (*p) {
+        BDSP_CUDA_OK(cudaStreamSynchronize(g_stream));
+        BDSP_CUDA_OK(cudaFree(*p));
+    }
+    *p = n;
+    *cap = want;
+    return 0;
+}
+template <typename T> int ensure_scratch(Vec<T>* v, size_t n) { return reserve(&v->scratch, &v->scap, n, false, 0); }
+template <typename T> void trade(Vec<T>* v) {
+    T* p = v->d; v->d = v->scratch; v->scratch = p;
+    size_t c = v->cap; v->cap = v->scap; v->scap = c;
+}
+
+template <typename T> Vec<T>* vec_new(int is_complex, int domain, T init, size_t length, T delta) {
+    Vec<T>* v = new Vec<T>();
+    v->is_complex = is_complex != 0;
+    v->domain = domain == 0 ? 0 : 1;
+    v->delta = delta;
+    if (reserve(&v->d, &v->cap, length, false, 0) != 0) { fprintf(stderr, "basic_dsp_b200: %s\n", get_last_error()); abort(); }
+    // to_gen_dsp_vec: a complex vector needs an even number of scalars (support_std.rs:369)
+    v->len = (v->is_complex && (length % 2)) ? 0 : length;
+    if (length) ew_fill<T>(v->d, length, (double)init, g_stream);
+    return v;
+}
+
+template <typename T> void vec_delete(Vec<T>* v) {
+    if (!v) return;
+    cudaStreamSynchronize(g_stream);
+    if (v->d) cudaFree(v->d);
+    if (v->scratch) cudaFree(v->scratch);
+    if (v->Hs) cudaFree(v->Hs);
+    delete v;
+}
+
+template <typename T> int vec_resize(Vec<T>* v, size_t len) {
+    if (v->is_complex && (len % 2)) return E_EVEN_LEN;
+    if (len > v->cap) {
+        size_t old = v->cap;
+        int rc = reserve(&v->d, &v->cap, len, true, old);
+        if (rc) return rc;
+        // Vec::resize(len, 0): new storage is zero filled (support_std.rs:227-230)
+        BDSP_CUDA_OK(cudaMemsetAsync(v->d + old, 0, (len - old) * sizeof(T), g_stream));
+    }
+    v->len = len;
+    v->version++;
+    return 0;
+}
+
+template <typename T> bool meta_agrees(const Vec<T>* a, const Vec<T>* b) {
+    // assert_meta_data! (elementary.rs:370-381, convolution.rs:257-268)
+    T ratio = a->delta / b->delta;
+    return a->is_complex == b->is_complex && a->domain == b->domain && !(ratio > (T)1.1) && !(ratio < (T)0.9);
+}
+
+// ---- transforms ------------------------------------------------------------------------------------
+template <typename T> Res<T> op_fft(Vec<T>* v, bool inverse, bool shifted, bool magnitude) {
+    // time_to_freq.rs:136-165, freq_to_time.rs:138-168, time_freq/mod.rs:32-63
+    const int want_domain = inverse ? 1 : 0;
+    if (v->domain != want_domain) {
+        mark_invalid(v);
+        v->is_complex = 1;
+        v->domain = 1;
+        return done(v, 0);
+    }
+    const size_t points = points_of(v);
+    FftOpts o;
+    o.inverse = inverse;
+    o.real_input = !v->is_complex;
+    o.magnitude = magnitude;
+    if (points) {
+        if (shifted && !inverse) o.out_rot = points / 2;                       // fft_shift (freq.rs:85-87)
+        if (shifted && inverse) {                                              // ifft: scale -> ifft_shift -> plain_ifft
+            o.in_rot = points / 2;
+            o.scale = (double)((T)1 / (T)points);
+        }
+        const size_t out_scalars = magnitude ? points : 2 * points;
+        int rc = ensure_scratch(v, 2 * points);
+        if (!rc) rc = fft_exec<T>(v->d, v->scratch, points, 1, o, nullptr, 0, g_stream);
+        if (rc) return done(v, rc);
+        trade(v);
+        v->len = out_scalars;
+    }
+    v->delta = (T)points * v->delta;                                           // Q1: both directions
+    v->is_complex = magnitude ? 0 : 1;
+    v->domain = inverse ? 0 : 1;                                               // Q2: ifft reports Time
+    return done(v, 0);
+}
+
+template <typename T> Res<T> op_rotate(Vec<T>* v, bool forward) {
+    // swap_halves_priv (vector_types/mod.rs:510-524): new[(p + step) % n] = old[p]
+    const size_t n = points_of(v);
+    if (n < 2) return done(v, 0);
+    const size_t step = forward ? n / 2 : n - n / 2;
+    int rc = ensure_scratch(v, v->len);
+    if (!rc) rc = ew_rotate<T>(v->d, v->scratch, n, step, v->is_complex ? 2 : 1, g_stream);
+    if (rc) return done(v, rc);
+    trade(v);
+    return done(v, 0);
+}
+
+template <typename T> Res<T> op_zero_interleave(Vec<T>* v, int factor) {
+    if (factor < 1) return done(v, E_ARG_LEN);
+    const size_t n = points_of(v);
+    const size_t new_len = v->len * (size_t)factor;
+    if (n) {
+        int rc = ensure_scratch(v, new_len);
+        if (!rc) rc = ew_zero_interleave<T>(v->d, v->scratch, n, factor, v->is_complex ? 2 : 1, g_stream);
+        if (rc) return done(v, rc);
+        trade(v);
+    }
+    v->len = new_len;
+    return done(v, 0);
+}
+
+template <typename T> Res<T> op_to_complex(Vec<T>* v) {
+    // to_complex_b (real_to_complex.rs:96-111)
+    if (v->is_complex) { mark_invalid(v); return done(v, 0); }
+    Res<T> r = op_zero_interleave(v, 2);
+    v->is_complex = 1;
+    return done(v, r.result_code);
+}
+
+template <typename T> Res<T> op_zero_pad(Vec<T>* v, size_t points, int option) {
+    // zero_pad_b (data_reorganization.rs:407-463)
+    const size_t len_before = v->len;
+    const size_t step = v->is_complex ? 2 : 1;
+    const size_t len = step * points;
+    if (len <= len_before) return done(v, E_ARG_LEN);
+    int rc = ensure_scratch(v, len);
+    if (rc) return done(v, rc);
+    T* t = v->scratch;
+    cudaMemsetAsync(t, 0, len * sizeof(T), g_stream);
+    if (option == 0) {
+        cudaMemcpyAsync(t, v->d, len_before * sizeof(T), cudaMemcpyDeviceToDevice, g_stream);
+    } else if (option == 1) {
+        size_t diff = (len - len_before) / step;
+        size_t right = diff / 2, left = (diff - right) * step;
+        cudaMemcpyAsync(t + left, v->d, len_before * sizeof(T), cudaMemcpyDeviceToDevice, g_stream);
+    } else {
+        size_t pb = len_before / step;
+        size_t right = (pb / 2) * step, left = (pb - pb / 2) * step;
+        cudaMemcpyAsync(t + len - right, v->d + len_before - right, right * sizeof(T), cudaMemcpyDeviceToDevice, g_stream);
+        cudaMemcpyAsync(t, v->d, left * sizeof(T), cudaMemcpyDeviceToDevice, g_stream);
+    }
+    trade(v);
+    v->len = len;
+    return done(v, 0);
+}
+
+// ---- elementwise -----------------------------------------------------------------------------------
+template <typename T> Res<T> op_binary(Vec<T>* v, const Vec<T>* o, int op) {
+    // elementary.rs:383-455,540-589
+    if (v->len != o->len) return done(v, E_SAME_SIZE);
+    if (!meta_agrees(v, o)) return done(v, E_META);
+    int rc = 0;
+    if (v->len) rc = ew_binary<T>(op, v->d, o->d, v->d, v->len, v->is_complex, g_stream);
+    return done(v, rc);
+}
+
+template <typename T> Res<T> op_real_const(Vec<T>* v, int op, T c) {
+    int rc = 0;
+    if (v->len) {
+        if (op == EW_OFFSET && v->is_complex) rc = ew_complex_const<T>(EW_OFFSET, v->d, v->d, v->len / 2, (double)c, 0.0, g_stream);
+        else rc = ew_scalar<T>(op, v->d, v->d, v->len, (double)c, g_stream);
+    }
+    return done(v, rc);
+}
+
+template <typename T> Res<T> op_complex_const(Vec<T>* v, int op, T re, T im) {
+    if (!v->is_complex) { mark_invalid(v); return done(v, 0); }   // assert_complex!
+    int rc = 0;
+    if (v->len) rc = ew_complex_const<T>(op, v->d, v->d, v->len / 2, (double)re, (double)im, g_stream);
+    return done(v, rc);
+}
+
+template <typename T> Res<T> op_complex_divide(Vec<T>* v, T re, T im) {
+    // Complex::new(1,0) / Complex::new(re,im) evaluated in T (num-complex Div), facade32.rs:550-557
+    T ns = re * re + im * im;
+    T qr = ((T)1 * re + (T)0 * im) / ns;
+    T qi = ((T)0 * re - (T)1 * im) / ns;
+    return op_complex_const(v, EW_SCALE, qr, qi);
+}
+
+template <typename T> Res<T> op_c2r(Vec<T>* v, int op) {
+    // complex_to_real.rs:365-478
+    if (!v->is_complex) { mark_invalid(v); v->is_complex = 0; return done(v, 0); }
+    const size_t points = v->len / 2;
+    if (points) {
+        int rc = ensure_scratch(v, points);
+        if (!rc) rc = ew_complex_to_real<T>(op, v->d, v->scratch, points, g_stream);
+        if (rc) return done(v, rc);
+        trade(v);
+    }
+    v->len = points;
+    v->is_complex = 0;
+    return done(v, 0);
+}
+
+template <typename T> int32_t op_get_c2r(Vec<T>* v, Vec<T>* dst, int op) {
+    // complex_to_real.rs:595-680; convert_void -> 9 (Q8)
+    if (!v->is_complex || dst->is_complex) { dst->len = 0; dst->version++; return VOID_OK; }
+    const size_t points = v->len / 2;
+    if (vec_resize(dst, points) > 0) return VOID_OK;
+    dst->delta = v->delta;
+    if (points) {
+        int rc = ew_complex_to_real<T>(op, v->d, dst->d, points, g_stream);
+        if (rc) return rc;
+    }
+    dst->version++;
+    return VOID_OK;
+}
+
+template <typename T> int32_t op_get_mag_phase(Vec<T>* v, Vec<T>* mag, Vec<T>* ph) {
+    if (!v->is_complex || mag->is_complex || ph->is_complex) {
+        mag->len = 0; ph->len = 0; mag->version++; ph->version++;
+        return VOID_OK;
+    }
+    const size_t points = v->len / 2;
+    vec_resize(mag, points);
+    vec_resize(ph, points);
+    if (points) {
+        int rc = ew_mag_phase<T>(v->d, mag->d, ph->d, points, g_stream);
+        if (rc) return rc;
+    }
+    return VOID_OK;
+}
+
+// ---- impulse responses evaluated on the host in precision T (conv_types.rs:391-518) ---------------
+template <typename T> T host_sinc(T x) {
+    if (x == (T)0) return (T)1;
+    T pi_x = (T)M_PI * x;
+    return (T)sin(pi_x) / pi_x;
+}
+template <typename T> T host_rc(T x, T rolloff) {
+    if (x == (T)0) return (T)1;
+    const T one = 1, two = 2, pi = (T)M_PI;
+    const T four = two * two;
+    if ((T)fabs(x) == one / (two * rolloff)) {
+        T arg = pi / two / rolloff;
+        return (T)sin(arg) / arg * pi / four;
+    }
+    T pi_x = pi * x;
+    T arg = two * rolloff * x;
+    return (T)sin(pi_x) * (T)cos(pi_x * rolloff) / pi_x / (one - (arg * arg));
+}
+template <typename T> T host_sinc_freq(T x) { return (T)fabs(x) <= (T)1 ? (T)1 : (T)0; }
+template <typename T> T host_rc_freq(T x, T rolloff) {
+    const T one = 1, two = 2, pi = (T)M_PI;
+    T ax = (T)fabs(x);
+    if (ax <= (one - rolloff)) return one;
+    if (((one - rolloff) < ax) && (ax <= (one + rolloff)))
+        return one / two * (one + (T)cos(pi / rolloff * (ax - (one - rolloff)) / two));
+    return (T)0;
+}
+
+// generic host evaluator: built-in kinds or a C callback
+template <typename T> struct RealFn {
+    int kind = 0;        // 0 sinc, 1 raised cosine, 2 callback
+    T rolloff = 0;
+    T (*fn)(const void*, T) = nullptr;
+    const void* data = nullptr;
+    bool freq = false;   // evaluate the frequency response instead of the impulse response
+    T operator()(T x) const {
+        if (kind == 2) return fn(data, x);
+        if (freq) return kind == 0 ? host_sinc_freq<T>(x) : host_rc_freq<T>(x, rolloff);
+        return kind == 0 ? host_sinc<T>(x) : host_rc<T>(x, rolloff);
+    }
+};
+
+template <typename T> int upload_table(const std::vector<T>& h, T** dev) {
+    BDSP_CUDA_OK(cudaMalloc(dev, (h.size() ? h.size() : 1) * sizeof(T)));
+    BDSP_CUDA_OK(cudaMemcpyAsync(*dev, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, g_stream));
+    BDSP_CUDA_OK(cudaStreamSynchronize(g_stream));  // h is pageable and dies with the caller's frame
+    return 0;
+}
+
+// ---- convolution -----------------------------------------------------------------------------------
+// circular FIR / fast convolution dispatch for taps resident on the device
+template <typename T>
+int convolve_taps(Vec<T>* v, const T* h_dev, size_t L, bool h_complex, T** Hs_cache, size_t* Hs_M, bool* Hs_valid) {
+    const size_t N = points_of(v);
+    int rc = ensure_scratch(v, v->len);
+    if (rc) return rc;
+    const size_t cl = L - L / 2;
+    const size_t direct_max = h_complex ? 24 : 96;
+    if (L <= direct_max) {
+        rc = fir_convolve<T>(v->d, v->scratch, h_dev, N, 1, L, cl, v->is_complex, h_complex, g_stream);
+    } else if (L <= ols_max_taps<T>()) {
+        const size_t M = ols_block_len<T>(L);
+        T* Hs = nullptr;
+        bool own = false;
+        if (Hs_cache && *Hs_valid && *Hs_M == M) Hs = *Hs_cache;
+        else {
+            BDSP_CUDA_OK(cudaMalloc(&Hs, 2 * M * sizeof(T)));
+            rc = ols_prepare<T>(h_dev, L, !h_complex, Hs, M, g_stream);
+            if (rc) { cudaFree(Hs); return rc; }
+            if (Hs_cache) {
+                if (*Hs_cache) { cudaStreamSynchronize(g_stream); cudaFree(*Hs_cache); }
+                *Hs_cache = Hs; *Hs_M = M; *Hs_valid = true;
+            } else own = true;
+        }
+        rc = ols_convolve<T>(v->d, v->scratch, N, 1, L, Hs, M, !v->is_complex, g_stream);
+        if (own) { cudaStreamSynchronize(g_stream); cudaFree(Hs); }
+    } else {
+        rc = fft_convolve_full<T>(v->d, v->scratch, h_dev, N, 1, L, !v->is_complex, !h_complex, g_stream);
+    }
+    if (rc) return rc;
+    trade(v);
+    return 0;
+}
+
+template <typename T> Res<T> op_convolve_signal(Vec<T>* v, Vec<T>* h) {
+    // convolution.rs:477-542
+    if (!meta_agrees(v, h)) return done(v, E_META);
+    if (v->domain != 0) return done(v, E_TIME);
+    const size_t N = points_of(v), L = points_of(h);
+    if (N < L) return done(v, E_ARG_LEN);
+    if (N == 0 || L == 0) {
+        if (N) cudaMemsetAsync(v->d, 0, v->len * sizeof(T), g_stream);
+        return done(v, 0);
+    }
+    bool valid = h->Hs_version == h->version;
+    int rc = convolve_taps<T>(v, h->d, L, h->is_complex, &h->Hs, &h->Hs_M, &valid);
+    if (valid) h->Hs_version = h->version;
+    return done(v, rc);
+}
+
+template <typename T> Res<T> op_convolve_fn(Vec<T>* v, const RealFn<T>& f, T ratio, size_t len) {
+    // convolution.rs:136-192 (real impulse response)
+    if (v->domain != 0) { mark_invalid(v); return done(v, 0); }   // assert_time!
+    const size_t N = points_of(v);
+    if (N == 0) return done(v, 0);
+    const T ratio_inv = (T)1 / ratio;
+    const bool simd_branch = len <= 202 && v->len > 2000 && (T)fabs((T)round(ratio_inv) - ratio_inv) < (T)1e-6 && ratio > (T)0.5;
+    std::vector<T> taps;
+    if (simd_branch) {
+        // taps f(j/ratio), j = -len..len, handed to convolve_signal (convolution.rs:151-172).
+        // Deviation Q4: for real vectors the reference fills only every second tap.
+        T j = -(T)len;
+        for (size_t q = 0; q < 2 * len + 1; q++) { taps.push_back(f(j * ratio_inv)); j = j + (T)1; }
+    } else {
+        // convolve_function_priv (time_freq/mod.rs:174-213): y[i] = sum_{m=-L..L} x[i+m] f(-m*ratio)
+        // == circular FIR with h[k] = f(-(L-k)*ratio), k = 0..2L (centre cl = L+1)
+        const size_t L = len > N ? N : len;
+        std::vector<T> t(2 * L + 1);
+        T j = -(T)L;
+        for (size_t q = 0; q < 2 * L + 1; q++) { t[q] = f(-j * ratio); j = j + (T)1; }
+        taps.assign(t.rbegin(), t.rend());
+    }
+    if (taps.size() > N) {
+        // more taps than points: fold the taps modulo N (the window wraps around the vector)
+        std::vector<T> folded(N, (T)0);
+        const size_t Lt = taps.size(), cl = Lt - Lt / 2;
+        // y[i] = sum_k x[(i + cl - 1 - k) mod N] t[k]; re-centre on an N-tap kernel with cl' = N - N/2
+        const size_t cl2 = N - N / 2;
+        for (size_t k = 0; k < Lt; k++) {
+            long long off = (long long)cl - 1 - (long long)k;           // x index offset
+            long long k2 = ((long long)cl2 - 1 - off) % (long long)N;   // tap slot with the same offset
+            if (k2 < 0) k2 += (long long)N;
+            folded[(size_t)k2] += taps[k];
+        }
+        taps.swap(folded);
+    }
+    T* h_dev = nullptr;
+    int rc = upload_table(taps, &h_dev);
+    if (rc) return done(v, rc);
+    rc = convolve_taps<T>(v, h_dev, taps.size(), false, nullptr, nullptr, nullptr);
+    cudaStreamSynchronize(g_stream);
+    cudaFree(h_dev);
+    return done(v, rc);
+}
+
+template <typename T, typename CT>
+Res<T> op_convolve_cfn(Vec<T>* v, CT (*fn)(const void*, T), const void* data, T ratio, size_t len) {
+    // convolution.rs:195-255 (complex impulse response); only the convolve_function_priv branch of
+    // the reference is meaningful (Q5), which is what is implemented for every ratio
+    if (!v->is_complex) { mark_invalid(v); return done(v, 0); }
+    if (v->domain != 0) { mark_invalid(v); return done(v, 0); }
+    const size_t N = points_of(v);
+    if (N == 0) return done(v, 0);
+    const size_t L = len > N ? N : len;
+    if (2 * L + 1 > N) return done(v, E_ARG_LEN);
+    std::vector<T> t(2 * (2 * L + 1));
+    T j = -(T)L;
+    for (size_t q = 0; q < 2 * L + 1; q++) {
+        CT c = fn(data, -j * ratio);
+        size_t k = 2 * L - q;  // reversed: h[k] = f(-(L-k)*ratio)
+        t[2 * k] = c.re; t[2 * k + 1] = c.im;
+        j = j + (T)1;
+    }
+    T* h_dev = nullptr;
+    int rc = upload_table(t, &h_dev);
+    if (rc) return done(v, rc);
+    rc = convolve_taps<T>(v, h_dev, 2 * L + 1, true, nullptr, nullptr, nullptr);
+    cudaStreamSynchronize(g_stream);
+    cudaFree(h_dev);
+    return done(v, rc);
+}
+
+template <typename T> Res<T> op_mul_freq_resp(Vec<T>* v, const RealFn<T>& f, T ratio) {
+    // convolution.rs:576-610 + multiply_function_priv (time_freq/mod.rs:612-723)
+    if (v->domain != 1) { mark_invalid(v); return done(v, 0); }
+    const size_t points = points_of(v);
+    if (!points) return done(v, 0);
+    int rc;
+    if (f.kind != 2) {
+        rc = ew_mul_freq_resp<T>(v->d, points, v->is_complex, f.kind, (double)f.rolloff, (double)ratio, g_stream);
+    } else {
+        std::vector<T> tab(points);
+        const size_t offset = points % 2;
+        const T mx = (T)(points - offset) / (T)2;
+        T j = -(T)(points - offset) / (T)2;
+        for (size_t i = 0; i < points; i++) { tab[i] = ratio * f(j / mx * ratio); j = j + (T)1; }
+        T* dev = nullptr;
+        rc = upload_table(tab, &dev);
+        if (!rc) rc = ew_mul_table<T>(v->d, dev, points, v->is_complex, 0, g_stream);
+        cudaStreamSynchronize(g_stream);
+        if (dev) cudaFree(dev);
+    }
+    return done(v, rc);
+}
+
+template <typename T, typename CT>
+Res<T> op_mul_freq_resp_c(Vec<T>* v, CT (*fn)(const void*, T), const void* data, T ratio) {
+    if (!v->is_complex || v->domain != 1) { mark_invalid(v); return done(v, 0); }
+    const size_t points = points_of(v);
+    if (!points) return done(v, 0);
+    std::vector<T> tab(2 * points);
+    const size_t offset = points % 2;
+    const T mx = (T)(points - offset) / (T)2;
+    T j = -(T)(points - offset) / (T)2;
+    for (size_t i = 0; i < points; i++) {
+        CT c = fn(data, j / mx * ratio);
+        tab[2 * i] = ratio * c.re; tab[2 * i + 1] = ratio * c.im;
+        j = j + (T)1;
+    }
+    T* dev = nullptr;
+    int rc = upload_table(tab, &dev);
+    if (!rc) rc = ew_mul_table<T>(v->d, dev, points, 1, 1, g_stream);
+    cudaStreamSynchronize(g_stream);
+    if (dev) cudaFree(dev);
+    return done(v, rc);
+}
+
+// ---- interpolation ---------------------------------------------------------------------------------
+template <typename T> Res<T> op_interpolatef(Vec<T>* v, const RealFn<T>& f, T factor, T delay, size_t conv_len) {
+    // interpolation.rs:387-482
+    delay = delay / v->delta;
+    const size_t len = v->len;
+    const size_t N = points_of(v);
+    const size_t points_half = N / 2;
+    if (conv_len > points_half) conv_len = points_half;
+    const double nl = round((double)((T)len * factor));
+    if (!(nl >= 0) || N == 0) return done(v, N == 0 ? 0 : E_ARG_LEN);
+    size_t new_len = (size_t)nl;
+    new_len += new_len % 2;
+    const size_t new_points = v->is_complex ? new_len / 2 : new_len;
+    int rc = ensure_scratch(v, new_len);
+    if (rc) return done(v, rc);
+    const bool integer = (T)fabs((T)round(factor) - factor) < (T)1e-6;
+    if (conv_len <= 202 && new_len >= 2000 && integer) {
+        const int F = (int)round(factor);
+        const int L = (int)conv_len;
+        const int J = 2 * L + 3;
+        // function_to_vectors (interpolation.rs:133-181): v_s[k] = f(j_k - s/F), j_0 = -(L-1) + delay
+        std::vector<T> vs((size_t)F * (2 * L + 1));
+        for (int s = 0; s < F; s++) {
+            T offset = (T)s / (T)F;
+            T j = -((T)L - (T)1) + delay;
+            for (int k = 0; k < 2 * L + 1; k++) { vs[(size_t)s * (2 * L + 1) + k] = f(j - offset); j = j + (T)1; }
+        }
+        // tables over the window superset n = r-L-1+jj, jj in [0, J)
+        std::vector<T> tab((size_t)2 * F * J, (T)0);
+        for (int s = 0; s < F; s++) {
+            T* ti = &tab[(size_t)s * J];                    // interior (interpolation.rs:244-275)
+            if (s == 0) { for (int jj = 0; jj <= 2 * L; jj++) ti[jj] = vs[2 * L - jj]; }
+            else { for (int jj = 1; jj <= 2 * L + 1; jj++) ti[jj] = vs[(size_t)(F - s) * (2 * L + 1) + (2 * L + 1 - jj)]; }
+            T* te = &tab[(size_t)(F + s) * J];              // edges (interpolation.rs:293-315)
+            for (int k = 0; k <= 2 * L; k++) te[k + 2] = vs[(size_t)s * (2 * L + 1) + k];
+        }
+        T* dev = nullptr;
+        rc = upload_table(tab, &dev);
+        if (!rc) rc = interp_poly<T>(v->d, v->scratch, dev, N, new_points, F, L, v->is_complex, g_stream);
+        cudaStreamSynchronize(g_stream);
+        if (dev) cudaFree(dev);
+    } else {
+        if (f.kind == 2) return done(v, E_ARG_LEN);   // custom callback + per-output taps: not supported on the device
+        rc = interp_frac<T>(v->d, v->scratch, N, new_points, (double)factor, (double)delay, (int)conv_len, f.kind,
+                            (double)f.rolloff, v->is_complex, g_stream);
+    }
+    if (rc) return done(v, rc);
+    trade(v);
+    v->len = new_len;
+    return done(v, 0);
+}
+
+template <typename T> Res<T> op_interpolate_lin(Vec<T>* v, T factor, T delay) {
+    // real_interpolation.rs:33-71
+    if (v->is_complex) { mark_invalid(v); return done(v, 0); }
+    const size_t n = v->len;
+    if (n == 0) return done(v, 0);
+    const size_t dest_len = (size_t)round((double)((T)(n - 1) * factor)) + 1;
+    int rc = ensure_scratch(v, dest_len);
+    if (!rc) rc = interp_lin<T>(v->d, v->scratch, n, dest_len, (double)factor, (double)delay, g_stream);
+    if (rc) return done(v, rc);
+    trade(v);
+    v->len = dest_len;
+    return done(v, 0);
+}
+
+// ---- host access -----------------------------------------------------------------------------------
+template <typename T> const T* host_mirror(const Vec<T>* cv) {
+    Vec<T>* v = const_cast<Vec<T>*>(cv);
+    v->host.resize(v->len ? v->len : 1);
+    if (v->len) {
+        cudaMemcpyAsync(v->host.data(), v->d, v->len * sizeof(T), cudaMemcpyDeviceToHost, g_stream);
+        cudaStreamSynchronize(g_stream);
+    }
+    return v->host.data();
+}
+
+template <typename T> int upload(Vec<T>* v, const T* host, size_t len) {
+    if (len != v->len) {
+        int rc = vec_resize(v, len);
+        if (rc) return rc;
+    }
+    if (len) BDSP_CUDA_OK(cudaMemcpyAsync(v->d, host, len * sizeof(T), cudaMemcpyHostToDevice, g_stream));
+    v->version++;
+    return 0;
+}
+template <typename T> int download(const Vec<T>* v, T* host, size_t len) {
+    if (len > v->len) return E_ARG_LEN;
+    if (len) BDSP_CUDA_OK(cudaMemcpyAsync(host, v->d, len * sizeof(T), cudaMemcpyDeviceToHost, g_stream));
+    BDSP_CUDA_OK(cudaStreamSynchronize(g_stream));
+    return 0;
+}
+
+template <typename T>
+int scale_mul_mag_phase(Vec<T>* v, T cre, T cim, const Vec<T>* w, Vec<T>* mag, Vec<T>* ph, int write_back) {
+    if (!v->is_complex || !w->is_complex) return E_COMPLEX;
+    if (mag->is_complex || ph->is_complex) return E_REAL;
+    if (v->len != w->len) return E_SAME_SIZE;
+    if (!meta_agrees(v, w)) return E_META;
+    const size_t points = v->len / 2;
+    int rc = vec_resize(mag, points);
+    if (!rc) rc = vec_resize(ph, points);
+    if (rc) return rc;
+    mag->delta = v->delta; ph->delta = v->delta;
+    if (points) rc = ew_scale_mul_mag_phase<T>(v->d, w->d, mag->d, ph->d, points, (double)cre, (double)cim, cim != (T)0, write_back, g_stream);
+    if (write_back) v->version++;
+    return rc;
+}
+
+struct ConvPlan {
+    int is64;
+    size_t L, M;
+    void* Hs;       // overlap-save spectrum (M complex) or nullptr
+    void* taps;     // copy of the taps (L complex) for the direct / full-length paths
+};
+
+template <typename T> ConvPlan* conv_plan_create(const void* h_dev, size_t L) {
+    typedef typename CpxOf<T>::type C;
+    if (!h_dev || !L) { set_last_error("conv plan: empty impulse response"); return nullptr; }
+    ConvPlan* p = new ConvPlan();
+    p->is64 = sizeof(T) == 8; p->L = L; p->M = 0; p->Hs = nullptr; p->taps = nullptr;
+    if (cudaMalloc(&p->taps, L * sizeof(C)) != cudaSuccess) { delete p; return nullptr; }
+    cudaMemcpyAsync(p->taps, h_dev, L * sizeof(C), cudaMemcpyDeviceToDevice, g_stream);
+    if (L > 24 && L <= ols_max_taps<T>()) {
+        p->M = ols_block_len<T>(L);
+        if (cudaMalloc(&p->Hs, p->M * sizeof(C)) != cudaSuccess || ols_prepare<T>(p->taps, L, 0, p->Hs, p->M, g_stream) != 0) {
+            cudaFree(p->taps); if (p->Hs) cudaFree(p->Hs); delete p; return nullptr;
+        }
+    }
+    return p;
+}
+
+template <typename T> int conv_rows(const void* in, void* out, size_t points, size_t rows, const ConvPlan* p) {
+    if (!p || p->is64 != (sizeof(T) == 8)) { set_last_error("conv rows: plan precision mismatch"); return -2; }
+    if (points < p->L) return E_ARG_LEN;
+    if (!points || !rows) return 0;
+    if (p->Hs) return ols_convolve<T>(in, out, points, rows, p->L, p->Hs, p->M, 0, g_stream);
+    if (p->L <= 24) return fir_convolve<T>(in, out, p->taps, points, rows, p->L, p->L - p->L / 2, 1, 1, g_stream);
+    return fft_convolve_full<T>(in, out, p->taps, points, rows, p->L, 0, 0, g_stream);
+}
+
+template <typename T> int fft_rows(const void* in, void* out, size_t points, size_t rows, int flags) {
+    FftOpts o;
+    o.inverse = (flags & BDSP_F_INVERSE) != 0;
+    o.magnitude = (flags & BDSP_F_MAGNITUDE) != 0;
+    o.real_input = (flags & BDSP_F_REAL_INPUT) != 0;
+    if ((flags & BDSP_F_SHIFT) && points) {
+        if (o.inverse) { o.in_rot = points / 2; o.scale = (double)((T)1 / (T)points); }
+        else o.out_rot = points / 2;
+    }
+    return fft_exec<T>(in, out, points, rows, o, nullptr, 0, g_stream);
+}
+
+}  // namespace
+
+// =====================================================================================================
+// extern "C" surface
+// =====================================================================================================
+#define V32(p) reinterpret_cast<Vec<float>*>(p)
+#define V64(p) reinterpret_cast<Vec<double>*>(p)
+#define CV32(p) reinterpret_cast<const Vec<float>*>(p)
+#define CV64(p) reinterpret_cast<const Vec<double>*>(p)
+
+template <typename R, typename T> static inline R as_res(Res<T> r) {
+    R out;
+    out.result_code = r.result_code;
+    out.vector = reinterpret_cast<decltype(out.vector)>(r.vector);
+    return out;
+}
+
+#define BDSP_FACADE(S, T, VEC, CVEC, RES, HV, CPLX, RFN, CFN)                                                         \
+    extern "C" HV* new##S(int32_t is_complex, int32_t domain, T init_value, size_t length, T delta) {                  \
+        return reinterpret_cast<HV*>(vec_new<T>(is_complex, domain, init_value, length, delta));                       \
+    }                                                                                                                  \
+    extern "C" HV* new_with_performance_options##S(int32_t is_complex, int32_t domain, T init_value, size_t length,    \
+                                                   T delta, size_t) {                                                  \
+        return reinterpret_cast<HV*>(vec_new<T>(is_complex, domain, init_value, length, delta));                       \
+    }                                                                                                                  \
+    extern "C" HV* new_with_detailed_performance_options##S(int32_t is_complex, int32_t domain, T init_value,          \
+                                                            size_t length, T delta, size_t, size_t, size_t, size_t,    \
+                                                            size_t) {                                                  \
+        return reinterpret_cast<HV*>(vec_new<T>(is_complex, domain, init_value, length, delta));                       \
+    }                                                                                                                  \
+    extern "C" void delete_vector##S(HV* v) { vec_delete(VEC(v)); }                                                    \
+    extern "C" HV* clone##S(HV* v) {                                                                                   \
+        Vec<T>* s = VEC(v);                                                                                            \
+        Vec<T>* c = vec_new<T>(s->is_complex, s->domain, (T)0, 0, s->delta);                                           \
+        if (reserve(&c->d, &c->cap, s->len, false, 0) == 0 && s->len)                                                  \
+            cudaMemcpyAsync(c->d, s->d, s->len * sizeof(T), cudaMemcpyDeviceToDevice, g_stream);                       \
+        c->len = s->len;                                                                                               \
+        return reinterpret_cast<HV*>(c);                                                                               \
+    }                                                                                                                  \
+    extern "C" T get_value##S(const HV* v, size_t index) {                                                             \
+        T r = (T)NAN;                                                                                                  \
+        if (index < CVEC(v)->len) {                                                                                    \
+            cudaMemcpyAsync(&r, CVEC(v)->d + index, sizeof(T), cudaMemcpyDeviceToHost, g_stream);                      \
+            cudaStreamSynchronize(g_stream);                                                                           \
+        }                                                                                                              \
+        return r;                                                                                                      \
+    }                                                                                                                  \
+    extern "C" void set_value##S(HV* v, size_t index, T value) {                                                       \
+        if (index < VEC(v)->len) {                                                                                     \
+            cudaMemcpyAsync(VEC(v)->d + index, &value, sizeof(T), cudaMemcpyHostToDevice, g_stream);                   \
+            cudaStreamSynchronize(g_stream);                                                                           \
+            VEC(v)->version++;                                                                                         \
+        }                                                                                                              \
+    }                                                                                                                  \
+    extern "C" int32_t is_complex##S(const HV* v) { return CVEC(v)->is_complex ? 1 : 0; }                              \
+    extern "C" int32_t get_domain##S(const HV* v) { return CVEC(v)->domain; }                                          \
+    extern "C" size_t get_len##S(const HV* v) { return CVEC(v)->len; }                                                 \
+    extern "C" void set_len##S(HV* v, size_t len) { (void)vec_resize(VEC(v), len); }                                   \
+    extern "C" size_t get_points##S(const HV* v) { return points_of(CVEC(v)); }                                        \
+    extern "C" T get_delta##S(const HV* v) { return CVEC(v)->delta; }                                                  \
+    extern "C" const T* data##S(const HV* v) { return host_mirror(CVEC(v)); }                                          \
+    extern "C" const CPLX* complex_data##S(const HV* v) { return reinterpret_cast<const CPLX*>(host_mirror(CVEC(v))); } \
+    extern "C" size_t get_allocated_len##S(const HV* v) { return CVEC(v)->cap; }                                       \
+    extern "C" RES overwrite_data##S(HV* v, const T* data, size_t len) {                                               \
+        Vec<T>* s = VEC(v);                                                                                            \
+        int code = E_ARG_LEN;                                                                                          \
+        if (len < s->len) { /* strict, as in the reference (Q9) */                                                     \
+            code = 0;                                                                                                  \
+            if (len) {                                                                                                 \
+                cudaMemcpyAsync(s->d, data, len * sizeof(T), cudaMemcpyHostToDevice, g_stream);                        \
+                cudaStreamSynchronize(g_stream);                                                                       \
+            }                                                                                                          \
+            s->version++;                                                                                              \
+        }                                                                                                              \
+        RES r; r.result_code = code; r.vector = v; return r;                                                           \
+    }                                                                                                                  \
+    extern "C" RES add##S(HV* v, const HV* o) { return as_res<RES>(op_binary(VEC(v), CVEC(o), EW_ADD)); }              \
+    extern "C" RES sub##S(HV* v, const HV* o) { return as_res<RES>(op_binary(VEC(v), CVEC(o), EW_SUB)); }              \
+    extern "C" RES div##S(HV* v, const HV* o) { return as_res<RES>(op_binary(VEC(v), CVEC(o), EW_DIV)); }              \
+    extern "C" RES mul##S(HV* v, const HV* o) { return as_res<RES>(op_binary(VEC(v), CVEC(o), EW_MUL)); }              \
+    extern "C" RES add_vector##S(HV* v, const HV* o) { return as_res<RES>(op_binary(VEC(v), CVEC(o), EW_ADD)); }       \
+    extern "C" RES sub_vector##S(HV* v, const HV* o) { return as_res<RES>(op_binary(VEC(v), CVEC(o), EW_SUB)); }       \
+    extern "C" RES div_vector##S(HV* v, const HV* o) { return as_res<RES>(op_binary(VEC(v), CVEC(o), EW_DIV)); }       \
+    extern "C" RES mul_vector##S(HV* v, const HV* o) { return as_res<RES>(op_binary(VEC(v), CVEC(o), EW_MUL)); }       \
+    extern "C" RES real_offset##S(HV* v, T c) { return as_res<RES>(op_real_const(VEC(v), EW_OFFSET, c)); }             \
+    extern "C" RES real_scale##S(HV* v, T c) { return as_res<RES>(op_real_const(VEC(v), EW_SCALE, c)); }               \
+    extern "C" RES complex_offset##S(HV* v, T re, T im) { return as_res<RES>(op_complex_const(VEC(v), EW_OFFSET, re, im)); } \
+    extern "C" RES complex_scale##S(HV* v, T re, T im) { return as_res<RES>(op_complex_const(VEC(v), EW_SCALE, re, im)); } \
+    extern "C" RES complex_divide##S(HV* v, T re, T im) { return as_res<RES>(op_complex_divide(VEC(v), re, im)); }     \
+    extern "C" RES conj##S(HV* v) { return as_res<RES>(op_complex_const(VEC(v), EW_CONJ, (T)0, (T)0)); }               \
+    extern "C" RES to_complex##S(HV* v) { return as_res<RES>(op_to_complex(VEC(v))); }                                 \
+    extern "C" RES magnitude##S(HV* v) { return as_res<RES>(op_c2r(VEC(v), C2R_MAG_SQRT)); }                           \
+    extern "C" RES magnitude_squared##S(HV* v) { return as_res<RES>(op_c2r(VEC(v), C2R_MAG_SQ)); }                     \
+    extern "C" RES phase##S(HV* v) { return as_res<RES>(op_c2r(VEC(v), C2R_PHASE)); }                                  \
+    extern "C" RES to_real##S(HV* v) { return as_res<RES>(op_c2r(VEC(v), C2R_REAL)); }                                 \
+    extern "C" RES to_imag##S(HV* v) { return as_res<RES>(op_c2r(VEC(v), C2R_IMAG)); }                                 \
+    extern "C" int32_t get_magnitude##S(HV* v, HV* d) { return op_get_c2r(VEC(v), VEC(d), C2R_MAG_SQRT); }             \
+    extern "C" int32_t get_magnitude_squared##S(HV* v, HV* d) { return op_get_c2r(VEC(v), VEC(d), C2R_MAG_SQ); }       \
+    extern "C" int32_t get_phase##S(HV* v, HV* d) { return op_get_c2r(VEC(v), VEC(d), C2R_PHASE); }                    \
+    extern "C" int32_t get_real##S(HV* v, HV* d) { return op_get_c2r(VEC(v), VEC(d), C2R_REAL); }                      \
+    extern "C" int32_t get_imag##S(HV* v, HV* d) { return op_get_c2r(VEC(v), VEC(d), C2R_IMAG); }                      \
+    extern "C" int32_t get_mag_phase##S(HV* v, HV* m, HV* p) { return op_get_mag_phase(VEC(v), VEC(m), VEC(p)); }      \
+    extern "C" RES plain_fft##S(HV* v) { return as_res<RES>(op_fft(VEC(v), false, false, false)); }                    \
+    extern "C" RES plain_ifft##S(HV* v) { return as_res<RES>(op_fft(VEC(v), true, false, false)); }                    \
+    extern "C" RES fft##S(HV* v) { return as_res<RES>(op_fft(VEC(v), false, true, false)); }                           \
+    extern "C" RES ifft##S(HV* v) { return as_res<RES>(op_fft(VEC(v), true, true, false)); }                           \
+    extern "C" RES bdsp_fft_magnitude##S(HV* v) { return as_res<RES>(op_fft(VEC(v), false, true, true)); }             \
+    extern "C" RES swap_halves##S(HV* v) { return as_res<RES>(op_rotate(VEC(v), true)); }                              \
+    extern "C" RES fft_shift##S(HV* v) { return as_res<RES>(op_rotate(VEC(v), true)); }                                \
+    extern "C" RES ifft_shift##S(HV* v) { return as_res<RES>(op_rotate(VEC(v), false)); }                              \
+    extern "C" RES zero_pad##S(HV* v, size_t points, int32_t opt) { return as_res<RES>(op_zero_pad(VEC(v), points, opt)); } \
+    extern "C" RES zero_interleave##S(HV* v, int32_t factor) { return as_res<RES>(op_zero_interleave(VEC(v), factor)); } \
+    extern "C" RES convolve_signal##S(HV* v, const HV* h) {                                                            \
+        return as_res<RES>(op_convolve_signal(VEC(v), const_cast<Vec<T>*>(CVEC(h))));                                  \
+    }                                                                                                                  \
+    extern "C" RES convolve##S(HV* v, int32_t kind, T rolloff, T ratio, size_t len) {                                  \
+        RealFn<T> f; f.kind = kind == 0 ? 0 : 1; f.rolloff = rolloff;                                                  \
+        return as_res<RES>(op_convolve_fn<T>(VEC(v), f, ratio, len));                                         \
+    }                                                                                                                  \
+    extern "C" RES convolve_real##S(HV* v, RFN fn, const void* data, uint8_t, T ratio, size_t len) {                   \
+        RealFn<T> f; f.kind = 2; f.fn = fn; f.data = data;                                                             \
+        return as_res<RES>(op_convolve_fn<T>(VEC(v), f, ratio, len));                                         \
+    }                                                                                                                  \
+    extern "C" RES convolve_complex##S(HV* v, CFN fn, const void* data, uint8_t, T ratio, size_t len) {                \
+        return as_res<RES>(op_convolve_cfn<T, CPLX>(VEC(v), fn, data, ratio, len));                                    \
+    }                                                                                                                  \
+    extern "C" RES multiply_frequency_response##S(HV* v, int32_t kind, T rolloff, T ratio) {                           \
+        RealFn<T> f; f.kind = kind == 0 ? 0 : 1; f.rolloff = rolloff; f.freq = true;                                   \
+        return as_res<RES>(op_mul_freq_resp<T>(VEC(v), f, ratio));                                                     \
+    }                                                                                                                  \
+    extern "C" RES multiply_frequency_response_real##S(HV* v, RFN fn, const void* data, uint8_t, T ratio) {            \
+        RealFn<T> f; f.kind = 2; f.fn = fn; f.data = data; f.freq = true;                                              \
+        return as_res<RES>(op_mul_freq_resp<T>(VEC(v), f, ratio));                                                     \
+    }                                                                                                                  \
+    extern "C" RES multiply_frequency_response_complex##S(HV* v, CFN fn, const void* data, uint8_t, T ratio) {         \
+        return as_res<RES>(op_mul_freq_resp_c<T, CPLX>(VEC(v), fn, data, ratio));                                      \
+    }                                                                                                                  \
+    extern "C" RES interpolatef##S(HV* v, int32_t kind, T rolloff, T factor, T delay, size_t len) {                    \
+        RealFn<T> f; f.kind = kind == 0 ? 0 : 1; f.rolloff = rolloff;                                                  \
+        return as_res<RES>(op_interpolatef<T>(VEC(v), f, factor, delay, len));                                         \
+    }                                                                                                                  \
+    extern "C" RES interpolatef_custom##S(HV* v, RFN fn, const void* data, uint8_t, T factor, T delay, size_t len) {   \
+        RealFn<T> f; f.kind = 2; f.fn = fn; f.data = data;                                                             \
+        return as_res<RES>(op_interpolatef<T>(VEC(v), f, factor, delay, len));                                         \
+    }                                                                                                                  \
+    extern "C" RES interpolate_lin##S(HV* v, T factor, T delay) { return as_res<RES>(op_interpolate_lin(VEC(v), factor, delay)); } \
+    extern "C" int32_t bdsp_upload##S(HV* v, const T* host, size_t len) { return upload(VEC(v), host, len); }          \
+    extern "C" int32_t bdsp_download##S(const HV* v, T* host, size_t len) { return download(CVEC(v), host, len); }     \
+    extern "C" void* bdsp_device_ptr##S(HV* v) { return VEC(v)->d; }                                                   \
+    extern "C" int32_t bdsp_scale_mul_mag_phase##S(HV* v, T cre, T cim, const HV* w, HV* m, HV* p, int32_t wb) {       \
+        return scale_mul_mag_phase<T>(VEC(v), cre, cim, CVEC(w), VEC(m), VEC(p), wb);                                  \
+    }
+
+BDSP_FACADE(32, float, V32, CV32, BdspVecResult32, BdspVec32, BdspComplex32, BdspRealFn32, BdspComplexFn32)
+BDSP_FACADE(64, double, V64, CV64, BdspVecResult64, BdspVec64, BdspComplex64, BdspRealFn64, BdspComplexFn64)
+
+extern "C" const char* bdsp_version(void) { return "basic_dsp_b200 0.1.0 (sm_100a)"; }
+extern "C" const char* bdsp_last_error(void) { return get_last_error(); }
+extern "C" int32_t bdsp_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+extern "C" int32_t bdsp_set_device(int32_t device) { BDSP_CUDA_OK(cudaSetDevice(device)); return 0; }
+extern "C" int32_t bdsp_sync(void) { BDSP_CUDA_OK(cudaStreamSynchronize(g_stream)); return 0; }
+extern "C" void bdsp_set_stream(void* s) { g_stream = reinterpret_cast<cudaStream_t>(s); }
+
+extern "C" int32_t bdsp_fft_rows_c32(const void* in, void* out, size_t points, size_t rows, int32_t flags) { return fft_rows<float>(in, out, points, rows, flags); }
+extern "C" int32_t bdsp_fft_rows_c64(const void* in, void* out, size_t points, size_t rows, int32_t flags) { return fft_rows<double>(in, out, points, rows, flags); }
+extern "C" BdspConvPlan* bdsp_conv_plan_create_c32(const void* h, size_t L) { return reinterpret_cast<BdspConvPlan*>(conv_plan_create<float>(h, L)); }
+extern "C" BdspConvPlan* bdsp_conv_plan_create_c64(const void* h, size_t L) { return reinterpret_cast<BdspConvPlan*>(conv_plan_create<double>(h, L)); }
+extern "C" void bdsp_conv_plan_destroy(BdspConvPlan* plan) {
+    ConvPlan* p = reinterpret_cast<ConvPlan*>(plan);
+    if (!p) return;
+    cudaStreamSynchronize(g_stream);
+    if (p->Hs) cudaFree(p->Hs);
+    if (p->taps) cudaFree(p->taps);
+    delete p;
+}
+extern "C" int32_t bdsp_convolve_signal_rows_c32(const void* in, void* out, size_t points, size_t rows, const BdspConvPlan* plan) {
+    return conv_rows<float>(in, out, points, rows, reinterpret_cast<const ConvPlan*>(plan));
+}
+extern "C" int32_t bdsp_convolve_signal_rows_c64(const void* in, void* out, size_t points, size_t rows, const BdspConvPlan* plan) {
+    return conv_rows<double>(in, out, points, rows, reinterpret_cast<const ConvPlan*>(plan));
+}
+extern "C" void* bdsp_malloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) { set_last_error("bdsp_malloc(%zu) failed", bytes); return nullptr; }
+    return p;
+}
+extern "C" void bdsp_free(void* p) { if (p) { cudaStreamSynchronize(g_stream); cudaFree(p); } }
+extern "C" void* bdsp_malloc_host(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { set_last_error("bdsp_malloc_host(%zu) failed", bytes); return nullptr; }
+    return p;
+}
+extern "C" void bdsp_free_host(void* p) { if (p) cudaFreeHost(p); }
+extern "C" int32_t bdsp_memcpy_h2d(void* d, const void* h, size_t bytes) { BDSP_CUDA_OK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, g_stream)); return 0; }
+extern "C" int32_t bdsp_memcpy_d2h(void* h, const void* d, size_t bytes) { BDSP_CUDA_OK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, g_stream)); return 0; }
+extern "C" int32_t bdsp_memset(void* d, int32_t value, size_t bytes) { BDSP_CUDA_OK(cudaMemsetAsync(d, value, bytes, g_stream)); return 0; }
+extern "C" void* bdsp_event_create(void) {
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+    return e;
+}
+extern "C" void bdsp_event_destroy(void* e) { if (e) cudaEventDestroy(reinterpret_cast<cudaEvent_t>(e)); }
+extern "C" int32_t bdsp_event_record(void* e) { BDSP_CUDA_OK(cudaEventRecord(reinterpret_cast<cudaEvent_t>(e), g_stream)); return 0; }
+extern "C" float bdsp_event_elapsed_ms(void* a, void* b) {
+    float ms = -1.f;
+    if (cudaEventSynchronize(reinterpret_cast<cudaEvent_t>(b)) != cudaSuccess) return -1.f;
+    if (cudaEventElapsedTime(&ms, reinterpret_cast<cudaEvent_t>(a), reinterpret_cast<cudaEvent_t>(b)) != cudaSuccess) return -1.f;
+    return ms;
+}
+extern "C" uint64_t bdsp_kernel_launch_count(void) { return launch_count(); }

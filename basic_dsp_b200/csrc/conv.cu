@@ -1,0 +1,322 @@
+// Convolution kernels: fused overlap-save fast convolution and direct circular FIR.
+//
+// Both compute the reference's centred circular convolution
+//     y[i] = sum_{k<L} x[(i + cl - 1 - k) mod N] * h[k],   cl = L - L/2
+// (ConvolutionOps::convolve_signal, vector/src/vector_types/time_freq/convolution.rs:477-542;
+//  convolve_iteration, time_freq/mod.rs:456-473).  They replace the reference's overlap_discard
+// (convolution.rs:304-461), its SIMD FIR (time_freq/mod.rs:531-610) and its OpenCL kernels
+// conv_vecs_r/conv_vecs_c/multiply_vector (gpu_support/ocl/ocl_kernels32.rs).
+#include "conv.cuh"
+#include "fft.cuh"
+#include "fft_core.cuh"
+
+namespace bdsp {
+
+// ------------------------------------------------------------------------------------------
+// Overlap-save: one CTA = one block of M points of one vector, everything in shared memory:
+//   load M inputs (circular) -> FFT -> * Hs (H/M, L2 resident) -> IFFT -> store M-L+1 outputs.
+// HBM traffic per output sample: 8 B read * M/(M-L+1) + 8 B write (c32).
+// ------------------------------------------------------------------------------------------
+template <typename T, bool REAL>
+__global__ void __launch_bounds__(sizeof(T) == 4 ? 1024 : 512)
+ols_conv_kernel(const void* __restrict__ x_, void* __restrict__ y_, long long N, long long batch, int L, int log2M,
+                long long blocks_per_vec, const typename CpxOf<T>::type* __restrict__ Hs,
+                const typename CpxOf<T>::type* __restrict__ tw) {
+    typedef typename CpxOf<T>::type C;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C* s = reinterpret_cast<C*>(smem_raw);
+    const int M = 1 << log2M;
+    const int step = M - L + 1;
+    const int cl = L - L / 2;
+    const long long vec = blockIdx.x / blocks_per_vec;
+    const long long blk = blockIdx.x - vec * blocks_per_vec;
+    const long long i0 = blk * step;              // first output index of this block
+    long long p0 = (i0 - (L - cl)) % N;            // first input index (may be negative before wrap)
+    if (p0 < 0) p0 += N;
+    // ---- load (circular) ----
+    {
+        long long g = (p0 + threadIdx.x) % N;
+        const long long adv = blockDim.x % N;
+        for (int idx = threadIdx.x; idx < M; idx += blockDim.x) {
+            C v;
+            if (REAL) { v.x = reinterpret_cast<const T*>(x_)[vec * N + g]; v.y = 0; }
+            else v = reinterpret_cast<const C*>(x_)[vec * N + g];
+            s[spad(idx)] = v;
+            g += adv; if (g >= N) g -= N;
+        }
+    }
+    __syncthreads();
+    block_fft<T, false>(s, log2M, 1, tw);
+    // ---- spectrum multiply (Hs already holds the 1/M scaling) ----
+    for (int idx = threadIdx.x; idx < M; idx += blockDim.x) {
+        C v = s[spad(idx)];
+        s[spad(idx)] = cmul(v, __ldg(&Hs[idx]));
+    }
+    __syncthreads();
+    block_fft<T, true>(s, log2M, 1, tw);
+    // ---- store the valid part: m in [L-1, M) -> y[i0 + m - (L-1)] ----
+    for (int idx = threadIdx.x; idx < step; idx += blockDim.x) {
+        long long i = i0 + idx;
+        if (i < N) {
+            C v = s[spad(idx + L - 1)];
+            if (REAL) reinterpret_cast<T*>(y_)[vec * N + i] = v.x;
+            else reinterpret_cast<C*>(y_)[vec * N + i] = v;
+        }
+    }
+}
+
+// Hs[k] = FFT_M(pad(h))[k] / M
+template <typename T>
+__global__ void ols_pad_h_kernel(const void* __restrict__ h_, typename CpxOf<T>::type* __restrict__ hp, int L, int M,
+                                 int h_is_real) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    typename CpxOf<T>::type v = mk<T>(0, 0);
+    if (i < L) {
+        if (h_is_real) v.x = reinterpret_cast<const T*>(h_)[i];
+        else v = reinterpret_cast<const typename CpxOf<T>::type*>(h_)[i];
+    }
+    hp[i] = v;
+}
+
+template <typename T> size_t ols_block_len(size_t L) {
+    // same rule as the reference (fft_len >= 4*overlap, convolution.rs:323-331) with a 4096 floor so
+    // that the block transform amortises its overlap; capped by the shared-memory transform limit
+    size_t m = next_pow2(4 * (L > 1 ? L - 1 : 1));
+    if (m < 4096) m = 4096;
+    if (m > fft_block_max_n<T>()) m = fft_block_max_n<T>();
+    return m;
+}
+
+template <typename T> size_t ols_max_taps() { return fft_block_max_n<T>() / 2; }
+
+template <typename T>
+int ols_prepare(const void* h, size_t L, int h_is_real, void* Hs, size_t M, cudaStream_t st) {
+    typedef typename CpxOf<T>::type C;
+    ols_pad_h_kernel<T><<<(unsigned)((M + 255) / 256), 256, 0, st>>>(h, reinterpret_cast<C*>(Hs), (int)L, (int)M, h_is_real);
+    BDSP_LAUNCHED();
+    FftOpts o;
+    o.scale = 1.0 / (double)M;
+    return fft_exec<T>(Hs, Hs, M, 1, o, nullptr, 0, st);
+}
+
+template <typename T>
+int ols_convolve(const void* x, void* y, size_t N, size_t batch, size_t L, const void* Hs, size_t M, int is_real,
+                 cudaStream_t st) {
+    typedef typename CpxOf<T>::type C;
+    if (x == y) { set_last_error("ols_convolve: in-place operation is not supported"); return -3; }
+    const size_t step = M - L + 1;
+    const long long bpv = (long long)((N + step - 1) / step);
+    const int log2M = ilog2(M);
+    const int threads = block_fft_threads((int)M, 1);
+    const size_t smem = spad_host(M) * sizeof(C);
+    const long long grid = bpv * (long long)batch;
+    if (grid > 0x7fffffffll) { set_last_error("ols_convolve: grid too large"); return -2; }
+    const C* tw = twiddle_table<T>();
+    if (is_real) {
+        if (smem > 48 * 1024) BDSP_CUDA_OK(cudaFuncSetAttribute(ols_conv_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ols_conv_kernel<T, true><<<(unsigned)grid, threads, smem, st>>>(x, y, (long long)N, (long long)batch, (int)L, log2M, bpv,
+                                                                       reinterpret_cast<const C*>(Hs), tw);
+    } else {
+        if (smem > 48 * 1024) BDSP_CUDA_OK(cudaFuncSetAttribute(ols_conv_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ols_conv_kernel<T, false><<<(unsigned)grid, threads, smem, st>>>(x, y, (long long)N, (long long)batch, (int)L, log2M, bpv,
+                                                                        reinterpret_cast<const C*>(Hs), tw);
+    }
+    BDSP_LAUNCHED();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Direct circular FIR.  Tile of FIR_TILE outputs per CTA; the input window (tile + L - 1 halo,
+// circular) and the taps are staged in shared memory; each thread produces FIR_U consecutive
+// outputs from a sliding register window (one shared load of x and one broadcast load of a tap per
+// FIR_U multiply-accumulates).
+//   XC: x complex (else real), HC: taps complex (else real)
+// ------------------------------------------------------------------------------------------
+#define FIR_THREADS 256
+#define FIR_U 8
+#define FIR_TILE (FIR_THREADS * FIR_U)
+// skewed window index: threads are FIR_U elements apart, the skew makes their banks distinct
+__device__ __forceinline__ int fpad(int w) { return w + (w >> 3); }
+
+template <typename T, bool XC, bool HC> struct FirTypes {
+    typedef typename CpxOf<T>::type C;
+};
+
+template <typename T, bool XC, bool HC>
+__global__ void __launch_bounds__(FIR_THREADS)
+fir_kernel(const void* __restrict__ x_, void* __restrict__ y_, const void* __restrict__ h_, long long N, long long batch,
+           int L, int cl, long long tiles_per_vec) {
+    typedef typename CpxOf<T>::type C;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // layout: taps (L entries of C), then the window (FIR_TILE + L - 1 entries of C, +pad)
+    C* sh = reinterpret_cast<C*>(smem_raw);
+    C* sx = sh + L;
+    const long long vec = blockIdx.x / tiles_per_vec;
+    const long long tile = blockIdx.x - vec * tiles_per_vec;
+    const long long i0 = tile * FIR_TILE;
+    const int W = FIR_TILE + L - 1;
+    // window element w corresponds to x[(i0 - (L - cl) + w) mod N]
+    long long p0 = (i0 - (L - cl)) % N;
+    if (p0 < 0) p0 += N;
+    for (int k = threadIdx.x; k < L; k += FIR_THREADS) {
+        C t;
+        if (HC) t = reinterpret_cast<const C*>(h_)[k];
+        else { t.x = reinterpret_cast<const T*>(h_)[k]; t.y = 0; }
+        sh[k] = t;
+    }
+    {
+        long long g = (p0 + threadIdx.x) % N;
+        const long long adv = FIR_THREADS % N;
+        for (int w = threadIdx.x; w < W; w += FIR_THREADS) {
+            C v;
+            if (XC) v = reinterpret_cast<const C*>(x_)[vec * N + g];
+            else { v.x = reinterpret_cast<const T*>(x_)[vec * N + g]; v.y = 0; }
+            sx[fpad(w)] = v;
+            g += adv; if (g >= N) g -= N;
+        }
+    }
+    __syncthreads();
+    // thread t produces outputs u0..u0+U-1 (u0 = t*U) from a circular register window:
+    // at tap offset o = L-1-k the window holds x_window[u0 + o + u] in r[(o + u) % U]
+    const int u0 = threadIdx.x * FIR_U;
+    C acc[FIR_U];
+    C r[FIR_U];
+#pragma unroll
+    for (int u = 0; u < FIR_U; u++) { acc[u] = mk<T>(0, 0); r[u] = sx[fpad(u0 + u)]; }
+    for (int ob = 0; ob < L; ob += FIR_U) {
+#pragma unroll
+        for (int oo = 0; oo < FIR_U; oo++) {
+            const int o = ob + oo;
+            if (o < L) {
+                const C t = sh[L - 1 - o];
+#pragma unroll
+                for (int u = 0; u < FIR_U; u++) {
+                    const C xv = r[(oo + u) % FIR_U];
+                    if (HC) {
+                        acc[u].x += xv.x * t.x - xv.y * t.y;
+                        acc[u].y += xv.x * t.y + xv.y * t.x;
+                    } else {
+                        acc[u].x += xv.x * t.x;
+                        if (XC) acc[u].y += xv.y * t.x;
+                    }
+                }
+                r[oo] = sx[fpad(u0 + o + FIR_U)];
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < FIR_U; u++) {
+        long long i = i0 + u0 + u;
+        if (i < N) {
+            if (XC) reinterpret_cast<C*>(y_)[vec * N + i] = acc[u];
+            else reinterpret_cast<T*>(y_)[vec * N + i] = acc[u].x;
+        }
+    }
+}
+
+template <typename T>
+int fir_convolve(const void* x, void* y, const void* h, size_t N, size_t batch, size_t L, size_t cl, int x_complex,
+                 int h_complex, cudaStream_t st) {
+    typedef typename CpxOf<T>::type C;
+    if (x == y) { set_last_error("fir_convolve: in-place operation is not supported"); return -3; }
+    const long long tpv = (long long)((N + FIR_TILE - 1) / FIR_TILE);
+    const size_t W = FIR_TILE + L - 1 + FIR_U + 1;
+    const size_t smem = (L + W + W / 8 + 2) * sizeof(C);
+    if (smem > 200 * 1024) { set_last_error("fir_convolve: too many taps (%zu)", L); return -2; }
+    const long long grid = tpv * (long long)batch;
+#define BDSP_FIR(XC_, HC_)                                                                                             \
+    do {                                                                                                               \
+        if (smem > 48 * 1024) BDSP_CUDA_OK(cudaFuncSetAttribute(fir_kernel<T, XC_, HC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        fir_kernel<T, XC_, HC_><<<(unsigned)grid, FIR_THREADS, smem, st>>>(x, y, h, (long long)N, (long long)batch, (int)L, (int)cl, tpv); \
+    } while (0)
+    if (x_complex && h_complex) BDSP_FIR(true, true);
+    else if (x_complex) BDSP_FIR(true, false);
+    else if (!h_complex) BDSP_FIR(false, false);
+    else { set_last_error("fir_convolve: real vector with complex taps"); return -2; }
+#undef BDSP_FIR
+    BDSP_LAUNCHED();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// full-length frequency-domain path for impulse responses too long for a block transform:
+//   y = IFFT(FFT(x) * FFT(roll(pad(h, N), -(cl-1)))) / N
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void pad_roll_h_kernel(const void* __restrict__ h_, typename CpxOf<T>::type* __restrict__ hp, long long L,
+                                  long long N, long long shift, int h_is_real) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    // hp[i] = padded[(i + shift) mod N]
+    long long src = (i + shift) % N;
+    typename CpxOf<T>::type v = mk<T>(0, 0);
+    if (src < L) {
+        if (h_is_real) v.x = reinterpret_cast<const T*>(h_)[src];
+        else v = reinterpret_cast<const typename CpxOf<T>::type*>(h_)[src];
+    }
+    hp[i] = v;
+}
+
+template <typename T>
+__global__ void spectrum_mul_kernel(typename CpxOf<T>::type* __restrict__ X, const typename CpxOf<T>::type* __restrict__ H,
+                                    long long N, long long batch, T scale) {
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= N * batch) return;
+    typename CpxOf<T>::type v = cmul(X[gid], H[gid % N]);
+    v.x *= scale; v.y *= scale;
+    X[gid] = v;
+}
+
+template <typename T>
+__global__ void real_to_complex_kernel(const T* __restrict__ in, typename CpxOf<T>::type* __restrict__ out, long long n) {
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid < n) out[gid] = mk<T>(in[gid], (T)0);
+}
+template <typename T>
+__global__ void complex_to_real_kernel(const typename CpxOf<T>::type* __restrict__ in, T* __restrict__ out, long long n) {
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid < n) out[gid] = in[gid].x;
+}
+
+template <typename T>
+int fft_convolve_full(const void* x, void* y, const void* h, size_t N, size_t batch, size_t L, int is_real,
+                      int h_is_real, cudaStream_t st) {
+    typedef typename CpxOf<T>::type C;
+    const size_t cl = L - L / 2;
+    C* Hf = reinterpret_cast<C*>(workspace(N * sizeof(C), 2));
+    C* X = reinterpret_cast<C*>(workspace(N * batch * sizeof(C), 3));
+    pad_roll_h_kernel<T><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(h, Hf, (long long)L, (long long)N, (long long)(cl - 1), h_is_real);
+    BDSP_LAUNCHED();
+    FftOpts f;
+    int rc = fft_exec<T>(Hf, Hf, N, 1, f, nullptr, 0, st);
+    if (rc) return rc;
+    FftOpts fx;
+    fx.real_input = is_real;
+    rc = fft_exec<T>(x, X, N, batch, fx, nullptr, 0, st);
+    if (rc) return rc;
+    const long long tot = (long long)(N * batch);
+    spectrum_mul_kernel<T><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(X, Hf, (long long)N, (long long)batch, (T)(1.0 / (double)N));
+    BDSP_LAUNCHED();
+    FftOpts inv;
+    inv.inverse = 1;
+    if (!is_real) return fft_exec<T>(X, y, N, batch, inv, nullptr, 0, st);
+    rc = fft_exec<T>(X, X, N, batch, inv, nullptr, 0, st);
+    if (rc) return rc;
+    complex_to_real_kernel<T><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(X, reinterpret_cast<T*>(y), tot);
+    BDSP_LAUNCHED();
+    return 0;
+}
+
+#define BDSP_INST(T)                                                                                                    \
+    template size_t ols_block_len<T>(size_t);                                                                           \
+    template size_t ols_max_taps<T>();                                                                                  \
+    template int ols_prepare<T>(const void*, size_t, int, void*, size_t, cudaStream_t);                                  \
+    template int ols_convolve<T>(const void*, void*, size_t, size_t, size_t, const void*, size_t, int, cudaStream_t);    \
+    template int fir_convolve<T>(const void*, void*, const void*, size_t, size_t, size_t, size_t, int, int, cudaStream_t); \
+    template int fft_convolve_full<T>(const void*, void*, const void*, size_t, size_t, size_t, int, int, cudaStream_t);
+BDSP_INST(float)
+BDSP_INST(double)
+#undef BDSP_INST
+
+}  // namespace bdsp

@@ -1,0 +1,543 @@
+// FFT engine: plain unnormalised DFT of any length on device-resident interleaved complex data.
+//
+// Replaces the reference's call into rustfft (vector/src/vector_types/time_freq/mod.rs:32-63) and
+// its clFFT offload (vector/src/gpu_support/ocl/mod.rs:335-349,395-413).
+//
+//   n = 2^k <= block limit : one CTA per (group of) sequence(s), whole sequence in shared memory
+//                            -> one HBM read + one HBM write (fft_block_kernel)
+//   n = 2^k larger         : 2 or 3 passes of shared-memory tiles (fft_tile_kernel); the twiddle
+//                            between passes is fused into the store of the earlier pass and the
+//                            transposition into the store of the last one
+//   n = q * 2^k, q odd<=31 : one radix-q pass (dft_q_pass_kernel) + the power-of-two machinery
+//   any other n            : Bluestein chirp-z on top of the power-of-two transform
+//
+// ifft_shift / scaling / real->complex are fused into the load of the first pass, fft_shift and
+// magnitude into the store of the last one (FftOpts).
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "fft.cuh"
+#include "fft_core.cuh"
+
+namespace bdsp {
+
+// ------------------------------------------------------------------------------------------
+// per-device state: twiddle tables, workspaces
+// ------------------------------------------------------------------------------------------
+namespace {
+struct DeviceState {
+    float2* tw32 = nullptr;
+    double2* tw64 = nullptr;
+    void* ws[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t ws_bytes[4] = {0, 0, 0, 0};
+    int sms = 0;
+};
+std::mutex g_mu;
+std::map<int, DeviceState> g_dev;
+
+DeviceState& dev_state() {
+    int d = 0;
+    BDSP_CUDA_ABORT(cudaGetDevice(&d));
+    std::lock_guard<std::mutex> lk(g_mu);
+    DeviceState& s = g_dev[d];
+    if (!s.tw32) {
+        std::vector<float2> h32(BDSP_TW_LEN);
+        std::vector<double2> h64(BDSP_TW_LEN);
+        for (int i = 0; i < BDSP_TW_LEN; i++) {
+            // exact octant symmetry is not needed: long double evaluation then rounding
+            long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)i / (long double)BDSP_TW_LEN;
+            long double c = cosl(a), sn = sinl(a);
+            if (i == 0) { c = 1; sn = 0; }
+            if (i == BDSP_TW_LEN / 4) { c = 0; sn = -1; }
+            if (i == BDSP_TW_LEN / 2) { c = -1; sn = 0; }
+            if (i == 3 * BDSP_TW_LEN / 4) { c = 0; sn = 1; }
+            h64[i].x = (double)c; h64[i].y = (double)sn;
+            h32[i].x = (float)c; h32[i].y = (float)sn;
+        }
+        BDSP_CUDA_ABORT(cudaMalloc(&s.tw32, sizeof(float2) * BDSP_TW_LEN));
+        BDSP_CUDA_ABORT(cudaMalloc(&s.tw64, sizeof(double2) * BDSP_TW_LEN));
+        BDSP_CUDA_ABORT(cudaMemcpy(s.tw32, h32.data(), sizeof(float2) * BDSP_TW_LEN, cudaMemcpyHostToDevice));
+        BDSP_CUDA_ABORT(cudaMemcpy(s.tw64, h64.data(), sizeof(double2) * BDSP_TW_LEN, cudaMemcpyHostToDevice));
+        BDSP_CUDA_ABORT(cudaDeviceGetAttribute(&s.sms, cudaDevAttrMultiProcessorCount, d));
+    }
+    return s;
+}
+}  // namespace
+
+int sm_count() { return dev_state().sms; }
+
+template <> const float2* twiddle_table<float>() { return dev_state().tw32; }
+template <> const double2* twiddle_table<double>() { return dev_state().tw64; }
+
+void* workspace(size_t bytes, int slot) {
+    DeviceState& s = dev_state();
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (s.ws_bytes[slot] < bytes) {
+        if (s.ws[slot]) {
+            BDSP_CUDA_ABORT(cudaDeviceSynchronize());
+            BDSP_CUDA_ABORT(cudaFree(s.ws[slot]));
+        }
+        size_t want = bytes + bytes / 8;
+        BDSP_CUDA_ABORT(cudaMalloc(&s.ws[slot], want));
+        s.ws_bytes[slot] = want;
+    }
+    return s.ws[slot];
+}
+
+template <> size_t fft_block_max_n<float>() { return 16384; }
+template <> size_t fft_block_max_n<double>() { return 8192; }
+
+// ------------------------------------------------------------------------------------------
+// output addressing shared by all "last pass" kernels
+// ------------------------------------------------------------------------------------------
+struct OutMap {
+    // result element k of inner sequence b goes to
+    //   group = b / seq_group, r = b % seq_group, local = r + k*oes,
+    //   address = group*group_stride + (local + rot) mod rot_n
+    long long seq_group;
+    long long oes;
+    long long group_stride;
+    long long rot;
+    long long rot_n;
+};
+
+__device__ __forceinline__ long long out_addr(const OutMap& m, long long b, long long k) {
+    long long g = b / m.seq_group, r = b - g * m.seq_group;
+    long long local = r + k * m.oes + m.rot;
+    if (local >= m.rot_n) local -= m.rot_n;
+    return g * m.group_stride + local;
+}
+
+template <typename T> __device__ __forceinline__ T mag_of(T re, T im) { return sqrt(re * re + im * im); }
+
+// ------------------------------------------------------------------------------------------
+// single-CTA kernel: nfft sequences of n = 2^log2n points per CTA
+// ------------------------------------------------------------------------------------------
+template <typename T, bool INV, bool REAL_IN, bool MAG>
+__global__ void __launch_bounds__(sizeof(T) == 4 ? 1024 : 512) fft_block_kernel(const void* __restrict__ in_, void* __restrict__ out_, int log2n, int nfft,
+                                 long long batch, long long in_rot, T scale, OutMap om,
+                                 const typename CpxOf<T>::type* __restrict__ tw) {
+    typedef typename CpxOf<T>::type C;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C* s = reinterpret_cast<C*>(smem_raw);
+    const int n = 1 << log2n;
+    const int total = n * nfft;
+    const long long seq0 = (long long)blockIdx.x * nfft;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        int f = idx >> log2n, p = idx & (n - 1);
+        long long seq = seq0 + f;
+        C v = mk<T>(0, 0);
+        if (seq < batch) {
+            long long src = (p + in_rot) & (n - 1);
+            if (REAL_IN) v.x = reinterpret_cast<const T*>(in_)[seq * n + src];
+            else v = reinterpret_cast<const C*>(in_)[seq * n + src];
+            v.x *= scale; v.y *= scale;
+        }
+        s[spad(idx)] = v;
+    }
+    __syncthreads();
+    block_fft<T, INV>(s, log2n, nfft, tw);
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        int f = idx >> log2n, k = idx & (n - 1);
+        long long seq = seq0 + f;
+        if (seq < batch) {
+            C v = s[spad(idx)];
+            long long a = out_addr(om, seq, k);
+            if (MAG) reinterpret_cast<T*>(out_)[a] = mag_of(v.x, v.y);
+            else reinterpret_cast<C*>(out_)[a] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// tile kernel for multi-pass transforms: CT lanes x m points per CTA
+// ------------------------------------------------------------------------------------------
+struct TileParams {
+    const void* in;
+    void* out;
+    int log2m;
+    int ct;                    // lanes per tile (power of two)
+    long long lanes;           // lanes per o1 group
+    long long o1_count;
+    long long in_lane_stride, in_point_stride, in_o1_stride, in_batch_stride;
+    long long out_lane_stride, out_point_stride, out_o1_stride, out_batch_stride;
+    long long tw_n;            // 0: no twiddle; else multiply result (lane, k) by W_{tw_n}^{lane*k}
+    long long in_rot, in_n;    // first pass: read element (g + in_rot) mod in_n of the sequence
+    int real_input;
+    int last;                  // last pass: out index goes through OutMap (batch = inner sequence)
+    int magnitude;
+    OutMap om;
+};
+
+template <typename T, bool INV>
+__global__ void __launch_bounds__(sizeof(T) == 4 ? 1024 : 512) fft_tile_kernel(TileParams p, T scale, const typename CpxOf<T>::type* __restrict__ tw) {
+    typedef typename CpxOf<T>::type C;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C* s = reinterpret_cast<C*>(smem_raw);
+    const int m = 1 << p.log2m;
+    const int ct = p.ct;
+    const int sstride = m + 16;  // sequence stride in shared memory (keeps lane-major accesses conflict free)
+    const long long tiles_per_o1 = p.lanes / ct;
+    long long t = blockIdx.x;
+    const long long tile = t % tiles_per_o1; t /= tiles_per_o1;
+    const long long o1 = t % p.o1_count;
+    const long long b = t / p.o1_count;
+    const long long lane0 = tile * ct;
+    const long long in_base = b * p.in_batch_stride + o1 * p.in_o1_stride;
+    const int total = m * ct;
+    // ---- load ----
+    if (p.in_point_stride == 1) {
+        for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+            int l = idx >> p.log2m, pt = idx & (m - 1);
+            long long g = o1 * p.in_o1_stride + (lane0 + l) * p.in_lane_stride + pt;
+            g += p.in_rot; if (g >= p.in_n) g -= p.in_n;
+            C v;
+            if (p.real_input) { v.x = reinterpret_cast<const T*>(p.in)[b * p.in_batch_stride + g]; v.y = 0; }
+            else v = reinterpret_cast<const C*>(p.in)[b * p.in_batch_stride + g];
+            v.x *= scale; v.y *= scale;
+            s[spad(l * sstride + pt)] = v;
+        }
+    } else {
+        const int lct = __ffs(ct) - 1;
+        for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+            int pt = idx >> lct, l = idx & (ct - 1);
+            long long g = o1 * p.in_o1_stride + (lane0 + l) * p.in_lane_stride + (long long)pt * p.in_point_stride;
+            g += p.in_rot; if (g >= p.in_n) g -= p.in_n;
+            C v;
+            if (p.real_input) { v.x = reinterpret_cast<const T*>(p.in)[b * p.in_batch_stride + g]; v.y = 0; }
+            else v = reinterpret_cast<const C*>(p.in)[b * p.in_batch_stride + g];
+            v.x *= scale; v.y *= scale;
+            s[spad(l * sstride + pt)] = v;
+        }
+    }
+    (void)in_base;
+    __syncthreads();
+    // ---- transform ----
+    {
+        const int n = m;
+        int Ns = 1, rem = p.log2m;
+        // same stage sequence as block_fft, but with the padded sequence stride
+        while (rem >= 4) { stockham_stage_strided<T, 16, INV, 1>(s, n, ct, sstride, Ns, tw); Ns <<= 4; rem -= 4; }
+        if (rem == 3) stockham_stage_strided<T, 8, INV, 2>(s, n, ct, sstride, Ns, tw);
+        else if (rem == 2) stockham_stage_strided<T, 4, INV, 4>(s, n, ct, sstride, Ns, tw);
+        else if (rem == 1) stockham_stage_strided<T, 2, INV, 8>(s, n, ct, sstride, Ns, tw);
+    }
+    // ---- twiddle + store ----
+    const bool lane_major = (p.out_lane_stride <= p.out_point_stride);
+    const int lct = __ffs(ct) - 1;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        int l, k;
+        if (lane_major) { k = idx >> lct; l = idx & (ct - 1); }
+        else { l = idx >> p.log2m; k = idx & (m - 1); }
+        C v = s[spad(l * sstride + k)];
+        const long long lane = lane0 + l;
+        if (p.tw_n) {
+            C w = unit_root<T>((unsigned long long)lane * (unsigned long long)k, (unsigned long long)p.tw_n, INV ? 1 : -1);
+            v = cmul(v, w);
+        }
+        long long local = o1 * p.out_o1_stride + lane * p.out_lane_stride + (long long)k * p.out_point_stride;
+        if (p.last) {
+            long long a = out_addr(p.om, b, local);
+            if (p.magnitude) reinterpret_cast<T*>(p.out)[a] = mag_of(v.x, v.y);
+            else reinterpret_cast<C*>(p.out)[a] = v;
+        } else {
+            reinterpret_cast<C*>(p.out)[b * p.out_batch_stride + local] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// radix-q pass for n = q * P, q odd and small:  y[k1*P + n2] = W_n^{n2 k1} sum_{n1} x[n1*P + n2] W_q^{n1 k1}
+// ------------------------------------------------------------------------------------------
+template <typename T, bool INV>
+__global__ void dft_q_pass_kernel(const void* __restrict__ in_, typename CpxOf<T>::type* __restrict__ out, int q,
+                                  long long P, long long batch, long long in_rot, int real_input, T scale) {
+    typedef typename CpxOf<T>::type C;
+    const long long n = (long long)q * P;
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= P * batch) return;
+    const long long b = gid / P, n2 = gid - b * P;
+    const int sign = INV ? 1 : -1;
+    for (int k1 = 0; k1 < q; k1++) {
+        C acc = mk<T>(0, 0);
+        for (int n1 = 0; n1 < q; n1++) {
+            long long g = (long long)n1 * P + n2 + in_rot;
+            if (g >= n) g -= n;
+            C v;
+            if (real_input) { v.x = reinterpret_cast<const T*>(in_)[b * n + g]; v.y = 0; }
+            else v = reinterpret_cast<const C*>(in_)[b * n + g];
+            C w = unit_root<T>((unsigned long long)((n1 * k1) % q), (unsigned long long)q, sign);
+            acc = cadd(acc, cmul(v, w));
+        }
+        C w = unit_root<T>((unsigned long long)n2 * (unsigned long long)k1, (unsigned long long)n, sign);
+        acc = cmul(acc, w);
+        acc.x *= scale; acc.y *= scale;
+        out[b * n + (long long)k1 * P + n2] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Bluestein helpers:  X[k] = conj(c[k]) * sum_n (x[n] conj(c[n])) c[k-n],  c[n] = exp(+-i pi n^2 / N)
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ typename CpxOf<T>::type chirp(long long i, long long n, int sign) {
+    // exp(sign * i*pi*i^2/n); i^2 mod 2n computed exactly
+    unsigned long long m = (unsigned long long)i % (unsigned long long)(2 * n);
+    unsigned long long sq = (m * m) % (unsigned long long)(2 * n);  // m < 2^32 guaranteed by the host
+    return unit_root<T>(sq, (unsigned long long)(2 * n), sign);
+}
+
+template <typename T, bool INV>
+__global__ void bluestein_pre_kernel(const void* __restrict__ in_, typename CpxOf<T>::type* __restrict__ a,
+                                     long long n, long long M, long long batch, long long in_rot, int real_input, T scale) {
+    typedef typename CpxOf<T>::type C;
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= M * batch) return;
+    long long b = gid / M, i = gid - b * M;
+    C v = mk<T>(0, 0);
+    if (i < n) {
+        long long g = i + in_rot; if (g >= n) g -= n;
+        if (real_input) v.x = reinterpret_cast<const T*>(in_)[b * n + g];
+        else v = reinterpret_cast<const C*>(in_)[b * n + g];
+        v.x *= scale; v.y *= scale;
+        v = cmul(v, chirp<T>(i, n, INV ? 1 : -1));
+    }
+    a[gid] = v;
+}
+
+template <typename T, bool INV>
+__global__ void bluestein_filter_kernel(typename CpxOf<T>::type* __restrict__ bfilt, long long n, long long M) {
+    typedef typename CpxOf<T>::type C;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    C v = mk<T>(0, 0);
+    if (i < n) v = chirp<T>(i, n, INV ? -1 : 1);
+    else if (i > M - n) v = chirp<T>(M - i, n, INV ? -1 : 1);
+    bfilt[i] = v;
+}
+
+template <typename T>
+__global__ void pointwise_mul_bcast_kernel(typename CpxOf<T>::type* __restrict__ a,
+                                           const typename CpxOf<T>::type* __restrict__ bspec, long long M,
+                                           long long batch, T scale) {
+    typedef typename CpxOf<T>::type C;
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= M * batch) return;
+    C v = cmul(a[gid], bspec[gid % M]);
+    v.x *= scale; v.y *= scale;
+    a[gid] = v;
+}
+
+template <typename T, bool INV>
+__global__ void bluestein_post_kernel(const typename CpxOf<T>::type* __restrict__ c, void* __restrict__ out_,
+                                      long long n, long long M, long long batch, OutMap om, int magnitude) {
+    typedef typename CpxOf<T>::type C;
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= n * batch) return;
+    long long b = gid / n, k = gid - b * n;
+    C v = cmul(c[b * M + k], chirp<T>(k, n, INV ? 1 : -1));
+    long long a = out_addr(om, b, k);
+    if (magnitude) reinterpret_cast<T*>(out_)[a] = mag_of(v.x, v.y);
+    else reinterpret_cast<C*>(out_)[a] = v;
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+namespace {
+
+template <typename K> int set_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) BDSP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return 0;
+}
+
+template <typename T, bool INV>
+int launch_block(const void* in, void* out, size_t n, size_t batch, bool real_in, bool mag, long long in_rot,
+                 T scale, const OutMap& om, cudaStream_t st) {
+    typedef typename CpxOf<T>::type C;
+    const int log2n = ilog2(n);
+    int nfft = (int)(4096 / n);
+    if (nfft < 1) nfft = 1;
+    if ((size_t)nfft > batch) nfft = (int)batch;
+    const int threads = block_fft_threads((int)n, nfft);
+    const size_t smem = spad_host(n * nfft) * sizeof(C);
+    const long long grid = ((long long)batch + nfft - 1) / nfft;
+    const C* tw = twiddle_table<T>();
+#define BDSP_LAUNCH_BLOCK(RI, MG)                                                                   \
+    do {                                                                                            \
+        int rc = set_smem(fft_block_kernel<T, INV, RI, MG>, smem);                                  \
+        if (rc) return rc;                                                                          \
+        fft_block_kernel<T, INV, RI, MG><<<(unsigned)grid, threads, smem, st>>>(                    \
+            in, out, log2n, nfft, (long long)batch, in_rot, scale, om, tw);                         \
+    } while (0)
+    if (real_in && mag) BDSP_LAUNCH_BLOCK(true, true);
+    else if (real_in) BDSP_LAUNCH_BLOCK(true, false);
+    else if (mag) BDSP_LAUNCH_BLOCK(false, true);
+    else BDSP_LAUNCH_BLOCK(false, false);
+#undef BDSP_LAUNCH_BLOCK
+    BDSP_LAUNCHED();
+    return 0;
+}
+
+template <typename T, bool INV>
+int launch_tile(const TileParams& p, long long batch, T scale, cudaStream_t st) {
+    typedef typename CpxOf<T>::type C;
+    const int m = 1 << p.log2m;
+    const size_t smem = spad_host((size_t)(m + 16) * p.ct) * sizeof(C);
+    int threads = block_fft_threads(m, p.ct);
+    const long long grid = batch * p.o1_count * (p.lanes / p.ct);
+    int rc = set_smem(fft_tile_kernel<T, INV>, smem);
+    if (rc) return rc;
+    fft_tile_kernel<T, INV><<<(unsigned)grid, threads, smem, st>>>(p, scale, twiddle_table<T>());
+    BDSP_LAUNCHED();
+    return 0;
+}
+
+template <typename T> int tile_log2m_max() { return sizeof(T) == 4 ? 10 : 9; }
+
+// power-of-two transform of `batch` sequences; handles any supported size
+template <typename T, bool INV>
+int fft_pow2(const void* in, void* out, size_t n, size_t batch, bool real_in, bool mag, long long in_rot, T scale,
+             const OutMap& om, void* work, cudaStream_t st) {
+    if (n <= fft_block_max_n<T>()) return launch_block<T, INV>(in, out, n, batch, real_in, mag, in_rot, scale, om, st);
+    const int L = ilog2(n);
+    const int mx = tile_log2m_max<T>();
+    int npass = (L + mx - 1) / mx;
+    if (npass > 3) { set_last_error("fft: length 2^%d too large for this build", L); return -2; }
+    int l[3] = {0, 0, 0};
+    for (int i = 0; i < npass; i++) l[i] = L / npass + (i < L % npass ? 1 : 0);
+    const long long n1 = 1ll << l[0], n2 = 1ll << l[1], n3 = npass == 3 ? (1ll << l[2]) : 1;
+    typedef typename CpxOf<T>::type C;
+    C* tmp = reinterpret_cast<C*>(work);
+    TileParams p;
+    // pass A: columns of length n1, stride n/n1, lanes contiguous
+    p.in = in; p.out = tmp; p.log2m = l[0];
+    p.lanes = (long long)n / n1; p.ct = (int)(p.lanes < 16 ? p.lanes : 16); p.o1_count = 1;
+    p.in_lane_stride = 1; p.in_point_stride = (long long)n / n1; p.in_o1_stride = 0; p.in_batch_stride = (long long)n;
+    p.out_lane_stride = 1; p.out_point_stride = (long long)n / n1; p.out_o1_stride = 0; p.out_batch_stride = (long long)n;
+    p.tw_n = (long long)n; p.in_rot = in_rot; p.in_n = (long long)n; p.real_input = real_in; p.last = 0; p.magnitude = 0;
+    p.om = om;
+    int rc = launch_tile<T, INV>(p, (long long)batch, scale, st);
+    if (rc) return rc;
+    if (npass == 3) {
+        // pass B: inside every row k1: columns of length n2, stride n3, in place
+        p.in = tmp; p.out = tmp; p.log2m = l[1];
+        p.lanes = n3; p.ct = (int)(n3 < 16 ? n3 : 16); p.o1_count = n1;
+        p.in_lane_stride = 1; p.in_point_stride = n3; p.in_o1_stride = n2 * n3;
+        p.out_lane_stride = 1; p.out_point_stride = n3; p.out_o1_stride = n2 * n3;
+        p.tw_n = n2 * n3; p.in_rot = 0; p.real_input = 0;
+        rc = launch_tile<T, INV>(p, (long long)batch, (T)1, st);
+        if (rc) return rc;
+    }
+    // last pass: rows of length nl (contiguous), lanes = k1 (stride n/n1), transposing store
+    const long long nl = npass == 3 ? n3 : n2;
+    p.in = tmp; p.out = out; p.log2m = npass == 3 ? l[2] : l[1];
+    p.lanes = n1; p.ct = (int)(n1 < 16 ? n1 : 16);
+    p.o1_count = npass == 3 ? n2 : 1;
+    p.in_lane_stride = (long long)n / n1; p.in_point_stride = 1; p.in_o1_stride = npass == 3 ? nl : 0;
+    p.out_lane_stride = 1; p.out_point_stride = npass == 3 ? n1 * n2 : n1; p.out_o1_stride = npass == 3 ? n1 : 0;
+    p.tw_n = 0; p.in_rot = 0; p.real_input = 0; p.last = 1; p.magnitude = mag;
+    return launch_tile<T, INV>(p, (long long)batch, (T)1, st);
+}
+
+struct BluesteinKey {
+    size_t n; int inv; int is64; int dev;
+    bool operator<(const BluesteinKey& o) const {
+        if (n != o.n) return n < o.n;
+        if (inv != o.inv) return inv < o.inv;
+        if (is64 != o.is64) return is64 < o.is64;
+        return dev < o.dev;
+    }
+};
+std::map<BluesteinKey, void*> g_bluestein;
+
+template <typename T, bool INV>
+int fft_any(const void* in, void* out, size_t n, size_t batch, const FftOpts& o, void* work, size_t work_bytes,
+            cudaStream_t st) {
+    typedef typename CpxOf<T>::type C;
+    OutMap om;
+    om.seq_group = 1; om.oes = 1; om.group_stride = (long long)n; om.rot = (long long)(o.out_rot % n); om.rot_n = (long long)n;
+    const long long in_rot = (long long)(o.in_rot % n);
+    const T scale = (T)o.scale;
+    if (is_pow2(n)) {
+        void* w = work;
+        if (n > fft_block_max_n<T>()) {
+            size_t need = n * batch * sizeof(C);
+            if (!w || work_bytes < need) w = workspace(need, 0);
+        }
+        return fft_pow2<T, INV>(in, out, n, batch, o.real_input, o.magnitude, in_rot, scale, om, w, st);
+    }
+    // n = q * P with q odd
+    size_t P = 1;
+    while ((n % (2 * P)) == 0) P *= 2;
+    const size_t q = n / P;
+    if (q <= 31 && P >= 2) {
+        size_t need = n * batch * sizeof(C);
+        C* w1 = reinterpret_cast<C*>(workspace(need, 1));
+        const long long tot = (long long)(P * batch);
+        dft_q_pass_kernel<T, INV><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(in, w1, (int)q, (long long)P, (long long)batch,
+                                                                                  in_rot, o.real_input, scale);
+        BDSP_LAUNCHED();
+        OutMap om2;
+        om2.seq_group = (long long)q; om2.oes = (long long)q; om2.group_stride = (long long)n;
+        om2.rot = om.rot; om2.rot_n = (long long)n;
+        void* w0 = nullptr;
+        if (P > fft_block_max_n<T>()) w0 = workspace(need, 0);
+        return fft_pow2<T, INV>(w1, out, P, batch * q, false, o.magnitude, 0, (T)1, om2, w0, st);
+    }
+    // Bluestein
+    if (n >= (1ull << 31)) { set_last_error("fft: length %zu not supported", n); return -2; }
+    const size_t M = next_pow2(2 * n - 1);
+    C* a = reinterpret_cast<C*>(workspace(M * batch * sizeof(C), 1));
+    C* bspec = nullptr;
+    {
+        int d = 0; BDSP_CUDA_OK(cudaGetDevice(&d));
+        BluesteinKey key{n, INV ? 1 : 0, sizeof(T) == 8 ? 1 : 0, d};
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_bluestein.find(key);
+        if (it != g_bluestein.end()) bspec = reinterpret_cast<C*>(it->second);
+    }
+    OutMap plain; plain.seq_group = 1; plain.oes = 1; plain.group_stride = (long long)M; plain.rot = 0; plain.rot_n = (long long)M;
+    void* w0 = M > fft_block_max_n<T>() ? workspace(M * (batch > 1 ? batch : 1) * sizeof(C), 0) : nullptr;
+    if (!bspec) {
+        BDSP_CUDA_OK(cudaMalloc(&bspec, M * sizeof(C)));
+        bluestein_filter_kernel<T, INV><<<(unsigned)((M + 255) / 256), 256, 0, st>>>(bspec, (long long)n, (long long)M);
+        BDSP_LAUNCHED();
+        int rc = fft_pow2<T, false>(bspec, bspec, M, 1, false, false, 0, (T)1, plain, w0, st);
+        if (rc) return rc;
+        int d = 0; BDSP_CUDA_OK(cudaGetDevice(&d));
+        BluesteinKey key{n, INV ? 1 : 0, sizeof(T) == 8 ? 1 : 0, d};
+        std::lock_guard<std::mutex> lk(g_mu);
+        g_bluestein[key] = bspec;
+    }
+    const long long totM = (long long)(M * batch);
+    bluestein_pre_kernel<T, INV><<<(unsigned)((totM + 255) / 256), 256, 0, st>>>(in, a, (long long)n, (long long)M, (long long)batch,
+                                                                                 in_rot, o.real_input, scale);
+    BDSP_LAUNCHED();
+    int rc = fft_pow2<T, false>(a, a, M, batch, false, false, 0, (T)1, plain, w0, st);
+    if (rc) return rc;
+    pointwise_mul_bcast_kernel<T><<<(unsigned)((totM + 255) / 256), 256, 0, st>>>(a, bspec, (long long)M, (long long)batch, (T)(1.0 / (double)M));
+    BDSP_LAUNCHED();
+    rc = fft_pow2<T, true>(a, a, M, batch, false, false, 0, (T)1, plain, w0, st);
+    if (rc) return rc;
+    const long long totn = (long long)(n * batch);
+    bluestein_post_kernel<T, INV><<<(unsigned)((totn + 255) / 256), 256, 0, st>>>(a, out, (long long)n, (long long)M, (long long)batch, om, o.magnitude);
+    BDSP_LAUNCHED();
+    return 0;
+}
+
+}  // namespace
+
+template <typename T>
+int fft_exec(const void* in, void* out, size_t n, size_t batch, const FftOpts& opts, void* work, size_t work_bytes,
+             cudaStream_t stream) {
+    if (n == 0 || batch == 0) return 0;
+    if (opts.inverse) return fft_any<T, true>(in, out, n, batch, opts, work, work_bytes, stream);
+    return fft_any<T, false>(in, out, n, batch, opts, work, work_bytes, stream);
+}
+
+template int fft_exec<float>(const void*, void*, size_t, size_t, const FftOpts&, void*, size_t, cudaStream_t);
+template int fft_exec<double>(const void*, void*, size_t, size_t, const FftOpts&, void*, size_t, cudaStream_t);
+
+}  // namespace bdsp

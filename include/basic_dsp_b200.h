@@ -1,0 +1,288 @@
+/*
+ * basic_dsp_b200 - C ABI of the B200-native (sm_100a) implementation of basic_dsp's FFT-centred
+ * vector hot path.  The library is a drop-in for the hot-path subset of the reference's `interop`
+ * crate: every function in section 1 has the name, argument order, return struct and error codes of
+ * the `#[no_mangle] extern "C"` function it replaces (cited as file:line in the reference tree,
+ * liebharc/basic_dsp v0.10.0).  `...64` variants are identical with f32 -> f64
+ * (interop/src/facade64.rs is generated from facade32.rs by facade64_create.pl).
+ *
+ * Differences a caller must know about (all documented in INTEGRATION.md):
+ *   - A vector handle owns DEVICE memory (HBM).  `data32`/`complex_data32` return a pointer to a
+ *     host mirror that is refreshed by that call (device -> host copy + sync); writing through it
+ *     does not change the vector.  Use bdsp_upload32/bdsp_download32 for bulk transfers.
+ *   - plain_ifft32/ifft32 return a vector in the TIME domain (the reference leaves the domain tag of
+ *     a GenDspVec at Frequency).
+ *   - Custom impulse-response callbacks are evaluated on the host to build tap tables; they are not
+ *     supported by interpolatef_custom32 for non-integer factors (returns error 7).
+ *   - There is no CPU fallback: every compute entry point fails with a negative code when no CUDA
+ *     device is usable.
+ *
+ * Result codes (interop/src/lib.rs:107-151): 0 ok; -1 vector is in the error state (wrong
+ * real/complex or time/freq for the operation); 1 same size; 2 meta data; 3 must be complex; 4 must
+ * be real; 5 must be time domain; 6 must be frequency domain; 7 invalid argument length; 8 conj
+ * symmetric; 9 odd length; 10 symmetric function; 11 combined-op arguments; 12 not empty; 13 even
+ * length; 14 cannot resize.  Codes <= -1000 are CUDA errors (-(1000 + cudaError_t)); see
+ * bdsp_last_error().
+ */
+#ifndef BASIC_DSP_B200_H
+#define BASIC_DSP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+/* Opaque handles: InteropVec<f32> / InteropVec<f64> (interop/src/lib.rs:16-22). */
+typedef struct BdspVec32 BdspVec32;
+typedef struct BdspVec64 BdspVec64;
+
+/* VectorInteropResult (interop/src/lib.rs:203-212): the vector handle is taken by value and handed
+ * back; callers continue with the returned pointer. */
+typedef struct { int32_t result_code; BdspVec32* vector; } BdspVecResult32;
+typedef struct { int32_t result_code; BdspVec64* vector; } BdspVecResult64;
+
+typedef struct { float re, im; } BdspComplex32;
+typedef struct { double re, im; } BdspComplex64;
+
+/* Callback types of the *_real / *_complex / *_custom entry points (interop/src/lib.rs:279-377). */
+typedef float (*BdspRealFn32)(const void* data, float x);
+typedef double (*BdspRealFn64)(const void* data, double x);
+typedef BdspComplex32 (*BdspComplexFn32)(const void* data, float x);
+typedef BdspComplex64 (*BdspComplexFn64)(const void* data, double x);
+
+/* ===================================================================================================
+ * 1. Reference C ABI, hot-path subset (interop/src/facade32.rs; f64 twins in facade64.rs)
+ * =================================================================================================== */
+
+/* ---- life cycle and meta data -------------------------------------------------------------------- */
+BdspVec32* new32(int32_t is_complex, int32_t domain, float init_value, size_t length, float delta);     /* facade32.rs:22 */
+BdspVec32* new_with_performance_options32(int32_t is_complex, int32_t domain, float init_value, size_t length,
+                                          float delta, size_t core_limit);                                 /* :44, core_limit ignored */
+BdspVec32* new_with_detailed_performance_options32(int32_t is_complex, int32_t domain, float init_value, size_t length,
+                                                   float delta, size_t core_limit, size_t med_dual_core_threshold,
+                                                   size_t med_multi_core_threshold, size_t large_dual_core_threshold,
+                                                   size_t large_multi_core_threshold);                     /* :70 */
+void delete_vector32(BdspVec32* vector);                                                                   /* :17 */
+BdspVec32* clone32(BdspVec32* vector);                                                                     /* :687 (argument is NOT consumed here, unlike the reference which moves it) */
+float get_value32(const BdspVec32* vector, size_t index);                                                  /* :105 */
+void set_value32(BdspVec32* vector, size_t index, float value);                                            /* :110 */
+int32_t is_complex32(const BdspVec32* vector);                                                             /* :115 */
+int32_t get_domain32(const BdspVec32* vector);                                                             /* :130, 0 time / 1 frequency */
+size_t get_len32(const BdspVec32* vector);                                                                 /* :138 */
+void set_len32(BdspVec32* vector, size_t len);                                                             /* :143 */
+size_t get_points32(const BdspVec32* vector);                                                              /* :148 */
+float get_delta32(const BdspVec32* vector);                                                                /* :153 */
+const float* data32(const BdspVec32* vector);                                                              /* :158, host mirror */
+const BdspComplex32* complex_data32(const BdspVec32* vector);                                              /* :163, host mirror */
+size_t get_allocated_len32(const BdspVec32* vector);                                                       /* :168 */
+BdspVecResult32 overwrite_data32(BdspVec32* vector, const float* data, size_t len);                        /* :827, requires len < get_len32 (Q9) */
+
+/* ---- elementwise ------------------------------------------------------------------------------------ */
+BdspVecResult32 add32(BdspVec32* vector, const BdspVec32* operand);                                        /* :173 */
+BdspVecResult32 sub32(BdspVec32* vector, const BdspVec32* operand);                                        /* :178 */
+BdspVecResult32 div32(BdspVec32* vector, const BdspVec32* operand);                                        /* :183 */
+BdspVecResult32 mul32(BdspVec32* vector, const BdspVec32* operand);                                        /* :188 */
+BdspVecResult32 add_vector32(BdspVec32* vector, const BdspVec32* operand);                                 /* :704 */
+BdspVecResult32 sub_vector32(BdspVec32* vector, const BdspVec32* operand);                                 /* :712 */
+BdspVecResult32 div_vector32(BdspVec32* vector, const BdspVec32* operand);                                 /* :720 */
+BdspVecResult32 mul_vector32(BdspVec32* vector, const BdspVec32* operand);                                 /* :728 */
+BdspVecResult32 real_offset32(BdspVec32* vector, float value);                                             /* :363 */
+BdspVecResult32 real_scale32(BdspVec32* vector, float value);                                              /* :368 */
+BdspVecResult32 complex_offset32(BdspVec32* vector, float real, float imag);                               /* :532 */
+BdspVecResult32 complex_scale32(BdspVec32* vector, float real, float imag);                                /* :541 */
+BdspVecResult32 complex_divide32(BdspVec32* vector, float real, float imag);                               /* :550 */
+BdspVecResult32 conj32(BdspVec32* vector);                                                                 /* :579 */
+BdspVecResult32 to_complex32(BdspVec32* vector);                                                           /* :418 */
+
+/* ---- complex -> real ---------------------------------------------------------------------------------- */
+BdspVecResult32 magnitude32(BdspVec32* vector);                                                            /* :559 */
+BdspVecResult32 magnitude_squared32(BdspVec32* vector);                                                    /* :574 */
+BdspVecResult32 phase32(BdspVec32* vector);                                                                /* :662 */
+BdspVecResult32 to_real32(BdspVec32* vector);                                                              /* :584 */
+BdspVecResult32 to_imag32(BdspVec32* vector);                                                              /* :589 */
+/* The getters return 9 on success (convert_void, interop/src/lib.rs:100-105, Q8).  The reference
+ * takes `vector` by value and drops it; here the source vector stays valid and owned by the caller. */
+int32_t get_magnitude32(BdspVec32* vector, BdspVec32* destination);                                        /* :564 */
+int32_t get_magnitude_squared32(BdspVec32* vector, BdspVec32* destination);                                /* :569 */
+int32_t get_phase32(BdspVec32* vector, BdspVec32* destination);                                            /* :667 */
+int32_t get_real32(BdspVec32* vector, BdspVec32* destination);                                             /* :652 */
+int32_t get_imag32(BdspVec32* vector, BdspVec32* destination);                                             /* :657 */
+int32_t get_mag_phase32(BdspVec32* vector, BdspVec32* mag, BdspVec32* phase);                              /* :777 */
+
+/* ---- transforms -------------------------------------------------------------------------------------------- */
+BdspVecResult32 plain_fft32(BdspVec32* vector);                                                            /* :672 */
+BdspVecResult32 plain_ifft32(BdspVec32* vector);                                                           /* :682 */
+BdspVecResult32 fft32(BdspVec32* vector);                                                                  /* :934 */
+BdspVecResult32 ifft32(BdspVec32* vector);                                                                 /* :944 */
+BdspVecResult32 swap_halves32(BdspVec32* vector);                                                          /* :527 */
+BdspVecResult32 fft_shift32(BdspVec32* vector);                                                            /* :963 (not exported by the reference: missing #[no_mangle], Q10) */
+BdspVecResult32 ifft_shift32(BdspVec32* vector);                                                           /* :967 */
+BdspVecResult32 zero_pad32(BdspVec32* vector, size_t points, int32_t padding_option);                      /* :330, 0 End / 1 Surround / 2 Center */
+BdspVecResult32 zero_interleave32(BdspVec32* vector, int32_t factor);                                      /* :340 */
+
+/* ---- convolution ---------------------------------------------------------------------------------------------- */
+BdspVecResult32 convolve_signal32(BdspVec32* vector, const BdspVec32* impulse_response);                   /* :1171 */
+BdspVecResult32 convolve32(BdspVec32* vector, int32_t impulse_response, float rolloff, float ratio, size_t len); /* :1231, 0 Sinc / else RaisedCosine */
+BdspVecResult32 convolve_real32(BdspVec32* vector, BdspRealFn32 impulse_response, const void* impulse_response_data,
+                                uint8_t is_symmetric, float ratio, size_t len);                            /* :1183 */
+BdspVecResult32 convolve_complex32(BdspVec32* vector, BdspComplexFn32 impulse_response, const void* impulse_response_data,
+                                   uint8_t is_symmetric, float ratio, size_t len);                         /* :1206 */
+BdspVecResult32 multiply_frequency_response32(BdspVec32* vector, int32_t frequency_response, float rolloff, float ratio); /* :1293 */
+BdspVecResult32 multiply_frequency_response_real32(BdspVec32* vector, BdspRealFn32 frequency_response,
+                                                   const void* frequency_response_data, uint8_t is_symmetric, float ratio); /* :1247 */
+BdspVecResult32 multiply_frequency_response_complex32(BdspVec32* vector, BdspComplexFn32 frequency_response,
+                                                      const void* frequency_response_data, uint8_t is_symmetric, float ratio); /* :1269 */
+
+/* ---- interpolation --------------------------------------------------------------------------------------------- */
+BdspVecResult32 interpolatef32(BdspVec32* vector, int32_t impulse_response, float rolloff, float interpolation_factor,
+                               float delay, size_t len);                                                   /* :1334 */
+BdspVecResult32 interpolatef_custom32(BdspVec32* vector, BdspRealFn32 impulse_response, const void* impulse_response_data,
+                                      uint8_t is_symmetric, float interpolation_factor, float delay, size_t len); /* :1308 */
+BdspVecResult32 interpolate_lin32(BdspVec32* vector, float interpolation_factor, float delay);             /* :1437 */
+
+/* ---- f64 twins (interop/src/facade64.rs, same line numbers + 1) ------------------------------------------------ */
+BdspVec64* new64(int32_t is_complex, int32_t domain, double init_value, size_t length, double delta);
+BdspVec64* new_with_performance_options64(int32_t is_complex, int32_t domain, double init_value, size_t length, double delta, size_t core_limit);
+BdspVec64* new_with_detailed_performance_options64(int32_t is_complex, int32_t domain, double init_value, size_t length,
+                                                   double delta, size_t core_limit, size_t med_dual_core_threshold,
+                                                   size_t med_multi_core_threshold, size_t large_dual_core_threshold,
+                                                   size_t large_multi_core_threshold);
+void delete_vector64(BdspVec64* vector);
+BdspVec64* clone64(BdspVec64* vector);
+double get_value64(const BdspVec64* vector, size_t index);
+void set_value64(BdspVec64* vector, size_t index, double value);
+int32_t is_complex64(const BdspVec64* vector);
+int32_t get_domain64(const BdspVec64* vector);
+size_t get_len64(const BdspVec64* vector);
+void set_len64(BdspVec64* vector, size_t len);
+size_t get_points64(const BdspVec64* vector);
+double get_delta64(const BdspVec64* vector);
+const double* data64(const BdspVec64* vector);
+const BdspComplex64* complex_data64(const BdspVec64* vector);
+size_t get_allocated_len64(const BdspVec64* vector);
+BdspVecResult64 overwrite_data64(BdspVec64* vector, const double* data, size_t len);
+BdspVecResult64 add64(BdspVec64* vector, const BdspVec64* operand);
+BdspVecResult64 sub64(BdspVec64* vector, const BdspVec64* operand);
+BdspVecResult64 div64(BdspVec64* vector, const BdspVec64* operand);
+BdspVecResult64 mul64(BdspVec64* vector, const BdspVec64* operand);
+BdspVecResult64 add_vector64(BdspVec64* vector, const BdspVec64* operand);
+BdspVecResult64 sub_vector64(BdspVec64* vector, const BdspVec64* operand);
+BdspVecResult64 div_vector64(BdspVec64* vector, const BdspVec64* operand);
+BdspVecResult64 mul_vector64(BdspVec64* vector, const BdspVec64* operand);
+BdspVecResult64 real_offset64(BdspVec64* vector, double value);
+BdspVecResult64 real_scale64(BdspVec64* vector, double value);
+BdspVecResult64 complex_offset64(BdspVec64* vector, double real, double imag);
+BdspVecResult64 complex_scale64(BdspVec64* vector, double real, double imag);
+BdspVecResult64 complex_divide64(BdspVec64* vector, double real, double imag);
+BdspVecResult64 conj64(BdspVec64* vector);
+BdspVecResult64 to_complex64(BdspVec64* vector);
+BdspVecResult64 magnitude64(BdspVec64* vector);
+BdspVecResult64 magnitude_squared64(BdspVec64* vector);
+BdspVecResult64 phase64(BdspVec64* vector);
+BdspVecResult64 to_real64(BdspVec64* vector);
+BdspVecResult64 to_imag64(BdspVec64* vector);
+int32_t get_magnitude64(BdspVec64* vector, BdspVec64* destination);
+int32_t get_magnitude_squared64(BdspVec64* vector, BdspVec64* destination);
+int32_t get_phase64(BdspVec64* vector, BdspVec64* destination);
+int32_t get_real64(BdspVec64* vector, BdspVec64* destination);
+int32_t get_imag64(BdspVec64* vector, BdspVec64* destination);
+int32_t get_mag_phase64(BdspVec64* vector, BdspVec64* mag, BdspVec64* phase);
+BdspVecResult64 plain_fft64(BdspVec64* vector);
+BdspVecResult64 plain_ifft64(BdspVec64* vector);
+BdspVecResult64 fft64(BdspVec64* vector);
+BdspVecResult64 ifft64(BdspVec64* vector);
+BdspVecResult64 swap_halves64(BdspVec64* vector);
+BdspVecResult64 fft_shift64(BdspVec64* vector);
+BdspVecResult64 ifft_shift64(BdspVec64* vector);
+BdspVecResult64 zero_pad64(BdspVec64* vector, size_t points, int32_t padding_option);
+BdspVecResult64 zero_interleave64(BdspVec64* vector, int32_t factor);
+BdspVecResult64 convolve_signal64(BdspVec64* vector, const BdspVec64* impulse_response);
+BdspVecResult64 convolve64(BdspVec64* vector, int32_t impulse_response, double rolloff, double ratio, size_t len);
+BdspVecResult64 convolve_real64(BdspVec64* vector, BdspRealFn64 impulse_response, const void* impulse_response_data,
+                                uint8_t is_symmetric, double ratio, size_t len);
+BdspVecResult64 convolve_complex64(BdspVec64* vector, BdspComplexFn64 impulse_response, const void* impulse_response_data,
+                                   uint8_t is_symmetric, double ratio, size_t len);
+BdspVecResult64 multiply_frequency_response64(BdspVec64* vector, int32_t frequency_response, double rolloff, double ratio);
+BdspVecResult64 multiply_frequency_response_real64(BdspVec64* vector, BdspRealFn64 frequency_response,
+                                                   const void* frequency_response_data, uint8_t is_symmetric, double ratio);
+BdspVecResult64 multiply_frequency_response_complex64(BdspVec64* vector, BdspComplexFn64 frequency_response,
+                                                      const void* frequency_response_data, uint8_t is_symmetric, double ratio);
+BdspVecResult64 interpolatef64(BdspVec64* vector, int32_t impulse_response, double rolloff, double interpolation_factor,
+                               double delay, size_t len);
+BdspVecResult64 interpolatef_custom64(BdspVec64* vector, BdspRealFn64 impulse_response, const void* impulse_response_data,
+                                      uint8_t is_symmetric, double interpolation_factor, double delay, size_t len);
+BdspVecResult64 interpolate_lin64(BdspVec64* vector, double interpolation_factor, double delay);
+
+/* ===================================================================================================
+ * 2. Device-residency extensions (no counterpart in the reference: its vectors live in host memory)
+ * =================================================================================================== */
+const char* bdsp_version(void);
+const char* bdsp_last_error(void);
+int32_t bdsp_device_count(void);
+int32_t bdsp_set_device(int32_t device);              /* device used by subsequent calls of this host thread */
+int32_t bdsp_sync(void);                              /* wait for all work queued by this thread's stream */
+void bdsp_set_stream(void* cuda_stream);              /* cudaStream_t for subsequent calls of this thread (default: stream 0) */
+/* bulk transfers: `len` T scalars; upload resizes the vector (like set_len32) when len != get_len32 */
+int32_t bdsp_upload32(BdspVec32* vector, const float* host, size_t len);
+int32_t bdsp_download32(const BdspVec32* vector, float* host, size_t len);
+int32_t bdsp_upload64(BdspVec64* vector, const double* host, size_t len);
+int32_t bdsp_download64(const BdspVec64* vector, double* host, size_t len);
+void* bdsp_device_ptr32(BdspVec32* vector);           /* device pointer of the vector's storage (interleaved) */
+void* bdsp_device_ptr64(BdspVec64* vector);
+/* fused chain of the sequential trait calls scale(c) -> mul(&w) -> get_mag_phase(&mut mag, &mut phase)
+ * in ONE pass over memory; `vector` keeps scale(c)*w when write_back != 0 */
+int32_t bdsp_scale_mul_mag_phase32(BdspVec32* vector, float scale_re, float scale_im, const BdspVec32* w,
+                                   BdspVec32* mag, BdspVec32* phase, int32_t write_back);
+int32_t bdsp_scale_mul_mag_phase64(BdspVec64* vector, double scale_re, double scale_im, const BdspVec64* w,
+                                   BdspVec64* mag, BdspVec64* phase, int32_t write_back);
+/* fft followed by magnitude in one kernel (fft(&mut buffer).magnitude(), the C3 chain) */
+BdspVecResult32 bdsp_fft_magnitude32(BdspVec32* vector);
+BdspVecResult64 bdsp_fft_magnitude64(BdspVec64* vector);
+
+/* ===================================================================================================
+ * 3. Batched kernels on raw device pointers (rows of the reference's MatrixMxN, matrix/src/time_freq.rs:
+ *    52-74, processed in one launch).  Pointers are device pointers; `rows` independent vectors of
+ *    `points` complex points each, row r at element offset r*points.  flags: see BDSP_F_*.
+ * =================================================================================================== */
+#define BDSP_F_INVERSE 1      /* inverse direction (unnormalised) */
+#define BDSP_F_SHIFT 2        /* forward: fft_shift the result; inverse: scale(1/points) + ifft_shift the input (fft()/ifft() semantics) */
+#define BDSP_F_MAGNITUDE 4    /* store |X| (points real scalars per row) */
+#define BDSP_F_REAL_INPUT 8   /* rows hold `points` real scalars */
+int32_t bdsp_fft_rows_c32(const void* in, void* out, size_t points, size_t rows, int32_t flags);
+int32_t bdsp_fft_rows_c64(const void* in, void* out, size_t points, size_t rows, int32_t flags);
+/* convolve_signal for every row with one impulse response of h_points complex taps (device pointer);
+ * `plan` caches the impulse-response spectrum between calls (create once, reuse, destroy) */
+typedef struct BdspConvPlan BdspConvPlan;
+BdspConvPlan* bdsp_conv_plan_create_c32(const void* h_device, size_t h_points);
+BdspConvPlan* bdsp_conv_plan_create_c64(const void* h_device, size_t h_points);
+void bdsp_conv_plan_destroy(BdspConvPlan* plan);
+int32_t bdsp_convolve_signal_rows_c32(const void* in, void* out, size_t points, size_t rows, const BdspConvPlan* plan);
+int32_t bdsp_convolve_signal_rows_c64(const void* in, void* out, size_t points, size_t rows, const BdspConvPlan* plan);
+/* raw memory helpers so that non-CUDA hosts (ctypes, cgo, JNI) can drive section 3 */
+void* bdsp_malloc(size_t bytes);
+void bdsp_free(void* device_ptr);
+void* bdsp_malloc_host(size_t bytes);                 /* pinned host memory */
+void bdsp_free_host(void* host_ptr);
+int32_t bdsp_memcpy_h2d(void* device_dst, const void* host_src, size_t bytes);   /* async on the thread's stream */
+int32_t bdsp_memcpy_d2h(void* host_dst, const void* device_src, size_t bytes);   /* async on the thread's stream */
+int32_t bdsp_memset(void* device_dst, int32_t value, size_t bytes);
+/* CUDA-event timing on the thread's stream (the stream the kernels above are launched on) */
+void* bdsp_event_create(void);
+void bdsp_event_destroy(void* event);
+int32_t bdsp_event_record(void* event);
+float bdsp_event_elapsed_ms(void* start, void* stop);  /* synchronises on `stop` */
+/* number of kernels launched by this library since process start (all threads) */
+uint64_t bdsp_kernel_launch_count(void);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* BASIC_DSP_B200_H */

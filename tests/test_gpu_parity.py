@@ -1,0 +1,442 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via ctypes) against the CPU oracle and the
+reference's golden vectors.  Tolerances are BASELINE.json's: relative L2 <= 1e-5*log2(N) for f32,
+<= 1e-12*log2(N) for f64, <= 4 ulp for elementwise operations."""
+import math
+
+import numpy as np
+import pytest
+
+import basic_dsp_b200 as bd
+from basic_dsp_b200 import DspVec
+from oracle import dsp_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+
+def tol(n, dtype):
+    return (1e-5 if dtype == np.float32 else 1e-12) * max(1.0, math.log2(max(n, 2)))
+
+
+def rand_c(rng, n, dtype):
+    ct = np.complex64 if dtype == np.float32 else np.complex128
+    return (rng.uniform(-10, 10, n) + 1j * rng.uniform(-10, 10, n)).astype(ct)
+
+
+def vals(kats, key):
+    return np.array(kats[key]["values"], dtype=np.float64)
+
+
+def cplx(interleaved):
+    a = np.asarray(interleaved, dtype=np.float64)
+    return a[0::2] + 1j * a[1::2]
+
+
+# --------------------------------------------------------------------------------------------------
+# transforms
+# --------------------------------------------------------------------------------------------------
+def test_doc_vectors(kats):
+    for key, fn in (("doc_plain_fft", "plain_fft"), ("doc_fft", "fft")):
+        v = DspVec(cplx(kats[key]["input"]).astype(np.complex64))
+        got = getattr(v, fn)().to_numpy()
+        assert np.allclose(got, cplx(kats[key]["values"]), atol=1e-4), key
+        assert v.domain() == bd.FREQ
+    for key, fn in (("doc_plain_ifft", "plain_ifft"), ("doc_ifft", "ifft")):
+        v = DspVec(cplx(kats[key]["input"]).astype(np.complex64), domain=bd.FREQ)
+        got = getattr(v, fn)().to_numpy()
+        assert np.allclose(got, cplx(kats[key]["values"]), atol=1e-4), key
+        assert v.domain() == bd.TIME  # deliberate deviation Q2
+
+
+def test_fft_vector64_golden(kats):  # tests/time_freq_test.rs:45-120
+    n = np.arange(64, dtype=np.float64)
+    x = np.cos(n * 0.1 * 2.0 * np.pi + 0.25)
+    v = DspVec(x, dtype=np.float64).to_complex().fft().magnitude()
+    assert np.max(np.abs(v.to_numpy() - vals(kats, "fft_vector64"))) < 1e-6
+    # real input goes through zero_interleave inside plain_fft (time_to_freq.rs:147-150)
+    v2 = DspVec(x, dtype=np.float64).fft().magnitude()
+    assert np.max(np.abs(v2.to_numpy() - vals(kats, "fft_vector64"))) < 1e-6
+
+
+SIZES = [1, 2, 4, 8, 16, 32, 128, 256, 512, 1024, 2048, 4096, 8192, 16384,      # single CTA
+         1 << 15, 1 << 16, 1 << 18, 1 << 20, 1 << 21,                           # multi-pass
+         3, 5, 6, 12, 24, 3 * 64, 5 * 1024, 7 * 4096, 3 * (1 << 16), 15 * (1 << 14),  # q * 2^k
+         17 * 29, 1001, 9973, 10007 * 3, 127 * 127]                             # Bluestein
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("n", SIZES)
+def test_plain_fft_sizes(n, dtype):
+    rng = np.random.default_rng(n)
+    x = rand_c(rng, n, dtype)
+    v = DspVec(x, delta=0.5)
+    got = v.plain_fft().to_numpy()
+    assert o.rel_l2(got, o.plain_fft(x)) <= tol(n, dtype)
+    assert v.domain() == bd.FREQ and v.is_complex()
+    T = dtype
+    assert v.delta() == float(o.delta_after_fft(0.5, n, T))
+    # inverse (unnormalised) brings back n * x
+    back = v.plain_ifft().to_numpy()
+    assert o.rel_l2(back / n, x) <= 2 * tol(n, dtype)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [7, 8, 64, 1000, 1001, 4096, 65536, 3 * 4096, 1 << 17])
+def test_fft_ifft_shifted(n, dtype):
+    rng = np.random.default_rng(100 + n)
+    x = rand_c(rng, n, dtype)
+    v = DspVec(x)
+    X = v.fft().to_numpy()
+    assert o.rel_l2(X, o.fft(x)) <= tol(n, dtype)
+    y = v.ifft().to_numpy()
+    assert o.rel_l2(y, x) <= 2 * tol(n, dtype)
+    assert o.rel_l2(DspVec(X.copy(), domain=bd.FREQ).ifft().to_numpy(), o.ifft(X)) <= tol(n, dtype)
+
+
+@pytest.mark.parametrize("n", [64, 1001, 4096, 1 << 16])
+def test_real_input_fft(n):  # tests/real_test.rs:581-605
+    rng = np.random.default_rng(n)
+    x = rng.uniform(-10, 10, n).astype(np.float32)
+    got = DspVec(x).plain_fft().to_numpy()
+    assert len(got) == n
+    assert o.rel_l2(got, o.plain_fft(x)) <= tol(n, np.float32)
+
+
+def test_fft_wrong_domain_marks_invalid():
+    v = DspVec(np.ones(8, dtype=np.complex64), domain=bd.FREQ)
+    assert v.result_code_of("fft") == -1
+    assert v.len() == 0 and math.isnan(v.delta())
+    v = DspVec(np.ones(8, dtype=np.complex64), domain=bd.TIME)
+    assert v.result_code_of("ifft") == -1
+
+
+@pytest.mark.parametrize("n", [2, 5, 8, 9, 1000, 1001])
+def test_swap_halves(n):
+    x = np.arange(n, dtype=np.float32)
+    assert np.array_equal(DspVec(x).swap_halves().to_numpy(), np.fft.fftshift(x))
+    c = (np.arange(n) + 1j * np.arange(n)[::-1]).astype(np.complex64)
+    assert np.array_equal(DspVec(c, domain=bd.FREQ).fft_shift().to_numpy(), np.fft.fftshift(c))
+    assert np.array_equal(DspVec(c, domain=bd.FREQ).ifft_shift().to_numpy(), np.fft.ifftshift(c))
+
+
+def test_fft_rows_batched():
+    rng = np.random.default_rng(5)
+    L = bd.lib()
+    for n, rows in [(16384, 8), (1024, 33), (64, 100), (1 << 15, 3)]:
+        x = rand_c(rng, n * rows, np.float32)
+        v = DspVec(x)
+        out = DspVec.zeros(n * rows, dtype=np.float32)
+        rc = L.bdsp_fft_rows_c32(v._fn("bdsp_device_ptr")(v._h), out._fn("bdsp_device_ptr")(out._h), n, rows,
+                                 bd.F_SHIFT | bd.F_MAGNITUDE)
+        assert rc == 0
+        got = out.to_numpy().reshape(rows, n)
+        ref = np.abs(np.fft.fftshift(np.fft.fft(x.reshape(rows, n).astype(np.complex128), axis=1), axes=1))
+        assert o.rel_l2(got, ref) <= tol(n, np.float32)
+
+
+def test_fft_magnitude_fused():
+    rng = np.random.default_rng(6)
+    x = rand_c(rng, 16384, np.float32)
+    got = DspVec(x).fft_magnitude()
+    assert not got.is_complex() and got.len() == 16384
+    assert o.rel_l2(got.to_numpy(), np.abs(o.fft(x))) <= tol(16384, np.float32)
+
+
+# --------------------------------------------------------------------------------------------------
+# convolution
+# --------------------------------------------------------------------------------------------------
+def test_convolve_signal_kats(kats):
+    a = np.arange(10, dtype=np.float32).astype(np.complex64)
+    b = np.zeros(10, dtype=np.complex64); b[4] = 1
+    got = DspVec(a).convolve_signal(DspVec(b)).magnitude().to_numpy()
+    assert np.allclose(got, vals(kats, "shift_left_by_1_as_conv"), atol=1e-4)
+    b = np.array([0, 0, 1], dtype=np.complex64)
+    got = DspVec(a).convolve_signal(DspVec(b)).magnitude().to_numpy()
+    assert np.allclose(got, vals(kats, "shift_left_by_1_as_conv_shorter"), atol=1e-4)
+    # convolution.rs:737-775
+    n = 11
+    x = np.zeros(n, dtype=np.complex64); x[n // 2] = 1
+    h = np.array([o.sinc_impulse(np.float32(v * 0.5), np.float32) for v in np.arange(-5.0, 6.0)]).astype(np.complex64)
+    got = DspVec(x).convolve_signal(DspVec(h)).magnitude().to_numpy()
+    assert np.allclose(got, vals(kats, "convolve_complex_vectors32"), atol=1e-4)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("n,l", [(64, 1), (64, 2), (65, 7), (300, 24), (300, 25), (1000, 129), (5000, 1023),
+                                 (9500, 100), (20000, 1023), (4096, 4096), (10000, 2500), (40000, 5001),
+                                 (3 * 4096 + 5, 2000)])
+def test_convolve_signal_vs_oracle(n, l, dtype):
+    rng = np.random.default_rng(n * 7 + l)
+    x = rand_c(rng, n, dtype)
+    h = (rand_c(rng, l, dtype) / 10).astype(x.dtype)
+    got = DspVec(x).convolve_signal(DspVec(h)).to_numpy()
+    ref = o.convolve_signal_direct(x, h) if n * l < 3e7 else o.convolve_signal(x, h)
+    assert o.rel_l2(got, ref) <= tol(max(n, 4096), dtype)
+
+
+@pytest.mark.parametrize("n,l", [(100, 6), (5000, 63), (20000, 200)])
+def test_convolve_signal_real_vectors(n, l):
+    rng = np.random.default_rng(n + l)
+    x = rng.uniform(-10, 10, n).astype(np.float32)
+    h = rng.uniform(-1, 1, l).astype(np.float32)
+    got = DspVec(x).convolve_signal(DspVec(h)).to_numpy()
+    assert o.rel_l2(got, o.convolve_signal_direct(x, h)) <= tol(4096, np.float32)
+
+
+def test_convolve_signal_c2a_full_size():
+    """BASELINE config C2a: 2^20 c32 with the 1023-tap raised cosine h[k] = RC_0.35((k-511)*0.25)."""
+    n, l = 1 << 20, 1023
+    rng = np.random.default_rng(20260102)
+    x = rand_c(rng, n, np.float32)
+    h = np.array([o.raised_cosine_impulse(np.float32((k - 511) * 0.25), 0.35, np.float32) for k in range(l)])
+    hv = DspVec(h.astype(np.complex64))
+    v = DspVec(x)
+    got = v.convolve_signal(hv).to_numpy()
+    ref = o.convolve_signal(x, h.astype(np.complex128))
+    assert o.rel_l2(got, ref) <= tol(n, np.float32)
+    # size-independent properties: linearity and shift equivariance of the circular convolution
+    x2 = rand_c(rng, n, np.float32)
+    y2 = DspVec(x2).convolve_signal(hv).to_numpy()
+    ys = DspVec((x + 2 * x2).astype(np.complex64)).convolve_signal(hv).to_numpy()
+    assert o.rel_l2(ys, got.astype(np.complex128) + 2 * y2.astype(np.complex128)) <= 4 * tol(n, np.float32)
+    yr = DspVec(np.roll(x, 12345)).convolve_signal(hv).to_numpy()
+    assert o.rel_l2(yr, np.roll(got, 12345)) <= 4 * tol(n, np.float32)
+    # second call reuses the cached impulse-response spectrum
+    again = DspVec(x).convolve_signal(hv).to_numpy()
+    assert np.array_equal(again, got)
+
+
+def test_convolve_signal_rows_api():
+    L = bd.lib()
+    n, rows, l = 20000, 5, 1023
+    rng = np.random.default_rng(9)
+    x = rand_c(rng, n * rows, np.float32)
+    h = (rand_c(rng, l, np.float32) / 10).astype(np.complex64)
+    xv, hv, out = DspVec(x), DspVec(h), DspVec.zeros(2 * n * rows, is_complex=True)
+    dp = lambda v: v._fn("bdsp_device_ptr")(v._h)
+    plan = L.bdsp_conv_plan_create_c32(dp(hv), l)
+    assert plan
+    assert L.bdsp_convolve_signal_rows_c32(dp(xv), dp(out), n, rows, plan) == 0
+    got = out.to_numpy().reshape(rows, n)
+    for r in range(rows):
+        assert o.rel_l2(got[r], o.convolve_signal(x.reshape(rows, n)[r], h)) <= tol(4096, np.float32)
+    L.bdsp_conv_plan_destroy(plan)
+
+
+def test_convolve_signal_errors():
+    x = DspVec(np.ones(10, dtype=np.complex64))
+    assert x.result_code_of("convolve_signal", DspVec(np.ones(11, dtype=np.complex64))) == o.ERR_INVALID_ARG_LEN
+    assert x.result_code_of("convolve_signal", DspVec(np.ones(5, dtype=np.float32))) == o.ERR_META_DATA
+    assert x.result_code_of("convolve_signal", DspVec(np.ones(5, dtype=np.complex64), delta=2.0)) == o.ERR_META_DATA
+    f = DspVec(np.ones(10, dtype=np.complex64), domain=bd.FREQ)
+    assert f.result_code_of("convolve_signal", DspVec(np.ones(5, dtype=np.complex64), domain=bd.FREQ)) == o.ERR_MUST_BE_TIME
+    assert x.result_code_of("convolve_signal", DspVec(np.ones(5, dtype=np.complex64))) == 0
+
+
+def test_convolve_function_kats(kats):
+    x = np.zeros(10, dtype=np.float32); x[5] = 1
+    got = DspVec(x).convolve(bd.RAISED_COSINE, 0.35, 0.2, 5).to_numpy()
+    assert np.max(np.abs(got - vals(kats, "convolve_real_time_and_time32"))) < 1e-4
+    n = 11
+    c = np.zeros(n, dtype=np.complex64); c[n // 2] = 1
+    got = DspVec(c).convolve(bd.SINC, 0.0, 0.5, n // 2).magnitude().to_numpy()
+    assert np.max(np.abs(got - vals(kats, "convolve_complex_time_and_time32"))) < 1e-4
+
+
+@pytest.mark.parametrize("n,ratio,length,cplx_", [(1 << 20, 0.25, 31, True), (5000, 1.0, 12, True), (3000, 1.0, 12, False),
+                                                  (1500, 0.5, 40, False), (20, 0.5, 200, True)])
+def test_convolve_function_vs_oracle(n, ratio, length, cplx_):
+    """(2^20, 0.25, 31) is BASELINE config C2b: 63-tap raised-cosine `convolve`."""
+    rng = np.random.default_rng(n + length)
+    x = rand_c(rng, n, np.float32) if cplx_ else rng.uniform(-10, 10, n).astype(np.float32)
+    got = DspVec(x).convolve(bd.RAISED_COSINE, 0.35, ratio, length).to_numpy()
+    ref = o.convolve_function(x, lambda t: o.raised_cosine_impulse(t, 0.35, np.float32), ratio, length, np.float32)
+    assert o.rel_l2(got, ref) <= tol(4096, np.float32)
+    cb = DspVec(x).convolve(lambda t: float(o.raised_cosine_impulse(t, 0.35, np.float32)), 0.0, ratio, length).to_numpy()
+    assert o.rel_l2(cb, ref) <= tol(4096, np.float32)
+
+
+def test_convolve_complex_callback():
+    rng = np.random.default_rng(77)
+    x = rand_c(rng, 3000, np.float32)
+    fn = lambda t: complex(o.sinc_impulse(t, np.float32), 0.5 * o.sinc_impulse(t * 0.5, np.float32))
+    got = DspVec(x).convolve_complex(fn, 0.5, 10).to_numpy()
+    idx = np.arange(3000)
+    ref = np.zeros(3000, dtype=np.complex128)
+    for m in range(-10, 11):
+        ref += x[(idx + m) % 3000].astype(np.complex128) * fn(np.float32(-m * 0.5))
+    assert o.rel_l2(got, ref) <= tol(4096, np.float32)
+
+
+def test_multiply_frequency_response(kats):
+    for n, key in ((5, "convolve_complex_freq_and_freq32"), (6, "convolve_complex_freq_and_freq_even32")):
+        v = DspVec(np.ones(n, dtype=np.complex64) * (1 + 1j), domain=bd.FREQ)
+        got = v.multiply_frequency_response(bd.RAISED_COSINE, 1.0, 2.0).to_numpy()
+        flat = np.empty(2 * n); flat[0::2], flat[1::2] = got.real, got.imag
+        assert np.max(np.abs(flat - vals(kats, key))) < 1e-4
+    rng = np.random.default_rng(3)
+    X = rand_c(rng, 1001, np.float32)
+    got = DspVec(X, domain=bd.FREQ).multiply_frequency_response(bd.RAISED_COSINE, 0.35, 0.8).to_numpy()
+    ref = o.multiply_frequency_response(X, lambda t: o.raised_cosine_freq(t, 0.35, np.float32), 0.8, np.float32)
+    assert o.rel_l2(got, ref) <= 1e-6
+    cb = DspVec(X, domain=bd.FREQ).multiply_frequency_response(lambda t: float(o.raised_cosine_freq(t, 0.35, np.float32)), 0.0, 0.8).to_numpy()
+    assert o.rel_l2(cb, ref) <= 1e-6
+    assert DspVec(X).result_code_of("multiply_frequency_response", 0, 0.0, 1.0) == -1
+
+
+# --------------------------------------------------------------------------------------------------
+# interpolation
+# --------------------------------------------------------------------------------------------------
+def test_interpolatef_kats(kats):
+    for n, key in ((6, "interpolatef_by_integer_sinc_even_test"), (7, "interpolatef_by_integer_sinc_odd_test")):
+        x = np.zeros(n, dtype=np.complex64); x[n // 2] = 1
+        got = DspVec(x).interpolatef(bd.SINC, 0.0, 2.0, 0.0, n).to_real().to_numpy()
+        assert np.max(np.abs(got - vals(kats, key))) < 0.1
+    x = np.zeros(6, dtype=np.complex64); x[3] = 1
+    got = DspVec(x).interpolatef(bd.SINC, 0.0, 13.0 / 6.0, 0.0, 6).to_real().to_numpy()
+    e = vals(kats, "interpolatef_by_fractional_sinc_test")
+    assert len(got) == len(e) and np.max(np.abs(got - e)) < 0.1
+    got = DspVec(x).interpolatef(bd.SINC, 0.0, 2.0, 1.0, 6).magnitude().to_numpy()
+    assert np.max(np.abs(got - vals(kats, "interpolatef_delayed_sinc_test"))) < 0.1
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("n,F,L,delay,cplx_", [(1000, 4, 12, 0.0, False), (1000, 4, 12, 0.0, True), (777, 3, 5, 0.3, False),
+                                               (2000, 2, 10, 0.0, True), (600, 8, 20, 0.0, False), (500, 16, 4, 0.0, False),
+                                               (1 << 18, 4, 12, 0.0, False), (301, 7, 13, -0.2, True)])
+def test_interpolatef_integer_vs_oracle(n, F, L, delay, cplx_, dtype):
+    rng = np.random.default_rng(n + F)
+    x = rand_c(rng, n, dtype) if cplx_ else rng.uniform(-10, 10, n).astype(dtype)
+    got = DspVec(x).interpolatef(bd.SINC, 0.0, float(F), delay, L).to_numpy()
+    ref = o.interpolatef(x, lambda t: o.sinc_impulse(t, dtype), float(F), delay, L, dtype)
+    assert len(got) == len(ref)
+    assert o.rel_l2(got, ref) <= tol(4096, dtype)
+    # 4-argument custom callback path builds the same tables on the host
+    if n <= 2000:
+        cb = DspVec(x).interpolatef(lambda t: float(o.sinc_impulse(t, dtype)), 0.0, float(F), delay, L).to_numpy()
+        assert o.rel_l2(cb, ref) <= tol(4096, dtype)
+
+
+@pytest.mark.parametrize("n,factor,L,delay,kind", [(400, 2.5, 8, 0.0, 0), (300, 13.0 / 6.0, 6, 0.0, 0), (500, 0.5, 10, 0.0, 1),
+                                                   (100, 3.0, 10, 0.25, 1)])
+def test_interpolatef_scalar_path_vs_oracle(n, factor, L, delay, kind):
+    rng = np.random.default_rng(n)
+    x = rand_c(rng, n, np.float32)
+    f = (lambda t: o.sinc_impulse(t, np.float32)) if kind == 0 else (lambda t: o.raised_cosine_impulse(t, 0.35, np.float32))
+    got = DspVec(x).interpolatef(kind, 0.35, np.float32(factor), delay, L).to_numpy()
+    ref = o.interpolatef(x, f, np.float32(factor), delay, L, np.float32)
+    assert len(got) == len(ref)
+    assert o.rel_l2(got, ref) <= 1e-4  # taps evaluated with device sin/cos in f32
+
+
+def test_interpolate_lin(kats):
+    x = np.array([-1.0, -2.0, -1.0, 0.0, 1.0, 3.0, 4.0], dtype=np.float32)
+    got = DspVec(x).interpolate_lin(4.0, 0.0).to_numpy()
+    assert np.max(np.abs(got - vals(kats, "linear_test"))) < 1e-6
+    rng = np.random.default_rng(1)
+    for dtype in (np.float32, np.float64):
+        for n, F, d in [(1000, 4.0, 0.0), (12345, 3.0, 0.0), (999, 2.5, 0.25), (1 << 20, 4.0, 0.0)]:
+            x = rng.uniform(-10, 10, n).astype(dtype)
+            got = DspVec(x).interpolate_lin(F, d).to_numpy()
+            ref = o.interpolate_lin(x, F, d, dtype)
+            assert len(got) == len(ref)
+            assert np.array_equal(got, ref), (dtype, n, F, d)   # bit exact: same IEEE operations
+    assert DspVec(np.ones(8, dtype=np.complex64)).result_code_of("interpolate_lin", 2.0, 0.0) == -1
+
+
+# --------------------------------------------------------------------------------------------------
+# elementwise chain (<= 4 ulp)
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_elementwise_ulp(dtype):
+    rng = np.random.default_rng(42)
+    n = 100003
+    x, w = rand_c(rng, n, dtype), rand_c(rng, n, dtype)
+    assert np.array_equal(DspVec(x).scale(2.5).to_numpy(), o.real_scale(x, 2.5, dtype))
+    assert np.array_equal(DspVec(x).scale(complex(1.5, -0.25)).to_numpy(), o.complex_scale(x, complex(1.5, -0.25), dtype))
+    assert np.array_equal(DspVec(x).mul(DspVec(w)).to_numpy(), o.mul(x, w, dtype))
+    assert np.array_equal(DspVec(x).add(DspVec(w)).to_numpy(), o.add(x, w, dtype))
+    assert np.array_equal(DspVec(x).sub(DspVec(w)).to_numpy(), o.sub(x, w, dtype))
+    d = DspVec(x).div(DspVec(w)).to_numpy()
+    dr = o.div(x, w, dtype)
+    assert o.ulp_diff(d.real, dr.real, dtype).max() <= 4 and o.ulp_diff(d.imag, dr.imag, dtype).max() <= 4
+    assert o.ulp_diff(DspVec(x).magnitude().to_numpy(), o.magnitude(x, dtype), dtype).max() <= 4
+    assert np.array_equal(DspVec(x).magnitude_squared().to_numpy(), o.magnitude_squared(x, dtype))
+    assert o.ulp_diff(DspVec(x).phase().to_numpy(), o.phase(x, dtype), dtype).max() <= 4
+    assert np.array_equal(DspVec(x).to_real().to_numpy(), x.real)
+    assert np.array_equal(DspVec(x).to_imag().to_numpy(), x.imag)
+    assert np.array_equal(DspVec(x).conj().to_numpy(), np.conj(x))
+    r = rng.uniform(-10, 10, n).astype(dtype)
+    assert np.array_equal(DspVec(r).mul(DspVec(r[::-1].copy())).to_numpy(), o.mul(r, r[::-1], dtype))
+    assert np.array_equal(DspVec(r).offset(1.25).to_numpy(), (r + dtype(1.25)).astype(dtype))
+    assert np.array_equal(DspVec(r).to_complex().to_numpy(), r.astype(x.dtype))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_fused_chain_equals_sequential_calls(dtype):
+    rng = np.random.default_rng(8)
+    n = 70001
+    x, w = rand_c(rng, n, dtype), rand_c(rng, n, dtype)
+    c = complex(0.75, -1.5)
+    seq = DspVec(x).scale(c).mul(DspVec(w))
+    m1, p1 = DspVec.zeros(0, dtype=dtype), DspVec.zeros(0, dtype=dtype)
+    assert seq.get_mag_phase(m1, p1) == o.CONVERT_VOID_OK
+    m2, p2 = DspVec.zeros(0, dtype=dtype), DspVec.zeros(0, dtype=dtype)
+    v = DspVec(x)
+    v.scale_mul_mag_phase(c, DspVec(w), m2, p2, write_back=True)
+    assert np.array_equal(m1.to_numpy(), m2.to_numpy()) and np.array_equal(p1.to_numpy(), p2.to_numpy())
+    assert np.array_equal(v.to_numpy(), seq.to_numpy())
+    ref = o.mul(o.complex_scale(x, c, dtype), w, dtype)
+    assert o.ulp_diff(m2.to_numpy(), o.magnitude(ref, dtype), dtype).max() <= 4
+    assert o.ulp_diff(p2.to_numpy(), o.phase(ref, dtype), dtype).max() <= 4
+
+
+def test_elementwise_errors_and_getters():
+    a = DspVec(np.ones(8, dtype=np.complex64))
+    assert a.result_code_of("mul", DspVec(np.ones(7, dtype=np.complex64))) == o.ERR_SAME_SIZE
+    assert a.result_code_of("mul", DspVec(np.ones(16, dtype=np.float32))) == o.ERR_META_DATA
+    assert a.result_code_of("add", DspVec(np.ones(8, dtype=np.complex64), domain=bd.FREQ)) == o.ERR_META_DATA
+    r = DspVec(np.ones(8, dtype=np.float32))
+    assert r.result_code_of("complex_scale", 1.0, 1.0) == -1          # assert_complex! marks the vector invalid
+    assert r.len() == 0 and math.isnan(r.delta())
+    src = DspVec(np.array([3 - 4j, -3 + 4j], dtype=np.complex64), delta=0.25)
+    dst = DspVec.zeros(0)
+    assert src.get_magnitude(dst) == o.CONVERT_VOID_OK               # Q8
+    assert np.array_equal(dst.to_numpy(), [5.0, 5.0]) and dst.delta() == 0.25
+    cdst = DspVec.zeros(4, is_complex=True)
+    assert src.get_phase(cdst) == o.CONVERT_VOID_OK and cdst.len() == 0
+
+
+def test_metadata_and_host_access():
+    v = DspVec.zeros(10, init=1.5)
+    assert v.len() == 10 and v.points() == 10 and not v.is_complex() and v.domain() == bd.TIME
+    assert v.get_value(3) == 1.5
+    v.set_value(3, 2.0)
+    assert np.array_equal(v.data_via_host_mirror(), [1.5, 1.5, 1.5, 2.0] + [1.5] * 6)
+    c = DspVec.zeros(7, is_complex=True)          # odd length complex -> valid_len 0 (support_std.rs:369)
+    assert c.len() == 0 and c.alloc_len() >= 7
+    c = DspVec.zeros(8, is_complex=True)
+    c.set_len(5)                                    # odd -> ignored (InputMustHaveAnEvenLength)
+    assert c.len() == 8
+    c.set_len(20)                                   # grows, zero filled
+    assert c.len() == 20 and np.array_equal(c.to_numpy(), np.zeros(10))
+    data = np.arange(5, dtype=np.float32)
+    L = bd.lib()
+    import ctypes
+    res = L.overwrite_data32(v._h, data.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), 5)
+    assert res.result_code == 0 and np.array_equal(v.to_numpy()[:5], data)
+    big = np.arange(10, dtype=np.float32)
+    res = L.overwrite_data32(v._h, big.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), 10)
+    assert res.result_code == o.ERR_INVALID_ARG_LEN  # Q9: strict len < vec.len()
+    w = v.clone()
+    assert np.array_equal(w.to_numpy(), v.to_numpy())
+    assert bd.kernel_launch_count() > 0
+
+
+def test_zero_pad_and_interleave():
+    x = np.arange(1, 6, dtype=np.float32)
+    assert np.array_equal(DspVec(x).zero_pad(8, 0).to_numpy(), [1, 2, 3, 4, 5, 0, 0, 0])
+    assert np.array_equal(DspVec(x).zero_pad(9, 1).to_numpy(), [0, 0, 1, 2, 3, 4, 5, 0, 0])
+    assert np.array_equal(DspVec(x).zero_interleave(3).to_numpy(), [1, 0, 0, 2, 0, 0, 3, 0, 0, 4, 0, 0, 5, 0, 0])
+    c = np.array([1 + 2j, 3 + 4j], dtype=np.complex64)
+    assert np.array_equal(DspVec(c).zero_interleave(2).to_numpy(), [1 + 2j, 0, 3 + 4j, 0])
+    assert DspVec(x).result_code_of("zero_pad", 5, 0) == o.ERR_INVALID_ARG_LEN
