@@ -352,7 +352,7 @@ int convolve_taps(Vec<T>* v, const T* h_dev, size_t L, bool h_complex, T** Hs_ca
         bool own = false;
         if (Hs_cache && *Hs_valid && *Hs_M == M) Hs = *Hs_cache;
         else {
-            BDSP_CUDA_OK(cudaMalloc(&Hs, 2 * M * sizeof(T)));
+            BDSP_CUDA_OK(cudaMalloc(&Hs, ols_spectrum_bytes<T>(M)));
             rc = ols_prepare<T>(h_dev, L, !h_complex, Hs, M, g_stream);
             if (rc) { cudaFree(Hs); return rc; }
             if (Hs_cache) {
@@ -628,7 +628,7 @@ template <typename T> ConvPlan* conv_plan_create(const void* h_dev, size_t L) {
     cudaMemcpyAsync(p->taps, h_dev, L * sizeof(C), cudaMemcpyDeviceToDevice, g_stream);
     if (L > 24 && L <= ols_max_taps<T>()) {
         p->M = ols_block_len<T>(L);
-        if (cudaMalloc(&p->Hs, p->M * sizeof(C)) != cudaSuccess || ols_prepare<T>(p->taps, L, 0, p->Hs, p->M, g_stream) != 0) {
+        if (cudaMalloc(&p->Hs, ols_spectrum_bytes<T>(p->M)) != cudaSuccess || ols_prepare<T>(p->taps, L, 0, p->Hs, p->M, g_stream) != 0) {
             cudaFree(p->taps); if (p->Hs) cudaFree(p->Hs); delete p; return nullptr;
         }
     }

@@ -90,6 +90,14 @@ template <typename T> size_t ols_block_len(size_t L) {
 
 template <typename T> size_t ols_max_taps() { return fft_block_max_n<T>() / 2; }
 
+// the spectrum buffer holds Hs (M complex, natural order) followed by the same spectrum in the
+// layout of the fused 4096-point kernel (planar, position order; f32 only)
+template <typename T> size_t ols_spectrum_bytes(size_t M) { return 2 * M * sizeof(typename CpxOf<T>::type); }
+
+bool ols4096_applicable(size_t N, size_t L, size_t M);
+int ols4096_prepare(const void* Hs, void* Hpos, cudaStream_t st);
+int ols4096_convolve(const void* x, void* y, size_t N, size_t batch, size_t L, const void* Hpos, cudaStream_t st);
+
 template <typename T>
 int ols_prepare(const void* h, size_t L, int h_is_real, void* Hs, size_t M, cudaStream_t st) {
     typedef typename CpxOf<T>::type C;
@@ -97,7 +105,10 @@ int ols_prepare(const void* h, size_t L, int h_is_real, void* Hs, size_t M, cuda
     BDSP_LAUNCHED();
     FftOpts o;
     o.scale = 1.0 / (double)M;
-    return fft_exec<T>(Hs, Hs, M, 1, o, nullptr, 0, st);
+    int rc = fft_exec<T>(Hs, Hs, M, 1, o, nullptr, 0, st);
+    if (rc) return rc;
+    if (sizeof(T) == 4 && M == 4096) rc = ols4096_prepare(Hs, reinterpret_cast<C*>(Hs) + M, st);
+    return rc;
 }
 
 template <typename T>
@@ -105,6 +116,8 @@ int ols_convolve(const void* x, void* y, size_t N, size_t batch, size_t L, const
                  cudaStream_t st) {
     typedef typename CpxOf<T>::type C;
     if (x == y) { set_last_error("ols_convolve: in-place operation is not supported"); return -3; }
+    if (sizeof(T) == 4 && !is_real && ols4096_applicable(N, L, M))
+        return ols4096_convolve(x, y, N, batch, L, reinterpret_cast<const C*>(Hs) + M, st);
     const size_t step = M - L + 1;
     const long long bpv = (long long)((N + step - 1) / step);
     const int log2M = ilog2(M);
@@ -311,6 +324,7 @@ int fft_convolve_full(const void* x, void* y, const void* h, size_t N, size_t ba
 #define BDSP_INST(T)                                                                                                    \
     template size_t ols_block_len<T>(size_t);                                                                           \
     template size_t ols_max_taps<T>();                                                                                  \
+    template size_t ols_spectrum_bytes<T>(size_t);                                                                      \
     template int ols_prepare<T>(const void*, size_t, int, void*, size_t, cudaStream_t);                                  \
     template int ols_convolve<T>(const void*, void*, size_t, size_t, size_t, const void*, size_t, int, cudaStream_t);    \
     template int fir_convolve<T>(const void*, void*, const void*, size_t, size_t, size_t, size_t, int, int, cudaStream_t); \

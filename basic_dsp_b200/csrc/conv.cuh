@@ -8,7 +8,9 @@ namespace bdsp {
 template <typename T> size_t ols_block_len(size_t L);
 // largest L the overlap-save kernel supports
 template <typename T> size_t ols_max_taps();
-// Hs (M complex values) <- FFT_M(pad(h)) / M.  h: L complex (or real) taps on the device.
+// bytes the caller must provide for Hs
+template <typename T> size_t ols_spectrum_bytes(size_t M);
+// Hs (ols_spectrum_bytes(M) bytes) <- FFT_M(pad(h)) / M (+ the permuted copy for the fused kernel).  h: L complex (or real) taps on the device.
 template <typename T> int ols_prepare(const void* h, size_t L, int h_is_real, void* Hs, size_t M, cudaStream_t st);
 // y <- centred circular convolution of every one of `batch` vectors of N points with h (via Hs)
 template <typename T>

@@ -1,0 +1,276 @@
+// Fused 4096-point overlap-save kernel (see ols4096.cuh) + its plan helpers.
+#include <math.h>
+
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "conv.cuh"
+#include "ols4096.cuh"
+
+namespace bdsp {
+
+using namespace ols16;
+
+// 64-bit shared store that the compiler cannot fuse with its neighbour into a 128-bit store
+__device__ __forceinline__ void sts64(float* p, float2 v) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"((unsigned)__cvta_generic_to_shared(p)), "f"(v.x), "f"(v.y) : "memory");
+}
+
+// twiddle table layout (floats): [0,256) Re W4096^c, [256,512) Im W4096^c, [512,528) Re W256^n, [528,544) Im W256^n
+#define OLS_TW_FLOATS 544
+
+template <bool ALIGNED_STORE>
+__global__ void __launch_bounds__(OLS_THREADS, 4)
+ols4096_kernel(const float2* __restrict__ x, float2* __restrict__ y, int N, int m_first, int step, int cl,
+               int blocks_per_vec, const float* __restrict__ Hre, const float* __restrict__ Him,
+               const float* __restrict__ tw) {
+    __shared__ __align__(16) float sre[OLS_PLANE];
+    __shared__ __align__(16) float sim[OLS_PLANE];
+    const int t = threadIdx.x;
+    const int vec = blockIdx.x / blocks_per_vec;
+    const int blk = blockIdx.x - vec * blocks_per_vec;
+    const int i0 = blk * step;
+    const float2* xr = x + (size_t)vec * (size_t)N;
+    float2* yr = y + (size_t)vec * (size_t)N;
+
+    cp v[16];
+    // ------------------------------------------------------------------ F1: stride 256, from global
+    {
+        const int c = 2 * t;
+        // block position m holds x[(p0 + m) mod N], p0 = i0 + cl - 1 - m_first  (p0 > -4096)
+        const int p0 = i0 + cl - 1 - m_first;
+        if (p0 >= 0 && p0 + OLS_M <= N) {   // block-uniform: no wrap-around inside this block
+            const float2* px = xr + p0 + c;
+#pragma unroll
+            for (int n2 = 0; n2 < 16; n2++) {
+                const float2 a = __ldg(px + 256 * n2);
+                const float2 b = __ldg(px + 256 * n2 + 1);
+                v[n2].re = make_float2(a.x, b.x);
+                v[n2].im = make_float2(a.y, b.y);
+            }
+        } else {                             // first / last block of a vector: circular indexing
+            int idx = p0 + c;
+            if (idx < 0) idx += N;
+            if (idx >= N) idx -= N;
+#pragma unroll
+            for (int n2 = 0; n2 < 16; n2++) {
+                int i1 = idx + 1; if (i1 >= N) i1 -= N;
+                const float2 a = __ldg(&xr[idx]);
+                const float2 b = __ldg(&xr[i1]);
+                v[n2].re = make_float2(a.x, b.x);
+                v[n2].im = make_float2(a.y, b.y);
+                idx += 256; if (idx >= N) idx -= N;
+            }
+        }
+        r16<false>(v);
+        cp w1;
+        w1.re = *reinterpret_cast<const float2*>(tw + c);
+        w1.im = *reinterpret_cast<const float2*>(tw + 256 + c);
+        apply_twiddles<true>(v, w1);
+        const int g = t >> 3, j = 2 * (t & 7);
+        const int off = 16 * g + ((j + 4 * rot_of(g)) & 15);
+#pragma unroll
+        for (int s = 0; s < 16; s++) {
+            const int k0 = r16_k(s);
+            *reinterpret_cast<float2*>(&sre[272 * k0 + off]) = v[s].re;
+            *reinterpret_cast<float2*>(&sim[272 * k0 + off]) = v[s].im;
+        }
+    }
+    __syncthreads();
+    // ------------------------------------------------------------------ F2: stride 16
+    const int k0_2 = t >> 3, n0_2 = 2 * (t & 7);
+    int off2[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) off2[r] = 272 * k0_2 + ((n0_2 + 4 * r) & 15);
+    cp w2;  // W256^{n0}, W256^{n0+1}
+    w2.re = *reinterpret_cast<const float2*>(tw + 512 + n0_2);
+    w2.im = *reinterpret_cast<const float2*>(tw + 528 + n0_2);
+    {
+#pragma unroll
+        for (int n1 = 0; n1 < 16; n1++) {
+            const int a = 16 * n1 + off2[(n1 >> 1) & 3];
+            v[n1].re = *reinterpret_cast<const float2*>(&sre[a]);
+            v[n1].im = *reinterpret_cast<const float2*>(&sim[a]);
+        }
+        r16<false>(v);
+        apply_twiddles<true>(v, w2);
+#pragma unroll
+        for (int s = 0; s < 16; s++) {
+            const int k1 = r16_k(s);
+            const int a = 16 * k1 + off2[(k1 >> 1) & 3];
+            *reinterpret_cast<float2*>(&sre[a]) = v[s].re;
+            *reinterpret_cast<float2*>(&sim[a]) = v[s].im;
+        }
+    }
+    __syncthreads();
+    // ------------------------------------------------------------------ F3 | *H | I3 on two groups of 16 contiguous points
+#pragma unroll 1
+    for (int half = 0; half < 2; half++) {
+        const int gg = t + 128 * half;           // group index 0..255
+        const int k0 = gg >> 4, g = gg & 15, r = rot_of(g);
+        const int base = 272 * k0 + 16 * g;
+        cp P[8];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int a = base + 4 * ((q + r) & 3);
+            const float4 fr = *reinterpret_cast<const float4*>(&sre[a]);
+            const float4 fi = *reinterpret_cast<const float4*>(&sim[a]);
+            P[2 * q].re = make_float2(fr.x, fr.y); P[2 * q + 1].re = make_float2(fr.z, fr.w);
+            P[2 * q].im = make_float2(fi.x, fi.y); P[2 * q + 1].im = make_float2(fi.z, fi.w);
+        }
+        fft16_dif_fwd(P);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const float4 hr = __ldg(reinterpret_cast<const float4*>(Hre + 16 * gg + 4 * q));
+            const float4 hi = __ldg(reinterpret_cast<const float4*>(Him + 16 * gg + 4 * q));
+            cp h0, h1;
+            h0.re = make_float2(hr.x, hr.y); h0.im = make_float2(hi.x, hi.y);
+            h1.re = make_float2(hr.z, hr.w); h1.im = make_float2(hi.z, hi.w);
+            P[2 * q] = cmul(P[2 * q], h0);
+            P[2 * q + 1] = cmul(P[2 * q + 1], h1);
+        }
+        fft16_dit_inv(P);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int a = base + 4 * ((q + r) & 3);
+            // 64-bit stores: a 128-bit store would need the four values in one aligned register quad (4 MOVs)
+            sts64(&sre[a], P[2 * q].re);
+            sts64(&sre[a + 2], P[2 * q + 1].re);
+            sts64(&sim[a], P[2 * q].im);
+            sts64(&sim[a + 2], P[2 * q + 1].im);
+        }
+    }
+    __syncthreads();
+    // ------------------------------------------------------------------ I2: stride 16 (DIT: twiddle first)
+    {
+#pragma unroll
+        for (int k1 = 0; k1 < 16; k1++) {
+            const int a = 16 * k1 + off2[(k1 >> 1) & 3];
+            v[k1].re = *reinterpret_cast<const float2*>(&sre[a]);
+            v[k1].im = *reinterpret_cast<const float2*>(&sim[a]);
+        }
+        cp wc = w2; wc.im = pneg(wc.im);
+        apply_twiddles<false>(v, wc);
+        r16<true>(v);
+#pragma unroll
+        for (int s = 0; s < 16; s++) {
+            const int n1 = r16_k(s);
+            const int a = 16 * n1 + off2[(n1 >> 1) & 3];
+            *reinterpret_cast<float2*>(&sre[a]) = v[s].re;
+            *reinterpret_cast<float2*>(&sim[a]) = v[s].im;
+        }
+    }
+    __syncthreads();
+    // ------------------------------------------------------------------ I1: stride 256, valid outputs to global
+    {
+        const int c = 2 * t;
+        const int g = t >> 3, j = 2 * (t & 7);
+        const int off = 16 * g + ((j + 4 * rot_of(g)) & 15);
+#pragma unroll
+        for (int k0 = 0; k0 < 16; k0++) {
+            v[k0].re = *reinterpret_cast<const float2*>(&sre[272 * k0 + off]);
+            v[k0].im = *reinterpret_cast<const float2*>(&sim[272 * k0 + off]);
+        }
+        cp w1;
+        w1.re = *reinterpret_cast<const float2*>(tw + c);
+        w1.im = pneg(*reinterpret_cast<const float2*>(tw + 256 + c));
+        apply_twiddles<false>(v, w1);
+        r16<true>(v);
+        // output i = i0 + m, m = c + 256*n2 - m_first in [0, step) and i < N
+        const int mlo = c - m_first;                       // m for n2 = 0
+        int mhi = step;                                    // exclusive bound on m
+        if (i0 + step > N) mhi = N - i0;                   // last block of the vector
+        float2* py = yr + i0 + mlo;
+#pragma unroll
+        for (int s = 0; s < 16; s++) {
+            const int n2 = r16_k(s);
+            const int m = mlo + 256 * n2;
+            if (ALIGNED_STORE) {
+                if (m >= 0 && m < mhi)
+                    *reinterpret_cast<float4*>(py + 256 * n2) = make_float4(v[s].re.x, v[s].im.x, v[s].re.y, v[s].im.y);
+            } else {
+                if (m >= 0 && m < mhi) py[256 * n2] = make_float2(v[s].re.x, v[s].im.x);
+                if (m + 1 >= 0 && m + 1 < mhi) py[256 * n2 + 1] = make_float2(v[s].re.y, v[s].im.y);
+            }
+        }
+    }
+}
+
+// Hpos (planar, position order) <- Hs (interleaved, natural order, already scaled by 1/M)
+__global__ void ols4096_permute_h_kernel(const float2* __restrict__ Hs, float* __restrict__ Hre, float* __restrict__ Him) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= OLS_M) return;
+    const float2 h = Hs[freq_of_pos(p)];
+    Hre[p] = h.x;
+    Him[p] = h.y;
+}
+
+namespace {
+std::mutex g_tw_mu;
+std::map<int, float*> g_tw;  // per device
+}
+
+static const float* ols4096_twiddles() {
+    int d = 0;
+    BDSP_CUDA_ABORT(cudaGetDevice(&d));
+    std::lock_guard<std::mutex> lk(g_tw_mu);
+    auto it = g_tw.find(d);
+    if (it != g_tw.end()) return it->second;
+    std::vector<float> h(OLS_TW_FLOATS);
+    for (int c = 0; c < 256; c++) {
+        const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)c / 4096.0L;
+        h[c] = (float)cosl(a);
+        h[256 + c] = (float)sinl(a);
+    }
+    for (int n = 0; n < 16; n++) {
+        const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)n / 256.0L;
+        h[512 + n] = (float)cosl(a);
+        h[528 + n] = (float)sinl(a);
+    }
+    float* dev = nullptr;
+    BDSP_CUDA_ABORT(cudaMalloc(&dev, OLS_TW_FLOATS * sizeof(float)));
+    BDSP_CUDA_ABORT(cudaMemcpy(dev, h.data(), OLS_TW_FLOATS * sizeof(float), cudaMemcpyHostToDevice));
+    g_tw[d] = dev;
+    return dev;
+}
+
+bool ols4096_applicable(size_t N, size_t L, size_t M) {
+    // needs one wrap at most per strided load and 32-bit row indices
+    return M == OLS_M && L >= 2 && L <= OLS_M / 2 && N >= OLS_M && N < (1ull << 30);
+}
+
+// Hpos: 2*4096 floats (re plane, im plane) <- Hs from ols_prepare<float>()
+int ols4096_prepare(const void* Hs, void* Hpos, cudaStream_t st) {
+    float* hp = reinterpret_cast<float*>(Hpos);
+    ols4096_permute_h_kernel<<<OLS_M / 256, 256, 0, st>>>(reinterpret_cast<const float2*>(Hs), hp, hp + OLS_M);
+    BDSP_LAUNCHED();
+    return 0;
+}
+
+int ols4096_convolve(const void* x, void* y, size_t N, size_t batch, size_t L, const void* Hpos, cudaStream_t st) {
+    if (x == y) { set_last_error("ols4096_convolve: in-place operation is not supported"); return -3; }
+    const int cl = (int)(L - L / 2);
+    // output window of a block: positions [m_first, m_first + step); m_first >= L-1 and even so that
+    // (c even, i0 even) the two outputs of a thread start at an even index (16-byte stores)
+    int m_first = (int)L - 1;
+    if (m_first & 1) m_first++;
+    int step = OLS_M - m_first;
+    step &= ~1;
+    const long long bpv = ((long long)N + step - 1) / step;
+    const long long grid = bpv * (long long)batch;
+    if (grid > 0x7fffffffll) { set_last_error("ols4096_convolve: grid too large"); return -2; }
+    const float* hp = reinterpret_cast<const float*>(Hpos);
+    const float* tw = ols4096_twiddles();
+    const bool aligned = (N % 2 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+    if (aligned)
+        ols4096_kernel<true><<<(unsigned)grid, OLS_THREADS, 0, st>>>(reinterpret_cast<const float2*>(x), reinterpret_cast<float2*>(y), (int)N,
+                                                                     m_first, step, cl, (int)bpv, hp, hp + OLS_M, tw);
+    else
+        ols4096_kernel<false><<<(unsigned)grid, OLS_THREADS, 0, st>>>(reinterpret_cast<const float2*>(x), reinterpret_cast<float2*>(y), (int)N,
+                                                                      m_first, step, cl, (int)bpv, hp, hp + OLS_M, tw);
+    BDSP_LAUNCHED();
+    return 0;
+}
+
+}  // namespace bdsp

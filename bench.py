@@ -1,0 +1,318 @@
+#!/usr/bin/env python3
+"""Benchmark of the hot path named by BASELINE.json: c32 FFT fast convolution, 2^20-point vectors,
+batched, on 1/2/4/8 B200 (weak scaling: every GPU convolves its own rows, no collective).
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference's CPU algorithm (C port), host cores
+
+One step = one pass of `convolve_signal` (1023-tap raised cosine)
+over ROWS = 64 independent 2^20-point complex f32 vectors per GPU (512 MiB in, 512 MiB out: larger than
+the 126 MB L2, so no L2 flush is needed between iterations).  Rank 0 prints ONE JSON line.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_POINTS = 1 << 20
+TAPS = 1023
+ROWS = 64
+METRIC = "Msamples/s c32 FFT fast-conv 2^20 batched"
+WORKLOAD = "C2a-B: convolve_signal, %d x 2^20-point c32 vectors per GPU, %d-tap RaisedCosine(0.35) h[k]=RC((k-511)*0.25)" % (ROWS, TAPS)
+
+
+def make_taps():
+    """h[k] = RC_0.35((k - 511) * 0.25) evaluated in f32 like the reference (conv_types.rs:406-423)."""
+    k = np.arange(TAPS, dtype=np.float32)
+    x = ((k - np.float32(511)) * np.float32(0.25)).astype(np.float32)
+    pi = np.float32(np.pi)
+    beta = np.float32(0.35)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        pi_x = pi * x
+        arg = np.float32(2) * beta * x
+        v = np.sin(pi_x) * np.cos(pi_x * beta) / pi_x / (np.float32(1) - arg * arg)
+    v = v.astype(np.float32)
+    v[x == 0] = 1.0
+    return v.astype(np.complex64)
+
+
+def make_rows(rows, seed):
+    rng = np.random.default_rng(seed)
+    out = np.empty((rows, N_POINTS), dtype=np.complex64)
+    for r in range(rows):  # re, im i.i.d. uniform [-10, 10) (tests/tools/mod.rs:124-131)
+        out[r].real = rng.uniform(-10, 10, N_POINTS).astype(np.float32)
+        out[r].imag = rng.uniform(-10, 10, N_POINTS).astype(np.float32)
+    return out
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_port_rate(rows, threads, steps=1, warmup=0):
+    """Msamples/s of the C port of the reference's CPU path on `rows` vectors with `threads` threads."""
+    from oracle import ref_port
+    x0 = make_rows(rows, 20260102)
+    h = make_taps()
+    times = []
+    for it in range(warmup + steps):
+        x = x0.copy()
+        t0 = time.perf_counter()
+        rc = ref_port.convolve_signal_rows_inplace(x, h, threads)
+        dt = time.perf_counter() - t0
+        if rc:
+            raise RuntimeError("reference port failed: %d" % rc)
+        if it >= warmup:
+            times.append(dt)
+    total = sum(times)
+    return rows * N_POINTS * len(times) / total / 1e6, total / len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    rows = cores  # bounded sample: one 2^20-point vector per host thread per step (~1 s of CPU each)
+    warm = min(args.warmup, 1)
+    steps = max(1, min(args.steps, 5))
+    rate, sec = cpu_port_rate(rows, cores, steps=steps, warmup=warm)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": "%d rows of 2^20 points per step on %d host threads" % (rows, cores)},
+        "cpu_baseline": {"value": rate, "unit": "Msamples/s", "cores": cores, "kind": "port",
+                         "sample": "%d x 2^20-point vectors per step, %d steps, C port of overlap_discard incl. its scalar head/tail "
+                                   "loops (oracle/ref_port.c), one OpenMP thread per vector" % (rows, steps)},
+        "e2e": {"value": rate, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import basic_dsp_b200 as bd
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    L = bd.lib()
+    if L.bdsp_set_device(local) != 0:
+        raise SystemExit("bdsp_set_device failed: %s" % L.bdsp_last_error())
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        L.bdsp_sync()
+
+    # ---- inputs: this rank's shard (rows [rank*ROWS, (rank+1)*ROWS) of the global batch) ------------
+    nbytes = ROWS * N_POINTS * 8
+    h = make_taps()
+    host_in = L.bdsp_malloc_host(nbytes)
+    host_out = L.bdsp_malloc_host(nbytes)
+    if not host_in or not host_out:
+        raise SystemExit("pinned host allocation failed")
+    hin = np.ctypeslib.as_array((ctypes.c_float * (2 * ROWS * N_POINTS)).from_address(host_in))
+    hin[:] = make_rows(ROWS, 20260102 + rank).view(np.float32).ravel()
+    d_in, d_out, d_h = L.bdsp_malloc(nbytes), L.bdsp_malloc(nbytes), L.bdsp_malloc(TAPS * 8)
+    if not d_in or not d_out or not d_h:
+        raise SystemExit("device allocation failed: %s" % L.bdsp_last_error())
+    L.bdsp_memcpy_h2d(d_in, host_in, nbytes)
+    L.bdsp_memcpy_h2d(d_h, h.ctypes.data, TAPS * 8)
+    L.bdsp_sync()
+    plan = L.bdsp_conv_plan_create_c32(d_h, TAPS)
+    if not plan:
+        raise SystemExit("conv plan failed: %s" % L.bdsp_last_error())
+
+    def step():
+        rc = L.bdsp_convolve_signal_rows_c32(d_in, d_out, N_POINTS, ROWS, plan)
+        if rc:
+            raise SystemExit("bdsp_convolve_signal_rows_c32 -> %d (%s)" % (rc, L.bdsp_last_error()))
+
+    # ---- device-resident throughput ---------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = bd.kernel_launch_count()
+    evs = [L.bdsp_event_create() for _ in range(args.steps + 1)]
+    barrier()
+    L.bdsp_event_record(evs[0])
+    for i in range(args.steps):
+        step()
+        L.bdsp_event_record(evs[i + 1])
+    barrier()
+    total_ms = L.bdsp_event_elapsed_ms(evs[0], evs[args.steps])
+    per_launch_ms = [L.bdsp_event_elapsed_ms(evs[i], evs[i + 1]) for i in range(args.steps)]
+    launches = bd.kernel_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    samples = world * ROWS * N_POINTS * args.steps
+    value = samples / (total_ms_max * 1e-3) / 1e6
+
+    # ---- end to end through the C ABI with HOST buffers: upload -> convolve_signal32 -> download, every step --------
+    hv = bd.DspVec(h)
+    vec = bd.DspVec.zeros(2 * N_POINTS, is_complex=True, dtype=np.float32)
+    fptr = ctypes.POINTER(ctypes.c_float)
+    row_floats = 2 * N_POINTS
+
+    def e2e_step():
+        for r in range(ROWS):
+            src = ctypes.cast(host_in + r * row_floats * 4, fptr)
+            dst = ctypes.cast(host_out + r * row_floats * 4, fptr)
+            if L.bdsp_upload32(vec._h, src, row_floats):
+                raise SystemExit("upload failed")
+            vec.convolve_signal(hv)
+            if L.bdsp_download32(vec._h, dst, row_floats):
+                raise SystemExit("download failed")
+
+    e2e_steps = max(1, min(args.steps, 10))
+    for _ in range(min(args.warmup, 2)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * ROWS * N_POINTS * e2e_steps / float(t.item()) / 1e6
+    # the e2e result of the last row must equal the device-resident result (same kernel, same input)
+    hout = np.ctypeslib.as_array((ctypes.c_float * (2 * ROWS * N_POINTS)).from_address(host_out))
+    chk = np.empty(row_floats, dtype=np.float32)
+    L.bdsp_memcpy_d2h(chk.ctypes.data, d_out + (ROWS - 1) * row_floats * 4, row_floats * 4)
+    L.bdsp_sync()
+    if not np.array_equal(chk, hout[(ROWS - 1) * row_floats:]):
+        raise SystemExit("e2e result differs from the device-resident result")
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        alg_bytes = 16.0 * N_POINTS * ROWS          # 16 B per sample (8 read + 8 write)
+        avg_ms = statistics.mean(per_launch_ms)
+        achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
+        flops = ROWS * N_POINTS * (2 * 5 * 20 + 6)   # 5 N log2 N convention, forward + inverse + multiply
+        line = {
+            "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "rows_per_gpu": ROWS, "points": N_POINTS, "taps": TAPS,
+                       "l2": "inputs larger than L2 (512 MiB in + 512 MiB out per step), no flush",
+                       "sharding": "rows, no collective"},
+            "gflops_5nlog2n": flops * world / (total_ms_max / args.steps * 1e-3) / 1e9,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "ols_conv_kernel<float,false>", "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_ms,
+                         "min_launch_ms": min(per_launch_ms)},
+            "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+                    "steps": e2e_steps, "path": "bdsp_upload32 -> convolve_signal32 -> bdsp_download32 per row, pinned host buffers"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            rate, sec = cpu_port_rate(cores, cores, steps=1, warmup=0)
+            line["cpu_baseline"] = {"value": rate, "unit": "Msamples/s", "cores": cores, "kind": "port",
+                                    "sample": "%d x 2^20-point vectors (one per host thread), %.1f s; C port of the reference's "
+                                              "overlap_discard incl. scalar head/tail (oracle/ref_port.c)" % (cores, sec)}
+        print(json.dumps(line))
+    barrier()
+    L.bdsp_conv_plan_destroy(plan)
+    for p in (d_in, d_out, d_h):
+        L.bdsp_free(p)
+    L.bdsp_free_host(host_in)
+    L.bdsp_free_host(host_out)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

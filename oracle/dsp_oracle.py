@@ -527,13 +527,19 @@ def sub(x, w, dtype):
 
 
 def div(x, w, dtype):
-    """ElementaryOps::div; complex division evaluated in float64 then rounded (<= 1 ulp of the
-    reference's num-complex Div, inside the 4-ulp budget)."""
+    """ElementaryOps::div.  Complex: num-complex `Div` = (a*conj(b)) / |b|^2 component-wise, every
+    operation rounded to T (elementary.rs:574-588 -> div_complex -> Complex::div)."""
     x = np.asarray(x)
+    w = np.asarray(w)
     if np.iscomplexobj(x):
         ct = np.complex64 if dtype == np.float32 else np.complex128
-        return (x.astype(np.complex128) / np.asarray(w).astype(np.complex128)).astype(ct)
-    return (x.astype(dtype) / np.asarray(w).astype(dtype)).astype(dtype)
+        a, b = x.astype(ct), w.astype(ct)
+        ar, ai, br, bi = (np.asarray(v, dtype=dtype) for v in (a.real, a.imag, b.real, b.imag))
+        ns = ((br * br).astype(dtype) + (bi * bi).astype(dtype)).astype(dtype)
+        re = ((ar * br).astype(dtype) + (ai * bi).astype(dtype)).astype(dtype)
+        im = ((ai * br).astype(dtype) - (ar * bi).astype(dtype)).astype(dtype)
+        return ((re / ns).astype(dtype) + 1j * (im / ns).astype(dtype)).astype(ct)
+    return (x.astype(dtype) / w.astype(dtype)).astype(dtype)
 
 
 def magnitude(x, dtype):
