@@ -19,7 +19,7 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int32, c_s
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbasic_dsp_b200.so")
+LIB_PATH = os.environ.get("BASIC_DSP_B200_LIB", os.path.join(_HERE, "libbasic_dsp_b200.so"))
 
 F_INVERSE, F_SHIFT, F_MAGNITUDE, F_REAL_INPUT = 1, 2, 4, 8
 TIME, FREQ = 0, 1
@@ -116,6 +116,7 @@ def _declare(lib):
         ext = {
             "bdsp_upload": (c_int32, [H, POINTER(T), c_size_t]),
             "bdsp_download": (c_int32, [H, POINTER(T), c_size_t]),
+            "bdsp_download_async": (c_int32, [H, POINTER(T), c_size_t]),
             "bdsp_device_ptr": (c_void_p, [H]),
             "bdsp_scale_mul_mag_phase": (c_int32, [H, T, T, H, H, H, c_int32]),
             "bdsp_fft_magnitude": (_VecResult, [H]),
@@ -131,6 +132,9 @@ def _declare(lib):
     lib.bdsp_set_device.restype, lib.bdsp_set_device.argtypes = c_int32, [c_int32]
     lib.bdsp_sync.restype, lib.bdsp_sync.argtypes = c_int32, []
     lib.bdsp_set_stream.restype, lib.bdsp_set_stream.argtypes = None, [c_void_p]
+    lib.bdsp_stream_create.restype, lib.bdsp_stream_create.argtypes = c_void_p, []
+    lib.bdsp_stream_destroy.restype, lib.bdsp_stream_destroy.argtypes = None, [c_void_p]
+    lib.bdsp_stream_sync.restype, lib.bdsp_stream_sync.argtypes = c_int32, [c_void_p]
     for s in ("32", "64"):
         f = getattr(lib, "bdsp_fft_rows_c" + s)
         f.restype, f.argtypes = c_int32, [c_void_p, c_void_p, c_size_t, c_size_t, c_int32]

@@ -328,11 +328,45 @@ template <typename T> struct RealFn {
     }
 };
 
+// Small host-built tables (tap tables, custom frequency responses) go through a per-thread grow-only
+// pinned staging buffer + device buffer, so that a call does no cudaMalloc/cudaFree and never blocks on
+// the GPU: the copy is queued on the caller's stream, the consumer kernel follows on the same stream.
+struct TableStage {
+    void* dev = nullptr;
+    void* host = nullptr;
+    size_t bytes = 0;
+    cudaEvent_t copied = nullptr;   // staging buffer has been read by the last copy
+    cudaEvent_t used = nullptr;     // device buffer has been consumed by the last kernel
+};
+thread_local TableStage g_stage;
+
 template <typename T> int upload_table(const std::vector<T>& h, T** dev) {
-    BDSP_CUDA_OK(cudaMalloc(dev, (h.size() ? h.size() : 1) * sizeof(T)));
-    BDSP_CUDA_OK(cudaMemcpyAsync(*dev, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, g_stream));
-    BDSP_CUDA_OK(cudaStreamSynchronize(g_stream));  // h is pageable and dies with the caller's frame
+    TableStage& s = g_stage;
+    const size_t need = (h.size() ? h.size() : 1) * sizeof(T);
+    if (!s.copied) {
+        BDSP_CUDA_OK(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
+        BDSP_CUDA_OK(cudaEventCreateWithFlags(&s.used, cudaEventDisableTiming));
+    }
+    if (need > s.bytes) {
+        BDSP_CUDA_OK(cudaDeviceSynchronize());
+        if (s.dev) cudaFree(s.dev);
+        if (s.host) cudaFreeHost(s.host);
+        s.bytes = need * 2 < 65536 ? 65536 : need * 2;
+        BDSP_CUDA_OK(cudaMalloc(&s.dev, s.bytes));
+        BDSP_CUDA_OK(cudaMallocHost(&s.host, s.bytes));
+    } else {
+        BDSP_CUDA_OK(cudaEventSynchronize(s.copied));            // host staging free again (old, tiny copy)
+        BDSP_CUDA_OK(cudaStreamWaitEvent(g_stream, s.used, 0));  // device table free again (GPU-side wait)
+    }
+    memcpy(s.host, h.data(), h.size() * sizeof(T));
+    BDSP_CUDA_OK(cudaMemcpyAsync(s.dev, s.host, h.size() * sizeof(T), cudaMemcpyHostToDevice, g_stream));
+    BDSP_CUDA_OK(cudaEventRecord(s.copied, g_stream));
+    *dev = reinterpret_cast<T*>(s.dev);
     return 0;
+}
+// call after the kernel that reads the table has been launched
+inline void table_consumed() {
+    if (g_stage.used) cudaEventRecord(g_stage.used, g_stream);
 }
 
 // ---- convolution -----------------------------------------------------------------------------------
@@ -426,8 +460,7 @@ template <typename T> Res<T> op_convolve_fn(Vec<T>* v, const RealFn<T>& f, T rat
     int rc = upload_table(taps, &h_dev);
     if (rc) return done(v, rc);
     rc = convolve_taps<T>(v, h_dev, taps.size(), false, nullptr, nullptr, nullptr);
-    cudaStreamSynchronize(g_stream);
-    cudaFree(h_dev);
+    table_consumed();
     return done(v, rc);
 }
 
@@ -453,8 +486,7 @@ Res<T> op_convolve_cfn(Vec<T>* v, CT (*fn)(const void*, T), const void* data, T 
     int rc = upload_table(t, &h_dev);
     if (rc) return done(v, rc);
     rc = convolve_taps<T>(v, h_dev, 2 * L + 1, true, nullptr, nullptr, nullptr);
-    cudaStreamSynchronize(g_stream);
-    cudaFree(h_dev);
+    table_consumed();
     return done(v, rc);
 }
 
@@ -475,8 +507,7 @@ template <typename T> Res<T> op_mul_freq_resp(Vec<T>* v, const RealFn<T>& f, T r
         T* dev = nullptr;
         rc = upload_table(tab, &dev);
         if (!rc) rc = ew_mul_table<T>(v->d, dev, points, v->is_complex, 0, g_stream);
-        cudaStreamSynchronize(g_stream);
-        if (dev) cudaFree(dev);
+        table_consumed();
     }
     return done(v, rc);
 }
@@ -498,8 +529,7 @@ Res<T> op_mul_freq_resp_c(Vec<T>* v, CT (*fn)(const void*, T), const void* data,
     T* dev = nullptr;
     int rc = upload_table(tab, &dev);
     if (!rc) rc = ew_mul_table<T>(v->d, dev, points, 1, 1, g_stream);
-    cudaStreamSynchronize(g_stream);
-    if (dev) cudaFree(dev);
+    table_consumed();
     return done(v, rc);
 }
 
@@ -542,8 +572,7 @@ template <typename T> Res<T> op_interpolatef(Vec<T>* v, const RealFn<T>& f, T fa
         T* dev = nullptr;
         rc = upload_table(tab, &dev);
         if (!rc) rc = interp_poly<T>(v->d, v->scratch, dev, N, new_points, F, L, v->is_complex, g_stream);
-        cudaStreamSynchronize(g_stream);
-        if (dev) cudaFree(dev);
+        table_consumed();
     } else {
         if (f.kind == 2) return done(v, E_ARG_LEN);   // custom callback + per-output taps: not supported on the device
         rc = interp_frac<T>(v->d, v->scratch, N, new_points, (double)factor, (double)delay, (int)conv_len, f.kind,
@@ -589,10 +618,10 @@ template <typename T> int upload(Vec<T>* v, const T* host, size_t len) {
     v->version++;
     return 0;
 }
-template <typename T> int download(const Vec<T>* v, T* host, size_t len) {
+template <typename T> int download(const Vec<T>* v, T* host, size_t len, bool wait) {
     if (len > v->len) return E_ARG_LEN;
     if (len) BDSP_CUDA_OK(cudaMemcpyAsync(host, v->d, len * sizeof(T), cudaMemcpyDeviceToHost, g_stream));
-    BDSP_CUDA_OK(cudaStreamSynchronize(g_stream));
+    if (wait) BDSP_CUDA_OK(cudaStreamSynchronize(g_stream));
     return 0;
 }
 
@@ -803,7 +832,8 @@ template <typename R, typename T> static inline R as_res(Res<T> r) {
     }                                                                                                                  \
     extern "C" RES interpolate_lin##S(HV* v, T factor, T delay) { return as_res<RES>(op_interpolate_lin(VEC(v), factor, delay)); } \
     extern "C" int32_t bdsp_upload##S(HV* v, const T* host, size_t len) { return upload(VEC(v), host, len); }          \
-    extern "C" int32_t bdsp_download##S(const HV* v, T* host, size_t len) { return download(CVEC(v), host, len); }     \
+    extern "C" int32_t bdsp_download##S(const HV* v, T* host, size_t len) { return download(CVEC(v), host, len, true); } \
+    extern "C" int32_t bdsp_download_async##S(const HV* v, T* host, size_t len) { return download(CVEC(v), host, len, false); } \
     extern "C" void* bdsp_device_ptr##S(HV* v) { return VEC(v)->d; }                                                   \
     extern "C" int32_t bdsp_scale_mul_mag_phase##S(HV* v, T cre, T cim, const HV* w, HV* m, HV* p, int32_t wb) {       \
         return scale_mul_mag_phase<T>(VEC(v), cre, cim, CVEC(w), VEC(m), VEC(p), wb);                                  \
@@ -822,6 +852,13 @@ extern "C" int32_t bdsp_device_count(void) {
 extern "C" int32_t bdsp_set_device(int32_t device) { BDSP_CUDA_OK(cudaSetDevice(device)); return 0; }
 extern "C" int32_t bdsp_sync(void) { BDSP_CUDA_OK(cudaStreamSynchronize(g_stream)); return 0; }
 extern "C" void bdsp_set_stream(void* s) { g_stream = reinterpret_cast<cudaStream_t>(s); }
+extern "C" void* bdsp_stream_create(void) {
+    cudaStream_t s = nullptr;
+    if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    return s;
+}
+extern "C" void bdsp_stream_destroy(void* s) { if (s) cudaStreamDestroy(reinterpret_cast<cudaStream_t>(s)); }
+extern "C" int32_t bdsp_stream_sync(void* s) { BDSP_CUDA_OK(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(s))); return 0; }
 
 extern "C" int32_t bdsp_fft_rows_c32(const void* in, void* out, size_t points, size_t rows, int32_t flags) { return fft_rows<float>(in, out, points, rows, flags); }
 extern "C" int32_t bdsp_fft_rows_c64(const void* in, void* out, size_t points, size_t rows, int32_t flags) { return fft_rows<double>(in, out, points, rows, flags); }

@@ -95,7 +95,7 @@ template <typename T> size_t ols_max_taps() { return fft_block_max_n<T>() / 2; }
 template <typename T> size_t ols_spectrum_bytes(size_t M) { return 2 * M * sizeof(typename CpxOf<T>::type); }
 
 bool ols4096_applicable(size_t N, size_t L, size_t M);
-int ols4096_prepare(const void* Hs, void* Hpos, cudaStream_t st);
+int ols4096_prepare(const void* Hs, void* Hpos, size_t L, cudaStream_t st);
 int ols4096_convolve(const void* x, void* y, size_t N, size_t batch, size_t L, const void* Hpos, cudaStream_t st);
 
 template <typename T>
@@ -107,7 +107,7 @@ int ols_prepare(const void* h, size_t L, int h_is_real, void* Hs, size_t M, cuda
     o.scale = 1.0 / (double)M;
     int rc = fft_exec<T>(Hs, Hs, M, 1, o, nullptr, 0, st);
     if (rc) return rc;
-    if (sizeof(T) == 4 && M == 4096) rc = ols4096_prepare(Hs, reinterpret_cast<C*>(Hs) + M, st);
+    if (sizeof(T) == 4 && M == 4096) rc = ols4096_prepare(Hs, reinterpret_cast<C*>(Hs) + M, L, st);
     return rc;
 }
 

@@ -184,20 +184,30 @@ int interp_frac(const void* x, void* y, size_t N, size_t new_points, double fact
 // ------------------------------------------------------------------------------------------
 // interpolate_lin (real_interpolation.rs:33-71): every operation individually rounded in T.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float lin_eval(float i, float F, float d, const float* __restrict__ x) {
+__device__ __forceinline__ float lin_eval(float i, float F, float d, const float* __restrict__ x, long long n) {
     float p = __fadd_rn(__fdiv_rn(i, F), d);
     float bf = floorf(p);
     long long b = (long long)bf;
+    if (b < 0) b = 0;                // the reference panics on an out-of-range index; clamp instead
+    if (b > n - 2) b = n - 2;
     float y0 = x[b], y1 = x[b + 1];
     return __fadd_rn(y0, __fmul_rn(__fsub_rn(y1, y0), __fsub_rn(p, bf)));
 }
-__device__ __forceinline__ double lin_eval(double i, double F, double d, const double* __restrict__ x) {
+__device__ __forceinline__ double lin_eval(double i, double F, double d, const double* __restrict__ x, long long n) {
     double p = __dadd_rn(__ddiv_rn(i, F), d);
     double bf = floor(p);
     long long b = (long long)bf;
+    if (b < 0) b = 0;
+    if (b > n - 2) b = n - 2;
     double y0 = x[b], y1 = x[b + 1];
     return __dadd_rn(y0, __dmul_rn(__dsub_rn(y1, y0), __dsub_rn(p, bf)));
 }
+
+// The reference counts the output index in precision T by repeated `+ 1.0` (real_interpolation.rs:53,65);
+// in f32 that counter stops advancing at 2^24 (Q7).  The same saturation is applied here so that the
+// result is bit-identical to the reference for every length (and the read index stays in bounds).
+__device__ __forceinline__ float counter_value(long long i, float) { return i >= 16777216ll ? 16777216.0f : (float)i; }
+__device__ __forceinline__ double counter_value(long long i, double) { return i >= 9007199254740992ll ? 9007199254740992.0 : (double)i; }
 
 template <typename T>
 __global__ void interp_lin_kernel(const T* __restrict__ x, T* __restrict__ y, long long n, long long dest_len, T F, T d) {
@@ -205,7 +215,7 @@ __global__ void interp_lin_kernel(const T* __restrict__ x, T* __restrict__ y, lo
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (; i < dest_len; i += stride) {
         if (i == dest_len - 1) y[i] = x[n - 1];
-        else y[i] = lin_eval((T)i, F, d, x);
+        else y[i] = lin_eval(counter_value(i, (T)0), F, d, x, n);
     }
 }
 

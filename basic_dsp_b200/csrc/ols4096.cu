@@ -17,12 +17,41 @@ __device__ __forceinline__ void sts64(float* p, float2 v) {
     asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"((unsigned)__cvta_generic_to_shared(p)), "f"(v.x), "f"(v.y) : "memory");
 }
 
-// twiddle table layout (floats): [0,256) Re W4096^c, [256,512) Im W4096^c, [512,528) Re W256^n, [528,544) Im W256^n
-#define OLS_TW_FLOATS 544
+// twiddle table layout (floats):
+//   [0,256) Re W4096^c, [256,512) Im W4096^c                       (base roots of the stride-256 stages)
+//   [512 + (8*k + n/2)*4 + {0,1,2,3}] = {Re W256^{k*n}, Re W256^{k*(n+1)}, Im W256^{k*n}, Im W256^{k*(n+1)}}, n even
+//                                                                k, n in [0,16)  (stride-16 stages, one 128-bit load each)
+//   [1024 + 256*k + c] Re W4096^{k*c}, [1024 + 4096 + 256*k + c] Im W4096^{k*c}  k in [0,16), c in [0,256)
+#define OLS_TW_FLOATS (1024 + 8192)
+#define OLS_TW2_RE 512
+#define OLS_TW2_IM 768
+#define OLS_TW1_RE 1024
+#define OLS_TW1_IM (1024 + 4096)
+#ifndef OLS_UNROLL_F3
+#define OLS_UNROLL_F3 0
+#endif
+#ifndef OLS_MIN_CTAS
+#define OLS_MIN_CTAS 4
+#endif
+#ifndef OLS_TABLE_TW1
+#define OLS_TABLE_TW1 0  // measured on B200: the table variant (L1-bound) is 10% slower than computing the powers
+#endif
 
-template <bool ALIGNED_STORE>
-__global__ void __launch_bounds__(OLS_THREADS, 4)
-ols4096_kernel(const float2* __restrict__ x, float2* __restrict__ y, int N, int m_first, int step, int cl,
+// apply conj(w): a * conj(w)
+__device__ __forceinline__ cp cmul_conj(cp a, cp w) {
+    cp r;
+    r.re = pfma(a.re, w.re, pmul(a.im, w.im));
+    r.im = pfma(a.im, w.re, pneg(pmul(a.re, w.im)));
+    return r;
+}
+
+// ALIGNED: rows start on 16-byte boundaries (N even, 16-byte aligned base pointers); together with the
+// even block offsets chosen by the plan every thread then moves its two adjacent points with one
+// 128-bit access.  `shift` = cl - 1 + d is the (even) distance between a block position's input index
+// and its output index.
+template <bool ALIGNED>
+__global__ void __launch_bounds__(OLS_THREADS, OLS_MIN_CTAS)
+ols4096_kernel(const float2* __restrict__ x, float2* __restrict__ y, int N, int m_first, int step, int shift,
                int blocks_per_vec, const float* __restrict__ Hre, const float* __restrict__ Him,
                const float* __restrict__ tw) {
     __shared__ __align__(16) float sre[OLS_PLANE];
@@ -38,16 +67,22 @@ ols4096_kernel(const float2* __restrict__ x, float2* __restrict__ y, int N, int 
     // ------------------------------------------------------------------ F1: stride 256, from global
     {
         const int c = 2 * t;
-        // block position m holds x[(p0 + m) mod N], p0 = i0 + cl - 1 - m_first  (p0 > -4096)
-        const int p0 = i0 + cl - 1 - m_first;
+        // block position m holds x[(p0 + m) mod N], p0 = i0 + shift - m_first  (p0 > -4096, even)
+        const int p0 = i0 + shift - m_first;
         if (p0 >= 0 && p0 + OLS_M <= N) {   // block-uniform: no wrap-around inside this block
             const float2* px = xr + p0 + c;
 #pragma unroll
             for (int n2 = 0; n2 < 16; n2++) {
-                const float2 a = __ldg(px + 256 * n2);
-                const float2 b = __ldg(px + 256 * n2 + 1);
-                v[n2].re = make_float2(a.x, b.x);
-                v[n2].im = make_float2(a.y, b.y);
+                if (ALIGNED) {
+                    const float4 ab = __ldg(reinterpret_cast<const float4*>(px + 256 * n2));
+                    v[n2].re = make_float2(ab.x, ab.z);
+                    v[n2].im = make_float2(ab.y, ab.w);
+                } else {
+                    const float2 a = __ldg(px + 256 * n2);
+                    const float2 b = __ldg(px + 256 * n2 + 1);
+                    v[n2].re = make_float2(a.x, b.x);
+                    v[n2].im = make_float2(a.y, b.y);
+                }
             }
         } else {                             // first / last block of a vector: circular indexing
             int idx = p0 + c;
@@ -64,10 +99,21 @@ ols4096_kernel(const float2* __restrict__ x, float2* __restrict__ y, int N, int 
             }
         }
         r16<false>(v);
+#if OLS_TABLE_TW1
+#pragma unroll
+        for (int s = 1; s < 16; s++) {
+            const int k0 = r16_k(s);
+            cp w;
+            w.re = __ldg(reinterpret_cast<const float2*>(tw + OLS_TW1_RE + 256 * k0 + c));
+            w.im = __ldg(reinterpret_cast<const float2*>(tw + OLS_TW1_IM + 256 * k0 + c));
+            v[s] = cmul(v[s], w);
+        }
+#else
         cp w1;
         w1.re = *reinterpret_cast<const float2*>(tw + c);
         w1.im = *reinterpret_cast<const float2*>(tw + 256 + c);
         apply_twiddles<true>(v, w1);
+#endif
         const int g = t >> 3, j = 2 * (t & 7);
         const int off = 16 * g + ((j + 4 * rot_of(g)) & 15);
 #pragma unroll
@@ -83,9 +129,7 @@ ols4096_kernel(const float2* __restrict__ x, float2* __restrict__ y, int N, int 
     int off2[4];
 #pragma unroll
     for (int r = 0; r < 4; r++) off2[r] = 272 * k0_2 + ((n0_2 + 4 * r) & 15);
-    cp w2;  // W256^{n0}, W256^{n0+1}
-    w2.re = *reinterpret_cast<const float2*>(tw + 512 + n0_2);
-    w2.im = *reinterpret_cast<const float2*>(tw + 528 + n0_2);
+    const float4* tw2 = reinterpret_cast<const float4*>(tw + OLS_TW2_RE) + (n0_2 >> 1);   // tw2[8*k]: roots for (k, n0), (k, n0+1)
     {
 #pragma unroll
         for (int n1 = 0; n1 < 16; n1++) {
@@ -94,7 +138,15 @@ ols4096_kernel(const float2* __restrict__ x, float2* __restrict__ y, int N, int 
             v[n1].im = *reinterpret_cast<const float2*>(&sim[a]);
         }
         r16<false>(v);
-        apply_twiddles<true>(v, w2);
+#pragma unroll
+        for (int s = 1; s < 16; s++) {
+            const int k1 = r16_k(s);
+            const float4 f = __ldg(tw2 + 8 * k1);
+            cp w;
+            w.re = make_float2(f.x, f.y);
+            w.im = make_float2(f.z, f.w);
+            v[s] = cmul(v[s], w);
+        }
 #pragma unroll
         for (int s = 0; s < 16; s++) {
             const int k1 = r16_k(s);
@@ -105,7 +157,11 @@ ols4096_kernel(const float2* __restrict__ x, float2* __restrict__ y, int N, int 
     }
     __syncthreads();
     // ------------------------------------------------------------------ F3 | *H | I3 on two groups of 16 contiguous points
+#if OLS_UNROLL_F3
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
     for (int half = 0; half < 2; half++) {
         const int gg = t + 128 * half;           // group index 0..255
         const int k0 = gg >> 4, g = gg & 15, r = rot_of(g);
@@ -122,8 +178,9 @@ ols4096_kernel(const float2* __restrict__ x, float2* __restrict__ y, int N, int 
         fft16_dif_fwd(P);
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-            const float4 hr = __ldg(reinterpret_cast<const float4*>(Hre + 16 * gg + 4 * q));
-            const float4 hi = __ldg(reinterpret_cast<const float4*>(Him + 16 * gg + 4 * q));
+            // plan layout: [half][q][thread][4] -> a warp reads 512 contiguous bytes per request
+            const float4 hr = __ldg(reinterpret_cast<const float4*>(Hre + ((half * 4 + q) * OLS_THREADS + t) * 4));
+            const float4 hi = __ldg(reinterpret_cast<const float4*>(Him + ((half * 4 + q) * OLS_THREADS + t) * 4));
             cp h0, h1;
             h0.re = make_float2(hr.x, hr.y); h0.im = make_float2(hi.x, hi.y);
             h1.re = make_float2(hr.z, hr.w); h1.im = make_float2(hi.z, hi.w);
@@ -150,8 +207,14 @@ ols4096_kernel(const float2* __restrict__ x, float2* __restrict__ y, int N, int 
             v[k1].re = *reinterpret_cast<const float2*>(&sre[a]);
             v[k1].im = *reinterpret_cast<const float2*>(&sim[a]);
         }
-        cp wc = w2; wc.im = pneg(wc.im);
-        apply_twiddles<false>(v, wc);
+#pragma unroll
+        for (int k1 = 1; k1 < 16; k1++) {
+            const float4 f = __ldg(tw2 + 8 * k1);
+            cp w;
+            w.re = make_float2(f.x, f.y);
+            w.im = make_float2(f.z, f.w);
+            v[k1] = cmul_conj(v[k1], w);
+        }
         r16<true>(v);
 #pragma unroll
         for (int s = 0; s < 16; s++) {
@@ -172,10 +235,20 @@ ols4096_kernel(const float2* __restrict__ x, float2* __restrict__ y, int N, int 
             v[k0].re = *reinterpret_cast<const float2*>(&sre[272 * k0 + off]);
             v[k0].im = *reinterpret_cast<const float2*>(&sim[272 * k0 + off]);
         }
+#if OLS_TABLE_TW1
+#pragma unroll
+        for (int k0 = 1; k0 < 16; k0++) {
+            cp w;
+            w.re = __ldg(reinterpret_cast<const float2*>(tw + OLS_TW1_RE + 256 * k0 + c));
+            w.im = __ldg(reinterpret_cast<const float2*>(tw + OLS_TW1_IM + 256 * k0 + c));
+            v[k0] = cmul_conj(v[k0], w);
+        }
+#else
         cp w1;
         w1.re = *reinterpret_cast<const float2*>(tw + c);
         w1.im = pneg(*reinterpret_cast<const float2*>(tw + 256 + c));
         apply_twiddles<false>(v, w1);
+#endif
         r16<true>(v);
         // output i = i0 + m, m = c + 256*n2 - m_first in [0, step) and i < N
         const int mlo = c - m_first;                       // m for n2 = 0
@@ -186,7 +259,7 @@ ols4096_kernel(const float2* __restrict__ x, float2* __restrict__ y, int N, int 
         for (int s = 0; s < 16; s++) {
             const int n2 = r16_k(s);
             const int m = mlo + 256 * n2;
-            if (ALIGNED_STORE) {
+            if (ALIGNED) {
                 if (m >= 0 && m < mhi)
                     *reinterpret_cast<float4*>(py + 256 * n2) = make_float4(v[s].re.x, v[s].im.x, v[s].re.y, v[s].im.y);
             } else {
@@ -197,13 +270,20 @@ ols4096_kernel(const float2* __restrict__ x, float2* __restrict__ y, int N, int 
     }
 }
 
-// Hpos (planar, position order) <- Hs (interleaved, natural order, already scaled by 1/M)
-__global__ void ols4096_permute_h_kernel(const float2* __restrict__ Hs, float* __restrict__ Hre, float* __restrict__ Him) {
+// Hpos (planar, kernel layout) <- Hs (interleaved, natural order, already scaled by 1/M), delayed by d
+// samples: H_d[k] = H[k] * exp(-2 pi i k d / M).  Kernel layout: value of block position
+// p = 16*(t + 128*half) + 4*q + e is stored at ((half*4 + q)*128 + t)*4 + e.
+__global__ void ols4096_permute_h_kernel(const float2* __restrict__ Hs, float* __restrict__ Hre, float* __restrict__ Him, int d) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= OLS_M) return;
-    const float2 h = Hs[freq_of_pos(p)];
-    Hre[p] = h.x;
-    Him[p] = h.y;
+    const int k = freq_of_pos(p);
+    float2 h = Hs[k];
+    if (d) h = cmul(h, unit_root<float>((unsigned long long)k * (unsigned long long)d, OLS_M, -1));
+    const int gg = p >> 4, q = (p >> 2) & 3, e = p & 3;
+    const int t = gg & 127, half = gg >> 7;
+    const int dst = ((half * 4 + q) * OLS_THREADS + t) * 4 + e;
+    Hre[dst] = h.x;
+    Him[dst] = h.y;
 }
 
 namespace {
@@ -223,11 +303,18 @@ static const float* ols4096_twiddles() {
         h[c] = (float)cosl(a);
         h[256 + c] = (float)sinl(a);
     }
-    for (int n = 0; n < 16; n++) {
-        const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)n / 256.0L;
-        h[512 + n] = (float)cosl(a);
-        h[528 + n] = (float)sinl(a);
-    }
+    for (int k = 0; k < 16; k++)
+        for (int n = 0; n < 16; n++) {
+            const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)((k * n) % 256) / 256.0L;
+            h[OLS_TW2_RE + (8 * k + n / 2) * 4 + (n & 1)] = (float)cosl(a);
+            h[OLS_TW2_RE + (8 * k + n / 2) * 4 + 2 + (n & 1)] = (float)sinl(a);
+        }
+    for (int k = 0; k < 16; k++)
+        for (int c = 0; c < 256; c++) {
+            const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)((k * c) % 4096) / 4096.0L;
+            h[OLS_TW1_RE + 256 * k + c] = (float)cosl(a);
+            h[OLS_TW1_IM + 256 * k + c] = (float)sinl(a);
+        }
     float* dev = nullptr;
     BDSP_CUDA_ABORT(cudaMalloc(&dev, OLS_TW_FLOATS * sizeof(float)));
     BDSP_CUDA_ABORT(cudaMemcpy(dev, h.data(), OLS_TW_FLOATS * sizeof(float), cudaMemcpyHostToDevice));
@@ -237,38 +324,46 @@ static const float* ols4096_twiddles() {
 
 bool ols4096_applicable(size_t N, size_t L, size_t M) {
     // needs one wrap at most per strided load and 32-bit row indices
-    return M == OLS_M && L >= 2 && L <= OLS_M / 2 && N >= OLS_M && N < (1ull << 30);
+    return M == OLS_M && L >= 2 && L <= OLS_M / 2 - 2 && N >= OLS_M && N < (1ull << 30);
+}
+
+// plan geometry shared by prepare and convolve: delay d makes the input->output index distance even
+static inline void ols4096_geometry(size_t L, int* d, int* shift, int* m_first, int* step) {
+    const int cl = (int)(L - L / 2);
+    *d = (cl - 1) & 1;
+    *shift = cl - 1 + *d;
+    int mf = (int)L - 1 + *d;      // first block position whose circular convolution value is valid
+    if (mf & 1) mf++;
+    *m_first = mf;
+    *step = (OLS_M - mf) & ~1;
 }
 
 // Hpos: 2*4096 floats (re plane, im plane) <- Hs from ols_prepare<float>()
-int ols4096_prepare(const void* Hs, void* Hpos, cudaStream_t st) {
+int ols4096_prepare(const void* Hs, void* Hpos, size_t L, cudaStream_t st) {
+    int d, shift, m_first, step;
+    ols4096_geometry(L, &d, &shift, &m_first, &step);
     float* hp = reinterpret_cast<float*>(Hpos);
-    ols4096_permute_h_kernel<<<OLS_M / 256, 256, 0, st>>>(reinterpret_cast<const float2*>(Hs), hp, hp + OLS_M);
+    ols4096_permute_h_kernel<<<OLS_M / 256, 256, 0, st>>>(reinterpret_cast<const float2*>(Hs), hp, hp + OLS_M, d);
     BDSP_LAUNCHED();
     return 0;
 }
 
 int ols4096_convolve(const void* x, void* y, size_t N, size_t batch, size_t L, const void* Hpos, cudaStream_t st) {
     if (x == y) { set_last_error("ols4096_convolve: in-place operation is not supported"); return -3; }
-    const int cl = (int)(L - L / 2);
-    // output window of a block: positions [m_first, m_first + step); m_first >= L-1 and even so that
-    // (c even, i0 even) the two outputs of a thread start at an even index (16-byte stores)
-    int m_first = (int)L - 1;
-    if (m_first & 1) m_first++;
-    int step = OLS_M - m_first;
-    step &= ~1;
+    int d, shift, m_first, step;
+    ols4096_geometry(L, &d, &shift, &m_first, &step);
     const long long bpv = ((long long)N + step - 1) / step;
     const long long grid = bpv * (long long)batch;
     if (grid > 0x7fffffffll) { set_last_error("ols4096_convolve: grid too large"); return -2; }
     const float* hp = reinterpret_cast<const float*>(Hpos);
     const float* tw = ols4096_twiddles();
-    const bool aligned = (N % 2 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+    const bool aligned = (N % 2 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     if (aligned)
         ols4096_kernel<true><<<(unsigned)grid, OLS_THREADS, 0, st>>>(reinterpret_cast<const float2*>(x), reinterpret_cast<float2*>(y), (int)N,
-                                                                     m_first, step, cl, (int)bpv, hp, hp + OLS_M, tw);
+                                                                     m_first, step, shift, (int)bpv, hp, hp + OLS_M, tw);
     else
         ols4096_kernel<false><<<(unsigned)grid, OLS_THREADS, 0, st>>>(reinterpret_cast<const float2*>(x), reinterpret_cast<float2*>(y), (int)N,
-                                                                      m_first, step, cl, (int)bpv, hp, hp + OLS_M, tw);
+                                                                      m_first, step, shift, (int)bpv, hp, hp + OLS_M, tw);
     BDSP_LAUNCHED();
     return 0;
 }

@@ -227,9 +227,16 @@ int32_t bdsp_device_count(void);
 int32_t bdsp_set_device(int32_t device);              /* device used by subsequent calls of this host thread */
 int32_t bdsp_sync(void);                              /* wait for all work queued by this thread's stream */
 void bdsp_set_stream(void* cuda_stream);              /* cudaStream_t for subsequent calls of this thread (default: stream 0) */
+void* bdsp_stream_create(void);                       /* a new non-blocking cudaStream_t (for pipelining transfers against kernels) */
+void bdsp_stream_destroy(void* cuda_stream);
+int32_t bdsp_stream_sync(void* cuda_stream);
 /* bulk transfers: `len` T scalars; upload resizes the vector (like set_len32) when len != get_len32 */
 int32_t bdsp_upload32(BdspVec32* vector, const float* host, size_t len);
 int32_t bdsp_download32(const BdspVec32* vector, float* host, size_t len);
+/* like bdsp_download32 but does not wait: the copy is queued on the thread's stream (host must be pinned
+ * for it to overlap); call bdsp_sync() before reading `host` */
+int32_t bdsp_download_async32(const BdspVec32* vector, float* host, size_t len);
+int32_t bdsp_download_async64(const BdspVec64* vector, double* host, size_t len);
 int32_t bdsp_upload64(BdspVec64* vector, const double* host, size_t len);
 int32_t bdsp_download64(const BdspVec64* vector, double* host, size_t len);
 void* bdsp_device_ptr32(BdspVec32* vector);           /* device pointer of the vector's storage (interleaved) */

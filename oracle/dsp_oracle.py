@@ -443,14 +443,14 @@ def interpolate_lin_dest_len(data_len, factor, dtype):
     return int(np.round(T(data_len - 1) * T(factor))) + 1
 
 
-def interpolate_lin(x, factor, delay, dtype, replicate_counter_saturation=False):
+def interpolate_lin(x, factor, delay, dtype, replicate_counter_saturation=True):
     """dest_len = round((len-1)*F)+1; for i < dest_len-1: p = T(i)/F + delay (in T), b = floor(p),
     y[i] = x[b] + (x[b+1]-x[b])*(p-b) evaluated in T without FMA; last = x[len-1].
 
     The position p is computed in precision T exactly as the reference does, so the result is
-    bit-reproducible.  Deliberate deviation: the reference counts `i` in T by repeated
-    `+ 1.0` (:53,65), which stops advancing at 2^24 in f32; the product converts the integer index
-    to T (round-to-nearest) instead.  `replicate_counter_saturation=True` reproduces the reference."""
+    bit-reproducible.  Q7: the reference counts `i` in T by repeated `+ 1.0` (:53,65), which stops
+    advancing at 2^24 in f32 (every later output is computed from the same position); the product
+    replicates that saturation, and so does this oracle by default."""
     T = _T(dtype)
     x = np.asarray(x, dtype=dtype)
     n = len(x)
@@ -460,10 +460,10 @@ def interpolate_lin(x, factor, delay, dtype, replicate_counter_saturation=False)
     idx = np.arange(dest_len - 1, dtype=np.int64)
     i_T = idx.astype(dtype)
     if replicate_counter_saturation and dtype == np.float32:
-        i_T = np.minimum(i_T, T(2 ** 24))
+        i_T = np.where(idx >= 2 ** 24, T(2 ** 24), i_T).astype(dtype)
     p = (i_T / F + d).astype(dtype)
     bf = np.floor(p)
-    b = bf.astype(np.int64)
+    b = np.clip(bf.astype(np.int64), 0, n - 2)
     y0 = x[b]
     y1 = x[b + 1]
     out = np.empty(dest_len, dtype=dtype)

@@ -343,6 +343,18 @@ def test_interpolate_lin(kats):
     assert DspVec(np.ones(8, dtype=np.complex64)).result_code_of("interpolate_lin", 2.0, 0.0) == -1
 
 
+def test_interpolate_lin_c4b_full_size_counter_saturation():
+    """BASELINE config C4b (2^24 real f32, x4): beyond output 2^24 the reference's f32 counter is stuck (Q7)."""
+    n = 1 << 24
+    rng = np.random.default_rng(4)
+    x = rng.uniform(-10, 10, n).astype(np.float32)
+    got = DspVec(x).interpolate_lin(4.0, 0.0).to_numpy()
+    ref = o.interpolate_lin(x, 4.0, 0.0, np.float32)
+    assert len(got) == len(ref) == 4 * (n - 1) + 1
+    assert np.array_equal(got, ref)
+    assert np.all(got[(1 << 24):-1] == got[1 << 24])
+
+
 # --------------------------------------------------------------------------------------------------
 # elementwise chain (<= 4 ulp)
 # --------------------------------------------------------------------------------------------------

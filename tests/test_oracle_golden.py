@@ -257,7 +257,7 @@ def test_interpolate_lin(kats):  # real_interpolation.rs:226-237
 
 def test_interpolate_lin_counter_saturation_flag():
     x = np.arange(8, dtype=np.float32)
-    a = o.interpolate_lin(x, 2.0, 0.0, np.float32)
+    a = o.interpolate_lin(x, 2.0, 0.0, np.float32, replicate_counter_saturation=False)
     b = o.interpolate_lin(x, 2.0, 0.0, np.float32, replicate_counter_saturation=True)
     assert np.array_equal(a, b)  # identical below 2^24
 
