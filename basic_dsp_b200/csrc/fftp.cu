@@ -1,0 +1,322 @@
+// Packed-FP32x2 shared-memory FFT for c32 sequences of n = 4096 * R0 points, R0 in {1, 2, 4}
+// (4096, 8192, 16384): natural order in, natural order out, one HBM read and one HBM write per point.
+// Same building blocks as the fused overlap-save kernel (ols4096.cuh):
+//   F0  radix-R0 DIF over stride 4096 (global -> shared), twiddle W_n^{k0' c}
+//   F1  radix-16 DIF over stride 256, F2 radix-16 DIF over stride 16 (in place in shared memory)
+//   F3  radix-16 DIF over 16 contiguous points in registers -> global, natural order
+//       (output k = k0' + R0*(k0 + 16*k1 + 256*k2); lanes walk k0', k0 so that stores coalesce)
+// With CL = 2 a sequence is split over a thread-block CLUSTER of two CTAs: each CTA owns R0/2 of the
+// 4096-point sub-transforms and the F0 results that belong to the partner are written straight into
+// its shared memory (distributed shared memory), so that three CTAs fit on an SM and the load / compute
+// / store phases of different sequences overlap.
+// Replaces rustfft for these lengths (vector/src/vector_types/time_freq/mod.rs:45-58) incl. the fused
+// fft_shift (time_to_freq.rs:163), ifft's scale + ifft_shift (freq_to_time.rs:165-167) and magnitude.
+#include <cooperative_groups.h>
+
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "fft.cuh"
+#include "ols4096.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace bdsp {
+using namespace ols16;
+
+#define FP_B 4352   // floats per sub-block plane (16 rows of 272)
+
+// layout inside a sub-block: p = 256*row + 16*g + j  ->  272*row + 16*g + ((j + 4*(rot(g) + (row>>1))) & 15)
+__device__ __forceinline__ int fp_rot(int row, int g) { return (((g >> 1) + (row >> 1)) & 3); }
+
+// twiddle table (floats): [0,256) Re W4096^c, [256,512) Im W4096^c, [512,1024) stride-16 table (see ols4096.cu),
+// [1024 + 8192*i + c] Re W_{8192<<i}^c, [1024 + 8192*i + 4096 + c] Im, c in [0,4096), i in {0,1}
+#define FP_TW_FLOATS (1024 + 2 * 8192)
+
+template <int R0, int CL, bool INV, bool SHIFT_IN, bool SHIFT_OUT, bool MAG>
+__global__ void __launch_bounds__(128 * (R0 / CL), 4 / (R0 / CL))
+fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, float scale, const float* __restrict__ tw) {
+    constexpr int NSB = R0 / CL;          // sub-blocks (4096-point transforms) owned by this CTA
+    constexpr int NT = 128 * NSB;         // threads
+    constexpr int N = 4096 * R0;
+    extern __shared__ __align__(16) float smem[];
+    float* sre = smem;
+    float* sim = smem + NSB * FP_B;
+    const int t = threadIdx.x;
+    const int rank = CL > 1 ? (int)(blockIdx.x % CL) : 0;
+    const size_t row = blockIdx.x / CL;
+    const float2* xr = x + row * (size_t)N;
+
+    cp v[16];
+    // ------------------------------------------------------------------ F0: radix-R0 over stride 4096
+    if constexpr (R0 > 1) {
+        float* rre[CL];
+        float* rim[CL];
+        if constexpr (CL > 1) {
+            cg::cluster_group cluster = cg::this_cluster();
+#pragma unroll
+            for (int o = 0; o < CL; o++) {
+                rre[o] = cluster.map_shared_rank(sre, o);
+                rim[o] = cluster.map_shared_rank(sim, o);
+            }
+            cluster.sync();   // the partner CTA is resident before anyone writes into its shared memory
+        } else {
+            rre[0] = sre; rim[0] = sim;
+        }
+        const float* tw0 = tw + 1024 + (R0 == 4 ? 8192 : 0);
+        constexpr int NU = 16 / R0;   // column pairs per thread: (2048 / CL) / NT
+#pragma unroll
+        for (int u = 0; u < NU; u++) {
+            const int pi = rank * (2048 / CL) + t + NT * u;     // column pair index, c = 2*pi
+            const int c = 2 * pi;
+            cp a[R0];
+#pragma unroll
+            for (int n3 = 0; n3 < R0; n3++) {
+                const int src = SHIFT_IN ? ((n3 + R0 / 2) % R0) : n3;
+                const float4 ab = __ldg(reinterpret_cast<const float4*>(xr + c + 4096 * src));
+                a[n3].re = make_float2(ab.x, ab.z);
+                a[n3].im = make_float2(ab.y, ab.w);
+            }
+            if constexpr (R0 == 4) r4<INV>(a[0], a[1], a[2], a[3]);
+            else { cp s = cadd(a[0], a[1]); cp d = csub(a[0], a[1]); a[0] = s; a[1] = d; }
+            cp w1;
+            w1.re = __ldg(reinterpret_cast<const float2*>(tw0 + c));
+            w1.im = __ldg(reinterpret_cast<const float2*>(tw0 + 4096 + c));
+            if (INV) w1.im = pneg(w1.im);
+            a[1] = cmul(a[1], w1);
+            if constexpr (R0 == 4) {
+                cp w2 = cmul(w1, w1);
+                a[2] = cmul(a[2], w2);
+                a[3] = cmul(a[3], cmul(w2, w1));
+            }
+            const int prow = pi >> 7, g = (pi >> 3) & 15, j = 2 * (pi & 7);
+            const int off = 272 * prow + 16 * g + ((j + 4 * fp_rot(prow, g)) & 15);
+#pragma unroll
+            for (int k = 0; k < R0; k++) {
+                const int owner = k / NSB, lsb = k % NSB;
+                *reinterpret_cast<float2*>(rre[owner] + lsb * FP_B + off) = a[k].re;
+                *reinterpret_cast<float2*>(rim[owner] + lsb * FP_B + off) = a[k].im;
+            }
+        }
+        if constexpr (CL > 1) cg::this_cluster().sync();
+        else __syncthreads();
+    }
+    // ------------------------------------------------------------------ F1: stride 256 inside every sub-block
+    const int sb = t >> 7, tt = t & 127;
+    float* bre = sre + sb * FP_B;
+    float* bim = sim + sb * FP_B;
+    {
+        const int c = 2 * tt;
+        const int g = tt >> 3, j = 2 * (tt & 7);
+        int off[4];   // row>>1 takes 8 values but only (row>>1)&3 matters: 4 rotations
+#pragma unroll
+        for (int r = 0; r < 4; r++) off[r] = 16 * g + ((j + 4 * (((g >> 1) + r) & 3)) & 15);
+        if constexpr (R0 > 1) {
+#pragma unroll
+            for (int n2 = 0; n2 < 16; n2++) {
+                v[n2].re = *reinterpret_cast<const float2*>(bre + 272 * n2 + off[(n2 >> 1) & 3]);
+                v[n2].im = *reinterpret_cast<const float2*>(bim + 272 * n2 + off[(n2 >> 1) & 3]);
+            }
+        } else {
+#pragma unroll
+            for (int n2 = 0; n2 < 16; n2++) {
+                const int src = SHIFT_IN ? (n2 ^ 8) : n2;
+                const float4 ab = __ldg(reinterpret_cast<const float4*>(xr + c + 256 * src));
+                v[n2].re = make_float2(ab.x, ab.z);
+                v[n2].im = make_float2(ab.y, ab.w);
+            }
+        }
+        r16<INV>(v);
+        cp w1;
+        w1.re = *reinterpret_cast<const float2*>(tw + c);
+        w1.im = *reinterpret_cast<const float2*>(tw + 256 + c);
+        if (INV) w1.im = pneg(w1.im);
+        apply_twiddles<true>(v, w1);
+#pragma unroll
+        for (int s = 0; s < 16; s++) {
+            const int k0 = r16_k(s);
+            *reinterpret_cast<float2*>(bre + 272 * k0 + off[(k0 >> 1) & 3]) = v[s].re;
+            *reinterpret_cast<float2*>(bim + 272 * k0 + off[(k0 >> 1) & 3]) = v[s].im;
+        }
+    }
+    __syncthreads();
+    // ------------------------------------------------------------------ F2: stride 16
+    {
+        const int k0 = tt >> 3, n0 = 2 * (tt & 7);
+        int off2[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) off2[r] = 272 * k0 + ((n0 + 4 * ((r + (k0 >> 1)) & 3)) & 15);
+        const float4* tw2 = reinterpret_cast<const float4*>(tw + 512) + (n0 >> 1);
+#pragma unroll
+        for (int n1 = 0; n1 < 16; n1++) {
+            const int a = 16 * n1 + off2[(n1 >> 1) & 3];
+            v[n1].re = *reinterpret_cast<const float2*>(bre + a);
+            v[n1].im = *reinterpret_cast<const float2*>(bim + a);
+        }
+        r16<INV>(v);
+#pragma unroll
+        for (int s = 1; s < 16; s++) {
+            const int k1 = r16_k(s);
+            const float4 f = __ldg(tw2 + 8 * k1);
+            cp w;
+            w.re = make_float2(f.x, f.y);
+            w.im = make_float2(f.z, f.w);
+            v[s] = INV ? cmul_conj(v[s], w) : cmul(v[s], w);
+        }
+#pragma unroll
+        for (int s = 0; s < 16; s++) {
+            const int k1 = r16_k(s);
+            const int a = 16 * k1 + off2[(k1 >> 1) & 3];
+            *reinterpret_cast<float2*>(bre + a) = v[s].re;
+            *reinterpret_cast<float2*>(bim + a) = v[s].im;
+        }
+    }
+    __syncthreads();
+    // ------------------------------------------------------------------ F3: 16 contiguous points -> global
+#pragma unroll 1
+    for (int half = 0; half < 2; half++) {
+        const int gl = t + NT * half;                 // local group index: lsb + NSB*(k0 + 16*k1)
+        const int lsb = gl % NSB, k0 = (gl / NSB) & 15, k1 = gl / (16 * NSB);
+        const int r = fp_rot(k0, k1);
+        const int base = lsb * FP_B + 272 * k0 + 16 * k1;
+        cp P[8];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int a = base + 4 * ((q + r) & 3);
+            const float4 fr = *reinterpret_cast<const float4*>(sre + a);
+            const float4 fi = *reinterpret_cast<const float4*>(sim + a);
+            P[2 * q].re = make_float2(fr.x, fr.y); P[2 * q + 1].re = make_float2(fr.z, fr.w);
+            P[2 * q].im = make_float2(fi.x, fi.y); P[2 * q + 1].im = make_float2(fi.z, fi.w);
+        }
+        fft16_dif<INV>(P);
+        // slot j holds k2 = bitrev4(j); k = (rank*NSB + lsb) + R0*(k0 + 16*k1 + 256*k2)
+        const int klow = rank * NSB + lsb + R0 * (k0 + 16 * k1);
+        if constexpr (MAG) {
+            float* o = reinterpret_cast<float*>(out_) + row * (size_t)N + klow;
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                pk m2 = pfma(P[m].re, P[m].re, pmul(P[m].im, P[m].im));
+                const int ka = bitrev4(2 * m) ^ (SHIFT_OUT ? 8 : 0), kb = bitrev4(2 * m + 1) ^ (SHIFT_OUT ? 8 : 0);
+                o[256 * R0 * ka] = sqrtf(m2.x) * scale;
+                o[256 * R0 * kb] = sqrtf(m2.y) * scale;
+            }
+        } else {
+            float2* o = reinterpret_cast<float2*>(out_) + row * (size_t)N + klow;
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                const int ka = bitrev4(2 * m) ^ (SHIFT_OUT ? 8 : 0), kb = bitrev4(2 * m + 1) ^ (SHIFT_OUT ? 8 : 0);
+                o[256 * R0 * ka] = make_float2(P[m].re.x * scale, P[m].im.x * scale);
+                o[256 * R0 * kb] = make_float2(P[m].re.y * scale, P[m].im.y * scale);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+namespace {
+std::mutex g_fp_mu;
+std::map<int, float*> g_fp_tw;
+
+const float* fftp_twiddles() {
+    int d = 0;
+    BDSP_CUDA_ABORT(cudaGetDevice(&d));
+    std::lock_guard<std::mutex> lk(g_fp_mu);
+    auto it = g_fp_tw.find(d);
+    if (it != g_fp_tw.end()) return it->second;
+    std::vector<float> h(FP_TW_FLOATS, 0.f);
+    const long double tau = 2.0L * 3.14159265358979323846264338327950288L;
+    for (int c = 0; c < 256; c++) {
+        h[c] = (float)cosl(-tau * c / 4096.0L);
+        h[256 + c] = (float)sinl(-tau * c / 4096.0L);
+    }
+    for (int k = 0; k < 16; k++)
+        for (int n = 0; n < 16; n++) {
+            const long double a = -tau * (long double)((k * n) % 256) / 256.0L;
+            h[512 + (8 * k + n / 2) * 4 + (n & 1)] = (float)cosl(a);
+            h[512 + (8 * k + n / 2) * 4 + 2 + (n & 1)] = (float)sinl(a);
+        }
+    for (int i = 0; i < 2; i++)
+        for (int c = 0; c < 4096; c++) {
+            const long double a = -tau * (long double)c / (long double)(8192 << i);
+            h[1024 + 8192 * i + c] = (float)cosl(a);
+            h[1024 + 8192 * i + 4096 + c] = (float)sinl(a);
+        }
+    float* dev = nullptr;
+    BDSP_CUDA_ABORT(cudaMalloc(&dev, FP_TW_FLOATS * sizeof(float)));
+    BDSP_CUDA_ABORT(cudaMemcpy(dev, h.data(), FP_TW_FLOATS * sizeof(float), cudaMemcpyHostToDevice));
+    g_fp_tw[d] = dev;
+    return dev;
+}
+
+template <int R0, int CL, bool INV, bool SI, bool SO, bool MAG>
+int fftp_launch(const void* in, void* out, size_t rows, float scale, cudaStream_t st) {
+    constexpr int NSB = R0 / CL;
+    const size_t smem = (size_t)2 * NSB * FP_B * sizeof(float);
+    auto kern = fftp_kernel<R0, CL, INV, SI, SO, MAG>;
+    static bool configured = false;   // per instantiation
+    if (!configured) {
+        BDSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const float* tw = fftp_twiddles();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(rows * CL));
+    cfg.blockDim = dim3(128 * NSB);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = CL > 1 ? 1 : 0;
+    BDSP_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, reinterpret_cast<const float2*>(in), out, scale, tw));
+    BDSP_LAUNCHED();
+    return 0;
+}
+
+template <int R0, int CL>
+int fftp_dispatch(const void* in, void* out, size_t rows, bool inv, bool shift_in, bool shift_out, bool mag, float scale,
+                  cudaStream_t st) {
+    if (!inv) {
+        if (mag) return shift_out ? fftp_launch<R0, CL, false, false, true, true>(in, out, rows, scale, st)
+                                  : fftp_launch<R0, CL, false, false, false, true>(in, out, rows, scale, st);
+        return shift_out ? fftp_launch<R0, CL, false, false, true, false>(in, out, rows, scale, st)
+                         : fftp_launch<R0, CL, false, false, false, false>(in, out, rows, scale, st);
+    }
+    if (mag || shift_out) return 1;   // not instantiated: caller falls back to the generic kernel
+    return shift_in ? fftp_launch<R0, CL, true, true, false, false>(in, out, rows, scale, st)
+                    : fftp_launch<R0, CL, true, false, false, false>(in, out, rows, scale, st);
+}
+}  // namespace
+
+// CTAs per sequence for n >= 8192: 2 = thread-block cluster with distributed shared memory (default),
+// 1 = one CTA per sequence.  BDSP_FFTP_CLUSTER=1 selects the latter (for A/B measurements).
+static int fftp_cluster_mode() {
+    static int mode = [] {
+        const char* e = getenv("BDSP_FFTP_CLUSTER");
+        return (e && e[0] == '1') ? 1 : 2;
+    }();
+    return mode;
+}
+
+// returns 0 on success, 1 when this configuration is not covered (caller uses the generic kernel)
+int fftp_try(const void* in, void* out, size_t n, size_t rows, bool inverse, size_t in_rot, size_t out_rot, double scale,
+             bool magnitude, cudaStream_t st) {
+    if (n != 4096 && n != 8192 && n != 16384) return 1;
+    if ((in_rot != 0 && in_rot != n / 2) || (out_rot != 0 && out_rot != n / 2)) return 1;
+    if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 7)) return 1;
+    if (in == out) return 1;   // rows are consumed while other CTAs may still read them only within a row; keep it simple
+    if (rows * 2 > 0x7fffffffull) return 1;
+    const bool si = in_rot != 0, so = out_rot != 0;
+    const float sc = (float)scale;
+    if (n == 4096) return fftp_dispatch<1, 1>(in, out, rows, inverse, si, so, magnitude, sc, st);
+    if (n == 8192) return fftp_cluster_mode() == 2 ? fftp_dispatch<2, 2>(in, out, rows, inverse, si, so, magnitude, sc, st)
+                                              : fftp_dispatch<2, 1>(in, out, rows, inverse, si, so, magnitude, sc, st);
+    return fftp_cluster_mode() == 2 ? fftp_dispatch<4, 2>(in, out, rows, inverse, si, so, magnitude, sc, st)
+                               : fftp_dispatch<4, 1>(in, out, rows, inverse, si, so, magnitude, sc, st);
+}
+
+}  // namespace bdsp

@@ -37,14 +37,6 @@ __device__ __forceinline__ void sts64(float* p, float2 v) {
 #define OLS_TABLE_TW1 0  // measured on B200: the table variant (L1-bound) is 10% slower than computing the powers
 #endif
 
-// apply conj(w): a * conj(w)
-__device__ __forceinline__ cp cmul_conj(cp a, cp w) {
-    cp r;
-    r.re = pfma(a.re, w.re, pmul(a.im, w.im));
-    r.im = pfma(a.im, w.re, pneg(pmul(a.re, w.im)));
-    return r;
-}
-
 // ALIGNED: rows start on 16-byte boundaries (N even, 16-byte aligned base pointers); together with the
 // even block offsets chosen by the plan every thread then moves its two adjacent points with one
 // 128-bit access.  `shift` = cl - 1 + d is the (even) distance between a block position's input index

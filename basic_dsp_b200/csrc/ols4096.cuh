@@ -44,6 +44,13 @@ __device__ __forceinline__ cp cmul(cp a, cp w) {
     r.im = pfma(a.re, w.im, pmul(a.im, w.re));
     return r;
 }
+// a * conj(w)
+__device__ __forceinline__ cp cmul_conj(cp a, cp w) {
+    cp r;
+    r.re = pfma(a.re, w.re, pmul(a.im, w.im));
+    r.im = pfma(a.im, w.re, pneg(pmul(a.re, w.im)));
+    return r;
+}
 // a * (wr + i*wi) with per-lane constants
 __device__ __forceinline__ cp cmulc(cp a, pk wr, pk wi) {
     cp r;
@@ -128,11 +135,12 @@ __device__ __forceinline__ int rot_of(int g) { return (g >> 1) & 3; }
 __device__ __forceinline__ int phys(int k0, int g, int j) { return 272 * k0 + 16 * g + ((j + 4 * rot_of(g)) & 15); }
 
 // ---- in-register 16-point transforms over 16 CONTIGUOUS points, packed over adjacent points ------
-// P[m] = {a[2m], a[2m+1]}.  Forward: DIF, natural in -> bit-reversed out.
-__device__ __forceinline__ void fft16_dif_fwd(cp (&P)[8]) {
+// P[m] = {a[2m], a[2m+1]}.  DIF, natural in -> bit-reversed out; INV selects exp(+i...).
+template <bool INV> __device__ __forceinline__ void fft16_dif(cp (&P)[8]) {
+    const float sg = INV ? -1.f : 1.f;   // sign applied to the imaginary parts of the forward roots
     // level 1, span 8: twiddle W16^{j}, j = 2m, 2m+1
     const pk t1r[4] = {make_float2(1.f, OLS_C1), make_float2(OLS_H, OLS_S1), make_float2(0.f, -OLS_S1), make_float2(-OLS_H, -OLS_C1)};
-    const pk t1i[4] = {make_float2(0.f, -OLS_S1), make_float2(-OLS_H, -OLS_C1), make_float2(-1.f, -OLS_C1), make_float2(-OLS_H, -OLS_S1)};
+    const pk t1i[4] = {make_float2(0.f, -sg * OLS_S1), make_float2(-sg * OLS_H, -sg * OLS_C1), make_float2(-sg, -sg * OLS_C1), make_float2(-sg * OLS_H, -sg * OLS_S1)};
 #pragma unroll
     for (int m = 0; m < 4; m++) {
         cp u = cadd(P[m], P[m + 4]);
@@ -142,7 +150,7 @@ __device__ __forceinline__ void fft16_dif_fwd(cp (&P)[8]) {
     }
     // level 2, span 4: twiddle W8^{j}, j = 2m, 2m+1
     const pk t2r[2] = {make_float2(1.f, OLS_H), make_float2(0.f, -OLS_H)};
-    const pk t2i[2] = {make_float2(0.f, -OLS_H), make_float2(-1.f, -OLS_H)};
+    const pk t2i[2] = {make_float2(0.f, -sg * OLS_H), make_float2(-sg, -sg * OLS_H)};
 #pragma unroll
     for (int b = 0; b < 8; b += 4) {
 #pragma unroll
@@ -153,22 +161,26 @@ __device__ __forceinline__ void fft16_dif_fwd(cp (&P)[8]) {
             P[b + m + 2] = cmulc(d, t2r[m], t2i[m]);
         }
     }
-    // level 3, span 2 (twiddle {1, -i} of the difference deferred into level 4) and level 4, span 1
+    // level 3, span 2 (twiddle {1, -+i} of the difference deferred into level 4) and level 4, span 1
 #pragma unroll
     for (int b = 0; b < 8; b += 2) {
         cp u = cadd(P[b], P[b + 1]);
         cp d = csub(P[b], P[b + 1]);
-        // u: plain butterfly of its two lanes
         cp o;
         o.re = make_float2(u.re.x + u.re.y, u.re.x - u.re.y);
         o.im = make_float2(u.im.x + u.im.y, u.im.x - u.im.y);
         P[b] = o;
-        // d: lane y carries the deferred -i: y' = (y.im, -y.re)
-        o.re = make_float2(d.re.x + d.im.y, d.re.x - d.im.y);
-        o.im = make_float2(d.im.x - d.re.y, d.im.x + d.re.y);
+        if (!INV) {   // lane y carries the deferred -i: y' = (y.im, -y.re)
+            o.re = make_float2(d.re.x + d.im.y, d.re.x - d.im.y);
+            o.im = make_float2(d.im.x - d.re.y, d.im.x + d.re.y);
+        } else {      // +i: y' = (-y.im, y.re)
+            o.re = make_float2(d.re.x - d.im.y, d.re.x + d.im.y);
+            o.im = make_float2(d.im.x + d.re.y, d.im.x - d.re.y);
+        }
         P[b + 1] = o;
     }
 }
+__device__ __forceinline__ void fft16_dif_fwd(cp (&P)[8]) { fft16_dif<false>(P); }
 
 // Inverse: DIT, bit-reversed in -> natural out.
 __device__ __forceinline__ void fft16_dit_inv(cp (&P)[8]) {
