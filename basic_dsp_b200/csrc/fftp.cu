@@ -25,7 +25,10 @@ namespace cg = cooperative_groups;
 namespace bdsp {
 using namespace ols16;
 
-#define FP_B 4352   // floats per sub-block plane (16 rows of 272)
+// floats per sub-block plane: 16 rows of 272 plus a pad that spreads the sub-blocks over the 16-byte
+// bank windows, so that the 8 lanes of every quarter-warp of the 128-bit loads in F3 (lanes walk
+// sub-block, then row) hit 8 different windows: NSB = 2 -> +8 floats, NSB = 4 -> +4 floats
+#define FP_B_OF(NSB_) (4352 + ((NSB_) == 2 ? 8 : (NSB_) == 4 ? 4 : 0))
 
 // layout inside a sub-block: p = 256*row + 16*g + j  ->  272*row + 16*g + ((j + 4*(rot(g) + (row>>1))) & 15)
 __device__ __forceinline__ int fp_rot(int row, int g) { return (((g >> 1) + (row >> 1)) & 3); }
@@ -35,18 +38,47 @@ __device__ __forceinline__ int fp_rot(int row, int g) { return (((g >> 1) + (row
 #define FP_TW_FLOATS (1024 + 2 * 8192)
 
 template <int R0, int CL, bool INV, bool SHIFT_IN, bool SHIFT_OUT, bool MAG>
-__global__ void __launch_bounds__(128 * (R0 / CL), 4 / (R0 / CL))
-fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, float scale, const float* __restrict__ tw) {
+// FP_PREFETCH=1: persistent CTAs + register prefetch of the next row.  Measured on B200 (C3): 0.336 ms vs
+// 0.275 ms without (register pressure -> spills; the extra barrier), so it is off by default.
+#ifndef FP_PREFETCH
+#define FP_PREFETCH 0
+#endif
+#ifndef FP_MINB256
+#define FP_MINB256 2
+#endif
+__global__ void __launch_bounds__(128 * (R0 / CL), (R0 / CL) == 2 ? FP_MINB256 : 4 / (R0 / CL))
+fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, long long rows, float scale, const float* __restrict__ tw) {
     constexpr int NSB = R0 / CL;          // sub-blocks (4096-point transforms) owned by this CTA
     constexpr int NT = 128 * NSB;         // threads
     constexpr int N = 4096 * R0;
+    constexpr int FP_B = FP_B_OF(NSB);
     extern __shared__ __align__(16) float smem[];
     float* sre = smem;
     float* sim = smem + NSB * FP_B;
     const int t = threadIdx.x;
     const int rank = CL > 1 ? (int)(blockIdx.x % CL) : 0;
-    const size_t row = blockIdx.x / CL;
-    const float2* xr = x + row * (size_t)N;
+    // CL == 1: persistent CTAs walk the rows and prefetch the next row's inputs (registers) while the
+    // last stage of the current row runs, so that the HBM latency of the load phase is hidden even with
+    // one CTA per SM.  CL == 2: one cluster per row.
+    constexpr bool PREFETCH = FP_PREFETCH && (CL == 1 && R0 > 1);
+    constexpr int NU = R0 > 1 ? 16 / R0 : 1;   // column pairs per thread in F0: (2048 / CL) / NT
+    float4 raw[PREFETCH ? NU * R0 : 1];
+    const long long row_step = gridDim.x / CL;
+    long long row = blockIdx.x / CL;
+    if constexpr (PREFETCH) {
+        if (row < rows) {
+            const float2* xr0 = x + (size_t)row * (size_t)N;
+#pragma unroll
+            for (int u = 0; u < NU; u++)
+#pragma unroll
+                for (int n3 = 0; n3 < R0; n3++) {
+                    const int src = SHIFT_IN ? ((n3 + R0 / 2) % R0) : n3;
+                    raw[u * R0 + n3] = __ldg(reinterpret_cast<const float4*>(xr0 + 2 * (t + NT * u) + 4096 * src));
+                }
+        }
+    }
+    for (; row < rows; row += row_step) {
+    const float2* xr = x + (size_t)row * (size_t)N;
 
     cp v[16];
     // ------------------------------------------------------------------ F0: radix-R0 over stride 4096
@@ -60,12 +92,11 @@ fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, float scale, 
                 rre[o] = cluster.map_shared_rank(sre, o);
                 rim[o] = cluster.map_shared_rank(sim, o);
             }
-            cluster.sync();   // the partner CTA is resident before anyone writes into its shared memory
+            cluster.sync();   // the partner CTA is resident (and done with its previous row) before anyone writes into its shared memory
         } else {
             rre[0] = sre; rim[0] = sim;
         }
         const float* tw0 = tw + 1024 + (R0 == 4 ? 8192 : 0);
-        constexpr int NU = 16 / R0;   // column pairs per thread: (2048 / CL) / NT
 #pragma unroll
         for (int u = 0; u < NU; u++) {
             const int pi = rank * (2048 / CL) + t + NT * u;     // column pair index, c = 2*pi
@@ -73,8 +104,12 @@ fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, float scale, 
             cp a[R0];
 #pragma unroll
             for (int n3 = 0; n3 < R0; n3++) {
-                const int src = SHIFT_IN ? ((n3 + R0 / 2) % R0) : n3;
-                const float4 ab = __ldg(reinterpret_cast<const float4*>(xr + c + 4096 * src));
+                float4 ab;
+                if constexpr (PREFETCH) ab = raw[u * R0 + n3];
+                else {
+                    const int src = SHIFT_IN ? ((n3 + R0 / 2) % R0) : n3;
+                    ab = __ldg(reinterpret_cast<const float4*>(xr + c + 4096 * src));
+                }
                 a[n3].re = make_float2(ab.x, ab.z);
                 a[n3].im = make_float2(ab.y, ab.w);
             }
@@ -173,6 +208,19 @@ fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, float scale, 
         }
     }
     __syncthreads();
+    if constexpr (PREFETCH) {
+        const long long nrow = row + row_step;
+        if (nrow < rows) {
+            const float2* xn = x + (size_t)nrow * (size_t)N;
+#pragma unroll
+            for (int u = 0; u < NU; u++)
+#pragma unroll
+                for (int n3 = 0; n3 < R0; n3++) {
+                    const int src = SHIFT_IN ? ((n3 + R0 / 2) % R0) : n3;
+                    raw[u * R0 + n3] = __ldg(reinterpret_cast<const float4*>(xn + 2 * (t + NT * u) + 4096 * src));
+                }
+        }
+    }
     // ------------------------------------------------------------------ F3: 16 contiguous points -> global
 #pragma unroll 1
     for (int half = 0; half < 2; half++) {
@@ -211,6 +259,8 @@ fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, float scale, 
             }
         }
     }
+    if (row + row_step < rows) __syncthreads();   // the next row's F0 overwrites the shared memory F3 just read
+    }  // rows
 }
 
 // ------------------------------------------------------------------------------------------
@@ -252,7 +302,7 @@ const float* fftp_twiddles() {
 template <int R0, int CL, bool INV, bool SI, bool SO, bool MAG>
 int fftp_launch(const void* in, void* out, size_t rows, float scale, cudaStream_t st) {
     constexpr int NSB = R0 / CL;
-    const size_t smem = (size_t)2 * NSB * FP_B * sizeof(float);
+    const size_t smem = (size_t)2 * NSB * FP_B_OF(NSB) * sizeof(float);
     auto kern = fftp_kernel<R0, CL, INV, SI, SO, MAG>;
     static bool configured = false;   // per instantiation
     if (!configured) {
@@ -261,7 +311,14 @@ int fftp_launch(const void* in, void* out, size_t rows, float scale, cudaStream_
     }
     const float* tw = fftp_twiddles();
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(rows * CL));
+    // CL == 1 and n >= 8192: persistent CTAs (one per SM, 139/70 KB of shared memory each)
+    size_t ctas = rows * CL;
+    if (FP_PREFETCH && CL == 1 && R0 > 1) {
+        const size_t per_sm = R0 == 4 ? 1 : 2;
+        const size_t cap = (size_t)sm_count() * per_sm;
+        if (ctas > cap) ctas = cap;
+    }
+    cfg.gridDim = dim3((unsigned)ctas);
     cfg.blockDim = dim3(128 * NSB);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
@@ -272,7 +329,7 @@ int fftp_launch(const void* in, void* out, size_t rows, float scale, cudaStream_
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = CL > 1 ? 1 : 0;
-    BDSP_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, reinterpret_cast<const float2*>(in), out, scale, tw));
+    BDSP_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, reinterpret_cast<const float2*>(in), out, (long long)rows, scale, tw));
     BDSP_LAUNCHED();
     return 0;
 }
@@ -292,12 +349,13 @@ int fftp_dispatch(const void* in, void* out, size_t rows, bool inv, bool shift_i
 }
 }  // namespace
 
-// CTAs per sequence for n >= 8192: 2 = thread-block cluster with distributed shared memory (default),
-// 1 = one CTA per sequence.  BDSP_FFTP_CLUSTER=1 selects the latter (for A/B measurements).
+// CTAs per sequence for n >= 8192: 1 = one persistent CTA per SM with register prefetch (default,
+// measured faster on B200), 2 = thread-block cluster of two CTAs exchanging the first stage through
+// distributed shared memory.  BDSP_FFTP_CLUSTER=2 selects the latter (for A/B measurements).
 static int fftp_cluster_mode() {
     static int mode = [] {
         const char* e = getenv("BDSP_FFTP_CLUSTER");
-        return (e && e[0] == '1') ? 1 : 2;
+        return (e && e[0] == '2') ? 2 : 1;
     }();
     return mode;
 }

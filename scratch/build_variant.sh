@@ -4,8 +4,8 @@ set -e
 name=$1; shift
 cd /root/repo/basic_dsp_b200/csrc
 objs=""
-for f in common fft conv ols4096 interp elementwise capi; do
-  if [ "$f" = "ols4096" ]; then
+for f in common fft conv ols4096 fftp interp elementwise capi; do
+  if [ "$f" = "ols4096" ] || [ "$f" = "fftp" ]; then
     nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden "$@" -c $f.cu -o /tmp/var_${name}_$f.o
     objs="$objs /tmp/var_${name}_$f.o"
   else
