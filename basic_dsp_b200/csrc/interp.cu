@@ -93,6 +93,231 @@ __global__ void interp_poly_generic_kernel(const void* __restrict__ x_, void* __
     reinterpret_cast<X*>(y_)[i] = acc;
 }
 
+// ------------------------------------------------------------------------------------------
+// Register-tiled polyphase kernel (the one used for F <= 8): a thread owns RP consecutive input
+// positions x F phases = RP*F accumulators; per tap it issues ONE shared load for the sliding input
+// window and one (vector, warp-uniform) load for the F taps, i.e. RP*F FMAs per two shared loads.
+// CTAs whose outputs touch the first/last (2L+1)*F outputs (different tap window there, see the header
+// comment) take the per-output path of interp_poly_generic_kernel's logic.
+// ------------------------------------------------------------------------------------------
+#define IP2_THREADS 256
+__device__ __forceinline__ int ip_skew(int i) { return i + (i >> 5); }   // lanes are RP elements apart
+
+template <typename T, bool CPLX, int FMAX, int RP>
+__global__ void __launch_bounds__(IP2_THREADS)
+interp_poly_tiled_kernel(const void* __restrict__ x_, void* __restrict__ y_, const T* __restrict__ tab, long long N,
+                         long long new_points, int F, int L, long long scalar_len) {
+    typedef typename CpxOf<T>::type C;
+    typedef typename std::conditional<CPLX, C, T>::type X;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int J = 2 * L + 3;
+    constexpr int POS = IP2_THREADS * RP;                     // input positions per CTA
+    T* stab = reinterpret_cast<T*>(smem_raw);                 // interior taps, [J][FMAX]
+    X* sx = reinterpret_cast<X*>(stab + ((J * FMAX + 3) & ~3));
+    const long long r0 = (long long)blockIdx.x * POS;
+    const bool interior = (r0 * F >= scalar_len) && ((r0 + POS) * F <= new_points - scalar_len);
+    if (!interior) {
+        // edge CTA: one output at a time, tap table chosen per output
+        for (long long i = r0 * F + threadIdx.x; i < (r0 + POS) * F && i < new_points; i += IP2_THREADS) {
+            const long long r = i / F; const int s = (int)(i - r * F);
+            const bool in = (i >= scalar_len) && (i < new_points - scalar_len);
+            const T* t = tab + (in ? 0 : F * J) + s * J;
+            long long g = (r - L - 1) % N; if (g < 0) g += N;
+            X acc = X();
+            for (int j = 0; j < J; j++) {
+                const X xv = reinterpret_cast<const X*>(x_)[g];
+                if constexpr (CPLX) { acc.x += xv.x * t[j]; acc.y += xv.y * t[j]; } else acc += xv * t[j];
+                g++; if (g >= N) g -= N;
+            }
+            reinterpret_cast<X*>(y_)[i] = acc;
+        }
+        return;
+    }
+    for (int i = threadIdx.x; i < J * FMAX; i += IP2_THREADS) {
+        const int j = i / FMAX, s = i - j * FMAX;
+        stab[i] = s < F ? tab[s * J + j] : (T)0;
+    }
+    const int W = POS + J - 1;
+    {
+        long long g = r0 - L - 1 + threadIdx.x;               // interior: no wrap-around
+        for (int w = threadIdx.x; w < W; w += IP2_THREADS) {
+            sx[ip_skew(w)] = reinterpret_cast<const X*>(x_)[g];
+            g += IP2_THREADS;
+        }
+    }
+    __syncthreads();
+    X acc[RP][FMAX];
+#pragma unroll
+    for (int p = 0; p < RP; p++)
+#pragma unroll
+        for (int s = 0; s < FMAX; s++) acc[p][s] = X();
+    const int base = threadIdx.x * RP;
+    X win[RP];                                                 // win[(j + p) % RP] = window[base + j + p]
+#pragma unroll
+    for (int p = 0; p < RP; p++) win[p] = sx[ip_skew(base + p)];
+    for (int jb = 0; jb < J; jb += RP) {
+#pragma unroll
+        for (int jj = 0; jj < RP; jj++) {
+            const int j = jb + jj;
+            if (j < J) {
+                T tp[FMAX];
+#pragma unroll
+                for (int s = 0; s < FMAX; s++) tp[s] = stab[j * FMAX + s];
+#pragma unroll
+                for (int p = 0; p < RP; p++) {
+                    const X xv = win[(jj + p) % RP];
+                    if constexpr (std::is_same<T, float>::value && !CPLX) {
+                        // packed FP32x2: two phases per FFMA2 (scalar 3-register FFMA issues at ~0.55/clk/SMSP on sm_100)
+                        const float2 xx = make_float2(xv, xv);
+#pragma unroll
+                        for (int s = 0; s < FMAX; s += 2) {
+                            const float2 r = __ffma2_rn(xx, make_float2(tp[s], tp[s + 1]), make_float2(acc[p][s], acc[p][s + 1]));
+                            acc[p][s] = r.x; acc[p][s + 1] = r.y;
+                        }
+                    } else if constexpr (std::is_same<T, float>::value && CPLX) {
+#pragma unroll
+                        for (int s = 0; s < FMAX; s++) acc[p][s] = __ffma2_rn(xv, make_float2(tp[s], tp[s]), acc[p][s]);
+                    } else {
+#pragma unroll
+                        for (int s = 0; s < FMAX; s++) {
+                            if constexpr (CPLX) { acc[p][s].x += xv.x * tp[s]; acc[p][s].y += xv.y * tp[s]; }
+                            else acc[p][s] += xv * tp[s];
+                        }
+                    }
+                }
+                win[jj] = sx[ip_skew(base + j + RP)];
+            }
+        }
+    }
+    // stage the RP*F results of every thread in shared memory (padded rows) and write them out with
+    // fully coalesced stores: consecutive threads -> consecutive outputs
+    __syncthreads();
+    X* so = reinterpret_cast<X*>(smem_raw);
+    constexpr int ROW = RP * FMAX + 4;
+#pragma unroll
+    for (int p = 0; p < RP; p++)
+#pragma unroll
+        for (int s = 0; s < FMAX; s++)
+            if (s < F) so[threadIdx.x * ROW + p * F + s] = acc[p][s];
+    __syncthreads();
+    const int per_thread = RP * F;
+    const int total = POS * F;
+    X* yo = reinterpret_cast<X*>(y_) + r0 * F;
+    for (int o = threadIdx.x; o < total; o += IP2_THREADS) {
+        const int tt = o / per_thread, e = o - tt * per_thread;
+        yo[o] = so[tt * ROW + e];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Real f32, F <= 4 (BASELINE config C4a): 8 positions x 4 phases per thread, everything packed FP32x2.
+// The input window is stored DUPLICATED ({x, x} pairs) so that one 64-bit shared load yields the splat
+// operand of FFMA2 without a MOV; per tap and thread: 1 LDS.128 (4 taps, warp-uniform) + 1 LDS.64 +
+// 16 FFMA2 for 32 outputs.
+// ------------------------------------------------------------------------------------------
+#define IPF_RP 8
+#define IPF_POS (IP2_THREADS * IPF_RP)
+#define IPF_ROW 34   // staging row stride in floats (17 x 8 B: conflict-free 64-bit stores)
+__device__ __forceinline__ int ipf_skew(int i) { return i + (i >> 3); }
+
+__global__ void __launch_bounds__(IP2_THREADS, 4)
+interp_poly_f32_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ tab, long long N,
+                       long long new_points, int F, int L, long long scalar_len) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int J = 2 * L + 3;
+    const int JI = 2 * L + 2;                                  // the last window slot has no interior tap
+    float4* stab = reinterpret_cast<float4*>(smem_raw);        // interior taps, [J] x {s0, s1, s2, s3}
+    float2* sxx = reinterpret_cast<float2*>(stab + J);         // duplicated window
+    const long long r0 = (long long)blockIdx.x * IPF_POS;
+    const bool interior = (r0 * F >= scalar_len) && ((r0 + IPF_POS) * F <= new_points - scalar_len);
+    if (!interior) {
+        for (long long i = r0 * F + threadIdx.x; i < (r0 + IPF_POS) * F && i < new_points; i += IP2_THREADS) {
+            const long long r = i / F; const int s = (int)(i - r * F);
+            const bool in = (i >= scalar_len) && (i < new_points - scalar_len);
+            const float* t = tab + (in ? 0 : F * J) + s * J;
+            long long g = (r - L - 1) % N; if (g < 0) g += N;
+            float acc = 0.f;
+            for (int j = 0; j < J; j++) {
+                acc += x[g] * t[j];
+                g++; if (g >= N) g -= N;
+            }
+            y[i] = acc;
+        }
+        return;
+    }
+    for (int j = threadIdx.x; j < J; j += IP2_THREADS) {
+        float4 t4;
+        t4.x = tab[j];
+        t4.y = F > 1 ? tab[J + j] : 0.f;
+        t4.z = F > 2 ? tab[2 * J + j] : 0.f;
+        t4.w = F > 3 ? tab[3 * J + j] : 0.f;
+        stab[j] = t4;
+    }
+    const int W = IPF_POS + JI - 1 + IPF_RP;
+    {
+        const float* xs = x + (r0 - L - 1);
+        for (int w = threadIdx.x; w < W; w += IP2_THREADS) {
+            const float v = xs[w];
+            sxx[ipf_skew(w)] = make_float2(v, v);
+        }
+    }
+    __syncthreads();
+    float2 acc[IPF_RP][2];
+#pragma unroll
+    for (int p = 0; p < IPF_RP; p++) { acc[p][0] = make_float2(0.f, 0.f); acc[p][1] = make_float2(0.f, 0.f); }
+    const int base = threadIdx.x * IPF_RP;
+    float2 win[IPF_RP];
+#pragma unroll
+    for (int p = 0; p < IPF_RP; p++) win[p] = sxx[ipf_skew(base + p)];
+    for (int jb = 0; jb < JI; jb += IPF_RP) {
+#pragma unroll
+        for (int jj = 0; jj < IPF_RP; jj++) {
+            const int j = jb + jj;
+            if (j < JI) {
+                const float4 t4 = stab[j];
+                const float2 ta = make_float2(t4.x, t4.y), tb = make_float2(t4.z, t4.w);
+#pragma unroll
+                for (int p = 0; p < IPF_RP; p++) {
+                    const float2 xx = win[(jj + p) % IPF_RP];
+                    acc[p][0] = __ffma2_rn(xx, ta, acc[p][0]);
+                    acc[p][1] = __ffma2_rn(xx, tb, acc[p][1]);
+                }
+                win[jj] = sxx[ipf_skew(base + j + IPF_RP)];
+            }
+        }
+    }
+    __syncthreads();
+    float* so = reinterpret_cast<float*>(smem_raw);
+    if (F == 4) {
+#pragma unroll
+        for (int p = 0; p < IPF_RP; p++) {
+            *reinterpret_cast<float2*>(so + threadIdx.x * IPF_ROW + 4 * p) = acc[p][0];
+            *reinterpret_cast<float2*>(so + threadIdx.x * IPF_ROW + 4 * p + 2) = acc[p][1];
+        }
+    } else {
+#pragma unroll
+        for (int p = 0; p < IPF_RP; p++) {
+            const float a4[4] = {acc[p][0].x, acc[p][0].y, acc[p][1].x, acc[p][1].y};
+#pragma unroll
+            for (int s = 0; s < 4; s++)
+                if (s < F) so[threadIdx.x * IPF_ROW + p * F + s] = a4[s];
+        }
+    }
+    __syncthreads();
+    float* yo = y + r0 * F;
+    if (F == 4) {   // 32 outputs per staging row: no integer division in the copy-out loop
+#pragma unroll 8
+        for (int o = threadIdx.x; o < IPF_POS * 4; o += IP2_THREADS) yo[o] = so[(o >> 5) * IPF_ROW + (o & 31)];
+    } else {
+        const int per_thread = IPF_RP * F;
+        const int total = IPF_POS * F;
+        for (int o = threadIdx.x; o < total; o += IP2_THREADS) {
+            const int tt = o / per_thread, e = o - tt * per_thread;
+            yo[o] = so[tt * IPF_ROW + e];
+        }
+    }
+}
+
 template <typename T>
 int interp_poly(const void* x, void* y, const T* tab_dev, size_t N, size_t new_points, int F, int L, int is_complex,
                 cudaStream_t st) {
@@ -101,18 +326,37 @@ int interp_poly(const void* x, void* y, const T* tab_dev, size_t N, size_t new_p
     const int J = 2 * L + 3;
     if (F <= 8) {
         const size_t xs = is_complex ? sizeof(C) : sizeof(T);
-        const size_t tab_pad = ((size_t)2 * F * J + 3) & ~(size_t)3;
-        const size_t smem = tab_pad * sizeof(T) + (IP_THREADS + J) * xs;
         const long long rows = ((long long)new_points + F - 1) / F;
-        const long long grid = (rows + IP_THREADS - 1) / IP_THREADS;
-#define BDSP_IP(CP, FM)                                                                                              \
-    do {                                                                                                             \
-        if (smem > 48 * 1024) BDSP_CUDA_OK(cudaFuncSetAttribute(interp_poly_kernel<T, CP, FM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        interp_poly_kernel<T, CP, FM><<<(unsigned)grid, IP_THREADS, smem, st>>>(x, y, tab_dev, (long long)N, (long long)new_points, F, L, scalar_len); \
+#define BDSP_IP2(CP, FM, RPV)                                                                                          \
+    do {                                                                                                               \
+        const int pos = IP2_THREADS * RPV;                                                                             \
+        const size_t wlen = (size_t)pos + J + RPV + 1;                                                                 \
+        size_t smem = (((size_t)J * FM + 3) & ~(size_t)3) * sizeof(T) + (wlen + wlen / 32 + 2) * xs;                   \
+        const size_t stage = (size_t)IP2_THREADS * (RPV * FM + 4) * xs;                                                \
+        if (smem < stage) smem = stage;                                                                                \
+        const long long grid = (rows + pos - 1) / pos;                                                                 \
+        if (smem > 48 * 1024) BDSP_CUDA_OK(cudaFuncSetAttribute(interp_poly_tiled_kernel<T, CP, FM, RPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        interp_poly_tiled_kernel<T, CP, FM, RPV><<<(unsigned)grid, IP2_THREADS, smem, st>>>(x, y, tab_dev, (long long)N, (long long)new_points, F, L, scalar_len); \
     } while (0)
-        if (is_complex) { if (F <= 4) BDSP_IP(true, 4); else BDSP_IP(true, 8); }
-        else { if (F <= 4) BDSP_IP(false, 4); else BDSP_IP(false, 8); }
-#undef BDSP_IP
+        if (is_complex) { if (F <= 4) BDSP_IP2(true, 4, 2); else BDSP_IP2(true, 8, 1); }
+        else if (F <= 4 && sizeof(T) == 4) {
+            const size_t wlen = (size_t)IPF_POS + J + 2 * IPF_RP;
+            size_t smem = (size_t)J * 16 + (wlen + wlen / 8 + 2) * 8;
+            const size_t stage = (size_t)IP2_THREADS * IPF_ROW * 4;
+            if (smem < stage) smem = stage;
+            const long long grid = (rows + IPF_POS - 1) / IPF_POS;
+            static bool configured = false;
+            if (!configured) {
+                BDSP_CUDA_OK(cudaFuncSetAttribute(interp_poly_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024)));
+                BDSP_CUDA_OK(cudaFuncSetAttribute(interp_poly_f32_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                configured = true;
+            }
+            interp_poly_f32_kernel<<<(unsigned)grid, IP2_THREADS, smem, st>>>(reinterpret_cast<const float*>(x), reinterpret_cast<float*>(y),
+                                                                              reinterpret_cast<const float*>(tab_dev), (long long)N,
+                                                                              (long long)new_points, F, L, scalar_len);
+        }
+        else { if (F <= 4) BDSP_IP2(false, 4, 4); else BDSP_IP2(false, 8, 2); }
+#undef BDSP_IP2
     } else {
         const long long grid = ((long long)new_points + 255) / 256;
         if (is_complex) interp_poly_generic_kernel<T, true><<<(unsigned)grid, 256, 0, st>>>(x, y, tab_dev, (long long)N, (long long)new_points, F, L, scalar_len);
