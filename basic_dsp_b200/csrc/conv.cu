@@ -6,6 +6,8 @@
 //  convolve_iteration, time_freq/mod.rs:456-473).  They replace the reference's overlap_discard
 // (convolution.rs:304-461), its SIMD FIR (time_freq/mod.rs:531-610) and its OpenCL kernels
 // conv_vecs_r/conv_vecs_c/multiply_vector (gpu_support/ocl/ocl_kernels32.rs).
+#include <type_traits>
+
 #include "conv.cuh"
 #include "fft.cuh"
 #include "fft_core.cuh"
@@ -175,7 +177,7 @@ fir_kernel(const void* __restrict__ x_, void* __restrict__ y_, const void* __res
     for (int k = threadIdx.x; k < L; k += FIR_THREADS) {
         C t;
         if (HC) t = reinterpret_cast<const C*>(h_)[k];
-        else { t.x = reinterpret_cast<const T*>(h_)[k]; t.y = 0; }
+        else { t.x = reinterpret_cast<const T*>(h_)[k]; t.y = (sizeof(T) == 4 && XC) ? t.x : (T)0; }   // f32: {t, t} splat for FFMA2
         sh[k] = t;
     }
     {
@@ -206,7 +208,9 @@ fir_kernel(const void* __restrict__ x_, void* __restrict__ y_, const void* __res
 #pragma unroll
                 for (int u = 0; u < FIR_U; u++) {
                     const C xv = r[(oo + u) % FIR_U];
-                    if (HC) {
+                    if constexpr (std::is_same<T, float>::value && XC && !HC) {
+                        acc[u] = __ffma2_rn(xv, t, acc[u]);   // {re, im} * {t, t} + acc: one packed instruction per tap
+                    } else if (HC) {
                         acc[u].x += xv.x * t.x - xv.y * t.y;
                         acc[u].y += xv.x * t.y + xv.y * t.x;
                     } else {
@@ -218,12 +222,17 @@ fir_kernel(const void* __restrict__ x_, void* __restrict__ y_, const void* __res
             }
         }
     }
+    // stage the 8 consecutive outputs of every thread in (skewed) shared memory and copy out coalesced
+    __syncthreads();
 #pragma unroll
-    for (int u = 0; u < FIR_U; u++) {
-        long long i = i0 + u0 + u;
+    for (int u = 0; u < FIR_U; u++) sx[fpad(u0 + u)] = acc[u];
+    __syncthreads();
+    for (int o = threadIdx.x; o < FIR_TILE; o += FIR_THREADS) {
+        const long long i = i0 + o;
         if (i < N) {
-            if (XC) reinterpret_cast<C*>(y_)[vec * N + i] = acc[u];
-            else reinterpret_cast<T*>(y_)[vec * N + i] = acc[u].x;
+            const C v = sx[fpad(o)];
+            if (XC) reinterpret_cast<C*>(y_)[vec * N + i] = v;
+            else reinterpret_cast<T*>(y_)[vec * N + i] = v.x;
         }
     }
 }

@@ -113,6 +113,7 @@ __device__ __forceinline__ long long out_addr(const OutMap& m, long long b, long
 }
 
 template <typename T> __device__ __forceinline__ T mag_of(T re, T im) { return sqrt(re * re + im * im); }
+__device__ __forceinline__ int spad_host_dev(int n) { return n + (n >> 4) + 1; }
 
 // ------------------------------------------------------------------------------------------
 // single-CTA kernel: nfft sequences of n = 2^log2n points per CTA
@@ -227,6 +228,26 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? 1024 : 512) fft_tile_kernel(T
         else if (rem == 1) stockham_stage_strided<T, 2, INV, 8>(s, n, ct, sstride, Ns, tw);
     }
     // ---- twiddle + store ----
+    // W_{tw_n}^{lane*k} = A[l][k & 31] * B[l][k >> 5] with A[l][a] = W^{lane*a}, B[l][b] = W^{lane*32*b}:
+    // ct*(32 + m/32) exactly reduced roots per tile (sincospi) instead of one per element.
+    C* twA = s + spad_host_dev((m + 16) * ct);
+    C* twB = twA + ct * 32;
+    const int nb = (m + 31) >> 5;
+    if (p.tw_n) {
+        for (int i = threadIdx.x; i < ct * (32 + nb); i += blockDim.x) {
+            const bool isB = i >= ct * 32;
+            const int ii = isB ? i - ct * 32 : i;
+            const int l = isB ? ii / nb : ii >> 5;
+            const int e = isB ? ii - l * nb : ii & 31;
+            const unsigned long long lane = (unsigned long long)(lane0 + l);
+            const unsigned long long mul = isB ? 32ull * (unsigned long long)e : (unsigned long long)e;
+            // lane < tw_n <= 2^40 and mul < 2^15: reduce lane*mul without overflow
+            const unsigned long long num = ((lane % (unsigned long long)p.tw_n) * mul) % (unsigned long long)p.tw_n;
+            const C w = unit_root<T>(num, (unsigned long long)p.tw_n, INV ? 1 : -1);
+            if (isB) twB[l * nb + e] = w; else twA[l * 32 + e] = w;
+        }
+        __syncthreads();
+    }
     const bool lane_major = (p.out_lane_stride <= p.out_point_stride);
     const int lct = __ffs(ct) - 1;
     for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
@@ -236,7 +257,7 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? 1024 : 512) fft_tile_kernel(T
         C v = s[spad(l * sstride + k)];
         const long long lane = lane0 + l;
         if (p.tw_n) {
-            C w = unit_root<T>((unsigned long long)lane * (unsigned long long)k, (unsigned long long)p.tw_n, INV ? 1 : -1);
+            const C w = cmul(twA[l * 32 + (k & 31)], twB[l * nb + (k >> 5)]);
             v = cmul(v, w);
         }
         long long local = o1 * p.out_o1_stride + lane * p.out_lane_stride + (long long)k * p.out_point_stride;
@@ -262,21 +283,49 @@ __global__ void dft_q_pass_kernel(const void* __restrict__ in_, typename CpxOf<T
     if (gid >= P * batch) return;
     const long long b = gid / P, n2 = gid - b * P;
     const int sign = INV ? 1 : -1;
+    C xin[31], wq[31];   // q <= 31
+    for (int n1 = 0; n1 < q; n1++) {
+        long long g = (long long)n1 * P + n2 + in_rot;
+        if (g >= n) g -= n;
+        C v;
+        if (real_input) { v.x = reinterpret_cast<const T*>(in_)[b * n + g]; v.y = 0; }
+        else v = reinterpret_cast<const C*>(in_)[b * n + g];
+        xin[n1] = v;
+        wq[n1] = unit_root<T>((unsigned long long)n1, (unsigned long long)q, sign);
+    }
+    const C w1 = unit_root<T>((unsigned long long)n2, (unsigned long long)n, sign);   // W_n^{n2}
+    C wk = mk<T>(1, 0);                                                                // W_n^{n2*k1}
     for (int k1 = 0; k1 < q; k1++) {
-        C acc = mk<T>(0, 0);
-        for (int n1 = 0; n1 < q; n1++) {
-            long long g = (long long)n1 * P + n2 + in_rot;
-            if (g >= n) g -= n;
-            C v;
-            if (real_input) { v.x = reinterpret_cast<const T*>(in_)[b * n + g]; v.y = 0; }
-            else v = reinterpret_cast<const C*>(in_)[b * n + g];
-            C w = unit_root<T>((unsigned long long)((n1 * k1) % q), (unsigned long long)q, sign);
-            acc = cadd(acc, cmul(v, w));
+        C acc = xin[0];
+        int e = 0;
+        for (int n1 = 1; n1 < q; n1++) {
+            e += k1; if (e >= q) e -= q;          // (n1*k1) mod q
+            acc = cadd(acc, cmul(xin[n1], wq[e]));
         }
-        C w = unit_root<T>((unsigned long long)n2 * (unsigned long long)k1, (unsigned long long)n, sign);
-        acc = cmul(acc, w);
+        acc = cmul(acc, wk);
         acc.x *= scale; acc.y *= scale;
         out[b * n + (long long)k1 * P + n2] = acc;
+        wk = cmul(wk, w1);
+    }
+}
+
+// out[b*n + ((k1 + q*k2 + rot) mod n)] = z[(b*q + k1)*P + k2]: the index interleave that follows the q
+// row transforms of a q*2^k transform.  A separate, fully coalesced pass: folding it into the strided
+// stores of the last tile pass made every 32-byte sector be written q times (read-modify-write in DRAM).
+template <typename T>
+__global__ void interleave_q_kernel(const typename CpxOf<T>::type* __restrict__ z, void* __restrict__ out_, int q, long long P,
+                                    long long batch, long long rot, int magnitude) {
+    typedef typename CpxOf<T>::type C;
+    const long long n = (long long)q * P;
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= P * batch) return;
+    const long long b = gid / P, k2 = gid - b * P;
+    for (int k1 = 0; k1 < q; k1++) {
+        const C v = z[(b * q + k1) * P + k2];
+        long long k = k1 + (long long)q * k2 + rot;
+        if (k >= n) k -= n;
+        if (magnitude) reinterpret_cast<T*>(out_)[b * n + k] = mag_of(v.x, v.y);
+        else reinterpret_cast<C*>(out_)[b * n + k] = v;
     }
 }
 
@@ -387,7 +436,7 @@ template <typename T, bool INV>
 int launch_tile(const TileParams& p, long long batch, T scale, cudaStream_t st) {
     typedef typename CpxOf<T>::type C;
     const int m = 1 << p.log2m;
-    const size_t smem = spad_host((size_t)(m + 16) * p.ct) * sizeof(C);
+    const size_t smem = (spad_host((size_t)(m + 16) * p.ct) + (size_t)p.ct * (32 + ((m + 31) >> 5))) * sizeof(C);
     int threads = block_fft_threads(m, p.ct);
     const long long grid = batch * p.o1_count * (p.lanes / p.ct);
     int rc = set_smem(fft_tile_kernel<T, INV>, smem);
@@ -398,6 +447,8 @@ int launch_tile(const TileParams& p, long long batch, T scale, cudaStream_t st) 
 }
 
 template <typename T> int tile_log2m_max() { return sizeof(T) == 4 ? 10 : 9; }
+// lanes per tile: 128 contiguous bytes per row segment (f32: 16, f64: 8) -> 72 KB tiles, 3 CTAs per SM
+template <typename T> long long tile_lanes() { return sizeof(T) == 4 ? 16 : 8; }
 
 // power-of-two transform of `batch` sequences; handles any supported size
 template <typename T, bool INV>
@@ -416,7 +467,7 @@ int fft_pow2(const void* in, void* out, size_t n, size_t batch, bool real_in, bo
     TileParams p;
     // pass A: columns of length n1, stride n/n1, lanes contiguous
     p.in = in; p.out = tmp; p.log2m = l[0];
-    p.lanes = (long long)n / n1; p.ct = (int)(p.lanes < 16 ? p.lanes : 16); p.o1_count = 1;
+    p.lanes = (long long)n / n1; p.ct = (int)(p.lanes < tile_lanes<T>() ? p.lanes : tile_lanes<T>()); p.o1_count = 1;
     p.in_lane_stride = 1; p.in_point_stride = (long long)n / n1; p.in_o1_stride = 0; p.in_batch_stride = (long long)n;
     p.out_lane_stride = 1; p.out_point_stride = (long long)n / n1; p.out_o1_stride = 0; p.out_batch_stride = (long long)n;
     p.tw_n = (long long)n; p.in_rot = in_rot; p.in_n = (long long)n; p.real_input = real_in; p.last = 0; p.magnitude = 0;
@@ -426,7 +477,7 @@ int fft_pow2(const void* in, void* out, size_t n, size_t batch, bool real_in, bo
     if (npass == 3) {
         // pass B: inside every row k1: columns of length n2, stride n3, in place
         p.in = tmp; p.out = tmp; p.log2m = l[1];
-        p.lanes = n3; p.ct = (int)(n3 < 16 ? n3 : 16); p.o1_count = n1;
+        p.lanes = n3; p.ct = (int)(n3 < tile_lanes<T>() ? n3 : tile_lanes<T>()); p.o1_count = n1;
         p.in_lane_stride = 1; p.in_point_stride = n3; p.in_o1_stride = n2 * n3;
         p.out_lane_stride = 1; p.out_point_stride = n3; p.out_o1_stride = n2 * n3;
         p.tw_n = n2 * n3; p.in_rot = 0; p.real_input = 0;
@@ -436,7 +487,7 @@ int fft_pow2(const void* in, void* out, size_t n, size_t batch, bool real_in, bo
     // last pass: rows of length nl (contiguous), lanes = k1 (stride n/n1), transposing store
     const long long nl = npass == 3 ? n3 : n2;
     p.in = tmp; p.out = out; p.log2m = npass == 3 ? l[2] : l[1];
-    p.lanes = n1; p.ct = (int)(n1 < 16 ? n1 : 16);
+    p.lanes = n1; p.ct = (int)(n1 < tile_lanes<T>() ? n1 : tile_lanes<T>());
     p.o1_count = npass == 3 ? n2 : 1;
     p.in_lane_stride = (long long)n / n1; p.in_point_stride = 1; p.in_o1_stride = npass == 3 ? nl : 0;
     p.out_lane_stride = 1; p.out_point_stride = npass == 3 ? n1 * n2 : n1; p.out_o1_stride = npass == 3 ? n1 : 0;
@@ -490,9 +541,18 @@ int fft_any(const void* in, void* out, size_t n, size_t batch, const FftOpts& o,
         OutMap om2;
         om2.seq_group = (long long)q; om2.oes = (long long)q; om2.group_stride = (long long)n;
         om2.rot = om.rot; om2.rot_n = (long long)n;
-        void* w0 = nullptr;
-        if (P > fft_block_max_n<T>()) w0 = workspace(need, 0);
-        return fft_pow2<T, INV>(w1, out, P, batch * q, false, o.magnitude, 0, (T)1, om2, w0, st);
+        if (P > fft_block_max_n<T>()) {
+            // multi-pass row transforms: natural-order rows into a second buffer, then one interleave pass
+            void* w0 = workspace(need, 0);
+            C* w2 = reinterpret_cast<C*>(workspace(need, 2));
+            OutMap plainP; plainP.seq_group = 1; plainP.oes = 1; plainP.group_stride = (long long)P; plainP.rot = 0; plainP.rot_n = (long long)P;
+            int rc = fft_pow2<T, INV>(w1, w2, P, batch * q, false, false, 0, (T)1, plainP, w0, st);
+            if (rc) return rc;
+            interleave_q_kernel<T><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(w2, out, (int)q, (long long)P, (long long)batch, om.rot, o.magnitude);
+            BDSP_LAUNCHED();
+            return 0;
+        }
+        return fft_pow2<T, INV>(w1, out, P, batch * q, false, o.magnitude, 0, (T)1, om2, nullptr, st);
     }
     // Bluestein
     if (n >= (1ull << 31)) { set_last_error("fft: length %zu not supported", n); return -2; }

@@ -126,11 +126,31 @@ __device__ __forceinline__ void stockham_stage_strided(typename CpxOf<T>::type* 
 #pragma unroll
             for (int r = 0; r < R; r++) v[b][r] = src[spad(base + r * bpf)];
             if (Ns > 1) {
+                // one table load (W^k) per butterfly; the powers W^{k r} are products A_a * B_b, r = a + 4b
+                // (depth <= 4).  R - 1 scattered table loads per butterfly made this stage L1-bound.
+                C w1 = __ldg(&tw[k * tw_scale]);
+                if (INV) w1.y = -w1.y;
+                if (R <= 4) {
+                    C w = w1;
 #pragma unroll
-                for (int r = 1; r < R; r++) {
-                    C t = __ldg(&tw[(k * r) * tw_scale]);
-                    if (INV) t.y = -t.y;
-                    v[b][r] = cmul(v[b][r], t);
+                    for (int r = 1; r < R; r++) {
+                        v[b][r] = cmul(v[b][r], w);
+                        if (r + 1 < R) w = cmul(w, w1);
+                    }
+                } else {
+                    C A[4], B[4];
+                    A[1] = w1; A[2] = cmul(w1, w1); A[3] = cmul(A[2], w1);
+                    B[1] = cmul(A[2], A[2]);
+                    if (R > 8) { B[2] = cmul(B[1], B[1]); B[3] = cmul(B[2], B[1]); }
+#pragma unroll
+                    for (int r = 1; r < R; r++) {
+                        const int a = r & 3, bb = r >> 2;
+                        C w;
+                        if (bb == 0) w = A[a];
+                        else if (a == 0) w = B[bb];
+                        else w = cmul(A[a], B[bb]);
+                        v[b][r] = cmul(v[b][r], w);
+                    }
                 }
             }
             RegFFT<T, R, INV>::run(v[b]);
