@@ -105,6 +105,12 @@ def _declare(lib):
         }
         for name in ("add", "sub", "div", "mul", "add_vector", "sub_vector", "div_vector", "mul_vector"):
             protos[name] = (_VecResult, [H, H])
+        for name in ("apply_window", "unapply_window", "windowed_fft", "windowed_ifft"):
+            protos[name] = (_VecResult, [H, c_int32])
+        protos["correlate"] = (_VecResult, [H, H])
+        protos["decimatei"] = (_VecResult, [H, ctypes.c_uint32, ctypes.c_uint32])
+        for name in ("prepare_argument", "prepare_argument_padded", "reverse"):
+            protos[name] = (_VecResult, [H])
         for name in ("conj", "to_complex", "magnitude", "magnitude_squared", "phase", "to_real", "to_imag",
                      "plain_fft", "plain_ifft", "fft", "ifft", "swap_halves", "fft_shift", "ifft_shift"):
             protos[name] = (_VecResult, [H])
@@ -400,6 +406,34 @@ class DspVec:
 
     def interpolate_lin(self, factor, delay):
         return self._call("interpolate_lin", factor, delay)
+
+    # -- next rows: TimeDomainOperations, CrossCorrelation*Ops, reverse, decimatei ----------------------
+    def apply_window(self, window):
+        return self._call("apply_window", window)
+
+    def unapply_window(self, window):
+        return self._call("unapply_window", window)
+
+    def windowed_fft(self, window):
+        return self._call("windowed_fft", window)
+
+    def windowed_ifft(self, window):
+        return self._call("windowed_ifft", window)
+
+    def prepare_argument(self):
+        return self._call("prepare_argument")
+
+    def prepare_argument_padded(self):
+        return self._call("prepare_argument_padded")
+
+    def correlate(self, prepared):
+        return self._call("correlate", prepared._h)
+
+    def reverse(self):
+        return self._call("reverse")
+
+    def decimatei(self, factor, delay):
+        return self._call("decimatei", factor, delay)
 
     # -- ScaleOps / OffsetOps / ElementaryOps -----------------------------------------------------------------
     def scale(self, c):

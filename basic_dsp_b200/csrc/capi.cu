@@ -533,6 +533,114 @@ Res<T> op_mul_freq_resp_c(Vec<T>* v, CT (*fn)(const void*, T), const void* data,
     return done(v, rc);
 }
 
+// ---- windows, correlation, reverse, decimatei --------------------------------------
+template <typename T> T host_window(int kind, size_t n, size_t length) {
+    // window_functions.rs:25-129, interop translate_to_window_function (lib.rs:153-164)
+    const T one = 1, two = 2, pi = (T)M_PI;
+    const T nn = (T)n, ln = (T)length;
+    if (kind == 0) return one - (T)fabs((nn - (ln - one) / two) / (ln / two));
+    if (kind == 1) { const T alpha = (T)0.54; return alpha - (one - alpha) * (T)cos(two * pi * nn / (ln - one)); }
+    if (kind == 2)
+        return (T)0.35875 - (T)0.48829 * (T)cos(two * pi * nn / (ln - one)) + (T)0.14128 * (T)cos((T)4 * pi * nn / (ln - one)) -
+               (T)0.01168 * (T)cos((T)6 * pi * nn / (ln - one));
+    return one;
+}
+
+template <typename T> Res<T> op_window(Vec<T>* v, int kind, bool unapply) {
+    // time.rs:33-66 + multiply_window_priv (vector_types/mod.rs:528-598): symmetric windows evaluate the
+    // first half and mirror it
+    if (v->domain != 0) { mark_invalid(v); return done(v, 0); }
+    const size_t points = points_of(v);
+    if (!points) return done(v, 0);
+    std::vector<T> tab(points);
+    for (size_t i = 0; i < points; i++) {
+        const size_t j = i < (points + 1) / 2 ? i : points - 1 - i;
+        const T w = host_window<T>(kind, j, points);
+        tab[i] = unapply ? (T)1 / w : w;
+    }
+    T* dev = nullptr;
+    int rc = upload_table(tab, &dev);
+    if (!rc) rc = ew_mul_table<T>(v->d, dev, points, v->is_complex, 0, g_stream);
+    table_consumed();
+    return done(v, rc);
+}
+
+template <typename T> Res<T> op_windowed_fft(Vec<T>* v, int kind) {
+    Res<T> r = op_window(v, kind, false);
+    if (r.result_code) return r;
+    return op_fft(v, false, true, false);
+}
+template <typename T> Res<T> op_windowed_ifft(Vec<T>* v, int kind) {
+    Res<T> r = op_fft(v, true, true, false);
+    if (r.result_code) return r;
+    return op_window(v, kind, true);
+}
+
+template <typename T> Res<T> op_prepare_argument(Vec<T>* v, bool padded) {
+    // correlation.rs:96-117
+    if (!v->is_complex || v->domain != 0) { mark_invalid(v); v->is_complex = 1; v->domain = 1; return done(v, 0); }
+    if (padded) {
+        const size_t points = points_of(v);
+        if (points) {
+            Res<T> r = op_zero_pad(v, 2 * points - 1, 1);
+            if (r.result_code && points > 1) return r;
+        }
+    }
+    Res<T> r = op_fft(v, false, false, false);
+    if (r.result_code) return r;
+    return op_complex_const(v, EW_CONJ, (T)0, (T)0);
+}
+
+template <typename T> Res<T> op_correlate(Vec<T>* v, const Vec<T>* other) {
+    // correlation.rs:131-163
+    if (v->domain != 0 || !v->is_complex || other->domain != 1 || !other->is_complex) {
+        mark_invalid(v); v->is_complex = 1; v->domain = 1;
+        return done(v, E_TIME);
+    }
+    const size_t points = points_of(other);
+    const T delta = v->delta;
+    Res<T> r = op_zero_pad(v, points, 1);
+    if (r.result_code) return r;
+    FftOpts f;
+    int rc = ensure_scratch(v, v->len);
+    if (!rc) rc = fft_exec<T>(v->d, v->scratch, points, 1, f, nullptr, 0, g_stream);
+    if (!rc) rc = ew_binary<T>(EW_MUL, v->scratch, other->d, v->scratch, 2 * points, 1, g_stream);
+    if (rc) return done(v, rc);
+    // plain_ifft, then scale(1/points) and swap_halves fused into the transform's store
+    FftOpts inv;
+    inv.inverse = 1;
+    inv.out_rot = points / 2;
+    rc = fft_exec<T>(v->scratch, v->d, points, 1, inv, nullptr, 0, g_stream);
+    if (!rc) rc = ew_scalar<T>(EW_SCALE, v->d, v->d, 2 * points, (double)((T)1 / (T)points), g_stream);
+    v->delta = delta;
+    return done(v, rc);
+}
+
+template <typename T> Res<T> op_reverse(Vec<T>* v) {
+    const size_t n = points_of(v);
+    if (n < 2) return done(v, 0);
+    int rc = ensure_scratch(v, v->len);
+    if (!rc) rc = ew_reverse<T>(v->d, v->scratch, n, v->is_complex ? 2 : 1, g_stream);
+    if (rc) return done(v, rc);
+    trade(v);
+    return done(v, 0);
+}
+
+template <typename T> Res<T> op_decimatei(Vec<T>* v, uint32_t factor, uint32_t delay) {
+    const size_t n = points_of(v);
+    if (factor == 0) return done(v, E_ARG_LEN);
+    const size_t out = delay < n ? (n - delay + factor - 1) / factor : 0;
+    const int esz = v->is_complex ? 2 : 1;
+    if (out) {
+        int rc = ensure_scratch(v, out * esz);
+        if (!rc) rc = ew_decimate<T>(v->d, v->scratch, out, factor, delay, esz, g_stream);
+        if (rc) return done(v, rc);
+        trade(v);
+    }
+    v->len = out * esz;
+    return done(v, 0);
+}
+
 // ---- interpolation ---------------------------------------------------------------------------------
 template <typename T> Res<T> op_interpolatef(Vec<T>* v, const RealFn<T>& f, T factor, T delay, size_t conv_len) {
     // interpolation.rs:387-482
@@ -831,6 +939,15 @@ template <typename R, typename T> static inline R as_res(Res<T> r) {
         return as_res<RES>(op_interpolatef<T>(VEC(v), f, factor, delay, len));                                         \
     }                                                                                                                  \
     extern "C" RES interpolate_lin##S(HV* v, T factor, T delay) { return as_res<RES>(op_interpolate_lin(VEC(v), factor, delay)); } \
+    extern "C" RES apply_window##S(HV* v, int32_t w) { return as_res<RES>(op_window(VEC(v), w, false)); }              \
+    extern "C" RES unapply_window##S(HV* v, int32_t w) { return as_res<RES>(op_window(VEC(v), w, true)); }             \
+    extern "C" RES windowed_fft##S(HV* v, int32_t w) { return as_res<RES>(op_windowed_fft(VEC(v), w)); }               \
+    extern "C" RES windowed_ifft##S(HV* v, int32_t w) { return as_res<RES>(op_windowed_ifft(VEC(v), w)); }             \
+    extern "C" RES prepare_argument##S(HV* v) { return as_res<RES>(op_prepare_argument(VEC(v), false)); }              \
+    extern "C" RES prepare_argument_padded##S(HV* v) { return as_res<RES>(op_prepare_argument(VEC(v), true)); }        \
+    extern "C" RES correlate##S(HV* v, const HV* o) { return as_res<RES>(op_correlate(VEC(v), CVEC(o))); }             \
+    extern "C" RES reverse##S(HV* v) { return as_res<RES>(op_reverse(VEC(v))); }                                       \
+    extern "C" RES decimatei##S(HV* v, uint32_t f, uint32_t d) { return as_res<RES>(op_decimatei(VEC(v), f, d)); }     \
     extern "C" int32_t bdsp_upload##S(HV* v, const T* host, size_t len) { return upload(VEC(v), host, len); }          \
     extern "C" int32_t bdsp_download##S(const HV* v, T* host, size_t len) { return download(CVEC(v), host, len, true); } \
     extern "C" int32_t bdsp_download_async##S(const HV* v, T* host, size_t len) { return download(CVEC(v), host, len, false); } \

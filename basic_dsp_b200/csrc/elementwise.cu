@@ -189,6 +189,30 @@ __global__ void zero_interleave_kernel(const T* __restrict__ in, T* __restrict__
     }
 }
 
+// out[i] = in[n-1-i] for elements of esz scalars (ReorganizeDataOps::reverse, data_reorganization.rs:237-246)
+template <typename T>
+__global__ void reverse_kernel(const T* __restrict__ in, T* __restrict__ out, long long n_elems, int esz) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long total = n_elems * esz;
+    for (; i < total; i += stride) {
+        long long e = i / esz, c = i - e * esz;
+        out[(n_elems - 1 - e) * esz + c] = in[i];
+    }
+}
+
+// out[j] = in[delay + j*factor] (InterpolationOps::decimatei, interpolation.rs:606-632)
+template <typename T>
+__global__ void decimate_kernel(const T* __restrict__ in, T* __restrict__ out, long long out_elems, long long factor, long long delay, int esz) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long total = out_elems * esz;
+    for (; i < total; i += stride) {
+        long long e = i / esz, c = i - e * esz;
+        out[i] = in[(delay + e * factor) * esz + c];
+    }
+}
+
 template <typename T>
 __global__ void fill_kernel(T* __restrict__ out, long long n, T v) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -340,6 +364,18 @@ int ew_zero_interleave(const void* in, void* out, size_t n_elems, int factor, in
     return 0;
 }
 
+template <typename T> int ew_reverse(const void* in, void* out, size_t n_elems, int esz, cudaStream_t st) {
+    reverse_kernel<T><<<ew_grid((long long)(n_elems * esz), 256), 256, 0, st>>>(reinterpret_cast<const T*>(in), reinterpret_cast<T*>(out), (long long)n_elems, esz);
+    BDSP_LAUNCHED();
+    return 0;
+}
+
+template <typename T> int ew_decimate(const void* in, void* out, size_t out_elems, size_t factor, size_t delay, int esz, cudaStream_t st) {
+    decimate_kernel<T><<<ew_grid((long long)(out_elems * esz), 256), 256, 0, st>>>(reinterpret_cast<const T*>(in), reinterpret_cast<T*>(out), (long long)out_elems, (long long)factor, (long long)delay, esz);
+    BDSP_LAUNCHED();
+    return 0;
+}
+
 template <typename T> int ew_fill(void* out, size_t n, double v, cudaStream_t st) {
     fill_kernel<T><<<ew_grid((long long)n, 256), 256, 0, st>>>(reinterpret_cast<T*>(out), (long long)n, (T)v);
     BDSP_LAUNCHED();
@@ -370,6 +406,8 @@ int ew_mul_table(void* data, const void* table, size_t points, int is_complex, i
     template int ew_rotate<T>(const void*, void*, size_t, size_t, int, cudaStream_t);                     \
     template int ew_zero_interleave<T>(const void*, void*, size_t, int, int, cudaStream_t);               \
     template int ew_fill<T>(void*, size_t, double, cudaStream_t);                                         \
+    template int ew_reverse<T>(const void*, void*, size_t, int, cudaStream_t);                            \
+    template int ew_decimate<T>(const void*, void*, size_t, size_t, size_t, int, cudaStream_t);           \
     template int ew_mul_freq_resp<T>(void*, size_t, int, int, double, double, cudaStream_t);              \
     template int ew_mul_table<T>(void*, const void*, size_t, int, int, cudaStream_t);
 BDSP_INST(float)

@@ -18,6 +18,8 @@ int ew_scale_mul_mag_phase(void* v, const void* w, void* mag, void* phase, size_
 template <typename T> int ew_rotate(const void* in, void* out, size_t n_elems, size_t rot, int esz, cudaStream_t st);
 template <typename T> int ew_zero_interleave(const void* in, void* out, size_t n_elems, int factor, int esz, cudaStream_t st);
 template <typename T> int ew_fill(void* out, size_t n, double v, cudaStream_t st);
+template <typename T> int ew_reverse(const void* in, void* out, size_t n_elems, int esz, cudaStream_t st);
+template <typename T> int ew_decimate(const void* in, void* out, size_t out_elems, size_t factor, size_t delay, int esz, cudaStream_t st);
 template <typename T> int ew_mul_freq_resp(void* data, size_t points, int is_complex, int kind, double rolloff, double ratio, cudaStream_t st);
 template <typename T> int ew_mul_table(void* data, const void* table, size_t points, int is_complex, int table_complex, cudaStream_t st);
 

@@ -145,7 +145,27 @@ BdspVecResult32 interpolatef_custom32(BdspVec32* vector, BdspRealFn32 impulse_re
                                       uint8_t is_symmetric, float interpolation_factor, float delay, size_t len); /* :1308 */
 BdspVecResult32 interpolate_lin32(BdspVec32* vector, float interpolation_factor, float delay);             /* :1437 */
 
+/* ---- next rows of the scope table: windows, correlation ("preparation" API), reverse, decimatei --- */
+BdspVecResult32 apply_window32(BdspVec32* vector, int32_t window);       /* :980, 0 Triangular / 1 Hamming / 2 BlackmanHarris / else Rectangular */
+BdspVecResult32 unapply_window32(BdspVec32* vector, int32_t window);     /* :987 */
+BdspVecResult32 windowed_fft32(BdspVec32* vector, int32_t window);       /* :997 */
+BdspVecResult32 windowed_ifft32(BdspVec32* vector, int32_t window);      /* :1011 */
+BdspVecResult32 prepare_argument32(BdspVec32* vector);                   /* :1156 */
+BdspVecResult32 prepare_argument_padded32(BdspVec32* vector);            /* :1161 */
+BdspVecResult32 correlate32(BdspVec32* vector, const BdspVec32* other);  /* :1166 */
+BdspVecResult32 reverse32(BdspVec32* vector);                            /* :1142 */
+BdspVecResult32 decimatei32(BdspVec32* vector, uint32_t decimation_factor, uint32_t delay); /* :1147 */
+
 /* ---- f64 twins (interop/src/facade64.rs, same line numbers + 1) ------------------------------------------------ */
+BdspVecResult64 apply_window64(BdspVec64* vector, int32_t window);
+BdspVecResult64 unapply_window64(BdspVec64* vector, int32_t window);
+BdspVecResult64 windowed_fft64(BdspVec64* vector, int32_t window);
+BdspVecResult64 windowed_ifft64(BdspVec64* vector, int32_t window);
+BdspVecResult64 prepare_argument64(BdspVec64* vector);
+BdspVecResult64 prepare_argument_padded64(BdspVec64* vector);
+BdspVecResult64 correlate64(BdspVec64* vector, const BdspVec64* other);
+BdspVecResult64 reverse64(BdspVec64* vector);
+BdspVecResult64 decimatei64(BdspVec64* vector, uint32_t decimation_factor, uint32_t delay);
 BdspVec64* new64(int32_t is_complex, int32_t domain, double init_value, size_t length, double delta);
 BdspVec64* new_with_performance_options64(int32_t is_complex, int32_t domain, double init_value, size_t length, double delta, size_t core_limit);
 BdspVec64* new_with_detailed_performance_options64(int32_t is_complex, int32_t domain, double init_value, size_t length,

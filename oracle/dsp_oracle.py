@@ -562,6 +562,101 @@ def phase(x, dtype):
     return np.arctan2(x.imag, x.real).astype(dtype)
 
 
+# --------------------------------------------------------------------------------------------
+# windows, correlation ("preparation" API), reverse, decimatei
+# --------------------------------------------------------------------------------------------
+def window_value(kind, n, length, dtype):
+    """window_functions.rs:25-129; kind as in interop translate_to_window_function (lib.rs:153-164):
+    0 Triangular, 1 Hamming(0.54), 2 BlackmanHarris, else Rectangular.  Evaluated in precision T."""
+    T = _T(dtype)
+    one, two = T(1), T(2)
+    pi = T(math.pi)
+    nn, ln = T(n), T(length)
+    if kind == 0:
+        return T(one - abs((nn - (ln - one) / two) / (ln / two)))
+    if kind == 1:
+        alpha = T(0.54)
+        return T(alpha - (one - alpha) * np.cos(two * pi * nn / (ln - one)))
+    if kind == 2:
+        a0, a1, a2, a3 = T(0.35875), T(0.48829), T(0.14128), T(0.01168)
+        return T(a0 - a1 * np.cos(two * pi * nn / (ln - one)) + a2 * np.cos(T(4) * pi * nn / (ln - one))
+                 - a3 * np.cos(T(6) * pi * nn / (ln - one)))
+    return one
+
+
+def window_table(kind, points, dtype, unapply=False):
+    """multiply_window_priv for symmetric windows (vector_types/mod.rs:528-598): element i of the second
+    half is multiplied with the value computed for its mirror index points-1-i."""
+    T = _T(dtype)
+    tab = np.empty(points, dtype=dtype)
+    for i in range(points):
+        j = i if i < (points + 1) // 2 else points - 1 - i
+        w = window_value(kind, j, points, dtype)
+        tab[i] = T(1) / w if unapply else w
+    return tab
+
+
+def apply_window(x, kind, dtype, unapply=False):
+    """TimeDomainOperations::apply_window / unapply_window (time.rs:33-66)."""
+    x = np.asarray(x)
+    tab = window_table(kind, len(x), dtype, unapply)
+    if np.iscomplexobj(x):
+        ct = np.complex64 if dtype == np.float32 else np.complex128
+        xx = x.astype(ct)
+        return ((xx.real.astype(dtype) * tab).astype(dtype) + 1j * (xx.imag.astype(dtype) * tab).astype(dtype)).astype(ct)
+    return (x.astype(dtype) * tab).astype(dtype)
+
+
+def windowed_fft(x, kind, dtype):
+    """apply_window -> plain_fft -> fft_shift (time_to_freq.rs:167-175)."""
+    return fft(apply_window(x, kind, dtype))
+
+
+def windowed_ifft(X, kind, dtype):
+    """ifft -> unapply_window (freq_to_time.rs:170-177)."""
+    y = ifft(X)
+    tab = window_table(kind, len(y), dtype, unapply=True).astype(np.float64)
+    return y * tab
+
+
+def zero_pad_surround(x, points):
+    """zero_pad_b(.., PaddingOption::Surround) (data_reorganization.rs:426-439)."""
+    x = np.asarray(x)
+    diff = points - len(x)
+    right = diff // 2
+    left = diff - right
+    return np.concatenate([np.zeros(left, dtype=x.dtype), x, np.zeros(right, dtype=x.dtype)])
+
+
+def prepare_argument(b):
+    """plain_fft then conj (correlation.rs:96-103)."""
+    return np.conj(plain_fft(b))
+
+
+def prepare_argument_padded(b):
+    """zero_pad(2*points - 1, Surround) -> plain_fft -> conj (correlation.rs:105-117)."""
+    b = np.asarray(b).astype(np.complex128)
+    return np.conj(plain_fft(zero_pad_surround(b, 2 * len(b) - 1)))
+
+
+def correlate(a, prepared):
+    """CrossCorrelationOps::correlate (correlation.rs:131-163): zero_pad(other.points, Surround) ->
+    plain_fft -> mul(other) -> plain_ifft -> scale(1/points) -> swap_halves."""
+    a = np.asarray(a).astype(np.complex128)
+    p = len(prepared)
+    ap = zero_pad_surround(a, p)
+    return swap_halves(plain_ifft(plain_fft(ap) * np.asarray(prepared)) / p)
+
+
+def reverse(x):
+    return np.asarray(x)[::-1].copy()
+
+
+def decimatei(x, factor, delay):
+    """interpolation.rs:606-632: keeps points delay, delay+factor, ..."""
+    return np.asarray(x)[delay::factor].copy()
+
+
 def ulp_diff(a, b, dtype):
     """Distance in units in the last place of `dtype` between two real arrays."""
     a = np.asarray(a, dtype=dtype)

@@ -40,6 +40,13 @@ CASES = [
     ("interpolatef_delayed_sinc_test", "vector/src/vector_types/time_freq/interpolation.rs", "interpolatef_delayed_sinc_test", "expected"),
     ("linear_test", "vector/src/vector_types/time_freq/real_interpolation.rs", "linear_test", "expected"),
     ("fft_swap_x_test", "vector/src/vector_types/time_freq/mod.rs", "fft_swap_x_test", "expected"),
+    ("time_correlation_test_a", "vector/src/vector_types/time_freq/correlation.rs", "time_correlation_test", "mut a"),
+    ("time_correlation_test_b", "vector/src/vector_types/time_freq/correlation.rs", "time_correlation_test", "b"),
+    ("time_correlation_test_c", "vector/src/vector_types/time_freq/correlation.rs", "time_correlation_test", "c"),
+    ("time_correlation_test2_c", "vector/src/vector_types/time_freq/correlation.rs", "time_correlation_test2", "c"),
+    ("triangular_window32_test", "vector/src/window_functions.rs", "triangular_window32_test", "expected"),
+    ("hamming_window32_test", "vector/src/window_functions.rs", "hamming_window32_test", "expected"),
+    ("blackmanharris_window32_test", "vector/src/window_functions.rs", "blackmanharris_window32_test", "expected"),
 ]
 
 NUM = r"[-+]?(?:\d+\.\d*|\.\d+|\d+)(?:[eE][-+]?\d+)?"
@@ -52,7 +59,7 @@ def extract(path, fn, var):
         raise SystemExit("test fn %s not found in %s" % (fn, path))
     line = src.count("\n", 0, m.start()) + 1
     body = src[m.end():]
-    m2 = re.search(r"let\s+%s\s*(?::[^=]*)?=\s*&?\[" % re.escape(var), body)
+    m2 = re.search(r"let\s+%s\s*(?::[^=]*)?=\s*&?(?:vec!)?\[" % re.escape(var), body)
     if not m2:
         raise SystemExit("array %s not found in %s::%s" % (var, path, fn))
     start = m2.end()

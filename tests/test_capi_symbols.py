@@ -79,3 +79,25 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.replace("no CPU fallback", ""), os.path.join(dirpath, f)
+
+
+def _build_cpp(tmp_path, libpath):
+    exe = str(tmp_path / "host_mirror")
+    src = os.path.join(ROOT, "tests", "cpp", "host_mirror.cpp")
+    cmd = ["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
+           "-L", os.path.dirname(libpath), "-lbasic_dsp_b200", "-Wl,-rpath," + os.path.dirname(libpath)]
+    subprocess.check_call(cmd)
+    return exe
+
+
+def test_cpp_host_mirror_compiles_and_links(tmp_path, libpath):
+    exe = _build_cpp(tmp_path, libpath)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_host_mirror_runs_on_gpu(tmp_path, libpath):
+    exe = _build_cpp(tmp_path, libpath)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "roundtrip" in out.stdout, out.stdout + out.stderr

@@ -452,3 +452,84 @@ def test_zero_pad_and_interleave():
     c = np.array([1 + 2j, 3 + 4j], dtype=np.complex64)
     assert np.array_equal(DspVec(c).zero_interleave(2).to_numpy(), [1 + 2j, 0, 3 + 4j, 0])
     assert DspVec(x).result_code_of("zero_pad", 5, 0) == o.ERR_INVALID_ARG_LEN
+
+
+# --------------------------------------------------------------------------------------------------
+# next rows of the scope table: windows, correlation, reverse, decimatei
+# --------------------------------------------------------------------------------------------------
+def test_windowed_fft_golden(kats):  # tests/time_freq_test.rs:122-197
+    n = np.arange(64, dtype=np.float64)
+    x = np.cos(n * 0.1 * 2.0 * np.pi + 0.25)
+    got = DspVec(x, dtype=np.float64).to_complex().windowed_fft(1).magnitude().to_numpy()
+    assert np.max(np.abs(got - vals(kats, "windowed_fft_vector64"))) < 1e-6
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("kind", [0, 1, 2, 3])
+def test_apply_window_and_roundtrip(kind, dtype):
+    rng = np.random.default_rng(kind)
+    for n in (5, 64, 1001):
+        x = rand_c(rng, n, dtype)
+        got = DspVec(x).apply_window(kind).to_numpy()
+        ref = o.apply_window(x, kind, dtype)
+        # the window values are evaluated on the host with libm's cos in precision T (as the reference does);
+        # NumPy's float32 cos can differ by 1 ulp, which alpha - beta*cos(..) amplifies near the window edges
+        # (BlackmanHarris edge values ~6e-5 are the result of a 4-term cancellation), so the cosine windows are
+        # compared in the L2 sense and only the cos-free windows to 4 ulp
+        assert o.rel_l2(got, ref) <= (1e-6 if dtype == np.float32 else 1e-14)
+        r = rng.uniform(-10, 10, n).astype(dtype)
+        gr, rr = DspVec(r).apply_window(kind).to_numpy(), o.apply_window(r, kind, dtype)
+        assert o.rel_l2(gr, rr) <= (1e-6 if dtype == np.float32 else 1e-14)
+        if kind in (0, 3):
+            assert o.ulp_diff(got.real, ref.real, dtype).max() <= 4 and o.ulp_diff(got.imag, ref.imag, dtype).max() <= 4
+            assert o.ulp_diff(gr, rr, dtype).max() <= 4
+    x = rand_c(rng, 4096, dtype)
+    if kind != 0:   # the triangular window is fine too, but keep away from tiny edge values in f32
+        back = DspVec(x).windowed_fft(kind).windowed_ifft(kind).to_numpy()
+        assert o.rel_l2(back, x) <= 50 * tol(4096, dtype)
+    X = DspVec(x).windowed_fft(kind).to_numpy()
+    assert o.rel_l2(X, o.windowed_fft(x, kind, dtype)) <= tol(4096, dtype)
+
+
+def test_correlation_golden(kats):  # correlation.rs:170-215
+    a = cplx(kats["time_correlation_test_a"]["values"]).astype(np.complex64)
+    b = cplx(kats["time_correlation_test_b"]["values"]).astype(np.complex64)
+    c = vals(kats, "time_correlation_test_c")
+    prepared = DspVec(b).prepare_argument_padded()
+    assert prepared.domain() == bd.FREQ and prepared.points() == 2 * len(b) - 1
+    got = DspVec(a).correlate(prepared).to_numpy()
+    flat = np.empty(2 * len(got)); flat[0::2], flat[1::2] = got.real, got.imag
+    assert len(flat) == len(c) and np.max(np.abs(flat - c)) < 0.1
+    a2 = np.array([1 + 1j, 2 + 1j, 3 + 1j], dtype=np.complex64)
+    b2 = np.array([4 + 1j, 5 + 1j, 6 + 1j], dtype=np.complex64)
+    got = DspVec(a2).correlate(DspVec(b2).prepare_argument_padded()).to_numpy()
+    flat = np.empty(2 * len(got)); flat[0::2], flat[1::2] = got.real, got.imag
+    assert np.max(np.abs(flat - vals(kats, "time_correlation_test2_c"))) < 1e-3
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [17, 1000, 5000, 40000])
+def test_correlate_vs_oracle(n, dtype):
+    rng = np.random.default_rng(n)
+    a, b = rand_c(rng, n, dtype), rand_c(rng, n, dtype)
+    prepared = DspVec(b).prepare_argument_padded()
+    assert o.rel_l2(prepared.to_numpy(), o.prepare_argument_padded(b)) <= tol(2 * n, dtype)
+    got = DspVec(a, delta=0.5).correlate(prepared)
+    assert got.domain() == bd.TIME and got.delta() == 0.5
+    assert o.rel_l2(got.to_numpy(), o.correlate(a, o.prepare_argument_padded(b))) <= 2 * tol(2 * n, dtype)
+    p2 = DspVec(b).prepare_argument()
+    assert o.rel_l2(p2.to_numpy(), o.prepare_argument(b)) <= tol(n, dtype)
+    # same number of points: zero_pad_b refuses (InvalidArgumentLength), as in the reference
+    assert DspVec(a).result_code_of("correlate", p2) == o.ERR_INVALID_ARG_LEN
+    assert DspVec(a).result_code_of("correlate", DspVec(b)) == o.ERR_MUST_BE_TIME   # other must be a frequency vector
+
+
+def test_reverse_and_decimatei():
+    x = np.arange(11, dtype=np.float32)
+    assert np.array_equal(DspVec(x).reverse().to_numpy(), x[::-1])
+    c = (np.arange(7) + 1j * np.arange(7)[::-1]).astype(np.complex64)
+    assert np.array_equal(DspVec(c).reverse().to_numpy(), c[::-1])
+    assert np.array_equal(DspVec(x).decimatei(3, 1).to_numpy(), o.decimatei(x, 3, 1))
+    assert np.array_equal(DspVec(c).decimatei(2, 0).to_numpy(), o.decimatei(c, 2, 0))
+    big = np.arange(100003, dtype=np.float64)
+    assert np.array_equal(DspVec(big).decimatei(7, 5).to_numpy(), big[5::7])

@@ -367,3 +367,44 @@ def test_mul_no_fma_semantics():
     assert o.rel_l2(got, exact) < 1e-6
     assert o.ulp_diff(np.float32([1.0]), np.nextafter(np.float32(1.0), np.float32(2.0)), np.float32)[0] == 1
     assert o.ulp_diff(np.float64([-1.0]), np.float64([-1.0]), np.float64)[0] == 0
+
+
+# --- windows and correlation -------------------------------------------------------
+@pytest.mark.parametrize("kind,key", [(0, "triangular_window32_test"), (1, "hamming_window32_test"), (2, "blackmanharris_window32_test")])
+def test_window_functions(kats, kind, key):  # window_functions.rs:156-175
+    e = vals(kats, key)
+    got = np.array([o.window_value(kind, i, len(e), np.float32) for i in range(len(e))], dtype=np.float64)
+    assert np.max(np.abs(got - e)) < 1e-4
+    assert np.allclose(o.window_table(kind, len(e), np.float32), got, atol=1e-7)
+    assert np.all(o.window_table(3, 7, np.float32) == 1.0)
+
+
+def test_windowed_fft_vector64(kats):  # tests/time_freq_test.rs:122-197
+    got = o.magnitude(o.windowed_fft(sinusoid64(), 1, np.float64), np.float64)
+    assert np.max(np.abs(got - vals(kats, "windowed_fft_vector64"))) < 1e-6
+
+
+def test_windowed_fft_ifft_roundtrip():  # tests/time_freq_test.rs:209-219
+    x = sinusoid64()
+    assert np.allclose(o.windowed_ifft(o.windowed_fft(x, 1, np.float64), 1, np.float64).real, x, atol=1e-10)
+
+
+def test_time_correlation(kats):  # correlation.rs:170-196
+    a = cplx(kats["time_correlation_test_a"]["values"])
+    b = cplx(kats["time_correlation_test_b"]["values"])
+    c = vals(kats, "time_correlation_test_c")
+    got = o.correlate(a, o.prepare_argument_padded(b))
+    flat = np.empty(2 * len(got)); flat[0::2], flat[1::2] = got.real, got.imag
+    assert len(flat) == len(c) and np.max(np.abs(flat - c)) < 0.1
+
+
+def test_time_correlation2(kats):  # correlation.rs:198-215
+    a = np.array([1 + 1j, 2 + 1j, 3 + 1j])
+    b = np.array([4 + 1j, 5 + 1j, 6 + 1j])
+    c = vals(kats, "time_correlation_test2_c")
+    got = o.correlate(a, o.prepare_argument_padded(b))
+    flat = np.empty(2 * len(got)); flat[0::2], flat[1::2] = got.real, got.imag
+    assert np.max(np.abs(flat - c)) < 0.1
+    # definition check: full cross-correlation sum_n a[n + k] conj(b[n])
+    ref = np.correlate(a, b, mode="full")
+    assert np.allclose(got, ref, atol=1e-10)
