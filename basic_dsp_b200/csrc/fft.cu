@@ -230,9 +230,11 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? 1024 : 512) fft_tile_kernel(T
     // ---- twiddle + store ----
     // W_{tw_n}^{lane*k} = A[l][k & 31] * B[l][k >> 5] with A[l][a] = W^{lane*a}, B[l][b] = W^{lane*32*b}:
     // ct*(32 + m/32) exactly reduced roots per tile (sincospi) instead of one per element.
+    // rows are padded to an odd length: consecutive lanes (rows) must fall into different banks
     C* twA = s + spad_host_dev((m + 16) * ct);
-    C* twB = twA + ct * 32;
+    C* twB = twA + ct * 33;
     const int nb = (m + 31) >> 5;
+    const int nbs = nb | 1;
     if (p.tw_n) {
         for (int i = threadIdx.x; i < ct * (32 + nb); i += blockDim.x) {
             const bool isB = i >= ct * 32;
@@ -244,7 +246,7 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? 1024 : 512) fft_tile_kernel(T
             // lane < tw_n <= 2^40 and mul < 2^15: reduce lane*mul without overflow
             const unsigned long long num = ((lane % (unsigned long long)p.tw_n) * mul) % (unsigned long long)p.tw_n;
             const C w = unit_root<T>(num, (unsigned long long)p.tw_n, INV ? 1 : -1);
-            if (isB) twB[l * nb + e] = w; else twA[l * 32 + e] = w;
+            if (isB) twB[l * nbs + e] = w; else twA[l * 33 + e] = w;
         }
         __syncthreads();
     }
@@ -257,7 +259,7 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? 1024 : 512) fft_tile_kernel(T
         C v = s[spad(l * sstride + k)];
         const long long lane = lane0 + l;
         if (p.tw_n) {
-            const C w = cmul(twA[l * 32 + (k & 31)], twB[l * nb + (k >> 5)]);
+            const C w = cmul(twA[l * 33 + (k & 31)], twB[l * nbs + (k >> 5)]);
             v = cmul(v, w);
         }
         long long local = o1 * p.out_o1_stride + lane * p.out_lane_stride + (long long)k * p.out_point_stride;
@@ -436,7 +438,7 @@ template <typename T, bool INV>
 int launch_tile(const TileParams& p, long long batch, T scale, cudaStream_t st) {
     typedef typename CpxOf<T>::type C;
     const int m = 1 << p.log2m;
-    const size_t smem = (spad_host((size_t)(m + 16) * p.ct) + (size_t)p.ct * (32 + ((m + 31) >> 5))) * sizeof(C);
+    const size_t smem = (spad_host((size_t)(m + 16) * p.ct) + (size_t)p.ct * (33 + (((m + 31) >> 5) | 1))) * sizeof(C);
     int threads = block_fft_threads(m, p.ct);
     const long long grid = batch * p.o1_count * (p.lanes / p.ct);
     int rc = set_smem(fft_tile_kernel<T, INV>, smem);

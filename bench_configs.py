@@ -134,6 +134,19 @@ def main():
         report("C3", "4096 x 2^14 c32 fft + magnitude (one launch)", n * rows, 12 * n * rows, 5 * n * 14 * rows, med, best)
         del vin, out
 
+    if "X1" in want:
+        # extra: plain 2^20-point c32 FFT, 64 rows (two-pass tile kernels), and one 2^24-point transform
+        n, rows = 1 << 20, 64
+        x = rand_c(rng, n * rows, np.float32)
+        vin = DspVec(x)
+        out = DspVec.zeros(2 * n * rows, is_complex=True, dtype=np.float32)
+        pin, pout = dptr(vin), dptr(out)
+        med, best = T.run(lambda: L.bdsp_fft_rows_c32(pin, pout, n, rows, 0), args.iters)
+        report("X1", "64 x 2^20 c32 plain fft (2-pass)", n * rows, 16 * n * rows, 5 * n * 20 * rows, med, best)
+        med, best = T.run(lambda: L.bdsp_fft_rows_c32(pin, pout, n * 16, rows // 16, 0), args.iters)
+        report("X1", "4 x 2^24 c32 plain fft (3-pass)", n * rows, 16 * n * rows, 5 * n * 24 * rows, med, best)
+        del vin, out
+
     if "C4a" in want or "C4b" in want:
         n = 1 << 24
         x = rng.uniform(-10, 10, n).astype(np.float32)
