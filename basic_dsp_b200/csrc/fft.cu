@@ -450,7 +450,7 @@ int launch_tile(const TileParams& p, long long batch, T scale, cudaStream_t st) 
 
 template <typename T> int tile_log2m_max() { return sizeof(T) == 4 ? 10 : 9; }
 // lanes per tile: 128 contiguous bytes per row segment (f32: 16, f64: 8) -> 72 KB tiles, 3 CTAs per SM
-template <typename T> long long tile_lanes() { return sizeof(T) == 4 ? 16 : 8; }
+template <typename T> long long tile_lanes() { return 8; }
 
 // power-of-two transform of `batch` sequences; handles any supported size
 template <typename T, bool INV>

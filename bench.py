@@ -293,7 +293,7 @@ def run_gpu(args):
                        "sharding": "rows, no collective"},
             "gflops_5nlog2n": flops * world / (total_ms_max / args.steps * 1e-3) / 1e9,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": 1029248768.0, "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/r1_ols4096_ncu.txt)",
+                         "traffic": 1032126464.0, "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/r1_ols4096_ncu.txt)",
                          "kernel": "ols4096_kernel<true>", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_ms,
                          "min_launch_ms": min(per_launch_ms)},
