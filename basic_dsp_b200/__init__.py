@@ -108,6 +108,8 @@ def _declare(lib):
         for name in ("apply_window", "unapply_window", "windowed_fft", "windowed_ifft"):
             protos[name] = (_VecResult, [H, c_int32])
         protos["correlate"] = (_VecResult, [H, H])
+        protos["interpolatei"] = (_VecResult, [H, c_int32, T, c_int32])
+        protos["interpolatei_custom"] = (_VecResult, [H, RFN, c_void_p, c_uint8, c_int32])
         protos["decimatei"] = (_VecResult, [H, ctypes.c_uint32, ctypes.c_uint32])
         for name in ("prepare_argument", "prepare_argument_padded", "reverse"):
             protos[name] = (_VecResult, [H])
@@ -428,6 +430,12 @@ class DspVec:
 
     def correlate(self, prepared):
         return self._call("correlate", prepared._h)
+
+    def interpolatei(self, frequency_response, rolloff, factor, is_symmetric=True):
+        if callable(frequency_response):
+            cb = getattr(lib(), "RealFn" + self._s)(lambda _d, x: float(frequency_response(x)))
+            return self._call("interpolatei_custom", cb, None, 1 if is_symmetric else 0, factor)
+        return self._call("interpolatei", frequency_response, rolloff, factor)
 
     def reverse(self):
         return self._call("reverse")

@@ -692,6 +692,65 @@ template <typename T> Res<T> op_interpolatef(Vec<T>* v, const RealFn<T>& f, T fa
     return done(v, 0);
 }
 
+template <typename T> Res<T> op_interpolatei(Vec<T>* v, const RealFn<T>& f, bool is_symmetric, uint32_t factor) {
+    // interpolation.rs:484-538: zero_interleave -> plain_fft -> * factor*f(shifted x * factor) -> plain_ifft ->
+    // scale(1/points) (-> to_real).  The multiplier table follows multiply_function_priv with
+    // is_fft_shifted = true, incl. the mirrored evaluation of symmetric functions.
+    if (factor <= 1) return done(v, 0);
+    if (!is_symmetric && !v->is_complex) return done(v, 10);   // ArgumentFunctionMustBeSymmetric
+    const bool was_complex = v->is_complex != 0;
+    const size_t n_in = points_of(v);
+    if (!n_in) return done(v, 0);
+    const size_t points = n_in * factor;
+    // complex buffer of `points` points in the scratch: x[i] at i*factor, zeros elsewhere
+    int rc = ensure_scratch(v, 2 * points);
+    if (rc) return done(v, rc);
+    if (was_complex) rc = ew_zero_interleave<T>(v->d, v->scratch, n_in, (int)factor, 2, g_stream);
+    else rc = ew_zero_interleave<T>(v->d, v->scratch, n_in, (int)(2 * factor), 1, g_stream);
+    if (rc) return done(v, rc);
+    trade(v);
+    rc = ensure_scratch(v, 2 * points);
+    if (rc) return done(v, rc);
+    FftOpts fw;
+    rc = fft_exec<T>(v->d, v->scratch, points, 1, fw, nullptr, 0, g_stream);
+    if (rc) return done(v, rc);
+    std::vector<T> tab(points);
+    {
+        const T ratio = (T)factor;
+        const size_t offset = points % 2;
+        const T mx = (T)(points - offset) / (T)2;
+        const size_t c = (points - offset) / 2;
+        auto val = [&](size_t i) {
+            const T j = -mx + (T)i;
+            const T xv = j <= (T)0 ? (T)1 + j / mx : -(mx - j + (T)1) / mx;
+            return ratio * f(xv * ratio);
+        };
+        if (!is_symmetric) {
+            for (size_t i = 0; i < points; i++) tab[i] = val(i);
+        } else {
+            for (size_t i = 0; i <= c; i++) tab[i] = val(i);
+            if (offset == 0) { for (size_t i = 1; i < c; i++) tab[points - i] = tab[i]; }
+            else { for (size_t i = 0; i < c; i++) tab[points - 1 - i] = tab[i]; }
+        }
+    }
+    T* dev = nullptr;
+    rc = upload_table(tab, &dev);
+    if (!rc) rc = ew_mul_table<T>(v->scratch, dev, points, 1, 0, g_stream);
+    table_consumed();
+    if (rc) return done(v, rc);
+    FftOpts inv;
+    inv.inverse = 1;
+    rc = fft_exec<T>(v->scratch, v->d, points, 1, inv, nullptr, 0, g_stream);
+    if (!rc) rc = ew_scalar<T>(EW_SCALE, v->d, v->d, 2 * points, (double)((T)1 / (T)points), g_stream);
+    if (rc) return done(v, rc);
+    if (was_complex) { v->len = 2 * points; return done(v, 0); }
+    rc = ew_complex_to_real<T>(C2R_REAL, v->d, v->scratch, points, g_stream);
+    if (rc) return done(v, rc);
+    trade(v);
+    v->len = points;
+    return done(v, 0);
+}
+
 template <typename T> Res<T> op_interpolate_lin(Vec<T>* v, T factor, T delay) {
     // real_interpolation.rs:33-71
     if (v->is_complex) { mark_invalid(v); return done(v, 0); }
@@ -939,6 +998,14 @@ template <typename R, typename T> static inline R as_res(Res<T> r) {
         return as_res<RES>(op_interpolatef<T>(VEC(v), f, factor, delay, len));                                         \
     }                                                                                                                  \
     extern "C" RES interpolate_lin##S(HV* v, T factor, T delay) { return as_res<RES>(op_interpolate_lin(VEC(v), factor, delay)); } \
+    extern "C" RES interpolatei##S(HV* v, int32_t kind, T rolloff, int32_t factor) {                                  \
+        RealFn<T> f; f.kind = kind == 0 ? 0 : 1; f.rolloff = rolloff; f.freq = true;                                   \
+        return as_res<RES>(op_interpolatei<T>(VEC(v), f, true, (uint32_t)factor));                                     \
+    }                                                                                                                  \
+    extern "C" RES interpolatei_custom##S(HV* v, RFN fn, const void* data, uint8_t is_symmetric, int32_t factor) {     \
+        RealFn<T> f; f.kind = 2; f.fn = fn; f.data = data; f.freq = true;                                              \
+        return as_res<RES>(op_interpolatei<T>(VEC(v), f, is_symmetric != 0, (uint32_t)factor));                        \
+    }                                                                                                                  \
     extern "C" RES apply_window##S(HV* v, int32_t w) { return as_res<RES>(op_window(VEC(v), w, false)); }              \
     extern "C" RES unapply_window##S(HV* v, int32_t w) { return as_res<RES>(op_window(VEC(v), w, true)); }             \
     extern "C" RES windowed_fft##S(HV* v, int32_t w) { return as_res<RES>(op_windowed_fft(VEC(v), w)); }               \

@@ -155,6 +155,9 @@ BdspVecResult32 prepare_argument_padded32(BdspVec32* vector);            /* :116
 BdspVecResult32 correlate32(BdspVec32* vector, const BdspVec32* other);  /* :1166 */
 BdspVecResult32 reverse32(BdspVec32* vector);                            /* :1142 */
 BdspVecResult32 decimatei32(BdspVec32* vector, uint32_t decimation_factor, uint32_t delay); /* :1147 */
+BdspVecResult32 interpolatei32(BdspVec32* vector, int32_t frequency_response, float rolloff, int32_t interpolation_factor); /* :1426 */
+BdspVecResult32 interpolatei_custom32(BdspVec32* vector, BdspRealFn32 frequency_response, const void* frequency_response_data,
+                                      uint8_t is_symmetric, int32_t interpolation_factor);     /* :1402 */
 
 /* ---- f64 twins (interop/src/facade64.rs, same line numbers + 1) ------------------------------------------------ */
 BdspVecResult64 apply_window64(BdspVec64* vector, int32_t window);
@@ -166,6 +169,9 @@ BdspVecResult64 prepare_argument_padded64(BdspVec64* vector);
 BdspVecResult64 correlate64(BdspVec64* vector, const BdspVec64* other);
 BdspVecResult64 reverse64(BdspVec64* vector);
 BdspVecResult64 decimatei64(BdspVec64* vector, uint32_t decimation_factor, uint32_t delay);
+BdspVecResult64 interpolatei64(BdspVec64* vector, int32_t frequency_response, double rolloff, int32_t interpolation_factor);
+BdspVecResult64 interpolatei_custom64(BdspVec64* vector, BdspRealFn64 frequency_response, const void* frequency_response_data,
+                                      uint8_t is_symmetric, int32_t interpolation_factor);
 BdspVec64* new64(int32_t is_complex, int32_t domain, double init_value, size_t length, double delta);
 BdspVec64* new_with_performance_options64(int32_t is_complex, int32_t domain, double init_value, size_t length, double delta, size_t core_limit);
 BdspVec64* new_with_detailed_performance_options64(int32_t is_complex, int32_t domain, double init_value, size_t length,

@@ -648,6 +648,55 @@ def correlate(a, prepared):
     return swap_halves(plain_ifft(plain_fft(ap) * np.asarray(prepared)) / p)
 
 
+def shifted_response_table(f, points, ratio, dtype, is_symmetric=True):
+    """Multiplier table of multiply_function_priv with is_fft_shifted = true (time_freq/mod.rs:612-723,
+    fft_swap_x :67-78) as used by interpolatei: X[i] *= ratio * f(swap(j_i) * ratio).
+    Symmetric functions go through execute_sym_pairs_with_range (threading.rs:552-612): only the first
+    half is evaluated (j <= 0: swap = 1 + j/max) and mirrored - element i pairs with points-i for an
+    even and with points-1-i for an odd number of points."""
+    T = _T(dtype)
+    ratio = T(ratio)
+    offset = points % 2
+    mx = T(points - offset) / T(2)
+    c = (points - offset) // 2
+    tab = np.empty(points, dtype=dtype)
+
+    def val(i):
+        j = -mx + T(i)
+        xv = (T(1) + j / mx) if j <= 0 else (-(mx - j + T(1)) / mx)
+        return T(ratio * T(f(T(xv * ratio))))
+
+    if not is_symmetric:
+        for i in range(points):
+            tab[i] = val(i)
+        return tab
+    for i in range(c + 1):
+        tab[i] = val(i)
+    if offset == 0:
+        for i in range(1, c):
+            tab[points - i] = tab[i]
+    else:
+        for i in range(c):
+            tab[points - 1 - i] = tab[i]
+    return tab
+
+
+def interpolatei(x, f, factor, dtype):
+    """InterpolationOps::interpolatei (interpolation.rs:484-538): zero_interleave -> plain_fft ->
+    multiply with the (fft-shifted) frequency response * factor -> plain_ifft -> scale(1/points);
+    real vectors are processed as complex and converted back with to_real."""
+    x = np.asarray(x)
+    if factor <= 1:
+        return x.copy()
+    is_complex = np.iscomplexobj(x)
+    z = np.zeros(len(x) * factor, dtype=np.complex128)
+    z[::factor] = x
+    points = len(z)
+    Z = plain_fft(z) * shifted_response_table(f, points, factor, dtype).astype(np.float64)
+    y = plain_ifft(Z) / points
+    return y if is_complex else y.real.copy()
+
+
 def reverse(x):
     return np.asarray(x)[::-1].copy()
 

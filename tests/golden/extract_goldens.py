@@ -44,6 +44,8 @@ CASES = [
     ("time_correlation_test_b", "vector/src/vector_types/time_freq/correlation.rs", "time_correlation_test", "b"),
     ("time_correlation_test_c", "vector/src/vector_types/time_freq/correlation.rs", "time_correlation_test", "c"),
     ("time_correlation_test2_c", "vector/src/vector_types/time_freq/correlation.rs", "time_correlation_test2", "c"),
+    ("interpolatei_sinc_test", "vector/src/vector_types/time_freq/interpolation.rs", "interpolatei_sinc_test", "expected"),
+    ("interpolatei_rc_test", "vector/src/vector_types/time_freq/interpolation.rs", "interpolatei_rc_test", "expected"),
     ("triangular_window32_test", "vector/src/window_functions.rs", "triangular_window32_test", "expected"),
     ("hamming_window32_test", "vector/src/window_functions.rs", "hamming_window32_test", "expected"),
     ("blackmanharris_window32_test", "vector/src/window_functions.rs", "blackmanharris_window32_test", "expected"),

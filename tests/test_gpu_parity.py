@@ -533,3 +533,28 @@ def test_reverse_and_decimatei():
     assert np.array_equal(DspVec(c).decimatei(2, 0).to_numpy(), o.decimatei(c, 2, 0))
     big = np.arange(100003, dtype=np.float64)
     assert np.array_equal(DspVec(big).decimatei(7, 5).to_numpy(), big[5::7])
+
+
+def test_interpolatei(kats):  # interpolation.rs:653-680, 722-750 + tests/interpolation_test.rs pattern
+    n = 6
+    x = np.zeros(n, dtype=np.complex64); x[n // 2] = 1
+    got = DspVec(x).interpolatei(bd.SINC, 0.0, 2).magnitude().to_numpy()
+    assert np.max(np.abs(got - vals(kats, "interpolatei_sinc_test"))) < 1e-4
+    got = DspVec(x).interpolatei(bd.RAISED_COSINE, 0.4, 2).magnitude().to_numpy()
+    assert np.max(np.abs(got - vals(kats, "interpolatei_rc_test"))) < 1e-4
+    rng = np.random.default_rng(12)
+    for dtype in (np.float32, np.float64):
+        for n, F, cplx_ in [(1000, 4, True), (777, 3, True), (512, 2, False), (301, 5, False)]:
+            x = rand_c(rng, n, dtype) if cplx_ else rng.uniform(-10, 10, n).astype(dtype)
+            f = lambda t: o.raised_cosine_freq(t, 0.35, dtype)
+            got = DspVec(x).interpolatei(bd.RAISED_COSINE, 0.35, F)
+            ref = o.interpolatei(x, f, F, dtype)
+            assert got.is_complex() == cplx_ and got.points() == n * F
+            assert o.rel_l2(got.to_numpy(), ref) <= 4 * tol(n * F, dtype)
+            cb = DspVec(x).interpolatei(lambda t: float(o.raised_cosine_freq(t, 0.35, dtype)), 0.0, F).to_numpy()
+            assert o.rel_l2(cb, ref) <= 4 * tol(n * F, dtype)
+    # decimatei is the inverse for a band-limited signal when the response is flat in band
+    x = np.cos(2 * np.pi * 5 * np.arange(256) / 256).astype(np.float32)
+    back = DspVec(x).interpolatei(bd.SINC, 0.0, 4).decimatei(4, 0).to_numpy()
+    assert np.max(np.abs(back - x)) < 1e-3
+    assert DspVec(x).result_code_of("interpolatei", 0, 0.0, 1) == 0   # factor <= 1: no-op

@@ -408,3 +408,13 @@ def test_time_correlation2(kats):  # correlation.rs:198-215
     # definition check: full cross-correlation sum_n a[n + k] conj(b[n])
     ref = np.correlate(a, b, mode="full")
     assert np.allclose(got, ref, atol=1e-10)
+
+
+def test_interpolatei_kats(kats):  # interpolation.rs:653-680 (sinc), :722-750 (raised cosine 0.4)
+    n = 6
+    x = np.zeros(n, dtype=np.complex128)
+    x[n // 2] = 1.0
+    got = np.abs(o.interpolatei(x, lambda t: o.sinc_freq(t, np.float32), 2, np.float32))
+    assert np.max(np.abs(got - vals(kats, "interpolatei_sinc_test"))) < 1e-4
+    got = np.abs(o.interpolatei(x, lambda t: o.raised_cosine_freq(t, 0.4, np.float32), 2, np.float32))
+    assert np.max(np.abs(got - vals(kats, "interpolatei_rc_test"))) < 1e-4
