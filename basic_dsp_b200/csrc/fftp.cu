@@ -35,9 +35,14 @@ __device__ __forceinline__ int fp_rot(int row, int g) { return (((g >> 1) + (row
 
 // twiddle table (floats): [0,256) Re W4096^c, [256,512) Im W4096^c, [512,1024) stride-16 table (see ols4096.cu),
 // [1024 + 8192*i + c] Re W_{8192<<i}^c, [1024 + 8192*i + 4096 + c] Im, c in [0,4096), i in {0,1}
-#define FP_TW_FLOATS (1024 + 2 * 8192)
+// [1024 + 16384 + 4*(16*ka + b)] splat table {c, c, s, s} of W256^{ka*b} (first pass of the 2^20 transform)
+#define FP_TW_SPLAT (1024 + 2 * 8192)
+#define FP_TW_FLOATS (FP_TW_SPLAT + 1024)
 
-template <int R0, int CL, bool INV, bool SHIFT_IN, bool SHIFT_OUT, bool MAG>
+// ROWS = true (R0 = 4, CL = 1): the CTA transforms FOUR independent, adjacent 4096-point rows (no F0) and
+// writes result k of row r to out[(r0 + r) + n1 * k]: the transposing last pass of a two-pass transform of
+// n1 * 4096 points, with the four rows providing the contiguous 32 bytes of every store sector.
+template <int R0, int CL, bool INV, bool SHIFT_IN, bool SHIFT_OUT, bool MAG, bool ROWS>
 // FP_PREFETCH=1: persistent CTAs + register prefetch of the next row.  Measured on B200 (C3): 0.336 ms vs
 // 0.275 ms without (register pressure -> spills; the extra barrier), so it is off by default.
 #ifndef FP_PREFETCH
@@ -47,7 +52,7 @@ template <int R0, int CL, bool INV, bool SHIFT_IN, bool SHIFT_OUT, bool MAG>
 #define FP_MINB256 2
 #endif
 __global__ void __launch_bounds__(128 * (R0 / CL), (R0 / CL) == 2 ? FP_MINB256 : 4 / (R0 / CL))
-fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, long long rows, float scale, const float* __restrict__ tw) {
+fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, long long rows, float scale, const float* __restrict__ tw, int n1) {
     constexpr int NSB = R0 / CL;          // sub-blocks (4096-point transforms) owned by this CTA
     constexpr int NT = 128 * NSB;         // threads
     constexpr int N = 4096 * R0;
@@ -78,11 +83,15 @@ fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, long long row
         }
     }
     for (; row < rows; row += row_step) {
-    const float2* xr = x + (size_t)row * (size_t)N;
+    // ROWS: `row` counts groups of four rows; groups_per_seq = n1 / 4
+    const size_t seq = ROWS ? (size_t)row / (size_t)(n1 >> 2) : (size_t)row;
+    const int grp = ROWS ? (int)((size_t)row % (size_t)(n1 >> 2)) : 0;
+    const size_t seq_len = ROWS ? (size_t)4096 * (size_t)n1 : (size_t)N;
+    const float2* xr = x + seq * seq_len + (ROWS ? (size_t)grp * 4 * 4096 : 0);
 
     cp v[16];
     // ------------------------------------------------------------------ F0: radix-R0 over stride 4096
-    if constexpr (R0 > 1) {
+    if constexpr (R0 > 1 && !ROWS) {
         float* rre[CL];
         float* rim[CL];
         if constexpr (CL > 1) {
@@ -147,7 +156,7 @@ fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, long long row
         int off[4];   // row>>1 takes 8 values but only (row>>1)&3 matters: 4 rotations
 #pragma unroll
         for (int r = 0; r < 4; r++) off[r] = 16 * g + ((j + 4 * (((g >> 1) + r) & 3)) & 15);
-        if constexpr (R0 > 1) {
+        if constexpr (R0 > 1 && !ROWS) {
 #pragma unroll
             for (int n2 = 0; n2 < 16; n2++) {
                 v[n2].re = *reinterpret_cast<const float2*>(bre + 272 * n2 + off[(n2 >> 1) & 3]);
@@ -157,7 +166,7 @@ fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, long long row
 #pragma unroll
             for (int n2 = 0; n2 < 16; n2++) {
                 const int src = SHIFT_IN ? (n2 ^ 8) : n2;
-                const float4 ab = __ldg(reinterpret_cast<const float4*>(xr + c + 256 * src));
+                const float4 ab = __ldg(reinterpret_cast<const float4*>(xr + (ROWS ? sb * 4096 : 0) + c + 256 * src));
                 v[n2].re = make_float2(ab.x, ab.z);
                 v[n2].im = make_float2(ab.y, ab.w);
             }
@@ -239,28 +248,145 @@ fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, long long row
         }
         fft16_dif<INV>(P);
         // slot j holds k2 = bitrev4(j); k = (rank*NSB + lsb) + R0*(k0 + 16*k1 + 256*k2)
-        const int klow = rank * NSB + lsb + R0 * (k0 + 16 * k1);
+        // (ROWS: k = (4*grp + lsb) + n1*(k0 + 16*k1 + 256*k2))
+        const int kst = ROWS ? n1 : R0;
+        const size_t klow = (ROWS ? (size_t)(4 * grp + lsb) : (size_t)(rank * NSB + lsb)) + (size_t)kst * (size_t)(k0 + 16 * k1);
+        const size_t k2s = (size_t)256 * (size_t)kst;
         if constexpr (MAG) {
-            float* o = reinterpret_cast<float*>(out_) + row * (size_t)N + klow;
+            float* o = reinterpret_cast<float*>(out_) + seq * seq_len + klow;
 #pragma unroll
             for (int m = 0; m < 8; m++) {
                 pk m2 = pfma(P[m].re, P[m].re, pmul(P[m].im, P[m].im));
                 const int ka = bitrev4(2 * m) ^ (SHIFT_OUT ? 8 : 0), kb = bitrev4(2 * m + 1) ^ (SHIFT_OUT ? 8 : 0);
-                o[256 * R0 * ka] = sqrtf(m2.x) * scale;
-                o[256 * R0 * kb] = sqrtf(m2.y) * scale;
+                o[k2s * ka] = sqrtf(m2.x) * scale;
+                o[k2s * kb] = sqrtf(m2.y) * scale;
             }
         } else {
-            float2* o = reinterpret_cast<float2*>(out_) + row * (size_t)N + klow;
+            float2* o = reinterpret_cast<float2*>(out_) + seq * seq_len + klow;
 #pragma unroll
             for (int m = 0; m < 8; m++) {
                 const int ka = bitrev4(2 * m) ^ (SHIFT_OUT ? 8 : 0), kb = bitrev4(2 * m + 1) ^ (SHIFT_OUT ? 8 : 0);
-                o[256 * R0 * ka] = make_float2(P[m].re.x * scale, P[m].im.x * scale);
-                o[256 * R0 * kb] = make_float2(P[m].re.y * scale, P[m].im.y * scale);
+                o[k2s * ka] = make_float2(P[m].re.x * scale, P[m].im.x * scale);
+                o[k2s * kb] = make_float2(P[m].re.y * scale, P[m].im.y * scale);
             }
         }
     }
     if (row + row_step < rows) __syncthreads();   // the next row's F0 overwrites the shared memory F3 just read
     }  // rows
+}
+
+
+// ------------------------------------------------------------------------------------------
+// two-pass transforms of n = N1 * 4096 points, N1 in {16, 256}  (n = 2^16, 2^20)
+//   pass A (below):  tmp[k1*4096 + n2] = W_n^{n2*k1} * sum_{n1} x[n1*4096 + n2] * W_N1^{n1*k1}
+//   pass B (fftp_kernel<ROWS>): X[k1 + N1*k2] = sum_{n2} tmp[k1*4096 + n2] * W_4096^{n2*k2}
+// Both passes move every point exactly once in full 32-byte sectors: 16 B/point of DRAM traffic each.
+// The inter-pass twiddle is evaluated with sincospif on an exactly representable argument (m/n with
+// m < 2^22) for the base root(s) and raised to the <= 15th power with the A_a*B_b product scheme.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ cp unit_root_pair(unsigned m0, unsigned m1, float two_over_n, bool inv) {
+    // {W_n^{m0}, W_n^{m1}} = cos(2 pi m/n) - i sin(2 pi m/n); conjugated for the inverse transform
+    float s0, c0, s1, c1;
+    sincospif((float)m0 * two_over_n, &s0, &c0);
+    sincospif((float)m1 * two_over_n, &s1, &c1);
+    cp w;
+    w.re = make_float2(c0, c1);
+    w.im = inv ? make_float2(s0, s1) : make_float2(-s0, -s1);
+    return w;
+}
+
+template <bool INV, bool SHIFT_IN>
+__global__ void __launch_bounds__(128) fftp_col16_kernel(const float2* __restrict__ x, float2* __restrict__ tmp) {
+    constexpr unsigned N = 16u * 4096u;
+    const unsigned pi = blockIdx.x * 128u + threadIdx.x;   // column pair over all sequences
+    const size_t seq = pi >> 11;
+    const unsigned c = 2u * (pi & 2047u);
+    const float2* xs = x + seq * N + c;
+    cp v[16];
+#pragma unroll
+    for (int a = 0; a < 16; a++) {
+        const int src = SHIFT_IN ? (a ^ 8) : a;
+        const float4 ab = __ldg(reinterpret_cast<const float4*>(xs + 4096 * src));
+        v[a].re = make_float2(ab.x, ab.z);
+        v[a].im = make_float2(ab.y, ab.w);
+    }
+    r16<INV>(v);
+    apply_twiddles<true>(v, unit_root_pair(c, c + 1, 2.0f / (float)N, INV));
+    float2* o = tmp + seq * N + c;
+#pragma unroll
+    for (int s = 0; s < 16; s++)
+        *reinterpret_cast<float4*>(o + 4096 * r16_k(s)) = make_float4(v[s].re.x, v[s].im.x, v[s].re.y, v[s].im.y);
+}
+
+template <bool INV, bool SHIFT_IN>
+__global__ void __launch_bounds__(128, 5) fftp_col256_kernel(const float2* __restrict__ x, float2* __restrict__ tmp,
+                                                             const float4* __restrict__ tws) {
+    constexpr unsigned N = 256u * 4096u;
+    __shared__ __align__(16) float sre[16 * 272];
+    __shared__ __align__(16) float sim[16 * 272];
+    const int t = threadIdx.x;
+    const size_t seq = blockIdx.x >> 8;
+    const unsigned c0 = (blockIdx.x & 255u) * 16u;     // 16 columns per CTA
+    const int hi = t >> 3, j = 2 * (t & 7);
+    cp v[16];
+    {   // stage 1: radix 16 over n1 = 16a + b, b = hi
+        const float2* xs = x + seq * N + c0 + j + (size_t)hi * 4096;
+#pragma unroll
+        for (int a = 0; a < 16; a++) {
+            const int src = SHIFT_IN ? (a ^ 8) : a;
+            const float4 ab = __ldg(reinterpret_cast<const float4*>(xs + (size_t)src * (16 * 4096)));
+            v[a].re = make_float2(ab.x, ab.z);
+            v[a].im = make_float2(ab.y, ab.w);
+        }
+        r16<INV>(v);
+        const int off = 16 * hi + ((j + 4 * rot_of(hi)) & 15);
+#pragma unroll
+        for (int s = 0; s < 16; s++) {
+            const int ka = r16_k(s);
+            if (s > 0) {
+                const float4 f = __ldg(tws + 16 * ka + hi);
+                cp w;
+                w.re = make_float2(f.x, f.y);
+                w.im = make_float2(f.z, f.w);
+                v[s] = INV ? cmul_conj(v[s], w) : cmul(v[s], w);
+            }
+            *reinterpret_cast<float2*>(sre + 272 * ka + off) = v[s].re;
+            *reinterpret_cast<float2*>(sim + 272 * ka + off) = v[s].im;
+        }
+    }
+    __syncthreads();
+    {   // stage 2: radix 16 over b for ka = hi; k1 = ka + 16*kb
+        const int ka = hi;
+#pragma unroll
+        for (int b = 0; b < 16; b++) {
+            const int a = 272 * ka + 16 * b + ((j + 4 * rot_of(b)) & 15);
+            v[b].re = *reinterpret_cast<const float2*>(sre + a);
+            v[b].im = *reinterpret_cast<const float2*>(sim + a);
+        }
+        r16<INV>(v);
+        // W_n^{n2*k1} = W_n^{n2*ka} * (W_n^{16*n2})^{kb}
+        const unsigned n2 = c0 + (unsigned)j;
+        const float ton = 2.0f / (float)N;
+        const cp w0 = unit_root_pair(n2 * (unsigned)ka, (n2 + 1) * (unsigned)ka, ton, INV);
+        const cp u = unit_root_pair(16u * n2, 16u * (n2 + 1), ton, INV);
+        cp A[4], B[4];
+        A[0] = w0;
+        A[1] = cmul(w0, u);
+        A[2] = cmul(A[1], u);
+        A[3] = cmul(A[2], u);
+        const cp u2 = cmul(u, u);
+        B[1] = cmul(u2, u2);
+        B[2] = cmul(B[1], B[1]);
+        B[3] = cmul(B[2], B[1]);
+        float2* o = tmp + seq * N + (size_t)ka * 4096 + c0 + j;
+#pragma unroll
+        for (int s = 0; s < 16; s++) {
+            const int kb = r16_k(s);
+            const cp w = (kb >> 2) == 0 ? A[kb & 3] : cmul(A[kb & 3], B[kb >> 2]);
+            const cp r = cmul(v[s], w);
+            *reinterpret_cast<float4*>(o + (size_t)kb * (16 * 4096)) = make_float4(r.re.x, r.im.x, r.re.y, r.im.y);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -292,6 +418,13 @@ const float* fftp_twiddles() {
             h[1024 + 8192 * i + c] = (float)cosl(a);
             h[1024 + 8192 * i + 4096 + c] = (float)sinl(a);
         }
+    for (int ka = 0; ka < 16; ka++)
+        for (int b = 0; b < 16; b++) {
+            const long double a = -tau * (long double)((ka * b) % 256) / 256.0L;
+            float* e = &h[FP_TW_SPLAT + 4 * (16 * ka + b)];
+            e[0] = e[1] = (float)cosl(a);
+            e[2] = e[3] = (float)sinl(a);
+        }
     float* dev = nullptr;
     BDSP_CUDA_ABORT(cudaMalloc(&dev, FP_TW_FLOATS * sizeof(float)));
     BDSP_CUDA_ABORT(cudaMemcpy(dev, h.data(), FP_TW_FLOATS * sizeof(float), cudaMemcpyHostToDevice));
@@ -299,11 +432,11 @@ const float* fftp_twiddles() {
     return dev;
 }
 
-template <int R0, int CL, bool INV, bool SI, bool SO, bool MAG>
-int fftp_launch(const void* in, void* out, size_t rows, float scale, cudaStream_t st) {
+template <int R0, int CL, bool INV, bool SI, bool SO, bool MAG, bool ROWS = false>
+int fftp_launch(const void* in, void* out, size_t rows, float scale, cudaStream_t st, int n1 = 1) {
     constexpr int NSB = R0 / CL;
     const size_t smem = (size_t)2 * NSB * FP_B_OF(NSB) * sizeof(float);
-    auto kern = fftp_kernel<R0, CL, INV, SI, SO, MAG>;
+    auto kern = fftp_kernel<R0, CL, INV, SI, SO, MAG, ROWS>;
     static bool configured = false;   // per instantiation
     if (!configured) {
         BDSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -329,7 +462,7 @@ int fftp_launch(const void* in, void* out, size_t rows, float scale, cudaStream_
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = CL > 1 ? 1 : 0;
-    BDSP_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, reinterpret_cast<const float2*>(in), out, (long long)rows, scale, tw));
+    BDSP_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, reinterpret_cast<const float2*>(in), out, (long long)rows, scale, tw, n1));
     BDSP_LAUNCHED();
     return 0;
 }
@@ -347,7 +480,66 @@ int fftp_dispatch(const void* in, void* out, size_t rows, bool inv, bool shift_i
     return shift_in ? fftp_launch<R0, CL, true, true, false, false>(in, out, rows, scale, st)
                     : fftp_launch<R0, CL, true, false, false, false>(in, out, rows, scale, st);
 }
+
+template <bool INV, bool SI>
+int fftp_colpass(const void* in, void* tmp, size_t n, size_t rows, cudaStream_t st) {
+    const float* tw = fftp_twiddles();
+    if (n == 65536) {
+        fftp_col16_kernel<INV, SI><<<(unsigned)(rows * 16), 128, 0, st>>>(reinterpret_cast<const float2*>(in), reinterpret_cast<float2*>(tmp));
+    } else {
+        fftp_col256_kernel<INV, SI><<<(unsigned)(rows * 256), 128, 0, st>>>(reinterpret_cast<const float2*>(in), reinterpret_cast<float2*>(tmp),
+                                                                         reinterpret_cast<const float4*>(tw + FP_TW_SPLAT));
+    }
+    BDSP_CUDA_OK(cudaGetLastError());
+    BDSP_LAUNCHED();
+    return 0;
+}
 }  // namespace
+
+// two-pass packed transform for n = 2^16 and 2^20 (tmp: n*rows complex values, distinct from in; may equal out only
+// if out != in).  Returns 1 when the configuration is not covered.
+int fftp_two_pass_try(const void* in, void* out, void* tmp, size_t n, size_t rows, bool inverse, size_t in_rot, size_t out_rot,
+                      double scale, bool magnitude, cudaStream_t st) {
+    if (n != 65536 && n != (1u << 20)) return 1;
+    if ((in_rot != 0 && in_rot != n / 2) || (out_rot != 0 && out_rot != n / 2)) return 1;
+    if (inverse && (magnitude || out_rot != 0)) return 1;
+    if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 7) || (reinterpret_cast<uintptr_t>(tmp) & 15)) return 1;
+    if (tmp == in || tmp == out) return 1;
+    const int n1 = (int)(n / 4096);
+    const size_t groups = rows * (size_t)(n1 / 4);
+    if (groups > 0x7fffffffull || rows * 256 > 0x7fffffffull) return 1;
+    const bool si = in_rot != 0, so = out_rot != 0;
+    const float sc = (float)scale;
+    // BDSP_FFTP_CHUNK_MB=<m> processes the sequences in chunks whose intermediate (8 bytes per point) is <= m MB so
+    // that it can stay in the 126 MB L2 between the passes.  Measured on B200 (64 x 2^20): one launch pair over the
+    // whole batch 0.448 ms; 64 MB chunks 0.571 ms; 32 MB 0.596 ms; 8 MB 1.18 ms (launch rate and wave tails cost more
+    // than the saved DRAM traffic), so chunking is off unless requested.
+    static const size_t chunk_bytes = [] {
+        const char* e = getenv("BDSP_FFTP_CHUNK_MB");
+        const long mb = e ? atol(e) : 0;
+        return mb > 0 ? (size_t)mb << 20 : ~(size_t)0;
+    }();
+    size_t chunk = chunk_bytes / (n * sizeof(float2));
+    if (chunk < 1) chunk = 1;
+    const size_t out_elem = magnitude ? sizeof(float) : sizeof(float2);
+    for (size_t r0 = 0; r0 < rows; r0 += chunk) {
+        const size_t nr = rows - r0 < chunk ? rows - r0 : chunk;
+        const void* cin = reinterpret_cast<const char*>(in) + r0 * n * sizeof(float2);
+        void* cout = reinterpret_cast<char*>(out) + r0 * n * out_elem;
+        const size_t groups_c = nr * (size_t)(n1 / 4);
+        int rc;
+        if (inverse) rc = si ? fftp_colpass<true, true>(cin, tmp, n, nr, st) : fftp_colpass<true, false>(cin, tmp, n, nr, st);
+        else rc = si ? fftp_colpass<false, true>(cin, tmp, n, nr, st) : fftp_colpass<false, false>(cin, tmp, n, nr, st);
+        if (rc) return rc;
+        if (inverse) rc = fftp_launch<4, 1, true, false, false, false, true>(tmp, cout, groups_c, sc, st, n1);
+        else if (magnitude) rc = so ? fftp_launch<4, 1, false, false, true, true, true>(tmp, cout, groups_c, sc, st, n1)
+                                    : fftp_launch<4, 1, false, false, false, true, true>(tmp, cout, groups_c, sc, st, n1);
+        else rc = so ? fftp_launch<4, 1, false, false, true, false, true>(tmp, cout, groups_c, sc, st, n1)
+                     : fftp_launch<4, 1, false, false, false, false, true>(tmp, cout, groups_c, sc, st, n1);
+        if (rc) return rc;
+    }
+    return 0;
+}
 
 // CTAs per sequence for n >= 8192: 1 = one persistent CTA per SM with register prefetch (default,
 // measured faster on B200), 2 = thread-block cluster of two CTAs exchanging the first stage through

@@ -80,7 +80,7 @@ def test_plain_fft_sizes(n, dtype):
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-@pytest.mark.parametrize("n", [7, 8, 64, 1000, 1001, 4096, 65536, 3 * 4096, 1 << 17])
+@pytest.mark.parametrize("n", [7, 8, 64, 1000, 1001, 4096, 65536, 3 * 4096, 1 << 17, 1 << 20])
 def test_fft_ifft_shifted(n, dtype):
     rng = np.random.default_rng(100 + n)
     x = rand_c(rng, n, dtype)
@@ -121,7 +121,7 @@ def test_swap_halves(n):
 def test_fft_rows_batched():
     rng = np.random.default_rng(5)
     L = bd.lib()
-    for n, rows in [(16384, 8), (1024, 33), (64, 100), (1 << 15, 3)]:
+    for n, rows in [(16384, 8), (1024, 33), (64, 100), (1 << 15, 3), (1 << 16, 5), (1 << 20, 3)]:
         x = rand_c(rng, n * rows, np.float32)
         v = DspVec(x)
         out = DspVec.zeros(n * rows, dtype=np.float32)
@@ -133,12 +133,31 @@ def test_fft_rows_batched():
         assert o.rel_l2(got, ref) <= tol(n, np.float32)
 
 
-def test_fft_magnitude_fused():
+@pytest.mark.parametrize("n", [16384, 1 << 16, 1 << 20])
+def test_fft_magnitude_fused(n):
     rng = np.random.default_rng(6)
-    x = rand_c(rng, 16384, np.float32)
+    x = rand_c(rng, n, np.float32)
     got = DspVec(x).fft_magnitude()
-    assert not got.is_complex() and got.len() == 16384
-    assert o.rel_l2(got.to_numpy(), np.abs(o.fft(x))) <= tol(16384, np.float32)
+    assert not got.is_complex() and got.len() == n
+    assert o.rel_l2(got.to_numpy(), np.abs(o.fft(x))) <= tol(n, np.float32)
+
+
+@pytest.mark.parametrize("n", [1 << 16, 1 << 20])
+def test_two_pass_rows_plain_and_inverse(n):
+    """packed two-pass path (fftp.cu): plain forward / inverse over several rows, unshifted."""
+    rng = np.random.default_rng(n)
+    L = bd.lib()
+    rows = 3
+    x = rand_c(rng, n * rows, np.float32)
+    v = DspVec(x)
+    out = DspVec.zeros(2 * n * rows, is_complex=True, dtype=np.float32)
+    pin, pout = v._fn("bdsp_device_ptr")(v._h), out._fn("bdsp_device_ptr")(out._h)
+    assert L.bdsp_fft_rows_c32(pin, pout, n, rows, 0) == 0
+    ref = np.fft.fft(x.reshape(rows, n).astype(np.complex128), axis=1)
+    assert o.rel_l2(out.to_numpy().reshape(rows, n), ref) <= tol(n, np.float32)
+    assert L.bdsp_fft_rows_c32(pin, pout, n, rows, bd.F_INVERSE) == 0
+    ref = np.fft.ifft(x.reshape(rows, n).astype(np.complex128), axis=1) * n
+    assert o.rel_l2(out.to_numpy().reshape(rows, n), ref) <= tol(n, np.float32)
 
 
 # --------------------------------------------------------------------------------------------------
