@@ -24,6 +24,7 @@ LIB_PATH = os.environ.get("BASIC_DSP_B200_LIB", os.path.join(_HERE, "libbasic_ds
 F_INVERSE, F_SHIFT, F_MAGNITUDE, F_REAL_INPUT = 1, 2, 4, 8
 TIME, FREQ = 0, 1
 SINC, RAISED_COSINE = 0, 1
+TRIANGULAR, HAMMING, BLACKMAN_HARRIS, RECTANGULAR = 0, 1, 2, 3   # translate_to_window_function (interop/src/lib.rs:153-164)
 
 
 class DspError(RuntimeError):
@@ -111,6 +112,14 @@ def _declare(lib):
         protos["interpolatei"] = (_VecResult, [H, c_int32, T, c_int32])
         protos["interpolatei_custom"] = (_VecResult, [H, RFN, c_void_p, c_uint8, c_int32])
         protos["decimatei"] = (_VecResult, [H, ctypes.c_uint32, ctypes.c_uint32])
+        protos["interpolate"] = (_VecResult, [H, c_int32, T, c_size_t, T])
+        protos["interpolate_custom"] = (_VecResult, [H, RFN, c_void_p, c_uint8, c_size_t, T])
+        protos["interpft"] = (_VecResult, [H, c_size_t])
+        protos["multiply_complex_exponential"] = (_VecResult, [H, T, T])
+        for name in ("windowed_sfft", "windowed_sifft"):
+            protos[name] = (_VecResult, [H, c_int32])
+        for name in ("mirror", "plain_sfft", "sfft", "plain_sifft", "sifft"):
+            protos[name] = (_VecResult, [H])
         for name in ("prepare_argument", "prepare_argument_padded", "reverse"):
             protos[name] = (_VecResult, [H])
         for name in ("conj", "to_complex", "magnitude", "magnitude_squared", "phase", "to_real", "to_imag",
@@ -436,6 +445,43 @@ class DspVec:
             cb = getattr(lib(), "RealFn" + self._s)(lambda _d, x: float(frequency_response(x)))
             return self._call("interpolatei_custom", cb, None, 1 if is_symmetric else 0, factor)
         return self._call("interpolatei", frequency_response, rolloff, factor)
+
+    def interpolate(self, frequency_response, rolloff, dest_points, delay, is_symmetric=True):
+        """InterpolationOps::interpolate; frequency_response None = interpft."""
+        if frequency_response is None:
+            return self._call("interpft", dest_points)
+        if callable(frequency_response):
+            cb = getattr(lib(), "RealFn" + self._s)(lambda _d, x: float(frequency_response(x)))
+            return self._call("interpolate_custom", cb, None, 1 if is_symmetric else 0, dest_points, delay)
+        return self._call("interpolate", frequency_response, rolloff, dest_points, delay)
+
+    def interpft(self, dest_points):
+        return self._call("interpft", dest_points)
+
+    def multiply_complex_exponential(self, a, b):
+        return self._call("multiply_complex_exponential", a, b)
+
+    # SymmetricTimeToFrequencyDomainOperations / SymmetricFrequencyToTimeDomainOperations / mirror
+    def mirror(self):
+        return self._call("mirror")
+
+    def plain_sfft(self):
+        return self._call("plain_sfft")
+
+    def sfft(self):
+        return self._call("sfft")
+
+    def windowed_sfft(self, window):
+        return self._call("windowed_sfft", window)
+
+    def plain_sifft(self):
+        return self._call("plain_sifft")
+
+    def sifft(self):
+        return self._call("sifft")
+
+    def windowed_sifft(self, window):
+        return self._call("windowed_sifft", window)
 
     def reverse(self):
         return self._call("reverse")

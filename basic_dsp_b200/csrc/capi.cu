@@ -692,6 +692,29 @@ template <typename T> Res<T> op_interpolatef(Vec<T>* v, const RealFn<T>& f, T fa
     return done(v, 0);
 }
 
+// multiplier table of multiply_function_priv with is_fft_shifted = true (time_freq/mod.rs:612-723, fft_swap_x :67-78):
+// ratio * f(swap(x_i) * ratio); symmetric functions are evaluated for the first half and mirrored
+// (execute_sym_pairs_with_range, threading.rs:552-612)
+template <typename T> std::vector<T> shifted_response_table(const RealFn<T>& f, bool is_symmetric, size_t points, T ratio) {
+    std::vector<T> tab(points);
+    const size_t offset = points % 2;
+    const T mx = (T)(points - offset) / (T)2;
+    const size_t c = (points - offset) / 2;
+    auto val = [&](size_t i) {
+        const T j = -mx + (T)i;
+        const T xv = j <= (T)0 ? (T)1 + j / mx : -(mx - j + (T)1) / mx;
+        return ratio * f(xv * ratio);
+    };
+    if (!is_symmetric) {
+        for (size_t i = 0; i < points; i++) tab[i] = val(i);
+    } else {
+        for (size_t i = 0; i <= c; i++) tab[i] = val(i);
+        if (offset == 0) { for (size_t i = 1; i < c; i++) tab[points - i] = tab[i]; }
+        else { for (size_t i = 0; i < c; i++) tab[points - 1 - i] = tab[i]; }
+    }
+    return tab;
+}
+
 template <typename T> Res<T> op_interpolatei(Vec<T>* v, const RealFn<T>& f, bool is_symmetric, uint32_t factor) {
     // interpolation.rs:484-538: zero_interleave -> plain_fft -> * factor*f(shifted x * factor) -> plain_ifft ->
     // scale(1/points) (-> to_real).  The multiplier table follows multiply_function_priv with
@@ -714,25 +737,7 @@ template <typename T> Res<T> op_interpolatei(Vec<T>* v, const RealFn<T>& f, bool
     FftOpts fw;
     rc = fft_exec<T>(v->d, v->scratch, points, 1, fw, nullptr, 0, g_stream);
     if (rc) return done(v, rc);
-    std::vector<T> tab(points);
-    {
-        const T ratio = (T)factor;
-        const size_t offset = points % 2;
-        const T mx = (T)(points - offset) / (T)2;
-        const size_t c = (points - offset) / 2;
-        auto val = [&](size_t i) {
-            const T j = -mx + (T)i;
-            const T xv = j <= (T)0 ? (T)1 + j / mx : -(mx - j + (T)1) / mx;
-            return ratio * f(xv * ratio);
-        };
-        if (!is_symmetric) {
-            for (size_t i = 0; i < points; i++) tab[i] = val(i);
-        } else {
-            for (size_t i = 0; i <= c; i++) tab[i] = val(i);
-            if (offset == 0) { for (size_t i = 1; i < c; i++) tab[points - i] = tab[i]; }
-            else { for (size_t i = 0; i < c; i++) tab[points - 1 - i] = tab[i]; }
-        }
-    }
+    std::vector<T> tab = shifted_response_table<T>(f, is_symmetric, points, (T)factor);
     T* dev = nullptr;
     rc = upload_table(tab, &dev);
     if (!rc) rc = ew_mul_table<T>(v->scratch, dev, points, 1, 0, g_stream);
@@ -748,6 +753,156 @@ template <typename T> Res<T> op_interpolatei(Vec<T>* v, const RealFn<T>& f, bool
     if (rc) return done(v, rc);
     trade(v);
     v->len = points;
+    return done(v, 0);
+}
+
+
+template <typename T> Res<T> op_interpolate(Vec<T>* v, const RealFn<T>* f, bool is_symmetric, size_t dest_points, T delay) {
+    // interpolation.rs:541-604 (f == nullptr: interpft :533-539)
+    if (f && !is_symmetric && !v->is_complex) return done(v, 10);   // ArgumentFunctionMustBeSymmetric
+    const bool was_complex = v->is_complex != 0;
+    const size_t n = points_of(v);
+    if (!n || !dest_points) return done(v, E_ARG_LEN);
+    const T delta_t = v->delta;
+    const T factor = (T)dest_points / (T)n;
+    int rc = 0;
+    if (!was_complex) {
+        rc = ensure_scratch(v, 2 * n);
+        if (!rc) rc = ew_zero_interleave<T>(v->d, v->scratch, n, 2, 1, g_stream);
+        if (rc) return done(v, rc);
+        trade(v);
+    }
+    const size_t big = 2 * (n > dest_points ? n : dest_points);
+    rc = ensure_scratch(v, big);
+    FftOpts fw;
+    if (!rc) rc = fft_exec<T>(v->d, v->scratch, n, 1, fw, nullptr, 0, g_stream);
+    if (!rc) rc = reserve(&v->d, &v->cap, big, false, 0);
+    if (rc) return done(v, rc);
+    // spectrum in the scratch -> re-binned spectrum in d
+    T* dev = nullptr;
+    bool have_table = false;
+    double scale = 1.0;
+    int use_scale = 0;
+    if (dest_points > n) {
+        if (f) {
+            std::vector<T> tab = shifted_response_table<T>(*f, is_symmetric, dest_points, factor);
+            rc = upload_table(tab, &dev);
+            if (rc) return done(v, rc);
+            have_table = true;
+        } else { scale = (double)factor; use_scale = 1; }
+    } else if (dest_points < n) {
+        scale = (double)((T)(2 * dest_points) / (T)(2 * n));
+        use_scale = 1;
+    }
+    const T pi = (T)M_PI;
+    const T phase_inc = (T)2 * pi * (delay / delta_t) / (T)n;
+    rc = ew_resample_spectrum<T>(v->scratch, v->d, n, dest_points, dev, scale, use_scale, (double)phase_inc, delay != (T)0, g_stream);
+    if (have_table) table_consumed();
+    if (rc) return done(v, rc);
+    FftOpts inv;
+    inv.inverse = 1;
+    inv.scale = (double)((T)1 / (T)dest_points);
+    rc = fft_exec<T>(v->d, v->scratch, dest_points, 1, inv, nullptr, 0, g_stream);
+    if (rc) return done(v, rc);
+    if (was_complex) {
+        trade(v);
+        v->len = 2 * dest_points;
+    } else {
+        rc = ew_complex_to_real<T>(C2R_REAL, v->scratch, v->d, dest_points, g_stream);
+        if (rc) return done(v, rc);
+        v->len = dest_points;
+    }
+    v->delta = delta_t / factor;
+    return done(v, 0);
+}
+
+template <typename T> Res<T> op_mul_cexp(Vec<T>* v, T a, T b) {
+    if (!v->is_complex) { mark_invalid(v); return done(v, 0); }
+    const T aa = a * v->delta, bb = b * v->delta;
+    return done(v, ew_mul_cexp<T>(v->d, points_of(v), (double)aa, (double)bb, g_stream));
+}
+
+template <typename T> Res<T> op_mirror(Vec<T>* v) {
+    // freq.rs:52-83
+    if (v->domain != 1 && !v->is_complex) { mark_invalid(v); return done(v, 0); }
+    const size_t p = v->len / 2;
+    if (!p) return done(v, 0);
+    int rc = ensure_scratch(v, 2 * (2 * p - 1));
+    if (!rc) rc = ew_mirror<T>(v->d, v->scratch, p, g_stream);
+    if (rc) return done(v, rc);
+    trade(v);
+    v->len = 2 * (2 * p - 1);
+    return done(v, 0);
+}
+
+template <typename T> Res<T> op_sfft(Vec<T>* v, bool shifted, int window) {
+    // time_to_freq.rs:197-298; kept length follows the statically typed vectors: (n + 1) / 2 complex points
+    if (v->domain != 0 || v->is_complex) {
+        mark_invalid(v); v->is_complex = 1; v->domain = 1;
+        return done(v, E_TIME);
+    }
+    const size_t n = v->len;
+    if (n % 2 == 0) {
+        mark_invalid(v); v->is_complex = 1; v->domain = 1;
+        return done(v, 9);   // InputMustHaveAnOddLength
+    }
+    if (window >= 0) {
+        Res<T> r = op_window(v, window, false);
+        if (r.result_code) return r;
+    }
+    Res<T> r = op_fft(v, false, shifted, false);
+    if (r.result_code) return r;
+    v->len = n + 1;
+    // The DC bin of a real signal is real.  Mixed-radix transforms deliver an exact zero there (which
+    // plain_sifft's |Im X[0]| <= 1e-10 test relies on, freq_to_time.rs:204); the chirp-z path used for
+    // general odd lengths leaves rounding noise, so the exact value is stored.
+    const size_t dc = shifted ? (n - 1) / 2 : 0;
+    cudaError_t e = cudaMemsetAsync(v->d + 2 * dc + 1, 0, sizeof(T), g_stream);
+    if (e != cudaSuccess) { set_last_error("sfft: %s", cudaGetErrorString(e)); return done(v, -1000 - (int)e); }
+    return done(v, 0);
+}
+
+template <typename T> Res<T> op_sifft(Vec<T>* v, bool shifted, int window) {
+    // freq_to_time.rs:190-248
+    if (shifted) {
+        const size_t points = points_of(v);
+        if (points) {
+            int rc = ew_scalar<T>(EW_SCALE, v->d, v->d, v->len, (double)((T)1 / (T)points), g_stream);
+            if (rc) return done(v, rc);
+        }
+        Res<T> r = op_rotate(v, false);
+        if (r.result_code) return r;
+    }
+    if (v->domain != 1 || !v->is_complex) {
+        mark_invalid(v); v->is_complex = 1; v->domain = 1;
+        return done(v, E_FREQ);
+    }
+    const size_t p = points_of(v);
+    if (p) {
+        T im0 = 0;
+        cudaError_t e = cudaMemcpyAsync(&im0, v->d + 1, sizeof(T), cudaMemcpyDeviceToHost, g_stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(g_stream);
+        if (e != cudaSuccess) { set_last_error("plain_sifft: %s", cudaGetErrorString(e)); return done(v, -1000 - (int)e); }
+        if (fabs((double)im0) > 1e-10) {
+            mark_invalid(v); v->is_complex = 1; v->domain = 1;
+            return done(v, 8);   // InputMustBeConjSymmetric
+        }
+    }
+    Res<T> r = op_mirror(v);
+    if (r.result_code) return r;
+    r = op_fft(v, true, false, false);
+    if (r.result_code) return r;
+    const size_t points = points_of(v);
+    if (points) {
+        int rc = ensure_scratch(v, points);
+        if (!rc) rc = ew_complex_to_real<T>(C2R_REAL, v->d, v->scratch, points, g_stream);
+        if (rc) return done(v, rc);
+        trade(v);
+    }
+    v->len = points;
+    v->is_complex = 0;
+    v->domain = 0;
+    if (window >= 0) return op_window(v, window, true);
     return done(v, 0);
 }
 
@@ -1006,6 +1161,23 @@ template <typename R, typename T> static inline R as_res(Res<T> r) {
         RealFn<T> f; f.kind = 2; f.fn = fn; f.data = data; f.freq = true;                                              \
         return as_res<RES>(op_interpolatei<T>(VEC(v), f, is_symmetric != 0, (uint32_t)factor));                        \
     }                                                                                                                  \
+    extern "C" RES interpolate##S(HV* v, int32_t kind, T rolloff, size_t dest_points, T delay) {                       \
+        RealFn<T> f; f.kind = kind == 0 ? 0 : 1; f.rolloff = rolloff; f.freq = true;                                   \
+        return as_res<RES>(op_interpolate<T>(VEC(v), &f, true, dest_points, delay));                                   \
+    }                                                                                                                  \
+    extern "C" RES interpolate_custom##S(HV* v, RFN fn, const void* data, uint8_t is_symmetric, size_t dest_points, T delay) { \
+        RealFn<T> f; f.kind = 2; f.fn = fn; f.data = data; f.freq = true;                                              \
+        return as_res<RES>(op_interpolate<T>(VEC(v), &f, is_symmetric != 0, dest_points, delay));                      \
+    }                                                                                                                  \
+    extern "C" RES interpft##S(HV* v, size_t dest_points) { return as_res<RES>(op_interpolate<T>(VEC(v), nullptr, true, dest_points, (T)0)); } \
+    extern "C" RES multiply_complex_exponential##S(HV* v, T a, T b) { return as_res<RES>(op_mul_cexp(VEC(v), a, b)); } \
+    extern "C" RES mirror##S(HV* v) { return as_res<RES>(op_mirror(VEC(v))); }                                         \
+    extern "C" RES plain_sfft##S(HV* v) { return as_res<RES>(op_sfft(VEC(v), false, -1)); }                            \
+    extern "C" RES sfft##S(HV* v) { return as_res<RES>(op_sfft(VEC(v), true, -1)); }                                   \
+    extern "C" RES windowed_sfft##S(HV* v, int32_t w) { return as_res<RES>(op_sfft(VEC(v), true, w < 0 || w > 3 ? 3 : w)); } \
+    extern "C" RES plain_sifft##S(HV* v) { return as_res<RES>(op_sifft(VEC(v), false, -1)); }                          \
+    extern "C" RES sifft##S(HV* v) { return as_res<RES>(op_sifft(VEC(v), true, -1)); }                                 \
+    extern "C" RES windowed_sifft##S(HV* v, int32_t w) { return as_res<RES>(op_sifft(VEC(v), true, w < 0 || w > 3 ? 3 : w)); } \
     extern "C" RES apply_window##S(HV* v, int32_t w) { return as_res<RES>(op_window(VEC(v), w, false)); }              \
     extern "C" RES unapply_window##S(HV* v, int32_t w) { return as_res<RES>(op_window(VEC(v), w, true)); }             \
     extern "C" RES windowed_fft##S(HV* v, int32_t w) { return as_res<RES>(op_windowed_fft(VEC(v), w)); }               \

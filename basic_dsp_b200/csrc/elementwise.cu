@@ -269,6 +269,70 @@ __global__ void mul_table_kernel(T* __restrict__ data, const T* __restrict__ tab
     }
 }
 
+
+// ---- FFT-based resampling: spectrum re-binning (interpolation.rs:541-604) ----------------------------
+// out[k] (dest bins) = in[src(k)] * phase(src) * (table ? table[k] : 1) * scale, zero where the padded
+// spectrum has no source bin.  n > dest: keep the first ceil(dest/2) and last floor(dest/2) bins;
+// n < dest: zero_pad Center (first ceil(n/2) bins in front, last floor(n/2) at the end).
+// phase: apply_linear_phase (interpolation.rs:319-339): bin i < n/2 -> exp(j*inc*i), else exp(j*inc*(i-n)).
+template <typename T>
+__global__ void resample_spectrum_kernel(const typename CpxOf<T>::type* __restrict__ in, typename CpxOf<T>::type* __restrict__ out,
+                                         long long n, long long dest, const T* __restrict__ table, T scale, int use_scale,
+                                         double phase_inc, int use_phase) {
+    typedef typename CpxOf<T>::type C;
+    typedef Arith<T> A;
+    long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; k < dest; k += stride) {
+        long long src;
+        if (dest >= n) {
+            const long long right = n / 2, left = n - right;
+            src = k < left ? k : (k >= dest - right ? k - (dest - n) : -1);
+        } else {
+            const long long neg = dest / 2, pos = dest - neg;
+            src = k < pos ? k : k + (n - dest);
+        }
+        C v = mk<T>((T)0, (T)0);
+        if (src >= 0) {
+            v = in[src];
+            if (use_phase) {
+                const long long m = src < n / 2 ? src : src - n;
+                double sn, cs;
+                sincos(phase_inc * (double)m, &sn, &cs);
+                v = cmul_nofma(v, mk<T>((T)cs, (T)sn));
+            }
+            if (table) { const T w = table[k]; v = cmul_nofma(v, mk<T>(w, (T)0)); }
+            if (use_scale) { v.x = A::mul(v.x, scale); v.y = A::mul(v.y, scale); }
+        }
+        out[k] = v;
+    }
+}
+
+// mirror (freq.rs:52-83): p points -> 2p - 1 points, out[p + i] = conj(in[p - 1 - i])
+template <typename T>
+__global__ void mirror_kernel(const typename CpxOf<T>::type* __restrict__ in, typename CpxOf<T>::type* __restrict__ out, long long p) {
+    typedef typename CpxOf<T>::type C;
+    long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long total = 2 * p - 1;
+    for (; k < total; k += stride) {
+        if (k < p) out[k] = in[k];
+        else { C v = in[total - k]; out[k] = mk<T>(v.x, -v.y); }
+    }
+}
+
+// multiply_complex_exponential (complex_ops.rs:81-105)
+template <typename T>
+__global__ void mul_cexp_kernel(typename CpxOf<T>::type* __restrict__ data, long long points, double a, double b) {
+    long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; k < points; k += stride) {
+        double sn, cs;
+        sincos(a * (double)k + b, &sn, &cs);
+        data[k] = cmul_nofma(data[k], mk<T>((T)cs, (T)sn));
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // host wrappers
 // ------------------------------------------------------------------------------------------
@@ -396,7 +460,38 @@ int ew_mul_table(void* data, const void* table, size_t points, int is_complex, i
     return 0;
 }
 
+
+template <typename T>
+int ew_resample_spectrum(const void* in, void* out, size_t n, size_t dest, const void* table, double scale, int use_scale,
+                         double phase_inc, int use_phase, cudaStream_t st) {
+    typedef typename CpxOf<T>::type C;
+    if (!dest) return 0;
+    resample_spectrum_kernel<T><<<ew_grid((long long)dest, 256), 256, 0, st>>>(reinterpret_cast<const C*>(in), reinterpret_cast<C*>(out),
+        (long long)n, (long long)dest, reinterpret_cast<const T*>(table), (T)scale, use_scale, phase_inc, use_phase);
+    BDSP_LAUNCHED();
+    return 0;
+}
+template <typename T>
+int ew_mirror(const void* in, void* out, size_t points, cudaStream_t st) {
+    typedef typename CpxOf<T>::type C;
+    if (!points) return 0;
+    mirror_kernel<T><<<ew_grid((long long)(2 * points - 1), 256), 256, 0, st>>>(reinterpret_cast<const C*>(in), reinterpret_cast<C*>(out), (long long)points);
+    BDSP_LAUNCHED();
+    return 0;
+}
+template <typename T>
+int ew_mul_cexp(void* data, size_t points, double a, double b, cudaStream_t st) {
+    typedef typename CpxOf<T>::type C;
+    if (!points) return 0;
+    mul_cexp_kernel<T><<<ew_grid((long long)points, 256), 256, 0, st>>>(reinterpret_cast<C*>(data), (long long)points, a, b);
+    BDSP_LAUNCHED();
+    return 0;
+}
+
 #define BDSP_INST(T)                                                                                     \
+    template int ew_resample_spectrum<T>(const void*, void*, size_t, size_t, const void*, double, int, double, int, cudaStream_t); \
+    template int ew_mirror<T>(const void*, void*, size_t, cudaStream_t);                                  \
+    template int ew_mul_cexp<T>(void*, size_t, double, double, cudaStream_t);                             \
     template int ew_scalar<T>(int, const void*, void*, size_t, double, cudaStream_t);                     \
     template int ew_complex_const<T>(int, const void*, void*, size_t, double, double, cudaStream_t);      \
     template int ew_binary<T>(int, const void*, const void*, void*, size_t, int, cudaStream_t);           \

@@ -159,6 +159,20 @@ BdspVecResult32 interpolatei32(BdspVec32* vector, int32_t frequency_response, fl
 BdspVecResult32 interpolatei_custom32(BdspVec32* vector, BdspRealFn32 frequency_response, const void* frequency_response_data,
                                       uint8_t is_symmetric, int32_t interpolation_factor);     /* :1402 */
 
+/* FFT-based resampling, symmetric (real <-> half spectrum) transforms, complex exponential */
+BdspVecResult32 interpolate32(BdspVec32* vector, int32_t frequency_response, float rolloff, size_t dest_points, float delay); /* :1379 */
+BdspVecResult32 interpolate_custom32(BdspVec32* vector, BdspRealFn32 frequency_response, const void* frequency_response_data,
+                                     uint8_t is_symmetric, size_t dest_points, float delay);   /* :1353 */
+BdspVecResult32 interpft32(BdspVec32* vector, size_t dest_points);       /* :1390 */
+BdspVecResult32 multiply_complex_exponential32(BdspVec32* vector, float a, float b); /* :695 */
+BdspVecResult32 mirror32(BdspVec32* vector);                             /* :959 */
+BdspVecResult32 plain_sfft32(BdspVec32* vector);                         /* :677; odd real length n -> (n + 1) / 2 bins */
+BdspVecResult32 sfft32(BdspVec32* vector);                               /* :939 */
+BdspVecResult32 windowed_sfft32(BdspVec32* vector, int32_t window);      /* :1004 */
+BdspVecResult32 plain_sifft32(BdspVec32* vector);                        /* :949; result code 8 unless Im X[0] == 0 */
+BdspVecResult32 sifft32(BdspVec32* vector);                              /* :954 */
+BdspVecResult32 windowed_sifft32(BdspVec32* vector, int32_t window);     /* :1018 */
+
 /* ---- f64 twins (interop/src/facade64.rs, same line numbers + 1) ------------------------------------------------ */
 BdspVecResult64 apply_window64(BdspVec64* vector, int32_t window);
 BdspVecResult64 unapply_window64(BdspVec64* vector, int32_t window);
@@ -172,6 +186,19 @@ BdspVecResult64 decimatei64(BdspVec64* vector, uint32_t decimation_factor, uint3
 BdspVecResult64 interpolatei64(BdspVec64* vector, int32_t frequency_response, double rolloff, int32_t interpolation_factor);
 BdspVecResult64 interpolatei_custom64(BdspVec64* vector, BdspRealFn64 frequency_response, const void* frequency_response_data,
                                       uint8_t is_symmetric, int32_t interpolation_factor);
+
+BdspVecResult64 interpolate64(BdspVec64* vector, int32_t frequency_response, double rolloff, size_t dest_points, double delay);
+BdspVecResult64 interpolate_custom64(BdspVec64* vector, BdspRealFn64 frequency_response, const void* frequency_response_data,
+                                     uint8_t is_symmetric, size_t dest_points, double delay);
+BdspVecResult64 interpft64(BdspVec64* vector, size_t dest_points);
+BdspVecResult64 multiply_complex_exponential64(BdspVec64* vector, double a, double b);
+BdspVecResult64 mirror64(BdspVec64* vector);
+BdspVecResult64 plain_sfft64(BdspVec64* vector);
+BdspVecResult64 sfft64(BdspVec64* vector);
+BdspVecResult64 windowed_sfft64(BdspVec64* vector, int32_t window);
+BdspVecResult64 plain_sifft64(BdspVec64* vector);
+BdspVecResult64 sifft64(BdspVec64* vector);
+BdspVecResult64 windowed_sifft64(BdspVec64* vector, int32_t window);
 BdspVec64* new64(int32_t is_complex, int32_t domain, double init_value, size_t length, double delta);
 BdspVec64* new_with_performance_options64(int32_t is_complex, int32_t domain, double init_value, size_t length, double delta, size_t core_limit);
 BdspVec64* new_with_detailed_performance_options64(int32_t is_complex, int32_t domain, double init_value, size_t length,

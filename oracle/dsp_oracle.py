@@ -697,6 +697,142 @@ def interpolatei(x, f, factor, dtype):
     return y if is_complex else y.real.copy()
 
 
+ERR_CONJ_SYMMETRIC = 8
+ERR_ODD_LENGTH = 9
+ERR_FUNCTION_SYMMETRIC = 10
+
+
+def zero_pad_center(X, points):
+    """zero_pad(points, PaddingOption::Center) (data_reorganization.rs:343-357): the first
+    ceil(n/2) points stay in front, the last floor(n/2) points move to the end, zeros in between."""
+    X = np.asarray(X)
+    n = len(X)
+    right = n // 2
+    left = n - right
+    out = np.zeros(points, dtype=X.dtype)
+    out[:left] = X[:left]
+    if right:
+        out[points - right:] = X[left:left + right]
+    return out
+
+
+def linear_phase_table(points, delay, dtype):
+    """apply_linear_phase (interpolation.rs:319-339): element i < points/2 is rotated by
+    exp(j*inc*i), element i >= points/2 by exp(j*inc*(i - points)), inc = 2*pi*delay/points in T.
+    The reference advances the phasor by repeated multiplication (complex_ops.rs:95-102); the restatement
+    evaluates each angle directly (the difference is rounding drift of the reference's recurrence)."""
+    T = _T(dtype)
+    pos = points // 2
+    neg = points - pos
+    inc = T(T(2) * T(np.pi) * T(delay) / T(points))
+    ang = np.empty(points, dtype=np.float64)
+    ang[:pos] = float(inc) * np.arange(pos)
+    ang[pos:] = float(T(-T(neg) * inc)) + float(inc) * np.arange(neg)
+    return np.exp(1j * ang)
+
+
+def interpolate(x, f, dest_points, delay, dtype, delta=1.0):
+    """InterpolationOps::interpolate (interpolation.rs:541-604); f = None is interpft (:533-539).
+    plain_fft -> linear phase (delay/delta) -> [upsample: zero_pad Center, * factor * f(shifted x * factor)
+    (or * factor without f) | downsample: keep the first ceil(d/2) and the last floor(d/2) bins, scale d/n]
+    -> plain_ifft -> scale(1/dest_points) (-> real part for real input)."""
+    T = _T(dtype)
+    x = np.asarray(x)
+    is_complex = np.iscomplexobj(x)
+    n = len(x)
+    factor = T(dest_points) / T(n)
+    X = plain_fft(x.astype(np.complex128))
+    if delay != 0:
+        X = X * linear_phase_table(n, T(delay) / T(delta), dtype)
+    if dest_points > n:
+        X = zero_pad_center(X, dest_points)
+        if f is None:
+            X = X * float(factor)
+        else:
+            X = X * shifted_response_table(f, dest_points, factor, dtype).astype(np.float64)
+    elif dest_points < n:
+        neg = dest_points // 2
+        pos = dest_points - neg
+        X = np.concatenate([X[:pos], X[n - neg:]]) if neg else X[:pos].copy()
+        X = X * float(T(2 * dest_points) / T(2 * n))
+    y = plain_ifft(X) / dest_points
+    return y if is_complex else y.real.copy()
+
+
+def interpft(x, dest_points, dtype):
+    return interpolate(x, None, dest_points, 0.0, dtype)
+
+
+def conj(x):
+    return np.conj(np.asarray(x))
+
+
+def multiply_complex_exponential(x, a, b, dtype, delta=1.0):
+    """ComplexOps::multiply_complex_exponential (complex_ops.rs:81-105): x[i] *= exp(j*(a*delta*i + b*delta))."""
+    T = _T(dtype)
+    a = T(T(a) * T(delta))
+    b = T(T(b) * T(delta))
+    i = np.arange(len(x))
+    return np.asarray(x).astype(np.complex128) * np.exp(1j * (float(a) * i + float(b)))
+
+
+def mirror(X):
+    """FrequencyDomainOperations::mirror (freq.rs:52-83): [X0, X1 .. X(p-1)] -> [X0, X1 .. X(p-1),
+    conj X(p-1) .. conj X1]  (2p - 1 points)."""
+    X = np.asarray(X)
+    return np.concatenate([X, np.conj(X[1:][::-1])])
+
+
+def plain_sfft(x):
+    """SymmetricTimeToFrequencyDomainOperations::plain_sfft (time_to_freq.rs:197-230) for a statically
+    real vector with an odd number n of points: the first (n + 1)/2 bins of the complex transform.
+    (Through the interop's dynamically typed vector the reference computes the kept length from the
+    complex point count and keeps n/2 + 1 SCALARS - an odd, rejected length for n = 1 mod 4; the drop-in
+    follows the statically typed behaviour its own test real_fft_test32 exercises.)"""
+    x = np.asarray(x)
+    assert not np.iscomplexobj(x) and len(x) % 2 == 1
+    return plain_fft(x.astype(np.complex128))[: (len(x) + 1) // 2]
+
+
+def sfft(x):
+    """sfft (time_to_freq.rs:232-264): fft (shifted) then the same truncation: bins -(n-1)/2 .. 0."""
+    x = np.asarray(x)
+    assert not np.iscomplexobj(x) and len(x) % 2 == 1
+    return fft(x.astype(np.complex128))[: (len(x) + 1) // 2]
+
+
+def windowed_sfft(x, kind, dtype):
+    """windowed_sfft (time_to_freq.rs:266-298): window on the complexified vector, then sfft."""
+    return sfft_of_complexified(apply_window(np.asarray(x).astype(dtype), kind, dtype))
+
+
+def sfft_of_complexified(x):
+    return fft(np.asarray(x).astype(np.complex128))[: (len(x) + 1) // 2]
+
+
+def plain_sifft(X):
+    """plain_sifft (freq_to_time.rs:190-221): needs Im X[0] ~ 0 (|.| <= 1e-10, else
+    InputMustBeConjSymmetric); mirror -> unnormalised inverse transform -> real part (2p - 1 points)."""
+    X = np.asarray(X).astype(np.complex128)
+    if len(X) and abs(X[0].imag) > 1e-10:
+        return ERR_CONJ_SYMMETRIC
+    return plain_ifft(mirror(X)).real.copy()
+
+
+def sifft(X):
+    """sifft (freq_to_time.rs:223-234): scale(1/points) with the HALF spectrum's point count,
+    ifft_shift of the half spectrum, plain_sifft."""
+    X = np.asarray(X).astype(np.complex128)
+    return plain_sifft(ifft_shift(X / len(X)))
+
+
+def windowed_sifft(X, kind, dtype):
+    y = sifft(X)
+    if isinstance(y, int):
+        return y
+    return y * window_table(kind, len(y), dtype, unapply=True).astype(np.float64)
+
+
 def reverse(x):
     return np.asarray(x)[::-1].copy()
 

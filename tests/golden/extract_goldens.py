@@ -45,6 +45,13 @@ CASES = [
     ("time_correlation_test_c", "vector/src/vector_types/time_freq/correlation.rs", "time_correlation_test", "c"),
     ("time_correlation_test2_c", "vector/src/vector_types/time_freq/correlation.rs", "time_correlation_test2", "c"),
     ("interpolatei_sinc_test", "vector/src/vector_types/time_freq/interpolation.rs", "interpolatei_sinc_test", "expected"),
+    ("interpolate_sinc_even_test", "vector/src/vector_types/time_freq/interpolation.rs", "interpolate_sinc_even_test", "expected"),
+    ("interpolate_sinc_odd_test", "vector/src/vector_types/time_freq/interpolation.rs", "interpolate_sinc_odd_test", "expected"),
+    ("interpolate_by_fractional_sinc_test", "vector/src/vector_types/time_freq/interpolation.rs", "interpolate_by_fractional_sinc_test", "expected"),
+    ("interpolate_by_fractional_sinc_real_data_test", "vector/src/vector_types/time_freq/interpolation.rs", "interpolate_by_fractional_sinc_real_data_test", "expected"),
+    ("interpolate_delayed_sinc_test", "vector/src/vector_types/time_freq/interpolation.rs", "interpolate_delayed_sinc_test", "expected"),
+    ("interpolate_identity", "vector/src/vector_types/time_freq/interpolation.rs", "interpolate_identity", "expected"),
+    ("decimate_with_interpolate_test", "vector/src/vector_types/time_freq/interpolation.rs", "decimate_with_interpolate_test", "expected"),
     ("interpolatei_rc_test", "vector/src/vector_types/time_freq/interpolation.rs", "interpolatei_rc_test", "expected"),
     ("triangular_window32_test", "vector/src/window_functions.rs", "triangular_window32_test", "expected"),
     ("hamming_window32_test", "vector/src/window_functions.rs", "hamming_window32_test", "expected"),

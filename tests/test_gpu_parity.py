@@ -577,3 +577,111 @@ def test_interpolatei(kats):  # interpolation.rs:653-680, 722-750 + tests/interp
     back = DspVec(x).interpolatei(bd.SINC, 0.0, 4).decimatei(4, 0).to_numpy()
     assert np.max(np.abs(back - x)) < 1e-3
     assert DspVec(x).result_code_of("interpolatei", 0, 0.0, 1) == 0   # factor <= 1: no-op
+
+
+# --------------------------------------------------------------------------------------------------
+# FFT-based resampling (interpolate / interpft), symmetric transforms, mirror, complex exponential
+# --------------------------------------------------------------------------------------------------
+def test_interpolate_kats(kats):  # interpolation.rs:681-720, 834-1008
+    FIR5 = [0.019827, 0.132513, 0.347660, 0.347660, 0.132513, 0.019827]
+    FIR12 = [-2.6551e-03, 1.5106e-04, 1.6104e-02, 5.9695e-02, 1.2705e-01, 1.9096e-01, 2.1739e-01, 1.9096e-01,
+             1.2705e-01, 5.9695e-02, 1.6104e-02, 1.5106e-04, -2.6551e-03]
+    d6 = np.zeros(6, dtype=np.complex64); d6[3] = 1
+    d7 = np.zeros(7, dtype=np.complex64); d7[3] = 1
+    got = DspVec(d6).interpolate(bd.SINC, 0.0, 12, 0.0).to_real().to_numpy()
+    assert np.max(np.abs(got - vals(kats, "interpolate_sinc_even_test"))) < 1e-4
+    got = DspVec(d7).interpolate(bd.SINC, 0.0, 14, 0.0).to_real().to_numpy()
+    assert np.max(np.abs(got - vals(kats, "interpolate_sinc_odd_test"))) < 1e-4
+    got = DspVec(d6).interpolate(bd.SINC, 0.0, 13, 0.0).to_real().to_numpy()
+    assert np.max(np.abs(got - vals(kats, "interpolate_by_fractional_sinc_test"))) < 0.1
+    r6 = np.zeros(6, dtype=np.float32); r6[3] = 1
+    v = DspVec(r6).interpolate(bd.SINC, 0.0, 13, 0.0)
+    assert not v.is_complex() and v.len() == 13
+    assert np.max(np.abs(v.to_numpy() - vals(kats, "interpolate_by_fractional_sinc_real_data_test"))) < 0.1
+    got = DspVec(np.array(FIR5, dtype=np.complex64)).interpolate(bd.SINC, 0.0, 12, 1.0).magnitude().to_numpy()
+    assert np.max(np.abs(got - vals(kats, "interpolate_delayed_sinc_test"))) < 0.1
+    got = DspVec(np.array(FIR5, dtype=np.float32)).interpft(6).to_numpy()
+    assert np.max(np.abs(got - vals(kats, "interpolate_identity"))) < 0.1
+    got = DspVec(np.array(FIR12, dtype=np.complex64)).interpolate(bd.SINC, 0.0, 6, 0.0).magnitude().to_numpy()
+    assert np.max(np.abs(got - vals(kats, "decimate_with_interpolate_test"))) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_interpolate_vs_oracle(dtype):
+    rng = np.random.default_rng(77)
+    cases = [(1000, 2500, True, 0.0, "rc"), (777, 1000, True, 1.5, "rc"), (512, 2048, False, 0.0, "sinc"),
+             (1001, 333, True, 0.25, "sinc"), (4096, 1024, False, 0.0, None), (300, 300, True, 2.0, None),
+             (5000, 65536, True, 0.0, None), (1 << 16, 1 << 18, False, 3.0, "rc")]
+    for n, dest, cplx_, delay, kind in cases:
+        x = rand_c(rng, n, dtype) if cplx_ else rng.uniform(-10, 10, n).astype(dtype)
+        delta = 0.5
+        if kind == "rc":
+            f = lambda t: o.raised_cosine_freq(t, 0.35, dtype)
+            got = DspVec(x, delta=delta).interpolate(bd.RAISED_COSINE, 0.35, dest, delay)
+        elif kind == "sinc":
+            f = lambda t: o.sinc_freq(t, dtype)
+            got = DspVec(x, delta=delta).interpolate(bd.SINC, 0.0, dest, delay)
+        else:
+            f = None
+            got = DspVec(x, delta=delta).interpolate(None, 0.0, dest, delay) if delay == 0 else \
+                DspVec(x, delta=delta).interpolate(lambda t: 1.0, 0.0, dest, delay)
+            if delay != 0:
+                f = lambda t: dtype(1.0)
+        ref = o.interpolate(x, f, dest, delay, dtype, delta=delta)
+        assert got.is_complex() == cplx_ and got.points() == dest
+        assert o.rel_l2(got.to_numpy(), ref) <= 4 * tol(max(n, dest), dtype), (n, dest, kind)
+        assert abs(got.delta() - delta / (dtype(dest) / dtype(n))) <= 1e-6 * delta
+    # band-limited signal: interpft reproduces the signal on the finer grid
+    n, m = 4096, 10240
+    t = np.arange(n) / n
+    x = (np.cos(2 * np.pi * 30 * t) + 0.5 * np.sin(2 * np.pi * 71 * t)).astype(dtype)
+    tm = np.arange(m) / m
+    want = np.cos(2 * np.pi * 30 * tm) + 0.5 * np.sin(2 * np.pi * 71 * tm)
+    assert np.max(np.abs(DspVec(x).interpft(m).to_numpy() - want)) < (1e-4 if dtype == np.float32 else 1e-11)
+    # real vector + asymmetric callback is rejected (ArgumentFunctionMustBeSymmetric = 10)
+    v = DspVec(x)
+    cb = getattr(bd.lib(), "RealFn" + v._s)(lambda _d, t: 1.0)
+    assert v.result_code_of("interpolate_custom", cb, None, 0, m, 0.0) == 10
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_symmetric_transforms(dtype):  # tests/real_test.rs:581-605
+    rng = np.random.default_rng(201511210)
+    for n in (1001, 7, 4097, 65537):
+        x = rng.uniform(-10, 10, n).astype(dtype)
+        S = DspVec(x).plain_sfft()
+        assert S.is_complex() and S.points() == (n + 1) // 2 and S.domain() == bd.FREQ
+        full = DspVec(x).to_complex().plain_fft().to_numpy()
+        mirrored = DspVec(x).plain_sfft().mirror()
+        assert mirrored.points() == n
+        assert o.rel_l2(mirrored.to_numpy(), full) <= tol(n, dtype)              # "Different FFT paths must equal"
+        assert o.rel_l2(S.to_numpy(), o.plain_sfft(x)) <= tol(n, dtype)
+        back = DspVec(x).plain_sfft().plain_sifft()
+        assert not back.is_complex() and back.len() == n and back.domain() == bd.TIME
+        assert o.rel_l2(back.to_numpy() / n, x) <= 2 * tol(n, dtype)             # "Ifft must give back the original"
+        assert o.rel_l2(DspVec(x).sfft().to_numpy(), o.sfft(x)) <= tol(n, dtype)
+        assert o.rel_l2(DspVec(x).windowed_sfft(bd.HAMMING).to_numpy(), o.windowed_sfft(x, bd.HAMMING, dtype)) <= 2 * tol(n, dtype)
+    # sifft / windowed_sifft on a half spectrum whose shifted first bin is real
+    p = 33
+    H = rand_c(rng, p, dtype)
+    Hs = H.copy(); Hs[(p // 2)] = Hs[p // 2].real      # ifft_shift brings element p//2 to the front
+    ref = o.sifft(Hs)
+    got = DspVec(Hs, domain=bd.FREQ).sifft()
+    assert not isinstance(ref, int) and got.len() == 2 * p - 1
+    assert o.rel_l2(got.to_numpy(), ref) <= 4 * tol(2 * p, dtype)
+    got = DspVec(Hs, domain=bd.FREQ).windowed_sifft(bd.HAMMING).to_numpy()
+    assert o.rel_l2(got, o.windowed_sifft(Hs, bd.HAMMING, dtype)) <= 4 * tol(2 * p, dtype)
+    # error behaviour
+    assert DspVec(np.ones(8, dtype=dtype)).result_code_of("plain_sfft") == 9          # even length
+    assert DspVec(np.ones(7, dtype=dtype).astype(np.complex64 if dtype == np.float32 else np.complex128)).result_code_of("sfft") == 5
+    bad = rand_c(rng, 9, dtype); bad[0] = 1 + 1j
+    assert DspVec(bad, domain=bd.FREQ).result_code_of("plain_sifft") == 8           # not conj-symmetric
+    assert DspVec(bad, domain=bd.TIME).result_code_of("plain_sifft") == 6
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_multiply_complex_exponential(dtype):  # complex_ops.rs:81-105
+    rng = np.random.default_rng(3)
+    x = rand_c(rng, 5000, dtype)
+    got = DspVec(x, delta=0.5).multiply_complex_exponential(0.01, 0.3).to_numpy()
+    assert o.rel_l2(got, o.multiply_complex_exponential(x, 0.01, 0.3, dtype, delta=0.5)) <= 1e-6 if dtype == np.float32 else 1e-14

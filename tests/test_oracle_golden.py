@@ -418,3 +418,64 @@ def test_interpolatei_kats(kats):  # interpolation.rs:653-680 (sinc), :722-750 (
     assert np.max(np.abs(got - vals(kats, "interpolatei_sinc_test"))) < 1e-4
     got = np.abs(o.interpolatei(x, lambda t: o.raised_cosine_freq(t, 0.4, np.float32), 2, np.float32))
     assert np.max(np.abs(got - vals(kats, "interpolatei_rc_test"))) < 1e-4
+
+
+# --------------------------------------------------------------------------------------------------
+# FFT-based resampling (interpolate / interpft) and the symmetric transforms
+# --------------------------------------------------------------------------------------------------
+FIR5 = [0.019827, 0.132513, 0.347660, 0.347660, 0.132513, 0.019827]              # interpolation.rs:914
+FIR12 = [-2.6551e-03, 1.5106e-04, 1.6104e-02, 5.9695e-02, 1.2705e-01, 1.9096e-01, 2.1739e-01, 1.9096e-01,
+         1.2705e-01, 5.9695e-02, 1.6104e-02, 1.5106e-04, -2.6551e-03]           # interpolation.rs:975-989
+
+
+def _dirac(n, cplx=True):
+    x = np.zeros(n, dtype=np.complex128 if cplx else np.float64)
+    x[n // 2] = 1.0
+    return x
+
+
+def test_interpolate_kats(kats):  # interpolation.rs:681-720, 834-910, 912-960, 962-1008
+    f32 = np.float32
+    sinc = lambda t: o.sinc_freq(t, f32)
+    got = o.interpolate(_dirac(6), sinc, 12, 0.0, f32).real
+    assert np.max(np.abs(got - vals(kats, "interpolate_sinc_even_test"))) < 1e-4
+    got = o.interpolate(_dirac(7), sinc, 14, 0.0, f32).real
+    assert np.max(np.abs(got - vals(kats, "interpolate_sinc_odd_test"))) < 1e-4
+    got = o.interpolate(_dirac(6), sinc, 13, 0.0, f32).real
+    assert np.max(np.abs(got - vals(kats, "interpolate_by_fractional_sinc_test"))) < 0.1
+    got = o.interpolate(_dirac(6, cplx=False), sinc, 13, 0.0, f32)
+    assert not np.iscomplexobj(got)
+    assert np.max(np.abs(got - vals(kats, "interpolate_by_fractional_sinc_real_data_test"))) < 0.1
+    got = np.abs(o.interpolate(np.array(FIR5, dtype=np.complex128), sinc, 12, 1.0, f32))
+    assert np.max(np.abs(got - vals(kats, "interpolate_delayed_sinc_test"))) < 0.1
+    got = o.interpft(np.array(FIR5), 6, f32)
+    assert np.max(np.abs(got - vals(kats, "interpolate_identity"))) < 0.1
+    got = np.abs(o.interpolate(np.array(FIR12, dtype=np.complex128), sinc, 6, 0.0, f32))
+    assert np.max(np.abs(got - vals(kats, "decimate_with_interpolate_test"))) < 1e-4
+
+
+def test_interpft_is_band_limited_resampling():
+    """interpft of a band-limited periodic signal reproduces the signal on the finer grid (the property behind
+    the reference's Octave interpft comparisons, interpolation.rs:920-960)."""
+    n, m = 64, 160
+    t = np.arange(n) / n
+    x = np.cos(2 * np.pi * 3 * t) + 0.5 * np.sin(2 * np.pi * 7 * t)
+    tm = np.arange(m) / m
+    want = np.cos(2 * np.pi * 3 * tm) + 0.5 * np.sin(2 * np.pi * 7 * tm)
+    assert np.max(np.abs(o.interpft(x, m, np.float64) - want)) < 1e-12
+    # and an integer delay is a circular advance
+    got = o.interpolate(x.astype(np.complex128), None, n, 2.0, np.float64)
+    assert np.max(np.abs(got.real - np.roll(x, -2))) < 1e-12
+
+
+def test_symmetric_transforms():  # tests/real_test.rs:581-605 (real_fft_test32)
+    rng = np.random.default_rng(201511210)
+    x = rng.uniform(-10, 10, 1001)
+    S = o.plain_sfft(x)
+    assert len(S) == 501
+    assert o.rel_l2(o.mirror(S), np.fft.fft(x)) < 1e-12            # "Different FFT paths must equal"
+    back = o.plain_sifft(S) / 1001.0
+    assert np.max(np.abs(back - x)) < 1e-9                         # "Ifft must give back the original result"
+    bad = S.copy(); bad[0] += 1j
+    assert o.plain_sifft(bad) == o.ERR_CONJ_SYMMETRIC
+    assert len(o.sfft(x)) == 501 and np.allclose(o.sfft(x)[-1], np.sum(x))   # shifted: DC is the last kept bin
