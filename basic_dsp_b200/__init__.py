@@ -47,6 +47,27 @@ class _Complex64(Structure):
     _fields_ = [("re", c_double), ("im", c_double)]
 
 
+def _stats_struct(V):
+    class _Stats(Structure):  # Statistics<T>, statistics.rs:11-31 (#[repr(C)])
+        _fields_ = [("sum", V), ("count", c_size_t), ("average", V), ("rms", V), ("min", V), ("min_index", c_size_t),
+                    ("max", V), ("max_index", c_size_t)]
+    return _Stats
+
+
+_Statistics32, _Statistics64 = _stats_struct(c_float), _stats_struct(c_double)
+_ComplexStatistics32, _ComplexStatistics64 = _stats_struct(_Complex32), _stats_struct(_Complex64)
+
+
+def _scalar_result(V):
+    class _Scalar(Structure):  # ScalarInteropResult<T>, interop/src/lib.rs:229-242
+        _fields_ = [("result_code", c_int32), ("result", V)]
+    return _Scalar
+
+
+_ScalarResult32, _ScalarResult64 = _scalar_result(c_float), _scalar_result(c_double)
+_ComplexScalarResult32, _ComplexScalarResult64 = _scalar_result(_Complex32), _scalar_result(_Complex64)
+_PointerResult = _scalar_result(c_void_p)
+
 _lib = None
 
 
@@ -122,6 +143,58 @@ def _declare(lib):
             protos[name] = (_VecResult, [H])
         for name in ("prepare_argument", "prepare_argument_padded", "reverse"):
             protos[name] = (_VecResult, [H])
+        # rest of the facade: elementwise math, reorganisation, reductions
+        for name in ("sin", "cos", "tan", "asin", "acos", "atan", "sinh", "cosh", "tanh", "asinh", "acosh", "atanh", "sqrt",
+                     "square", "ln", "exp", "abs", "ln_approx", "exp_approx", "sin_approx", "cos_approx", "diff",
+                     "diff_with_start", "cum_sum"):
+            protos[name] = (_VecResult, [H])
+        for name in ("root", "powf", "log", "expf", "wrap", "unwrap", "log_approx", "expf_approx", "powf_approx"):
+            protos[name] = (_VecResult, [H, T])
+        for name in ("add_smaller_vector", "sub_smaller_vector", "mul_smaller_vector", "div_smaller_vector"):
+            protos[name] = (_VecResult, [H, H])
+        protos["get_real_imag"] = (c_int32, [H, H, H])
+        protos["set_real_imag"] = (_VecResult, [H, H, H])
+        protos["set_mag_phase"] = (_VecResult, [H, H, H])
+        protos["split_into"] = (c_int32, [H, POINTER(c_void_p), c_size_t])
+        protos["merge"] = (_VecResult, [H, POINTER(c_void_p), c_size_t])
+        protos["interpolate_hermite"] = (_VecResult, [H, T, T])
+        WFN = ctypes.CFUNCTYPE(T, c_void_p, c_size_t, c_size_t)
+        setattr(lib, "WindowFn" + s, WFN)
+        for name in ("apply_custom_window", "unapply_custom_window", "windowed_custom_fft", "windowed_custom_ifft",
+                     "windowed_custom_sfft", "windowed_custom_sifft"):
+            protos[name] = (_VecResult, [H, WFN, c_void_p, c_uint8])
+        MAPR = ctypes.CFUNCTYPE(T, T, c_size_t)
+        setattr(lib, "MapRealFn" + s, MAPR)
+        protos["map_inplace_real"] = (_VecResult, [H, MAPR])
+        protos["map_inplace_complex"] = (_VecResult, [H, c_void_p])      # struct-returning callback: native pointer only
+        AGGM = ctypes.CFUNCTYPE(c_void_p, T, c_size_t)
+        AGG = ctypes.CFUNCTYPE(c_void_p, c_void_p, c_void_p)
+        setattr(lib, "MapAggregateRealFn" + s, AGGM)
+        setattr(lib, "AggregateFn" + s, AGG)
+        protos["map_aggregate_real"] = (_PointerResult, [H, AGGM, AGG])
+        protos["map_aggregate_complex"] = (_PointerResult, [H, c_void_p, AGG])
+        SR, CSR = (_ScalarResult32, _ComplexScalarResult32) if s == "32" else (_ScalarResult64, _ComplexScalarResult64)
+        ST, CST = (_Statistics32, _ComplexStatistics32) if s == "32" else (_Statistics64, _ComplexStatistics64)
+        protos["real_dot_product"] = (SR, [H, H])
+        protos["real_dot_product_prec"] = (SR, [H, H])
+        protos["complex_dot_product"] = (CSR, [H, H])
+        protos["complex_dot_product_prec"] = (CSR, [H, H])
+        protos["real_sum"] = (T, [H])
+        protos["real_sum_sq"] = (T, [H])
+        protos["complex_sum"] = (CT, [H])
+        protos["complex_sum_sq"] = (CT, [H])
+        protos["real_sum_prec"] = (c_double, [H])
+        protos["real_sum_sq_prec"] = (c_double, [H])
+        protos["complex_sum_prec"] = (_Complex64, [H])
+        protos["complex_sum_sq_prec"] = (_Complex64, [H])
+        protos["real_statistics"] = (ST, [H])
+        protos["complex_statistics"] = (CST, [H])
+        protos["real_statistics_prec"] = (_Statistics64, [H])
+        protos["complex_statistics_prec"] = (_ComplexStatistics64, [H])
+        protos["real_statistics_split"] = (c_int32, [H, POINTER(ST), c_size_t])
+        protos["complex_statistics_split"] = (c_int32, [H, POINTER(CST), c_size_t])
+        protos["real_statistics_split_prec"] = (c_int32, [H, POINTER(_Statistics64), c_size_t])
+        protos["complex_statistics_split_prec"] = (c_int32, [H, POINTER(_ComplexStatistics64), c_size_t])
         for name in ("conj", "to_complex", "magnitude", "magnitude_squared", "phase", "to_real", "to_imag",
                      "plain_fft", "plain_ifft", "fft", "ifft", "swap_halves", "fft_shift", "ifft_shift"):
             protos[name] = (_VecResult, [H])
@@ -485,6 +558,85 @@ class DspVec:
 
     def reverse(self):
         return self._call("reverse")
+
+    # -- rest of the facade: TrigOps / PowerOps / RealOps / ModuloOps / ApproximatedOps / DiffSumOps ------------------
+    def math(self, name, *args):
+        """sin, cos, tan, asin, acos, atan, sinh, cosh, tanh, asinh, acosh, atanh, sqrt, square, ln, exp, abs,
+        root(d), powf(e), log(base), expf(base), wrap(d), unwrap(d), *_approx, diff, diff_with_start, cum_sum."""
+        return self._call(name, *args)
+
+    def add_smaller(self, o):
+        return self._call("add_smaller_vector", o._h)
+
+    def sub_smaller(self, o):
+        return self._call("sub_smaller_vector", o._h)
+
+    def mul_smaller(self, o):
+        return self._call("mul_smaller_vector", o._h)
+
+    def div_smaller(self, o):
+        return self._call("div_smaller_vector", o._h)
+
+    def get_real_imag(self, real, imag):
+        return self._fn("get_real_imag")(self._h, real._h, imag._h)
+
+    def set_real_imag(self, real, imag):
+        return self._call("set_real_imag", real._h, imag._h)
+
+    def set_mag_phase(self, mag, phase):
+        return self._call("set_mag_phase", mag._h, phase._h)
+
+    def split_into(self, targets):
+        arr = (c_void_p * len(targets))(*[t._h for t in targets])
+        return int(self._fn("split_into")(self._h, arr, len(targets)))
+
+    def merge(self, sources):
+        arr = (c_void_p * len(sources))(*[t._h for t in sources])
+        return self._call("merge", arr, len(sources))
+
+    def interpolate_hermite(self, factor, delay):
+        return self._call("interpolate_hermite", factor, delay)
+
+    def custom_window(self, name, fn, is_symmetric=True):
+        """apply_custom_window / unapply_custom_window / windowed_custom_{fft,ifft,sfft,sifft} with fn(i, points)."""
+        cb = getattr(lib(), "WindowFn" + self._s)(lambda _d, i, p: float(fn(i, p)))
+        return self._call(name, cb, None, 1 if is_symmetric else 0)
+
+    def map_inplace(self, fn):
+        cb = getattr(lib(), "MapRealFn" + self._s)(lambda v, i: float(fn(v, i)))
+        return self._call("map_inplace_real", cb)
+
+    # -- reductions: DotProductOps / SumOps / StatisticsOps (+ _prec, + _split) -----------------------------------------
+    def _kind(self):
+        return "complex" if self.is_complex() else "real"
+
+    def dot_product(self, o, prec=False):
+        r = self._fn(self._kind() + "_dot_product" + ("_prec" if prec else ""))(self._h, o._h)
+        if r.result_code != 0:
+            raise DspError(r.result_code, "dot_product" + self._s)
+        return complex(r.result.re, r.result.im) if self.is_complex() else float(r.result)
+
+    def sum(self, prec=False, squared=False):
+        r = self._fn(self._kind() + ("_sum_sq" if squared else "_sum") + ("_prec" if prec else ""))(self._h)
+        return complex(r.re, r.im) if self.is_complex() else float(r)
+
+    @staticmethod
+    def _stats_dict(st, cplx):
+        conv = (lambda c: complex(c.re, c.im)) if cplx else float
+        return dict(sum=conv(st.sum), count=int(st.count), average=conv(st.average), rms=conv(st.rms), min=conv(st.min),
+                    min_index=int(st.min_index), max=conv(st.max), max_index=int(st.max_index))
+
+    def statistics(self, prec=False):
+        st = self._fn(self._kind() + "_statistics" + ("_prec" if prec else ""))(self._h)
+        return self._stats_dict(st, self.is_complex())
+
+    def statistics_split(self, parts, prec=False):
+        fn = self._fn(self._kind() + "_statistics_split" + ("_prec" if prec else ""))
+        arr = (fn.argtypes[1]._type_ * max(parts, 1))()
+        rc = fn(self._h, arr, parts)
+        if rc != 0:
+            raise DspError(rc, "statistics_split" + self._s)
+        return [self._stats_dict(arr[i], self.is_complex()) for i in range(parts)]
 
     def decimatei(self, factor, delay):
         return self._call("decimatei", factor, delay)

@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "conv.cuh"
 #include "elementwise.cuh"
+#include "mathops.cuh"
 #include "fft.cuh"
 #include "interp.cuh"
 
@@ -546,7 +547,16 @@ template <typename T> T host_window(int kind, size_t n, size_t length) {
     return one;
 }
 
-template <typename T> Res<T> op_window(Vec<T>* v, int kind, bool unapply) {
+// built-in window kind, or a foreign callback window(data, i, points) (facade32.rs:1030-1044)
+template <typename T> struct WinFn {
+    int kind = 3;
+    T (*fn)(const void*, size_t, size_t) = nullptr;
+    const void* data = nullptr;
+    bool symmetric = true;
+    T operator()(size_t i, size_t points) const { return fn ? fn(data, i, points) : host_window<T>(kind, i, points); }
+};
+
+template <typename T> Res<T> op_window_fn(Vec<T>* v, const WinFn<T>& w, bool unapply) {
     // time.rs:33-66 + multiply_window_priv (vector_types/mod.rs:528-598): symmetric windows evaluate the
     // first half and mirror it
     if (v->domain != 0) { mark_invalid(v); return done(v, 0); }
@@ -554,9 +564,9 @@ template <typename T> Res<T> op_window(Vec<T>* v, int kind, bool unapply) {
     if (!points) return done(v, 0);
     std::vector<T> tab(points);
     for (size_t i = 0; i < points; i++) {
-        const size_t j = i < (points + 1) / 2 ? i : points - 1 - i;
-        const T w = host_window<T>(kind, j, points);
-        tab[i] = unapply ? (T)1 / w : w;
+        const size_t j = !w.symmetric || i < (points + 1) / 2 ? i : points - 1 - i;
+        const T x = w(j, points);
+        tab[i] = unapply ? (T)1 / x : x;
     }
     T* dev = nullptr;
     int rc = upload_table(tab, &dev);
@@ -564,17 +574,23 @@ template <typename T> Res<T> op_window(Vec<T>* v, int kind, bool unapply) {
     table_consumed();
     return done(v, rc);
 }
+template <typename T> Res<T> op_window(Vec<T>* v, int kind, bool unapply) {
+    WinFn<T> w; w.kind = kind;
+    return op_window_fn(v, w, unapply);
+}
 
-template <typename T> Res<T> op_windowed_fft(Vec<T>* v, int kind) {
-    Res<T> r = op_window(v, kind, false);
+template <typename T> Res<T> op_windowed_fft_fn(Vec<T>* v, const WinFn<T>& w) {
+    Res<T> r = op_window_fn(v, w, false);
     if (r.result_code) return r;
     return op_fft(v, false, true, false);
 }
-template <typename T> Res<T> op_windowed_ifft(Vec<T>* v, int kind) {
+template <typename T> Res<T> op_windowed_ifft_fn(Vec<T>* v, const WinFn<T>& w) {
     Res<T> r = op_fft(v, true, true, false);
     if (r.result_code) return r;
-    return op_window(v, kind, true);
+    return op_window_fn(v, w, true);
 }
+template <typename T> Res<T> op_windowed_fft(Vec<T>* v, int kind) { WinFn<T> w; w.kind = kind; return op_windowed_fft_fn(v, w); }
+template <typename T> Res<T> op_windowed_ifft(Vec<T>* v, int kind) { WinFn<T> w; w.kind = kind; return op_windowed_ifft_fn(v, w); }
 
 template <typename T> Res<T> op_prepare_argument(Vec<T>* v, bool padded) {
     // correlation.rs:96-117
@@ -835,7 +851,7 @@ template <typename T> Res<T> op_mirror(Vec<T>* v) {
     return done(v, 0);
 }
 
-template <typename T> Res<T> op_sfft(Vec<T>* v, bool shifted, int window) {
+template <typename T> Res<T> op_sfft(Vec<T>* v, bool shifted, const WinFn<T>* window) {
     // time_to_freq.rs:197-298; kept length follows the statically typed vectors: (n + 1) / 2 complex points
     if (v->domain != 0 || v->is_complex) {
         mark_invalid(v); v->is_complex = 1; v->domain = 1;
@@ -846,8 +862,8 @@ template <typename T> Res<T> op_sfft(Vec<T>* v, bool shifted, int window) {
         mark_invalid(v); v->is_complex = 1; v->domain = 1;
         return done(v, 9);   // InputMustHaveAnOddLength
     }
-    if (window >= 0) {
-        Res<T> r = op_window(v, window, false);
+    if (window) {
+        Res<T> r = op_window_fn(v, *window, false);
         if (r.result_code) return r;
     }
     Res<T> r = op_fft(v, false, shifted, false);
@@ -862,7 +878,7 @@ template <typename T> Res<T> op_sfft(Vec<T>* v, bool shifted, int window) {
     return done(v, 0);
 }
 
-template <typename T> Res<T> op_sifft(Vec<T>* v, bool shifted, int window) {
+template <typename T> Res<T> op_sifft(Vec<T>* v, bool shifted, const WinFn<T>* window) {
     // freq_to_time.rs:190-248
     if (shifted) {
         const size_t points = points_of(v);
@@ -902,7 +918,7 @@ template <typename T> Res<T> op_sifft(Vec<T>* v, bool shifted, int window) {
     v->len = points;
     v->is_complex = 0;
     v->domain = 0;
-    if (window >= 0) return op_window(v, window, true);
+    if (window) return op_window_fn(v, *window, true);
     return done(v, 0);
 }
 
@@ -918,6 +934,179 @@ template <typename T> Res<T> op_interpolate_lin(Vec<T>* v, T factor, T delay) {
     trade(v);
     v->len = dest_len;
     return done(v, 0);
+}
+
+
+// ---- the rest of the C facade (elementwise math, reorganisation, reductions) -------
+template <typename T> Res<T> op_math(Vec<T>* v, int op, T arg, bool real_only) {
+    // trigonometry_and_powers.rs:198-377; real_only: assert_real! (real_ops.rs:227-234)
+    if (real_only && v->is_complex) { mark_invalid(v); return done(v, 0); }
+    return done(v, math_unary<T>(op, v->d, points_of(v), v->is_complex, (double)arg, g_stream));
+}
+
+template <typename T> Res<T> op_unwrap(Vec<T>* v, T divisor) {
+    if (v->is_complex) { mark_invalid(v); return done(v, 0); }
+    return done(v, math_unwrap<T>(v->d, v->len, (double)divisor, g_stream));
+}
+
+template <typename T> Res<T> op_diff(Vec<T>* v, bool with_start) {
+    // diff_sum.rs:63-109
+    const size_t step = v->is_complex ? 2 : 1;
+    if (v->len < step) return done(v, 0);
+    const size_t n_out = with_start ? v->len : v->len - step;
+    int rc = ensure_scratch(v, v->len);
+    if (!rc) rc = math_diff<T>(v->d, v->scratch, n_out, (int)step, with_start, g_stream);
+    if (rc) return done(v, rc);
+    trade(v);
+    v->len = n_out;
+    return done(v, 0);
+}
+
+template <typename T> Res<T> op_cum_sum(Vec<T>* v) {
+    // diff_sum.rs:111-122 (the running sum is evaluated as a parallel scan: same value up to rounding order)
+    const int lanes = v->is_complex ? 2 : 1;
+    const size_t points = points_of(v);
+    if (!points) return done(v, 0);
+    int rc = ensure_scratch(v, v->len);
+    if (rc) return done(v, rc);
+    void* work = workspace(math_cumsum_workspace(points, lanes, sizeof(T)), 3);
+    rc = math_cumsum<T>(v->d, v->scratch, work, points, lanes, g_stream);
+    if (rc) return done(v, rc);
+    trade(v);
+    return done(v, 0);
+}
+
+template <typename T> Res<T> op_binary_smaller(Vec<T>* v, const Vec<T>* o, int op) {
+    // elementary.rs:457-517,601-639
+    if (o->len == 0 || v->len % o->len != 0) return done(v, E_ARG_LEN);
+    if (!meta_agrees(v, o)) return done(v, E_META);
+    return done(v, math_binary_smaller<T>(op, v->d, o->d, points_of(v), points_of(o), v->is_complex, g_stream));
+}
+
+template <typename T> Res<T> op_set_pair(Vec<T>* v, const Vec<T>* a, const Vec<T>* b, bool polar) {
+    // complex_to_real.rs:726-770
+    if (a->len != b->len) return done(v, E_ARG_LEN);
+    const size_t points = a->len;
+    int rc = reserve(&v->d, &v->cap, 2 * points, false, 0);
+    if (!rc) rc = math_compose<T>(a->d, b->d, v->d, points, polar, g_stream);
+    if (rc) return done(v, rc);
+    v->len = 2 * points;
+    return done(v, 0);
+}
+
+template <typename T> int32_t op_get_real_imag(Vec<T>* v, Vec<T>* re, Vec<T>* im) {
+    // complex_to_real.rs:674-691
+    if (!v->is_complex || re->is_complex || im->is_complex) {
+        re->len = 0; im->len = 0; re->version++; im->version++;
+        return VOID_OK;
+    }
+    const size_t points = v->len / 2;
+    vec_resize(re, points);
+    vec_resize(im, points);
+    if (points) {
+        int rc = ew_complex_to_real<T>(C2R_REAL, v->d, re->d, points, g_stream);
+        if (!rc) rc = ew_complex_to_real<T>(C2R_IMAG, v->d, im->d, points, g_stream);
+        if (rc) return rc;
+    }
+    return VOID_OK;
+}
+
+template <typename T> int32_t op_split_into(const Vec<T>* v, Vec<T>** targets, size_t n) {
+    // data_reorganization.rs:484-512
+    if (n == 0 || v->len % n != 0) return E_ARG_LEN;
+    const size_t part_len = v->len / n;
+    std::vector<void*> ptrs(n);
+    for (size_t i = 0; i < n; i++) {
+        int rc = vec_resize(targets[i], part_len);
+        if (rc) return rc;
+        ptrs[i] = targets[i]->d;
+    }
+    const int esz = v->is_complex ? 2 : 1;
+    int rc = math_split_merge<T>(v->d, ptrs.data(), (int)n, v->len / esz, esz, 0, g_stream);
+    return rc ? rc : VOID_OK;
+}
+
+template <typename T> Res<T> op_merge(Vec<T>* v, Vec<T>* const* sources, size_t n) {
+    // data_reorganization.rs:522-557
+    if (n == 0) return done(v, E_ARG_LEN);
+    for (size_t i = 1; i < n; i++) if (sources[i]->len != sources[0]->len) return done(v, E_ARG_LEN);
+    int rc = vec_resize(v, sources[0]->len * n);
+    if (rc) return done(v, rc);
+    std::vector<void*> ptrs(n);
+    for (size_t i = 0; i < n; i++) ptrs[i] = sources[i]->d;
+    const int esz = v->is_complex ? 2 : 1;
+    return done(v, math_split_merge<T>(v->d, ptrs.data(), (int)n, v->len / esz, esz, 1, g_stream));
+}
+
+template <typename T> Res<T> op_interpolate_hermite(Vec<T>* v, T factor, T delay) {
+    // real_interpolation.rs:73-178
+    if (v->is_complex) { mark_invalid(v); return done(v, 0); }
+    const size_t n = v->len;
+    if (n < 3) return done(v, E_ARG_LEN);
+    const size_t dest_len = (size_t)round((double)((T)(n - 1) * factor)) + 1;
+    const double st = ceil((double)(((T)1 - delay) * factor));
+    const size_t start = st < 0 ? 0 : (size_t)st;
+    int rc = ensure_scratch(v, dest_len);
+    if (!rc) rc = math_hermite<T>(v->d, v->scratch, n, dest_len, start, (double)factor, (double)delay, g_stream);
+    if (rc) return done(v, rc);
+    trade(v);
+    v->len = dest_len;
+    return done(v, 0);
+}
+
+// reductions: values in double, converted by the facade to the reference's result types
+template <typename T> int sums_of(const Vec<T>* v, int prec, double* out4) {
+    out4[0] = out4[1] = out4[2] = out4[3] = 0.0;
+    if (!v->len) return 0;
+    return reduce_sums<T>(v->d, points_of(v), v->is_complex, prec, out4, g_stream);
+}
+
+template <typename T> int dot_of(const Vec<T>* v, const Vec<T>* o, bool want_complex, int prec, double* out2) {
+    // dot_products.rs:67-160, 289-345
+    out2[0] = out2[1] = 0.0;
+    if (want_complex) {
+        if (!v->is_complex) return E_COMPLEX;
+        if (!o->is_complex || v->domain != o->domain) return E_META;
+    } else if (v->is_complex) return E_REAL;
+    const size_t n = v->len < o->len ? v->len : o->len;
+    const size_t elems = want_complex ? n / 2 : n;
+    if (!elems) return 0;
+    return reduce_dot<T>(v->d, o->d, elems, want_complex, prec, out2, g_stream);
+}
+
+template <typename S> void stats_fill_real(S* out, const StatsRaw& r) {
+    typedef decltype(out->sum) V;
+    const double n = (double)r.count;
+    out->sum = (V)r.sum[0]; out->count = (size_t)r.count;
+    out->average = (V)((V)r.sum[0] / (V)n);
+    out->rms = (V)sqrt((double)((V)r.sumsq[0] / (V)n));
+    out->min = (V)r.min[0]; out->min_index = (size_t)r.min_index;
+    out->max = (V)r.max[0]; out->max_index = (size_t)r.max_index;
+}
+template <typename S, typename V> void stats_fill_complex(S* out, const StatsRaw& r) {
+    const V n = (V)r.count;
+    out->sum.re = (V)r.sum[0]; out->sum.im = (V)r.sum[1]; out->count = (size_t)r.count;
+    out->average.re = (V)r.sum[0] / n; out->average.im = (V)r.sum[1] / n;
+    // rms = sqrt(sum(z^2) / count), complex square root as in num-complex (principal branch)
+    const double qr = (double)((V)r.sumsq[0] / n), qi = (double)((V)r.sumsq[1] / n);
+    double sr, si;
+    if (qi == 0.0) { if (qr >= 0) { sr = sqrt(qr); si = qi; } else { sr = 0; si = sqrt(-qr); } }
+    else if (qr == 0.0) { const double x = sqrt(fabs(qi) / 2); sr = x; si = qi < 0 ? -x : x; }
+    else { const double m = sqrt(hypot(qr, qi)), th = atan2(qi, qr) / 2; sr = m * cos(th); si = m * sin(th); }
+    out->rms.re = (V)sr; out->rms.im = (V)si;
+    out->min.re = (V)r.min[0]; out->min.im = (V)r.min[1]; out->min_index = (size_t)r.min_index;
+    out->max.re = (V)r.max[0]; out->max.im = (V)r.max[1]; out->max_index = (size_t)r.max_index;
+}
+
+template <typename T> int stats_of(const Vec<T>* v, int parts, int prec, StatsRaw* raw) {
+    // statistics.rs:179-440; an empty vector yields the reference's empty record (count 0, NaN average / rms)
+    for (int p = 0; p < parts; p++) {
+        raw[p] = StatsRaw();
+        raw[p].min[0] = INFINITY; raw[p].min[1] = v->is_complex ? INFINITY : 0.0;
+        raw[p].max[0] = v->is_complex ? 0.0 : -INFINITY;
+    }
+    if (!v->len) return 0;
+    return reduce_stats<T>(v->d, points_of(v), v->is_complex, parts, prec, raw, g_stream);
 }
 
 // ---- host access -----------------------------------------------------------------------------------
@@ -945,6 +1134,41 @@ template <typename T> int download(const Vec<T>* v, T* host, size_t len, bool wa
     if (len) BDSP_CUDA_OK(cudaMemcpyAsync(host, v->d, len * sizeof(T), cudaMemcpyDeviceToHost, g_stream));
     if (wait) BDSP_CUDA_OK(cudaStreamSynchronize(g_stream));
     return 0;
+}
+
+
+// ---- host callbacks per element (mapping.rs:46-266; facade32.rs:594-647) -----------------------------
+// The computation IS the caller's host function, so the vector is staged through its host mirror: download,
+// apply the callback in index order, upload.  (No device work besides the two copies.)
+template <typename T> Res<T> op_map_inplace_real(Vec<T>* v, T (*map)(T, size_t)) {
+    if (v->is_complex) { mark_invalid(v); return done(v, 0); }
+    host_mirror(v);
+    for (size_t i = 0; i < v->len; i++) v->host[i] = map(v->host[i], i);
+    int rc = upload(v, v->host.data(), v->len);
+    if (!rc) { cudaError_t e = cudaStreamSynchronize(g_stream); if (e != cudaSuccess) rc = -1000 - (int)e; }
+    return done(v, rc);
+}
+template <typename T, typename CT> Res<T> op_map_inplace_complex(Vec<T>* v, CT (*map)(CT, size_t)) {
+    if (!v->is_complex) { mark_invalid(v); return done(v, 0); }
+    host_mirror(v);
+    CT* c = reinterpret_cast<CT*>(v->host.data());
+    for (size_t i = 0; i < v->len / 2; i++) c[i] = map(c[i], i);
+    int rc = upload(v, v->host.data(), v->len);
+    if (!rc) { cudaError_t e = cudaStreamSynchronize(g_stream); if (e != cudaSuccess) rc = -1000 - (int)e; }
+    return done(v, rc);
+}
+template <typename T, typename ET> BdspPointerResult op_map_aggregate(const Vec<T>* v, bool complex_variant, const void* (*map)(ET, size_t),
+                                                                      const void* (*aggregate)(const void*, const void*)) {
+    BdspPointerResult out; out.result_code = 0; out.result = nullptr;
+    if (complex_variant != (v->is_complex != 0)) { out.result_code = complex_variant ? E_COMPLEX : E_REAL; return out; }
+    if (v->len == 0) { out.result_code = 12; return out; }   // InputMustNotBeEmpty
+    const ET* h = reinterpret_cast<const ET*>(host_mirror(v));
+    const size_t n = complex_variant ? v->len / 2 : v->len;
+    const void* acc = map(h[0], 0);
+    for (size_t i = 1; i < n; i++) acc = aggregate(acc, map(h[i], i));
+    out.result = acc;
+    if (erroneous(v)) out.result_code = -1;
+    return out;
 }
 
 template <typename T>
@@ -1023,6 +1247,51 @@ template <typename R, typename T> static inline R as_res(Res<T> r) {
     out.vector = reinterpret_cast<decltype(out.vector)>(r.vector);
     return out;
 }
+
+#define BDSP_MATH_FACADE(S, T, VEC, CVEC, RES, HV)                                                                     \
+    extern "C" RES sin##S(HV* v) { return as_res<RES>(op_math<T>(VEC(v), M_SIN, (T)0, false)); }                       \
+    extern "C" RES cos##S(HV* v) { return as_res<RES>(op_math<T>(VEC(v), M_COS, (T)0, false)); }                       \
+    extern "C" RES tan##S(HV* v) { return as_res<RES>(op_math<T>(VEC(v), M_TAN, (T)0, false)); }                       \
+    extern "C" RES asin##S(HV* v) { return as_res<RES>(op_math<T>(VEC(v), M_ASIN, (T)0, false)); }                     \
+    extern "C" RES acos##S(HV* v) { return as_res<RES>(op_math<T>(VEC(v), M_ACOS, (T)0, false)); }                     \
+    extern "C" RES atan##S(HV* v) { return as_res<RES>(op_math<T>(VEC(v), M_ATAN, (T)0, false)); }                     \
+    extern "C" RES sinh##S(HV* v) { return as_res<RES>(op_math<T>(VEC(v), M_SINH, (T)0, false)); }                     \
+    extern "C" RES cosh##S(HV* v) { return as_res<RES>(op_math<T>(VEC(v), M_COSH, (T)0, false)); }                     \
+    extern "C" RES tanh##S(HV* v) { return as_res<RES>(op_math<T>(VEC(v), M_TANH, (T)0, false)); }                     \
+    extern "C" RES asinh##S(HV* v) { return as_res<RES>(op_math<T>(VEC(v), M_ASINH, (T)0, false)); }                   \
+    extern "C" RES acosh##S(HV* v) { return as_res<RES>(op_math<T>(VEC(v), M_ACOSH, (T)0, false)); }                   \
+    extern "C" RES atanh##S(HV* v) { return as_res<RES>(op_math<T>(VEC(v), M_ATANH, (T)0, false)); }                   \
+    extern "C" RES sqrt##S(HV* v) { return as_res<RES>(op_math<T>(VEC(v), M_SQRT, (T)0, false)); }                     \
+    extern "C" RES square##S(HV* v) { return as_res<RES>(op_math<T>(VEC(v), M_SQUARE, (T)0, false)); }                 \
+    extern "C" RES ln##S(HV* v) { return as_res<RES>(op_math<T>(VEC(v), M_LN, (T)0, false)); }                         \
+    extern "C" RES exp##S(HV* v) { return as_res<RES>(op_math<T>(VEC(v), M_EXP, (T)0, false)); }                       \
+    extern "C" RES abs##S(HV* v) { return as_res<RES>(op_math<T>(VEC(v), M_ABS, (T)0, true)); }                        \
+    extern "C" RES root##S(HV* v, T degree) { return as_res<RES>(op_math<T>(VEC(v), M_POWF, (T)1 / degree, false)); }  \
+    extern "C" RES bdsp_powf##S(HV* v, T e) { return as_res<RES>(op_math<T>(VEC(v), M_POWF, e, false)); }              \
+    extern "C" RES log##S(HV* v, T base) { return as_res<RES>(op_math<T>(VEC(v), M_LOG, base, false)); }               \
+    extern "C" RES bdsp_expf##S(HV* v, T base) { return as_res<RES>(op_math<T>(VEC(v), M_EXPF, base, false)); }        \
+    extern "C" RES wrap##S(HV* v, T d) { return as_res<RES>(op_math<T>(VEC(v), M_WRAP, d, true)); }                    \
+    extern "C" RES unwrap##S(HV* v, T d) { return as_res<RES>(op_unwrap<T>(VEC(v), d)); }                              \
+    extern "C" RES ln_approx##S(HV* v) { return as_res<RES>(op_math<T>(VEC(v), M_LN, (T)0, true)); }                   \
+    extern "C" RES exp_approx##S(HV* v) { return as_res<RES>(op_math<T>(VEC(v), M_EXP, (T)0, true)); }                 \
+    extern "C" RES sin_approx##S(HV* v) { return as_res<RES>(op_math<T>(VEC(v), M_SIN, (T)0, true)); }                 \
+    extern "C" RES cos_approx##S(HV* v) { return as_res<RES>(op_math<T>(VEC(v), M_COS, (T)0, true)); }                 \
+    extern "C" RES log_approx##S(HV* v, T base) { return as_res<RES>(op_math<T>(VEC(v), M_LOG, base, true)); }         \
+    extern "C" RES expf_approx##S(HV* v, T base) { return as_res<RES>(op_math<T>(VEC(v), M_EXPF, base, true)); }       \
+    extern "C" RES powf_approx##S(HV* v, T e) { return as_res<RES>(op_math<T>(VEC(v), M_POWF, e, true)); }             \
+    extern "C" RES diff##S(HV* v) { return as_res<RES>(op_diff<T>(VEC(v), false)); }                                   \
+    extern "C" RES diff_with_start##S(HV* v) { return as_res<RES>(op_diff<T>(VEC(v), true)); }                         \
+    extern "C" RES cum_sum##S(HV* v) { return as_res<RES>(op_cum_sum<T>(VEC(v))); }                                    \
+    extern "C" RES add_smaller_vector##S(HV* v, const HV* o) { return as_res<RES>(op_binary_smaller<T>(VEC(v), CVEC(o), 0)); } \
+    extern "C" RES sub_smaller_vector##S(HV* v, const HV* o) { return as_res<RES>(op_binary_smaller<T>(VEC(v), CVEC(o), 1)); } \
+    extern "C" RES mul_smaller_vector##S(HV* v, const HV* o) { return as_res<RES>(op_binary_smaller<T>(VEC(v), CVEC(o), 2)); } \
+    extern "C" RES div_smaller_vector##S(HV* v, const HV* o) { return as_res<RES>(op_binary_smaller<T>(VEC(v), CVEC(o), 3)); } \
+    extern "C" int32_t get_real_imag##S(HV* v, HV* re, HV* im) { return op_get_real_imag<T>(VEC(v), VEC(re), VEC(im)); } \
+    extern "C" RES set_real_imag##S(HV* v, const HV* re, const HV* im) { return as_res<RES>(op_set_pair<T>(VEC(v), CVEC(re), CVEC(im), false)); } \
+    extern "C" RES set_mag_phase##S(HV* v, const HV* m, const HV* p) { return as_res<RES>(op_set_pair<T>(VEC(v), CVEC(m), CVEC(p), true)); } \
+    extern "C" int32_t split_into##S(const HV* v, HV** targets, size_t len) { return op_split_into<T>(CVEC(v), reinterpret_cast<Vec<T>**>(targets), len); } \
+    extern "C" RES merge##S(HV* v, HV* const* sources, size_t len) { return as_res<RES>(op_merge<T>(VEC(v), reinterpret_cast<Vec<T>* const*>(sources), len)); } \
+    extern "C" RES interpolate_hermite##S(HV* v, T factor, T delay) { return as_res<RES>(op_interpolate_hermite<T>(VEC(v), factor, delay)); }
 
 #define BDSP_FACADE(S, T, VEC, CVEC, RES, HV, CPLX, RFN, CFN)                                                         \
     extern "C" HV* new##S(int32_t is_complex, int32_t domain, T init_value, size_t length, T delta) {                  \
@@ -1172,12 +1441,31 @@ template <typename R, typename T> static inline R as_res(Res<T> r) {
     extern "C" RES interpft##S(HV* v, size_t dest_points) { return as_res<RES>(op_interpolate<T>(VEC(v), nullptr, true, dest_points, (T)0)); } \
     extern "C" RES multiply_complex_exponential##S(HV* v, T a, T b) { return as_res<RES>(op_mul_cexp(VEC(v), a, b)); } \
     extern "C" RES mirror##S(HV* v) { return as_res<RES>(op_mirror(VEC(v))); }                                         \
-    extern "C" RES plain_sfft##S(HV* v) { return as_res<RES>(op_sfft(VEC(v), false, -1)); }                            \
-    extern "C" RES sfft##S(HV* v) { return as_res<RES>(op_sfft(VEC(v), true, -1)); }                                   \
-    extern "C" RES windowed_sfft##S(HV* v, int32_t w) { return as_res<RES>(op_sfft(VEC(v), true, w < 0 || w > 3 ? 3 : w)); } \
-    extern "C" RES plain_sifft##S(HV* v) { return as_res<RES>(op_sifft(VEC(v), false, -1)); }                          \
-    extern "C" RES sifft##S(HV* v) { return as_res<RES>(op_sifft(VEC(v), true, -1)); }                                 \
-    extern "C" RES windowed_sifft##S(HV* v, int32_t w) { return as_res<RES>(op_sifft(VEC(v), true, w < 0 || w > 3 ? 3 : w)); } \
+    extern "C" RES plain_sfft##S(HV* v) { return as_res<RES>(op_sfft<T>(VEC(v), false, nullptr)); }                    \
+    extern "C" RES sfft##S(HV* v) { return as_res<RES>(op_sfft<T>(VEC(v), true, nullptr)); }                           \
+    extern "C" RES windowed_sfft##S(HV* v, int32_t k) { WinFn<T> w; w.kind = k; return as_res<RES>(op_sfft<T>(VEC(v), true, &w)); } \
+    extern "C" RES plain_sifft##S(HV* v) { return as_res<RES>(op_sifft<T>(VEC(v), false, nullptr)); }                  \
+    extern "C" RES sifft##S(HV* v) { return as_res<RES>(op_sifft<T>(VEC(v), true, nullptr)); }                         \
+    extern "C" RES windowed_sifft##S(HV* v, int32_t k) { WinFn<T> w; w.kind = k; return as_res<RES>(op_sifft<T>(VEC(v), true, &w)); } \
+    extern "C" RES apply_custom_window##S(HV* v, BdspWindowFn##S fn, const void* data, uint8_t sym) {                              \
+        WinFn<T> w; w.fn = fn; w.data = data; w.symmetric = sym != 0; return as_res<RES>(op_window_fn<T>(VEC(v), w, false)); } \
+    extern "C" RES unapply_custom_window##S(HV* v, BdspWindowFn##S fn, const void* data, uint8_t sym) {                            \
+        WinFn<T> w; w.fn = fn; w.data = data; w.symmetric = sym != 0; return as_res<RES>(op_window_fn<T>(VEC(v), w, true)); } \
+    extern "C" RES windowed_custom_fft##S(HV* v, BdspWindowFn##S fn, const void* data, uint8_t sym) {                              \
+        WinFn<T> w; w.fn = fn; w.data = data; w.symmetric = sym != 0; return as_res<RES>(op_windowed_fft_fn<T>(VEC(v), w)); } \
+    extern "C" RES windowed_custom_ifft##S(HV* v, BdspWindowFn##S fn, const void* data, uint8_t sym) {                             \
+        WinFn<T> w; w.fn = fn; w.data = data; w.symmetric = sym != 0; return as_res<RES>(op_windowed_ifft_fn<T>(VEC(v), w)); } \
+    extern "C" RES windowed_custom_sfft##S(HV* v, BdspWindowFn##S fn, const void* data, uint8_t sym) {                             \
+        WinFn<T> w; w.fn = fn; w.data = data; w.symmetric = sym != 0; return as_res<RES>(op_sfft<T>(VEC(v), true, &w)); } \
+    extern "C" RES windowed_custom_sifft##S(HV* v, BdspWindowFn##S fn, const void* data, uint8_t sym) {                            \
+        WinFn<T> w; w.fn = fn; w.data = data; w.symmetric = sym != 0; return as_res<RES>(op_sifft<T>(VEC(v), true, &w)); } \
+    extern "C" RES map_inplace_real##S(HV* v, T (*map)(T, size_t)) { return as_res<RES>(op_map_inplace_real<T>(VEC(v), map)); } \
+    extern "C" RES map_inplace_complex##S(HV* v, CPLX (*map)(CPLX, size_t)) { return as_res<RES>(op_map_inplace_complex<T, CPLX>(VEC(v), map)); } \
+    extern "C" BdspPointerResult map_aggregate_real##S(const HV* v, const void* (*map)(T, size_t), const void* (*aggr)(const void*, const void*)) { \
+        return op_map_aggregate<T, T>(CVEC(v), false, map, aggr); }                                                    \
+    extern "C" BdspPointerResult map_aggregate_complex##S(const HV* v, const void* (*map)(CPLX, size_t), const void* (*aggr)(const void*, const void*)) { \
+        return op_map_aggregate<T, CPLX>(CVEC(v), true, map, aggr); }                                                  \
+    BDSP_MATH_FACADE(S, T, VEC, CVEC, RES, HV)                                                                         \
     extern "C" RES apply_window##S(HV* v, int32_t w) { return as_res<RES>(op_window(VEC(v), w, false)); }              \
     extern "C" RES unapply_window##S(HV* v, int32_t w) { return as_res<RES>(op_window(VEC(v), w, true)); }             \
     extern "C" RES windowed_fft##S(HV* v, int32_t w) { return as_res<RES>(op_windowed_fft(VEC(v), w)); }               \
@@ -1197,6 +1485,59 @@ template <typename R, typename T> static inline R as_res(Res<T> r) {
 
 BDSP_FACADE(32, float, V32, CV32, BdspVecResult32, BdspVec32, BdspComplex32, BdspRealFn32, BdspComplexFn32)
 BDSP_FACADE(64, double, V64, CV64, BdspVecResult64, BdspVec64, BdspComplex64, BdspRealFn64, BdspComplexFn64)
+
+
+// ---- reductions (facade32.rs:193-321, 848-931; facade64.rs likewise) ---------------------------------
+#define BDSP_REDUCE_FACADE(S, T, TP, CVEC, CPLX, CPLXP, HV)                                                            \
+    extern "C" BdspScalarResult##S real_dot_product##S(const HV* v, const HV* o) {                                     \
+        double r[2]; BdspScalarResult##S out; out.result_code = dot_of<T>(CVEC(v), CVEC(o), false, 0, r);              \
+        out.result = out.result_code ? (T)0 : (T)r[0]; if (!out.result_code && erroneous(CVEC(v))) out.result_code = -1; return out; } \
+    extern "C" BdspScalarResult##S real_dot_product_prec##S(const HV* v, const HV* o) {                                \
+        double r[2]; BdspScalarResult##S out; out.result_code = dot_of<T>(CVEC(v), CVEC(o), false, 1, r);              \
+        out.result = out.result_code ? (T)0 : (T)r[0]; if (!out.result_code && erroneous(CVEC(v))) out.result_code = -1; return out; } \
+    extern "C" BdspComplexScalarResult##S complex_dot_product##S(const HV* v, const HV* o) {                           \
+        double r[2]; BdspComplexScalarResult##S out; out.result_code = dot_of<T>(CVEC(v), CVEC(o), true, 0, r);        \
+        out.result.re = out.result_code ? (T)0 : (T)r[0]; out.result.im = out.result_code ? (T)0 : (T)r[1];            \
+        if (!out.result_code && erroneous(CVEC(v))) out.result_code = -1; return out; }                                \
+    extern "C" BdspComplexScalarResult##S complex_dot_product_prec##S(const HV* v, const HV* o) {                      \
+        double r[2]; BdspComplexScalarResult##S out; out.result_code = dot_of<T>(CVEC(v), CVEC(o), true, 1, r);        \
+        out.result.re = out.result_code ? (T)0 : (T)r[0]; out.result.im = out.result_code ? (T)0 : (T)r[1];            \
+        if (!out.result_code && erroneous(CVEC(v))) out.result_code = -1; return out; }                                \
+    extern "C" T real_sum##S(const HV* v) { double r[4]; sums_of<T>(CVEC(v), 0, r); return (T)r[0]; }                  \
+    extern "C" T real_sum_sq##S(const HV* v) { double r[4]; sums_of<T>(CVEC(v), 0, r); return (T)r[2]; }               \
+    extern "C" CPLX complex_sum##S(const HV* v) { double r[4]; sums_of<T>(CVEC(v), 0, r); CPLX c; c.re = (T)r[0]; c.im = (T)r[1]; return c; } \
+    extern "C" CPLX complex_sum_sq##S(const HV* v) { double r[4]; sums_of<T>(CVEC(v), 0, r); CPLX c; c.re = (T)r[2]; c.im = (T)r[3]; return c; } \
+    extern "C" TP real_sum_prec##S(const HV* v) { double r[4]; sums_of<T>(CVEC(v), 1, r); return (TP)r[0]; }           \
+    extern "C" TP real_sum_sq_prec##S(const HV* v) { double r[4]; sums_of<T>(CVEC(v), 1, r); return (TP)r[2]; }        \
+    extern "C" CPLXP complex_sum_prec##S(const HV* v) { double r[4]; sums_of<T>(CVEC(v), 1, r); CPLXP c; c.re = (TP)r[0]; c.im = (TP)r[1]; return c; } \
+    extern "C" CPLXP complex_sum_sq_prec##S(const HV* v) { double r[4]; sums_of<T>(CVEC(v), 1, r); CPLXP c; c.re = (TP)r[2]; c.im = (TP)r[3]; return c; } \
+    extern "C" BdspStatistics##S real_statistics##S(const HV* v) {                                                     \
+        StatsRaw raw; BdspStatistics##S out; stats_of<T>(CVEC(v), 1, 0, &raw); stats_fill_real(&out, raw); return out; } \
+    extern "C" BdspComplexStatistics##S complex_statistics##S(const HV* v) {                                           \
+        StatsRaw raw; BdspComplexStatistics##S out; stats_of<T>(CVEC(v), 1, 0, &raw); stats_fill_complex<BdspComplexStatistics##S, T>(&out, raw); return out; } \
+    extern "C" BdspStatistics64 real_statistics_prec##S(const HV* v) {                                                 \
+        StatsRaw raw; BdspStatistics64 out; stats_of<T>(CVEC(v), 1, 1, &raw); stats_fill_real(&out, raw); return out; } \
+    extern "C" BdspComplexStatistics64 complex_statistics_prec##S(const HV* v) {                                       \
+        StatsRaw raw; BdspComplexStatistics64 out; stats_of<T>(CVEC(v), 1, 1, &raw); stats_fill_complex<BdspComplexStatistics64, double>(&out, raw); return out; } \
+    extern "C" int32_t real_statistics_split##S(const HV* v, BdspStatistics##S* data, size_t len) {                    \
+        if (len == 0) return 0; if (len > 16) return E_ARG_LEN;                                                        \
+        StatsRaw raw[16]; int rc = stats_of<T>(CVEC(v), (int)len, 0, raw); if (rc) return rc;                          \
+        for (size_t i = 0; i < len; i++) stats_fill_real(&data[i], raw[i]); return 0; }                                \
+    extern "C" int32_t complex_statistics_split##S(const HV* v, BdspComplexStatistics##S* data, size_t len) {          \
+        if (len == 0) return 0; if (len > 16) return E_ARG_LEN;                                                        \
+        StatsRaw raw[16]; int rc = stats_of<T>(CVEC(v), (int)len, 0, raw); if (rc) return rc;                          \
+        for (size_t i = 0; i < len; i++) stats_fill_complex<BdspComplexStatistics##S, T>(&data[i], raw[i]); return 0; } \
+    extern "C" int32_t real_statistics_split_prec##S(const HV* v, BdspStatistics64* data, size_t len) {                \
+        if (len == 0) return 0; if (len > 16) return E_ARG_LEN;                                                        \
+        StatsRaw raw[16]; int rc = stats_of<T>(CVEC(v), (int)len, 1, raw); if (rc) return rc;                          \
+        for (size_t i = 0; i < len; i++) stats_fill_real(&data[i], raw[i]); return 0; }                                \
+    extern "C" int32_t complex_statistics_split_prec##S(const HV* v, BdspComplexStatistics64* data, size_t len) {      \
+        if (len == 0) return 0; if (len > 16) return E_ARG_LEN;                                                        \
+        StatsRaw raw[16]; int rc = stats_of<T>(CVEC(v), (int)len, 1, raw); if (rc) return rc;                          \
+        for (size_t i = 0; i < len; i++) stats_fill_complex<BdspComplexStatistics64, double>(&data[i], raw[i]); return 0; }
+
+BDSP_REDUCE_FACADE(32, float, double, CV32, BdspComplex32, BdspComplex64, BdspVec32)
+BDSP_REDUCE_FACADE(64, double, double, CV64, BdspComplex64, BdspComplex64, BdspVec64)
 
 extern "C" const char* bdsp_version(void) { return "basic_dsp_b200 0.1.0 (sm_100a)"; }
 extern "C" const char* bdsp_last_error(void) { return get_last_error(); }

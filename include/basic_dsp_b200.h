@@ -50,9 +50,33 @@ typedef struct { float re, im; } BdspComplex32;
 typedef struct { double re, im; } BdspComplex64;
 
 /* Callback types of the *_real / *_complex / *_custom entry points (interop/src/lib.rs:279-377). */
+/* Statistics<T> (vector/src/vector_types/general/statistics.rs:11-31, #[repr(C)]) and the scalar results of
+ * interop/src/lib.rs:229-242 */
+typedef struct { float sum; size_t count; float average; float rms; float min; size_t min_index; float max; size_t max_index; } BdspStatistics32;
+typedef struct { double sum; size_t count; double average; double rms; double min; size_t min_index; double max; size_t max_index; } BdspStatistics64;
+typedef struct { BdspComplex32 sum; size_t count; BdspComplex32 average; BdspComplex32 rms; BdspComplex32 min; size_t min_index; BdspComplex32 max; size_t max_index; } BdspComplexStatistics32;
+typedef struct { BdspComplex64 sum; size_t count; BdspComplex64 average; BdspComplex64 rms; BdspComplex64 min; size_t min_index; BdspComplex64 max; size_t max_index; } BdspComplexStatistics64;
+typedef struct { int32_t result_code; const void* result; } BdspPointerResult;
+typedef struct { int32_t result_code; float result; } BdspScalarResult32;
+typedef struct { int32_t result_code; double result; } BdspScalarResult64;
+typedef struct { int32_t result_code; BdspComplex32 result; } BdspComplexScalarResult32;
+typedef struct { int32_t result_code; BdspComplex64 result; } BdspComplexScalarResult64;
+
+/* expf32 / powf32 / expf64 / powf64 are also names of glibc's _Float32 / _Float64 functions (<math.h> with
+ * _GNU_SOURCE).  The library exports the reference's symbol names; C and C++ callers use the bdsp_-prefixed
+ * declarations below, which bind to those symbols. */
+#if defined(__GNUC__)
+#define BDSP_SYMBOL(name) __asm__(name)
+#else
+#define BDSP_SYMBOL(name)
+#endif
+
 typedef float (*BdspRealFn32)(const void* data, float x);
 typedef double (*BdspRealFn64)(const void* data, double x);
 typedef BdspComplex32 (*BdspComplexFn32)(const void* data, float x);
+/* ForeignWindowFunction (interop/src/lib.rs): window(data, index, points) */
+typedef float (*BdspWindowFn32)(const void* data, size_t i, size_t points);
+typedef double (*BdspWindowFn64)(const void* data, size_t i, size_t points);
 typedef BdspComplex64 (*BdspComplexFn64)(const void* data, double x);
 
 /* ===================================================================================================
@@ -173,6 +197,86 @@ BdspVecResult32 plain_sifft32(BdspVec32* vector);                        /* :949
 BdspVecResult32 sifft32(BdspVec32* vector);                              /* :954 */
 BdspVecResult32 windowed_sifft32(BdspVec32* vector, int32_t window);     /* :1018 */
 
+/* ---- rest of the C facade: elementwise math, reorganisation, reductions ----
+ * (interop/src/facade32.rs:193-321 reductions, :348-524 math, :736-824 reorganisation, :848-931 split statistics,
+ * :1030-1139 custom windows, :1446 hermite).  map_inplace_* / map_aggregate_* (:594-647) call a host function per element:
+ * the vector is staged through host memory for them. */
+BdspVecResult32 sin32(BdspVec32* vector);
+BdspVecResult32 cos32(BdspVec32* vector);
+BdspVecResult32 tan32(BdspVec32* vector);
+BdspVecResult32 asin32(BdspVec32* vector);
+BdspVecResult32 acos32(BdspVec32* vector);
+BdspVecResult32 atan32(BdspVec32* vector);
+BdspVecResult32 sinh32(BdspVec32* vector);
+BdspVecResult32 cosh32(BdspVec32* vector);
+BdspVecResult32 tanh32(BdspVec32* vector);
+BdspVecResult32 asinh32(BdspVec32* vector);
+BdspVecResult32 acosh32(BdspVec32* vector);
+BdspVecResult32 atanh32(BdspVec32* vector);
+BdspVecResult32 sqrt32(BdspVec32* vector);
+BdspVecResult32 square32(BdspVec32* vector);
+BdspVecResult32 ln32(BdspVec32* vector);
+BdspVecResult32 exp32(BdspVec32* vector);
+BdspVecResult32 abs32(BdspVec32* vector);
+BdspVecResult32 ln_approx32(BdspVec32* vector);
+BdspVecResult32 exp_approx32(BdspVec32* vector);
+BdspVecResult32 sin_approx32(BdspVec32* vector);
+BdspVecResult32 cos_approx32(BdspVec32* vector);
+BdspVecResult32 diff32(BdspVec32* vector);
+BdspVecResult32 diff_with_start32(BdspVec32* vector);
+BdspVecResult32 cum_sum32(BdspVec32* vector);
+BdspVecResult32 root32(BdspVec32* vector, float degree);
+BdspVecResult32 log32(BdspVec32* vector, float base);
+BdspVecResult32 wrap32(BdspVec32* vector, float divisor);
+BdspVecResult32 unwrap32(BdspVec32* vector, float divisor);
+BdspVecResult32 log_approx32(BdspVec32* vector, float base);
+BdspVecResult32 expf_approx32(BdspVec32* vector, float base);
+BdspVecResult32 powf_approx32(BdspVec32* vector, float exponent);
+BdspVecResult32 bdsp_powf32(BdspVec32* vector, float exponent) BDSP_SYMBOL("powf32");
+BdspVecResult32 bdsp_expf32(BdspVec32* vector, float base) BDSP_SYMBOL("expf32");
+BdspVecResult32 add_smaller_vector32(BdspVec32* vector, const BdspVec32* operand);
+BdspVecResult32 sub_smaller_vector32(BdspVec32* vector, const BdspVec32* operand);
+BdspVecResult32 mul_smaller_vector32(BdspVec32* vector, const BdspVec32* operand);
+BdspVecResult32 div_smaller_vector32(BdspVec32* vector, const BdspVec32* operand);
+int32_t get_real_imag32(BdspVec32* vector, BdspVec32* real, BdspVec32* imag);
+BdspVecResult32 set_real_imag32(BdspVec32* vector, const BdspVec32* real, const BdspVec32* imag);
+BdspVecResult32 set_mag_phase32(BdspVec32* vector, const BdspVec32* mag, const BdspVec32* phase);
+int32_t split_into32(const BdspVec32* vector, BdspVec32** targets, size_t len);
+BdspVecResult32 merge32(BdspVec32* vector, BdspVec32* const* sources, size_t len);
+BdspVecResult32 interpolate_hermite32(BdspVec32* vector, float interpolation_factor, float delay);
+BdspVecResult32 map_inplace_real32(BdspVec32* vector, float (*map)(float value, size_t index));
+BdspVecResult32 map_inplace_complex32(BdspVec32* vector, BdspComplex32 (*map)(BdspComplex32 value, size_t index));
+BdspPointerResult map_aggregate_real32(const BdspVec32* vector, const void* (*map)(float value, size_t index),
+                                       const void* (*aggregate)(const void* a, const void* b));
+BdspPointerResult map_aggregate_complex32(const BdspVec32* vector, const void* (*map)(BdspComplex32 value, size_t index),
+                                          const void* (*aggregate)(const void* a, const void* b));
+BdspVecResult32 apply_custom_window32(BdspVec32* vector, BdspWindowFn32 window, const void* window_data, uint8_t is_symmetric);
+BdspVecResult32 unapply_custom_window32(BdspVec32* vector, BdspWindowFn32 window, const void* window_data, uint8_t is_symmetric);
+BdspVecResult32 windowed_custom_fft32(BdspVec32* vector, BdspWindowFn32 window, const void* window_data, uint8_t is_symmetric);
+BdspVecResult32 windowed_custom_ifft32(BdspVec32* vector, BdspWindowFn32 window, const void* window_data, uint8_t is_symmetric);
+BdspVecResult32 windowed_custom_sfft32(BdspVec32* vector, BdspWindowFn32 window, const void* window_data, uint8_t is_symmetric);
+BdspVecResult32 windowed_custom_sifft32(BdspVec32* vector, BdspWindowFn32 window, const void* window_data, uint8_t is_symmetric);
+BdspScalarResult32 real_dot_product32(const BdspVec32* vector, const BdspVec32* operand);
+BdspScalarResult32 real_dot_product_prec32(const BdspVec32* vector, const BdspVec32* operand);
+BdspComplexScalarResult32 complex_dot_product32(const BdspVec32* vector, const BdspVec32* operand);
+BdspComplexScalarResult32 complex_dot_product_prec32(const BdspVec32* vector, const BdspVec32* operand);
+float real_sum32(const BdspVec32* vector);
+float real_sum_sq32(const BdspVec32* vector);
+BdspComplex32 complex_sum32(const BdspVec32* vector);
+BdspComplex32 complex_sum_sq32(const BdspVec32* vector);
+double real_sum_prec32(const BdspVec32* vector);
+double real_sum_sq_prec32(const BdspVec32* vector);
+BdspComplex64 complex_sum_prec32(const BdspVec32* vector);
+BdspComplex64 complex_sum_sq_prec32(const BdspVec32* vector);
+BdspStatistics32 real_statistics32(const BdspVec32* vector);
+BdspComplexStatistics32 complex_statistics32(const BdspVec32* vector);
+BdspStatistics64 real_statistics_prec32(const BdspVec32* vector);
+BdspComplexStatistics64 complex_statistics_prec32(const BdspVec32* vector);
+int32_t real_statistics_split32(const BdspVec32* vector, BdspStatistics32* data, size_t len);
+int32_t complex_statistics_split32(const BdspVec32* vector, BdspComplexStatistics32* data, size_t len);
+int32_t real_statistics_split_prec32(const BdspVec32* vector, BdspStatistics64* data, size_t len);
+int32_t complex_statistics_split_prec32(const BdspVec32* vector, BdspComplexStatistics64* data, size_t len);
+
 /* ---- f64 twins (interop/src/facade64.rs, same line numbers + 1) ------------------------------------------------ */
 BdspVecResult64 apply_window64(BdspVec64* vector, int32_t window);
 BdspVecResult64 unapply_window64(BdspVec64* vector, int32_t window);
@@ -199,6 +303,81 @@ BdspVecResult64 windowed_sfft64(BdspVec64* vector, int32_t window);
 BdspVecResult64 plain_sifft64(BdspVec64* vector);
 BdspVecResult64 sifft64(BdspVec64* vector);
 BdspVecResult64 windowed_sifft64(BdspVec64* vector, int32_t window);
+BdspVecResult64 sin64(BdspVec64* vector);
+BdspVecResult64 cos64(BdspVec64* vector);
+BdspVecResult64 tan64(BdspVec64* vector);
+BdspVecResult64 asin64(BdspVec64* vector);
+BdspVecResult64 acos64(BdspVec64* vector);
+BdspVecResult64 atan64(BdspVec64* vector);
+BdspVecResult64 sinh64(BdspVec64* vector);
+BdspVecResult64 cosh64(BdspVec64* vector);
+BdspVecResult64 tanh64(BdspVec64* vector);
+BdspVecResult64 asinh64(BdspVec64* vector);
+BdspVecResult64 acosh64(BdspVec64* vector);
+BdspVecResult64 atanh64(BdspVec64* vector);
+BdspVecResult64 sqrt64(BdspVec64* vector);
+BdspVecResult64 square64(BdspVec64* vector);
+BdspVecResult64 ln64(BdspVec64* vector);
+BdspVecResult64 exp64(BdspVec64* vector);
+BdspVecResult64 abs64(BdspVec64* vector);
+BdspVecResult64 ln_approx64(BdspVec64* vector);
+BdspVecResult64 exp_approx64(BdspVec64* vector);
+BdspVecResult64 sin_approx64(BdspVec64* vector);
+BdspVecResult64 cos_approx64(BdspVec64* vector);
+BdspVecResult64 diff64(BdspVec64* vector);
+BdspVecResult64 diff_with_start64(BdspVec64* vector);
+BdspVecResult64 cum_sum64(BdspVec64* vector);
+BdspVecResult64 root64(BdspVec64* vector, double degree);
+BdspVecResult64 log64(BdspVec64* vector, double base);
+BdspVecResult64 wrap64(BdspVec64* vector, double divisor);
+BdspVecResult64 unwrap64(BdspVec64* vector, double divisor);
+BdspVecResult64 log_approx64(BdspVec64* vector, double base);
+BdspVecResult64 expf_approx64(BdspVec64* vector, double base);
+BdspVecResult64 powf_approx64(BdspVec64* vector, double exponent);
+BdspVecResult64 bdsp_powf64(BdspVec64* vector, double exponent) BDSP_SYMBOL("powf64");
+BdspVecResult64 bdsp_expf64(BdspVec64* vector, double base) BDSP_SYMBOL("expf64");
+BdspVecResult64 add_smaller_vector64(BdspVec64* vector, const BdspVec64* operand);
+BdspVecResult64 sub_smaller_vector64(BdspVec64* vector, const BdspVec64* operand);
+BdspVecResult64 mul_smaller_vector64(BdspVec64* vector, const BdspVec64* operand);
+BdspVecResult64 div_smaller_vector64(BdspVec64* vector, const BdspVec64* operand);
+int32_t get_real_imag64(BdspVec64* vector, BdspVec64* real, BdspVec64* imag);
+BdspVecResult64 set_real_imag64(BdspVec64* vector, const BdspVec64* real, const BdspVec64* imag);
+BdspVecResult64 set_mag_phase64(BdspVec64* vector, const BdspVec64* mag, const BdspVec64* phase);
+int32_t split_into64(const BdspVec64* vector, BdspVec64** targets, size_t len);
+BdspVecResult64 merge64(BdspVec64* vector, BdspVec64* const* sources, size_t len);
+BdspVecResult64 interpolate_hermite64(BdspVec64* vector, double interpolation_factor, double delay);
+BdspVecResult64 map_inplace_real64(BdspVec64* vector, double (*map)(double value, size_t index));
+BdspVecResult64 map_inplace_complex64(BdspVec64* vector, BdspComplex64 (*map)(BdspComplex64 value, size_t index));
+BdspPointerResult map_aggregate_real64(const BdspVec64* vector, const void* (*map)(double value, size_t index),
+                                       const void* (*aggregate)(const void* a, const void* b));
+BdspPointerResult map_aggregate_complex64(const BdspVec64* vector, const void* (*map)(BdspComplex64 value, size_t index),
+                                          const void* (*aggregate)(const void* a, const void* b));
+BdspVecResult64 apply_custom_window64(BdspVec64* vector, BdspWindowFn64 window, const void* window_data, uint8_t is_symmetric);
+BdspVecResult64 unapply_custom_window64(BdspVec64* vector, BdspWindowFn64 window, const void* window_data, uint8_t is_symmetric);
+BdspVecResult64 windowed_custom_fft64(BdspVec64* vector, BdspWindowFn64 window, const void* window_data, uint8_t is_symmetric);
+BdspVecResult64 windowed_custom_ifft64(BdspVec64* vector, BdspWindowFn64 window, const void* window_data, uint8_t is_symmetric);
+BdspVecResult64 windowed_custom_sfft64(BdspVec64* vector, BdspWindowFn64 window, const void* window_data, uint8_t is_symmetric);
+BdspVecResult64 windowed_custom_sifft64(BdspVec64* vector, BdspWindowFn64 window, const void* window_data, uint8_t is_symmetric);
+BdspScalarResult64 real_dot_product64(const BdspVec64* vector, const BdspVec64* operand);
+BdspScalarResult64 real_dot_product_prec64(const BdspVec64* vector, const BdspVec64* operand);
+BdspComplexScalarResult64 complex_dot_product64(const BdspVec64* vector, const BdspVec64* operand);
+BdspComplexScalarResult64 complex_dot_product_prec64(const BdspVec64* vector, const BdspVec64* operand);
+double real_sum64(const BdspVec64* vector);
+double real_sum_sq64(const BdspVec64* vector);
+BdspComplex64 complex_sum64(const BdspVec64* vector);
+BdspComplex64 complex_sum_sq64(const BdspVec64* vector);
+double real_sum_prec64(const BdspVec64* vector);
+double real_sum_sq_prec64(const BdspVec64* vector);
+BdspComplex64 complex_sum_prec64(const BdspVec64* vector);
+BdspComplex64 complex_sum_sq_prec64(const BdspVec64* vector);
+BdspStatistics64 real_statistics64(const BdspVec64* vector);
+BdspComplexStatistics64 complex_statistics64(const BdspVec64* vector);
+BdspStatistics64 real_statistics_prec64(const BdspVec64* vector);
+BdspComplexStatistics64 complex_statistics_prec64(const BdspVec64* vector);
+int32_t real_statistics_split64(const BdspVec64* vector, BdspStatistics64* data, size_t len);
+int32_t complex_statistics_split64(const BdspVec64* vector, BdspComplexStatistics64* data, size_t len);
+int32_t real_statistics_split_prec64(const BdspVec64* vector, BdspStatistics64* data, size_t len);
+int32_t complex_statistics_split_prec64(const BdspVec64* vector, BdspComplexStatistics64* data, size_t len);
 BdspVec64* new64(int32_t is_complex, int32_t domain, double init_value, size_t length, double delta);
 BdspVec64* new_with_performance_options64(int32_t is_complex, int32_t domain, double init_value, size_t length, double delta, size_t core_limit);
 BdspVec64* new_with_detailed_performance_options64(int32_t is_complex, int32_t domain, double init_value, size_t length,

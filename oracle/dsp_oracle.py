@@ -833,6 +833,303 @@ def windowed_sifft(X, kind, dtype):
     return y * window_table(kind, len(y), dtype, unapply=True).astype(np.float64)
 
 
+# --------------------------------------------------------------------------------------------------
+# elementwise math (trigonometry_and_powers.rs:198-377, real_ops.rs:243-289)
+# Real vectors call the scalar libm function of T.  Complex vectors call num-complex (dependency
+# `num-complex = "^0.4"`, vector/Cargo.toml:39; not vendored in the reference tree): its published
+# formulas are restated below in precision T on separate re / im arrays.
+# --------------------------------------------------------------------------------------------------
+def _split(x, dtype):
+    x = np.asarray(x)
+    return np.ascontiguousarray(x.real, dtype=dtype), np.ascontiguousarray(x.imag, dtype=dtype)
+
+
+def _join(re, im, dtype):
+    ct = np.complex64 if dtype == np.float32 else np.complex128
+    out = np.empty(len(re), dtype=ct)
+    out.real = re
+    out.imag = im
+    return out
+
+
+def _c_mul(a, b):
+    return a[0] * b[0] - a[1] * b[1], a[0] * b[1] + a[1] * b[0]
+
+
+def _c_polar(a):
+    return np.hypot(a[0], a[1]), np.arctan2(a[1], a[0])
+
+
+def _c_from_polar(r, th):
+    return r * np.cos(th), r * np.sin(th)
+
+
+def _c_ln(a):
+    r, th = _c_polar(a)
+    return np.log(r), th
+
+
+def _c_sqrt(a):
+    """num-complex Complex::sqrt: exact branches for purely real / purely imaginary input, polar form otherwise."""
+    re, im = a
+    T = re.dtype.type
+    r, th = _c_polar(a)
+    gre, gim = _c_from_polar(np.sqrt(r), th / T(2))
+    # re == 0, im != 0
+    x = np.sqrt(np.abs(im) / T(2))
+    ore = np.where(re == 0, x, gre)
+    oim = np.where(re == 0, np.where(np.signbit(im), -x, x), gim)
+    # im == 0
+    pos = ~np.signbit(re)
+    sre = np.sqrt(np.abs(re))
+    ore = np.where(im == 0, np.where(pos, sre, T(0)), ore)
+    oim = np.where(im == 0, np.where(pos, im, np.where(np.signbit(im), -sre, sre)), oim)
+    return ore.astype(re.dtype), oim.astype(re.dtype)
+
+
+def complex_math(name, x, dtype, arg=None):
+    """pure_complex_operation with the num-complex method `name`."""
+    T = _T(dtype)
+    re, im = _split(x, dtype)
+    z = (re, im)
+    one = (np.ones_like(re), np.zeros_like(re))
+    with np.errstate(all="ignore"):
+        if name == "sin":
+            r = (np.sin(re) * np.cosh(im), np.cos(re) * np.sinh(im))
+        elif name == "cos":
+            r = (np.cos(re) * np.cosh(im), -np.sin(re) * np.sinh(im))
+        elif name == "tan":
+            tr, ti = re + re, im + im
+            d = np.cos(tr) + np.cosh(ti)
+            r = (np.sin(tr) / d, np.sinh(ti) / d)
+        elif name == "sinh":
+            r = (np.sinh(re) * np.cos(im), np.cosh(re) * np.sin(im))
+        elif name == "cosh":
+            r = (np.cosh(re) * np.cos(im), np.sinh(re) * np.sin(im))
+        elif name == "tanh":
+            tr, ti = re + re, im + im
+            d = np.cosh(tr) + np.cos(ti)
+            r = (np.sinh(tr) / d, np.sin(ti) / d)
+        elif name == "asin":      # -i ln(sqrt(1 - z^2) + i z)
+            zz = _c_mul(z, z)
+            s = _c_sqrt((one[0] - zz[0], one[1] - zz[1]))
+            w = _c_ln((s[0] - im, s[1] + re))
+            r = (w[1], -w[0])
+        elif name == "acos":      # -i ln(i sqrt(1 - z^2) + z)
+            zz = _c_mul(z, z)
+            s = _c_sqrt((one[0] - zz[0], one[1] - zz[1]))
+            w = _c_ln((-s[1] + re, s[0] + im))
+            r = (w[1], -w[0])
+        elif name == "atan":      # (ln(1 + i z) - ln(1 - i z)) / (2 i)
+            a = _c_ln((one[0] - im, one[1] + re))
+            b = _c_ln((one[0] + im, one[1] - re))
+            d = (a[0] - b[0], a[1] - b[1])
+            r = (d[1] / T(2), -d[0] / T(2))
+        elif name == "asinh":     # ln(z + sqrt(1 + z^2))
+            zz = _c_mul(z, z)
+            s = _c_sqrt((one[0] + zz[0], one[1] + zz[1]))
+            r = _c_ln((re + s[0], im + s[1]))
+        elif name == "acosh":     # 2 ln(sqrt((z + 1)/2) + sqrt((z - 1)/2))
+            a = _c_sqrt(((re + T(1)) / T(2), im / T(2)))
+            b = _c_sqrt(((re - T(1)) / T(2), im / T(2)))
+            w = _c_ln((a[0] + b[0], a[1] + b[1]))
+            r = (T(2) * w[0], T(2) * w[1])
+        elif name == "atanh":     # (ln(1 + z) - ln(1 - z)) / 2
+            a = _c_ln((one[0] + re, one[1] + im))
+            b = _c_ln((one[0] - re, one[1] - im))
+            r = ((a[0] - b[0]) / T(2), (a[1] - b[1]) / T(2))
+        elif name == "sqrt":
+            r = _c_sqrt(z)
+        elif name == "square":
+            r = _c_mul(z, z)
+        elif name == "ln":
+            r = _c_ln(z)
+        elif name == "exp":
+            r = _c_from_polar(np.exp(re), im)
+        elif name == "powf":
+            rr, th = _c_polar(z)
+            r = _c_from_polar(np.power(rr, T(arg)), th * T(arg))
+            if T(arg) == 0:
+                r = (np.ones_like(re), np.zeros_like(re))
+        elif name == "log":
+            rr, th = _c_polar(z)
+            lb = np.log(T(arg))
+            r = (np.log(rr) / lb, th / lb)
+        elif name == "expf":      # base^z = from_polar(base^re, im * ln(base))
+            r = _c_from_polar(np.power(T(arg), re), im * np.log(T(arg)))
+        else:
+            raise ValueError(name)
+    return _join(np.asarray(r[0], dtype=dtype), np.asarray(r[1], dtype=dtype), dtype)
+
+
+def real_math(name, x, dtype, arg=None):
+    """pure_real_operation / simd_real_operation with the scalar function of T."""
+    T = _T(dtype)
+    x = np.asarray(x, dtype=dtype)
+    f = {"sin": np.sin, "cos": np.cos, "tan": np.tan, "asin": np.arcsin, "acos": np.arccos, "atan": np.arctan,
+         "sinh": np.sinh, "cosh": np.cosh, "tanh": np.tanh, "asinh": np.arcsinh, "acosh": np.arccosh,
+         "atanh": np.arctanh, "sqrt": np.sqrt, "ln": np.log, "exp": np.exp, "abs": np.abs}
+    with np.errstate(all="ignore"):
+        if name in f:
+            return f[name](x).astype(dtype)
+        if name == "square":
+            return (x * x).astype(dtype)
+        if name == "powf":
+            return np.power(x, T(arg)).astype(dtype)
+        if name == "root":
+            return np.power(x, T(1) / T(arg)).astype(dtype)
+        if name == "log":
+            return (np.log(x) / np.log(T(arg))).astype(dtype)
+        if name == "expf":
+            return np.power(T(arg), x).astype(dtype)
+        if name == "wrap":        # Rust `%` on floats: fmod
+            return np.fmod(x, T(arg)).astype(dtype)
+    raise ValueError(name)
+
+
+def unwrap(x, divisor, dtype):
+    """ModuloOps::unwrap (real_ops.rs:266-288), sequential: each element is compared with its already
+    unwrapped predecessor."""
+    T = _T(dtype)
+    d = np.asarray(x, dtype=dtype).copy()
+    div = T(divisor)
+    half = T(div / T(2))
+    for j in range(1, len(d)):
+        diff = T(d[j] - d[j - 1])
+        if diff > half:
+            diff = T(np.fmod(diff, div))
+            diff = T(diff - div)
+            d[j] = T(d[j - 1] + diff)
+        elif diff < -half:
+            diff = T(np.fmod(diff, div))
+            diff = T(diff + div)
+            d[j] = T(d[j - 1] + diff)
+    return d
+
+
+def diff(x, with_start=False):
+    """DiffSumOps::diff / diff_with_start (diff_sum.rs:63-109)."""
+    x = np.asarray(x)
+    if with_start:
+        return np.concatenate([x[:1], x[1:] - x[:-1]]).astype(x.dtype)
+    return (x[1:] - x[:-1]).astype(x.dtype)
+
+
+def cum_sum(x):
+    """DiffSumOps::cum_sum (diff_sum.rs:111-122): sequential running sum in T."""
+    return np.cumsum(np.asarray(x), dtype=np.asarray(x).dtype)
+
+
+def binary_smaller(op, x, w, dtype):
+    """add/sub/mul/div_smaller (elementary.rs:457-517,601-639): operand element i % operand.len()."""
+    x = np.asarray(x)
+    w = np.asarray(w)
+    if len(x) % len(w) != 0:
+        return ERR_INVALID_ARG_LEN
+    ww = np.tile(w, len(x) // len(w))
+    return {"add": add, "sub": sub, "mul": mul, "div": div}[op](x, ww, dtype)
+
+
+def split_into(x, n):
+    """data_reorganization.rs:484-512: element i goes to target i % n at position i / n."""
+    x = np.asarray(x)
+    if n == 0 or len(x) % n != 0:
+        return ERR_INVALID_ARG_LEN
+    return [x[i::n].copy() for i in range(n)]
+
+
+def merge(sources):
+    """data_reorganization.rs:522-557: inverse of split_into."""
+    n = len(sources)
+    if n == 0 or any(len(s) != len(sources[0]) for s in sources):
+        return ERR_INVALID_ARG_LEN
+    out = np.empty(n * len(sources[0]), dtype=np.asarray(sources[0]).dtype)
+    for i, s in enumerate(sources):
+        out[i::n] = s
+    return out
+
+
+def set_mag_phase(mag, phase, dtype):
+    """complex_to_real.rs:749-770: Complex::from_polar(mag, phase) = (mag cos(phase), mag sin(phase))."""
+    mag = np.asarray(mag, dtype=dtype)
+    phase = np.asarray(phase, dtype=dtype)
+    return _join(mag * np.cos(phase), mag * np.sin(phase), dtype)
+
+
+def interpolate_hermite(x, factor, delay, dtype):
+    """RealInterpolationOps::interpolate_hermite (real_interpolation.rs:73-178), every operation in T,
+    including the output counter `i = i + 1` kept in T."""
+    T = _T(dtype)
+    x = np.asarray(x, dtype=dtype)
+    n = len(x)
+    F, d = T(factor), T(delay)
+    dest_len = int(np.round(T(n - 1) * F)) + 1
+    start = int(np.ceil((T(1) - d) * F))
+    end = start + 1
+    half, c15, two, c25 = T(0.5), T(1.5), T(2.0), T(2.5)
+    out = np.empty(dest_len, dtype=dtype)
+    i = T(0)
+    for k in range(dest_len):
+        rounded = T(i / F + d)
+        bf = T(np.floor(rounded))
+        b = int(bf)
+        if k < start:
+            y1, y2, y3 = x[b], x[b + 1], x[b + 2]
+            y0 = T(y1 - T(y2 - y1))
+        elif k < dest_len - end:
+            y0, y1, y2, y3 = x[b - 1], x[b], x[b + 1], x[b + 2]
+        else:
+            y0, y1 = x[b - 1], x[b]
+            y2 = x[b + 1] if b < n - 1 else T(y1 + T(y1 - y0))
+            y3 = x[b + 2] if b < n - 2 else T(y2 + T(y2 - y1))
+        xx = T(rounded - bf)
+        x2 = T(xx * xx)
+        a0 = T(T(T(T(-half * y0) + T(c15 * y1)) - T(c15 * y2)) + T(half * y3))
+        a1 = T(T(T(y0 - T(c25 * y1)) + T(two * y2)) - T(half * y3))
+        a2 = T(T(-half * y0) + T(half * y2))
+        out[k] = T(T(T(T(T(a0 * xx) * x2) + T(a1 * x2)) + T(a2 * xx)) + y1)
+        i = T(i + T(1))
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# reductions (statistics.rs, precise_stats.rs, dot_products.rs)
+# --------------------------------------------------------------------------------------------------
+def statistics(x):
+    """StatisticsOps::statistics (statistics.rs:179-340) as computed on ONE chunk (the reference merges
+    per-thread chunk results; its merge drops a chunk's minimum when the same chunk also raised the
+    maximum, :230-236 - the restatement is the single-chunk result).  Complex: min / max by norm,
+    rms = sqrt(sum(z^2) / count) (complex)."""
+    x = np.asarray(x)
+    n = len(x)
+    acc = x.astype(np.complex128 if np.iscomplexobj(x) else np.float64)
+    s = acc.sum()
+    ssq = (acc * acc).sum()
+    if n == 0:
+        nan = float("nan")
+        return dict(sum=s, count=0, average=nan, rms=nan, min=float("inf"), min_index=0, max=float("-inf"), max_index=0)
+    key = np.abs(acc) if np.iscomplexobj(x) else acc
+    imin, imax = int(np.argmin(key)), int(np.argmax(key))
+    return dict(sum=s, count=n, average=s / n, rms=np.sqrt(ssq / n), min=x[imin], min_index=imin, max=x[imax], max_index=imax)
+
+
+def statistics_split(x, parts):
+    """statistics_split (statistics.rs:395-440): element j belongs to part j % parts with index j / parts."""
+    if parts > 16:
+        return ERR_INVALID_ARG_LEN
+    x = np.asarray(x)
+    return [statistics(x[i::parts]) for i in range(parts)]
+
+
+def dot_product(a, b):
+    """DotProductOps::dot_product (dot_products.rs:67-160): sum(a[i] * b[i]) (no conjugation)."""
+    a = np.asarray(a)
+    b = np.asarray(b)
+    n = min(len(a), len(b))
+    wide = np.complex128 if np.iscomplexobj(a) else np.float64
+    return (a[:n].astype(wide) * b[:n].astype(wide)).sum()
+
+
 def reverse(x):
     return np.asarray(x)[::-1].copy()
 

@@ -16,8 +16,10 @@ def declared_functions():
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     src = re.sub(r"^\s*#.*$", "", src, flags=re.M)
     src = re.sub(r"typedef[^;]*;", "", src)
+    # `T name(args) BDSP_SYMBOL("sym");` declares the exported symbol `sym` (names that clash with glibc's <math.h>)
+    src = re.sub(r"\b[A-Za-z_][A-Za-z0-9_]*(\s*\([^;{}()]*\))\s*BDSP_SYMBOL\(\s*\"([A-Za-z0-9_]+)\"\s*\)\s*;", r"\2\1;", src)
     names = re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;{}]*\)\s*;", src)
-    return sorted({n for n in names if not n.startswith("Bdsp") and n not in ("defined",)})
+    return sorted({n for n in names if not n.startswith("Bdsp") and n not in ("defined", "__asm__")})
 
 
 @pytest.fixture(scope="module")

@@ -3,6 +3,7 @@
 Expected values come from tests/golden/reference_kats.json (extracted from the reference sources by
 tests/golden/extract_goldens.py); the input construction of every case is restated here with the
 reference file:line it follows.  CPU only."""
+import math
 import numpy as np
 import pytest
 
@@ -479,3 +480,63 @@ def test_symmetric_transforms():  # tests/real_test.rs:581-605 (real_fft_test32)
     bad = S.copy(); bad[0] += 1j
     assert o.plain_sifft(bad) == o.ERR_CONJ_SYMMETRIC
     assert len(o.sfft(x)) == 501 and np.allclose(o.sfft(x)[-1], np.sum(x))   # shifted: DC is the last kept bin
+
+
+# --------------------------------------------------------------------------------------------------
+# rest of the facade: the reference's doc examples and unit tests pin the oracle
+# --------------------------------------------------------------------------------------------------
+def test_hermite_kats():  # real_interpolation.rs:196-228
+    got = o.interpolate_hermite([-1.0, -2.0, -1.0, 0.0, 1.0, 3.0, 4.0], 4.0, 0.0, np.float32)
+    exp = [-1.0000, -1.4375, -1.7500, -1.9375, -2.0000, -1.8906, -1.6250, -1.2969, -1.0000, -0.7500, -0.5000, -0.2500, 0.0,
+           0.2344, 0.4583, 0.7031, 1.0000, 1.4375, 2.0000, 2.5625, 3.0000, 3.3203, 3.6042, 3.8359, 4.0]
+    assert len(got) == len(exp) and np.max(np.abs(got[4:-4] - np.array(exp)[4:-4])) < 6e-2
+    got = o.interpolate_hermite([-3.0, -2.0, -1.0, 0.0, 1.0, 2.0, 3.0], 3.0, 0.0, np.float32)
+    assert np.max(np.abs(got - np.linspace(-3, 3, 19))) < 5e-3
+
+
+def test_statistics_doc_examples():  # statistics.rs:45-66, 82-92, 98-131
+    z = np.array([1 + 2j, 3 + 4j, 5 + 6j], dtype=np.complex64)
+    st = o.statistics(z)
+    assert st["sum"] == 9 + 12j and st["count"] == 3 and st["average"] == 3 + 4j
+    assert abs(st["rms"] - (3.4027193 + 4.3102784j)) < 1e-4
+    assert (st["min"], st["min_index"], st["max"], st["max_index"]) == (1 + 2j, 0, 5 + 6j, 2)
+    sp = o.statistics_split(z, 2)
+    assert sp[0]["sum"] == 6 + 8j and sp[1]["sum"] == 3 + 4j
+    assert np.sum(z.astype(np.complex128) ** 2) == -21 + 88j
+    assert o.statistics_split(z, 17) == o.ERR_INVALID_ARG_LEN
+
+
+def test_elementwise_doc_examples():  # trigonometry_and_powers.rs:9-191, diff_sum.rs:13-60, real_ops.rs doc examples
+    f64 = np.float64
+    assert np.allclose(o.real_math("sin", [math.pi / 2, -math.pi / 2], f64), [1.0, -1.0])
+    assert np.array_equal(o.real_math("sqrt", [1.0, 4.0, 9.0, 16.0, 25.0], f64), [1, 2, 3, 4, 5])
+    assert np.array_equal(o.real_math("square", [1.0, 2.0, 3.0, 4.0, 5.0], f64), [1, 4, 9, 16, 25])
+    assert np.allclose(o.real_math("root", [1.0, 8.0, 27.0], f64, 3.0), [1, 2, 3])
+    assert np.allclose(o.real_math("powf", [1.0, 2.0, 3.0], f64, 3.0), [1, 8, 27])
+    assert np.allclose(o.real_math("ln", [2.718281828459045, 7.389056, 20.085537], f64), [1, 2, 3], atol=1e-6)
+    assert np.allclose(o.real_math("log", [10.0, 100.0, 1000.0], f64, 10.0), [1, 2, 3])
+    assert np.allclose(o.real_math("expf", [1.0, 2.0, 3.0], f64, 10.0), [10, 100, 1000])
+    assert np.array_equal(o.diff(np.array([2.0, 3.0, 2.0, 6.0])), [1.0, -1.0, 4.0])
+    assert np.array_equal(o.diff(np.array([2.0, 3.0, 2.0, 6.0]), with_start=True), [2.0, 1.0, -1.0, 4.0])
+    assert np.array_equal(o.cum_sum(np.array([2.0, 1.0, -1.0, 4.0])), [2.0, 3.0, 2.0, 6.0])
+    assert np.array_equal(o.real_math("wrap", [1.0, 2.0, 3.0, 4.0, 5.0, 6.0, 7.0, 8.0], f64, 4.0), [1, 2, 3, 0, 1, 2, 3, 0])
+    assert np.array_equal(o.unwrap(np.array([1.0, 2.0, 3.0, 0.0, 1.0, 2.0, 3.0, 0.0]), 4.0, f64), [1, 2, 3, 4, 5, 6, 7, 8])
+    # complex functions against an independent implementation (NumPy's C99 complex math) in f64
+    rng = np.random.default_rng(0)
+    z = rng.uniform(-2, 2, 500) + 1j * rng.uniform(-2, 2, 500)
+    for name, fn in [("sin", np.sin), ("cos", np.cos), ("sinh", np.sinh), ("cosh", np.cosh), ("asin", np.arcsin),
+                     ("acos", np.arccos), ("atan", np.arctan), ("asinh", np.arcsinh), ("acosh", np.arccosh),
+                     ("atanh", np.arctanh), ("sqrt", np.sqrt), ("ln", np.log), ("exp", np.exp)]:
+        got = o.complex_math(name, z, f64)
+        assert np.max(np.abs(got - fn(z)) / np.maximum(1, np.abs(fn(z)))) < 1e-13, name
+    assert np.max(np.abs(o.complex_math("powf", z, f64, 2.5) - z ** 2.5)) < 1e-12
+    assert np.max(np.abs(o.complex_math("expf", z, f64, 3.0) - 3.0 ** z)) < 1e-12
+
+
+def test_split_merge_and_smaller():
+    x = np.arange(12.0)
+    parts = o.split_into(x, 3)
+    assert [p.tolist() for p in parts] == [[0, 3, 6, 9], [1, 4, 7, 10], [2, 5, 8, 11]]
+    assert np.array_equal(o.merge(parts), x)
+    assert o.split_into(x, 5) == o.ERR_INVALID_ARG_LEN
+    assert np.array_equal(o.binary_smaller("add", x, np.array([10.0, 20.0]), np.float64), x + np.tile([10.0, 20.0], 6))
