@@ -151,17 +151,42 @@ template <typename T> __device__ T real_fn(int op, T x, T arg, T ln_arg) {
     }
 }
 
+// 16 bytes per thread and access; the n % W tail is handled by the first threads
+template <typename T> struct alignas(16) Pack { T v[16 / sizeof(T)]; };
 template <typename T>
 __global__ void math_real_kernel(T* __restrict__ data, long long n, int op, T arg, T ln_arg) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr int W = 16 / sizeof(T);
+    const long long nv = n / W;
+    Pack<T>* dv = reinterpret_cast<Pack<T>*>(data);
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (; i < n; i += stride) data[i] = real_fn<T>(op, data[i], arg, ln_arg);
+    for (long long i = tid; i < nv; i += stride) {
+        Pack<T> p = dv[i];
+#pragma unroll
+        for (int k = 0; k < W; k++) p.v[k] = real_fn<T>(op, p.v[k], arg, ln_arg);
+        dv[i] = p;
+    }
+    const long long t = nv * W + tid;
+    if (t < n) data[t] = real_fn<T>(op, data[t], arg, ln_arg);
 }
 template <typename T>
 __global__ void math_complex_kernel(C2<T>* __restrict__ data, long long n, int op, T arg, T ln_arg) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr int W = 16 / sizeof(C2<T>) > 0 ? 16 / sizeof(C2<T>) : 1;   // 2 (f32) or 1 (f64)
+    const long long nv = n / W;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (; i < n; i += stride) data[i] = complex_fn<T>(op, data[i], arg, ln_arg);
+    Pack<T>* dv = reinterpret_cast<Pack<T>*>(data);
+    for (long long i = tid; i < nv; i += stride) {
+        Pack<T> p = dv[i];
+#pragma unroll
+        for (int k = 0; k < W; k++) {
+            const C2<T> r = complex_fn<T>(op, mkc(p.v[2 * k], p.v[2 * k + 1]), arg, ln_arg);
+            p.v[2 * k] = r.re; p.v[2 * k + 1] = r.im;
+        }
+        dv[i] = p;
+    }
+    const long long t = nv * W + tid;
+    if (t < n) data[t] = complex_fn<T>(op, data[t], arg, ln_arg);
 }
 
 unsigned grid_for(long long items, int threads) {
@@ -249,13 +274,25 @@ __global__ void cumsum_totals_kernel(const T* __restrict__ in, T* __restrict__ t
     if (threadIdx.x == 0) totals[(long long)lane * gridDim.x + blockIdx.x] = sh[0];
 }
 template <typename T>
-__global__ void cumsum_scan_totals_kernel(T* __restrict__ totals, long long nblocks, int lanes) {
-    // one thread per lane: sequential exclusive scan (nblocks = points / 2048, small)
-    const int lane = threadIdx.x;
-    if (lane >= lanes) return;
-    T run = (T)0;
-    T* t = totals + (long long)lane * nblocks;
-    for (long long b = 0; b < nblocks; b++) { const T v = t[b]; t[b] = run; run = add_(run, v); }
+__global__ void __launch_bounds__(1024) cumsum_scan_totals_kernel(T* __restrict__ totals, long long nblocks, int lanes) {
+    // one block per lane: exclusive scan of the per-block totals (thread t owns a contiguous run)
+    __shared__ T sh[1024];
+    T* t = totals + (long long)blockIdx.x * nblocks;
+    const long long per = (nblocks + 1023) / 1024;
+    const long long b0 = (long long)threadIdx.x * per;
+    T s = (T)0;
+    for (long long b = b0; b < b0 + per && b < nblocks; b++) s = add_(s, t[b]);
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        T add = (T)0;
+        if (threadIdx.x >= off) add = sh[threadIdx.x - off];
+        __syncthreads();
+        if (threadIdx.x >= off) sh[threadIdx.x] = add_(sh[threadIdx.x], add);
+        __syncthreads();
+    }
+    T run = threadIdx.x ? sh[threadIdx.x - 1] : (T)0;
+    for (long long b = b0; b < b0 + per && b < nblocks; b++) { const T v = t[b]; t[b] = run; run = add_(run, v); }
 }
 template <typename T>
 __global__ void cumsum_apply_kernel(const T* __restrict__ in, T* __restrict__ out, const T* __restrict__ totals, long long points, int lanes) {
@@ -383,8 +420,9 @@ int math_unary(int op, void* data, size_t elems, int is_complex, double arg, cud
     const T a = (T)arg;
     T ln_arg;   // `base.ln()` evaluated in T
     if (sizeof(T) == 4) ln_arg = (T)logf((float)a); else ln_arg = (T)log((double)a);
-    if (is_complex) math_complex_kernel<T><<<grid_for((long long)elems, 256), 256, 0, st>>>(reinterpret_cast<C2<T>*>(data), (long long)elems, op, a, ln_arg);
-    else math_real_kernel<T><<<grid_for((long long)elems, 256), 256, 0, st>>>(reinterpret_cast<T*>(data), (long long)elems, op, a, ln_arg);
+    const long long items = (long long)elems * (is_complex ? 2 : 1) * (long long)sizeof(T) / 16 + 1;
+    if (is_complex) math_complex_kernel<T><<<grid_for(items, 256), 256, 0, st>>>(reinterpret_cast<C2<T>*>(data), (long long)elems, op, a, ln_arg);
+    else math_real_kernel<T><<<grid_for(items, 256), 256, 0, st>>>(reinterpret_cast<T*>(data), (long long)elems, op, a, ln_arg);
     BDSP_LAUNCHED();
     return 0;
 }
@@ -418,7 +456,7 @@ int math_cumsum(const void* in, void* out, void* work, size_t points, int lanes,
     dim3 grid(nblocks, (unsigned)lanes);
     cumsum_totals_kernel<T><<<grid, CS_THREADS, 0, st>>>(reinterpret_cast<const T*>(in), reinterpret_cast<T*>(work), (long long)points, lanes);
     BDSP_LAUNCHED();
-    cumsum_scan_totals_kernel<T><<<1, 32, 0, st>>>(reinterpret_cast<T*>(work), (long long)nblocks, lanes);
+    cumsum_scan_totals_kernel<T><<<lanes, 1024, 0, st>>>(reinterpret_cast<T*>(work), (long long)nblocks, lanes);
     BDSP_LAUNCHED();
     cumsum_apply_kernel<T><<<grid, CS_THREADS, 0, st>>>(reinterpret_cast<const T*>(in), reinterpret_cast<T*>(out), reinterpret_cast<const T*>(work), (long long)points, lanes);
     BDSP_LAUNCHED();

@@ -64,11 +64,12 @@ enum { R_SUMS = 0, R_DOT = 1, R_STATS = 2 };
 __device__ __forceinline__ double norm_T(float re, float im) { return (double)hypotf(re, im); }
 __device__ __forceinline__ double norm_T(double re, double im) { return hypot(re, im); }
 
+// one element: real (re; bre for the dot product) or complex (re, im; bre, bim)
 template <typename T, int MODE, bool PREC>
-__device__ __forceinline__ void rec_add(Rec& r, const T* __restrict__ a, const T* __restrict__ b, long long j, unsigned long long index, bool cplx) {
+__device__ __forceinline__ void rec_add(Rec& r, T tre, T tim, T tbre, T tbim, unsigned long long index, bool cplx) {
     if (!cplx) {
-        const double v = (double)a[j];
-        if (MODE == R_DOT) { kadd<PREC>(r.s[0], r.c[0], __dmul_rn(v, (double)b[j])); return; }
+        const double v = (double)tre;
+        if (MODE == R_DOT) { kadd<PREC>(r.s[0], r.c[0], __dmul_rn(v, (double)tbre)); return; }
         kadd<PREC>(r.s[0], r.c[0], v);
         kadd<PREC>(r.s[2], r.c[2], __dmul_rn(v, v));
         if (MODE == R_STATS) {
@@ -77,10 +78,9 @@ __device__ __forceinline__ void rec_add(Rec& r, const T* __restrict__ a, const T
             r.cnt++;
         }
     } else {
-        const T tre = a[2 * j], tim = a[2 * j + 1];
         const double re = (double)tre, im = (double)tim;
         if (MODE == R_DOT) {
-            const double bre = (double)b[2 * j], bim = (double)b[2 * j + 1];
+            const double bre = (double)tbre, bim = (double)tbim;
             kadd<PREC>(r.s[0], r.c[0], __dsub_rn(__dmul_rn(re, bre), __dmul_rn(im, bim)));
             kadd<PREC>(r.s[1], r.c[1], __dadd_rn(__dmul_rn(re, bim), __dmul_rn(im, bre)));
             return;
@@ -97,6 +97,13 @@ __device__ __forceinline__ void rec_add(Rec& r, const T* __restrict__ a, const T
         }
     }
 }
+template <typename T, int MODE, bool PREC>
+__device__ __forceinline__ void rec_add_at(Rec& r, const T* __restrict__ a, const T* __restrict__ b, long long j, unsigned long long index, bool cplx) {
+    if (!cplx) rec_add<T, MODE, PREC>(r, a[j], (T)0, MODE == R_DOT ? b[j] : (T)0, (T)0, index, false);
+    else rec_add<T, MODE, PREC>(r, a[2 * j], a[2 * j + 1], MODE == R_DOT ? b[2 * j] : (T)0, MODE == R_DOT ? b[2 * j + 1] : (T)0, index, true);
+}
+
+template <typename T> struct alignas(16) Pack { T v[16 / sizeof(T)]; };
 
 constexpr int RT = 256;
 
@@ -119,8 +126,33 @@ __global__ void __launch_bounds__(RT) reduce_kernel(const T* __restrict__ a, con
     Rec r;
     rec_init(r, cplx != 0);
     const long long stride = (long long)gridDim.x * RT;
-    for (long long m = (long long)blockIdx.x * RT + threadIdx.x; m < count; m += stride)
-        rec_add<T, MODE, PREC>(r, a, b, part + parts * m, (unsigned long long)m, cplx != 0);
+    const long long tid = (long long)blockIdx.x * RT + threadIdx.x;
+    if (parts == 1) {
+        // 16-byte loads: SC scalars = W elements per thread and step; indices stay increasing within a thread
+        constexpr int SC = 16 / sizeof(T);
+        const int W = cplx ? SC / 2 : SC;
+        const long long nv = count / W;
+        const Pack<T>* av = reinterpret_cast<const Pack<T>*>(a);
+        const Pack<T>* bv = reinterpret_cast<const Pack<T>*>(b);
+        for (long long m = tid; m < nv; m += stride) {
+            const Pack<T> pa = av[m];
+            Pack<T> pb = pa;
+            if (MODE == R_DOT) pb = bv[m];
+            if (!cplx) {
+#pragma unroll
+                for (int k = 0; k < SC; k++) rec_add<T, MODE, PREC>(r, pa.v[k], (T)0, pb.v[k], (T)0, (unsigned long long)(m * SC + k), false);
+            } else {
+#pragma unroll
+                for (int k = 0; k < SC / 2; k++)
+                    rec_add<T, MODE, PREC>(r, pa.v[2 * k], pa.v[2 * k + 1], pb.v[2 * k], pb.v[2 * k + 1], (unsigned long long)(m * (SC / 2) + k), true);
+            }
+        }
+        if (tid == 0)
+            for (long long j = nv * W; j < count; j++) rec_add_at<T, MODE, PREC>(r, a, b, j, (unsigned long long)j, cplx != 0);
+    } else {
+        for (long long m = tid; m < count; m += stride)
+            rec_add_at<T, MODE, PREC>(r, a, b, part + parts * m, (unsigned long long)m, cplx != 0);
+    }
     block_fold<PREC>(r, sh);
     if (threadIdx.x == 0) partial[(long long)part * gridDim.x + blockIdx.x] = sh[0];
 }

@@ -147,6 +147,33 @@ def main():
         report("X1", "4 x 2^24 c32 plain fft (3-pass)", n * rows, 16 * n * rows, 5 * n * 24 * rows, med, best)
         del vin, out
 
+
+    if "R1" in want:
+        # extra: reductions and elementwise math over 2^27 f32 scalars (512 MiB, > L2)
+        n = 1 << 27
+        x = rng.uniform(-10, 10, n).astype(np.float32)
+        v = DspVec(x)
+        w = DspVec(x[::-1].copy())
+        med, best = T.run(lambda: v.sum(), args.iters)
+        report("R1", "real f32 2^27 sum (incl. result read-back)", n, 4 * n, 0, med, best)
+        med, best = T.run(lambda: v.statistics(), args.iters)
+        report("R1", "real f32 2^27 statistics (sum, rms, min/max + indices)", n, 4 * n, 0, med, best)
+        med, best = T.run(lambda: v.dot_product(w), args.iters)
+        report("R1", "real f32 2^27 dot_product", n, 8 * n, 0, med, best)
+        c = DspVec(x.view(np.complex64))
+        med, best = T.run(lambda: c.statistics(), args.iters)
+        report("R1", "c32 2^26 statistics", n // 2, 4 * n, 0, med, best)
+        del w
+        med, best = T.run(lambda: v.math("abs"), args.iters)
+        report("R1", "real f32 2^27 abs (in place)", n, 8 * n, 0, med, best)
+        med, best = T.run(lambda: v.math("sin"), args.iters)
+        report("R1", "real f32 2^27 sin (in place)", n, 8 * n, 0, med, best)
+        med, best = T.run(lambda: c.math("sqrt"), args.iters)
+        report("R1", "c32 2^26 complex sqrt (in place)", n // 2, 8 * n, 0, med, best)
+        med, best = T.run(lambda: v.math("cum_sum"), args.iters)
+        report("R1", "real f32 2^27 cum_sum (3 launches)", n, 16 * n, 0, med, best)
+        del v, c
+
     if "C4a" in want or "C4b" in want:
         n = 1 << 24
         x = rng.uniform(-10, 10, n).astype(np.float32)
