@@ -83,11 +83,11 @@ fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, long long row
         }
     }
     for (; row < rows; row += row_step) {
-    // ROWS: `row` counts groups of four rows; groups_per_seq = n1 / 4
-    const size_t seq = ROWS ? (size_t)row / (size_t)(n1 >> 2) : (size_t)row;
-    const int grp = ROWS ? (int)((size_t)row % (size_t)(n1 >> 2)) : 0;
+    // ROWS: `row` counts groups of NSB rows; groups_per_seq = n1 / NSB
+    const size_t seq = ROWS ? (size_t)row / (size_t)(n1 / NSB) : (size_t)row;
+    const int grp = ROWS ? (int)((size_t)row % (size_t)(n1 / NSB)) : 0;
     const size_t seq_len = ROWS ? (size_t)4096 * (size_t)n1 : (size_t)N;
-    const float2* xr = x + seq * seq_len + (ROWS ? (size_t)grp * 4 * 4096 : 0);
+    const float2* xr = x + seq * seq_len + (ROWS ? (size_t)grp * NSB * 4096 : 0);
 
     cp v[16];
     // ------------------------------------------------------------------ F0: radix-R0 over stride 4096
@@ -248,9 +248,9 @@ fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, long long row
         }
         fft16_dif<INV>(P);
         // slot j holds k2 = bitrev4(j); k = (rank*NSB + lsb) + R0*(k0 + 16*k1 + 256*k2)
-        // (ROWS: k = (4*grp + lsb) + n1*(k0 + 16*k1 + 256*k2))
+        // (ROWS: k = (NSB*grp + lsb) + n1*(k0 + 16*k1 + 256*k2))
         const int kst = ROWS ? n1 : R0;
-        const size_t klow = (ROWS ? (size_t)(4 * grp + lsb) : (size_t)(rank * NSB + lsb)) + (size_t)kst * (size_t)(k0 + 16 * k1);
+        const size_t klow = (ROWS ? (size_t)(NSB * grp + lsb) : (size_t)(rank * NSB + lsb)) + (size_t)kst * (size_t)(k0 + 16 * k1);
         const size_t k2s = (size_t)256 * (size_t)kst;
         if constexpr (MAG) {
             float* o = reinterpret_cast<float*>(out_) + seq * seq_len + klow;
@@ -481,6 +481,19 @@ int fftp_dispatch(const void* in, void* out, size_t rows, bool inv, bool shift_i
                     : fftp_launch<R0, CL, true, false, false, false>(in, out, rows, scale, st);
 }
 
+
+#ifndef FP_ROWS_DEFAULT
+#define FP_ROWS_DEFAULT 4
+#endif
+template <int NR>
+int fftp_rows_pass(const void* tmp, void* out, size_t groups, bool inverse, bool so, bool magnitude, float sc, cudaStream_t st, int n1) {
+    if (inverse) return fftp_launch<NR, 1, true, false, false, false, true>(tmp, out, groups, sc, st, n1);
+    if (magnitude) return so ? fftp_launch<NR, 1, false, false, true, true, true>(tmp, out, groups, sc, st, n1)
+                             : fftp_launch<NR, 1, false, false, false, true, true>(tmp, out, groups, sc, st, n1);
+    return so ? fftp_launch<NR, 1, false, false, true, false, true>(tmp, out, groups, sc, st, n1)
+              : fftp_launch<NR, 1, false, false, false, false, true>(tmp, out, groups, sc, st, n1);
+}
+
 template <bool INV, bool SI>
 int fftp_colpass(const void* in, void* tmp, size_t n, size_t rows, cudaStream_t st) {
     const float* tw = fftp_twiddles();
@@ -506,7 +519,14 @@ int fftp_two_pass_try(const void* in, void* out, void* tmp, size_t n, size_t row
     if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 7) || (reinterpret_cast<uintptr_t>(tmp) & 15)) return 1;
     if (tmp == in || tmp == out) return 1;
     const int n1 = (int)(n / 4096);
-    const size_t groups = rows * (size_t)(n1 / 4);
+    // rows per CTA in the last pass: 4 (one 512-thread CTA per SM, full 32-byte store sectors) or 2 (two 256-thread
+    // CTAs per SM whose phases overlap; 16-byte half sectors that pair up in L2).  Measured on B200 (64 x 2^20):
+    // 0.453 ms with 4 rows, 0.494 ms with 2, so 4 is the default; BDSP_FFTP_ROWS selects for A/B runs.
+    static const int rows_per_cta = [] {
+        const char* e = getenv("BDSP_FFTP_ROWS");
+        return (e && e[0] == '4') ? 4 : (e && e[0] == '2') ? 2 : FP_ROWS_DEFAULT;
+    }();
+    const size_t groups = rows * (size_t)(n1 / rows_per_cta);
     if (groups > 0x7fffffffull || rows * 256 > 0x7fffffffull) return 1;
     const bool si = in_rot != 0, so = out_rot != 0;
     const float sc = (float)scale;
@@ -526,16 +546,13 @@ int fftp_two_pass_try(const void* in, void* out, void* tmp, size_t n, size_t row
         const size_t nr = rows - r0 < chunk ? rows - r0 : chunk;
         const void* cin = reinterpret_cast<const char*>(in) + r0 * n * sizeof(float2);
         void* cout = reinterpret_cast<char*>(out) + r0 * n * out_elem;
-        const size_t groups_c = nr * (size_t)(n1 / 4);
+        const size_t groups_c = nr * (size_t)(n1 / rows_per_cta);
         int rc;
         if (inverse) rc = si ? fftp_colpass<true, true>(cin, tmp, n, nr, st) : fftp_colpass<true, false>(cin, tmp, n, nr, st);
         else rc = si ? fftp_colpass<false, true>(cin, tmp, n, nr, st) : fftp_colpass<false, false>(cin, tmp, n, nr, st);
         if (rc) return rc;
-        if (inverse) rc = fftp_launch<4, 1, true, false, false, false, true>(tmp, cout, groups_c, sc, st, n1);
-        else if (magnitude) rc = so ? fftp_launch<4, 1, false, false, true, true, true>(tmp, cout, groups_c, sc, st, n1)
-                                    : fftp_launch<4, 1, false, false, false, true, true>(tmp, cout, groups_c, sc, st, n1);
-        else rc = so ? fftp_launch<4, 1, false, false, true, false, true>(tmp, cout, groups_c, sc, st, n1)
-                     : fftp_launch<4, 1, false, false, false, false, true>(tmp, cout, groups_c, sc, st, n1);
+        if (rows_per_cta == 4) rc = fftp_rows_pass<4>(tmp, cout, groups_c, inverse, so, magnitude, sc, st, n1);
+        else rc = fftp_rows_pass<2>(tmp, cout, groups_c, inverse, so, magnitude, sc, st, n1);
         if (rc) return rc;
     }
     return 0;
