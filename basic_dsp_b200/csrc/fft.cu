@@ -176,8 +176,11 @@ struct TileParams {
     OutMap om;
 };
 
+#ifndef BDSP_TILE_F64_RADIX8
+#define BDSP_TILE_F64_RADIX8 1
+#endif
 template <typename T, bool INV>
-__global__ void __launch_bounds__(sizeof(T) == 4 ? 1024 : 512) fft_tile_kernel(TileParams p, T scale, const typename CpxOf<T>::type* __restrict__ tw) {
+__global__ void __launch_bounds__(sizeof(T) == 4 ? 1024 : 512, (sizeof(T) == 8 && BDSP_TILE_F64_RADIX8) ? 2 : 1) fft_tile_kernel(TileParams p, T scale, const typename CpxOf<T>::type* __restrict__ tw) {
     typedef typename CpxOf<T>::type C;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C* s = reinterpret_cast<C*>(smem_raw);
@@ -192,29 +195,37 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? 1024 : 512) fft_tile_kernel(T
     const long long lane0 = tile * ct;
     const long long in_base = b * p.in_batch_stride + o1 * p.in_o1_stride;
     const int total = m * ct;
-    // ---- load ----
-    if (p.in_point_stride == 1) {
-        for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-            int l = idx >> p.log2m, pt = idx & (m - 1);
-            long long g = o1 * p.in_o1_stride + (lane0 + l) * p.in_lane_stride + pt;
-            g += p.in_rot; if (g >= p.in_n) g -= p.in_n;
-            C v;
-            if (p.real_input) { v.x = reinterpret_cast<const T*>(p.in)[b * p.in_batch_stride + g]; v.y = 0; }
-            else v = reinterpret_cast<const C*>(p.in)[b * p.in_batch_stride + g];
-            v.x *= scale; v.y *= scale;
-            s[spad(l * sstride + pt)] = v;
-        }
-    } else {
+    // ---- load ----  (UN independent global loads are issued before the first use: the loop is latency-bound otherwise)
+    {
+        constexpr int UN = 8;
+        const bool contiguous = p.in_point_stride == 1;
         const int lct = __ffs(ct) - 1;
-        for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-            int pt = idx >> lct, l = idx & (ct - 1);
-            long long g = o1 * p.in_o1_stride + (lane0 + l) * p.in_lane_stride + (long long)pt * p.in_point_stride;
-            g += p.in_rot; if (g >= p.in_n) g -= p.in_n;
-            C v;
-            if (p.real_input) { v.x = reinterpret_cast<const T*>(p.in)[b * p.in_batch_stride + g]; v.y = 0; }
-            else v = reinterpret_cast<const C*>(p.in)[b * p.in_batch_stride + g];
-            v.x *= scale; v.y *= scale;
-            s[spad(l * sstride + pt)] = v;
+        for (int base = threadIdx.x; base < total; base += blockDim.x * UN) {
+            C v[UN];
+#pragma unroll
+            for (int u = 0; u < UN; u++) {
+                const int idx = base + u * blockDim.x;
+                if (idx < total) {
+                    int l, pt;
+                    if (contiguous) { l = idx >> p.log2m; pt = idx & (m - 1); }
+                    else { pt = idx >> lct; l = idx & (ct - 1); }
+                    long long g = o1 * p.in_o1_stride + (lane0 + l) * p.in_lane_stride + (long long)pt * p.in_point_stride;
+                    g += p.in_rot; if (g >= p.in_n) g -= p.in_n;
+                    if (p.real_input) { v[u].x = reinterpret_cast<const T*>(p.in)[b * p.in_batch_stride + g]; v[u].y = 0; }
+                    else v[u] = reinterpret_cast<const C*>(p.in)[b * p.in_batch_stride + g];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UN; u++) {
+                const int idx = base + u * blockDim.x;
+                if (idx < total) {
+                    int l, pt;
+                    if (contiguous) { l = idx >> p.log2m; pt = idx & (m - 1); }
+                    else { pt = idx >> lct; l = idx & (ct - 1); }
+                    v[u].x *= scale; v[u].y *= scale;
+                    s[spad(l * sstride + pt)] = v[u];
+                }
+            }
         }
     }
     (void)in_base;
@@ -224,10 +235,18 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? 1024 : 512) fft_tile_kernel(T
         const int n = m;
         int Ns = 1, rem = p.log2m;
         // same stage sequence as block_fft, but with the padded sequence stride
-        while (rem >= 4) { stockham_stage_strided<T, 16, INV, 1>(s, n, ct, sstride, Ns, tw); Ns <<= 4; rem -= 4; }
-        if (rem == 3) stockham_stage_strided<T, 8, INV, 2>(s, n, ct, sstride, Ns, tw);
-        else if (rem == 2) stockham_stage_strided<T, 4, INV, 4>(s, n, ct, sstride, Ns, tw);
-        else if (rem == 1) stockham_stage_strided<T, 2, INV, 8>(s, n, ct, sstride, Ns, tw);
+        if constexpr (sizeof(T) == 8 && BDSP_TILE_F64_RADIX8) {
+            // f64: radix-8 stages, 8 points per thread (half the registers of radix 16 -> twice the resident warps;
+            // 2^9 = 8*8*8 needs the same three stages as 16*16*2)
+            while (rem >= 3) { stockham_stage_strided<T, 8, INV, 1>(s, n, ct, sstride, Ns, tw); Ns <<= 3; rem -= 3; }
+            if (rem == 2) stockham_stage_strided<T, 4, INV, 2>(s, n, ct, sstride, Ns, tw);
+            else if (rem == 1) stockham_stage_strided<T, 2, INV, 4>(s, n, ct, sstride, Ns, tw);
+        } else {
+            while (rem >= 4) { stockham_stage_strided<T, 16, INV, 1>(s, n, ct, sstride, Ns, tw); Ns <<= 4; rem -= 4; }
+            if (rem == 3) stockham_stage_strided<T, 8, INV, 2>(s, n, ct, sstride, Ns, tw);
+            else if (rem == 2) stockham_stage_strided<T, 4, INV, 4>(s, n, ct, sstride, Ns, tw);
+            else if (rem == 1) stockham_stage_strided<T, 2, INV, 8>(s, n, ct, sstride, Ns, tw);
+        }
     }
     // ---- twiddle + store ----
     // W_{tw_n}^{lane*k} = A[l][k & 31] * B[l][k >> 5] with A[l][a] = W^{lane*a}, B[l][b] = W^{lane*32*b}:
@@ -254,6 +273,7 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? 1024 : 512) fft_tile_kernel(T
     }
     const bool lane_major = (p.out_lane_stride <= p.out_point_stride);
     const int lct = __ffs(ct) - 1;
+#pragma unroll 4
     for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
         int l, k;
         if (lane_major) { k = idx >> lct; l = idx & (ct - 1); }
@@ -278,38 +298,53 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? 1024 : 512) fft_tile_kernel(T
 // ------------------------------------------------------------------------------------------
 // radix-q pass for n = q * P, q odd and small:  y[k1*P + n2] = W_n^{n2 k1} sum_{n1} x[n1*P + n2] W_q^{n1 k1}
 // ------------------------------------------------------------------------------------------
-template <typename T, bool INV>
-__global__ void dft_q_pass_kernel(const void* __restrict__ in_, typename CpxOf<T>::type* __restrict__ out, int q,
+// Q > 0: compile-time radix (registers, unrolled); Q == 0: any odd q <= 31 (arrays in local memory).
+// The q-th roots of unity are evaluated once per block into shared memory.
+template <typename T, bool INV, int Q>
+__global__ void dft_q_pass_kernel(const void* __restrict__ in_, typename CpxOf<T>::type* __restrict__ out, int q_rt,
                                   long long P, long long batch, long long in_rot, int real_input, T scale) {
     typedef typename CpxOf<T>::type C;
+    constexpr int QM = Q > 0 ? Q : 31;
+    const int q = Q > 0 ? Q : q_rt;
+    __shared__ C wq[31];
+    const int sign = INV ? 1 : -1;
+    if ((int)threadIdx.x < q) wq[threadIdx.x] = unit_root<T>((unsigned long long)threadIdx.x, (unsigned long long)q, sign);
+    __syncthreads();
     const long long n = (long long)q * P;
     long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= P * batch) return;
     const long long b = gid / P, n2 = gid - b * P;
-    const int sign = INV ? 1 : -1;
-    C xin[31], wq[31];   // q <= 31
-    for (int n1 = 0; n1 < q; n1++) {
-        long long g = (long long)n1 * P + n2 + in_rot;
-        if (g >= n) g -= n;
-        C v;
-        if (real_input) { v.x = reinterpret_cast<const T*>(in_)[b * n + g]; v.y = 0; }
-        else v = reinterpret_cast<const C*>(in_)[b * n + g];
-        xin[n1] = v;
-        wq[n1] = unit_root<T>((unsigned long long)n1, (unsigned long long)q, sign);
+    C xin[QM];
+#pragma unroll
+    for (int n1 = 0; n1 < QM; n1++) {
+        if (n1 < q) {
+            long long g = (long long)n1 * P + n2 + in_rot;
+            if (g >= n) g -= n;
+            C v;
+            if (real_input) { v.x = reinterpret_cast<const T*>(in_)[b * n + g]; v.y = 0; }
+            else v = reinterpret_cast<const C*>(in_)[b * n + g];
+            xin[n1] = v;
+        }
     }
     const C w1 = unit_root<T>((unsigned long long)n2, (unsigned long long)n, sign);   // W_n^{n2}
     C wk = mk<T>(1, 0);                                                                // W_n^{n2*k1}
-    for (int k1 = 0; k1 < q; k1++) {
-        C acc = xin[0];
-        int e = 0;
-        for (int n1 = 1; n1 < q; n1++) {
-            e += k1; if (e >= q) e -= q;          // (n1*k1) mod q
-            acc = cadd(acc, cmul(xin[n1], wq[e]));
+#pragma unroll
+    for (int k1 = 0; k1 < QM; k1++) {
+        if (k1 < q) {
+            C acc = xin[0];
+            int e = 0;
+#pragma unroll
+            for (int n1 = 1; n1 < QM; n1++) {
+                if (n1 < q) {
+                    e += k1; if (e >= q) e -= q;          // (n1*k1) mod q
+                    acc = cadd(acc, cmul(xin[n1], wq[e]));
+                }
+            }
+            acc = cmul(acc, wk);
+            acc.x *= scale; acc.y *= scale;
+            out[b * n + (long long)k1 * P + n2] = acc;
+            wk = cmul(wk, w1);
         }
-        acc = cmul(acc, wk);
-        acc.x *= scale; acc.y *= scale;
-        out[b * n + (long long)k1 * P + n2] = acc;
-        wk = cmul(wk, w1);
     }
 }
 
@@ -442,6 +477,7 @@ int launch_tile(const TileParams& p, long long batch, T scale, cudaStream_t st) 
     const int m = 1 << p.log2m;
     const size_t smem = (spad_host((size_t)(m + 16) * p.ct) + (size_t)p.ct * (33 + (((m + 31) >> 5) | 1))) * sizeof(C);
     int threads = block_fft_threads(m, p.ct);
+    if (sizeof(T) == 8 && BDSP_TILE_F64_RADIX8) { threads = (m * p.ct / 8 + 31) / 32 * 32; if (threads < 32) threads = 32; }
     const long long grid = batch * p.o1_count * (p.lanes / p.ct);
     int rc = set_smem(fft_tile_kernel<T, INV>, smem);
     if (rc) return rc;
@@ -544,8 +580,11 @@ int fft_any(const void* in, void* out, size_t n, size_t batch, const FftOpts& o,
         size_t need = n * batch * sizeof(C);
         C* w1 = reinterpret_cast<C*>(workspace(need, 1));
         const long long tot = (long long)(P * batch);
-        dft_q_pass_kernel<T, INV><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(in, w1, (int)q, (long long)P, (long long)batch,
-                                                                                  in_rot, o.real_input, scale);
+        const unsigned qgrid = (unsigned)((tot + 255) / 256);
+        if (q == 3) dft_q_pass_kernel<T, INV, 3><<<qgrid, 256, 0, st>>>(in, w1, 3, (long long)P, (long long)batch, in_rot, o.real_input, scale);
+        else if (q == 5) dft_q_pass_kernel<T, INV, 5><<<qgrid, 256, 0, st>>>(in, w1, 5, (long long)P, (long long)batch, in_rot, o.real_input, scale);
+        else if (q == 7) dft_q_pass_kernel<T, INV, 7><<<qgrid, 256, 0, st>>>(in, w1, 7, (long long)P, (long long)batch, in_rot, o.real_input, scale);
+        else dft_q_pass_kernel<T, INV, 0><<<qgrid, 256, 0, st>>>(in, w1, (int)q, (long long)P, (long long)batch, in_rot, o.real_input, scale);
         BDSP_LAUNCHED();
         OutMap om2;
         om2.seq_group = (long long)q; om2.oes = (long long)q; om2.group_stride = (long long)n;

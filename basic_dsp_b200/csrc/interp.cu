@@ -265,25 +265,41 @@ interp_poly_f32_kernel(const float* __restrict__ x, float* __restrict__ y, const
     float2 acc[IPF_RP][2];
 #pragma unroll
     for (int p = 0; p < IPF_RP; p++) { acc[p][0] = make_float2(0.f, 0.f); acc[p][1] = make_float2(0.f, 0.f); }
-    const int base = threadIdx.x * IPF_RP;
+    // window slot k of this thread lives at sxx[ipf_skew(8*tid + k)] = wbase[k + (k >> 3)]: within one block of 8 taps
+    // the 8 slots that enter the window are contiguous, and the block start advances by 9 float2
+    const float2* wbase = sxx + threadIdx.x * (IPF_RP + 1);
     float2 win[IPF_RP];
 #pragma unroll
-    for (int p = 0; p < IPF_RP; p++) win[p] = sxx[ipf_skew(base + p)];
-    for (int jb = 0; jb < JI; jb += IPF_RP) {
+    for (int p = 0; p < IPF_RP; p++) win[p] = wbase[p];
+    const int full = JI & ~(IPF_RP - 1);
+    const float2* wp = wbase + (IPF_RP + 1);
+    const float4* tp = stab;
+    for (int jb = 0; jb < full; jb += IPF_RP, wp += IPF_RP + 1, tp += IPF_RP) {
 #pragma unroll
         for (int jj = 0; jj < IPF_RP; jj++) {
-            const int j = jb + jj;
-            if (j < JI) {
-                const float4 t4 = stab[j];
-                const float2 ta = make_float2(t4.x, t4.y), tb = make_float2(t4.z, t4.w);
+            const float4 t4 = tp[jj];
+            const float2 ta = make_float2(t4.x, t4.y), tb = make_float2(t4.z, t4.w);
 #pragma unroll
-                for (int p = 0; p < IPF_RP; p++) {
-                    const float2 xx = win[(jj + p) % IPF_RP];
-                    acc[p][0] = __ffma2_rn(xx, ta, acc[p][0]);
-                    acc[p][1] = __ffma2_rn(xx, tb, acc[p][1]);
-                }
-                win[jj] = sxx[ipf_skew(base + j + IPF_RP)];
+            for (int p = 0; p < IPF_RP; p++) {
+                const float2 xx = win[(jj + p) % IPF_RP];
+                acc[p][0] = __ffma2_rn(xx, ta, acc[p][0]);
+                acc[p][1] = __ffma2_rn(xx, tb, acc[p][1]);
             }
+            win[jj] = wp[jj];
+        }
+    }
+#pragma unroll
+    for (int jj = 0; jj < IPF_RP; jj++) {
+        if (full + jj < JI) {      // remaining taps (warp-uniform condition)
+            const float4 t4 = tp[jj];
+            const float2 ta = make_float2(t4.x, t4.y), tb = make_float2(t4.z, t4.w);
+#pragma unroll
+            for (int p = 0; p < IPF_RP; p++) {
+                const float2 xx = win[(jj + p) % IPF_RP];
+                acc[p][0] = __ffma2_rn(xx, ta, acc[p][0]);
+                acc[p][1] = __ffma2_rn(xx, tb, acc[p][1]);
+            }
+            win[jj] = wp[jj];
         }
     }
     __syncthreads();
@@ -305,9 +321,14 @@ interp_poly_f32_kernel(const float* __restrict__ x, float* __restrict__ y, const
     }
     __syncthreads();
     float* yo = y + r0 * F;
-    if (F == 4) {   // 32 outputs per staging row: no integer division in the copy-out loop
-#pragma unroll 8
-        for (int o = threadIdx.x; o < IPF_POS * 4; o += IP2_THREADS) yo[o] = so[(o >> 5) * IPF_ROW + (o & 31)];
+    if (F == 4) {   // 32 outputs per staging row: no integer division in the copy-out loop; 16-byte stores
+#pragma unroll
+        for (int it = 0; it < IPF_RP; it++) {
+            const int o = 4 * (threadIdx.x + IP2_THREADS * it);
+            const float* sp = so + (o >> 5) * IPF_ROW + (o & 31);
+            const float2 a = *reinterpret_cast<const float2*>(sp), b = *reinterpret_cast<const float2*>(sp + 2);
+            *reinterpret_cast<float4*>(yo + o) = make_float4(a.x, a.y, b.x, b.y);
+        }
     } else {
         const int per_thread = IPF_RP * F;
         const int total = IPF_POS * F;
@@ -453,19 +474,27 @@ __device__ __forceinline__ double lin_eval(double i, double F, double d, const d
 __device__ __forceinline__ float counter_value(long long i, float) { return i >= 16777216ll ? 16777216.0f : (float)i; }
 __device__ __forceinline__ double counter_value(long long i, double) { return i >= 9007199254740992ll ? 9007199254740992.0 : (double)i; }
 
+template <typename T> struct alignas(16) LinPack { T v[16 / sizeof(T)]; };
+// 16 bytes of output per thread and step (4 f32 / 2 f64 consecutive results)
 template <typename T>
 __global__ void interp_lin_kernel(const T* __restrict__ x, T* __restrict__ y, long long n, long long dest_len, T F, T d) {
+    constexpr int W = 16 / sizeof(T);
+    const long long nv = (dest_len - 1) / W;          // packs that do not contain the last element
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (; i < dest_len; i += stride) {
-        if (i == dest_len - 1) y[i] = x[n - 1];
-        else y[i] = lin_eval(counter_value(i, (T)0), F, d, x, n);
+    for (long long v = i; v < nv; v += stride) {
+        LinPack<T> p;
+#pragma unroll
+        for (int k = 0; k < W; k++) p.v[k] = lin_eval(counter_value(v * W + k, (T)0), F, d, x, n);
+        reinterpret_cast<LinPack<T>*>(y)[v] = p;
     }
+    const long long t = nv * W + i;
+    if (t < dest_len) y[t] = t == dest_len - 1 ? x[n - 1] : lin_eval(counter_value(t, (T)0), F, d, x, n);
 }
 
 template <typename T>
 int interp_lin(const void* x, void* y, size_t n, size_t dest_len, double factor, double delay, cudaStream_t st) {
-    long long grid = ((long long)dest_len + 255) / 256;
+    long long grid = ((long long)dest_len / (16 / (long long)sizeof(T)) + 255) / 256 + 1;
     const long long cap = (long long)sm_count() * 32;
     if (grid > cap) grid = cap;
     interp_lin_kernel<T><<<(unsigned)grid, 256, 0, st>>>(reinterpret_cast<const T*>(x), reinterpret_cast<T*>(y), (long long)n,

@@ -228,7 +228,7 @@ def run_gpu(args):
     # Rows are pipelined over DEPTH (stream, vector handle) pairs so that the upload of row r+1, the kernel
     # of row r and the download of row r-1 overlap (PCIe is full duplex); every call is the reference's
     # per-vector C-ABI entry point.
-    DEPTH = 3
+    DEPTH = int(os.environ.get("BDSP_E2E_DEPTH", "3"))
     hv = bd.DspVec(h)
     hv_warm = bd.DspVec.zeros(2 * N_POINTS, is_complex=True, dtype=np.float32)
     hv_warm.convolve_signal(hv)   # builds and caches the impulse-response spectrum inside `hv`
