@@ -12,64 +12,8 @@ namespace bdsp {
 //   sel 0 = interior outputs  (interpolate_priv_simd, interpolation.rs:244-275; taps reversed)
 //   sel 1 = edge outputs      (interpolate_priv_simd_step, :293-315)
 // built on the host in precision T exactly as function_to_vectors (:133-181) evaluates them.
-// One thread = one input position r = all F phases; the x window is read once per thread from a
-// shared-memory tile (consecutive threads -> consecutive addresses), the taps are warp-uniform
-// broadcast loads.
 // ------------------------------------------------------------------------------------------
 #define IP_THREADS 256
-
-template <typename T, bool CPLX, int FMAX>
-__global__ void __launch_bounds__(IP_THREADS)
-interp_poly_kernel(const void* __restrict__ x_, void* __restrict__ y_, const T* __restrict__ tab, long long N,
-                   long long new_points, int F, int L, long long scalar_len) {
-    typedef typename CpxOf<T>::type C;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int J = 2 * L + 3;
-    T* stab = reinterpret_cast<T*>(smem_raw);                 // [2][F][J]
-    const int tab_elems = 2 * F * J;
-    const int tab_pad = (tab_elems + 3) & ~3;
-    typedef typename std::conditional<CPLX, C, T>::type X;
-    X* sx = reinterpret_cast<X*>(stab + tab_pad);             // IP_THREADS + J - 1 window
-    const long long r0 = (long long)blockIdx.x * IP_THREADS;
-    for (int i = threadIdx.x; i < tab_elems; i += IP_THREADS) stab[i] = tab[i];
-    const int W = IP_THREADS + J - 1;
-    long long g = (r0 - L - 1 + threadIdx.x) % N;
-    if (g < 0) g += N;
-    const long long adv = IP_THREADS % N;
-    for (int w = threadIdx.x; w < W; w += IP_THREADS) {
-        sx[w] = reinterpret_cast<const X*>(x_)[g];
-        g += adv; if (g >= N) g -= N;
-    }
-    __syncthreads();
-    const long long r = r0 + threadIdx.x;
-    if (r * F >= new_points) return;
-    X acc[FMAX];
-    int sel[FMAX];
-#pragma unroll
-    for (int s = 0; s < FMAX; s++) {
-        long long i = r * F + s;
-        bool interior = (i >= scalar_len) && (i < new_points - scalar_len);
-        sel[s] = (interior ? 0 : F * J) + s * J;
-        if (CPLX) { acc[s] = X(); }
-        acc[s] = X();
-    }
-    for (int j = 0; j < J; j++) {
-        const X xv = sx[threadIdx.x + j];
-#pragma unroll
-        for (int s = 0; s < FMAX; s++) {
-            if (s < F) {
-                const T t = stab[sel[s] + j];
-                if constexpr (CPLX) { acc[s].x += xv.x * t; acc[s].y += xv.y * t; }
-                else acc[s] += xv * t;
-            }
-        }
-    }
-#pragma unroll
-    for (int s = 0; s < FMAX; s++) {
-        long long i = r * F + s;
-        if (s < F && i < new_points) reinterpret_cast<X*>(y_)[i] = acc[s];
-    }
-}
 
 // generic-factor variant of the same polyphase kernel for F > 8: one thread per output
 template <typename T, bool CPLX>
