@@ -61,8 +61,9 @@ template <bool PREC> __device__ __forceinline__ void rec_merge(Rec& a, const Rec
 
 enum { R_SUMS = 0, R_DOT = 1, R_STATS = 2 };
 
-__device__ __forceinline__ double norm_T(float re, float im) { return (double)hypotf(re, im); }
-__device__ __forceinline__ double norm_T(double re, double im) { return hypot(re, im); }
+// ordering key of complex values: the squared norm in double (exact products for f32 data).  The reference orders
+// by norm() rounded to T; the two orders differ only between values whose norms round to the same T.
+__device__ __forceinline__ double norm_key(double re, double im) { return fma(re, re, im * im); }
 
 // one element: real (re; bre for the dot product) or complex (re, im; bre, bim)
 template <typename T, int MODE, bool PREC>
@@ -90,7 +91,7 @@ __device__ __forceinline__ void rec_add(Rec& r, T tre, T tim, T tbre, T tbim, un
         kadd<PREC>(r.s[2], r.c[2], __dsub_rn(__dmul_rn(re, re), __dmul_rn(im, im)));
         kadd<PREC>(r.s[3], r.c[3], __dadd_rn(__dmul_rn(re, im), __dmul_rn(im, re)));
         if (MODE == R_STATS) {
-            const double nn = norm_T(tre, tim);
+            const double nn = norm_key(re, im);
             if (nn > r.mxn) { r.mxn = nn; r.mx[0] = re; r.mx[1] = im; r.mxi = index; }
             if (nn < r.mnn) { r.mnn = nn; r.mn[0] = re; r.mn[1] = im; r.mni = index; }
             r.cnt++;
@@ -134,6 +135,59 @@ __global__ void __launch_bounds__(RT) reduce_kernel(const T* __restrict__ a, con
         const long long nv = count / W;
         const Pack<T>* av = reinterpret_cast<const Pack<T>*>(a);
         const Pack<T>* bv = reinterpret_cast<const Pack<T>*>(b);
+        if (MODE == R_STATS) {
+            // Per element only the ordering key and a 32-bit code (step * W + slot) are kept for the extremes; values and
+            // 64-bit indices are reconstructed after the loop.  Strict comparisons in increasing index order keep the
+            // first occurrence.
+            constexpr unsigned NONE = 0xffffffffu;
+            unsigned mxc = NONE, mnc = NONE, it = 0;
+            if (!cplx) {
+                T mxk = -(T)CUDART_INF, mnk = (T)CUDART_INF;
+                for (long long m = tid; m < nv; m += stride, it++) {
+                    const Pack<T> pa = av[m];
+#pragma unroll
+                    for (int k = 0; k < SC; k++) {
+                        const T x = pa.v[k];
+                        const double v = (double)x;
+                        kadd<PREC>(r.s[0], r.c[0], v);
+                        kadd<PREC>(r.s[2], r.c[2], __dmul_rn(v, v));
+                        const unsigned code = it * SC + k;
+                        if (x > mxk) { mxk = x; mxc = code; }
+                        if (x < mnk) { mnk = x; mnc = code; }
+                    }
+                    r.cnt += SC;
+                }
+                if (mxc != NONE) { r.mxn = r.mx[0] = (double)mxk; r.mxi = (unsigned long long)((tid + (long long)(mxc / SC) * stride) * SC + mxc % SC); }
+                if (mnc != NONE) { r.mnn = r.mn[0] = (double)mnk; r.mni = (unsigned long long)((tid + (long long)(mnc / SC) * stride) * SC + mnc % SC); }
+            } else {
+                constexpr int WC = SC / 2 > 0 ? SC / 2 : 1;
+                double mxk = 0.0, mnk = CUDART_INF;
+                for (long long m = tid; m < nv; m += stride, it++) {
+                    const Pack<T> pa = av[m];
+#pragma unroll
+                    for (int k = 0; k < WC; k++) {
+                        const double re = (double)pa.v[2 * k], im = (double)pa.v[2 * k + 1];
+                        kadd<PREC>(r.s[0], r.c[0], re);
+                        kadd<PREC>(r.s[1], r.c[1], im);
+                        kadd<PREC>(r.s[2], r.c[2], __dsub_rn(__dmul_rn(re, re), __dmul_rn(im, im)));
+                        kadd<PREC>(r.s[3], r.c[3], __dadd_rn(__dmul_rn(re, im), __dmul_rn(im, re)));
+                        const double nn = norm_key(re, im);
+                        const unsigned code = it * WC + k;
+                        if (nn > mxk) { mxk = nn; mxc = code; }
+                        if (nn < mnk) { mnk = nn; mnc = code; }
+                    }
+                    r.cnt += WC;
+                }
+                if (mxc != NONE) {
+                    const long long j = (tid + (long long)(mxc / WC) * stride) * WC + mxc % WC;
+                    r.mxn = mxk; r.mx[0] = (double)a[2 * j]; r.mx[1] = (double)a[2 * j + 1]; r.mxi = (unsigned long long)j;
+                }
+                if (mnc != NONE) {
+                    const long long j = (tid + (long long)(mnc / WC) * stride) * WC + mnc % WC;
+                    r.mnn = mnk; r.mn[0] = (double)a[2 * j]; r.mn[1] = (double)a[2 * j + 1]; r.mni = (unsigned long long)j;
+                }
+            }
+        } else
         for (long long m = tid; m < nv; m += stride) {
             const Pack<T> pa = av[m];
             Pack<T> pb = pa;
