@@ -22,6 +22,8 @@
 
 namespace bdsp {
 
+int fftp_rows1k_try(const void* tmp, void* out, size_t n, size_t rows, bool inverse, size_t out_rot, double scale, bool magnitude,
+                    cudaStream_t st);
 int fftp_two_pass_try(const void* in, void* out, void* tmp, size_t n, size_t rows, bool inverse, size_t in_rot, size_t out_rot,
                       double scale, bool magnitude, cudaStream_t st);
 int fftp_try(const void* in, void* out, size_t n, size_t rows, bool inverse, size_t in_rot, size_t out_rot, double scale,
@@ -497,6 +499,33 @@ int fft_pow2(const void* in, void* out, size_t n, size_t batch, bool real_in, bo
     if (n <= fft_block_max_n<T>()) return launch_block<T, INV>(in, out, n, batch, real_in, mag, in_rot, scale, om, st);
     const int L = ilog2(n);
     const int mx = tile_log2m_max<T>();
+    if (sizeof(T) == 4 && L - 10 <= mx && om.seq_group == 1 && om.oes == 1 && om.group_stride == (long long)n && om.rot_n == (long long)n &&
+        (om.rot == 0 || om.rot == (long long)n / 2) && !(INV && (mag || om.rot != 0))) {
+        // c32, n = n1 * 1024 with n1 <= 2^10: generic column pass (any input form: real, rotated, scaled) followed by the
+        // packed four-rows-per-CTA 1024-point pass of fftp.cu
+        typedef typename CpxOf<T>::type C;
+        TileParams p;
+        const long long n1 = (long long)n / 1024;
+        p.in = in; p.out = work; p.log2m = L - 10;
+        // short columns: more lanes per tile so that a CTA still holds >= 2048 points
+        p.lanes = 1024; p.ct = (int)tile_lanes<T>(); p.o1_count = 1;
+        while (p.ct < 64 && ((long long)p.ct << p.log2m) < 2048) p.ct *= 2;
+        p.in_lane_stride = 1; p.in_point_stride = 1024; p.in_o1_stride = 0; p.in_batch_stride = (long long)n;
+        p.out_lane_stride = 1; p.out_point_stride = 1024; p.out_o1_stride = 0; p.out_batch_stride = (long long)n;
+        p.tw_n = (long long)n; p.in_rot = in_rot; p.in_n = (long long)n; p.real_input = real_in; p.last = 0; p.magnitude = 0;
+        p.om = om;
+        (void)n1;
+        if (work != out && work != in) {
+            int rc = launch_tile<T, INV>(p, (long long)batch, scale, st);
+            if (rc) return rc;
+            rc = fftp_rows1k_try(work, out, n, batch, INV, (size_t)om.rot, 1.0, mag, st);
+            if (rc <= 0) return rc;
+            // not covered (alignment): fall through and redo everything with the generic passes
+        }
+    }
+    // (A three-pass variant of this hybrid - two generic column passes + the packed 1024-point pass - was measured
+    // slower than three generic passes for 2^21 (2.03 vs 1.73 ms per 2^26 points): short columns make the generic
+    // kernel's per-tile twiddle tables dominate.)
     int npass = (L + mx - 1) / mx;
     if (npass > 3) { set_last_error("fft: length 2^%d too large for this build", L); return -2; }
     int l[3] = {0, 0, 0};
@@ -565,7 +594,7 @@ int fft_any(const void* in, void* out, size_t n, size_t batch, const FftOpts& o,
             size_t need = n * batch * sizeof(C);
             if (!w || work_bytes < need) w = workspace(need, 0);
         }
-        if (sizeof(T) == 4 && !o.real_input && (n == 65536 || n == (1u << 20))) {
+        if (sizeof(T) == 4 && !o.real_input && (n == 65536 || n == (1u << 18) || n == (1u << 20))) {
             // packed two-pass path (fftp.cu): 16 B/point of traffic per pass
             const int rc = fftp_two_pass_try(in, out, w, n, batch, INV, (size_t)in_rot, (size_t)om.rot, o.scale, o.magnitude != 0, st);
             if (rc <= 0) return rc;

@@ -37,12 +37,17 @@ __device__ __forceinline__ int fp_rot(int row, int g) { return (((g >> 1) + (row
 // [1024 + 8192*i + c] Re W_{8192<<i}^c, [1024 + 8192*i + 4096 + c] Im, c in [0,4096), i in {0,1}
 // [1024 + 16384 + 4*(16*ka + b)] splat table {c, c, s, s} of W256^{ka*b} (first pass of the 2^20 transform)
 #define FP_TW_SPLAT (1024 + 2 * 8192)
-#define FP_TW_FLOATS (FP_TW_SPLAT + 1024)
+// [FP_TW_1K + c] Re W1024^c, [FP_TW_1K + 256 + c] Im, c in [0,256)
+#define FP_TW_1K (FP_TW_SPLAT + 1024)
+#define FP_TW_FLOATS (FP_TW_1K + 512)
 
 // ROWS = true (R0 = 4, CL = 1): the CTA transforms FOUR independent, adjacent 4096-point rows (no F0) and
 // writes result k of row r to out[(r0 + r) + n1 * k]: the transposing last pass of a two-pass transform of
 // n1 * 4096 points, with the four rows providing the contiguous 32 bytes of every store sector.
-template <int R0, int CL, bool INV, bool SHIFT_IN, bool SHIFT_OUT, bool MAG, bool ROWS>
+// R1K = true (with ROWS, R0 = 1): the CTA's 4096 points are FOUR adjacent 1024-point rows (k0 = 4*q + row): the first
+// stage is a radix-4 butterfly inside every row, the other two stages are unchanged; 128 threads and 35 KB of shared
+// memory per CTA as for a plain 4096-point transform (which runs at the HBM roofline), stores fill 32-byte sectors.
+template <int R0, int CL, bool INV, bool SHIFT_IN, bool SHIFT_OUT, bool MAG, bool ROWS, bool R1K = false>
 // FP_PREFETCH=1: persistent CTAs + register prefetch of the next row.  Measured on B200 (C3): 0.336 ms vs
 // 0.275 ms without (register pressure -> spills; the extra barrier), so it is off by default.
 #ifndef FP_PREFETCH
@@ -50,6 +55,9 @@ template <int R0, int CL, bool INV, bool SHIFT_IN, bool SHIFT_OUT, bool MAG, boo
 #endif
 #ifndef FP_MINB256
 #define FP_MINB256 2
+#endif
+#ifndef FP_DUP
+#define FP_DUP 1
 #endif
 __global__ void __launch_bounds__(128 * (R0 / CL), (R0 / CL) == 2 ? FP_MINB256 : 4 / (R0 / CL))
 fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, long long rows, float scale, const float* __restrict__ tw, int n1) {
@@ -66,7 +74,11 @@ fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, long long row
     // last stage of the current row runs, so that the HBM latency of the load phase is hidden even with
     // one CTA per SM.  CL == 2: one cluster per row.
     constexpr bool PREFETCH = FP_PREFETCH && (CL == 1 && R0 > 1);
-    constexpr int NU = R0 > 1 ? 16 / R0 : 1;   // column pairs per thread in F0: (2048 / CL) / NT
+    // CL > 1 without a cluster (FP_DUP): the CL CTAs of a row each run the first stage over ALL columns (the second
+    // reader is served by L2) and keep only their own NSB sub-blocks: no distributed shared memory, no cluster barrier,
+    // and CL smaller CTAs per row that overlap their phases on the SM.
+    constexpr bool DUP = FP_DUP && CL > 1;
+    constexpr int NU = R0 > 1 ? (2048 / (DUP ? 1 : CL)) / NT : 1;   // column pairs per thread in F0
     float4 raw[PREFETCH ? NU * R0 : 1];
     const long long row_step = gridDim.x / CL;
     long long row = blockIdx.x / CL;
@@ -84,17 +96,19 @@ fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, long long row
     }
     for (; row < rows; row += row_step) {
     // ROWS: `row` counts groups of NSB rows; groups_per_seq = n1 / NSB
-    const size_t seq = ROWS ? (size_t)row / (size_t)(n1 / NSB) : (size_t)row;
-    const int grp = ROWS ? (int)((size_t)row % (size_t)(n1 / NSB)) : 0;
-    const size_t seq_len = ROWS ? (size_t)4096 * (size_t)n1 : (size_t)N;
-    const float2* xr = x + seq * seq_len + (ROWS ? (size_t)grp * NSB * 4096 : 0);
+    constexpr int RPC = R1K ? 4 : NSB;            // rows per CTA (ROWS)
+    constexpr int RLEN = R1K ? 1024 : 4096;       // row length (ROWS)
+    const size_t seq = ROWS ? (size_t)row / (size_t)(n1 / RPC) : (size_t)row;
+    const int grp = ROWS ? (int)((size_t)row % (size_t)(n1 / RPC)) : 0;
+    const size_t seq_len = ROWS ? (size_t)RLEN * (size_t)n1 : (size_t)N;
+    const float2* xr = x + seq * seq_len + (ROWS ? (size_t)grp * RPC * RLEN : 0);
 
     cp v[16];
     // ------------------------------------------------------------------ F0: radix-R0 over stride 4096
     if constexpr (R0 > 1 && !ROWS) {
         float* rre[CL];
         float* rim[CL];
-        if constexpr (CL > 1) {
+        if constexpr (CL > 1 && !DUP) {
             cg::cluster_group cluster = cg::this_cluster();
 #pragma unroll
             for (int o = 0; o < CL; o++) {
@@ -108,7 +122,7 @@ fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, long long row
         const float* tw0 = tw + 1024 + (R0 == 4 ? 8192 : 0);
 #pragma unroll
         for (int u = 0; u < NU; u++) {
-            const int pi = rank * (2048 / CL) + t + NT * u;     // column pair index, c = 2*pi
+            const int pi = (DUP ? 0 : rank * (2048 / CL)) + t + NT * u;     // column pair index, c = 2*pi
             const int c = 2 * pi;
             cp a[R0];
 #pragma unroll
@@ -139,11 +153,18 @@ fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, long long row
 #pragma unroll
             for (int k = 0; k < R0; k++) {
                 const int owner = k / NSB, lsb = k % NSB;
-                *reinterpret_cast<float2*>(rre[owner] + lsb * FP_B + off) = a[k].re;
-                *reinterpret_cast<float2*>(rim[owner] + lsb * FP_B + off) = a[k].im;
+                if (DUP) {
+                    if (owner == rank) {
+                        *reinterpret_cast<float2*>(sre + lsb * FP_B + off) = a[k].re;
+                        *reinterpret_cast<float2*>(sim + lsb * FP_B + off) = a[k].im;
+                    }
+                } else {
+                    *reinterpret_cast<float2*>(rre[owner] + lsb * FP_B + off) = a[k].re;
+                    *reinterpret_cast<float2*>(rim[owner] + lsb * FP_B + off) = a[k].im;
+                }
             }
         }
-        if constexpr (CL > 1) cg::this_cluster().sync();
+        if constexpr (CL > 1 && !DUP) cg::this_cluster().sync();
         else __syncthreads();
     }
     // ------------------------------------------------------------------ F1: stride 256 inside every sub-block
@@ -166,22 +187,44 @@ fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, long long row
 #pragma unroll
             for (int n2 = 0; n2 < 16; n2++) {
                 const int src = SHIFT_IN ? (n2 ^ 8) : n2;
-                const float4 ab = __ldg(reinterpret_cast<const float4*>(xr + (ROWS ? sb * 4096 : 0) + c + 256 * src));
+                const float2* gp = R1K ? xr + (n2 & 3) * 1024 + 256 * (n2 >> 2) + c : xr + (ROWS ? sb * 4096 : 0) + c + 256 * src;
+                const float4 ab = __ldg(reinterpret_cast<const float4*>(gp));
                 v[n2].re = make_float2(ab.x, ab.z);
                 v[n2].im = make_float2(ab.y, ab.w);
             }
         }
-        r16<INV>(v);
-        cp w1;
-        w1.re = *reinterpret_cast<const float2*>(tw + c);
-        w1.im = *reinterpret_cast<const float2*>(tw + 256 + c);
-        if (INV) w1.im = pneg(w1.im);
-        apply_twiddles<true>(v, w1);
+        if constexpr (R1K) {
+            // radix 4 inside each of the four rows (v[row + 4q] -> v[row + 4q']), then W_1024^{c q'}
+            cp w1;
+            w1.re = *reinterpret_cast<const float2*>(tw + FP_TW_1K + c);
+            w1.im = *reinterpret_cast<const float2*>(tw + FP_TW_1K + 256 + c);
+            if (INV) w1.im = pneg(w1.im);
+            const cp w2 = cmul(w1, w1), w3 = cmul(w2, w1);
 #pragma unroll
-        for (int s = 0; s < 16; s++) {
-            const int k0 = r16_k(s);
-            *reinterpret_cast<float2*>(bre + 272 * k0 + off[(k0 >> 1) & 3]) = v[s].re;
-            *reinterpret_cast<float2*>(bim + 272 * k0 + off[(k0 >> 1) & 3]) = v[s].im;
+            for (int r = 0; r < 4; r++) {
+                r4<INV>(v[r], v[r + 4], v[r + 8], v[r + 12]);
+                v[r + 4] = cmul(v[r + 4], w1);
+                v[r + 8] = cmul(v[r + 8], w2);
+                v[r + 12] = cmul(v[r + 12], w3);
+            }
+#pragma unroll
+            for (int k0 = 0; k0 < 16; k0++) {
+                *reinterpret_cast<float2*>(bre + 272 * k0 + off[(k0 >> 1) & 3]) = v[k0].re;
+                *reinterpret_cast<float2*>(bim + 272 * k0 + off[(k0 >> 1) & 3]) = v[k0].im;
+            }
+        } else {
+            r16<INV>(v);
+            cp w1;
+            w1.re = *reinterpret_cast<const float2*>(tw + c);
+            w1.im = *reinterpret_cast<const float2*>(tw + 256 + c);
+            if (INV) w1.im = pneg(w1.im);
+            apply_twiddles<true>(v, w1);
+#pragma unroll
+            for (int s = 0; s < 16; s++) {
+                const int k0 = r16_k(s);
+                *reinterpret_cast<float2*>(bre + 272 * k0 + off[(k0 >> 1) & 3]) = v[s].re;
+                *reinterpret_cast<float2*>(bim + 272 * k0 + off[(k0 >> 1) & 3]) = v[s].im;
+            }
         }
     }
     __syncthreads();
@@ -249,9 +292,11 @@ fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, long long row
         fft16_dif<INV>(P);
         // slot j holds k2 = bitrev4(j); k = (rank*NSB + lsb) + R0*(k0 + 16*k1 + 256*k2)
         // (ROWS: k = (NSB*grp + lsb) + n1*(k0 + 16*k1 + 256*k2))
+        // (R1K: row = k0 & 3, k = (4*grp + row) + n1*((k0 >> 2) + 4*k1 + 64*k2))
         const int kst = ROWS ? n1 : R0;
-        const size_t klow = (ROWS ? (size_t)(NSB * grp + lsb) : (size_t)(rank * NSB + lsb)) + (size_t)kst * (size_t)(k0 + 16 * k1);
-        const size_t k2s = (size_t)256 * (size_t)kst;
+        const size_t klow = R1K ? (size_t)(4 * grp + (k0 & 3)) + (size_t)n1 * (size_t)((k0 >> 2) + 4 * k1)
+                                : (ROWS ? (size_t)(NSB * grp + lsb) : (size_t)(rank * NSB + lsb)) + (size_t)kst * (size_t)(k0 + 16 * k1);
+        const size_t k2s = R1K ? (size_t)64 * (size_t)n1 : (size_t)256 * (size_t)kst;
         if constexpr (MAG) {
             float* o = reinterpret_cast<float*>(out_) + seq * seq_len + klow;
 #pragma unroll
@@ -320,21 +365,24 @@ __global__ void __launch_bounds__(128) fftp_col16_kernel(const float2* __restric
 
 template <bool INV, bool SHIFT_IN>
 __global__ void __launch_bounds__(128, 5) fftp_col256_kernel(const float2* __restrict__ x, float2* __restrict__ tmp,
-                                                             const float4* __restrict__ tws) {
-    constexpr unsigned N = 256u * 4096u;
+                                                             const float4* __restrict__ tws, int log2n2) {
+    // n = 256 * N2 points per sequence, N2 = 2^log2n2 in {1024, 4096} = row length of the second pass
+    const unsigned N2 = 1u << log2n2;
+    const unsigned N = 256u * N2;
     __shared__ __align__(16) float sre[16 * 272];
     __shared__ __align__(16) float sim[16 * 272];
     const int t = threadIdx.x;
-    const size_t seq = blockIdx.x >> 8;
-    const unsigned c0 = (blockIdx.x & 255u) * 16u;     // 16 columns per CTA
+    const unsigned tiles = N2 >> 4;                    // 16 columns per CTA
+    const size_t seq = blockIdx.x / tiles;
+    const unsigned c0 = (blockIdx.x % tiles) * 16u;
     const int hi = t >> 3, j = 2 * (t & 7);
     cp v[16];
     {   // stage 1: radix 16 over n1 = 16a + b, b = hi
-        const float2* xs = x + seq * N + c0 + j + (size_t)hi * 4096;
+        const float2* xs = x + seq * N + c0 + j + (size_t)hi * N2;
 #pragma unroll
         for (int a = 0; a < 16; a++) {
             const int src = SHIFT_IN ? (a ^ 8) : a;
-            const float4 ab = __ldg(reinterpret_cast<const float4*>(xs + (size_t)src * (16 * 4096)));
+            const float4 ab = __ldg(reinterpret_cast<const float4*>(xs + (size_t)src * (16 * (size_t)N2)));
             v[a].re = make_float2(ab.x, ab.z);
             v[a].im = make_float2(ab.y, ab.w);
         }
@@ -378,13 +426,13 @@ __global__ void __launch_bounds__(128, 5) fftp_col256_kernel(const float2* __res
         B[1] = cmul(u2, u2);
         B[2] = cmul(B[1], B[1]);
         B[3] = cmul(B[2], B[1]);
-        float2* o = tmp + seq * N + (size_t)ka * 4096 + c0 + j;
+        float2* o = tmp + seq * N + (size_t)ka * N2 + c0 + j;
 #pragma unroll
         for (int s = 0; s < 16; s++) {
             const int kb = r16_k(s);
             const cp w = (kb >> 2) == 0 ? A[kb & 3] : cmul(A[kb & 3], B[kb >> 2]);
             const cp r = cmul(v[s], w);
-            *reinterpret_cast<float4*>(o + (size_t)kb * (16 * 4096)) = make_float4(r.re.x, r.im.x, r.re.y, r.im.y);
+            *reinterpret_cast<float4*>(o + (size_t)kb * (16 * (size_t)N2)) = make_float4(r.re.x, r.im.x, r.re.y, r.im.y);
         }
     }
 }
@@ -418,6 +466,10 @@ const float* fftp_twiddles() {
             h[1024 + 8192 * i + c] = (float)cosl(a);
             h[1024 + 8192 * i + 4096 + c] = (float)sinl(a);
         }
+    for (int c = 0; c < 256; c++) {
+        h[FP_TW_1K + c] = (float)cosl(-tau * c / 1024.0L);
+        h[FP_TW_1K + 256 + c] = (float)sinl(-tau * c / 1024.0L);
+    }
     for (int ka = 0; ka < 16; ka++)
         for (int b = 0; b < 16; b++) {
             const long double a = -tau * (long double)((ka * b) % 256) / 256.0L;
@@ -432,11 +484,11 @@ const float* fftp_twiddles() {
     return dev;
 }
 
-template <int R0, int CL, bool INV, bool SI, bool SO, bool MAG, bool ROWS = false>
+template <int R0, int CL, bool INV, bool SI, bool SO, bool MAG, bool ROWS = false, bool R1K = false>
 int fftp_launch(const void* in, void* out, size_t rows, float scale, cudaStream_t st, int n1 = 1) {
     constexpr int NSB = R0 / CL;
     const size_t smem = (size_t)2 * NSB * FP_B_OF(NSB) * sizeof(float);
-    auto kern = fftp_kernel<R0, CL, INV, SI, SO, MAG, ROWS>;
+    auto kern = fftp_kernel<R0, CL, INV, SI, SO, MAG, ROWS, R1K>;
     static bool configured = false;   // per instantiation
     if (!configured) {
         BDSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -461,7 +513,7 @@ int fftp_launch(const void* in, void* out, size_t rows, float scale, cudaStream_
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = CL > 1 ? 1 : 0;
+    cfg.numAttrs = (CL > 1 && !FP_DUP) ? 1 : 0;
     BDSP_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, reinterpret_cast<const float2*>(in), out, (long long)rows, scale, tw, n1));
     BDSP_LAUNCHED();
     return 0;
@@ -500,12 +552,22 @@ int fftp_colpass(const void* in, void* tmp, size_t n, size_t rows, cudaStream_t 
     if (n == 65536) {
         fftp_col16_kernel<INV, SI><<<(unsigned)(rows * 16), 128, 0, st>>>(reinterpret_cast<const float2*>(in), reinterpret_cast<float2*>(tmp));
     } else {
-        fftp_col256_kernel<INV, SI><<<(unsigned)(rows * 256), 128, 0, st>>>(reinterpret_cast<const float2*>(in), reinterpret_cast<float2*>(tmp),
-                                                                         reinterpret_cast<const float4*>(tw + FP_TW_SPLAT));
+        const int log2n2 = n == (1u << 18) ? 10 : 12;      // 2^18 = 256 x 1024, 2^20 = 256 x 4096
+        fftp_col256_kernel<INV, SI><<<(unsigned)(rows * ((size_t)1 << (log2n2 - 4))), 128, 0, st>>>(
+            reinterpret_cast<const float2*>(in), reinterpret_cast<float2*>(tmp), reinterpret_cast<const float4*>(tw + FP_TW_SPLAT), log2n2);
     }
     BDSP_CUDA_OK(cudaGetLastError());
     BDSP_LAUNCHED();
     return 0;
+}
+
+// last pass over 1024-point rows, four rows per 128-thread CTA
+int fftp_rows1k_pass(const void* tmp, void* out, size_t groups, bool inverse, bool so, bool magnitude, float sc, cudaStream_t st, int n1) {
+    if (inverse) return fftp_launch<1, 1, true, false, false, false, true, true>(tmp, out, groups, sc, st, n1);
+    if (magnitude) return so ? fftp_launch<1, 1, false, false, true, true, true, true>(tmp, out, groups, sc, st, n1)
+                             : fftp_launch<1, 1, false, false, false, true, true, true>(tmp, out, groups, sc, st, n1);
+    return so ? fftp_launch<1, 1, false, false, true, false, true, true>(tmp, out, groups, sc, st, n1)
+              : fftp_launch<1, 1, false, false, false, false, true, true>(tmp, out, groups, sc, st, n1);
 }
 }  // namespace
 
@@ -513,12 +575,13 @@ int fftp_colpass(const void* in, void* tmp, size_t n, size_t rows, cudaStream_t 
 // if out != in).  Returns 1 when the configuration is not covered.
 int fftp_two_pass_try(const void* in, void* out, void* tmp, size_t n, size_t rows, bool inverse, size_t in_rot, size_t out_rot,
                       double scale, bool magnitude, cudaStream_t st) {
-    if (n != 65536 && n != (1u << 20)) return 1;
+    if (n != 65536 && n != (1u << 18) && n != (1u << 20)) return 1;
     if ((in_rot != 0 && in_rot != n / 2) || (out_rot != 0 && out_rot != n / 2)) return 1;
     if (inverse && (magnitude || out_rot != 0)) return 1;
     if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 7) || (reinterpret_cast<uintptr_t>(tmp) & 15)) return 1;
     if (tmp == in || tmp == out) return 1;
-    const int n1 = (int)(n / 4096);
+    const bool r1k = n == (1u << 18);                    // 256 x 1024: four 1024-point rows per CTA in the last pass
+    const int n1 = (int)(n / (r1k ? 1024 : 4096));
     // rows per CTA in the last pass: 4 (one 512-thread CTA per SM, full 32-byte store sectors) or 2 (two 256-thread
     // CTAs per SM whose phases overlap; 16-byte half sectors that pair up in L2).  Measured on B200 (64 x 2^20):
     // 0.453 ms with 4 rows, 0.494 ms with 2, so 4 is the default; BDSP_FFTP_ROWS selects for A/B runs.
@@ -526,7 +589,8 @@ int fftp_two_pass_try(const void* in, void* out, void* tmp, size_t n, size_t row
         const char* e = getenv("BDSP_FFTP_ROWS");
         return (e && e[0] == '4') ? 4 : (e && e[0] == '2') ? 2 : FP_ROWS_DEFAULT;
     }();
-    const size_t groups = rows * (size_t)(n1 / rows_per_cta);
+    const int rpc = r1k ? 4 : rows_per_cta;
+    const size_t groups = rows * (size_t)(n1 / rpc);
     if (groups > 0x7fffffffull || rows * 256 > 0x7fffffffull) return 1;
     const bool si = in_rot != 0, so = out_rot != 0;
     const float sc = (float)scale;
@@ -546,16 +610,33 @@ int fftp_two_pass_try(const void* in, void* out, void* tmp, size_t n, size_t row
         const size_t nr = rows - r0 < chunk ? rows - r0 : chunk;
         const void* cin = reinterpret_cast<const char*>(in) + r0 * n * sizeof(float2);
         void* cout = reinterpret_cast<char*>(out) + r0 * n * out_elem;
-        const size_t groups_c = nr * (size_t)(n1 / rows_per_cta);
+        const size_t groups_c = nr * (size_t)(n1 / rpc);
         int rc;
         if (inverse) rc = si ? fftp_colpass<true, true>(cin, tmp, n, nr, st) : fftp_colpass<true, false>(cin, tmp, n, nr, st);
         else rc = si ? fftp_colpass<false, true>(cin, tmp, n, nr, st) : fftp_colpass<false, false>(cin, tmp, n, nr, st);
         if (rc) return rc;
-        if (rows_per_cta == 4) rc = fftp_rows_pass<4>(tmp, cout, groups_c, inverse, so, magnitude, sc, st, n1);
+        if (r1k) rc = fftp_rows1k_pass(tmp, cout, groups_c, inverse, so, magnitude, sc, st, n1);
+        else if (rows_per_cta == 4) rc = fftp_rows_pass<4>(tmp, cout, groups_c, inverse, so, magnitude, sc, st, n1);
         else rc = fftp_rows_pass<2>(tmp, cout, groups_c, inverse, so, magnitude, sc, st, n1);
         if (rc) return rc;
     }
     return 0;
+}
+
+
+// Last pass of a two-pass transform of n = n1 * 1024 points whose first pass (any kernel) left tmp[k1 * 1024 + n2]
+// (k1-th column transform, inter-pass twiddle applied): X[k1 + n1 * k2] = sum_n2 tmp[k1][n2] W_1024^{n2 k2}.
+// Returns 1 when the configuration is not covered.
+int fftp_rows1k_try(const void* tmp, void* out, size_t n, size_t rows, bool inverse, size_t out_rot, double scale, bool magnitude,
+                    cudaStream_t st) {
+    if (n < 4096 || (n & (n - 1)) || n > ((size_t)1 << 30)) return 1;
+    if (out_rot != 0 && out_rot != n / 2) return 1;
+    if (inverse && (magnitude || out_rot != 0)) return 1;
+    if ((reinterpret_cast<uintptr_t>(tmp) & 15) || (reinterpret_cast<uintptr_t>(out) & 7) || tmp == out) return 1;
+    const int n1 = (int)(n / 1024);
+    const size_t groups = rows * (size_t)(n1 / 4);
+    if (groups > 0x7fffffffull) return 1;
+    return fftp_rows1k_pass(tmp, out, groups, inverse, out_rot != 0, magnitude, (float)scale, st, n1);
 }
 
 // CTAs per sequence for n >= 8192: 1 = one persistent CTA per SM with register prefetch (default,

@@ -58,7 +58,7 @@ def test_fft_vector64_golden(kats):  # tests/time_freq_test.rs:45-120
 
 
 SIZES = [1, 2, 4, 8, 16, 32, 128, 256, 512, 1024, 2048, 4096, 8192, 16384,      # single CTA
-         1 << 15, 1 << 16, 1 << 18, 1 << 20, 1 << 21,                           # multi-pass
+         1 << 15, 1 << 16, 1 << 17, 1 << 18, 1 << 19, 1 << 20, 1 << 21, 1 << 22,                           # multi-pass
          3, 5, 6, 12, 24, 3 * 64, 5 * 1024, 7 * 4096, 3 * (1 << 16), 15 * (1 << 14),  # q * 2^k
          17 * 29, 1001, 9973, 10007 * 3, 127 * 127]                             # Bluestein
 
@@ -80,7 +80,7 @@ def test_plain_fft_sizes(n, dtype):
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-@pytest.mark.parametrize("n", [7, 8, 64, 1000, 1001, 4096, 65536, 3 * 4096, 1 << 17, 1 << 20])
+@pytest.mark.parametrize("n", [7, 8, 64, 1000, 1001, 4096, 65536, 3 * 4096, 1 << 17, 1 << 18, 1 << 20])
 def test_fft_ifft_shifted(n, dtype):
     rng = np.random.default_rng(100 + n)
     x = rand_c(rng, n, dtype)
@@ -121,7 +121,7 @@ def test_swap_halves(n):
 def test_fft_rows_batched():
     rng = np.random.default_rng(5)
     L = bd.lib()
-    for n, rows in [(16384, 8), (1024, 33), (64, 100), (1 << 15, 3), (1 << 16, 5), (1 << 20, 3)]:
+    for n, rows in [(16384, 8), (1024, 33), (64, 100), (1 << 15, 3), (1 << 16, 5), (1 << 18, 5), (1 << 20, 3)]:
         x = rand_c(rng, n * rows, np.float32)
         v = DspVec(x)
         out = DspVec.zeros(n * rows, dtype=np.float32)
@@ -133,7 +133,7 @@ def test_fft_rows_batched():
         assert o.rel_l2(got, ref) <= tol(n, np.float32)
 
 
-@pytest.mark.parametrize("n", [16384, 1 << 16, 1 << 20])
+@pytest.mark.parametrize("n", [16384, 1 << 16, 1 << 18, 1 << 20])
 def test_fft_magnitude_fused(n):
     rng = np.random.default_rng(6)
     x = rand_c(rng, n, np.float32)
@@ -142,7 +142,7 @@ def test_fft_magnitude_fused(n):
     assert o.rel_l2(got.to_numpy(), np.abs(o.fft(x))) <= tol(n, np.float32)
 
 
-@pytest.mark.parametrize("n", [1 << 16, 1 << 20])
+@pytest.mark.parametrize("n", [1 << 16, 1 << 18, 1 << 20])
 def test_two_pass_rows_plain_and_inverse(n):
     """packed two-pass path (fftp.cu): plain forward / inverse over several rows, unshifted."""
     rng = np.random.default_rng(n)
