@@ -39,7 +39,10 @@ __device__ __forceinline__ int fp_rot(int row, int g) { return (((g >> 1) + (row
 #define FP_TW_SPLAT (1024 + 2 * 8192)
 // [FP_TW_1K + c] Re W1024^c, [FP_TW_1K + 256 + c] Im, c in [0,256)
 #define FP_TW_1K (FP_TW_SPLAT + 1024)
-#define FP_TW_FLOATS (FP_TW_1K + 512)
+// same for W512^c and W2048^c
+#define FP_TW_512 (FP_TW_1K + 512)
+#define FP_TW_2K (FP_TW_512 + 512)
+#define FP_TW_FLOATS (FP_TW_2K + 512)
 
 // ROWS = true (R0 = 4, CL = 1): the CTA transforms FOUR independent, adjacent 4096-point rows (no F0) and
 // writes result k of row r to out[(r0 + r) + n1 * k]: the transposing last pass of a two-pass transform of
@@ -47,7 +50,10 @@ __device__ __forceinline__ int fp_rot(int row, int g) { return (((g >> 1) + (row
 // R1K = true (with ROWS, R0 = 1): the CTA's 4096 points are FOUR adjacent 1024-point rows (k0 = 4*q + row): the first
 // stage is a radix-4 butterfly inside every row, the other two stages are unchanged; 128 threads and 35 KB of shared
 // memory per CTA as for a plain 4096-point transform (which runs at the HBM roofline), stores fill 32-byte sectors.
-template <int R0, int CL, bool INV, bool SHIFT_IN, bool SHIFT_OUT, bool MAG, bool ROWS, bool R1K = false>
+// NATQ = Q in {2, 4, 8} (R0 = 1, no ROWS): the CTA's 4096 contiguous points are 16/Q independent rows of 256*Q points
+// (k0 = q + Q*row); the first stage is a radix-Q butterfly inside every row, results are stored in natural order.
+// Batched 512 / 1024 / 2048-point transforms with the structure of the 4096-point kernel.
+template <int R0, int CL, bool INV, bool SHIFT_IN, bool SHIFT_OUT, bool MAG, bool ROWS, bool R1K = false, int NATQ = 0>
 // FP_PREFETCH=1: persistent CTAs + register prefetch of the next row.  Measured on B200 (C3): 0.336 ms vs
 // 0.275 ms without (register pressure -> spills; the extra barrier), so it is off by default.
 #ifndef FP_PREFETCH
@@ -101,7 +107,7 @@ fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, long long row
     const size_t seq = ROWS ? (size_t)row / (size_t)(n1 / RPC) : (size_t)row;
     const int grp = ROWS ? (int)((size_t)row % (size_t)(n1 / RPC)) : 0;
     const size_t seq_len = ROWS ? (size_t)RLEN * (size_t)n1 : (size_t)N;
-    const float2* xr = x + seq * seq_len + (ROWS ? (size_t)grp * RPC * RLEN : 0);
+    const float2* xr = x + seq * seq_len + (ROWS ? (size_t)grp * RPC * RLEN : 0);   // NATQ: N = 4096 = one group of rows
 
     cp v[16];
     // ------------------------------------------------------------------ F0: radix-R0 over stride 4096
@@ -187,13 +193,45 @@ fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, long long row
 #pragma unroll
             for (int n2 = 0; n2 < 16; n2++) {
                 const int src = SHIFT_IN ? (n2 ^ 8) : n2;
-                const float2* gp = R1K ? xr + (n2 & 3) * 1024 + 256 * (n2 >> 2) + c : xr + (ROWS ? sb * 4096 : 0) + c + 256 * src;
+                const float2* gp = NATQ ? xr + (n2 / (NATQ ? NATQ : 1)) * (256 * NATQ) + 256 * ((n2 % (NATQ ? NATQ : 1)) ^ (SHIFT_IN ? NATQ / 2 : 0)) + c
+                                   : R1K ? xr + (n2 & 3) * 1024 + 256 * (n2 >> 2) + c : xr + (ROWS ? sb * 4096 : 0) + c + 256 * src;
                 const float4 ab = __ldg(reinterpret_cast<const float4*>(gp));
                 v[n2].re = make_float2(ab.x, ab.z);
                 v[n2].im = make_float2(ab.y, ab.w);
             }
         }
-        if constexpr (R1K) {
+        if constexpr (NATQ > 0) {
+            // radix Q inside each row (v[Q*row + q] -> v[Q*row + q']), then W_{256Q}^{c q'}
+            constexpr int TWO = NATQ == 2 ? FP_TW_512 : NATQ == 4 ? FP_TW_1K : FP_TW_2K;
+            cp w[8];
+            w[1].re = *reinterpret_cast<const float2*>(tw + TWO + c);
+            w[1].im = *reinterpret_cast<const float2*>(tw + TWO + 256 + c);
+            if (INV) w[1].im = pneg(w[1].im);
+            if constexpr (NATQ >= 4) { w[2] = cmul(w[1], w[1]); w[3] = cmul(w[2], w[1]); }
+            if constexpr (NATQ == 8) { w[4] = cmul(w[2], w[2]); w[5] = cmul(w[4], w[1]); w[6] = cmul(w[4], w[2]); w[7] = cmul(w[4], w[3]); }
+#pragma unroll
+            for (int r = 0; r < 16 / NATQ; r++) {
+                cp* u = v + NATQ * r;
+                if constexpr (NATQ == 2) { const cp a = cadd(u[0], u[1]), b = csub(u[0], u[1]); u[0] = a; u[1] = b; }
+                else if constexpr (NATQ == 4) r4<INV>(u[0], u[1], u[2], u[3]);
+                else {
+                    // 8-point DIF: a_j = x_j + x_{j+4}, b_j = (x_j - x_{j+4}) W8^j; X[2m] = DFT4(a)[m], X[2m+1] = DFT4(b)[m]
+                    cp a0 = cadd(u[0], u[4]), a1 = cadd(u[1], u[5]), a2 = cadd(u[2], u[6]), a3 = cadd(u[3], u[7]);
+                    cp b0 = csub(u[0], u[4]), b1 = mul_w16<2, INV>(csub(u[1], u[5])), b2 = mul_w16<4, INV>(csub(u[2], u[6])),
+                       b3 = mul_w16<6, INV>(csub(u[3], u[7]));
+                    r4<INV>(a0, a1, a2, a3);
+                    r4<INV>(b0, b1, b2, b3);
+                    u[0] = a0; u[2] = a1; u[4] = a2; u[6] = a3; u[1] = b0; u[3] = b1; u[5] = b2; u[7] = b3;
+                }
+#pragma unroll
+                for (int q = 1; q < NATQ; q++) u[q] = cmul(u[q], w[q]);
+            }
+#pragma unroll
+            for (int k0 = 0; k0 < 16; k0++) {
+                *reinterpret_cast<float2*>(bre + 272 * k0 + off[(k0 >> 1) & 3]) = v[k0].re;
+                *reinterpret_cast<float2*>(bim + 272 * k0 + off[(k0 >> 1) & 3]) = v[k0].im;
+            }
+        } else if constexpr (R1K) {
             // radix 4 inside each of the four rows (v[row + 4q] -> v[row + 4q']), then W_1024^{c q'}
             cp w1;
             w1.re = *reinterpret_cast<const float2*>(tw + FP_TW_1K + c);
@@ -294,9 +332,11 @@ fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, long long row
         // (ROWS: k = (NSB*grp + lsb) + n1*(k0 + 16*k1 + 256*k2))
         // (R1K: row = k0 & 3, k = (4*grp + row) + n1*((k0 >> 2) + 4*k1 + 64*k2))
         const int kst = ROWS ? n1 : R0;
-        const size_t klow = R1K ? (size_t)(4 * grp + (k0 & 3)) + (size_t)n1 * (size_t)((k0 >> 2) + 4 * k1)
+        // (NATQ: row = k0 / Q, k = row*256*Q + (k0 % Q) + Q*(k1 + 16*k2))
+        const size_t klow = NATQ ? (size_t)((k0 / (NATQ ? NATQ : 1)) * (256 * NATQ) + (k0 % (NATQ ? NATQ : 1)) + NATQ * k1)
+                            : R1K ? (size_t)(4 * grp + (k0 & 3)) + (size_t)n1 * (size_t)((k0 >> 2) + 4 * k1)
                                 : (ROWS ? (size_t)(NSB * grp + lsb) : (size_t)(rank * NSB + lsb)) + (size_t)kst * (size_t)(k0 + 16 * k1);
-        const size_t k2s = R1K ? (size_t)64 * (size_t)n1 : (size_t)256 * (size_t)kst;
+        const size_t k2s = NATQ ? (size_t)(16 * NATQ) : R1K ? (size_t)64 * (size_t)n1 : (size_t)256 * (size_t)kst;
         if constexpr (MAG) {
             float* o = reinterpret_cast<float*>(out_) + seq * seq_len + klow;
 #pragma unroll
@@ -469,6 +509,10 @@ const float* fftp_twiddles() {
     for (int c = 0; c < 256; c++) {
         h[FP_TW_1K + c] = (float)cosl(-tau * c / 1024.0L);
         h[FP_TW_1K + 256 + c] = (float)sinl(-tau * c / 1024.0L);
+        h[FP_TW_512 + c] = (float)cosl(-tau * c / 512.0L);
+        h[FP_TW_512 + 256 + c] = (float)sinl(-tau * c / 512.0L);
+        h[FP_TW_2K + c] = (float)cosl(-tau * c / 2048.0L);
+        h[FP_TW_2K + 256 + c] = (float)sinl(-tau * c / 2048.0L);
     }
     for (int ka = 0; ka < 16; ka++)
         for (int b = 0; b < 16; b++) {
@@ -484,11 +528,11 @@ const float* fftp_twiddles() {
     return dev;
 }
 
-template <int R0, int CL, bool INV, bool SI, bool SO, bool MAG, bool ROWS = false, bool R1K = false>
+template <int R0, int CL, bool INV, bool SI, bool SO, bool MAG, bool ROWS = false, bool R1K = false, int NATQ = 0>
 int fftp_launch(const void* in, void* out, size_t rows, float scale, cudaStream_t st, int n1 = 1) {
     constexpr int NSB = R0 / CL;
     const size_t smem = (size_t)2 * NSB * FP_B_OF(NSB) * sizeof(float);
-    auto kern = fftp_kernel<R0, CL, INV, SI, SO, MAG, ROWS, R1K>;
+    auto kern = fftp_kernel<R0, CL, INV, SI, SO, MAG, ROWS, R1K, NATQ>;
     static bool configured = false;   // per instantiation
     if (!configured) {
         BDSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -517,6 +561,19 @@ int fftp_launch(const void* in, void* out, size_t rows, float scale, cudaStream_
     BDSP_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, reinterpret_cast<const float2*>(in), out, (long long)rows, scale, tw, n1));
     BDSP_LAUNCHED();
     return 0;
+}
+
+template <int Q>
+int fftp_dispatch_nat(const void* in, void* out, size_t groups, bool inv, bool shift_in, bool shift_out, bool mag, float scale, cudaStream_t st) {
+    if (!inv) {
+        if (mag) return shift_out ? fftp_launch<1, 1, false, false, true, true, false, false, Q>(in, out, groups, scale, st)
+                                  : fftp_launch<1, 1, false, false, false, true, false, false, Q>(in, out, groups, scale, st);
+        return shift_out ? fftp_launch<1, 1, false, false, true, false, false, false, Q>(in, out, groups, scale, st)
+                         : fftp_launch<1, 1, false, false, false, false, false, false, Q>(in, out, groups, scale, st);
+    }
+    if (mag || shift_out) return 1;
+    return shift_in ? fftp_launch<1, 1, true, true, false, false, false, false, Q>(in, out, groups, scale, st)
+                    : fftp_launch<1, 1, true, false, false, false, false, false, Q>(in, out, groups, scale, st);
 }
 
 template <int R0, int CL>
@@ -653,8 +710,20 @@ static int fftp_cluster_mode() {
 // returns 0 on success, 1 when this configuration is not covered (caller uses the generic kernel)
 int fftp_try(const void* in, void* out, size_t n, size_t rows, bool inverse, size_t in_rot, size_t out_rot, double scale,
              bool magnitude, cudaStream_t st) {
-    if (n != 4096 && n != 8192 && n != 16384) return 1;
+    if (n != 512 && n != 1024 && n != 2048 && n != 4096 && n != 8192 && n != 16384) return 1;
     if ((in_rot != 0 && in_rot != n / 2) || (out_rot != 0 && out_rot != n / 2)) return 1;
+    if (n < 4096) {
+        // several rows per CTA: whole groups of 4096 points only (the caller handles other batch sizes generically)
+        const size_t per = 4096 / n;
+        if (rows % per != 0) return 1;
+        if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 7) || in == out) return 1;
+        const size_t groups = rows / per;
+        if (groups > 0x7fffffffull) return 1;
+        const bool si = in_rot != 0, so = out_rot != 0;
+        if (n == 512) return fftp_dispatch_nat<2>(in, out, groups, inverse, si, so, magnitude, (float)scale, st);
+        if (n == 1024) return fftp_dispatch_nat<4>(in, out, groups, inverse, si, so, magnitude, (float)scale, st);
+        return fftp_dispatch_nat<8>(in, out, groups, inverse, si, so, magnitude, (float)scale, st);
+    }
     if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 7)) return 1;
     if (in == out) return 1;   // rows are consumed while other CTAs may still read them only within a row; keep it simple
     if (rows * 2 > 0x7fffffffull) return 1;

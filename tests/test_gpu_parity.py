@@ -121,7 +121,8 @@ def test_swap_halves(n):
 def test_fft_rows_batched():
     rng = np.random.default_rng(5)
     L = bd.lib()
-    for n, rows in [(16384, 8), (1024, 33), (64, 100), (1 << 15, 3), (1 << 16, 5), (1 << 18, 5), (1 << 20, 3)]:
+    for n, rows in [(16384, 8), (1024, 33), (64, 100), (1 << 15, 3), (1 << 16, 5), (1 << 18, 5), (1 << 20, 3),
+                    (512, 64), (1024, 32), (2048, 6)]:
         x = rand_c(rng, n * rows, np.float32)
         v = DspVec(x)
         out = DspVec.zeros(n * rows, dtype=np.float32)
@@ -140,6 +141,26 @@ def test_fft_magnitude_fused(n):
     got = DspVec(x).fft_magnitude()
     assert not got.is_complex() and got.len() == n
     assert o.rel_l2(got.to_numpy(), np.abs(o.fft(x))) <= tol(n, np.float32)
+
+
+@pytest.mark.parametrize("n", [512, 1024, 2048, 4096, 8192])
+def test_small_row_batches_all_flag_combinations(n):
+    """several rows per CTA (fftp.cu NATQ modes) and the 4096 / 8192-point kernels: forward, shifted, inverse, ifft."""
+    rng = np.random.default_rng(n + 1)
+    L = bd.lib()
+    rows = 3 * (4096 // n if n < 4096 else 1) * 8
+    x = rand_c(rng, n * rows, np.float32)
+    v = DspVec(x)
+    out = DspVec.zeros(2 * n * rows, is_complex=True, dtype=np.float32)
+    pin, pout = v._fn("bdsp_device_ptr")(v._h), out._fn("bdsp_device_ptr")(out._h)
+    xr = x.reshape(rows, n).astype(np.complex128)
+    cases = [(0, np.fft.fft(xr, axis=1)),
+             (bd.F_SHIFT, np.fft.fftshift(np.fft.fft(xr, axis=1), axes=1)),
+             (bd.F_INVERSE, np.fft.ifft(xr, axis=1) * n),
+             (bd.F_INVERSE | bd.F_SHIFT, np.fft.ifft(np.fft.ifftshift(xr, axes=1), axis=1))]
+    for flags, ref in cases:
+        assert L.bdsp_fft_rows_c32(pin, pout, n, rows, flags) == 0
+        assert o.rel_l2(out.to_numpy().reshape(rows, n), ref) <= tol(n, np.float32), (n, flags)
 
 
 @pytest.mark.parametrize("n", [1 << 16, 1 << 18, 1 << 20])
