@@ -594,7 +594,7 @@ int fft_any(const void* in, void* out, size_t n, size_t batch, const FftOpts& o,
             size_t need = n * batch * sizeof(C);
             if (!w || work_bytes < need) w = workspace(need, 0);
         }
-        if (sizeof(T) == 4 && !o.real_input && (n == 65536 || n == (1u << 18) || n == (1u << 20))) {
+        if (sizeof(T) == 4 && !o.real_input && n >= (1u << 15) && n <= (1u << 20)) {
             // packed two-pass path (fftp.cu): 16 B/point of traffic per pass
             const int rc = fftp_two_pass_try(in, out, w, n, batch, INV, (size_t)in_rot, (size_t)om.rot, o.scale, o.magnitude != 0, st);
             if (rc <= 0) return rc;

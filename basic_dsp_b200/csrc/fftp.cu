@@ -47,13 +47,14 @@ __device__ __forceinline__ int fp_rot(int row, int g) { return (((g >> 1) + (row
 // ROWS = true (R0 = 4, CL = 1): the CTA transforms FOUR independent, adjacent 4096-point rows (no F0) and
 // writes result k of row r to out[(r0 + r) + n1 * k]: the transposing last pass of a two-pass transform of
 // n1 * 4096 points, with the four rows providing the contiguous 32 bytes of every store sector.
-// R1K = true (with ROWS, R0 = 1): the CTA's 4096 points are FOUR adjacent 1024-point rows (k0 = 4*q + row): the first
-// stage is a radix-4 butterfly inside every row, the other two stages are unchanged; 128 threads and 35 KB of shared
-// memory per CTA as for a plain 4096-point transform (which runs at the HBM roofline), stores fill 32-byte sectors.
+// TQ = Q in {2, 4} (with ROWS, R0 = 1): the CTA's 4096 points are 16/Q adjacent rows of 256*Q points (k0 = (16/Q)*q + row):
+// the first stage is a radix-Q butterfly inside every row, the other two stages are unchanged; 128 threads and 35 KB of
+// shared memory per CTA as for a plain 4096-point transform (which runs at the HBM roofline); the adjacent rows make
+// the transposing stores fill 32-byte (Q = 4) or 64-byte (Q = 2) runs.
 // NATQ = Q in {2, 4, 8} (R0 = 1, no ROWS): the CTA's 4096 contiguous points are 16/Q independent rows of 256*Q points
 // (k0 = q + Q*row); the first stage is a radix-Q butterfly inside every row, results are stored in natural order.
 // Batched 512 / 1024 / 2048-point transforms with the structure of the 4096-point kernel.
-template <int R0, int CL, bool INV, bool SHIFT_IN, bool SHIFT_OUT, bool MAG, bool ROWS, bool R1K = false, int NATQ = 0>
+template <int R0, int CL, bool INV, bool SHIFT_IN, bool SHIFT_OUT, bool MAG, bool ROWS, int TQ = 0, int NATQ = 0>
 // FP_PREFETCH=1: persistent CTAs + register prefetch of the next row.  Measured on B200 (C3): 0.336 ms vs
 // 0.275 ms without (register pressure -> spills; the extra barrier), so it is off by default.
 #ifndef FP_PREFETCH
@@ -102,8 +103,9 @@ fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, long long row
     }
     for (; row < rows; row += row_step) {
     // ROWS: `row` counts groups of NSB rows; groups_per_seq = n1 / NSB
-    constexpr int RPC = R1K ? 4 : NSB;            // rows per CTA (ROWS)
-    constexpr int RLEN = R1K ? 1024 : 4096;       // row length (ROWS)
+    constexpr bool R1K = TQ > 0;
+    constexpr int RPC = R1K ? 16 / TQ : NSB;      // rows per CTA (ROWS)
+    constexpr int RLEN = R1K ? 256 * TQ : 4096;   // row length (ROWS)
     const size_t seq = ROWS ? (size_t)row / (size_t)(n1 / RPC) : (size_t)row;
     const int grp = ROWS ? (int)((size_t)row % (size_t)(n1 / RPC)) : 0;
     const size_t seq_len = ROWS ? (size_t)RLEN * (size_t)n1 : (size_t)N;
@@ -194,7 +196,7 @@ fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, long long row
             for (int n2 = 0; n2 < 16; n2++) {
                 const int src = SHIFT_IN ? (n2 ^ 8) : n2;
                 const float2* gp = NATQ ? xr + (n2 / (NATQ ? NATQ : 1)) * (256 * NATQ) + 256 * ((n2 % (NATQ ? NATQ : 1)) ^ (SHIFT_IN ? NATQ / 2 : 0)) + c
-                                   : R1K ? xr + (n2 & 3) * 1024 + 256 * (n2 >> 2) + c : xr + (ROWS ? sb * 4096 : 0) + c + 256 * src;
+                                   : R1K ? xr + (n2 % RPC) * RLEN + 256 * (n2 / RPC) + c : xr + (ROWS ? sb * 4096 : 0) + c + 256 * src;
                 const float4 ab = __ldg(reinterpret_cast<const float4*>(gp));
                 v[n2].re = make_float2(ab.x, ab.z);
                 v[n2].im = make_float2(ab.y, ab.w);
@@ -232,18 +234,44 @@ fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, long long row
                 *reinterpret_cast<float2*>(bim + 272 * k0 + off[(k0 >> 1) & 3]) = v[k0].im;
             }
         } else if constexpr (R1K) {
-            // radix 4 inside each of the four rows (v[row + 4q] -> v[row + 4q']), then W_1024^{c q'}
-            cp w1;
-            w1.re = *reinterpret_cast<const float2*>(tw + FP_TW_1K + c);
-            w1.im = *reinterpret_cast<const float2*>(tw + FP_TW_1K + 256 + c);
-            if (INV) w1.im = pneg(w1.im);
-            const cp w2 = cmul(w1, w1), w3 = cmul(w2, w1);
+            // radix Q inside each row (v[row + RPC*q] -> v[row + RPC*q']), then W_{256Q}^{c q'}  (Q = 1: nothing to do)
+            if constexpr (TQ > 1) {
+                cp w1;
+                constexpr int TWO = TQ == 2 ? FP_TW_512 : TQ == 4 ? FP_TW_1K : FP_TW_2K;
+                w1.re = *reinterpret_cast<const float2*>(tw + TWO + c);
+                w1.im = *reinterpret_cast<const float2*>(tw + TWO + 256 + c);
+                if (INV) w1.im = pneg(w1.im);
+                if constexpr (TQ == 8) {
+                    cp w[8];
+                    w[1] = w1; w[2] = cmul(w1, w1); w[3] = cmul(w[2], w1); w[4] = cmul(w[2], w[2]);
+                    w[5] = cmul(w[4], w1); w[6] = cmul(w[4], w[2]); w[7] = cmul(w[4], w[3]);
 #pragma unroll
-            for (int r = 0; r < 4; r++) {
-                r4<INV>(v[r], v[r + 4], v[r + 8], v[r + 12]);
-                v[r + 4] = cmul(v[r + 4], w1);
-                v[r + 8] = cmul(v[r + 8], w2);
-                v[r + 12] = cmul(v[r + 12], w3);
+                    for (int r = 0; r < 2; r++) {   // row r holds v[r + 2q]
+                        cp a0 = cadd(v[r], v[r + 8]), a1 = cadd(v[r + 2], v[r + 10]), a2 = cadd(v[r + 4], v[r + 12]), a3 = cadd(v[r + 6], v[r + 14]);
+                        cp b0 = csub(v[r], v[r + 8]), b1 = mul_w16<2, INV>(csub(v[r + 2], v[r + 10])),
+                           b2 = mul_w16<4, INV>(csub(v[r + 4], v[r + 12])), b3 = mul_w16<6, INV>(csub(v[r + 6], v[r + 14]));
+                        r4<INV>(a0, a1, a2, a3);
+                        r4<INV>(b0, b1, b2, b3);
+                        v[r] = a0; v[r + 4] = cmul(a1, w[2]); v[r + 8] = cmul(a2, w[4]); v[r + 12] = cmul(a3, w[6]);
+                        v[r + 2] = cmul(b0, w[1]); v[r + 6] = cmul(b1, w[3]); v[r + 10] = cmul(b2, w[5]); v[r + 14] = cmul(b3, w[7]);
+                    }
+                } else if constexpr (TQ == 4) {
+                    const cp w2 = cmul(w1, w1), w3 = cmul(w2, w1);
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        r4<INV>(v[r], v[r + 4], v[r + 8], v[r + 12]);
+                        v[r + 4] = cmul(v[r + 4], w1);
+                        v[r + 8] = cmul(v[r + 8], w2);
+                        v[r + 12] = cmul(v[r + 12], w3);
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 8; r++) {
+                        const cp a = cadd(v[r], v[r + 8]), b = csub(v[r], v[r + 8]);
+                        v[r] = a;
+                        v[r + 8] = cmul(b, w1);
+                    }
+                }
             }
 #pragma unroll
             for (int k0 = 0; k0 < 16; k0++) {
@@ -330,13 +358,13 @@ fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, long long row
         fft16_dif<INV>(P);
         // slot j holds k2 = bitrev4(j); k = (rank*NSB + lsb) + R0*(k0 + 16*k1 + 256*k2)
         // (ROWS: k = (NSB*grp + lsb) + n1*(k0 + 16*k1 + 256*k2))
-        // (R1K: row = k0 & 3, k = (4*grp + row) + n1*((k0 >> 2) + 4*k1 + 64*k2))
+        // (TQ: row = k0 % RPC, k = (RPC*grp + row) + n1*((k0 / RPC) + Q*(k1 + 16*k2)))
         const int kst = ROWS ? n1 : R0;
         // (NATQ: row = k0 / Q, k = row*256*Q + (k0 % Q) + Q*(k1 + 16*k2))
         const size_t klow = NATQ ? (size_t)((k0 / (NATQ ? NATQ : 1)) * (256 * NATQ) + (k0 % (NATQ ? NATQ : 1)) + NATQ * k1)
-                            : R1K ? (size_t)(4 * grp + (k0 & 3)) + (size_t)n1 * (size_t)((k0 >> 2) + 4 * k1)
+                            : R1K ? (size_t)(RPC * grp + (k0 % RPC)) + (size_t)n1 * (size_t)((k0 / RPC) + TQ * k1)
                                 : (ROWS ? (size_t)(NSB * grp + lsb) : (size_t)(rank * NSB + lsb)) + (size_t)kst * (size_t)(k0 + 16 * k1);
-        const size_t k2s = NATQ ? (size_t)(16 * NATQ) : R1K ? (size_t)64 * (size_t)n1 : (size_t)256 * (size_t)kst;
+        const size_t k2s = NATQ ? (size_t)(16 * NATQ) : R1K ? (size_t)(16 * TQ) * (size_t)n1 : (size_t)256 * (size_t)kst;
         if constexpr (MAG) {
             float* o = reinterpret_cast<float*>(out_) + seq * seq_len + klow;
 #pragma unroll
@@ -381,17 +409,18 @@ __device__ __forceinline__ cp unit_root_pair(unsigned m0, unsigned m1, float two
 }
 
 template <bool INV, bool SHIFT_IN>
-__global__ void __launch_bounds__(128) fftp_col16_kernel(const float2* __restrict__ x, float2* __restrict__ tmp) {
-    constexpr unsigned N = 16u * 4096u;
+__global__ void __launch_bounds__(128) fftp_col16_kernel(const float2* __restrict__ x, float2* __restrict__ tmp, int log2n2) {
+    // n = 16 * N2 points per sequence, N2 = 2^log2n2 = row length of the second pass
+    const unsigned N2 = 1u << log2n2, N = 16u * N2;
     const unsigned pi = blockIdx.x * 128u + threadIdx.x;   // column pair over all sequences
-    const size_t seq = pi >> 11;
-    const unsigned c = 2u * (pi & 2047u);
+    const size_t seq = pi >> (log2n2 - 1);
+    const unsigned c = 2u * (pi & (N2 / 2 - 1));
     const float2* xs = x + seq * N + c;
     cp v[16];
 #pragma unroll
     for (int a = 0; a < 16; a++) {
         const int src = SHIFT_IN ? (a ^ 8) : a;
-        const float4 ab = __ldg(reinterpret_cast<const float4*>(xs + 4096 * src));
+        const float4 ab = __ldg(reinterpret_cast<const float4*>(xs + (size_t)N2 * src));
         v[a].re = make_float2(ab.x, ab.z);
         v[a].im = make_float2(ab.y, ab.w);
     }
@@ -400,7 +429,7 @@ __global__ void __launch_bounds__(128) fftp_col16_kernel(const float2* __restric
     float2* o = tmp + seq * N + c;
 #pragma unroll
     for (int s = 0; s < 16; s++)
-        *reinterpret_cast<float4*>(o + 4096 * r16_k(s)) = make_float4(v[s].re.x, v[s].im.x, v[s].re.y, v[s].im.y);
+        *reinterpret_cast<float4*>(o + (size_t)N2 * r16_k(s)) = make_float4(v[s].re.x, v[s].im.x, v[s].re.y, v[s].im.y);
 }
 
 template <bool INV, bool SHIFT_IN>
@@ -528,11 +557,11 @@ const float* fftp_twiddles() {
     return dev;
 }
 
-template <int R0, int CL, bool INV, bool SI, bool SO, bool MAG, bool ROWS = false, bool R1K = false, int NATQ = 0>
+template <int R0, int CL, bool INV, bool SI, bool SO, bool MAG, bool ROWS = false, int TQ = 0, int NATQ = 0>
 int fftp_launch(const void* in, void* out, size_t rows, float scale, cudaStream_t st, int n1 = 1) {
     constexpr int NSB = R0 / CL;
     const size_t smem = (size_t)2 * NSB * FP_B_OF(NSB) * sizeof(float);
-    auto kern = fftp_kernel<R0, CL, INV, SI, SO, MAG, ROWS, R1K, NATQ>;
+    auto kern = fftp_kernel<R0, CL, INV, SI, SO, MAG, ROWS, TQ, NATQ>;
     static bool configured = false;   // per instantiation
     if (!configured) {
         BDSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -566,14 +595,14 @@ int fftp_launch(const void* in, void* out, size_t rows, float scale, cudaStream_
 template <int Q>
 int fftp_dispatch_nat(const void* in, void* out, size_t groups, bool inv, bool shift_in, bool shift_out, bool mag, float scale, cudaStream_t st) {
     if (!inv) {
-        if (mag) return shift_out ? fftp_launch<1, 1, false, false, true, true, false, false, Q>(in, out, groups, scale, st)
-                                  : fftp_launch<1, 1, false, false, false, true, false, false, Q>(in, out, groups, scale, st);
-        return shift_out ? fftp_launch<1, 1, false, false, true, false, false, false, Q>(in, out, groups, scale, st)
-                         : fftp_launch<1, 1, false, false, false, false, false, false, Q>(in, out, groups, scale, st);
+        if (mag) return shift_out ? fftp_launch<1, 1, false, false, true, true, false, 0, Q>(in, out, groups, scale, st)
+                                  : fftp_launch<1, 1, false, false, false, true, false, 0, Q>(in, out, groups, scale, st);
+        return shift_out ? fftp_launch<1, 1, false, false, true, false, false, 0, Q>(in, out, groups, scale, st)
+                         : fftp_launch<1, 1, false, false, false, false, false, 0, Q>(in, out, groups, scale, st);
     }
     if (mag || shift_out) return 1;
-    return shift_in ? fftp_launch<1, 1, true, true, false, false, false, false, Q>(in, out, groups, scale, st)
-                    : fftp_launch<1, 1, true, false, false, false, false, false, Q>(in, out, groups, scale, st);
+    return shift_in ? fftp_launch<1, 1, true, true, false, false, false, 0, Q>(in, out, groups, scale, st)
+                    : fftp_launch<1, 1, true, false, false, false, false, 0, Q>(in, out, groups, scale, st);
 }
 
 template <int R0, int CL>
@@ -604,12 +633,12 @@ int fftp_rows_pass(const void* tmp, void* out, size_t groups, bool inverse, bool
 }
 
 template <bool INV, bool SI>
-int fftp_colpass(const void* in, void* tmp, size_t n, size_t rows, cudaStream_t st) {
+int fftp_colpass(const void* in, void* tmp, int n1, int log2n2, size_t rows, cudaStream_t st) {
     const float* tw = fftp_twiddles();
-    if (n == 65536) {
-        fftp_col16_kernel<INV, SI><<<(unsigned)(rows * 16), 128, 0, st>>>(reinterpret_cast<const float2*>(in), reinterpret_cast<float2*>(tmp));
+    if (n1 == 16) {
+        fftp_col16_kernel<INV, SI><<<(unsigned)(rows * ((size_t)1 << (log2n2 - 8))), 128, 0, st>>>(
+            reinterpret_cast<const float2*>(in), reinterpret_cast<float2*>(tmp), log2n2);
     } else {
-        const int log2n2 = n == (1u << 18) ? 10 : 12;      // 2^18 = 256 x 1024, 2^20 = 256 x 4096
         fftp_col256_kernel<INV, SI><<<(unsigned)(rows * ((size_t)1 << (log2n2 - 4))), 128, 0, st>>>(
             reinterpret_cast<const float2*>(in), reinterpret_cast<float2*>(tmp), reinterpret_cast<const float4*>(tw + FP_TW_SPLAT), log2n2);
     }
@@ -618,13 +647,14 @@ int fftp_colpass(const void* in, void* tmp, size_t n, size_t rows, cudaStream_t 
     return 0;
 }
 
-// last pass over 1024-point rows, four rows per 128-thread CTA
-int fftp_rows1k_pass(const void* tmp, void* out, size_t groups, bool inverse, bool so, bool magnitude, float sc, cudaStream_t st, int n1) {
-    if (inverse) return fftp_launch<1, 1, true, false, false, false, true, true>(tmp, out, groups, sc, st, n1);
-    if (magnitude) return so ? fftp_launch<1, 1, false, false, true, true, true, true>(tmp, out, groups, sc, st, n1)
-                             : fftp_launch<1, 1, false, false, false, true, true, true>(tmp, out, groups, sc, st, n1);
-    return so ? fftp_launch<1, 1, false, false, true, false, true, true>(tmp, out, groups, sc, st, n1)
-              : fftp_launch<1, 1, false, false, false, false, true, true>(tmp, out, groups, sc, st, n1);
+// last pass over rows of 256*Q points, 16/Q adjacent rows per 128-thread CTA
+template <int Q>
+int fftp_rowsq_pass(const void* tmp, void* out, size_t groups, bool inverse, bool so, bool magnitude, float sc, cudaStream_t st, int n1) {
+    if (inverse) return fftp_launch<1, 1, true, false, false, false, true, Q>(tmp, out, groups, sc, st, n1);
+    if (magnitude) return so ? fftp_launch<1, 1, false, false, true, true, true, Q>(tmp, out, groups, sc, st, n1)
+                             : fftp_launch<1, 1, false, false, false, true, true, Q>(tmp, out, groups, sc, st, n1);
+    return so ? fftp_launch<1, 1, false, false, true, false, true, Q>(tmp, out, groups, sc, st, n1)
+              : fftp_launch<1, 1, false, false, false, false, true, Q>(tmp, out, groups, sc, st, n1);
 }
 }  // namespace
 
@@ -632,23 +662,36 @@ int fftp_rows1k_pass(const void* tmp, void* out, size_t groups, bool inverse, bo
 // if out != in).  Returns 1 when the configuration is not covered.
 int fftp_two_pass_try(const void* in, void* out, void* tmp, size_t n, size_t rows, bool inverse, size_t in_rot, size_t out_rot,
                       double scale, bool magnitude, cudaStream_t st) {
-    if (n != 65536 && n != (1u << 18) && n != (1u << 20)) return 1;
+    // n = n1 * N2:  2^15 = 16 x 2048, 2^16 = 256 x 256, 2^17 = 256 x 512, 2^18 = 256 x 1024, 2^19 = 256 x 2048, 2^20 = 256 x 4096.
+    // Last pass: 16/Q adjacent rows of N2 = 256*Q points per 128-thread CTA (Q = N2/256 <= 8), or four 4096-point rows per
+    // 512-thread CTA.  BDSP_FFTP_2_16=16 selects the 16 x 4096 split for 2^16 (A/B runs).
+    int n1, log2n2;
+    switch (n) {
+    case 1u << 15: n1 = 16; log2n2 = 11; break;
+    case 1u << 16: n1 = 256; log2n2 = 8; break;
+    case 1u << 17: n1 = 256; log2n2 = 9; break;
+    case 1u << 18: n1 = 256; log2n2 = 10; break;
+    case 1u << 19: n1 = 256; log2n2 = 11; break;
+    case 1u << 20: n1 = 256; log2n2 = 12; break;
+    default: return 1;
+    }
+    static const bool split16 = [] { const char* e = getenv("BDSP_FFTP_2_16"); return e && e[0] == '1'; }();
+    if (n == (1u << 16) && split16) { n1 = 16; log2n2 = 12; }
     if ((in_rot != 0 && in_rot != n / 2) || (out_rot != 0 && out_rot != n / 2)) return 1;
     if (inverse && (magnitude || out_rot != 0)) return 1;
     if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 7) || (reinterpret_cast<uintptr_t>(tmp) & 15)) return 1;
     if (tmp == in || tmp == out) return 1;
-    const bool r1k = n == (1u << 18);                    // 256 x 1024: four 1024-point rows per CTA in the last pass
-    const int n1 = (int)(n / (r1k ? 1024 : 4096));
-    // rows per CTA in the last pass: 4 (one 512-thread CTA per SM, full 32-byte store sectors) or 2 (two 256-thread
+    const int tq = log2n2 < 12 ? 1 << (log2n2 - 8) : 0;
+    // rows per CTA in the 4096-point last pass: 4 (one 512-thread CTA per SM, full 32-byte store sectors) or 2 (two 256-thread
     // CTAs per SM whose phases overlap; 16-byte half sectors that pair up in L2).  Measured on B200 (64 x 2^20):
     // 0.453 ms with 4 rows, 0.494 ms with 2, so 4 is the default; BDSP_FFTP_ROWS selects for A/B runs.
     static const int rows_per_cta = [] {
         const char* e = getenv("BDSP_FFTP_ROWS");
         return (e && e[0] == '4') ? 4 : (e && e[0] == '2') ? 2 : FP_ROWS_DEFAULT;
     }();
-    const int rpc = r1k ? 4 : rows_per_cta;
+    const int rpc = tq ? 16 / tq : rows_per_cta;
     const size_t groups = rows * (size_t)(n1 / rpc);
-    if (groups > 0x7fffffffull || rows * 256 > 0x7fffffffull) return 1;
+    if (groups > 0x7fffffffull || rows * 4096 > 0x7fffffffull) return 1;
     const bool si = in_rot != 0, so = out_rot != 0;
     const float sc = (float)scale;
     // BDSP_FFTP_CHUNK_MB=<m> processes the sequences in chunks whose intermediate (8 bytes per point) is <= m MB so
@@ -669,17 +712,19 @@ int fftp_two_pass_try(const void* in, void* out, void* tmp, size_t n, size_t row
         void* cout = reinterpret_cast<char*>(out) + r0 * n * out_elem;
         const size_t groups_c = nr * (size_t)(n1 / rpc);
         int rc;
-        if (inverse) rc = si ? fftp_colpass<true, true>(cin, tmp, n, nr, st) : fftp_colpass<true, false>(cin, tmp, n, nr, st);
-        else rc = si ? fftp_colpass<false, true>(cin, tmp, n, nr, st) : fftp_colpass<false, false>(cin, tmp, n, nr, st);
+        if (inverse) rc = si ? fftp_colpass<true, true>(cin, tmp, n1, log2n2, nr, st) : fftp_colpass<true, false>(cin, tmp, n1, log2n2, nr, st);
+        else rc = si ? fftp_colpass<false, true>(cin, tmp, n1, log2n2, nr, st) : fftp_colpass<false, false>(cin, tmp, n1, log2n2, nr, st);
         if (rc) return rc;
-        if (r1k) rc = fftp_rows1k_pass(tmp, cout, groups_c, inverse, so, magnitude, sc, st, n1);
+        if (tq == 8) rc = fftp_rowsq_pass<8>(tmp, cout, groups_c, inverse, so, magnitude, sc, st, n1);
+        else if (tq == 4) rc = fftp_rowsq_pass<4>(tmp, cout, groups_c, inverse, so, magnitude, sc, st, n1);
+        else if (tq == 2) rc = fftp_rowsq_pass<2>(tmp, cout, groups_c, inverse, so, magnitude, sc, st, n1);
+        else if (tq == 1) rc = fftp_rowsq_pass<1>(tmp, cout, groups_c, inverse, so, magnitude, sc, st, n1);
         else if (rows_per_cta == 4) rc = fftp_rows_pass<4>(tmp, cout, groups_c, inverse, so, magnitude, sc, st, n1);
         else rc = fftp_rows_pass<2>(tmp, cout, groups_c, inverse, so, magnitude, sc, st, n1);
         if (rc) return rc;
     }
     return 0;
 }
-
 
 // Last pass of a two-pass transform of n = n1 * 1024 points whose first pass (any kernel) left tmp[k1 * 1024 + n2]
 // (k1-th column transform, inter-pass twiddle applied): X[k1 + n1 * k2] = sum_n2 tmp[k1][n2] W_1024^{n2 k2}.
@@ -693,7 +738,7 @@ int fftp_rows1k_try(const void* tmp, void* out, size_t n, size_t rows, bool inve
     const int n1 = (int)(n / 1024);
     const size_t groups = rows * (size_t)(n1 / 4);
     if (groups > 0x7fffffffull) return 1;
-    return fftp_rows1k_pass(tmp, out, groups, inverse, out_rot != 0, magnitude, (float)scale, st, n1);
+    return fftp_rowsq_pass<4>(tmp, out, groups, inverse, out_rot != 0, magnitude, (float)scale, st, n1);
 }
 
 // CTAs per sequence for n >= 8192: 1 = one persistent CTA per SM with register prefetch (default,

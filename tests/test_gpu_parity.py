@@ -80,7 +80,7 @@ def test_plain_fft_sizes(n, dtype):
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-@pytest.mark.parametrize("n", [7, 8, 64, 1000, 1001, 4096, 65536, 3 * 4096, 1 << 17, 1 << 18, 1 << 20])
+@pytest.mark.parametrize("n", [7, 8, 64, 1000, 1001, 4096, 1 << 15, 65536, 3 * 4096, 1 << 17, 1 << 18, 1 << 19, 1 << 20])
 def test_fft_ifft_shifted(n, dtype):
     rng = np.random.default_rng(100 + n)
     x = rand_c(rng, n, dtype)
@@ -121,7 +121,7 @@ def test_swap_halves(n):
 def test_fft_rows_batched():
     rng = np.random.default_rng(5)
     L = bd.lib()
-    for n, rows in [(16384, 8), (1024, 33), (64, 100), (1 << 15, 3), (1 << 16, 5), (1 << 18, 5), (1 << 20, 3),
+    for n, rows in [(16384, 8), (1024, 33), (64, 100), (1 << 15, 3), (1 << 16, 5), (1 << 17, 3), (1 << 18, 5), (1 << 19, 3), (1 << 20, 3),
                     (512, 64), (1024, 32), (2048, 6)]:
         x = rand_c(rng, n * rows, np.float32)
         v = DspVec(x)
@@ -134,7 +134,7 @@ def test_fft_rows_batched():
         assert o.rel_l2(got, ref) <= tol(n, np.float32)
 
 
-@pytest.mark.parametrize("n", [16384, 1 << 16, 1 << 18, 1 << 20])
+@pytest.mark.parametrize("n", [16384, 1 << 15, 1 << 16, 1 << 17, 1 << 18, 1 << 19, 1 << 20])
 def test_fft_magnitude_fused(n):
     rng = np.random.default_rng(6)
     x = rand_c(rng, n, np.float32)
@@ -163,7 +163,7 @@ def test_small_row_batches_all_flag_combinations(n):
         assert o.rel_l2(out.to_numpy().reshape(rows, n), ref) <= tol(n, np.float32), (n, flags)
 
 
-@pytest.mark.parametrize("n", [1 << 16, 1 << 18, 1 << 20])
+@pytest.mark.parametrize("n", [1 << 15, 1 << 16, 1 << 17, 1 << 18, 1 << 19, 1 << 20])
 def test_two_pass_rows_plain_and_inverse(n):
     """packed two-pass path (fftp.cu): plain forward / inverse over several rows, unshifted."""
     rng = np.random.default_rng(n)
