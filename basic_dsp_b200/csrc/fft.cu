@@ -122,8 +122,11 @@ __device__ __forceinline__ int spad_host_dev(int n) { return n + (n >> 4) + 1; }
 // ------------------------------------------------------------------------------------------
 // single-CTA kernel: nfft sequences of n = 2^log2n points per CTA
 // ------------------------------------------------------------------------------------------
+#ifndef BDSP_TILE_F64_RADIX8
+#define BDSP_TILE_F64_RADIX8 1
+#endif
 template <typename T, bool INV, bool REAL_IN, bool MAG>
-__global__ void __launch_bounds__(sizeof(T) == 4 ? 1024 : 512) fft_block_kernel(const void* __restrict__ in_, void* __restrict__ out_, int log2n, int nfft,
+__global__ void __launch_bounds__(sizeof(T) == 4 ? 1024 : 1024, 1) fft_block_kernel(const void* __restrict__ in_, void* __restrict__ out_, int log2n, int nfft,
                                  long long batch, long long in_rot, T scale, OutMap om,
                                  const typename CpxOf<T>::type* __restrict__ tw) {
     typedef typename CpxOf<T>::type C;
@@ -132,20 +135,45 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? 1024 : 512) fft_block_kernel(
     const int n = 1 << log2n;
     const int total = n * nfft;
     const long long seq0 = (long long)blockIdx.x * nfft;
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        int f = idx >> log2n, p = idx & (n - 1);
-        long long seq = seq0 + f;
-        C v = mk<T>(0, 0);
-        if (seq < batch) {
-            long long src = (p + in_rot) & (n - 1);
-            if (REAL_IN) v.x = reinterpret_cast<const T*>(in_)[seq * n + src];
-            else v = reinterpret_cast<const C*>(in_)[seq * n + src];
-            v.x *= scale; v.y *= scale;
+    {   // UN independent global loads are issued before the first use (the loop is latency-bound otherwise)
+        constexpr int UN = 8;
+        for (int base = threadIdx.x; base < total; base += blockDim.x * UN) {
+            C v[UN];
+#pragma unroll
+            for (int u = 0; u < UN; u++) {
+                const int idx = base + u * blockDim.x;
+                v[u] = mk<T>(0, 0);
+                if (idx < total) {
+                    const int f = idx >> log2n, p = idx & (n - 1);
+                    const long long seq = seq0 + f;
+                    if (seq < batch) {
+                        const long long src = (p + in_rot) & (n - 1);
+                        if (REAL_IN) v[u].x = reinterpret_cast<const T*>(in_)[seq * n + src];
+                        else v[u] = reinterpret_cast<const C*>(in_)[seq * n + src];
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UN; u++) {
+                const int idx = base + u * blockDim.x;
+                if (idx < total) {
+                    v[u].x *= scale; v[u].y *= scale;
+                    s[spad(idx)] = v[u];
+                }
+            }
         }
-        s[spad(idx)] = v;
     }
     __syncthreads();
-    block_fft<T, INV>(s, log2n, nfft, tw);
+    if constexpr (sizeof(T) == 8 && BDSP_TILE_F64_RADIX8) {
+        // f64: radix-8 stages, 8 points per thread (see fft_tile_kernel)
+        int Ns = 1, rem = log2n;
+        while (rem >= 3) { stockham_stage_strided<T, 8, INV, 1>(s, n, nfft, n, Ns, tw); Ns <<= 3; rem -= 3; }
+        if (rem == 2) stockham_stage_strided<T, 4, INV, 2>(s, n, nfft, n, Ns, tw);
+        else if (rem == 1) stockham_stage_strided<T, 2, INV, 4>(s, n, nfft, n, Ns, tw);
+    } else {
+        block_fft<T, INV>(s, log2n, nfft, tw);
+    }
+#pragma unroll 4
     for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
         int f = idx >> log2n, k = idx & (n - 1);
         long long seq = seq0 + f;
@@ -178,9 +206,6 @@ struct TileParams {
     OutMap om;
 };
 
-#ifndef BDSP_TILE_F64_RADIX8
-#define BDSP_TILE_F64_RADIX8 1
-#endif
 template <typename T, bool INV>
 __global__ void __launch_bounds__(sizeof(T) == 4 ? 1024 : 512, (sizeof(T) == 8 && BDSP_TILE_F64_RADIX8) ? 2 : 1) fft_tile_kernel(TileParams p, T scale, const typename CpxOf<T>::type* __restrict__ tw) {
     typedef typename CpxOf<T>::type C;
@@ -453,7 +478,8 @@ int launch_block(const void* in, void* out, size_t n, size_t batch, bool real_in
     int nfft = (int)(4096 / n);
     if (nfft < 1) nfft = 1;
     if ((size_t)nfft > batch) nfft = (int)batch;
-    const int threads = block_fft_threads((int)n, nfft);
+    int threads = block_fft_threads((int)n, nfft);
+    if (sizeof(T) == 8 && BDSP_TILE_F64_RADIX8) { threads = ((int)n * nfft / 8 + 31) / 32 * 32; if (threads < 32) threads = 32; }
     const size_t smem = spad_host(n * nfft) * sizeof(C);
     const long long grid = ((long long)batch + nfft - 1) / nfft;
     const C* tw = twiddle_table<T>();
