@@ -1548,13 +1548,18 @@ extern "C" int32_t bdsp_device_count(void) {
 }
 extern "C" int32_t bdsp_set_device(int32_t device) { BDSP_CUDA_OK(cudaSetDevice(device)); return 0; }
 extern "C" int32_t bdsp_sync(void) { BDSP_CUDA_OK(cudaStreamSynchronize(g_stream)); return 0; }
-extern "C" void bdsp_set_stream(void* s) { g_stream = reinterpret_cast<cudaStream_t>(s); }
+extern "C" void bdsp_set_stream(void* s) { g_stream = reinterpret_cast<cudaStream_t>(s); workspace_bind_stream(g_stream); }
 extern "C" void* bdsp_stream_create(void) {
     cudaStream_t s = nullptr;
     if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
     return s;
 }
-extern "C" void bdsp_stream_destroy(void* s) { if (s) cudaStreamDestroy(reinterpret_cast<cudaStream_t>(s)); }
+extern "C" void bdsp_stream_destroy(void* s) {
+    if (!s) return;
+    cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(s));
+    workspace_release_stream(reinterpret_cast<cudaStream_t>(s));
+    cudaStreamDestroy(reinterpret_cast<cudaStream_t>(s));
+}
 extern "C" int32_t bdsp_stream_sync(void* s) { BDSP_CUDA_OK(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(s))); return 0; }
 
 extern "C" int32_t bdsp_fft_rows_c32(const void* in, void* out, size_t points, size_t rows, int32_t flags) { return fft_rows<float>(in, out, points, rows, flags); }

@@ -36,8 +36,6 @@ namespace {
 struct DeviceState {
     float2* tw32 = nullptr;
     double2* tw64 = nullptr;
-    void* ws[4] = {nullptr, nullptr, nullptr, nullptr};
-    size_t ws_bytes[4] = {0, 0, 0, 0};
     int sms = 0;
 };
 std::mutex g_mu;
@@ -77,19 +75,41 @@ int sm_count() { return dev_state().sms; }
 template <> const float2* twiddle_table<float>() { return dev_state().tw32; }
 template <> const double2* twiddle_table<double>() { return dev_state().tw64; }
 
-void* workspace(size_t bytes, int slot) {
-    DeviceState& s = dev_state();
+// Workspaces are kept per (device, stream): work queued on different streams may run concurrently, so it must not
+// share scratch buffers.  The calling thread binds its stream with workspace_bind_stream (capi: bdsp_set_stream).
+namespace {
+thread_local cudaStream_t tl_ws_stream = nullptr;
+struct WsSet { void* p[4] = {nullptr, nullptr, nullptr, nullptr}; size_t bytes[4] = {0, 0, 0, 0}; };
+std::map<std::pair<int, cudaStream_t>, WsSet> g_ws;
+}  // namespace
+
+void workspace_bind_stream(cudaStream_t st) { tl_ws_stream = st; }
+
+void workspace_release_stream(cudaStream_t st) {
     std::lock_guard<std::mutex> lk(g_mu);
-    if (s.ws_bytes[slot] < bytes) {
-        if (s.ws[slot]) {
-            BDSP_CUDA_ABORT(cudaDeviceSynchronize());
-            BDSP_CUDA_ABORT(cudaFree(s.ws[slot]));
+    for (auto it = g_ws.begin(); it != g_ws.end();) {
+        if (it->first.second == st) {
+            for (int i = 0; i < 4; i++) if (it->second.p[i]) cudaFree(it->second.p[i]);
+            it = g_ws.erase(it);
+        } else ++it;
+    }
+}
+
+void* workspace(size_t bytes, int slot) {
+    int d = 0;
+    BDSP_CUDA_ABORT(cudaGetDevice(&d));
+    std::lock_guard<std::mutex> lk(g_mu);
+    WsSet& s = g_ws[std::make_pair(d, tl_ws_stream)];
+    if (s.bytes[slot] < bytes) {
+        if (s.p[slot]) {
+            BDSP_CUDA_ABORT(cudaStreamSynchronize(tl_ws_stream));
+            BDSP_CUDA_ABORT(cudaFree(s.p[slot]));
         }
         size_t want = bytes + bytes / 8;
-        BDSP_CUDA_ABORT(cudaMalloc(&s.ws[slot], want));
-        s.ws_bytes[slot] = want;
+        BDSP_CUDA_ABORT(cudaMalloc(&s.p[slot], want));
+        s.bytes[slot] = want;
     }
-    return s.ws[slot];
+    return s.p[slot];
 }
 
 template <> size_t fft_block_max_n<float>() { return 16384; }

@@ -29,5 +29,7 @@ template <typename T> const typename CpxOf<T>::type* twiddle_table();
 
 // grow-only per-device workspace (device memory); not thread safe across host threads sharing a device
 void* workspace(size_t bytes, int slot);
+void workspace_bind_stream(cudaStream_t st);
+void workspace_release_stream(cudaStream_t st);
 
 }  // namespace bdsp

@@ -706,3 +706,26 @@ def test_multiply_complex_exponential(dtype):  # complex_ops.rs:81-105
     x = rand_c(rng, 5000, dtype)
     got = DspVec(x, delta=0.5).multiply_complex_exponential(0.01, 0.3).to_numpy()
     assert o.rel_l2(got, o.multiply_complex_exponential(x, 0.01, 0.3, dtype, delta=0.5)) <= 1e-6 if dtype == np.float32 else 1e-14
+
+
+def test_streams_do_not_share_workspace():
+    """Calls queued on different streams may overlap on the device: their scratch buffers must be distinct."""
+    rng = np.random.default_rng(99)
+    L = bd.lib()
+    n = 1 << 18
+    xs = [rand_c(rng, n, np.float32) for _ in range(3)]
+    streams = [L.bdsp_stream_create() for _ in xs]
+    vecs = [DspVec(x) for x in xs]
+    for _ in range(3):                       # several rounds in flight on every stream before anything is synchronised
+        for st, v in zip(streams, vecs):
+            L.bdsp_set_stream(st)
+            v.plain_fft()
+            v.plain_ifft()
+            v.scale(1.0 / n)
+    for st in streams:
+        L.bdsp_stream_sync(st)
+    L.bdsp_set_stream(None)
+    for v, x in zip(vecs, xs):
+        assert o.rel_l2(v.to_numpy(), x) <= 8 * tol(n, np.float32)
+    for st in streams:
+        L.bdsp_stream_destroy(st)
