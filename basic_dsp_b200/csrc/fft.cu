@@ -24,6 +24,8 @@ namespace bdsp {
 
 int fftp_rows1k_try(const void* tmp, void* out, size_t n, size_t rows, bool inverse, size_t out_rot, double scale, bool magnitude,
                     cudaStream_t st);
+int fftp_three_pass_try(const void* in, void* out, void* tmp, size_t n, size_t rows, bool inverse, size_t in_rot, size_t out_rot,
+                        double scale, bool magnitude, cudaStream_t st);
 int fftp_two_pass_try(const void* in, void* out, void* tmp, size_t n, size_t rows, bool inverse, size_t in_rot, size_t out_rot,
                       double scale, bool magnitude, cudaStream_t st);
 int fftp_try(const void* in, void* out, size_t n, size_t rows, bool inverse, size_t in_rot, size_t out_rot, double scale,
@@ -643,6 +645,11 @@ int fft_any(const void* in, void* out, size_t n, size_t batch, const FftOpts& o,
         if (sizeof(T) == 4 && !o.real_input && n >= (1u << 15) && n <= (1u << 20)) {
             // packed two-pass path (fftp.cu): 16 B/point of traffic per pass
             const int rc = fftp_two_pass_try(in, out, w, n, batch, INV, (size_t)in_rot, (size_t)om.rot, o.scale, o.magnitude != 0, st);
+            if (rc <= 0) return rc;
+        }
+        if (sizeof(T) == 4 && !o.real_input && n >= (1u << 21) && n <= (1u << 24)) {
+            // packed three-pass path (fftp.cu)
+            const int rc = fftp_three_pass_try(in, out, w, n, batch, INV, (size_t)in_rot, (size_t)om.rot, o.scale, o.magnitude != 0, st);
             if (rc <= 0) return rc;
         }
         return fft_pow2<T, INV>(in, out, n, batch, o.real_input, o.magnitude, in_rot, scale, om, w, st);

@@ -67,7 +67,7 @@ template <int R0, int CL, bool INV, bool SHIFT_IN, bool SHIFT_OUT, bool MAG, boo
 #define FP_DUP 1
 #endif
 __global__ void __launch_bounds__(128 * (R0 / CL), (R0 / CL) == 2 ? FP_MINB256 : 4 / (R0 / CL))
-fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, long long rows, float scale, const float* __restrict__ tw, int n1) {
+fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, long long rows, float scale, const float* __restrict__ tw, int n1, int n2c) {
     constexpr int NSB = R0 / CL;          // sub-blocks (4096-point transforms) owned by this CTA
     constexpr int NT = 128 * NSB;         // threads
     constexpr int N = 4096 * R0;
@@ -106,10 +106,17 @@ fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, long long row
     constexpr bool R1K = TQ > 0;
     constexpr int RPC = R1K ? 16 / TQ : NSB;      // rows per CTA (ROWS)
     constexpr int RLEN = R1K ? 256 * TQ : 4096;   // row length (ROWS)
-    const size_t seq = ROWS ? (size_t)row / (size_t)(n1 / RPC) : (size_t)row;
-    const int grp = ROWS ? (int)((size_t)row % (size_t)(n1 / RPC)) : 0;
-    const size_t seq_len = ROWS ? (size_t)RLEN * (size_t)n1 : (size_t)N;
-    const float2* xr = x + seq * seq_len + (ROWS ? (size_t)grp * RPC * RLEN : 0);   // NATQ: N = 4096 = one group of rows
+    // ROWS: the sequence has n1 * n2c rows of RLEN points; row (k1, k2o) sits at tmp[(k1 * n2c + k2o) * RLEN] and its result
+    // index kk goes to out[k1 + n1 * k2o + n1 * n2c * kk].  n2c = 1: last pass of a two-pass transform; n2c > 1: of a
+    // three-pass transform (k2o = index of the middle pass).  A CTA takes RPC rows with consecutive k1.
+    const int gpo = ROWS ? n1 / RPC : 1;
+    const size_t per_seq = (size_t)gpo * (size_t)(ROWS ? n2c : 1);
+    const size_t seq = ROWS ? (size_t)row / per_seq : (size_t)row;
+    const int k2o = ROWS ? (int)(((size_t)row % per_seq) / (size_t)gpo) : 0;
+    const int grp = ROWS ? (int)(((size_t)row % per_seq) % (size_t)gpo) : 0;
+    const size_t seq_len = ROWS ? (size_t)RLEN * (size_t)n1 * (size_t)n2c : (size_t)N;
+    const size_t rstride = ROWS ? (size_t)RLEN * (size_t)n2c : (size_t)RLEN;
+    const float2* xr = x + seq * seq_len + (ROWS ? (size_t)k2o * RLEN + (size_t)grp * RPC * rstride : 0);   // NATQ: N = 4096 = one group of rows
 
     cp v[16];
     // ------------------------------------------------------------------ F0: radix-R0 over stride 4096
@@ -196,7 +203,7 @@ fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, long long row
             for (int n2 = 0; n2 < 16; n2++) {
                 const int src = SHIFT_IN ? (n2 ^ 8) : n2;
                 const float2* gp = NATQ ? xr + (n2 / (NATQ ? NATQ : 1)) * (256 * NATQ) + 256 * ((n2 % (NATQ ? NATQ : 1)) ^ (SHIFT_IN ? NATQ / 2 : 0)) + c
-                                   : R1K ? xr + (n2 % RPC) * RLEN + 256 * (n2 / RPC) + c : xr + (ROWS ? sb * 4096 : 0) + c + 256 * src;
+                                   : R1K ? xr + (n2 % RPC) * rstride + 256 * (n2 / RPC) + c : xr + (ROWS ? sb * rstride : 0) + c + 256 * src;
                 const float4 ab = __ldg(reinterpret_cast<const float4*>(gp));
                 v[n2].re = make_float2(ab.x, ab.z);
                 v[n2].im = make_float2(ab.y, ab.w);
@@ -359,12 +366,13 @@ fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, long long row
         // slot j holds k2 = bitrev4(j); k = (rank*NSB + lsb) + R0*(k0 + 16*k1 + 256*k2)
         // (ROWS: k = (NSB*grp + lsb) + n1*(k0 + 16*k1 + 256*k2))
         // (TQ: row = k0 % RPC, k = (RPC*grp + row) + n1*((k0 / RPC) + Q*(k1 + 16*k2)))
-        const int kst = ROWS ? n1 : R0;
+        const size_t kst = ROWS ? (size_t)n1 * (size_t)n2c : (size_t)R0;
+        const size_t kbase = ROWS ? (size_t)n1 * (size_t)k2o : 0;
         // (NATQ: row = k0 / Q, k = row*256*Q + (k0 % Q) + Q*(k1 + 16*k2))
         const size_t klow = NATQ ? (size_t)((k0 / (NATQ ? NATQ : 1)) * (256 * NATQ) + (k0 % (NATQ ? NATQ : 1)) + NATQ * k1)
-                            : R1K ? (size_t)(RPC * grp + (k0 % RPC)) + (size_t)n1 * (size_t)((k0 / RPC) + TQ * k1)
-                                : (ROWS ? (size_t)(NSB * grp + lsb) : (size_t)(rank * NSB + lsb)) + (size_t)kst * (size_t)(k0 + 16 * k1);
-        const size_t k2s = NATQ ? (size_t)(16 * NATQ) : R1K ? (size_t)(16 * TQ) * (size_t)n1 : (size_t)256 * (size_t)kst;
+                            : R1K ? kbase + (size_t)(RPC * grp + (k0 % RPC)) + kst * (size_t)((k0 / RPC) + TQ * k1)
+                                : kbase + (ROWS ? (size_t)(NSB * grp + lsb) : (size_t)(rank * NSB + lsb)) + kst * (size_t)(k0 + 16 * k1);
+        const size_t k2s = NATQ ? (size_t)(16 * NATQ) : R1K ? (size_t)(16 * TQ) * kst : (size_t)256 * kst;
         if constexpr (MAG) {
             float* o = reinterpret_cast<float*>(out_) + seq * seq_len + klow;
 #pragma unroll
@@ -558,7 +566,7 @@ const float* fftp_twiddles() {
 }
 
 template <int R0, int CL, bool INV, bool SI, bool SO, bool MAG, bool ROWS = false, int TQ = 0, int NATQ = 0>
-int fftp_launch(const void* in, void* out, size_t rows, float scale, cudaStream_t st, int n1 = 1) {
+int fftp_launch(const void* in, void* out, size_t rows, float scale, cudaStream_t st, int n1 = 1, int n2c = 1) {
     constexpr int NSB = R0 / CL;
     const size_t smem = (size_t)2 * NSB * FP_B_OF(NSB) * sizeof(float);
     auto kern = fftp_kernel<R0, CL, INV, SI, SO, MAG, ROWS, TQ, NATQ>;
@@ -587,7 +595,7 @@ int fftp_launch(const void* in, void* out, size_t rows, float scale, cudaStream_
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = (CL > 1 && !FP_DUP) ? 1 : 0;
-    BDSP_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, reinterpret_cast<const float2*>(in), out, (long long)rows, scale, tw, n1));
+    BDSP_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, reinterpret_cast<const float2*>(in), out, (long long)rows, scale, tw, n1, n2c));
     BDSP_LAUNCHED();
     return 0;
 }
@@ -649,12 +657,13 @@ int fftp_colpass(const void* in, void* tmp, int n1, int log2n2, size_t rows, cud
 
 // last pass over rows of 256*Q points, 16/Q adjacent rows per 128-thread CTA
 template <int Q>
-int fftp_rowsq_pass(const void* tmp, void* out, size_t groups, bool inverse, bool so, bool magnitude, float sc, cudaStream_t st, int n1) {
-    if (inverse) return fftp_launch<1, 1, true, false, false, false, true, Q>(tmp, out, groups, sc, st, n1);
-    if (magnitude) return so ? fftp_launch<1, 1, false, false, true, true, true, Q>(tmp, out, groups, sc, st, n1)
-                             : fftp_launch<1, 1, false, false, false, true, true, Q>(tmp, out, groups, sc, st, n1);
-    return so ? fftp_launch<1, 1, false, false, true, false, true, Q>(tmp, out, groups, sc, st, n1)
-              : fftp_launch<1, 1, false, false, false, false, true, Q>(tmp, out, groups, sc, st, n1);
+int fftp_rowsq_pass(const void* tmp, void* out, size_t groups, bool inverse, bool so, bool magnitude, float sc, cudaStream_t st, int n1,
+                    int n2c = 1) {
+    if (inverse) return fftp_launch<1, 1, true, false, false, false, true, Q>(tmp, out, groups, sc, st, n1, n2c);
+    if (magnitude) return so ? fftp_launch<1, 1, false, false, true, true, true, Q>(tmp, out, groups, sc, st, n1, n2c)
+                             : fftp_launch<1, 1, false, false, false, true, true, Q>(tmp, out, groups, sc, st, n1, n2c);
+    return so ? fftp_launch<1, 1, false, false, true, false, true, Q>(tmp, out, groups, sc, st, n1, n2c)
+              : fftp_launch<1, 1, false, false, false, false, true, Q>(tmp, out, groups, sc, st, n1, n2c);
 }
 }  // namespace
 
@@ -724,6 +733,44 @@ int fftp_two_pass_try(const void* in, void* out, void* tmp, size_t n, size_t row
         if (rc) return rc;
     }
     return 0;
+}
+
+
+// three-pass packed transform for n = 2^21 .. 2^24:  n = nA * 256 * N3 with nA in {16, 256}:
+//   pass A: nA-point columns over stride n/nA (+ W_n twiddle), pass B: 256-point columns inside every block of 256*N3
+//   points (exactly the first pass of the two-pass transform of that length, in place), pass C: rows of N3 = 256*Q points,
+//   16/Q rows with consecutive k1 per CTA, stored at k1 + nA*k2 + nA*256*k3.
+int fftp_three_pass_try(const void* in, void* out, void* tmp, size_t n, size_t rows, bool inverse, size_t in_rot, size_t out_rot,
+                        double scale, bool magnitude, cudaStream_t st) {
+    int nA, log2n3;
+    switch (n) {
+    case 1u << 21: nA = 16; log2n3 = 9; break;
+    case 1u << 22: nA = 16; log2n3 = 10; break;
+    case 1u << 23: nA = 16; log2n3 = 11; break;
+    case 1u << 24: nA = 256; log2n3 = 8; break;
+    default: return 1;
+    }
+    if ((in_rot != 0 && in_rot != n / 2) || (out_rot != 0 && out_rot != n / 2)) return 1;
+    if (inverse && (magnitude || out_rot != 0)) return 1;
+    if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 7) || (reinterpret_cast<uintptr_t>(tmp) & 15)) return 1;
+    if (tmp == in || tmp == out) return 1;
+    const int tq = 1 << (log2n3 - 8);
+    if (rows * (n >> 4) > 0x7fffffffull) return 1;
+    const bool si = in_rot != 0, so = out_rot != 0;
+    int rc;
+    int l2 = 0;
+    while (((size_t)nA << l2) < n) l2++;                 // n / nA = 2^l2
+    if (inverse) rc = si ? fftp_colpass<true, true>(in, tmp, nA, l2, rows, st) : fftp_colpass<true, false>(in, tmp, nA, l2, rows, st);
+    else rc = si ? fftp_colpass<false, true>(in, tmp, nA, l2, rows, st) : fftp_colpass<false, false>(in, tmp, nA, l2, rows, st);
+    if (rc) return rc;
+    rc = inverse ? fftp_colpass<true, false>(tmp, tmp, 256, log2n3, rows * (size_t)nA, st) : fftp_colpass<false, false>(tmp, tmp, 256, log2n3, rows * (size_t)nA, st);
+    if (rc) return rc;
+    const size_t groups = rows * (size_t)(nA / (16 / tq)) * 256;
+    const float sc = (float)scale;
+    if (tq == 8) return fftp_rowsq_pass<8>(tmp, out, groups, inverse, so, magnitude, sc, st, nA, 256);
+    if (tq == 4) return fftp_rowsq_pass<4>(tmp, out, groups, inverse, so, magnitude, sc, st, nA, 256);
+    if (tq == 2) return fftp_rowsq_pass<2>(tmp, out, groups, inverse, so, magnitude, sc, st, nA, 256);
+    return fftp_rowsq_pass<1>(tmp, out, groups, inverse, so, magnitude, sc, st, nA, 256);
 }
 
 // Last pass of a two-pass transform of n = n1 * 1024 points whose first pass (any kernel) left tmp[k1 * 1024 + n2]

@@ -708,6 +708,30 @@ def test_multiply_complex_exponential(dtype):  # complex_ops.rs:81-105
     assert o.rel_l2(got, o.multiply_complex_exponential(x, 0.01, 0.3, dtype, delta=0.5)) <= 1e-6 if dtype == np.float32 else 1e-14
 
 
+@pytest.mark.parametrize("log2n", [21, 22, 23, 24])
+def test_three_pass_transforms(log2n):
+    """packed three-pass path (fftp.cu): forward (plain, shifted + magnitude) and inverse of one long sequence."""
+    n = 1 << log2n
+    rng = np.random.default_rng(log2n)
+    L = bd.lib()
+    rows = 2 if log2n < 23 else 1
+    x = rand_c(rng, n * rows, np.float32)
+    v = DspVec(x)
+    out = DspVec.zeros(2 * n * rows, is_complex=True, dtype=np.float32)
+    pin, pout = v._fn("bdsp_device_ptr")(v._h), out._fn("bdsp_device_ptr")(out._h)
+    xr = x.reshape(rows, n).astype(np.complex128)
+    X = np.fft.fft(xr, axis=1)
+    assert L.bdsp_fft_rows_c32(pin, pout, n, rows, 0) == 0
+    assert o.rel_l2(out.to_numpy().reshape(rows, n), X) <= tol(n, np.float32)
+    assert L.bdsp_fft_rows_c32(pin, pout, n, rows, bd.F_INVERSE) == 0
+    assert o.rel_l2(out.to_numpy().reshape(rows, n), np.fft.ifft(xr, axis=1) * n) <= tol(n, np.float32)
+    assert L.bdsp_fft_rows_c32(pin, pout, n, rows, bd.F_INVERSE | bd.F_SHIFT) == 0
+    assert o.rel_l2(out.to_numpy().reshape(rows, n), np.fft.ifft(np.fft.ifftshift(xr, axes=1), axis=1)) <= tol(n, np.float32)
+    mag = DspVec.zeros(n * rows, dtype=np.float32)
+    assert L.bdsp_fft_rows_c32(pin, mag._fn("bdsp_device_ptr")(mag._h), n, rows, bd.F_SHIFT | bd.F_MAGNITUDE) == 0
+    assert o.rel_l2(mag.to_numpy().reshape(rows, n), np.abs(np.fft.fftshift(X, axes=1))) <= tol(n, np.float32)
+
+
 def test_streams_do_not_share_workspace():
     """Calls queued on different streams may overlap on the device: their scratch buffers must be distinct."""
     rng = np.random.default_rng(99)
