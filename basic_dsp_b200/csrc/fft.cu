@@ -676,7 +676,10 @@ int fft_any(const void* in, void* out, size_t n, size_t batch, const FftOpts& o,
             void* w0 = workspace(need, 0);
             C* w2 = reinterpret_cast<C*>(workspace(need, 2));
             OutMap plainP; plainP.seq_group = 1; plainP.oes = 1; plainP.group_stride = (long long)P; plainP.rot = 0; plainP.rot_n = (long long)P;
-            int rc = fft_pow2<T, INV>(w1, w2, P, batch * q, false, false, 0, (T)1, plainP, w0, st);
+            (void)plainP;
+            FftOpts po;   // plain transform of the q*batch rows: takes the packed passes where they exist
+            po.inverse = INV;
+            int rc = fft_any<T, INV>(w1, w2, P, batch * q, po, w0, need, st);
             if (rc) return rc;
             interleave_q_kernel<T><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(w2, out, (int)q, (long long)P, (long long)batch, om.rot, o.magnitude);
             BDSP_LAUNCHED();
