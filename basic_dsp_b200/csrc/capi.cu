@@ -382,7 +382,7 @@ int convolve_taps(Vec<T>* v, const T* h_dev, size_t L, bool h_complex, T** Hs_ca
     if (L <= direct_max) {
         rc = fir_convolve<T>(v->d, v->scratch, h_dev, N, 1, L, cl, v->is_complex, h_complex, g_stream);
     } else if (L <= ols_max_taps<T>()) {
-        const size_t M = ols_block_len<T>(L);
+        const size_t M = ols_block_len<T>(L, v->is_complex != 0);
         T* Hs = nullptr;
         bool own = false;
         if (Hs_cache && *Hs_valid && *Hs_M == M) Hs = *Hs_cache;
@@ -1202,7 +1202,7 @@ template <typename T> ConvPlan* conv_plan_create(const void* h_dev, size_t L) {
     if (cudaMalloc(&p->taps, L * sizeof(C)) != cudaSuccess) { delete p; return nullptr; }
     cudaMemcpyAsync(p->taps, h_dev, L * sizeof(C), cudaMemcpyDeviceToDevice, g_stream);
     if (L > 24 && L <= ols_max_taps<T>()) {
-        p->M = ols_block_len<T>(L);
+        p->M = ols_block_len<T>(L, true);
         if (cudaMalloc(&p->Hs, ols_spectrum_bytes<T>(p->M)) != cudaSuccess || ols_prepare<T>(p->taps, L, 0, p->Hs, p->M, g_stream) != 0) {
             cudaFree(p->taps); if (p->Hs) cudaFree(p->Hs); delete p; return nullptr;
         }

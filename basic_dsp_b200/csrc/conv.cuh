@@ -5,7 +5,7 @@
 namespace bdsp {
 
 // block length the overlap-save kernel uses for an L-tap impulse response
-template <typename T> size_t ols_block_len(size_t L);
+template <typename T> size_t ols_block_len(size_t L, bool complex_signal);
 // largest L the overlap-save kernel supports
 template <typename T> size_t ols_max_taps();
 // bytes the caller must provide for Hs

@@ -203,7 +203,7 @@ def test_convolve_signal_kats(kats):
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("n,l", [(64, 1), (64, 2), (65, 7), (300, 24), (300, 25), (1000, 129), (5000, 1023),
                                  (9500, 100), (20000, 1023), (4096, 4096), (10000, 2500), (40000, 5001),
-                                 (3 * 4096 + 5, 2000)])
+                                 (3 * 4096 + 5, 2000), (20000, 2046), (20000, 2047), (9000, 1500), (4096, 1024)])
 def test_convolve_signal_vs_oracle(n, l, dtype):
     rng = np.random.default_rng(n * 7 + l)
     x = rand_c(rng, n, dtype)
