@@ -1,0 +1,56 @@
+"""Small invocations of every kernel family (run under compute-sanitizer)."""
+import sys
+import numpy as np
+sys.path.insert(0, ".")
+import basic_dsp_b200 as bd
+from basic_dsp_b200 import DspVec
+
+L = bd.lib(); bd.require_device()
+rng = np.random.default_rng(0)
+def rc(n, dt=np.complex64): return (rng.uniform(-1, 1, n) + 1j * rng.uniform(-1, 1, n)).astype(dt)
+dp = lambda v: v._fn("bdsp_device_ptr")(v._h)
+# FFT sizes through every path (single vectors and small batches)
+for n in (8, 1000, 1001, 4096, 8192, 16384, 1 << 15, 1 << 16, 1 << 17, 1 << 18, 1 << 19, 1 << 20, 1 << 21, 3 * 4096, 3 * (1 << 16)):
+    DspVec(rc(n)).fft().ifft().to_numpy()
+for n in (1000, 4096, 1 << 15, 3 * 4096):
+    DspVec(rc(n, np.complex128)).fft().ifft().to_numpy()
+for n, rows in ((512, 16), (1024, 8), (2048, 4), (4096, 3), (8192, 3), (16384, 2), (1 << 22, 1)):
+    x = DspVec(rc(n * rows)); out = DspVec.zeros(2 * n * rows, is_complex=True, dtype=np.float32)
+    for flags in (0, bd.F_SHIFT | bd.F_MAGNITUDE, bd.F_INVERSE, bd.F_INVERSE | bd.F_SHIFT):
+        assert L.bdsp_fft_rows_c32(dp(x), dp(out), n, rows, flags) == 0
+# convolution
+for n, l in ((20000, 1023), (5000, 63), (9000, 2000), (40000, 5001), (300, 25)):
+    DspVec(rc(n)).convolve_signal(DspVec(rc(l))).to_numpy()
+DspVec(rc(20000)).convolve(bd.RAISED_COSINE, 0.35, 0.25, 31).to_numpy()
+DspVec(rng.uniform(-1, 1, 20000).astype(np.float32)).convolve_signal(DspVec(rng.uniform(-1, 1, 200).astype(np.float32))).to_numpy()
+# interpolation
+r = rng.uniform(-1, 1, 20001).astype(np.float32)
+DspVec(r).interpolatef(bd.SINC, 0.0, 4.0, 0.0, 12).to_numpy()
+DspVec(r).interpolatef(bd.SINC, 0.0, 2.5, 0.1, 12).to_numpy()
+DspVec(rc(5000)).interpolatef(bd.RAISED_COSINE, 0.35, 3.0, 0.0, 10).to_numpy()
+DspVec(r).interpolate_lin(4.0, 0.0).to_numpy()
+DspVec(r).interpolate_hermite(3.0, 0.0).to_numpy()
+DspVec(r).interpolatei(bd.SINC, 0.0, 3).to_numpy()
+DspVec(r).interpolate(bd.SINC, 0.0, 30011, 0.5).to_numpy()
+DspVec(r).interpft(7001).to_numpy()
+# symmetric transforms, windows, correlation
+DspVec(r).plain_sfft().plain_sifft().to_numpy()
+DspVec(r).windowed_sfft(bd.HAMMING).to_numpy()
+DspVec(rc(3001)).apply_window(bd.BLACKMAN_HARRIS).windowed_fft(bd.HAMMING).to_numpy()
+a, b = DspVec(rc(3001)), DspVec(rc(3001))
+a.correlate(b.prepare_argument_padded()) if False else None
+# elementwise math, reorganisation, reductions
+v = DspVec(r)
+for name in ("sin", "sqrt", "abs", "exp", "diff", "diff_with_start", "cum_sum"):
+    DspVec(np.abs(r) + 0.1).math(name).to_numpy()
+DspVec(r).math("unwrap", 6.28).to_numpy()
+c = DspVec(rc(20001))
+for name in ("sin", "sqrt", "ln", "tanh", "cum_sum", "diff"):
+    DspVec(rc(20001)).math(name).to_numpy()
+print(v.sum(), v.statistics()["max_index"], c.statistics()["min_index"], v.dot_product(DspVec(r)), c.statistics_split(3)[2]["count"])
+parts = [DspVec(np.zeros(2, dtype=np.float32)) for _ in range(3)]
+DspVec(r[:20001 - 20001 % 3]).split_into(parts)
+DspVec(np.zeros(2, dtype=np.float32)).merge(parts).to_numpy()
+DspVec(r).add_smaller(DspVec(r[:3])).to_numpy() if 20001 % 3 == 0 else None
+L.bdsp_sync()
+print("sanitize smoke done")
