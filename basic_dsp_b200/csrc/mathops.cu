@@ -253,25 +253,51 @@ __global__ void diff_kernel(const T* __restrict__ in, T* __restrict__ out, long 
     }
 }
 
-// ---- cum_sum: three-phase scan over `lanes` interleaved sequences (1 real, 2 complex) -------------------
-// phase 1: per-block totals; phase 2: exclusive scan of the totals (one block); phase 3: block-local
-// sequential-in-thread scan + offsets.  Each thread owns CS_PER consecutive elements of one lane.
+// ---- cum_sum: three-phase scan over LANES interleaved sequences (1 real, 2 complex) ---------------------
+// phase 1: per-block totals; phase 2: exclusive scan of the totals (one block per lane); phase 3: block-local scan +
+// offsets.  A thread owns CS_PER consecutive points (all lanes) and moves them with 16-byte accesses.
 constexpr int CS_THREADS = 256;
 constexpr int CS_PER = 8;
-template <typename T>
-__global__ void cumsum_totals_kernel(const T* __restrict__ in, T* __restrict__ totals, long long points, int lanes) {
-    __shared__ T sh[CS_THREADS];
-    const int lane = blockIdx.y;
+
+template <typename T, int LANES>
+__device__ __forceinline__ void cs_load(const T* __restrict__ in, long long base, long long points, T (&v)[CS_PER * LANES]) {
+    constexpr int W = 16 / sizeof(T);                 // scalars per pack
+    constexpr int NP = CS_PER * LANES / W;            // packs per thread
+    if (base + CS_PER <= points) {
+        const Pack<T>* pv = reinterpret_cast<const Pack<T>*>(in + base * LANES);
+#pragma unroll
+        for (int q = 0; q < NP; q++) {
+            const Pack<T> pk = pv[q];
+#pragma unroll
+            for (int e = 0; e < W; e++) v[q * W + e] = pk.v[e];
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < CS_PER * LANES; k++) v[k] = (base * LANES + k < points * LANES) ? in[base * LANES + k] : (T)0;
+    }
+}
+
+template <typename T, int LANES>
+__global__ void __launch_bounds__(CS_THREADS) cumsum_totals_kernel(const T* __restrict__ in, T* __restrict__ totals, long long points) {
+    __shared__ T sh[LANES][CS_THREADS];
     const long long base = ((long long)blockIdx.x * CS_THREADS + threadIdx.x) * CS_PER;
-    T s = (T)0;
-    for (int k = 0; k < CS_PER; k++) { const long long p = base + k; if (p < points) s = add_(s, in[p * lanes + lane]); }
-    sh[threadIdx.x] = s;
+    T v[CS_PER * LANES];
+    cs_load<T, LANES>(in, base, points, v);
+#pragma unroll
+    for (int l = 0; l < LANES; l++) {
+        T s = (T)0;
+#pragma unroll
+        for (int k = 0; k < CS_PER; k++) s = add_(s, v[k * LANES + l]);
+        sh[l][threadIdx.x] = s;
+    }
     __syncthreads();
     for (int off = CS_THREADS / 2; off > 0; off >>= 1) {
-        if (threadIdx.x < off) sh[threadIdx.x] = add_(sh[threadIdx.x], sh[threadIdx.x + off]);
+        if (threadIdx.x < off)
+#pragma unroll
+            for (int l = 0; l < LANES; l++) sh[l][threadIdx.x] = add_(sh[l][threadIdx.x], sh[l][threadIdx.x + off]);
         __syncthreads();
     }
-    if (threadIdx.x == 0) totals[(long long)lane * gridDim.x + blockIdx.x] = sh[0];
+    if (threadIdx.x < LANES) totals[(long long)threadIdx.x * gridDim.x + blockIdx.x] = sh[threadIdx.x][0];
 }
 template <typename T>
 __global__ void __launch_bounds__(1024) cumsum_scan_totals_kernel(T* __restrict__ totals, long long nblocks, int lanes) {
@@ -294,33 +320,53 @@ __global__ void __launch_bounds__(1024) cumsum_scan_totals_kernel(T* __restrict_
     T run = threadIdx.x ? sh[threadIdx.x - 1] : (T)0;
     for (long long b = b0; b < b0 + per && b < nblocks; b++) { const T v = t[b]; t[b] = run; run = add_(run, v); }
 }
-template <typename T>
-__global__ void cumsum_apply_kernel(const T* __restrict__ in, T* __restrict__ out, const T* __restrict__ totals, long long points, int lanes) {
-    __shared__ T sh[CS_THREADS];
-    const int lane = blockIdx.y;
+template <typename T, int LANES>
+__global__ void __launch_bounds__(CS_THREADS) cumsum_apply_kernel(const T* __restrict__ in, T* __restrict__ out, const T* __restrict__ totals,
+                                                                long long points) {
+    __shared__ T sh[LANES][CS_THREADS];
     const long long base = ((long long)blockIdx.x * CS_THREADS + threadIdx.x) * CS_PER;
-    T v[CS_PER];
-    T s = (T)0;
-    for (int k = 0; k < CS_PER; k++) {
-        const long long p = base + k;
-        v[k] = p < points ? in[p * lanes + lane] : (T)0;
-        s = add_(s, v[k]);
-        v[k] = s;
+    T v[CS_PER * LANES];
+    cs_load<T, LANES>(in, base, points, v);
+#pragma unroll
+    for (int l = 0; l < LANES; l++) {
+        T s = (T)0;
+#pragma unroll
+        for (int k = 0; k < CS_PER; k++) { s = add_(s, v[k * LANES + l]); v[k * LANES + l] = s; }
+        sh[l][threadIdx.x] = s;
     }
-    sh[threadIdx.x] = s;
     __syncthreads();
     // Hillis-Steele inclusive scan of the per-thread sums
     for (int off = 1; off < CS_THREADS; off <<= 1) {
-        T add = (T)0;
-        if (threadIdx.x >= off) add = sh[threadIdx.x - off];
+        T add[LANES];
+#pragma unroll
+        for (int l = 0; l < LANES; l++) add[l] = threadIdx.x >= off ? sh[l][threadIdx.x - off] : (T)0;
         __syncthreads();
-        if (threadIdx.x >= off) sh[threadIdx.x] = add_(sh[threadIdx.x], add);
+        if (threadIdx.x >= off)
+#pragma unroll
+            for (int l = 0; l < LANES; l++) sh[l][threadIdx.x] = add_(sh[l][threadIdx.x], add[l]);
         __syncthreads();
     }
-    const T offset = add_(totals[(long long)lane * gridDim.x + blockIdx.x], threadIdx.x ? sh[threadIdx.x - 1] : (T)0);
-    for (int k = 0; k < CS_PER; k++) {
-        const long long p = base + k;
-        if (p < points) out[p * lanes + lane] = add_(offset, v[k]);
+    T offset[LANES];
+#pragma unroll
+    for (int l = 0; l < LANES; l++)
+        offset[l] = add_(totals[(long long)l * gridDim.x + blockIdx.x], threadIdx.x ? sh[l][threadIdx.x - 1] : (T)0);
+#pragma unroll
+    for (int k = 0; k < CS_PER * LANES; k++) v[k] = add_(offset[k % LANES], v[k]);
+    constexpr int W = 16 / sizeof(T);
+    constexpr int NP = CS_PER * LANES / W;
+    if (base + CS_PER <= points) {
+        Pack<T>* pv = reinterpret_cast<Pack<T>*>(out + base * LANES);
+#pragma unroll
+        for (int q = 0; q < NP; q++) {
+            Pack<T> pk;
+#pragma unroll
+            for (int e = 0; e < W; e++) pk.v[e] = v[q * W + e];
+            pv[q] = pk;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < CS_PER * LANES; k++)
+            if (base * LANES + k < points * LANES) out[base * LANES + k] = v[k];
     }
 }
 
@@ -453,12 +499,16 @@ int math_cumsum(const void* in, void* out, void* work, size_t points, int lanes,
     if (!points) return 0;
     const size_t per_block = (size_t)CS_THREADS * CS_PER;
     const unsigned nblocks = (unsigned)((points + per_block - 1) / per_block);
-    dim3 grid(nblocks, (unsigned)lanes);
-    cumsum_totals_kernel<T><<<grid, CS_THREADS, 0, st>>>(reinterpret_cast<const T*>(in), reinterpret_cast<T*>(work), (long long)points, lanes);
+    const T* i = reinterpret_cast<const T*>(in);
+    T* o = reinterpret_cast<T*>(out);
+    T* w = reinterpret_cast<T*>(work);
+    if (lanes == 1) cumsum_totals_kernel<T, 1><<<nblocks, CS_THREADS, 0, st>>>(i, w, (long long)points);
+    else cumsum_totals_kernel<T, 2><<<nblocks, CS_THREADS, 0, st>>>(i, w, (long long)points);
     BDSP_LAUNCHED();
-    cumsum_scan_totals_kernel<T><<<lanes, 1024, 0, st>>>(reinterpret_cast<T*>(work), (long long)nblocks, lanes);
+    cumsum_scan_totals_kernel<T><<<lanes, 1024, 0, st>>>(w, (long long)nblocks, lanes);
     BDSP_LAUNCHED();
-    cumsum_apply_kernel<T><<<grid, CS_THREADS, 0, st>>>(reinterpret_cast<const T*>(in), reinterpret_cast<T*>(out), reinterpret_cast<const T*>(work), (long long)points, lanes);
+    if (lanes == 1) cumsum_apply_kernel<T, 1><<<nblocks, CS_THREADS, 0, st>>>(i, o, w, (long long)points);
+    else cumsum_apply_kernel<T, 2><<<nblocks, CS_THREADS, 0, st>>>(i, o, w, (long long)points);
     BDSP_LAUNCHED();
     return 0;
 }
