@@ -416,36 +416,74 @@ __device__ __forceinline__ cp unit_root_pair(unsigned m0, unsigned m1, float two
     return w;
 }
 
-template <bool INV, bool SHIFT_IN>
+// W_32^a, a = 0..15 (forward sign: cos - i sin)
+__device__ __constant__ float FP_C32[16] = {1.f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f,
+                                            0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508977173f, 0.19509032201612826785f,
+                                            0.f, -0.19509032201612826785f, -0.38268343236508977173f, -0.55557023301960222474f,
+                                            -0.70710678118654752440f, -0.83146961230254523708f, -0.92387953251128675613f, -0.98078528040323044913f};
+__device__ __constant__ float FP_S32[16] = {0.f, 0.19509032201612826785f, 0.38268343236508977173f, 0.55557023301960222474f,
+                                            0.70710678118654752440f, 0.83146961230254523708f, 0.92387953251128675613f, 0.98078528040323044913f,
+                                            1.f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f,
+                                            0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508977173f, 0.19509032201612826785f};
+
+// NH = 2: 32-point columns as a radix-2 step in front of the 16-point transform (two sweeps over the inputs: the
+// second one is served by L2): y_h[a] = (x[a] + (-1)^h x[a + 16]) W_32^{a h}, X[2k' + h] = DFT16(y_h)[k'].
+template <bool INV, bool SHIFT_IN, int NH>
 __global__ void __launch_bounds__(128) fftp_col16_kernel(const float2* __restrict__ x, float2* __restrict__ tmp, int log2n2) {
-    // n = 16 * N2 points per sequence, N2 = 2^log2n2 = row length of the second pass
-    const unsigned N2 = 1u << log2n2, N = 16u * N2;
+    // n = 16 * NH * N2 points per sequence, N2 = 2^log2n2 = row length of the second pass
+    const unsigned N2 = 1u << log2n2, N = 16u * NH * N2;
     const unsigned pi = blockIdx.x * 128u + threadIdx.x;   // column pair over all sequences
     const size_t seq = pi >> (log2n2 - 1);
     const unsigned c = 2u * (pi & (N2 / 2 - 1));
     const float2* xs = x + seq * N + c;
-    cp v[16];
-#pragma unroll
-    for (int a = 0; a < 16; a++) {
-        const int src = SHIFT_IN ? (a ^ 8) : a;
-        const float4 ab = __ldg(reinterpret_cast<const float4*>(xs + (size_t)N2 * src));
-        v[a].re = make_float2(ab.x, ab.z);
-        v[a].im = make_float2(ab.y, ab.w);
-    }
-    r16<INV>(v);
-    apply_twiddles<true>(v, unit_root_pair(c, c + 1, 2.0f / (float)N, INV));
     float2* o = tmp + seq * N + c;
+    const float ton = 2.0f / (float)N;
+#pragma unroll 1
+    for (int h = 0; h < NH; h++) {
+        cp v[16];
 #pragma unroll
-    for (int s = 0; s < 16; s++)
-        *reinterpret_cast<float4*>(o + (size_t)N2 * r16_k(s)) = make_float4(v[s].re.x, v[s].im.x, v[s].re.y, v[s].im.y);
+        for (int a = 0; a < 16; a++) {
+            if constexpr (NH == 1) {
+                const int src = SHIFT_IN ? (a ^ 8) : a;
+                const float4 ab = __ldg(reinterpret_cast<const float4*>(xs + (size_t)N2 * src));
+                v[a].re = make_float2(ab.x, ab.z);
+                v[a].im = make_float2(ab.y, ab.w);
+            } else {
+                // SHIFT_IN rotates the input by n/2 = 16 rows: the two halves swap
+                const float4 lo = __ldg(reinterpret_cast<const float4*>(xs + (size_t)N2 * (a + (SHIFT_IN ? 16 : 0))));
+                const float4 hi = __ldg(reinterpret_cast<const float4*>(xs + (size_t)N2 * (a + (SHIFT_IN ? 0 : 16))));
+                cp l, g;
+                l.re = make_float2(lo.x, lo.z); l.im = make_float2(lo.y, lo.w);
+                g.re = make_float2(hi.x, hi.z); g.im = make_float2(hi.y, hi.w);
+                if (h == 0) v[a] = cadd(l, g);
+                else v[a] = cmulc(csub(l, g), splat(FP_C32[a]), splat(INV ? FP_S32[a] : -FP_S32[a]));
+            }
+        }
+        r16<INV>(v);
+        if constexpr (NH == 1) {
+            apply_twiddles<true>(v, unit_root_pair(c, c + 1, ton, INV));
+        } else {
+            apply_twiddles<true>(v, unit_root_pair(2u * c, 2u * (c + 1), ton, INV));     // (W_n^{2 n2})^{k'}
+            if (h == 1) {
+                const cp wh = unit_root_pair(c, c + 1, ton, INV);                        // W_n^{n2 h}
+#pragma unroll
+                for (int s = 0; s < 16; s++) v[s] = cmul(v[s], wh);
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < 16; s++)
+            *reinterpret_cast<float4*>(o + (size_t)N2 * (NH * r16_k(s) + h)) = make_float4(v[s].re.x, v[s].im.x, v[s].re.y, v[s].im.y);
+    }
 }
 
-template <bool INV, bool SHIFT_IN>
+// NH = 2: 512-point columns, radix-2 step in front of the 256-point transform (two sweeps, see fftp_col16_kernel):
+// y_h[m] = (x[m] + (-1)^h x[m + 256]) W_512^{m h}, X[2k' + h] = DFT256(y_h)[k'].  Not usable in place.
+template <bool INV, bool SHIFT_IN, int NH>
 __global__ void __launch_bounds__(128, 5) fftp_col256_kernel(const float2* __restrict__ x, float2* __restrict__ tmp,
                                                              const float4* __restrict__ tws, int log2n2) {
-    // n = 256 * N2 points per sequence, N2 = 2^log2n2 in {1024, 4096} = row length of the second pass
+    // n = 256 * NH * N2 points per sequence, N2 = 2^log2n2 = row length of the second pass
     const unsigned N2 = 1u << log2n2;
-    const unsigned N = 256u * N2;
+    const unsigned N = 256u * NH * N2;
     __shared__ __align__(16) float sre[16 * 272];
     __shared__ __align__(16) float sim[16 * 272];
     const int t = threadIdx.x;
@@ -453,15 +491,34 @@ __global__ void __launch_bounds__(128, 5) fftp_col256_kernel(const float2* __res
     const size_t seq = blockIdx.x / tiles;
     const unsigned c0 = (blockIdx.x % tiles) * 16u;
     const int hi = t >> 3, j = 2 * (t & 7);
+    const float ton = 2.0f / (float)N;
+#pragma unroll 1
+    for (int h = 0; h < NH; h++) {
     cp v[16];
-    {   // stage 1: radix 16 over n1 = 16a + b, b = hi
+    {   // stage 1: radix 16 over m = 16a + b, b = hi
         const float2* xs = x + seq * N + c0 + j + (size_t)hi * N2;
+        cp wb;
+        if constexpr (NH == 2) wb = unit_root_pair((unsigned)hi, (unsigned)hi, 2.0f / 512.0f, INV);   // W_512^b (both lanes)
 #pragma unroll
         for (int a = 0; a < 16; a++) {
-            const int src = SHIFT_IN ? (a ^ 8) : a;
-            const float4 ab = __ldg(reinterpret_cast<const float4*>(xs + (size_t)src * (16 * (size_t)N2)));
-            v[a].re = make_float2(ab.x, ab.z);
-            v[a].im = make_float2(ab.y, ab.w);
+            if constexpr (NH == 1) {
+                const int src = SHIFT_IN ? (a ^ 8) : a;
+                const float4 ab = __ldg(reinterpret_cast<const float4*>(xs + (size_t)src * (16 * (size_t)N2)));
+                v[a].re = make_float2(ab.x, ab.z);
+                v[a].im = make_float2(ab.y, ab.w);
+            } else {
+                const size_t r0 = (size_t)a * (16 * (size_t)N2), half = (size_t)256 * N2;
+                const float4 lo = __ldg(reinterpret_cast<const float4*>(xs + r0 + (SHIFT_IN ? half : 0)));
+                const float4 hh = __ldg(reinterpret_cast<const float4*>(xs + r0 + (SHIFT_IN ? 0 : half)));
+                cp l, g;
+                l.re = make_float2(lo.x, lo.z); l.im = make_float2(lo.y, lo.w);
+                g.re = make_float2(hh.x, hh.z); g.im = make_float2(hh.y, hh.w);
+                if (h == 0) v[a] = cadd(l, g);
+                else {   // W_512^{16a + b} = W_32^a W_512^b
+                    const cp d = cmulc(csub(l, g), splat(FP_C32[a]), splat(INV ? FP_S32[a] : -FP_S32[a]));
+                    v[a] = cmul(d, wb);
+                }
+            }
         }
         r16<INV>(v);
         const int off = 16 * hi + ((j + 4 * rot_of(hi)) & 15);
@@ -480,7 +537,7 @@ __global__ void __launch_bounds__(128, 5) fftp_col256_kernel(const float2* __res
         }
     }
     __syncthreads();
-    {   // stage 2: radix 16 over b for ka = hi; k1 = ka + 16*kb
+    {   // stage 2: radix 16 over b for ka = hi; k' = ka + 16*kb, output row k1 = NH*k' + h
         const int ka = hi;
 #pragma unroll
         for (int b = 0; b < 16; b++) {
@@ -489,11 +546,11 @@ __global__ void __launch_bounds__(128, 5) fftp_col256_kernel(const float2* __res
             v[b].im = *reinterpret_cast<const float2*>(sim + a);
         }
         r16<INV>(v);
-        // W_n^{n2*k1} = W_n^{n2*ka} * (W_n^{16*n2})^{kb}
+        // W_n^{n2*k1} = W_n^{n2*(NH*ka + h)} * (W_n^{16*NH*n2})^{kb}
         const unsigned n2 = c0 + (unsigned)j;
-        const float ton = 2.0f / (float)N;
-        const cp w0 = unit_root_pair(n2 * (unsigned)ka, (n2 + 1) * (unsigned)ka, ton, INV);
-        const cp u = unit_root_pair(16u * n2, 16u * (n2 + 1), ton, INV);
+        const unsigned kl = (unsigned)(NH * ka + h);
+        const cp w0 = unit_root_pair(n2 * kl, (n2 + 1) * kl, ton, INV);
+        const cp u = unit_root_pair(16u * NH * n2, 16u * NH * (n2 + 1), ton, INV);
         cp A[4], B[4];
         A[0] = w0;
         A[1] = cmul(w0, u);
@@ -503,14 +560,16 @@ __global__ void __launch_bounds__(128, 5) fftp_col256_kernel(const float2* __res
         B[1] = cmul(u2, u2);
         B[2] = cmul(B[1], B[1]);
         B[3] = cmul(B[2], B[1]);
-        float2* o = tmp + seq * N + (size_t)ka * N2 + c0 + j;
+        float2* o = tmp + seq * N + (size_t)kl * N2 + c0 + j;
 #pragma unroll
         for (int s = 0; s < 16; s++) {
             const int kb = r16_k(s);
             const cp w = (kb >> 2) == 0 ? A[kb & 3] : cmul(A[kb & 3], B[kb >> 2]);
             const cp r = cmul(v[s], w);
-            *reinterpret_cast<float4*>(o + (size_t)kb * (16 * (size_t)N2)) = make_float4(r.re.x, r.im.x, r.re.y, r.im.y);
+            *reinterpret_cast<float4*>(o + (size_t)kb * (16 * NH * (size_t)N2)) = make_float4(r.re.x, r.im.x, r.re.y, r.im.y);
         }
+    }
+    if (NH > 1) __syncthreads();   // the next sweep overwrites the shared tile
     }
 }
 
@@ -643,13 +702,14 @@ int fftp_rows_pass(const void* tmp, void* out, size_t groups, bool inverse, bool
 template <bool INV, bool SI>
 int fftp_colpass(const void* in, void* tmp, int n1, int log2n2, size_t rows, cudaStream_t st) {
     const float* tw = fftp_twiddles();
-    if (n1 == 16) {
-        fftp_col16_kernel<INV, SI><<<(unsigned)(rows * ((size_t)1 << (log2n2 - 8))), 128, 0, st>>>(
-            reinterpret_cast<const float2*>(in), reinterpret_cast<float2*>(tmp), log2n2);
-    } else {
-        fftp_col256_kernel<INV, SI><<<(unsigned)(rows * ((size_t)1 << (log2n2 - 4))), 128, 0, st>>>(
-            reinterpret_cast<const float2*>(in), reinterpret_cast<float2*>(tmp), reinterpret_cast<const float4*>(tw + FP_TW_SPLAT), log2n2);
-    }
+    const float2* i2 = reinterpret_cast<const float2*>(in);
+    float2* t2 = reinterpret_cast<float2*>(tmp);
+    const float4* tws = reinterpret_cast<const float4*>(tw + FP_TW_SPLAT);
+    const unsigned g16 = (unsigned)(rows * ((size_t)1 << (log2n2 - 8))), g256 = (unsigned)(rows * ((size_t)1 << (log2n2 - 4)));
+    if (n1 == 16) fftp_col16_kernel<INV, SI, 1><<<g16, 128, 0, st>>>(i2, t2, log2n2);
+    else if (n1 == 32) fftp_col16_kernel<INV, SI, 2><<<g16, 128, 0, st>>>(i2, t2, log2n2);
+    else if (n1 == 256) fftp_col256_kernel<INV, SI, 1><<<g256, 128, 0, st>>>(i2, t2, tws, log2n2);
+    else fftp_col256_kernel<INV, SI, 2><<<g256, 128, 0, st>>>(i2, t2, tws, log2n2);
     BDSP_CUDA_OK(cudaGetLastError());
     BDSP_LAUNCHED();
     return 0;
@@ -671,16 +731,17 @@ int fftp_rowsq_pass(const void* tmp, void* out, size_t groups, bool inverse, boo
 // if out != in).  Returns 1 when the configuration is not covered.
 int fftp_two_pass_try(const void* in, void* out, void* tmp, size_t n, size_t rows, bool inverse, size_t in_rot, size_t out_rot,
                       double scale, bool magnitude, cudaStream_t st) {
-    // n = n1 * N2:  2^15 = 16 x 2048, 2^16 = 256 x 256, 2^17 = 256 x 512, 2^18 = 256 x 1024, 2^19 = 256 x 2048, 2^20 = 256 x 4096.
+    // n = n1 * N2:  2^15 = 32 x 1024, 2^16 = 256 x 256, 2^17 = 256 x 512, 2^18 = 256 x 1024, 2^19 = 512 x 1024, 2^20 = 256 x 4096.
+    // (two adjacent 2048-point rows give only 16-byte store runs: 16 x 2048 took 0.46 ms and 256 x 2048 0.48 ms per 2^26 points)
     // Last pass: 16/Q adjacent rows of N2 = 256*Q points per 128-thread CTA (Q = N2/256 <= 8), or four 4096-point rows per
     // 512-thread CTA.  BDSP_FFTP_2_16=16 selects the 16 x 4096 split for 2^16 (A/B runs).
     int n1, log2n2;
     switch (n) {
-    case 1u << 15: n1 = 16; log2n2 = 11; break;
+    case 1u << 15: n1 = 32; log2n2 = 10; break;
     case 1u << 16: n1 = 256; log2n2 = 8; break;
     case 1u << 17: n1 = 256; log2n2 = 9; break;
     case 1u << 18: n1 = 256; log2n2 = 10; break;
-    case 1u << 19: n1 = 256; log2n2 = 11; break;
+    case 1u << 19: n1 = 512; log2n2 = 10; break;
     case 1u << 20: n1 = 256; log2n2 = 12; break;
     default: return 1;
     }
@@ -736,7 +797,7 @@ int fftp_two_pass_try(const void* in, void* out, void* tmp, size_t n, size_t row
 }
 
 
-// three-pass packed transform for n = 2^21 .. 2^24:  n = nA * 256 * N3 with nA in {16, 256}:
+// three-pass packed transform for n = 2^21 .. 2^24:  n = nA * 256 * N3 with nA in {16, 32, 256}:
 //   pass A: nA-point columns over stride n/nA (+ W_n twiddle), pass B: 256-point columns inside every block of 256*N3
 //   points (exactly the first pass of the two-pass transform of that length, in place), pass C: rows of N3 = 256*Q points,
 //   16/Q rows with consecutive k1 per CTA, stored at k1 + nA*k2 + nA*256*k3.
@@ -746,7 +807,7 @@ int fftp_three_pass_try(const void* in, void* out, void* tmp, size_t n, size_t r
     switch (n) {
     case 1u << 21: nA = 16; log2n3 = 9; break;
     case 1u << 22: nA = 16; log2n3 = 10; break;
-    case 1u << 23: nA = 16; log2n3 = 11; break;
+    case 1u << 23: nA = 32; log2n3 = 10; break;
     case 1u << 24: nA = 256; log2n3 = 8; break;
     default: return 1;
     }
