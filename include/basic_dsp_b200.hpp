@@ -76,6 +76,21 @@ template <typename T> struct Api;
         static int scale_mul_mag_phase(Handle* h, T re, T im, const Handle* w, Handle* m, Handle* p, int wb) {    \
             return bdsp_scale_mul_mag_phase##S(h, re, im, w, m, p, wb);                                           \
         }                                                                                                         \
+        static Result apply_window(Handle* h, int w) { return apply_window##S(h, w); }                            \
+        static Result unapply_window(Handle* h, int w) { return unapply_window##S(h, w); }                        \
+        static Result windowed_fft(Handle* h, int w) { return windowed_fft##S(h, w); }                            \
+        static Result windowed_ifft(Handle* h, int w) { return windowed_ifft##S(h, w); }                          \
+        static Result prepare_argument(Handle* h) { return prepare_argument##S(h); }                              \
+        static Result prepare_argument_padded(Handle* h) { return prepare_argument_padded##S(h); }                \
+        static Result correlate(Handle* h, const Handle* o) { return correlate##S(h, o); }                        \
+        static Result interpolatei(Handle* h, int k, T ro, int f) { return interpolatei##S(h, k, ro, f); }        \
+        static Result interpolate(Handle* h, int k, T ro, size_t n, T d) { return interpolate##S(h, k, ro, n, d); } \
+        static Result interpft(Handle* h, size_t n) { return interpft##S(h, n); }                                 \
+        static Result decimatei(Handle* h, uint32_t f, uint32_t d) { return decimatei##S(h, f, d); }              \
+        static Result plain_sfft(Handle* h) { return plain_sfft##S(h); }                                          \
+        static Result plain_sifft(Handle* h) { return plain_sifft##S(h); }                                        \
+        static Result conj(Handle* h) { return conj##S(h); }                                                      \
+        static T real_sum(const Handle* h) { return real_sum##S(h); }                                             \
     };
 BDSP_API_STRUCT(32, float, BdspVec32, BdspVecResult32)
 BDSP_API_STRUCT(64, double, BdspVec64, BdspVecResult64)
@@ -146,6 +161,22 @@ public:
     GpuVec& magnitude() { return take(A::magnitude(h_), "magnitude"); }
     GpuVec& phase() { return take(A::phase(h_), "phase"); }
     void get_mag_phase(GpuVec& mag, GpuVec& ph) { A::get_mag_phase(h_, mag.h_, ph.h_); }
+    // TimeDomainOperations / CrossCorrelation*Ops / InterpolationOps (FFT based) / Symmetric*DomainOperations
+    GpuVec& apply_window(int window) { return take(A::apply_window(h_, window), "apply_window"); }
+    GpuVec& unapply_window(int window) { return take(A::unapply_window(h_, window), "unapply_window"); }
+    GpuVec& windowed_fft(int window) { return take(A::windowed_fft(h_, window), "windowed_fft"); }
+    GpuVec& windowed_ifft(int window) { return take(A::windowed_ifft(h_, window), "windowed_ifft"); }
+    GpuVec& prepare_argument() { return take(A::prepare_argument(h_), "prepare_argument"); }
+    GpuVec& prepare_argument_padded() { return take(A::prepare_argument_padded(h_), "prepare_argument_padded"); }
+    GpuVec& correlate(const GpuVec& prepared) { return take(A::correlate(h_, prepared.h_), "correlate"); }
+    GpuVec& interpolatei(Response f, T rolloff, int factor) { return take(A::interpolatei(h_, (int)f, rolloff, factor), "interpolatei"); }
+    GpuVec& interpolate(Response f, T rolloff, size_t dest_points, T delay) { return take(A::interpolate(h_, (int)f, rolloff, dest_points, delay), "interpolate"); }
+    GpuVec& interpft(size_t dest_points) { return take(A::interpft(h_, dest_points), "interpft"); }
+    GpuVec& decimatei(uint32_t factor, uint32_t delay) { return take(A::decimatei(h_, factor, delay), "decimatei"); }
+    GpuVec& plain_sfft() { return take(A::plain_sfft(h_), "plain_sfft"); }
+    GpuVec& plain_sifft() { return take(A::plain_sifft(h_), "plain_sifft"); }
+    GpuVec& conj() { return take(A::conj(h_), "conj"); }
+    T sum() const { return A::real_sum(h_); }
     // fused chain of the three sequential calls scale(c); mul(&w); get_mag_phase(..) in one pass
     void scale_mul_mag_phase(std::complex<T> c, const GpuVec& w, GpuVec& mag, GpuVec& ph, bool write_back = false) {
         if (int rc = A::scale_mul_mag_phase(h_, c.real(), c.imag(), w.h_, mag.h_, ph.h_, write_back)) throw DspError(rc, "scale_mul_mag_phase");
