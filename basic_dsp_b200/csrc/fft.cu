@@ -538,7 +538,12 @@ int launch_tile(const TileParams& p, long long batch, T scale, cudaStream_t st) 
 
 template <typename T> int tile_log2m_max() { return sizeof(T) == 4 ? 10 : 9; }
 // lanes per tile: 128 contiguous bytes per row segment (f32: 16, f64: 8) -> 72 KB tiles, 3 CTAs per SM
-template <typename T> long long tile_lanes() { return 8; }
+// lanes per f64 tile: 4 (64-byte row segments, twice the CTAs) measured mixed on B200: C5a 8.83 -> 8.51 ms, 2^18 0.80 -> 0.73 ms,
+// but 2^14 0.82 -> 0.88 and 2^20 1.20 -> 1.31 ms per 2^25 points; 8 stays the default
+#ifndef BDSP_TILE_LANES_F64
+#define BDSP_TILE_LANES_F64 8
+#endif
+template <typename T> long long tile_lanes() { return sizeof(T) == 8 ? BDSP_TILE_LANES_F64 : 8; }
 
 // power-of-two transform of `batch` sequences; handles any supported size
 template <typename T, bool INV>
