@@ -19,6 +19,7 @@
 
 #include "fft.cuh"
 #include "fft_core.cuh"
+#include "elementwise.cuh"
 
 namespace bdsp {
 
@@ -637,6 +638,17 @@ int fft_any(const void* in, void* out, size_t n, size_t batch, const FftOpts& o,
     const long long in_rot = (long long)(o.in_rot % n);
     const T scale = (T)o.scale;
     if (is_pow2(n)) {
+        if (sizeof(T) == 4 && o.real_input && n >= 512 && n <= (1u << 24) && (n >= (1u << 15) || n * batch >= (1u << 18)) &&
+            (n >= 4096 || batch % (4096 / n) == 0)) {
+            // real f32 input in the throughput regime: one complexifying pass (4 B read + 8 B written per point) and the
+            // packed complex passes beat the generic kernels that fuse the conversion into their first load
+            C* cx = reinterpret_cast<C*>(workspace(n * batch * sizeof(C), 1));
+            int rc = ew_zero_interleave<T>(in, cx, n * batch, 2, 1, st);
+            if (rc) return rc;
+            FftOpts oc = o;
+            oc.real_input = 0;
+            return fft_any<T, INV>(cx, out, n, batch, oc, work, work_bytes, st);
+        }
         if (sizeof(T) == 4 && !o.real_input && n >= 512 && n <= 16384) {
             // packed-FP32x2 kernel (fftp.cu); returns 1 when the configuration is not covered
             const int rc = fftp_try(in, out, n, batch, INV, (size_t)in_rot, (size_t)om.rot, o.scale, o.magnitude != 0, st);

@@ -92,13 +92,29 @@ def test_fft_ifft_shifted(n, dtype):
     assert o.rel_l2(DspVec(X.copy(), domain=bd.FREQ).ifft().to_numpy(), o.ifft(X)) <= tol(n, dtype)
 
 
-@pytest.mark.parametrize("n", [64, 1001, 4096, 1 << 16])
+@pytest.mark.parametrize("n", [64, 1001, 4096, 1 << 15, 1 << 16, 1 << 18, 1 << 20, 1 << 21])
 def test_real_input_fft(n):  # tests/real_test.rs:581-605
     rng = np.random.default_rng(n)
     x = rng.uniform(-10, 10, n).astype(np.float32)
     got = DspVec(x).plain_fft().to_numpy()
     assert len(got) == n
     assert o.rel_l2(got, o.plain_fft(x)) <= tol(n, np.float32)
+
+
+@pytest.mark.parametrize("n,rows", [(1024, 256), (4096, 64), (1 << 16, 4), (512, 7)])
+def test_real_input_rows(n, rows):
+    """rows of real scalars (BDSP_F_REAL_INPUT): complexifying pass + packed passes in the throughput regime."""
+    rng = np.random.default_rng(n + rows)
+    L = bd.lib()
+    x = rng.uniform(-10, 10, n * rows).astype(np.float32)
+    v = DspVec(x)
+    out = DspVec.zeros(2 * n * rows, is_complex=True, dtype=np.float32)
+    pin, pout = v._fn("bdsp_device_ptr")(v._h), out._fn("bdsp_device_ptr")(out._h)
+    assert L.bdsp_fft_rows_c32(pin, pout, n, rows, bd.F_REAL_INPUT) == 0
+    ref = np.fft.fft(x.reshape(rows, n).astype(np.float64), axis=1)
+    assert o.rel_l2(out.to_numpy().reshape(rows, n), ref) <= tol(n, np.float32)
+    assert L.bdsp_fft_rows_c32(pin, pout, n, rows, bd.F_REAL_INPUT | bd.F_SHIFT) == 0
+    assert o.rel_l2(out.to_numpy().reshape(rows, n), np.fft.fftshift(ref, axes=1)) <= tol(n, np.float32)
 
 
 def test_fft_wrong_domain_marks_invalid():
