@@ -60,7 +60,7 @@ def test_fft_vector64_golden(kats):  # tests/time_freq_test.rs:45-120
 SIZES = [1, 2, 4, 8, 16, 32, 128, 256, 512, 1024, 2048, 4096, 8192, 16384,      # single CTA
          1 << 15, 1 << 16, 1 << 17, 1 << 18, 1 << 19, 1 << 20, 1 << 21, 1 << 22,                           # multi-pass
          3, 5, 6, 12, 24, 3 * 64, 5 * 1024, 7 * 4096, 3 * (1 << 16), 15 * (1 << 14),  # q * 2^k
-         17 * 29, 1001, 9973, 10007 * 3, 127 * 127]                             # Bluestein
+         17 * 29, 1001, 9973, 10007 * 3, 127 * 127, 1000003]                    # Bluestein
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
