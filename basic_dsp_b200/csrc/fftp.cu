@@ -66,6 +66,15 @@ template <int R0, int CL, bool INV, bool SHIFT_IN, bool SHIFT_OUT, bool MAG, boo
 #ifndef FP_DUP
 #define FP_DUP 1
 #endif
+// result stores: FP_STREAM_STORES=1 uses st.global.cs (evict-first) for the write-once output (measured: no difference)
+#ifndef FP_STREAM_STORES
+#define FP_STREAM_STORES 0
+#endif
+#if FP_STREAM_STORES
+#define FP_ST(p, v) __stcs((p), (v))
+#else
+#define FP_ST(p, v) (*(p) = (v))
+#endif
 __global__ void __launch_bounds__(128 * (R0 / CL), (R0 / CL) == 2 ? FP_MINB256 : 4 / (R0 / CL))
 fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, long long rows, float scale, const float* __restrict__ tw, int n1, int n2c) {
     constexpr int NSB = R0 / CL;          // sub-blocks (4096-point transforms) owned by this CTA
@@ -379,16 +388,16 @@ fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, long long row
             for (int m = 0; m < 8; m++) {
                 pk m2 = pfma(P[m].re, P[m].re, pmul(P[m].im, P[m].im));
                 const int ka = bitrev4(2 * m) ^ (SHIFT_OUT ? 8 : 0), kb = bitrev4(2 * m + 1) ^ (SHIFT_OUT ? 8 : 0);
-                o[k2s * ka] = sqrtf(m2.x) * scale;
-                o[k2s * kb] = sqrtf(m2.y) * scale;
+                FP_ST(o + k2s * ka, sqrtf(m2.x) * scale);
+                FP_ST(o + k2s * kb, sqrtf(m2.y) * scale);
             }
         } else {
             float2* o = reinterpret_cast<float2*>(out_) + seq * seq_len + klow;
 #pragma unroll
             for (int m = 0; m < 8; m++) {
                 const int ka = bitrev4(2 * m) ^ (SHIFT_OUT ? 8 : 0), kb = bitrev4(2 * m + 1) ^ (SHIFT_OUT ? 8 : 0);
-                o[k2s * ka] = make_float2(P[m].re.x * scale, P[m].im.x * scale);
-                o[k2s * kb] = make_float2(P[m].re.y * scale, P[m].im.y * scale);
+                FP_ST(o + k2s * ka, make_float2(P[m].re.x * scale, P[m].im.x * scale));
+                FP_ST(o + k2s * kb, make_float2(P[m].re.y * scale, P[m].im.y * scale));
             }
         }
     }
