@@ -4,6 +4,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
 #include <vector>
 
 #include "../../include/basic_dsp_b200.h"
@@ -405,6 +407,51 @@ int convolve_taps(Vec<T>* v, const T* h_dev, size_t L, bool h_complex, T** Hs_ca
     return 0;
 }
 
+// ---- cache of tap / response tables built from the BUILT-IN functions (kind 0 / 1) ----------------------
+// Repeated calls with the same parameters (the usual streaming use) skip the host evaluation and the upload.
+// Keyed by everything the table depends on; tables live in device memory until the process ends (<= 64 entries
+// per process, then the cache stops growing).  Callback functions are never cached.
+struct TableKey {
+    int dev, is64, what, kind, flag;
+    double rolloff, a, b;
+    size_t n0, n1;
+    bool operator<(const TableKey& o) const {
+        if (dev != o.dev) return dev < o.dev;
+        if (is64 != o.is64) return is64 < o.is64;
+        if (what != o.what) return what < o.what;
+        if (kind != o.kind) return kind < o.kind;
+        if (flag != o.flag) return flag < o.flag;
+        if (rolloff != o.rolloff) return rolloff < o.rolloff;
+        if (a != o.a) return a < o.a;
+        if (b != o.b) return b < o.b;
+        if (n0 != o.n0) return n0 < o.n0;
+        return n1 < o.n1;
+    }
+};
+std::mutex g_table_mu;
+std::map<TableKey, std::pair<void*, size_t>> g_table_cache;
+
+template <typename T> const T* table_cache_find(TableKey key, size_t* count) {
+    cudaGetDevice(&key.dev);
+    key.is64 = sizeof(T) == 8;
+    std::lock_guard<std::mutex> lk(g_table_mu);
+    auto it = g_table_cache.find(key);
+    if (it == g_table_cache.end()) return nullptr;
+    *count = it->second.second;
+    return reinterpret_cast<const T*>(it->second.first);
+}
+template <typename T> const T* table_cache_insert(TableKey key, const std::vector<T>& tab) {
+    cudaGetDevice(&key.dev);
+    key.is64 = sizeof(T) == 8;
+    std::lock_guard<std::mutex> lk(g_table_mu);
+    if (g_table_cache.size() >= 64) return nullptr;
+    void* dev = nullptr;
+    if (cudaMalloc(&dev, tab.size() * sizeof(T)) != cudaSuccess) return nullptr;
+    if (cudaMemcpy(dev, tab.data(), tab.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(dev); return nullptr; }
+    g_table_cache[key] = std::make_pair(dev, tab.size());
+    return reinterpret_cast<const T*>(dev);
+}
+
 template <typename T> Res<T> op_convolve_signal(Vec<T>* v, Vec<T>* h) {
     // convolution.rs:477-542
     if (!meta_agrees(v, h)) return done(v, E_META);
@@ -428,6 +475,13 @@ template <typename T> Res<T> op_convolve_fn(Vec<T>* v, const RealFn<T>& f, T rat
     if (N == 0) return done(v, 0);
     const T ratio_inv = (T)1 / ratio;
     const bool simd_branch = len <= 202 && v->len > 2000 && (T)fabs((T)round(ratio_inv) - ratio_inv) < (T)1e-6 && ratio > (T)0.5;
+    TableKey key = {};
+    key.what = 1; key.kind = f.kind; key.flag = simd_branch; key.rolloff = (double)f.rolloff; key.a = (double)ratio; key.n0 = len; key.n1 = N;
+    if (f.kind != 2) {
+        size_t cnt = 0;
+        const T* cached = table_cache_find<T>(key, &cnt);
+        if (cached) return done(v, convolve_taps<T>(v, cached, cnt, false, nullptr, nullptr, nullptr));
+    }
     std::vector<T> taps;
     if (simd_branch) {
         // taps f(j/ratio), j = -len..len, handed to convolve_signal (convolution.rs:151-172).
@@ -456,6 +510,10 @@ template <typename T> Res<T> op_convolve_fn(Vec<T>* v, const RealFn<T>& f, T rat
             folded[(size_t)k2] += taps[k];
         }
         taps.swap(folded);
+    }
+    if (f.kind != 2) {
+        const T* cached = table_cache_insert<T>(key, taps);
+        if (cached) return done(v, convolve_taps<T>(v, cached, taps.size(), false, nullptr, nullptr, nullptr));
     }
     T* h_dev = nullptr;
     int rc = upload_table(taps, &h_dev);
@@ -677,6 +735,17 @@ template <typename T> Res<T> op_interpolatef(Vec<T>* v, const RealFn<T>& f, T fa
         const int F = (int)round(factor);
         const int L = (int)conv_len;
         const int J = 2 * L + 3;
+        TableKey key = {};
+        key.what = 2; key.kind = f.kind; key.rolloff = (double)f.rolloff; key.a = (double)delay; key.n0 = (size_t)F; key.n1 = (size_t)L;
+        size_t cnt = 0;
+        const T* cached = f.kind != 2 ? table_cache_find<T>(key, &cnt) : nullptr;
+        if (cached) {
+            rc = interp_poly<T>(v->d, v->scratch, cached, N, new_points, F, L, v->is_complex, g_stream);
+            if (rc) return done(v, rc);
+            trade(v);
+            v->len = new_len;
+            return done(v, 0);
+        }
         // function_to_vectors (interpolation.rs:133-181): v_s[k] = f(j_k - s/F), j_0 = -(L-1) + delay
         std::vector<T> vs((size_t)F * (2 * L + 1));
         for (int s = 0; s < F; s++) {
@@ -693,10 +762,14 @@ template <typename T> Res<T> op_interpolatef(Vec<T>* v, const RealFn<T>& f, T fa
             T* te = &tab[(size_t)(F + s) * J];              // edges (interpolation.rs:293-315)
             for (int k = 0; k <= 2 * L; k++) te[k + 2] = vs[(size_t)s * (2 * L + 1) + k];
         }
-        T* dev = nullptr;
-        rc = upload_table(tab, &dev);
-        if (!rc) rc = interp_poly<T>(v->d, v->scratch, dev, N, new_points, F, L, v->is_complex, g_stream);
-        table_consumed();
+        cached = f.kind != 2 ? table_cache_insert<T>(key, tab) : nullptr;
+        if (cached) rc = interp_poly<T>(v->d, v->scratch, cached, N, new_points, F, L, v->is_complex, g_stream);
+        else {
+            T* dev = nullptr;
+            rc = upload_table(tab, &dev);
+            if (!rc) rc = interp_poly<T>(v->d, v->scratch, dev, N, new_points, F, L, v->is_complex, g_stream);
+            table_consumed();
+        }
     } else {
         if (f.kind == 2) return done(v, E_ARG_LEN);   // custom callback + per-output taps: not supported on the device
         rc = interp_frac<T>(v->d, v->scratch, N, new_points, (double)factor, (double)delay, (int)conv_len, f.kind,

@@ -121,7 +121,7 @@ def main():
             for flush in (False, True):
                 med, best = T.run(lambda: v.convolve(bd.RAISED_COSINE, 0.35, 0.25, 31), args.iters, flush=flush)
                 report("C2b", "c32 2^20 convolve, 63-tap RC (len=31, ratio=0.25)" + (" (L2 flushed)" if flush else " (L2 warm)"), n,
-                       16 * n, 4 * 63 * n, med, best, {"note": "includes host tap evaluation + 63-float upload per call"})
+                       16 * n, 4 * 63 * n, med, best, {"note": "tap table cached on the device after the first call"})
         del src
 
     if "C3" in want:
@@ -184,7 +184,7 @@ def main():
                 v.set_len(n)
             med, best = T.run(lambda: v.interpolatef(bd.SINC, 0.0, 4.0, 0.0, 12), args.iters, setup=setup)
             report("C4a", "real f32 2^24 interpolatef x4 sinc conv_len=12", n, 20 * n, 2 * 25 * 4 * n, med, best,
-                   {"note": "timed call includes the host tap-table build/upload; input length reset by set_len (data differs, same cost)"})
+                   {"note": "tap table cached on the device after the first call; input length reset by set_len (data differs, same cost)"})
             del v
         if "C4b" in want:
             v = DspVec(x)
