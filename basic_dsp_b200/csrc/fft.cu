@@ -26,11 +26,12 @@ namespace bdsp {
 int fftp_rows1k_try(const void* tmp, void* out, size_t n, size_t rows, bool inverse, size_t out_rot, double scale, bool magnitude,
                     cudaStream_t st);
 int fftp_three_pass_try(const void* in, void* out, void* tmp, size_t n, size_t rows, bool inverse, size_t in_rot, size_t out_rot,
-                        double scale, bool magnitude, cudaStream_t st);
+                        double scale, bool magnitude, cudaStream_t st, bool real_in);
 int fftp_two_pass_try(const void* in, void* out, void* tmp, size_t n, size_t rows, bool inverse, size_t in_rot, size_t out_rot,
-                      double scale, bool magnitude, cudaStream_t st);
+                      double scale, bool magnitude, cudaStream_t st, bool real_in);
 int fftp_try(const void* in, void* out, size_t n, size_t rows, bool inverse, size_t in_rot, size_t out_rot, double scale,
              bool magnitude, cudaStream_t st);
+int fftp_try_real(const void* in, void* out, size_t n, size_t rows, size_t out_rot, double scale, bool magnitude, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------
 // per-device state: twiddle tables, workspaces
@@ -638,7 +639,12 @@ int fft_any(const void* in, void* out, size_t n, size_t batch, const FftOpts& o,
     const long long in_rot = (long long)(o.in_rot % n);
     const T scale = (T)o.scale;
     if (is_pow2(n)) {
-        if (sizeof(T) == 4 && o.real_input && n >= 512 && n <= (1u << 24) && (n >= (1u << 15) || n * batch >= (1u << 18)) &&
+        if (sizeof(T) == 4 && o.real_input && !INV && in_rot == 0 && n >= 512 && n <= 16384 && n * batch >= (1u << 16)) {
+            // rows of real scalars, single pass: the packed kernel loads the reals directly (4 B read + 8 B written per point)
+            const int rc = fftp_try_real(in, out, n, batch, (size_t)om.rot, o.scale, o.magnitude != 0, st);
+            if (rc <= 0) return rc;
+        }
+        if (sizeof(T) == 4 && o.real_input && (INV || in_rot != 0) && n >= 512 && n <= (1u << 24) && (n >= (1u << 15) || n * batch >= (1u << 18)) &&
             (n >= 4096 || batch % (4096 / n) == 0)) {
             // real f32 input in the throughput regime: one complexifying pass (4 B read + 8 B written per point) and the
             // packed complex passes beat the generic kernels that fuse the conversion into their first load
@@ -659,14 +665,14 @@ int fft_any(const void* in, void* out, size_t n, size_t batch, const FftOpts& o,
             size_t need = n * batch * sizeof(C);
             if (!w || work_bytes < need) w = workspace(need, 0);
         }
-        if (sizeof(T) == 4 && !o.real_input && n >= (1u << 15) && n <= (1u << 20)) {
+        if (sizeof(T) == 4 && n >= (1u << 15) && n <= (1u << 20)) {
             // packed two-pass path (fftp.cu): 16 B/point of traffic per pass
-            const int rc = fftp_two_pass_try(in, out, w, n, batch, INV, (size_t)in_rot, (size_t)om.rot, o.scale, o.magnitude != 0, st);
+            const int rc = fftp_two_pass_try(in, out, w, n, batch, INV, (size_t)in_rot, (size_t)om.rot, o.scale, o.magnitude != 0, st, o.real_input != 0);
             if (rc <= 0) return rc;
         }
-        if (sizeof(T) == 4 && !o.real_input && n >= (1u << 21) && n <= (1u << 24)) {
+        if (sizeof(T) == 4 && n >= (1u << 21) && n <= (1u << 24)) {
             // packed three-pass path (fftp.cu)
-            const int rc = fftp_three_pass_try(in, out, w, n, batch, INV, (size_t)in_rot, (size_t)om.rot, o.scale, o.magnitude != 0, st);
+            const int rc = fftp_three_pass_try(in, out, w, n, batch, INV, (size_t)in_rot, (size_t)om.rot, o.scale, o.magnitude != 0, st, o.real_input != 0);
             if (rc <= 0) return rc;
         }
         return fft_pow2<T, INV>(in, out, n, batch, o.real_input, o.magnitude, in_rot, scale, om, w, st);

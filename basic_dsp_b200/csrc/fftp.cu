@@ -51,10 +51,12 @@ __device__ __forceinline__ int fp_rot(int row, int g) { return (((g >> 1) + (row
 // the first stage is a radix-Q butterfly inside every row, the other two stages are unchanged; 128 threads and 35 KB of
 // shared memory per CTA as for a plain 4096-point transform (which runs at the HBM roofline); the adjacent rows make
 // the transposing stores fill 32-byte (Q = 4) or 64-byte (Q = 2) runs.
+// RIN = true (forward, no ROWS): `x` holds REAL scalars (one float per point); the first stage loads two adjacent reals
+// per column pair and the imaginary parts start as zero.
 // NATQ = Q in {2, 4, 8} (R0 = 1, no ROWS): the CTA's 4096 contiguous points are 16/Q independent rows of 256*Q points
 // (k0 = q + Q*row); the first stage is a radix-Q butterfly inside every row, results are stored in natural order.
 // Batched 512 / 1024 / 2048-point transforms with the structure of the 4096-point kernel.
-template <int R0, int CL, bool INV, bool SHIFT_IN, bool SHIFT_OUT, bool MAG, bool ROWS, int TQ = 0, int NATQ = 0>
+template <int R0, int CL, bool INV, bool SHIFT_IN, bool SHIFT_OUT, bool MAG, bool ROWS, int TQ = 0, int NATQ = 0, bool RIN = false>
 // FP_PREFETCH=1: persistent CTAs + register prefetch of the next row.  Measured on B200 (C3): 0.336 ms vs
 // 0.275 ms without (register pressure -> spills; the extra barrier), so it is off by default.
 #ifndef FP_PREFETCH
@@ -127,6 +129,15 @@ fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, long long row
     const size_t rstride = ROWS ? (size_t)RLEN * (size_t)n2c : (size_t)RLEN;
     const float2* xr = x + seq * seq_len + (ROWS ? (size_t)k2o * RLEN + (size_t)grp * RPC * rstride : 0);   // NATQ: N = 4096 = one group of rows
 
+    // two adjacent points starting at complex element pointer gp: {re0, im0, re1, im1}
+    auto ldpair = [&](const float2* gp) -> float4 {
+        if constexpr (RIN) {
+            const float2 r = __ldg(reinterpret_cast<const float2*>(reinterpret_cast<const float*>(x) + (gp - x)));
+            return make_float4(r.x, 0.f, r.y, 0.f);
+        } else {
+            return __ldg(reinterpret_cast<const float4*>(gp));
+        }
+    };
     cp v[16];
     // ------------------------------------------------------------------ F0: radix-R0 over stride 4096
     if constexpr (R0 > 1 && !ROWS) {
@@ -155,7 +166,7 @@ fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, long long row
                 if constexpr (PREFETCH) ab = raw[u * R0 + n3];
                 else {
                     const int src = SHIFT_IN ? ((n3 + R0 / 2) % R0) : n3;
-                    ab = __ldg(reinterpret_cast<const float4*>(xr + c + 4096 * src));
+                    ab = ldpair(xr + c + 4096 * src);
                 }
                 a[n3].re = make_float2(ab.x, ab.z);
                 a[n3].im = make_float2(ab.y, ab.w);
@@ -213,7 +224,7 @@ fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, long long row
                 const int src = SHIFT_IN ? (n2 ^ 8) : n2;
                 const float2* gp = NATQ ? xr + (n2 / (NATQ ? NATQ : 1)) * (256 * NATQ) + 256 * ((n2 % (NATQ ? NATQ : 1)) ^ (SHIFT_IN ? NATQ / 2 : 0)) + c
                                    : R1K ? xr + (n2 % RPC) * rstride + 256 * (n2 / RPC) + c : xr + (ROWS ? sb * rstride : 0) + c + 256 * src;
-                const float4 ab = __ldg(reinterpret_cast<const float4*>(gp));
+                const float4 ab = ldpair(gp);
                 v[n2].re = make_float2(ab.x, ab.z);
                 v[n2].im = make_float2(ab.y, ab.w);
             }
@@ -437,7 +448,17 @@ __device__ __constant__ float FP_S32[16] = {0.f, 0.19509032201612826785f, 0.3826
 
 // NH = 2: 32-point columns as a radix-2 step in front of the 16-point transform (two sweeps over the inputs: the
 // second one is served by L2): y_h[a] = (x[a] + (-1)^h x[a + 16]) W_32^{a h}, X[2k' + h] = DFT16(y_h)[k'].
-template <bool INV, bool SHIFT_IN, int NH>
+// RIN: x holds real scalars (see fftp_kernel)
+template <bool RIN> __device__ __forceinline__ float4 col_ldpair(const float2* x, const float2* gp) {
+    if constexpr (RIN) {
+        const float2 r = __ldg(reinterpret_cast<const float2*>(reinterpret_cast<const float*>(x) + (gp - x)));
+        return make_float4(r.x, 0.f, r.y, 0.f);
+    } else {
+        return __ldg(reinterpret_cast<const float4*>(gp));
+    }
+}
+
+template <bool INV, bool SHIFT_IN, int NH, bool RIN = false>
 __global__ void __launch_bounds__(128) fftp_col16_kernel(const float2* __restrict__ x, float2* __restrict__ tmp, int log2n2) {
     // n = 16 * NH * N2 points per sequence, N2 = 2^log2n2 = row length of the second pass
     const unsigned N2 = 1u << log2n2, N = 16u * NH * N2;
@@ -454,13 +475,13 @@ __global__ void __launch_bounds__(128) fftp_col16_kernel(const float2* __restric
         for (int a = 0; a < 16; a++) {
             if constexpr (NH == 1) {
                 const int src = SHIFT_IN ? (a ^ 8) : a;
-                const float4 ab = __ldg(reinterpret_cast<const float4*>(xs + (size_t)N2 * src));
+                const float4 ab = col_ldpair<RIN>(x, xs + (size_t)N2 * src);
                 v[a].re = make_float2(ab.x, ab.z);
                 v[a].im = make_float2(ab.y, ab.w);
             } else {
                 // SHIFT_IN rotates the input by n/2 = 16 rows: the two halves swap
-                const float4 lo = __ldg(reinterpret_cast<const float4*>(xs + (size_t)N2 * (a + (SHIFT_IN ? 16 : 0))));
-                const float4 hi = __ldg(reinterpret_cast<const float4*>(xs + (size_t)N2 * (a + (SHIFT_IN ? 0 : 16))));
+                const float4 lo = col_ldpair<RIN>(x, xs + (size_t)N2 * (a + (SHIFT_IN ? 16 : 0)));
+                const float4 hi = col_ldpair<RIN>(x, xs + (size_t)N2 * (a + (SHIFT_IN ? 0 : 16)));
                 cp l, g;
                 l.re = make_float2(lo.x, lo.z); l.im = make_float2(lo.y, lo.w);
                 g.re = make_float2(hi.x, hi.z); g.im = make_float2(hi.y, hi.w);
@@ -487,7 +508,7 @@ __global__ void __launch_bounds__(128) fftp_col16_kernel(const float2* __restric
 
 // NH = 2: 512-point columns, radix-2 step in front of the 256-point transform (two sweeps, see fftp_col16_kernel):
 // y_h[m] = (x[m] + (-1)^h x[m + 256]) W_512^{m h}, X[2k' + h] = DFT256(y_h)[k'].  Not usable in place.
-template <bool INV, bool SHIFT_IN, int NH>
+template <bool INV, bool SHIFT_IN, int NH, bool RIN = false>
 __global__ void __launch_bounds__(128, 5) fftp_col256_kernel(const float2* __restrict__ x, float2* __restrict__ tmp,
                                                              const float4* __restrict__ tws, int log2n2) {
     // n = 256 * NH * N2 points per sequence, N2 = 2^log2n2 = row length of the second pass
@@ -512,13 +533,13 @@ __global__ void __launch_bounds__(128, 5) fftp_col256_kernel(const float2* __res
         for (int a = 0; a < 16; a++) {
             if constexpr (NH == 1) {
                 const int src = SHIFT_IN ? (a ^ 8) : a;
-                const float4 ab = __ldg(reinterpret_cast<const float4*>(xs + (size_t)src * (16 * (size_t)N2)));
+                const float4 ab = col_ldpair<RIN>(x, xs + (size_t)src * (16 * (size_t)N2));
                 v[a].re = make_float2(ab.x, ab.z);
                 v[a].im = make_float2(ab.y, ab.w);
             } else {
                 const size_t r0 = (size_t)a * (16 * (size_t)N2), half = (size_t)256 * N2;
-                const float4 lo = __ldg(reinterpret_cast<const float4*>(xs + r0 + (SHIFT_IN ? half : 0)));
-                const float4 hh = __ldg(reinterpret_cast<const float4*>(xs + r0 + (SHIFT_IN ? 0 : half)));
+                const float4 lo = col_ldpair<RIN>(x, xs + r0 + (SHIFT_IN ? half : 0));
+                const float4 hh = col_ldpair<RIN>(x, xs + r0 + (SHIFT_IN ? 0 : half));
                 cp l, g;
                 l.re = make_float2(lo.x, lo.z); l.im = make_float2(lo.y, lo.w);
                 g.re = make_float2(hh.x, hh.z); g.im = make_float2(hh.y, hh.w);
@@ -633,11 +654,11 @@ const float* fftp_twiddles() {
     return dev;
 }
 
-template <int R0, int CL, bool INV, bool SI, bool SO, bool MAG, bool ROWS = false, int TQ = 0, int NATQ = 0>
+template <int R0, int CL, bool INV, bool SI, bool SO, bool MAG, bool ROWS = false, int TQ = 0, int NATQ = 0, bool RIN = false>
 int fftp_launch(const void* in, void* out, size_t rows, float scale, cudaStream_t st, int n1 = 1, int n2c = 1) {
     constexpr int NSB = R0 / CL;
     const size_t smem = (size_t)2 * NSB * FP_B_OF(NSB) * sizeof(float);
-    auto kern = fftp_kernel<R0, CL, INV, SI, SO, MAG, ROWS, TQ, NATQ>;
+    auto kern = fftp_kernel<R0, CL, INV, SI, SO, MAG, ROWS, TQ, NATQ, RIN>;
     static bool configured = false;   // per instantiation
     if (!configured) {
         BDSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -708,17 +729,17 @@ int fftp_rows_pass(const void* tmp, void* out, size_t groups, bool inverse, bool
               : fftp_launch<NR, 1, false, false, false, false, true>(tmp, out, groups, sc, st, n1);
 }
 
-template <bool INV, bool SI>
+template <bool INV, bool SI, bool RIN = false>
 int fftp_colpass(const void* in, void* tmp, int n1, int log2n2, size_t rows, cudaStream_t st) {
     const float* tw = fftp_twiddles();
     const float2* i2 = reinterpret_cast<const float2*>(in);
     float2* t2 = reinterpret_cast<float2*>(tmp);
     const float4* tws = reinterpret_cast<const float4*>(tw + FP_TW_SPLAT);
     const unsigned g16 = (unsigned)(rows * ((size_t)1 << (log2n2 - 8))), g256 = (unsigned)(rows * ((size_t)1 << (log2n2 - 4)));
-    if (n1 == 16) fftp_col16_kernel<INV, SI, 1><<<g16, 128, 0, st>>>(i2, t2, log2n2);
-    else if (n1 == 32) fftp_col16_kernel<INV, SI, 2><<<g16, 128, 0, st>>>(i2, t2, log2n2);
-    else if (n1 == 256) fftp_col256_kernel<INV, SI, 1><<<g256, 128, 0, st>>>(i2, t2, tws, log2n2);
-    else fftp_col256_kernel<INV, SI, 2><<<g256, 128, 0, st>>>(i2, t2, tws, log2n2);
+    if (n1 == 16) fftp_col16_kernel<INV, SI, 1, RIN><<<g16, 128, 0, st>>>(i2, t2, log2n2);
+    else if (n1 == 32) fftp_col16_kernel<INV, SI, 2, RIN><<<g16, 128, 0, st>>>(i2, t2, log2n2);
+    else if (n1 == 256) fftp_col256_kernel<INV, SI, 1, RIN><<<g256, 128, 0, st>>>(i2, t2, tws, log2n2);
+    else fftp_col256_kernel<INV, SI, 2, RIN><<<g256, 128, 0, st>>>(i2, t2, tws, log2n2);
     BDSP_CUDA_OK(cudaGetLastError());
     BDSP_LAUNCHED();
     return 0;
@@ -739,7 +760,8 @@ int fftp_rowsq_pass(const void* tmp, void* out, size_t groups, bool inverse, boo
 // two-pass packed transform for n = 2^16 and 2^20 (tmp: n*rows complex values, distinct from in; may equal out only
 // if out != in).  Returns 1 when the configuration is not covered.
 int fftp_two_pass_try(const void* in, void* out, void* tmp, size_t n, size_t rows, bool inverse, size_t in_rot, size_t out_rot,
-                      double scale, bool magnitude, cudaStream_t st) {
+                      double scale, bool magnitude, cudaStream_t st, bool real_in) {
+    if (real_in && (inverse || in_rot != 0)) return 1;
     // n = n1 * N2:  2^15 = 32 x 1024, 2^16 = 256 x 256, 2^17 = 256 x 512, 2^18 = 256 x 1024, 2^19 = 512 x 1024, 2^20 = 256 x 4096.
     // (two adjacent 2048-point rows give only 16-byte store runs: 16 x 2048 took 0.46 ms and 256 x 2048 0.48 ms per 2^26 points)
     // Last pass: 16/Q adjacent rows of N2 = 256*Q points per 128-thread CTA (Q = N2/256 <= 8), or four 4096-point rows per
@@ -758,7 +780,7 @@ int fftp_two_pass_try(const void* in, void* out, void* tmp, size_t n, size_t row
     if (n == (1u << 16) && split16) { n1 = 16; log2n2 = 12; }
     if ((in_rot != 0 && in_rot != n / 2) || (out_rot != 0 && out_rot != n / 2)) return 1;
     if (inverse && (magnitude || out_rot != 0)) return 1;
-    if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 7) || (reinterpret_cast<uintptr_t>(tmp) & 15)) return 1;
+    if ((reinterpret_cast<uintptr_t>(in) & (real_in ? 7 : 15)) || (reinterpret_cast<uintptr_t>(out) & 7) || (reinterpret_cast<uintptr_t>(tmp) & 15)) return 1;
     if (tmp == in || tmp == out) return 1;
     const int tq = log2n2 < 12 ? 1 << (log2n2 - 8) : 0;
     // rows per CTA in the 4096-point last pass: 4 (one 512-thread CTA per SM, full 32-byte store sectors) or 2 (two 256-thread
@@ -787,11 +809,12 @@ int fftp_two_pass_try(const void* in, void* out, void* tmp, size_t n, size_t row
     const size_t out_elem = magnitude ? sizeof(float) : sizeof(float2);
     for (size_t r0 = 0; r0 < rows; r0 += chunk) {
         const size_t nr = rows - r0 < chunk ? rows - r0 : chunk;
-        const void* cin = reinterpret_cast<const char*>(in) + r0 * n * sizeof(float2);
+        const void* cin = reinterpret_cast<const char*>(in) + r0 * n * (real_in ? sizeof(float) : sizeof(float2));
         void* cout = reinterpret_cast<char*>(out) + r0 * n * out_elem;
         const size_t groups_c = nr * (size_t)(n1 / rpc);
         int rc;
-        if (inverse) rc = si ? fftp_colpass<true, true>(cin, tmp, n1, log2n2, nr, st) : fftp_colpass<true, false>(cin, tmp, n1, log2n2, nr, st);
+        if (real_in) rc = fftp_colpass<false, false, true>(cin, tmp, n1, log2n2, nr, st);
+        else if (inverse) rc = si ? fftp_colpass<true, true>(cin, tmp, n1, log2n2, nr, st) : fftp_colpass<true, false>(cin, tmp, n1, log2n2, nr, st);
         else rc = si ? fftp_colpass<false, true>(cin, tmp, n1, log2n2, nr, st) : fftp_colpass<false, false>(cin, tmp, n1, log2n2, nr, st);
         if (rc) return rc;
         if (tq == 8) rc = fftp_rowsq_pass<8>(tmp, cout, groups_c, inverse, so, magnitude, sc, st, n1);
@@ -811,7 +834,8 @@ int fftp_two_pass_try(const void* in, void* out, void* tmp, size_t n, size_t row
 //   points (exactly the first pass of the two-pass transform of that length, in place), pass C: rows of N3 = 256*Q points,
 //   16/Q rows with consecutive k1 per CTA, stored at k1 + nA*k2 + nA*256*k3.
 int fftp_three_pass_try(const void* in, void* out, void* tmp, size_t n, size_t rows, bool inverse, size_t in_rot, size_t out_rot,
-                        double scale, bool magnitude, cudaStream_t st) {
+                        double scale, bool magnitude, cudaStream_t st, bool real_in) {
+    if (real_in && (inverse || in_rot != 0)) return 1;
     int nA, log2n3;
     switch (n) {
     case 1u << 21: nA = 16; log2n3 = 9; break;
@@ -822,7 +846,7 @@ int fftp_three_pass_try(const void* in, void* out, void* tmp, size_t n, size_t r
     }
     if ((in_rot != 0 && in_rot != n / 2) || (out_rot != 0 && out_rot != n / 2)) return 1;
     if (inverse && (magnitude || out_rot != 0)) return 1;
-    if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 7) || (reinterpret_cast<uintptr_t>(tmp) & 15)) return 1;
+    if ((reinterpret_cast<uintptr_t>(in) & (real_in ? 7 : 15)) || (reinterpret_cast<uintptr_t>(out) & 7) || (reinterpret_cast<uintptr_t>(tmp) & 15)) return 1;
     if (tmp == in || tmp == out) return 1;
     const int tq = 1 << (log2n3 - 8);
     if (rows * (n >> 4) > 0x7fffffffull) return 1;
@@ -830,7 +854,8 @@ int fftp_three_pass_try(const void* in, void* out, void* tmp, size_t n, size_t r
     int rc;
     int l2 = 0;
     while (((size_t)nA << l2) < n) l2++;                 // n / nA = 2^l2
-    if (inverse) rc = si ? fftp_colpass<true, true>(in, tmp, nA, l2, rows, st) : fftp_colpass<true, false>(in, tmp, nA, l2, rows, st);
+    if (real_in) rc = fftp_colpass<false, false, true>(in, tmp, nA, l2, rows, st);
+    else if (inverse) rc = si ? fftp_colpass<true, true>(in, tmp, nA, l2, rows, st) : fftp_colpass<true, false>(in, tmp, nA, l2, rows, st);
     else rc = si ? fftp_colpass<false, true>(in, tmp, nA, l2, rows, st) : fftp_colpass<false, false>(in, tmp, nA, l2, rows, st);
     if (rc) return rc;
     rc = inverse ? fftp_colpass<true, false>(tmp, tmp, 256, log2n3, rows * (size_t)nA, st) : fftp_colpass<false, false>(tmp, tmp, 256, log2n3, rows * (size_t)nA, st);
@@ -896,6 +921,35 @@ int fftp_try(const void* in, void* out, size_t n, size_t rows, bool inverse, siz
                                               : fftp_dispatch<2, 1>(in, out, rows, inverse, si, so, magnitude, sc, st);
     return fftp_cluster_mode() == 2 ? fftp_dispatch<4, 2>(in, out, rows, inverse, si, so, magnitude, sc, st)
                                : fftp_dispatch<4, 1>(in, out, rows, inverse, si, so, magnitude, sc, st);
+}
+
+// real-input forward transforms (fftp_kernel<RIN>): rows of `n` real scalars, n in {512 ... 16384}
+template <int R0, int Q>
+int fftp_dispatch_real(const void* in, void* out, size_t groups, bool shift_out, bool mag, float scale, cudaStream_t st) {
+    if (mag) return shift_out ? fftp_launch<R0, 1, false, false, true, true, false, 0, Q, true>(in, out, groups, scale, st)
+                              : fftp_launch<R0, 1, false, false, false, true, false, 0, Q, true>(in, out, groups, scale, st);
+    return shift_out ? fftp_launch<R0, 1, false, false, true, false, false, 0, Q, true>(in, out, groups, scale, st)
+                     : fftp_launch<R0, 1, false, false, false, false, false, 0, Q, true>(in, out, groups, scale, st);
+}
+
+int fftp_try_real(const void* in, void* out, size_t n, size_t rows, size_t out_rot, double scale, bool magnitude, cudaStream_t st) {
+    if (n != 512 && n != 1024 && n != 2048 && n != 4096 && n != 8192 && n != 16384) return 1;
+    if (out_rot != 0 && out_rot != n / 2) return 1;
+    if ((reinterpret_cast<uintptr_t>(in) & 7) || (reinterpret_cast<uintptr_t>(out) & 7) || in == out) return 1;
+    const size_t per = n < 4096 ? 4096 / n : 1;
+    if (rows % per != 0) return 1;
+    const size_t groups = rows / per;
+    if (groups * 2 > 0x7fffffffull) return 1;
+    const bool so = out_rot != 0;
+    const float sc = (float)scale;
+    switch (n) {
+    case 512: return fftp_dispatch_real<1, 2>(in, out, groups, so, magnitude, sc, st);
+    case 1024: return fftp_dispatch_real<1, 4>(in, out, groups, so, magnitude, sc, st);
+    case 2048: return fftp_dispatch_real<1, 8>(in, out, groups, so, magnitude, sc, st);
+    case 4096: return fftp_dispatch_real<1, 0>(in, out, groups, so, magnitude, sc, st);
+    case 8192: return fftp_dispatch_real<2, 0>(in, out, groups, so, magnitude, sc, st);
+    default: return fftp_dispatch_real<4, 0>(in, out, groups, so, magnitude, sc, st);
+    }
 }
 
 }  // namespace bdsp

@@ -101,7 +101,7 @@ def test_real_input_fft(n):  # tests/real_test.rs:581-605
     assert o.rel_l2(got, o.plain_fft(x)) <= tol(n, np.float32)
 
 
-@pytest.mark.parametrize("n,rows", [(1024, 256), (4096, 64), (1 << 16, 4), (512, 7)])
+@pytest.mark.parametrize("n,rows", [(512, 128), (1024, 256), (2048, 32), (4096, 64), (8192, 8), (16384, 4), (1 << 15, 4), (1 << 16, 4), (1 << 19, 2), (1 << 20, 2), (1 << 22, 1), (512, 7)])
 def test_real_input_rows(n, rows):
     """rows of real scalars (BDSP_F_REAL_INPUT): complexifying pass + packed passes in the throughput regime."""
     rng = np.random.default_rng(n + rows)
@@ -115,6 +115,9 @@ def test_real_input_rows(n, rows):
     assert o.rel_l2(out.to_numpy().reshape(rows, n), ref) <= tol(n, np.float32)
     assert L.bdsp_fft_rows_c32(pin, pout, n, rows, bd.F_REAL_INPUT | bd.F_SHIFT) == 0
     assert o.rel_l2(out.to_numpy().reshape(rows, n), np.fft.fftshift(ref, axes=1)) <= tol(n, np.float32)
+    mag = DspVec.zeros(n * rows, dtype=np.float32)
+    assert L.bdsp_fft_rows_c32(pin, mag._fn("bdsp_device_ptr")(mag._h), n, rows, bd.F_REAL_INPUT | bd.F_SHIFT | bd.F_MAGNITUDE) == 0
+    assert o.rel_l2(mag.to_numpy().reshape(rows, n), np.abs(np.fft.fftshift(ref, axes=1))) <= tol(n, np.float32)
 
 
 def test_fft_wrong_domain_marks_invalid():
