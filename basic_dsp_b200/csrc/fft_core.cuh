@@ -111,20 +111,33 @@ template <typename T, int R, bool INV, int MAXB>
 __device__ __forceinline__ void stockham_stage_strided(typename CpxOf<T>::type* s, int n, int nfft, int sstride, int Ns,
                                                        const typename CpxOf<T>::type* __restrict__ tw) {
     typedef typename CpxOf<T>::type C;
-    const int bpf = n / R;            // butterflies per sequence
+    const int bpf = n / R;            // butterflies per sequence (a power of two)
+    const int lbpf = 31 - __clz(bpf);
     const int total = bpf * nfft;     // butterflies in this CTA
+    // spad(a + b) = spad(a) + b + (b >> 4) when b is a multiple of 16: element strides that are multiples of 16 turn the
+    // per-element padding into one constant stride
+    const bool ld_fast = (bpf & 15) == 0;
+    const int ld_stride = bpf + (bpf >> 4);
+    const bool st_fast = (Ns & 15) == 0 || (Ns == 1 && (R == 8 || R == 16));
+    const int st_stride = Ns == 1 ? 1 : Ns + (Ns >> 4);
     C v[MAXB][R];
     const int tw_scale = BDSP_TW_LEN / (Ns * R);
 #pragma unroll
     for (int b = 0; b < MAXB; b++) {
         int w = threadIdx.x + b * blockDim.x;
         if (w < total) {
-            int f = w / bpf, j = w - f * bpf;
+            int f = w >> lbpf, j = w & (bpf - 1);
             int k = j & (Ns - 1);
             const C* src = s;
             int base = f * sstride + j;
+            if (ld_fast) {
+                const C* p0 = src + spad(base);
 #pragma unroll
-            for (int r = 0; r < R; r++) v[b][r] = src[spad(base + r * bpf)];
+                for (int r = 0; r < R; r++) v[b][r] = p0[r * ld_stride];
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; r++) v[b][r] = src[spad(base + r * bpf)];
+            }
             if (Ns > 1) {
                 // one table load (W^k) per butterfly; the powers W^{k r} are products A_a * B_b, r = a + 4b
                 // (depth <= 4).  R - 1 scattered table loads per butterfly made this stage L1-bound.
@@ -161,11 +174,17 @@ __device__ __forceinline__ void stockham_stage_strided(typename CpxOf<T>::type* 
     for (int b = 0; b < MAXB; b++) {
         int w = threadIdx.x + b * blockDim.x;
         if (w < total) {
-            int f = w / bpf, j = w - f * bpf;
+            int f = w >> lbpf, j = w & (bpf - 1);
             int k = j & (Ns - 1);
             int obase = f * sstride + (j - k) * R + k;
+            if (st_fast) {
+                C* p0 = s + spad(obase);
 #pragma unroll
-            for (int r = 0; r < R; r++) s[spad(obase + r * Ns)] = v[b][r];
+                for (int r = 0; r < R; r++) p0[r * st_stride] = v[b][r];
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; r++) s[spad(obase + r * Ns)] = v[b][r];
+            }
         }
     }
     __syncthreads();
