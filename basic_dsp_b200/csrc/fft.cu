@@ -251,6 +251,9 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? 1024 : 512, (sizeof(T) == 8 &
         constexpr int UN = 8;
         const bool contiguous = p.in_point_stride == 1;
         const int lct = __ffs(ct) - 1;
+        const int in_ls = (int)p.in_lane_stride, in_ps = (int)p.in_point_stride;
+        const long long in_seq0 = o1 * p.in_o1_stride + lane0 * p.in_lane_stride + p.in_rot;
+        const long long in_b0 = b * p.in_batch_stride;
         for (int base = threadIdx.x; base < total; base += blockDim.x * UN) {
             C v[UN];
 #pragma unroll
@@ -260,10 +263,11 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? 1024 : 512, (sizeof(T) == 8 &
                     int l, pt;
                     if (contiguous) { l = idx >> p.log2m; pt = idx & (m - 1); }
                     else { pt = idx >> lct; l = idx & (ct - 1); }
-                    long long g = o1 * p.in_o1_stride + (lane0 + l) * p.in_lane_stride + (long long)pt * p.in_point_stride;
-                    g += p.in_rot; if (g >= p.in_n) g -= p.in_n;
-                    if (p.real_input) { v[u].x = reinterpret_cast<const T*>(p.in)[b * p.in_batch_stride + g]; v[u].y = 0; }
-                    else v[u] = reinterpret_cast<const C*>(p.in)[b * p.in_batch_stride + g];
+                    // 32 x 32 -> 64-bit products (strides are below 2^31: sequences have fewer than 2^31 points)
+                    long long g = in_seq0 + (long long)l * in_ls + (long long)pt * in_ps;
+                    if (g >= p.in_n) g -= p.in_n;
+                    if (p.real_input) { v[u].x = reinterpret_cast<const T*>(p.in)[in_b0 + g]; v[u].y = 0; }
+                    else v[u] = reinterpret_cast<const C*>(p.in)[in_b0 + g];
                 }
             }
 #pragma unroll
@@ -324,18 +328,19 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? 1024 : 512, (sizeof(T) == 8 &
     }
     const bool lane_major = (p.out_lane_stride <= p.out_point_stride);
     const int lct = __ffs(ct) - 1;
+    const int out_ls = (int)p.out_lane_stride, out_ps = (int)p.out_point_stride;
+    const long long out_seq0 = o1 * p.out_o1_stride + lane0 * p.out_lane_stride;
 #pragma unroll 4
     for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
         int l, k;
         if (lane_major) { k = idx >> lct; l = idx & (ct - 1); }
         else { l = idx >> p.log2m; k = idx & (m - 1); }
         C v = s[spad(l * sstride + k)];
-        const long long lane = lane0 + l;
         if (p.tw_n) {
             const C w = cmul(twA[l * 33 + (k & 31)], twB[l * nbs + (k >> 5)]);
             v = cmul(v, w);
         }
-        long long local = o1 * p.out_o1_stride + lane * p.out_lane_stride + (long long)k * p.out_point_stride;
+        long long local = out_seq0 + (long long)l * out_ls + (long long)k * out_ps;
         if (p.last) {
             long long a = out_addr(p.om, b, local);
             if (p.magnitude) reinterpret_cast<T*>(p.out)[a] = mag_of(v.x, v.y);
