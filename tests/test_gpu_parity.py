@@ -772,3 +772,25 @@ def test_streams_do_not_share_workspace():
         assert o.rel_l2(v.to_numpy(), x) <= 8 * tol(n, np.float32)
     for st in streams:
         L.bdsp_stream_destroy(st)
+
+
+@pytest.mark.parametrize("log2n", [20, 24])
+def test_large_transform_properties(log2n):
+    """size-independent properties at the BASELINE / maximum sizes: Parseval, linearity, fft -> ifft round trip."""
+    n = 1 << log2n
+    rng = np.random.default_rng(1000 + log2n)
+    x = rand_c(rng, n, np.float32)
+    y = rand_c(rng, n, np.float32)
+    X = DspVec(x).plain_fft().to_numpy().astype(np.complex128)
+    Y = DspVec(y).plain_fft().to_numpy().astype(np.complex128)
+    e_time = float(np.sum(np.abs(x.astype(np.complex128)) ** 2))
+    assert abs(float(np.sum(np.abs(X) ** 2)) / n - e_time) <= 1e-5 * e_time                     # Parseval
+    Z = DspVec((x + 2 * y).astype(np.complex64)).plain_fft().to_numpy().astype(np.complex128)
+    assert o.rel_l2(Z, X + 2 * Y) <= 2 * tol(n, np.float32)                                    # linearity
+    back = DspVec(x).fft().ifft().to_numpy()
+    assert o.rel_l2(back, x) <= 2 * tol(n, np.float32)                                         # round trip
+    # a pure tone lands in one bin
+    k0 = 12345
+    tone = np.exp(2j * np.pi * k0 * np.arange(n) / n).astype(np.complex64)
+    T = np.abs(DspVec(tone).plain_fft().to_numpy())
+    assert int(np.argmax(T)) == k0 and abs(T[k0] / n - 1) < 1e-3
