@@ -94,7 +94,8 @@ fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, long long row
     constexpr bool PREFETCH = FP_PREFETCH && (CL == 1 && R0 > 1);
     // CL > 1 without a cluster (FP_DUP): the CL CTAs of a row each run the first stage over ALL columns (the second
     // reader is served by L2) and keep only their own NSB sub-blocks: no distributed shared memory, no cluster barrier,
-    // and CL smaller CTAs per row that overlap their phases on the SM.
+    // and CL smaller CTAs per row that overlap their phases on the SM.  Measured on B200 (C3): one CTA 0.278 ms, two CTAs
+    // 0.293 ms, four CTAs (four reads of the row through L2) 0.461 ms.
     constexpr bool DUP = FP_DUP && CL > 1;
     constexpr int NU = R0 > 1 ? (2048 / (DUP ? 1 : CL)) / NT : 1;   // column pairs per thread in F0
     float4 raw[PREFETCH ? NU * R0 : 1];
