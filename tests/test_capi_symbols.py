@@ -103,3 +103,27 @@ def test_cpp_host_mirror_runs_on_gpu(tmp_path, libpath):
     exe = _build_cpp(tmp_path, libpath)
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "roundtrip" in out.stdout, out.stdout + out.stderr
+
+
+def _build_c_example(tmp_path, libpath):
+    exe = str(tmp_path / "c_example")
+    src = os.path.join(ROOT, "examples", "c_example.c")
+    cmd = ["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
+           "-L", os.path.dirname(libpath), "-lbasic_dsp_b200", "-Wl,-rpath," + os.path.dirname(libpath), "-lm"]
+    subprocess.check_call(cmd)
+    return exe
+
+
+def test_header_is_valid_c11_and_the_c_example_links(tmp_path, libpath):
+    """include/basic_dsp_b200.h is a C header (the reference's ABI is consumed from C, C#, Python ...)."""
+    _build_c_example(tmp_path, libpath)
+
+
+@pytest.mark.gpu
+def test_c_example_runs_on_gpu(tmp_path, libpath):
+    exe = _build_c_example(tmp_path, libpath)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "spectrum peak" in out.stdout, out.stdout + out.stderr
+    # cos(0.001 n) over 2^16 points: energy next to DC, which fft32 places at the centre bin
+    idx = int(out.stdout.split("at bin")[1].split()[0])
+    assert abs(idx - 32768) <= 12
