@@ -1,14 +1,22 @@
-// Packed-FP32x2 shared-memory FFT for c32 sequences of n = 4096 * R0 points, R0 in {1, 2, 4}
-// (4096, 8192, 16384): natural order in, natural order out, one HBM read and one HBM write per point.
-// Same building blocks as the fused overlap-save kernel (ols4096.cuh):
-//   F0  radix-R0 DIF over stride 4096 (global -> shared), twiddle W_n^{k0' c}
+// Packed-FP32x2 shared-memory FFT kernels for c32 (and real f32 input) sequences.
+//
+// fftp_kernel: one 128-thread group per 4096 points, same building blocks as the fused overlap-save kernel (ols4096.cuh):
+//   F0  radix-R0 DIF over stride 4096 (global -> shared), twiddle W_n^{k0' c}          (n = 4096*R0, R0 in {2, 4})
 //   F1  radix-16 DIF over stride 256, F2 radix-16 DIF over stride 16 (in place in shared memory)
 //   F3  radix-16 DIF over 16 contiguous points in registers -> global, natural order
 //       (output k = k0' + R0*(k0 + 16*k1 + 256*k2); lanes walk k0', k0 so that stores coalesce)
-// With CL = 2 a sequence is split over a thread-block CLUSTER of two CTAs: each CTA owns R0/2 of the
-// 4096-point sub-transforms and the F0 results that belong to the partner are written straight into
-// its shared memory (distributed shared memory), so that three CTAs fit on an SM and the load / compute
-// / store phases of different sequences overlap.
+// Modes (template parameters):
+//   plain     n = 4096 / 8192 / 16384, one sequence per CTA (R0 = 1, 2, 4)
+//   NATQ = Q  16/Q sequences of 256*Q points per CTA (512, 1024, 2048): F1 becomes a radix-Q step inside every sequence
+//   ROWS      last pass of a multi-pass transform: four adjacent 4096-point rows per CTA, transposing store
+//   TQ = Q    last pass with 16/Q adjacent rows of 256*Q points per CTA (128 threads), transposing store
+//   RIN       the input holds real scalars
+//   CL = 2    (measured, not default) two CTAs per sequence, as a thread-block cluster with distributed shared memory or,
+//             with FP_DUP, as two independent CTAs that each repeat F0
+// fftp_col16_kernel / fftp_col256_kernel: first pass(es) of the multi-pass transforms: 16- / 256-point (NH = 2: 32- / 512-point)
+//   columns of 16 adjacent columns per CTA, inter-pass twiddle evaluated with sincospif on exact arguments.
+// Dispatchers: fftp_try (single pass), fftp_try_real, fftp_two_pass_try (2^15..2^20), fftp_three_pass_try (2^21..2^24),
+//   fftp_rows1k_try (packed last pass behind a generic column pass).
 // Replaces rustfft for these lengths (vector/src/vector_types/time_freq/mod.rs:45-58) incl. the fused
 // fft_shift (time_to_freq.rs:163), ifft's scale + ifft_shift (freq_to_time.rs:165-167) and magnitude.
 #include <cooperative_groups.h>
