@@ -620,6 +620,8 @@ template <typename T> Res<T> op_window_fn(Vec<T>* v, const WinFn<T>& w, bool una
     if (v->domain != 0) { mark_invalid(v); return done(v, 0); }
     const size_t points = points_of(v);
     if (!points) return done(v, 0);
+    // built-in windows are evaluated on the device (no host work, no table); callbacks through a host-built table
+    if (!w.fn) return done(v, ew_window<T>(v->d, points, v->is_complex, w.kind < 0 || w.kind > 2 ? 3 : w.kind, unapply, g_stream));
     std::vector<T> tab(points);
     for (size_t i = 0; i < points; i++) {
         const size_t j = !w.symmetric || i < (points + 1) / 2 ? i : points - 1 - i;

@@ -253,6 +253,35 @@ __global__ void mul_freq_resp_kernel(T* __restrict__ data, long long points, int
     }
 }
 
+
+// apply_window / unapply_window for the built-in windows (window_functions.rs:25-129; time.rs:33-66; symmetric windows are
+// evaluated for the first half and mirrored, vector_types/mod.rs:528-598), evaluated on the device in precision T
+template <typename T> __device__ __forceinline__ T window_value_dev(int kind, long long n, long long length) {
+    const T one = (T)1, two = (T)2, pi = (T)3.14159265358979323846;
+    const T nn = (T)n, ln = (T)length;
+    if (kind == 0) return one - fabs((nn - (ln - one) / two) / (ln / two));
+    if (kind == 1) { const T alpha = (T)0.54; return alpha - (one - alpha) * cos(two * pi * nn / (ln - one)); }
+    if (kind == 2)
+        return (T)0.35875 - (T)0.48829 * cos(two * pi * nn / (ln - one)) + (T)0.14128 * cos((T)4 * pi * nn / (ln - one)) -
+               (T)0.01168 * cos((T)6 * pi * nn / (ln - one));
+    return one;
+}
+template <typename T>
+__global__ void window_kernel(T* __restrict__ data, long long points, int is_complex, int kind, int unapply) {
+    typedef Arith<T> A;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < points; i += stride) {
+        const long long j = i < (points + 1) / 2 ? i : points - 1 - i;
+        T w = window_value_dev<T>(kind, j, points);
+        if (unapply) w = A::div((T)1, w);
+        if (is_complex) {
+            typedef typename CpxOf<T>::type C;
+            reinterpret_cast<C*>(data)[i] = cmul_nofma(reinterpret_cast<C*>(data)[i], mk<T>(w, (T)0));
+        } else data[i] = A::mul(data[i], w);
+    }
+}
+
 // X[i] *= table[i] (complex or real table) - host-evaluated custom responses / windows
 template <typename T>
 __global__ void mul_table_kernel(T* __restrict__ data, const T* __restrict__ table, long long points, int is_complex, int table_complex) {
@@ -453,6 +482,15 @@ int ew_mul_freq_resp(void* data, size_t points, int is_complex, int kind, double
     return 0;
 }
 
+
+template <typename T>
+int ew_window(void* data, size_t points, int is_complex, int kind, int unapply, cudaStream_t st) {
+    if (!points) return 0;
+    window_kernel<T><<<ew_grid((long long)points, 256), 256, 0, st>>>(reinterpret_cast<T*>(data), (long long)points, is_complex, kind, unapply);
+    BDSP_LAUNCHED();
+    return 0;
+}
+
 template <typename T>
 int ew_mul_table(void* data, const void* table, size_t points, int is_complex, int table_complex, cudaStream_t st) {
     mul_table_kernel<T><<<ew_grid((long long)points, 256), 256, 0, st>>>(reinterpret_cast<T*>(data), reinterpret_cast<const T*>(table), (long long)points, is_complex, table_complex);
@@ -504,6 +542,7 @@ int ew_mul_cexp(void* data, size_t points, double a, double b, cudaStream_t st) 
     template int ew_reverse<T>(const void*, void*, size_t, int, cudaStream_t);                            \
     template int ew_decimate<T>(const void*, void*, size_t, size_t, size_t, int, cudaStream_t);           \
     template int ew_mul_freq_resp<T>(void*, size_t, int, int, double, double, cudaStream_t);              \
+    template int ew_window<T>(void*, size_t, int, int, int, cudaStream_t);                                \
     template int ew_mul_table<T>(void*, const void*, size_t, int, int, cudaStream_t);
 BDSP_INST(float)
 BDSP_INST(double)

@@ -25,6 +25,7 @@ template <typename T> int ew_resample_spectrum(const void* in, void* out, size_t
                                                double phase_inc, int use_phase, cudaStream_t st);
 template <typename T> int ew_mirror(const void* in, void* out, size_t points, cudaStream_t st);
 template <typename T> int ew_mul_cexp(void* data, size_t points, double a, double b, cudaStream_t st);
+template <typename T> int ew_window(void* data, size_t points, int is_complex, int kind, int unapply, cudaStream_t st);
 template <typename T> int ew_mul_table(void* data, const void* table, size_t points, int is_complex, int table_complex, cudaStream_t st);
 
 }  // namespace bdsp
