@@ -828,11 +828,16 @@ template <typename T> Res<T> op_interpolatei(Vec<T>* v, const RealFn<T>& f, bool
     FftOpts fw;
     rc = fft_exec<T>(v->d, v->scratch, points, 1, fw, nullptr, 0, g_stream);
     if (rc) return done(v, rc);
-    std::vector<T> tab = shifted_response_table<T>(f, is_symmetric, points, (T)factor);
-    T* dev = nullptr;
-    rc = upload_table(tab, &dev);
-    if (!rc) rc = ew_mul_table<T>(v->scratch, dev, points, 1, 0, g_stream);
-    table_consumed();
+    if (f.kind != 2 && is_symmetric) {
+        // built-in responses: evaluated on the device (no O(points) host work, no table upload)
+        rc = ew_mul_shifted_resp<T>(v->scratch, points, f.kind, (double)f.rolloff, (double)(T)factor, g_stream);
+    } else {
+        std::vector<T> tab = shifted_response_table<T>(f, is_symmetric, points, (T)factor);
+        T* dev = nullptr;
+        rc = upload_table(tab, &dev);
+        if (!rc) rc = ew_mul_table<T>(v->scratch, dev, points, 1, 0, g_stream);
+        table_consumed();
+    }
     if (rc) return done(v, rc);
     FftOpts inv;
     inv.inverse = 1;
@@ -874,8 +879,10 @@ template <typename T> Res<T> op_interpolate(Vec<T>* v, const RealFn<T>* f, bool 
     bool have_table = false;
     double scale = 1.0;
     int use_scale = 0;
+    int resp_kind = -1;
     if (dest_points > n) {
-        if (f) {
+        if (f && f->kind != 2 && is_symmetric) resp_kind = f->kind;      // built-in response: evaluated on the device
+        else if (f) {
             std::vector<T> tab = shifted_response_table<T>(*f, is_symmetric, dest_points, factor);
             rc = upload_table(tab, &dev);
             if (rc) return done(v, rc);
@@ -887,7 +894,8 @@ template <typename T> Res<T> op_interpolate(Vec<T>* v, const RealFn<T>* f, bool 
     }
     const T pi = (T)M_PI;
     const T phase_inc = (T)2 * pi * (delay / delta_t) / (T)n;
-    rc = ew_resample_spectrum<T>(v->scratch, v->d, n, dest_points, dev, scale, use_scale, (double)phase_inc, delay != (T)0, g_stream);
+    rc = ew_resample_spectrum<T>(v->scratch, v->d, n, dest_points, dev, scale, use_scale, (double)phase_inc, delay != (T)0, resp_kind,
+                                 f ? (double)f->rolloff : 0.0, (double)factor, g_stream);
     if (have_table) table_consumed();
     if (rc) return done(v, rc);
     FftOpts inv;

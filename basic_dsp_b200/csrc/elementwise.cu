@@ -299,6 +299,36 @@ __global__ void mul_table_kernel(T* __restrict__ data, const T* __restrict__ tab
 }
 
 
+
+// multiplier of multiply_function_priv with is_fft_shifted = true for the built-in frequency responses
+// (time_freq/mod.rs:612-723, fft_swap_x :67-78; symmetric: first half evaluated, second half mirrored):
+// ratio * f(x * ratio), x = 1 + (i' - mx)/mx for the mirrored index i' <= mx
+template <typename T> __device__ __forceinline__ T shifted_resp_dev(long long i, long long points, int kind, T rolloff, T ratio) {
+    const long long offset = points % 2;
+    const long long c = (points - offset) / 2;
+    const T mx = (T)(points - offset) / (T)2;
+    const long long ip = i <= c ? i : (offset == 0 ? points - i : points - 1 - i);
+    const T j = -mx + (T)ip;
+    const T xv = j <= (T)0 ? (T)1 + j / mx : -(mx - j + (T)1) / mx;
+    const T x = xv * ratio;
+    const T ax = fabs(x);
+    T f;
+    if (kind == 0) f = ax <= (T)1 ? (T)1 : (T)0;
+    else {
+        const T one = (T)1, two = (T)2, pi = (T)3.14159265358979323846;
+        if (ax <= (one - rolloff)) f = one;
+        else if (ax <= (one + rolloff)) f = one / two * (one + cos(pi / rolloff * (ax - (one - rolloff)) / two));
+        else f = (T)0;
+    }
+    return ratio * f;
+}
+template <typename T>
+__global__ void mul_shifted_resp_kernel(typename CpxOf<T>::type* __restrict__ data, long long points, int kind, T rolloff, T ratio) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < points; i += stride) data[i] = cmul_nofma(data[i], mk<T>(shifted_resp_dev<T>(i, points, kind, rolloff, ratio), (T)0));
+}
+
 // ---- FFT-based resampling: spectrum re-binning (interpolation.rs:541-604) ----------------------------
 // out[k] (dest bins) = in[src(k)] * phase(src) * (table ? table[k] : 1) * scale, zero where the padded
 // spectrum has no source bin.  n > dest: keep the first ceil(dest/2) and last floor(dest/2) bins;
@@ -307,7 +337,7 @@ __global__ void mul_table_kernel(T* __restrict__ data, const T* __restrict__ tab
 template <typename T>
 __global__ void resample_spectrum_kernel(const typename CpxOf<T>::type* __restrict__ in, typename CpxOf<T>::type* __restrict__ out,
                                          long long n, long long dest, const T* __restrict__ table, T scale, int use_scale,
-                                         double phase_inc, int use_phase) {
+                                         double phase_inc, int use_phase, int resp_kind, T resp_rolloff, T resp_ratio) {
     typedef typename CpxOf<T>::type C;
     typedef Arith<T> A;
     long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -331,6 +361,7 @@ __global__ void resample_spectrum_kernel(const typename CpxOf<T>::type* __restri
                 v = cmul_nofma(v, mk<T>((T)cs, (T)sn));
             }
             if (table) { const T w = table[k]; v = cmul_nofma(v, mk<T>(w, (T)0)); }
+            else if (resp_kind >= 0) v = cmul_nofma(v, mk<T>(shifted_resp_dev<T>(k, dest, resp_kind, resp_rolloff, resp_ratio), (T)0));
             if (use_scale) { v.x = A::mul(v.x, scale); v.y = A::mul(v.y, scale); }
         }
         out[k] = v;
@@ -501,14 +532,25 @@ int ew_mul_table(void* data, const void* table, size_t points, int is_complex, i
 
 template <typename T>
 int ew_resample_spectrum(const void* in, void* out, size_t n, size_t dest, const void* table, double scale, int use_scale,
-                         double phase_inc, int use_phase, cudaStream_t st) {
+                         double phase_inc, int use_phase, int resp_kind, double resp_rolloff, double resp_ratio, cudaStream_t st) {
     typedef typename CpxOf<T>::type C;
     if (!dest) return 0;
     resample_spectrum_kernel<T><<<ew_grid((long long)dest, 256), 256, 0, st>>>(reinterpret_cast<const C*>(in), reinterpret_cast<C*>(out),
-        (long long)n, (long long)dest, reinterpret_cast<const T*>(table), (T)scale, use_scale, phase_inc, use_phase);
+        (long long)n, (long long)dest, reinterpret_cast<const T*>(table), (T)scale, use_scale, phase_inc, use_phase, resp_kind,
+        (T)resp_rolloff, (T)resp_ratio);
     BDSP_LAUNCHED();
     return 0;
 }
+
+template <typename T>
+int ew_mul_shifted_resp(void* data, size_t points, int kind, double rolloff, double ratio, cudaStream_t st) {
+    typedef typename CpxOf<T>::type C;
+    if (!points) return 0;
+    mul_shifted_resp_kernel<T><<<ew_grid((long long)points, 256), 256, 0, st>>>(reinterpret_cast<C*>(data), (long long)points, kind, (T)rolloff, (T)ratio);
+    BDSP_LAUNCHED();
+    return 0;
+}
+
 template <typename T>
 int ew_mirror(const void* in, void* out, size_t points, cudaStream_t st) {
     typedef typename CpxOf<T>::type C;
@@ -527,7 +569,8 @@ int ew_mul_cexp(void* data, size_t points, double a, double b, cudaStream_t st) 
 }
 
 #define BDSP_INST(T)                                                                                     \
-    template int ew_resample_spectrum<T>(const void*, void*, size_t, size_t, const void*, double, int, double, int, cudaStream_t); \
+    template int ew_resample_spectrum<T>(const void*, void*, size_t, size_t, const void*, double, int, double, int, int, double, double, cudaStream_t); \
+    template int ew_mul_shifted_resp<T>(void*, size_t, int, double, double, cudaStream_t);            \
     template int ew_mirror<T>(const void*, void*, size_t, cudaStream_t);                                  \
     template int ew_mul_cexp<T>(void*, size_t, double, double, cudaStream_t);                             \
     template int ew_scalar<T>(int, const void*, void*, size_t, double, cudaStream_t);                     \

@@ -21,8 +21,10 @@ template <typename T> int ew_fill(void* out, size_t n, double v, cudaStream_t st
 template <typename T> int ew_reverse(const void* in, void* out, size_t n_elems, int esz, cudaStream_t st);
 template <typename T> int ew_decimate(const void* in, void* out, size_t out_elems, size_t factor, size_t delay, int esz, cudaStream_t st);
 template <typename T> int ew_mul_freq_resp(void* data, size_t points, int is_complex, int kind, double rolloff, double ratio, cudaStream_t st);
+// table == nullptr and resp_kind >= 0: built-in frequency response (0 sinc, 1 raised cosine) evaluated on the device
 template <typename T> int ew_resample_spectrum(const void* in, void* out, size_t n, size_t dest, const void* table, double scale, int use_scale,
-                                               double phase_inc, int use_phase, cudaStream_t st);
+                                               double phase_inc, int use_phase, int resp_kind, double resp_rolloff, double resp_ratio, cudaStream_t st);
+template <typename T> int ew_mul_shifted_resp(void* data, size_t points, int kind, double rolloff, double ratio, cudaStream_t st);
 template <typename T> int ew_mirror(const void* in, void* out, size_t points, cudaStream_t st);
 template <typename T> int ew_mul_cexp(void* data, size_t points, double a, double b, cudaStream_t st);
 template <typename T> int ew_window(void* data, size_t points, int is_complex, int kind, int unapply, cudaStream_t st);
