@@ -379,7 +379,11 @@ fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, long long row
 #pragma unroll 1
     for (int half = 0; half < 2; half++) {
         const int gl = t + NT * half;                 // local group index: lsb + NSB*(k0 + 16*k1)
-        const int lsb = gl % NSB, k0 = (gl / NSB) & 15, k1 = gl / (16 * NSB);
+        // NATQ: lanes take the low 3 bits of k0 and the low 2 bits of k1 (quarter-warps still walk k0: conflict-free 128-bit
+        // loads), so that one store instruction writes 4*Q-point runs (16 consecutive results for 1024-point rows)
+        const int lsb = gl % NSB;
+        const int k0 = NATQ ? ((gl & 7) | (((gl >> 5) & 1) << 3)) : (gl / NSB) & 15;
+        const int k1 = NATQ ? (((gl >> 3) & 3) | ((gl >> 6) << 2)) : gl / (16 * NSB);
         const int r = fp_rot(k0, k1);
         const int base = lsb * FP_B + 272 * k0 + 16 * k1;
         cp P[8];
