@@ -644,7 +644,7 @@ int fft_any(const void* in, void* out, size_t n, size_t batch, const FftOpts& o,
     const long long in_rot = (long long)(o.in_rot % n);
     const T scale = (T)o.scale;
     if (is_pow2(n)) {
-        if (sizeof(T) == 4 && o.real_input && !INV && in_rot == 0 && n >= 512 && n <= 16384 && n * batch >= (1u << 16)) {
+        if (sizeof(T) == 4 && o.real_input && !INV && in_rot == 0 && n >= 256 && n <= 16384 && n * batch >= (1u << 16)) {
             // rows of real scalars, single pass: the packed kernel loads the reals directly (4 B read + 8 B written per point)
             const int rc = fftp_try_real(in, out, n, batch, (size_t)om.rot, o.scale, o.magnitude != 0, st);
             if (rc <= 0) return rc;
@@ -660,7 +660,7 @@ int fft_any(const void* in, void* out, size_t n, size_t batch, const FftOpts& o,
             oc.real_input = 0;
             return fft_any<T, INV>(cx, out, n, batch, oc, work, work_bytes, st);
         }
-        if (sizeof(T) == 4 && !o.real_input && n >= 512 && n <= 16384) {
+        if (sizeof(T) == 4 && !o.real_input && n >= 256 && n <= 16384) {
             // packed-FP32x2 kernel (fftp.cu); returns 1 when the configuration is not covered
             const int rc = fftp_try(in, out, n, batch, INV, (size_t)in_rot, (size_t)om.rot, o.scale, o.magnitude != 0, st);
             if (rc <= 0) return rc;

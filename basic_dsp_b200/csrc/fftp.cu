@@ -61,7 +61,7 @@ __device__ __forceinline__ int fp_rot(int row, int g) { return (((g >> 1) + (row
 // the transposing stores fill 32-byte (Q = 4) or 64-byte (Q = 2) runs.
 // RIN = true (forward, no ROWS): `x` holds REAL scalars (one float per point); the first stage loads two adjacent reals
 // per column pair and the imaginary parts start as zero.
-// NATQ = Q in {2, 4, 8} (R0 = 1, no ROWS): the CTA's 4096 contiguous points are 16/Q independent rows of 256*Q points
+// NATQ = Q in {1, 2, 4, 8} (R0 = 1, no ROWS): the CTA's 4096 contiguous points are 16/Q independent rows of 256*Q points
 // (k0 = q + Q*row); the first stage is a radix-Q butterfly inside every row, results are stored in natural order.
 // Batched 512 / 1024 / 2048-point transforms with the structure of the 4096-point kernel.
 template <int R0, int CL, bool INV, bool SHIFT_IN, bool SHIFT_OUT, bool MAG, bool ROWS, int TQ = 0, int NATQ = 0, bool RIN = false>
@@ -231,14 +231,22 @@ fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, long long row
 #pragma unroll
             for (int n2 = 0; n2 < 16; n2++) {
                 const int src = SHIFT_IN ? (n2 ^ 8) : n2;
-                const float2* gp = NATQ ? xr + (n2 / (NATQ ? NATQ : 1)) * (256 * NATQ) + 256 * ((n2 % (NATQ ? NATQ : 1)) ^ (SHIFT_IN ? NATQ / 2 : 0)) + c
+                const float2* gp = NATQ ? xr + (n2 / (NATQ ? NATQ : 1)) * (256 * NATQ) + 256 * ((n2 % (NATQ ? NATQ : 1)) ^ (SHIFT_IN ? NATQ / 2 : 0)) +
+                                              (NATQ == 1 && SHIFT_IN ? (c ^ 128) : c)
                                    : R1K ? xr + (n2 % RPC) * rstride + 256 * (n2 / RPC) + c : xr + (ROWS ? sb * rstride : 0) + c + 256 * src;
                 const float4 ab = ldpair(gp);
                 v[n2].re = make_float2(ab.x, ab.z);
                 v[n2].im = make_float2(ab.y, ab.w);
             }
         }
-        if constexpr (NATQ > 0) {
+        if constexpr (NATQ == 1) {
+            // sixteen 256-point rows: the first stage is empty
+#pragma unroll
+            for (int k0 = 0; k0 < 16; k0++) {
+                *reinterpret_cast<float2*>(bre + 272 * k0 + off[(k0 >> 1) & 3]) = v[k0].re;
+                *reinterpret_cast<float2*>(bim + 272 * k0 + off[(k0 >> 1) & 3]) = v[k0].im;
+            }
+        } else if constexpr (NATQ > 1) {
             // radix Q inside each row (v[Q*row + q] -> v[Q*row + q']), then W_{256Q}^{c q'}
             constexpr int TWO = NATQ == 2 ? FP_TW_512 : NATQ == 4 ? FP_TW_1K : FP_TW_2K;
             cp w[8];
@@ -382,8 +390,12 @@ fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, long long row
         // NATQ: lanes take the low 3 bits of k0 and the low 2 bits of k1 (quarter-warps still walk k0: conflict-free 128-bit
         // loads), so that one store instruction writes 4*Q-point runs (16 consecutive results for 1024-point rows)
         const int lsb = gl % NSB;
-        const int k0 = NATQ ? ((gl & 7) | (((gl >> 5) & 1) << 3)) : (gl / NSB) & 15;
-        const int k1 = NATQ ? (((gl >> 3) & 3) | ((gl >> 6) << 2)) : gl / (16 * NSB);
+        // (Q = 2: lanes take q' = k0 bit 0 and all of k1, with the quarter-warp on (q', k1 bits 1-2) so that the eight 128-bit
+        // loads still fall into eight different bank windows: 32 consecutive results per store instruction)
+        const int k0 = (NATQ == 2 || NATQ == 1) ? ((gl & 1) | (((gl >> 5) & 7) << 1))
+                       : NATQ ? ((gl & 7) | (((gl >> 5) & 1) << 3)) : (gl / NSB) & 15;
+        const int k1 = (NATQ == 2 || NATQ == 1) ? (((gl >> 3) & 1) | (((gl >> 1) & 3) << 1) | (((gl >> 4) & 1) << 3))
+                       : NATQ ? (((gl >> 3) & 3) | ((gl >> 6) << 2)) : gl / (16 * NSB);
         const int r = fp_rot(k0, k1);
         const int base = lsb * FP_B + 272 * k0 + 16 * k1;
         cp P[8];
@@ -910,7 +922,7 @@ static int fftp_cluster_mode() {
 // returns 0 on success, 1 when this configuration is not covered (caller uses the generic kernel)
 int fftp_try(const void* in, void* out, size_t n, size_t rows, bool inverse, size_t in_rot, size_t out_rot, double scale,
              bool magnitude, cudaStream_t st) {
-    if (n != 512 && n != 1024 && n != 2048 && n != 4096 && n != 8192 && n != 16384) return 1;
+    if (n != 256 && n != 512 && n != 1024 && n != 2048 && n != 4096 && n != 8192 && n != 16384) return 1;
     if ((in_rot != 0 && in_rot != n / 2) || (out_rot != 0 && out_rot != n / 2)) return 1;
     if (n < 4096) {
         // several rows per CTA: whole groups of 4096 points only (the caller handles other batch sizes generically)
@@ -920,6 +932,7 @@ int fftp_try(const void* in, void* out, size_t n, size_t rows, bool inverse, siz
         const size_t groups = rows / per;
         if (groups > 0x7fffffffull) return 1;
         const bool si = in_rot != 0, so = out_rot != 0;
+        if (n == 256) return fftp_dispatch_nat<1>(in, out, groups, inverse, si, so, magnitude, (float)scale, st);
         if (n == 512) return fftp_dispatch_nat<2>(in, out, groups, inverse, si, so, magnitude, (float)scale, st);
         if (n == 1024) return fftp_dispatch_nat<4>(in, out, groups, inverse, si, so, magnitude, (float)scale, st);
         return fftp_dispatch_nat<8>(in, out, groups, inverse, si, so, magnitude, (float)scale, st);
@@ -946,7 +959,7 @@ int fftp_dispatch_real(const void* in, void* out, size_t groups, bool shift_out,
 }
 
 int fftp_try_real(const void* in, void* out, size_t n, size_t rows, size_t out_rot, double scale, bool magnitude, cudaStream_t st) {
-    if (n != 512 && n != 1024 && n != 2048 && n != 4096 && n != 8192 && n != 16384) return 1;
+    if (n != 256 && n != 512 && n != 1024 && n != 2048 && n != 4096 && n != 8192 && n != 16384) return 1;
     if (out_rot != 0 && out_rot != n / 2) return 1;
     if ((reinterpret_cast<uintptr_t>(in) & 7) || (reinterpret_cast<uintptr_t>(out) & 7) || in == out) return 1;
     const size_t per = n < 4096 ? 4096 / n : 1;
@@ -956,6 +969,7 @@ int fftp_try_real(const void* in, void* out, size_t n, size_t rows, size_t out_r
     const bool so = out_rot != 0;
     const float sc = (float)scale;
     switch (n) {
+    case 256: return fftp_dispatch_real<1, 1>(in, out, groups, so, magnitude, sc, st);
     case 512: return fftp_dispatch_real<1, 2>(in, out, groups, so, magnitude, sc, st);
     case 1024: return fftp_dispatch_real<1, 4>(in, out, groups, so, magnitude, sc, st);
     case 2048: return fftp_dispatch_real<1, 8>(in, out, groups, so, magnitude, sc, st);

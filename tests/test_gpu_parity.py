@@ -101,7 +101,7 @@ def test_real_input_fft(n):  # tests/real_test.rs:581-605
     assert o.rel_l2(got, o.plain_fft(x)) <= tol(n, np.float32)
 
 
-@pytest.mark.parametrize("n,rows", [(512, 128), (1024, 256), (2048, 32), (4096, 64), (8192, 8), (16384, 4), (1 << 15, 4), (1 << 16, 4), (1 << 19, 2), (1 << 20, 2), (1 << 22, 1), (512, 7)])
+@pytest.mark.parametrize("n,rows", [(256, 256), (512, 128), (1024, 256), (2048, 32), (4096, 64), (8192, 8), (16384, 4), (1 << 15, 4), (1 << 16, 4), (1 << 19, 2), (1 << 20, 2), (1 << 22, 1), (512, 7)])
 def test_real_input_rows(n, rows):
     """rows of real scalars (BDSP_F_REAL_INPUT): complexifying pass + packed passes in the throughput regime."""
     rng = np.random.default_rng(n + rows)
@@ -141,7 +141,7 @@ def test_fft_rows_batched():
     rng = np.random.default_rng(5)
     L = bd.lib()
     for n, rows in [(16384, 8), (1024, 33), (64, 100), (1 << 15, 3), (1 << 16, 5), (1 << 17, 3), (1 << 18, 5), (1 << 19, 3), (1 << 20, 3),
-                    (512, 64), (1024, 32), (2048, 6)]:
+                    (256, 48), (512, 64), (1024, 32), (2048, 6)]:
         x = rand_c(rng, n * rows, np.float32)
         v = DspVec(x)
         out = DspVec.zeros(n * rows, dtype=np.float32)
@@ -162,7 +162,7 @@ def test_fft_magnitude_fused(n):
     assert o.rel_l2(got.to_numpy(), np.abs(o.fft(x))) <= tol(n, np.float32)
 
 
-@pytest.mark.parametrize("n", [512, 1024, 2048, 4096, 8192])
+@pytest.mark.parametrize("n", [256, 512, 1024, 2048, 4096, 8192])
 def test_small_row_batches_all_flag_combinations(n):
     """several rows per CTA (fftp.cu NATQ modes) and the 4096 / 8192-point kernels: forward, shifted, inverse, ifft."""
     rng = np.random.default_rng(n + 1)
