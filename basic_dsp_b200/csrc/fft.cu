@@ -744,15 +744,23 @@ int fft_any(const void* in, void* out, size_t n, size_t batch, const FftOpts& o,
     bluestein_pre_kernel<T, INV><<<(unsigned)((totM + 255) / 256), 256, 0, st>>>(in, a, (long long)n, (long long)M, (long long)batch,
                                                                                  in_rot, o.real_input, scale);
     BDSP_LAUNCHED();
-    // the two length-M transforms of the chirp-z convolution take the packed passes where they exist (M > 16384, c32)
+    // the two length-M transforms of the chirp-z convolution take the packed passes where they exist: in place with the
+    // pass workspace for M > 16384, ping-pong between two buffers for the single-pass sizes (those kernels are out of place)
     FftOpts fo;
     const size_t w0_bytes = w0 ? M * (batch > 1 ? batch : 1) * sizeof(C) : 0;
-    int rc = w0 ? fft_any<T, false>(a, a, M, batch, fo, w0, w0_bytes, st) : fft_pow2<T, false>(a, a, M, batch, false, false, 0, (T)1, plain, w0, st);
+    int rc;
+    const bool pingpong = !w0 && sizeof(T) == 4 && M >= 256 && M * batch >= (1u << 16);
+    C* b2 = pingpong ? reinterpret_cast<C*>(workspace(M * batch * sizeof(C), 2)) : a;
+    if (w0) rc = fft_any<T, false>(a, a, M, batch, fo, w0, w0_bytes, st);
+    else if (pingpong) rc = fft_any<T, false>(a, b2, M, batch, fo, nullptr, 0, st);
+    else rc = fft_pow2<T, false>(a, a, M, batch, false, false, 0, (T)1, plain, w0, st);
     if (rc) return rc;
-    pointwise_mul_bcast_kernel<T><<<(unsigned)((totM + 255) / 256), 256, 0, st>>>(a, bspec, (long long)M, (long long)batch, (T)(1.0 / (double)M));
+    pointwise_mul_bcast_kernel<T><<<(unsigned)((totM + 255) / 256), 256, 0, st>>>(b2, bspec, (long long)M, (long long)batch, (T)(1.0 / (double)M));
     BDSP_LAUNCHED();
     fo.inverse = 1;
-    rc = w0 ? fft_any<T, true>(a, a, M, batch, fo, w0, w0_bytes, st) : fft_pow2<T, true>(a, a, M, batch, false, false, 0, (T)1, plain, w0, st);
+    if (w0) rc = fft_any<T, true>(a, a, M, batch, fo, w0, w0_bytes, st);
+    else if (pingpong) rc = fft_any<T, true>(b2, a, M, batch, fo, nullptr, 0, st);
+    else rc = fft_pow2<T, true>(a, a, M, batch, false, false, 0, (T)1, plain, w0, st);
     if (rc) return rc;
     const long long totn = (long long)(n * batch);
     bluestein_post_kernel<T, INV><<<(unsigned)((totn + 255) / 256), 256, 0, st>>>(a, out, (long long)n, (long long)M, (long long)batch, om, o.magnitude);
