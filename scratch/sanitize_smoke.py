@@ -14,10 +14,20 @@ for n in (8, 1000, 1001, 4096, 8192, 16384, 1 << 15, 1 << 16, 1 << 17, 1 << 18, 
     DspVec(rc(n)).fft().ifft().to_numpy()
 for n in (1000, 4096, 1 << 15, 3 * 4096):
     DspVec(rc(n, np.complex128)).fft().ifft().to_numpy()
-for n, rows in ((512, 16), (1024, 8), (2048, 4), (4096, 3), (8192, 3), (16384, 2), (1 << 22, 1)):
+for n, rows in ((256, 32), (512, 16), (1024, 8), (2048, 4), (4096, 3), (8192, 3), (16384, 2), (1 << 15, 2), (1 << 16, 2), (1 << 17, 1),
+                (1 << 18, 1), (1 << 19, 1), (1 << 20, 1), (1 << 21, 1), (1 << 22, 1), (1 << 23, 1), (1 << 24, 1)):
     x = DspVec(rc(n * rows)); out = DspVec.zeros(2 * n * rows, is_complex=True, dtype=np.float32)
     for flags in (0, bd.F_SHIFT | bd.F_MAGNITUDE, bd.F_INVERSE, bd.F_INVERSE | bd.F_SHIFT):
         assert L.bdsp_fft_rows_c32(dp(x), dp(out), n, rows, flags) == 0
+# real-input rows
+for n, rows in ((256, 256), (1024, 64), (4096, 16), (16384, 4), (1 << 15, 2), (1 << 19, 1), (1 << 21, 1)):
+    x = DspVec(rng.uniform(-1, 1, n * rows).astype(np.float32)); out = DspVec.zeros(2 * n * rows, is_complex=True, dtype=np.float32)
+    for flags in (bd.F_REAL_INPUT, bd.F_REAL_INPUT | bd.F_SHIFT | bd.F_MAGNITUDE):
+        assert L.bdsp_fft_rows_c32(dp(x), dp(out), n, rows, flags) == 0
+# chirp-z and q*2^k batches
+for n, rows in ((1000, 64), (3072, 16), (9973, 4)):
+    x = DspVec(rc(n * rows)); out = DspVec.zeros(2 * n * rows, is_complex=True, dtype=np.float32)
+    assert L.bdsp_fft_rows_c32(dp(x), dp(out), n, rows, 0) == 0
 # convolution
 for n, l in ((20000, 1023), (5000, 63), (9000, 2000), (40000, 5001), (300, 25)):
     DspVec(rc(n)).convolve_signal(DspVec(rc(l))).to_numpy()
