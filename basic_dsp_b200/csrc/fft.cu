@@ -149,6 +149,9 @@ __device__ __forceinline__ int spad_host_dev(int n) { return n + (n >> 4) + 1; }
 #ifndef BDSP_TILE_F64_RADIX8
 #define BDSP_TILE_F64_RADIX8 1
 #endif
+#ifndef BDSP_BLOCK_POINTS
+#define BDSP_BLOCK_POINTS 1024
+#endif
 template <typename T, bool INV, bool REAL_IN, bool MAG>
 __global__ void __launch_bounds__(sizeof(T) == 4 ? 1024 : 1024, 1) fft_block_kernel(const void* __restrict__ in_, void* __restrict__ out_, int log2n, int nfft,
                                  long long batch, long long in_rot, T scale, OutMap om,
@@ -504,7 +507,8 @@ int launch_block(const void* in, void* out, size_t n, size_t batch, bool real_in
                  T scale, const OutMap& om, cudaStream_t st) {
     typedef typename CpxOf<T>::type C;
     const int log2n = ilog2(n);
-    int nfft = (int)(4096 / n);
+    // points per CTA for short sequences (BDSP_BLOCK_POINTS): smaller CTAs overlap their load / compute / store phases better
+    int nfft = (int)(BDSP_BLOCK_POINTS / n);
     if (nfft < 1) nfft = 1;
     if ((size_t)nfft > batch) nfft = (int)batch;
     int threads = block_fft_threads((int)n, nfft);
