@@ -664,7 +664,7 @@ int fft_any(const void* in, void* out, size_t n, size_t batch, const FftOpts& o,
             oc.real_input = 0;
             return fft_any<T, INV>(cx, out, n, batch, oc, work, work_bytes, st);
         }
-        if (sizeof(T) == 4 && !o.real_input && n >= 256 && n <= 16384) {
+        if (sizeof(T) == 4 && !o.real_input && n >= 64 && n <= 16384) {
             // packed-FP32x2 kernel (fftp.cu); returns 1 when the configuration is not covered
             const int rc = fftp_try(in, out, n, batch, INV, (size_t)in_rot, (size_t)om.rot, o.scale, o.magnitude != 0, st);
             if (rc <= 0) return rc;

@@ -50,7 +50,10 @@ __device__ __forceinline__ int fp_rot(int row, int g) { return (((g >> 1) + (row
 // same for W512^c and W2048^c
 #define FP_TW_512 (FP_TW_1K + 512)
 #define FP_TW_2K (FP_TW_512 + 512)
-#define FP_TW_FLOATS (FP_TW_2K + 512)
+// second-stage tables of the short-row mode: float4 index (8*kg + j/2) = {Re(j), Re(j+1), Im(j), Im(j+1)} of W_{16P}^{kg*j}
+#define FP_TW_S4 (FP_TW_2K + 512)
+#define FP_TW_S8 (FP_TW_S4 + 128)
+#define FP_TW_FLOATS (FP_TW_S8 + 256)
 
 // ROWS = true (R0 = 4, CL = 1): the CTA transforms FOUR independent, adjacent 4096-point rows (no F0) and
 // writes result k of row r to out[(r0 + r) + n1 * k]: the transposing last pass of a two-pass transform of
@@ -61,10 +64,12 @@ __device__ __forceinline__ int fp_rot(int row, int g) { return (((g >> 1) + (row
 // the transposing stores fill 32-byte (Q = 4) or 64-byte (Q = 2) runs.
 // RIN = true (forward, no ROWS): `x` holds REAL scalars (one float per point); the first stage loads two adjacent reals
 // per column pair and the imaginary parts start as zero.
+// SQ = P in {4, 8} (with NATQ = 1): the CTA's 4096 contiguous points are 256/P rows of 16*P points (64, 128): the first stage
+// is empty, the second one is a radix-P step inside every row (instead of radix 16), the third one is unchanged.
 // NATQ = Q in {1, 2, 4, 8} (R0 = 1, no ROWS): the CTA's 4096 contiguous points are 16/Q independent rows of 256*Q points
 // (k0 = q + Q*row); the first stage is a radix-Q butterfly inside every row, results are stored in natural order.
 // Batched 512 / 1024 / 2048-point transforms with the structure of the 4096-point kernel.
-template <int R0, int CL, bool INV, bool SHIFT_IN, bool SHIFT_OUT, bool MAG, bool ROWS, int TQ = 0, int NATQ = 0, bool RIN = false>
+template <int R0, int CL, bool INV, bool SHIFT_IN, bool SHIFT_OUT, bool MAG, bool ROWS, int TQ = 0, int NATQ = 0, bool RIN = false, int SQ = 0>
 // FP_PREFETCH=1: persistent CTAs + register prefetch of the next row.  Measured on B200 (C3): 0.336 ms vs
 // 0.275 ms without (register pressure -> spills; the extra barrier), so it is off by default.
 #ifndef FP_PREFETCH
@@ -232,7 +237,7 @@ fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, long long row
             for (int n2 = 0; n2 < 16; n2++) {
                 const int src = SHIFT_IN ? (n2 ^ 8) : n2;
                 const float2* gp = NATQ ? xr + (n2 / (NATQ ? NATQ : 1)) * (256 * NATQ) + 256 * ((n2 % (NATQ ? NATQ : 1)) ^ (SHIFT_IN ? NATQ / 2 : 0)) +
-                                              (NATQ == 1 && SHIFT_IN ? (c ^ 128) : c)
+                                              (NATQ == 1 && SQ == 0 && SHIFT_IN ? (c ^ 128) : c)
                                    : R1K ? xr + (n2 % RPC) * rstride + 256 * (n2 / RPC) + c : xr + (ROWS ? sb * rstride : 0) + c + 256 * src;
                 const float4 ab = ldpair(gp);
                 v[n2].re = make_float2(ab.x, ab.z);
@@ -351,6 +356,43 @@ fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, long long row
             v[n1].re = *reinterpret_cast<const float2*>(bre + a);
             v[n1].im = *reinterpret_cast<const float2*>(bim + a);
         }
+        if constexpr (SQ > 0) {
+            // rows of 16*SQ points: g = SQ*rowsub + g'; radix SQ over g' (natural order), then W_{16 SQ}^{kg j}, j = n0, n0 + 1.
+            // SHIFT_IN (rotation by half a row = SQ/2 steps of g'): the butterfly inputs are taken from g' ^ (SQ/2).
+            const float4* tws = reinterpret_cast<const float4*>(tw + (SQ == 4 ? FP_TW_S4 : FP_TW_S8)) + (n0 >> 1);
+#pragma unroll
+            for (int r = 0; r < 16 / SQ; r++) {
+                cp u[SQ];
+#pragma unroll
+                for (int q = 0; q < SQ; q++) u[q] = v[SQ * r + (SHIFT_IN ? (q ^ (SQ / 2)) : q)];
+                if constexpr (SQ == 4) r4<INV>(u[0], u[1], u[2], u[3]);
+                else {
+                    cp a0 = cadd(u[0], u[4]), a1 = cadd(u[1], u[5]), a2 = cadd(u[2], u[6]), a3 = cadd(u[3], u[7]);
+                    cp b0 = csub(u[0], u[4]), b1 = mul_w16<2, INV>(csub(u[1], u[5])), b2 = mul_w16<4, INV>(csub(u[2], u[6])),
+                       b3 = mul_w16<6, INV>(csub(u[3], u[7]));
+                    r4<INV>(a0, a1, a2, a3);
+                    r4<INV>(b0, b1, b2, b3);
+                    u[0] = a0; u[2] = a1; u[4] = a2; u[6] = a3; u[1] = b0; u[3] = b1; u[5] = b2; u[7] = b3;
+                }
+#pragma unroll
+                for (int q = 0; q < SQ; q++) {
+                    if (q > 0) {
+                        const float4 f = __ldg(tws + 8 * q);
+                        cp w;
+                        w.re = make_float2(f.x, f.y);
+                        w.im = make_float2(f.z, f.w);
+                        u[q] = INV ? cmul_conj(u[q], w) : cmul(u[q], w);
+                    }
+                    v[SQ * r + q] = u[q];
+                }
+            }
+#pragma unroll
+            for (int n1 = 0; n1 < 16; n1++) {
+                const int a = 16 * n1 + off2[(n1 >> 1) & 3];
+                *reinterpret_cast<float2*>(bre + a) = v[n1].re;
+                *reinterpret_cast<float2*>(bim + a) = v[n1].im;
+            }
+        } else {
         r16<INV>(v);
 #pragma unroll
         for (int s = 1; s < 16; s++) {
@@ -367,6 +409,7 @@ fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, long long row
             const int a = 16 * k1 + off2[(k1 >> 1) & 3];
             *reinterpret_cast<float2*>(bre + a) = v[s].re;
             *reinterpret_cast<float2*>(bim + a) = v[s].im;
+        }
         }
     }
     __syncthreads();
@@ -392,9 +435,10 @@ fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, long long row
         const int lsb = gl % NSB;
         // (Q = 2: lanes take q' = k0 bit 0 and all of k1, with the quarter-warp on (q', k1 bits 1-2) so that the eight 128-bit
         // loads still fall into eight different bank windows: 32 consecutive results per store instruction)
-        const int k0 = (NATQ == 2 || NATQ == 1) ? ((gl & 1) | (((gl >> 5) & 7) << 1))
+        // (SQ: lanes take all of k1 = SQ*rowsub + kg and k0 bit 0: runs of SQ results per row and store instruction)
+        const int k0 = SQ ? (gl >> 4) : (NATQ == 2 || NATQ == 1) ? ((gl & 1) | (((gl >> 5) & 7) << 1))
                        : NATQ ? ((gl & 7) | (((gl >> 5) & 1) << 3)) : (gl / NSB) & 15;
-        const int k1 = (NATQ == 2 || NATQ == 1) ? (((gl >> 3) & 1) | (((gl >> 1) & 3) << 1) | (((gl >> 4) & 1) << 3))
+        const int k1 = SQ ? (gl & 15) : (NATQ == 2 || NATQ == 1) ? (((gl >> 3) & 1) | (((gl >> 1) & 3) << 1) | (((gl >> 4) & 1) << 3))
                        : NATQ ? (((gl >> 3) & 3) | ((gl >> 6) << 2)) : gl / (16 * NSB);
         const int r = fp_rot(k0, k1);
         const int base = lsb * FP_B + 272 * k0 + 16 * k1;
@@ -414,10 +458,12 @@ fftp_kernel(const float2* __restrict__ x, void* __restrict__ out_, long long row
         const size_t kst = ROWS ? (size_t)n1 * (size_t)n2c : (size_t)R0;
         const size_t kbase = ROWS ? (size_t)n1 * (size_t)k2o : 0;
         // (NATQ: row = k0 / Q, k = row*256*Q + (k0 % Q) + Q*(k1 + 16*k2))
-        const size_t klow = NATQ ? (size_t)((k0 / (NATQ ? NATQ : 1)) * (256 * NATQ) + (k0 % (NATQ ? NATQ : 1)) + NATQ * k1)
+        // (SQ: row = k0*(16/SQ) + k1/SQ, k = row*16*SQ + (k1 % SQ) + SQ*k2)
+        const size_t klow = SQ ? (size_t)((k0 * (16 / (SQ ? SQ : 1)) + k1 / (SQ ? SQ : 1)) * (16 * SQ) + (k1 % (SQ ? SQ : 1)))
+                            : NATQ ? (size_t)((k0 / (NATQ ? NATQ : 1)) * (256 * NATQ) + (k0 % (NATQ ? NATQ : 1)) + NATQ * k1)
                             : R1K ? kbase + (size_t)(RPC * grp + (k0 % RPC)) + kst * (size_t)((k0 / RPC) + TQ * k1)
                                 : kbase + (ROWS ? (size_t)(NSB * grp + lsb) : (size_t)(rank * NSB + lsb)) + kst * (size_t)(k0 + 16 * k1);
-        const size_t k2s = NATQ ? (size_t)(16 * NATQ) : R1K ? (size_t)(16 * TQ) * kst : (size_t)256 * kst;
+        const size_t k2s = SQ ? (size_t)SQ : NATQ ? (size_t)(16 * NATQ) : R1K ? (size_t)(16 * TQ) * kst : (size_t)256 * kst;
         if constexpr (MAG) {
             float* o = reinterpret_cast<float*>(out_) + seq * seq_len + klow;
 #pragma unroll
@@ -665,6 +711,14 @@ const float* fftp_twiddles() {
         h[FP_TW_2K + c] = (float)cosl(-tau * c / 2048.0L);
         h[FP_TW_2K + 256 + c] = (float)sinl(-tau * c / 2048.0L);
     }
+    for (int P = 4; P <= 8; P += 4)
+        for (int kg = 0; kg < P; kg++)
+            for (int j = 0; j < 16; j++) {
+                const long double a = -tau * (long double)((kg * j) % (16 * P)) / (long double)(16 * P);
+                float* e = &h[(P == 4 ? FP_TW_S4 : FP_TW_S8) + (8 * kg + j / 2) * 4];
+                e[j & 1] = (float)cosl(a);
+                e[2 + (j & 1)] = (float)sinl(a);
+            }
     for (int ka = 0; ka < 16; ka++)
         for (int b = 0; b < 16; b++) {
             const long double a = -tau * (long double)((ka * b) % 256) / 256.0L;
@@ -679,11 +733,11 @@ const float* fftp_twiddles() {
     return dev;
 }
 
-template <int R0, int CL, bool INV, bool SI, bool SO, bool MAG, bool ROWS = false, int TQ = 0, int NATQ = 0, bool RIN = false>
+template <int R0, int CL, bool INV, bool SI, bool SO, bool MAG, bool ROWS = false, int TQ = 0, int NATQ = 0, bool RIN = false, int SQ = 0>
 int fftp_launch(const void* in, void* out, size_t rows, float scale, cudaStream_t st, int n1 = 1, int n2c = 1) {
     constexpr int NSB = R0 / CL;
     const size_t smem = (size_t)2 * NSB * FP_B_OF(NSB) * sizeof(float);
-    auto kern = fftp_kernel<R0, CL, INV, SI, SO, MAG, ROWS, TQ, NATQ, RIN>;
+    auto kern = fftp_kernel<R0, CL, INV, SI, SO, MAG, ROWS, TQ, NATQ, RIN, SQ>;
     static bool configured = false;   // per instantiation
     if (!configured) {
         BDSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -725,6 +779,20 @@ int fftp_dispatch_nat(const void* in, void* out, size_t groups, bool inv, bool s
     if (mag || shift_out) return 1;
     return shift_in ? fftp_launch<1, 1, true, true, false, false, false, 0, Q>(in, out, groups, scale, st)
                     : fftp_launch<1, 1, true, false, false, false, false, 0, Q>(in, out, groups, scale, st);
+}
+
+// rows of 64 / 128 points (fftp_kernel<SQ>): whole groups of 4096 points
+template <int P>
+int fftp_dispatch_short(const void* in, void* out, size_t groups, bool inv, bool shift_in, bool shift_out, bool mag, float scale, cudaStream_t st) {
+    if (!inv) {
+        if (mag) return shift_out ? fftp_launch<1, 1, false, false, true, true, false, 0, 1, false, P>(in, out, groups, scale, st)
+                                  : fftp_launch<1, 1, false, false, false, true, false, 0, 1, false, P>(in, out, groups, scale, st);
+        return shift_out ? fftp_launch<1, 1, false, false, true, false, false, 0, 1, false, P>(in, out, groups, scale, st)
+                         : fftp_launch<1, 1, false, false, false, false, false, 0, 1, false, P>(in, out, groups, scale, st);
+    }
+    if (mag || shift_out) return 1;
+    return shift_in ? fftp_launch<1, 1, true, true, false, false, false, 0, 1, false, P>(in, out, groups, scale, st)
+                    : fftp_launch<1, 1, true, false, false, false, false, 0, 1, false, P>(in, out, groups, scale, st);
 }
 
 template <int R0, int CL>
@@ -922,7 +990,7 @@ static int fftp_cluster_mode() {
 // returns 0 on success, 1 when this configuration is not covered (caller uses the generic kernel)
 int fftp_try(const void* in, void* out, size_t n, size_t rows, bool inverse, size_t in_rot, size_t out_rot, double scale,
              bool magnitude, cudaStream_t st) {
-    if (n != 256 && n != 512 && n != 1024 && n != 2048 && n != 4096 && n != 8192 && n != 16384) return 1;
+    if (n != 64 && n != 128 && n != 256 && n != 512 && n != 1024 && n != 2048 && n != 4096 && n != 8192 && n != 16384) return 1;
     if ((in_rot != 0 && in_rot != n / 2) || (out_rot != 0 && out_rot != n / 2)) return 1;
     if (n < 4096) {
         // several rows per CTA: whole groups of 4096 points only (the caller handles other batch sizes generically)
@@ -932,6 +1000,8 @@ int fftp_try(const void* in, void* out, size_t n, size_t rows, bool inverse, siz
         const size_t groups = rows / per;
         if (groups > 0x7fffffffull) return 1;
         const bool si = in_rot != 0, so = out_rot != 0;
+        if (n == 64) return fftp_dispatch_short<4>(in, out, groups, inverse, si, so, magnitude, (float)scale, st);
+        if (n == 128) return fftp_dispatch_short<8>(in, out, groups, inverse, si, so, magnitude, (float)scale, st);
         if (n == 256) return fftp_dispatch_nat<1>(in, out, groups, inverse, si, so, magnitude, (float)scale, st);
         if (n == 512) return fftp_dispatch_nat<2>(in, out, groups, inverse, si, so, magnitude, (float)scale, st);
         if (n == 1024) return fftp_dispatch_nat<4>(in, out, groups, inverse, si, so, magnitude, (float)scale, st);

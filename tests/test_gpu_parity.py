@@ -141,7 +141,7 @@ def test_fft_rows_batched():
     rng = np.random.default_rng(5)
     L = bd.lib()
     for n, rows in [(16384, 8), (1024, 33), (64, 100), (1 << 15, 3), (1 << 16, 5), (1 << 17, 3), (1 << 18, 5), (1 << 19, 3), (1 << 20, 3),
-                    (256, 48), (512, 64), (1024, 32), (2048, 6)]:
+                    (64, 128), (128, 96), (256, 48), (512, 64), (1024, 32), (2048, 6)]:
         x = rand_c(rng, n * rows, np.float32)
         v = DspVec(x)
         out = DspVec.zeros(n * rows, dtype=np.float32)
@@ -162,7 +162,7 @@ def test_fft_magnitude_fused(n):
     assert o.rel_l2(got.to_numpy(), np.abs(o.fft(x))) <= tol(n, np.float32)
 
 
-@pytest.mark.parametrize("n", [256, 512, 1024, 2048, 4096, 8192])
+@pytest.mark.parametrize("n", [64, 128, 256, 512, 1024, 2048, 4096, 8192])
 def test_small_row_batches_all_flag_combinations(n):
     """several rows per CTA (fftp.cu NATQ modes) and the 4096 / 8192-point kernels: forward, shifted, inverse, ifft."""
     rng = np.random.default_rng(n + 1)
