@@ -14,7 +14,7 @@ for n in (8, 1000, 1001, 4096, 8192, 16384, 1 << 15, 1 << 16, 1 << 17, 1 << 18, 
     DspVec(rc(n)).fft().ifft().to_numpy()
 for n in (1000, 4096, 1 << 15, 3 * 4096):
     DspVec(rc(n, np.complex128)).fft().ifft().to_numpy()
-for n, rows in ((256, 32), (512, 16), (1024, 8), (2048, 4), (4096, 3), (8192, 3), (16384, 2), (1 << 15, 2), (1 << 16, 2), (1 << 17, 1),
+for n, rows in ((64, 128), (128, 64), (256, 32), (512, 16), (1024, 8), (2048, 4), (4096, 3), (8192, 3), (16384, 2), (1 << 15, 2), (1 << 16, 2), (1 << 17, 1),
                 (1 << 18, 1), (1 << 19, 1), (1 << 20, 1), (1 << 21, 1), (1 << 22, 1), (1 << 23, 1), (1 << 24, 1)):
     x = DspVec(rc(n * rows)); out = DspVec.zeros(2 * n * rows, is_complex=True, dtype=np.float32)
     for flags in (0, bd.F_SHIFT | bd.F_MAGNITUDE, bd.F_INVERSE, bd.F_INVERSE | bd.F_SHIFT):
