@@ -648,7 +648,7 @@ int fft_any(const void* in, void* out, size_t n, size_t batch, const FftOpts& o,
     const long long in_rot = (long long)(o.in_rot % n);
     const T scale = (T)o.scale;
     if (is_pow2(n)) {
-        if (sizeof(T) == 4 && o.real_input && !INV && in_rot == 0 && n >= 256 && n <= 16384 && n * batch >= (1u << 16)) {
+        if (sizeof(T) == 4 && o.real_input && !INV && in_rot == 0 && n >= 64 && n <= 16384 && n * batch >= (1u << 16)) {
             // rows of real scalars, single pass: the packed kernel loads the reals directly (4 B read + 8 B written per point)
             const int rc = fftp_try_real(in, out, n, batch, (size_t)om.rot, o.scale, o.magnitude != 0, st);
             if (rc <= 0) return rc;

@@ -1020,16 +1020,16 @@ int fftp_try(const void* in, void* out, size_t n, size_t rows, bool inverse, siz
 }
 
 // real-input forward transforms (fftp_kernel<RIN>): rows of `n` real scalars, n in {512 ... 16384}
-template <int R0, int Q>
+template <int R0, int Q, int SQ = 0>
 int fftp_dispatch_real(const void* in, void* out, size_t groups, bool shift_out, bool mag, float scale, cudaStream_t st) {
-    if (mag) return shift_out ? fftp_launch<R0, 1, false, false, true, true, false, 0, Q, true>(in, out, groups, scale, st)
-                              : fftp_launch<R0, 1, false, false, false, true, false, 0, Q, true>(in, out, groups, scale, st);
-    return shift_out ? fftp_launch<R0, 1, false, false, true, false, false, 0, Q, true>(in, out, groups, scale, st)
-                     : fftp_launch<R0, 1, false, false, false, false, false, 0, Q, true>(in, out, groups, scale, st);
+    if (mag) return shift_out ? fftp_launch<R0, 1, false, false, true, true, false, 0, Q, true, SQ>(in, out, groups, scale, st)
+                              : fftp_launch<R0, 1, false, false, false, true, false, 0, Q, true, SQ>(in, out, groups, scale, st);
+    return shift_out ? fftp_launch<R0, 1, false, false, true, false, false, 0, Q, true, SQ>(in, out, groups, scale, st)
+                     : fftp_launch<R0, 1, false, false, false, false, false, 0, Q, true, SQ>(in, out, groups, scale, st);
 }
 
 int fftp_try_real(const void* in, void* out, size_t n, size_t rows, size_t out_rot, double scale, bool magnitude, cudaStream_t st) {
-    if (n != 256 && n != 512 && n != 1024 && n != 2048 && n != 4096 && n != 8192 && n != 16384) return 1;
+    if (n != 64 && n != 128 && n != 256 && n != 512 && n != 1024 && n != 2048 && n != 4096 && n != 8192 && n != 16384) return 1;
     if (out_rot != 0 && out_rot != n / 2) return 1;
     if ((reinterpret_cast<uintptr_t>(in) & 7) || (reinterpret_cast<uintptr_t>(out) & 7) || in == out) return 1;
     const size_t per = n < 4096 ? 4096 / n : 1;
@@ -1039,6 +1039,8 @@ int fftp_try_real(const void* in, void* out, size_t n, size_t rows, size_t out_r
     const bool so = out_rot != 0;
     const float sc = (float)scale;
     switch (n) {
+    case 64: return fftp_dispatch_real<1, 1, 4>(in, out, groups, so, magnitude, sc, st);
+    case 128: return fftp_dispatch_real<1, 1, 8>(in, out, groups, so, magnitude, sc, st);
     case 256: return fftp_dispatch_real<1, 1>(in, out, groups, so, magnitude, sc, st);
     case 512: return fftp_dispatch_real<1, 2>(in, out, groups, so, magnitude, sc, st);
     case 1024: return fftp_dispatch_real<1, 4>(in, out, groups, so, magnitude, sc, st);

@@ -101,7 +101,7 @@ def test_real_input_fft(n):  # tests/real_test.rs:581-605
     assert o.rel_l2(got, o.plain_fft(x)) <= tol(n, np.float32)
 
 
-@pytest.mark.parametrize("n,rows", [(256, 256), (512, 128), (1024, 256), (2048, 32), (4096, 64), (8192, 8), (16384, 4), (1 << 15, 4), (1 << 16, 4), (1 << 19, 2), (1 << 20, 2), (1 << 22, 1), (512, 7)])
+@pytest.mark.parametrize("n,rows", [(64, 2048), (128, 1024), (256, 256), (512, 128), (1024, 256), (2048, 32), (4096, 64), (8192, 8), (16384, 4), (1 << 15, 4), (1 << 16, 4), (1 << 19, 2), (1 << 20, 2), (1 << 22, 1), (512, 7)])
 def test_real_input_rows(n, rows):
     """rows of real scalars (BDSP_F_REAL_INPUT): complexifying pass + packed passes in the throughput regime."""
     rng = np.random.default_rng(n + rows)
