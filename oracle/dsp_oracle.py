@@ -375,8 +375,11 @@ def interpolatef_tap_vectors(f, conv_len, factor_int, delay, dtype):
     return vs
 
 
-def interpolatef(x, f, factor, delay, conv_len, dtype, delta=1.0):
+def interpolatef(x, f, factor, delay, conv_len, dtype, delta=1.0, out_range=None):
     """InterpolationOps::interpolatef (interpolation.rs:387-482).
+
+    out_range=(lo, hi): evaluate only output points lo <= i < hi of the result (same formulas; lets the
+    tests walk BASELINE-sized vectors in bounded memory).
 
     * delay <- delay/delta (:397); L = min(conv_len, points/2) (:399-404).
     * integer-F fast path (interpolate_priv_simd :191-290): interior outputs use
@@ -396,13 +399,14 @@ def interpolatef(x, f, factor, delay, conv_len, dtype, delta=1.0):
     new_len = interpolatef_new_len(len_T, factor, dtype)
     new_points = new_len // 2 if is_complex else new_len
     out_dtype = np.complex128 if is_complex else np.float64
-    xx = x.astype(out_dtype)
-    y = np.zeros(new_points, dtype=out_dtype)
+    xx = x.astype(out_dtype) if out_range is None else x
+    lo, hi = (0, new_points) if out_range is None else (max(0, int(out_range[0])), min(new_points, int(out_range[1])))
+    y = np.zeros(hi - lo, dtype=out_dtype)
     if interpolatef_uses_fast_path(L, new_len, factor, dtype):
         F = int(np.round(T(factor)))
         vs = interpolatef_tap_vectors(f, L, F, delay, dtype).astype(np.float64)
         scalar_len = (2 * L + 1) * F
-        i = np.arange(new_points)
+        i = np.arange(lo, hi)
         interior = (i >= scalar_len) & (i < new_points - scalar_len)
         # interior
         ii = i[interior]
@@ -422,7 +426,7 @@ def interpolatef(x, f, factor, delay, conv_len, dtype, delta=1.0):
         y[~interior] = acc
         return y
     factor = T(factor)
-    for i in range(new_points):
+    for i in range(lo, hi):
         center = T(i) / factor
         rounded = np.floor(center)
         r = int(rounded)
@@ -431,7 +435,7 @@ def interpolatef(x, f, factor, delay, conv_len, dtype, delta=1.0):
         for k in range(2 * L + 1):
             acc = acc + xx[(r - L + k) % N] * float(f(j))
             j = j + T(1)
-        y[i] = acc
+        y[i - lo] = acc
     return y
 
 
