@@ -235,6 +235,7 @@ def _declare(lib):
     lib.bdsp_conv_plan_destroy.restype, lib.bdsp_conv_plan_destroy.argtypes = None, [c_void_p]
     lib.bdsp_malloc.restype, lib.bdsp_malloc.argtypes = c_void_p, [c_size_t]
     lib.bdsp_free.restype, lib.bdsp_free.argtypes = None, [c_void_p]
+    lib.bdsp_mem_free.restype, lib.bdsp_mem_free.argtypes = c_size_t, []
     lib.bdsp_malloc_host.restype, lib.bdsp_malloc_host.argtypes = c_void_p, [c_size_t]
     lib.bdsp_free_host.restype, lib.bdsp_free_host.argtypes = None, [c_void_p]
     lib.bdsp_memcpy_h2d.restype, lib.bdsp_memcpy_h2d.argtypes = c_int32, [c_void_p, c_void_p, c_size_t]

@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include <map>
+#include <memory>
 #include <mutex>
 #include <vector>
 
@@ -37,8 +38,11 @@ template <typename T> struct Vec {
     int is_complex = 0;
     int domain = 0;                           // 0 time, 1 frequency
     unsigned long long version = 0;           // bumped by every mutation (invalidates caches)
-    // cache: spectrum of this vector used as overlap-save impulse response
-    T* Hs = nullptr; size_t Hs_M = 0; unsigned long long Hs_version = ~0ull;
+    // cache: overlap-save plan of this vector used as impulse response.  The vector is only BORROWED by
+    // convolve_signal (`&VecBuf`, facade32.rs:1171), possibly by several threads at once: the cache is guarded by
+    // `plan_mu`, and the plan is immutable and reference counted (a caller keeps it alive while its kernel is queued).
+    std::mutex plan_mu;
+    std::shared_ptr<OlsPlan> plan; unsigned long long plan_version = ~0ull; int plan_complex_signal = -1;
     // host mirror for data32()
     std::vector<T> host;
 };
@@ -80,7 +84,8 @@ template <typename T> Vec<T>* vec_new(int is_complex, int domain, T init, size_t
     v->is_complex = is_complex != 0;
     v->domain = domain == 0 ? 0 : 1;
     v->delta = delta;
-    if (reserve(&v->d, &v->cap, length, false, 0) != 0) { fprintf(stderr, "basic_dsp_b200: %s\n", get_last_error()); abort(); }
+    // allocation failure: null handle (bdsp_last_error() says why) instead of taking the host process down
+    if (reserve(&v->d, &v->cap, length, false, 0) != 0) { delete v; return nullptr; }
     // to_gen_dsp_vec: a complex vector needs an even number of scalars (support_std.rs:369)
     v->len = (v->is_complex && (length % 2)) ? 0 : length;
     if (length) ew_fill<T>(v->d, length, (double)init, g_stream);
@@ -92,7 +97,7 @@ template <typename T> void vec_delete(Vec<T>* v) {
     cudaStreamSynchronize(g_stream);
     if (v->d) cudaFree(v->d);
     if (v->scratch) cudaFree(v->scratch);
-    if (v->Hs) cudaFree(v->Hs);
+    v->plan.reset();
     delete v;
 }
 
@@ -374,8 +379,17 @@ inline void table_consumed() {
 
 // ---- convolution -----------------------------------------------------------------------------------
 // circular FIR / fast convolution dispatch for taps resident on the device
+struct PlanCache {   // where convolve_taps may keep the plan between calls (an impulse-response vector)
+    std::mutex* mu;
+    std::shared_ptr<OlsPlan>* plan;
+    unsigned long long* plan_version;
+    int* plan_complex_signal;
+    unsigned long long version;
+};
+inline std::shared_ptr<OlsPlan> own_plan(OlsPlan* p) { return std::shared_ptr<OlsPlan>(p, [](OlsPlan* q) { ols_plan_destroy(q); }); }
+
 template <typename T>
-int convolve_taps(Vec<T>* v, const T* h_dev, size_t L, bool h_complex, T** Hs_cache, size_t* Hs_M, bool* Hs_valid) {
+int convolve_taps(Vec<T>* v, const T* h_dev, size_t L, bool h_complex, PlanCache* cache) {
     const size_t N = points_of(v);
     int rc = ensure_scratch(v, v->len);
     if (rc) return rc;
@@ -384,21 +398,24 @@ int convolve_taps(Vec<T>* v, const T* h_dev, size_t L, bool h_complex, T** Hs_ca
     if (L <= direct_max) {
         rc = fir_convolve<T>(v->d, v->scratch, h_dev, N, 1, L, cl, v->is_complex, h_complex, g_stream);
     } else if (L <= ols_max_taps<T>()) {
-        const size_t M = ols_block_len<T>(L, v->is_complex != 0);
-        T* Hs = nullptr;
-        bool own = false;
-        if (Hs_cache && *Hs_valid && *Hs_M == M) Hs = *Hs_cache;
-        else {
-            BDSP_CUDA_OK(cudaMalloc(&Hs, ols_spectrum_bytes<T>(M)));
-            rc = ols_prepare<T>(h_dev, L, !h_complex, Hs, M, g_stream);
-            if (rc) { cudaFree(Hs); return rc; }
-            if (Hs_cache) {
-                if (*Hs_cache) { cudaStreamSynchronize(g_stream); cudaFree(*Hs_cache); }
-                *Hs_cache = Hs; *Hs_M = M; *Hs_valid = true;
-            } else own = true;
+        std::shared_ptr<OlsPlan> plan;
+        if (cache) {
+            std::lock_guard<std::mutex> lk(*cache->mu);
+            if (*cache->plan && *cache->plan_version == cache->version && *cache->plan_complex_signal == v->is_complex)
+                plan = *cache->plan;
+            else {
+                plan = own_plan(ols_plan_create<T>(h_dev, L, !h_complex, v->is_complex != 0, g_stream));
+                if (!plan) return -1;
+                // other streams may use the plan as soon as it is published
+                BDSP_CUDA_OK(cudaStreamSynchronize(g_stream));
+                *cache->plan = plan; *cache->plan_version = cache->version; *cache->plan_complex_signal = v->is_complex;
+            }
+        } else {
+            plan = own_plan(ols_plan_create<T>(h_dev, L, !h_complex, v->is_complex != 0, g_stream));
+            if (!plan) return -1;
         }
-        rc = ols_convolve<T>(v->d, v->scratch, N, 1, L, Hs, M, !v->is_complex, g_stream);
-        if (own) { cudaStreamSynchronize(g_stream); cudaFree(Hs); }
+        rc = ols_plan_convolve<T>(plan.get(), v->d, v->scratch, N, 1, !v->is_complex, g_stream);
+        // an uncached plan is destroyed here (ols_plan_destroy synchronises the device first)
     } else {
         rc = fft_convolve_full<T>(v->d, v->scratch, h_dev, N, 1, L, !v->is_complex, !h_complex, g_stream);
     }
@@ -462,10 +479,8 @@ template <typename T> Res<T> op_convolve_signal(Vec<T>* v, Vec<T>* h) {
         if (N) cudaMemsetAsync(v->d, 0, v->len * sizeof(T), g_stream);
         return done(v, 0);
     }
-    bool valid = h->Hs_version == h->version;
-    int rc = convolve_taps<T>(v, h->d, L, h->is_complex, &h->Hs, &h->Hs_M, &valid);
-    if (valid) h->Hs_version = h->version;
-    return done(v, rc);
+    PlanCache cache{&h->plan_mu, &h->plan, &h->plan_version, &h->plan_complex_signal, h->version};
+    return done(v, convolve_taps<T>(v, h->d, L, h->is_complex, &cache));
 }
 
 template <typename T> Res<T> op_convolve_fn(Vec<T>* v, const RealFn<T>& f, T ratio, size_t len) {
@@ -480,7 +495,7 @@ template <typename T> Res<T> op_convolve_fn(Vec<T>* v, const RealFn<T>& f, T rat
     if (f.kind != 2) {
         size_t cnt = 0;
         const T* cached = table_cache_find<T>(key, &cnt);
-        if (cached) return done(v, convolve_taps<T>(v, cached, cnt, false, nullptr, nullptr, nullptr));
+        if (cached) return done(v, convolve_taps<T>(v, cached, cnt, false, nullptr));
     }
     std::vector<T> taps;
     if (simd_branch) {
@@ -513,12 +528,12 @@ template <typename T> Res<T> op_convolve_fn(Vec<T>* v, const RealFn<T>& f, T rat
     }
     if (f.kind != 2) {
         const T* cached = table_cache_insert<T>(key, taps);
-        if (cached) return done(v, convolve_taps<T>(v, cached, taps.size(), false, nullptr, nullptr, nullptr));
+        if (cached) return done(v, convolve_taps<T>(v, cached, taps.size(), false, nullptr));
     }
     T* h_dev = nullptr;
     int rc = upload_table(taps, &h_dev);
     if (rc) return done(v, rc);
-    rc = convolve_taps<T>(v, h_dev, taps.size(), false, nullptr, nullptr, nullptr);
+    rc = convolve_taps<T>(v, h_dev, taps.size(), false, nullptr);
     table_consumed();
     return done(v, rc);
 }
@@ -544,7 +559,7 @@ Res<T> op_convolve_cfn(Vec<T>* v, CT (*fn)(const void*, T), const void* data, T 
     T* h_dev = nullptr;
     int rc = upload_table(t, &h_dev);
     if (rc) return done(v, rc);
-    rc = convolve_taps<T>(v, h_dev, 2 * L + 1, true, nullptr, nullptr, nullptr);
+    rc = convolve_taps<T>(v, h_dev, 2 * L + 1, true, nullptr);
     table_consumed();
     return done(v, rc);
 }
@@ -1053,6 +1068,7 @@ template <typename T> Res<T> op_cum_sum(Vec<T>* v) {
     int rc = ensure_scratch(v, v->len);
     if (rc) return done(v, rc);
     void* work = workspace(math_cumsum_workspace(points, lanes, sizeof(T)), 3);
+    if (!work) return done(v, -1001);
     rc = math_cumsum<T>(v->d, v->scratch, work, points, lanes, g_stream);
     if (rc) return done(v, rc);
     trade(v);
@@ -1272,8 +1288,8 @@ int scale_mul_mag_phase(Vec<T>* v, T cre, T cim, const Vec<T>* w, Vec<T>* mag, V
 
 struct ConvPlan {
     int is64;
-    size_t L, M;
-    void* Hs;       // overlap-save spectrum (M complex) or nullptr
+    size_t L;
+    OlsPlan* ols;   // overlap-save plan or nullptr
     void* taps;     // copy of the taps (L complex) for the direct / full-length paths
 };
 
@@ -1281,14 +1297,12 @@ template <typename T> ConvPlan* conv_plan_create(const void* h_dev, size_t L) {
     typedef typename CpxOf<T>::type C;
     if (!h_dev || !L) { set_last_error("conv plan: empty impulse response"); return nullptr; }
     ConvPlan* p = new ConvPlan();
-    p->is64 = sizeof(T) == 8; p->L = L; p->M = 0; p->Hs = nullptr; p->taps = nullptr;
+    p->is64 = sizeof(T) == 8; p->L = L; p->ols = nullptr; p->taps = nullptr;
     if (cudaMalloc(&p->taps, L * sizeof(C)) != cudaSuccess) { delete p; return nullptr; }
     cudaMemcpyAsync(p->taps, h_dev, L * sizeof(C), cudaMemcpyDeviceToDevice, g_stream);
     if (L > 24 && L <= ols_max_taps<T>()) {
-        p->M = ols_block_len<T>(L, true);
-        if (cudaMalloc(&p->Hs, ols_spectrum_bytes<T>(p->M)) != cudaSuccess || ols_prepare<T>(p->taps, L, 0, p->Hs, p->M, g_stream) != 0) {
-            cudaFree(p->taps); if (p->Hs) cudaFree(p->Hs); delete p; return nullptr;
-        }
+        p->ols = ols_plan_create<T>(p->taps, L, 0, true, g_stream);
+        if (!p->ols) { cudaFree(p->taps); delete p; return nullptr; }
     }
     return p;
 }
@@ -1297,7 +1311,7 @@ template <typename T> int conv_rows(const void* in, void* out, size_t points, si
     if (!p || p->is64 != (sizeof(T) == 8)) { set_last_error("conv rows: plan precision mismatch"); return -2; }
     if (points < p->L) return E_ARG_LEN;
     if (!points || !rows) return 0;
-    if (p->Hs) return ols_convolve<T>(in, out, points, rows, p->L, p->Hs, p->M, 0, g_stream);
+    if (p->ols) return ols_plan_convolve<T>(p->ols, in, out, points, rows, 0, g_stream);
     if (p->L <= 24) return fir_convolve<T>(in, out, p->taps, points, rows, p->L, p->L - p->L / 2, 1, 1, g_stream);
     return fft_convolve_full<T>(in, out, p->taps, points, rows, p->L, 0, 0, g_stream);
 }
@@ -1393,8 +1407,9 @@ template <typename R, typename T> static inline R as_res(Res<T> r) {
     extern "C" HV* clone##S(HV* v) {                                                                                   \
         Vec<T>* s = VEC(v);                                                                                            \
         Vec<T>* c = vec_new<T>(s->is_complex, s->domain, (T)0, 0, s->delta);                                           \
-        if (reserve(&c->d, &c->cap, s->len, false, 0) == 0 && s->len)                                                  \
-            cudaMemcpyAsync(c->d, s->d, s->len * sizeof(T), cudaMemcpyDeviceToDevice, g_stream);                       \
+        if (!c) return nullptr;                                                                                        \
+        if (reserve(&c->d, &c->cap, s->len, false, 0) != 0) { vec_delete(c); return nullptr; }                          \
+        if (s->len) cudaMemcpyAsync(c->d, s->d, s->len * sizeof(T), cudaMemcpyDeviceToDevice, g_stream);               \
         c->len = s->len;                                                                                               \
         return reinterpret_cast<HV*>(c);                                                                               \
     }                                                                                                                  \
@@ -1561,7 +1576,8 @@ template <typename R, typename T> static inline R as_res(Res<T> r) {
     extern "C" int32_t bdsp_upload##S(HV* v, const T* host, size_t len) { return upload(VEC(v), host, len); }          \
     extern "C" int32_t bdsp_download##S(const HV* v, T* host, size_t len) { return download(CVEC(v), host, len, true); } \
     extern "C" int32_t bdsp_download_async##S(const HV* v, T* host, size_t len) { return download(CVEC(v), host, len, false); } \
-    extern "C" void* bdsp_device_ptr##S(HV* v) { return VEC(v)->d; }                                                   \
+    /* mutable access: caches derived from the vector's contents (the overlap-save plan) are invalidated */             \
+    extern "C" void* bdsp_device_ptr##S(HV* v) { VEC(v)->version++; return VEC(v)->d; }                                \
     extern "C" int32_t bdsp_scale_mul_mag_phase##S(HV* v, T cre, T cim, const HV* w, HV* m, HV* p, int32_t wb) {       \
         return scale_mul_mag_phase<T>(VEC(v), cre, cim, CVEC(w), VEC(m), VEC(p), wb);                                  \
     }
@@ -1653,7 +1669,7 @@ extern "C" void bdsp_conv_plan_destroy(BdspConvPlan* plan) {
     ConvPlan* p = reinterpret_cast<ConvPlan*>(plan);
     if (!p) return;
     cudaStreamSynchronize(g_stream);
-    if (p->Hs) cudaFree(p->Hs);
+    if (p->ols) ols_plan_destroy(p->ols);
     if (p->taps) cudaFree(p->taps);
     delete p;
 }
@@ -1669,6 +1685,10 @@ extern "C" void* bdsp_malloc(size_t bytes) {
     return p;
 }
 extern "C" void bdsp_free(void* p) { if (p) { cudaStreamSynchronize(g_stream); cudaFree(p); } }
+extern "C" size_t bdsp_mem_free(void) {
+    size_t f = 0, t = 0;
+    return cudaMemGetInfo(&f, &t) == cudaSuccess ? f : 0;
+}
 extern "C" void* bdsp_malloc_host(size_t bytes) {
     void* p = nullptr;
     if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { set_last_error("bdsp_malloc_host(%zu) failed", bytes); return nullptr; }

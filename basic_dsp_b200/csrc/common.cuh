@@ -32,15 +32,10 @@ unsigned long long launch_count();
         BDSP_CUDA_OK(cudaGetLastError());                                                   \
     } while (0)
 
-#define BDSP_CUDA_ABORT(expr)                                                               \
-    do {                                                                                    \
-        cudaError_t _e = (expr);                                                            \
-        if (_e != cudaSuccess) {                                                            \
-            fprintf(stderr, "basic_dsp_b200 fatal: %s:%d: %s -> %s\n", __FILE__, __LINE__,  \
-                    #expr, cudaGetErrorString(_e));                                         \
-            abort();                                                                        \
-        }                                                                                   \
-    } while (0)
+// workspace(): nullptr (and last error set) when the allocation fails
+#define BDSP_WS(ptr, T_, bytes, slot)                                                       \
+    T_ ptr = reinterpret_cast<T_>(bdsp::workspace((bytes), (slot)));                        \
+    if (!ptr) return -1001
 
 // --- complex scalar types ------------------------------------------------------------------
 template <typename T> struct CpxOf;

@@ -84,9 +84,10 @@ __global__ void ols_pad_h_kernel(const void* __restrict__ h_, typename CpxOf<T>:
 template <typename T> size_t ols_block_len(size_t L, bool complex_signal) {
     // same rule as the reference (fft_len >= 4*overlap, convolution.rs:323-331) with a 4096 floor so
     // that the block transform amortises its overlap; capped by the shared-memory transform limit.
-    // c32 signals keep 4096-point blocks up to 2046 taps: the fused kernel at 50 % block efficiency (0.50 ms per 2^26
-    // samples at 2047 taps) still beats the generic 8192-point kernel (1.36 ms).
+    // c32 signals: fused 4096-point blocks up to 2046 taps (+ an 8192-point plan next to it, see OlsPlan::M2),
+    // fused 8192-point blocks up to 4094 taps.
     if (sizeof(T) == 4 && complex_signal && L >= 2 && L <= 2046) return 4096;
+    if (sizeof(T) == 4 && complex_signal && L >= 2 && L <= 4094) return 8192;
     size_t m = next_pow2(4 * (L > 1 ? L - 1 : 1));
     if (m < 4096) m = 4096;
     if (m > fft_block_max_n<T>()) m = fft_block_max_n<T>();
@@ -95,34 +96,109 @@ template <typename T> size_t ols_block_len(size_t L, bool complex_signal) {
 
 template <typename T> size_t ols_max_taps() { return fft_block_max_n<T>() / 2; }
 
-// the spectrum buffer holds Hs (M complex, natural order) followed by the same spectrum in the
-// layout of the fused 4096-point kernel (planar, position order; f32 only)
-template <typename T> size_t ols_spectrum_bytes(size_t M) { return 2 * M * sizeof(typename CpxOf<T>::type); }
-
 bool ols4096_applicable(size_t N, size_t L, size_t M);
 int ols4096_prepare(const void* Hs, void* Hpos, size_t L, cudaStream_t st);
-int ols4096_convolve(const void* x, void* y, size_t N, size_t batch, size_t L, const void* Hpos, cudaStream_t st);
+int ols4096_convolve(const void* x, void* y, size_t N, size_t batch, size_t L, const void* Hpos, cudaTextureObject_t htex, cudaStream_t st);
+bool ols8192_applicable(size_t N, size_t L);
+int ols8192_prepare(const void* Hs, void* Hpos, size_t L, cudaStream_t st);
+int ols8192_convolve(const void* x, void* y, size_t N, size_t batch, size_t L, const void* Hpos, cudaTextureObject_t htex, cudaStream_t st);
+long long ols8192_blocks(size_t N, size_t L);
 
+namespace {
+// Hs (2*M complex) <- FFT_M(pad(h)) / M, then the fused kernel's layout behind it (c32, M = 4096 / 8192)
 template <typename T>
-int ols_prepare(const void* h, size_t L, int h_is_real, void* Hs, size_t M, cudaStream_t st) {
+int ols_spectrum(const void* h, size_t L, int h_is_real, size_t M, bool fused, void** Hs_out, cudaTextureObject_t* tex, cudaStream_t st) {
     typedef typename CpxOf<T>::type C;
+    void* Hs = nullptr;
+    BDSP_CUDA_OK(cudaMalloc(&Hs, 2 * M * sizeof(C)));
     ols_pad_h_kernel<T><<<(unsigned)((M + 255) / 256), 256, 0, st>>>(h, reinterpret_cast<C*>(Hs), (int)L, (int)M, h_is_real);
-    BDSP_LAUNCHED();
+    int rc = cudaGetLastError() == cudaSuccess ? 0 : -1;
+    count_launch();
     FftOpts o;
     o.scale = 1.0 / (double)M;
-    int rc = fft_exec<T>(Hs, Hs, M, 1, o, nullptr, 0, st);
-    if (rc) return rc;
-    if (sizeof(T) == 4 && M == 4096) rc = ols4096_prepare(Hs, reinterpret_cast<C*>(Hs) + M, L, st);
-    return rc;
+    if (!rc) rc = fft_exec<T>(Hs, Hs, M, 1, o, nullptr, 0, st);
+    if (!rc && fused) {
+        void* Hpos = reinterpret_cast<C*>(Hs) + M;
+        rc = M == 4096 ? ols4096_prepare(Hs, Hpos, L, st) : ols8192_prepare(Hs, Hpos, L, st);
+        if (!rc) {
+            cudaResourceDesc rd = {};
+            rd.resType = cudaResourceTypeLinear;
+            rd.res.linear.devPtr = Hpos;
+            rd.res.linear.desc = cudaCreateChannelDesc<float4>();
+            rd.res.linear.sizeInBytes = 2 * M * sizeof(float);
+            cudaTextureDesc td = {};
+            td.readMode = cudaReadModeElementType;
+            if (cudaCreateTextureObject(tex, &rd, &td, nullptr) != cudaSuccess) { set_last_error("ols plan: texture object"); rc = -1; }
+        }
+    }
+    if (rc) { cudaFree(Hs); return rc; }
+    *Hs_out = Hs;
+    return 0;
+}
+}  // namespace
+
+template <typename T>
+OlsPlan* ols_plan_create(const void* h, size_t L, int h_is_real, bool complex_signal, cudaStream_t st) {
+    if (!h || !L || L > ols_max_taps<T>()) { set_last_error("ols plan: unsupported impulse response length %zu", L); return nullptr; }
+    OlsPlan* p = new OlsPlan();
+    p->is64 = sizeof(T) == 8; p->L = L; p->h_is_real = h_is_real;
+    if (cudaGetDevice(&p->device) != cudaSuccess) { delete p; return nullptr; }
+    p->M = ols_block_len<T>(L, complex_signal);
+    const bool fused = sizeof(T) == 4 && complex_signal && L >= 2 && (p->M == 4096 || p->M == 8192);
+    int rc = ols_spectrum<T>(h, L, h_is_real, p->M, fused, &p->Hs, &p->htex, st);
+    if (!rc && fused && p->M == 4096) {
+        p->M2 = 8192;
+        rc = ols_spectrum<T>(h, L, h_is_real, p->M2, true, &p->Hs2, &p->htex2, st);
+    }
+    if (rc) { ols_plan_destroy(p); return nullptr; }
+    return p;
+}
+
+void ols_plan_destroy(OlsPlan* p) {
+    if (!p) return;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (cur != p->device) cudaSetDevice(p->device);
+    cudaDeviceSynchronize();    // kernels of any stream may still read the spectra
+    if (p->htex) cudaDestroyTextureObject(p->htex);
+    if (p->htex2) cudaDestroyTextureObject(p->htex2);
+    if (p->Hs) cudaFree(p->Hs);
+    if (p->Hs2) cudaFree(p->Hs2);
+    if (cur != p->device) cudaSetDevice(cur);
+    delete p;
+}
+
+// Choice between the two fused block lengths where both apply (2 <= L <= 2046).  Measured on B200, 64 x 2^20 points
+// (profiles/r2_ols_block_choice.txt): per POINT the 4096-point kernel is ~20 % faster (four independently phased CTAs per
+// SM against two), so the 8192-point kernel only wins once its better block efficiency (M - L)/M outweighs that.
+#ifndef BDSP_OLS8192_MIN_TAPS
+#define BDSP_OLS8192_MIN_TAPS 1450
+#endif
+#ifndef BDSP_OLS8192_MIN_BLOCKS
+#define BDSP_OLS8192_MIN_BLOCKS 592
+#endif
+static int ols_forced_block() {   // BDSP_OLS_FORCE=4096|8192: measurement override
+    static const int v = [] { const char* e = getenv("BDSP_OLS_FORCE"); return e ? atoi(e) : 0; }();
+    return v;
 }
 
 template <typename T>
-int ols_convolve(const void* x, void* y, size_t N, size_t batch, size_t L, const void* Hs, size_t M, int is_real,
-                 cudaStream_t st) {
+int ols_plan_convolve(const OlsPlan* p, const void* x, void* y, size_t N, size_t batch, int is_real, cudaStream_t st) {
     typedef typename CpxOf<T>::type C;
+    if (!p || p->is64 != (sizeof(T) == 8)) { set_last_error("ols_convolve: plan precision mismatch"); return -2; }
     if (x == y) { set_last_error("ols_convolve: in-place operation is not supported"); return -3; }
-    if (sizeof(T) == 4 && !is_real && ols4096_applicable(N, L, M))
-        return ols4096_convolve(x, y, N, batch, L, reinterpret_cast<const C*>(Hs) + M, st);
+    const size_t L = p->L, M = p->M;
+    if (sizeof(T) == 4 && !is_real) {
+        const int force = ols_forced_block();
+        const bool want8 = force ? force == 8192
+                                 : (L >= BDSP_OLS8192_MIN_TAPS && ols8192_blocks(N, L) * (long long)batch >= BDSP_OLS8192_MIN_BLOCKS);
+        if (p->htex2 && ols8192_applicable(N, L) && want8)
+            return ols8192_convolve(x, y, N, batch, L, reinterpret_cast<const C*>(p->Hs2) + p->M2, p->htex2, st);
+        if (p->htex && M == 4096 && ols4096_applicable(N, L, M))
+            return ols4096_convolve(x, y, N, batch, L, reinterpret_cast<const C*>(p->Hs) + M, p->htex, st);
+        if (p->htex && M == 8192 && ols8192_applicable(N, L))
+            return ols8192_convolve(x, y, N, batch, L, reinterpret_cast<const C*>(p->Hs) + M, p->htex, st);
+    }
     const size_t step = M - L + 1;
     const long long bpv = (long long)((N + step - 1) / step);
     const int log2M = ilog2(M);
@@ -131,14 +207,15 @@ int ols_convolve(const void* x, void* y, size_t N, size_t batch, size_t L, const
     const long long grid = bpv * (long long)batch;
     if (grid > 0x7fffffffll) { set_last_error("ols_convolve: grid too large"); return -2; }
     const C* tw = twiddle_table<T>();
+    if (!tw) return -1001;
     if (is_real) {
         if (smem > 48 * 1024) BDSP_CUDA_OK(cudaFuncSetAttribute(ols_conv_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ols_conv_kernel<T, true><<<(unsigned)grid, threads, smem, st>>>(x, y, (long long)N, (long long)batch, (int)L, log2M, bpv,
-                                                                       reinterpret_cast<const C*>(Hs), tw);
+                                                                       reinterpret_cast<const C*>(p->Hs), tw);
     } else {
         if (smem > 48 * 1024) BDSP_CUDA_OK(cudaFuncSetAttribute(ols_conv_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ols_conv_kernel<T, false><<<(unsigned)grid, threads, smem, st>>>(x, y, (long long)N, (long long)batch, (int)L, log2M, bpv,
-                                                                        reinterpret_cast<const C*>(Hs), tw);
+                                                                        reinterpret_cast<const C*>(p->Hs), tw);
     }
     BDSP_LAUNCHED();
     return 0;
@@ -309,8 +386,9 @@ int fft_convolve_full(const void* x, void* y, const void* h, size_t N, size_t ba
                       int h_is_real, cudaStream_t st) {
     typedef typename CpxOf<T>::type C;
     const size_t cl = L - L / 2;
-    C* Hf = reinterpret_cast<C*>(workspace(N * sizeof(C), 2));
-    C* X = reinterpret_cast<C*>(workspace(N * batch * sizeof(C), 3));
+    // slots 4 / 5: fft_exec below uses slots 0..2 for its own passes (mixed-radix interleave, chirp-z ping-pong)
+    BDSP_WS(Hf, C*, N * sizeof(C), 4);
+    BDSP_WS(X, C*, N * batch * sizeof(C), 5);
     pad_roll_h_kernel<T><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(h, Hf, (long long)L, (long long)N, (long long)(cl - 1), h_is_real);
     BDSP_LAUNCHED();
     FftOpts f;
@@ -334,11 +412,9 @@ int fft_convolve_full(const void* x, void* y, const void* h, size_t N, size_t ba
 }
 
 #define BDSP_INST(T)                                                                                                    \
-    template size_t ols_block_len<T>(size_t, bool);                                                                           \
     template size_t ols_max_taps<T>();                                                                                  \
-    template size_t ols_spectrum_bytes<T>(size_t);                                                                      \
-    template int ols_prepare<T>(const void*, size_t, int, void*, size_t, cudaStream_t);                                  \
-    template int ols_convolve<T>(const void*, void*, size_t, size_t, size_t, const void*, size_t, int, cudaStream_t);    \
+    template OlsPlan* ols_plan_create<T>(const void*, size_t, int, bool, cudaStream_t);                                 \
+    template int ols_plan_convolve<T>(const OlsPlan*, const void*, void*, size_t, size_t, int, cudaStream_t);           \
     template int fir_convolve<T>(const void*, void*, const void*, size_t, size_t, size_t, size_t, int, int, cudaStream_t); \
     template int fft_convolve_full<T>(const void*, void*, const void*, size_t, size_t, size_t, int, int, cudaStream_t);
 BDSP_INST(float)

@@ -14,6 +14,7 @@
 // ifft_shift / scaling / real->complex are fused into the load of the first pass, fft_shift and
 // magnitude into the store of the last one (FftOpts).
 #include <map>
+#include <memory>
 #include <mutex>
 #include <vector>
 
@@ -45,9 +46,10 @@ struct DeviceState {
 std::mutex g_mu;
 std::map<int, DeviceState> g_dev;
 
-DeviceState& dev_state() {
+// nullptr (last error set) when the device cannot be queried or the tables cannot be allocated
+DeviceState* dev_state() {
     int d = 0;
-    BDSP_CUDA_ABORT(cudaGetDevice(&d));
+    if (cudaGetDevice(&d) != cudaSuccess) { set_last_error("cudaGetDevice failed"); return nullptr; }
     std::lock_guard<std::mutex> lk(g_mu);
     DeviceState& s = g_dev[d];
     if (!s.tw32) {
@@ -64,53 +66,80 @@ DeviceState& dev_state() {
             h64[i].x = (double)c; h64[i].y = (double)sn;
             h32[i].x = (float)c; h32[i].y = (float)sn;
         }
-        BDSP_CUDA_ABORT(cudaMalloc(&s.tw32, sizeof(float2) * BDSP_TW_LEN));
-        BDSP_CUDA_ABORT(cudaMalloc(&s.tw64, sizeof(double2) * BDSP_TW_LEN));
-        BDSP_CUDA_ABORT(cudaMemcpy(s.tw32, h32.data(), sizeof(float2) * BDSP_TW_LEN, cudaMemcpyHostToDevice));
-        BDSP_CUDA_ABORT(cudaMemcpy(s.tw64, h64.data(), sizeof(double2) * BDSP_TW_LEN, cudaMemcpyHostToDevice));
-        BDSP_CUDA_ABORT(cudaDeviceGetAttribute(&s.sms, cudaDevAttrMultiProcessorCount, d));
+        float2* t32 = nullptr;
+        double2* t64 = nullptr;
+        int sms = 0;
+        if (cudaMalloc(&t32, sizeof(float2) * BDSP_TW_LEN) != cudaSuccess || cudaMalloc(&t64, sizeof(double2) * BDSP_TW_LEN) != cudaSuccess ||
+            cudaMemcpy(t32, h32.data(), sizeof(float2) * BDSP_TW_LEN, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(t64, h64.data(), sizeof(double2) * BDSP_TW_LEN, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d) != cudaSuccess) {
+            set_last_error("twiddle tables: %s", cudaGetErrorString(cudaGetLastError()));
+            if (t32) cudaFree(t32);
+            if (t64) cudaFree(t64);
+            return nullptr;
+        }
+        s.tw64 = t64; s.sms = sms; s.tw32 = t32;
     }
-    return s;
+    return &s;
 }
 }  // namespace
 
-int sm_count() { return dev_state().sms; }
+int sm_count() { DeviceState* s = dev_state(); return s ? s->sms : BDSP_SM_COUNT_DEFAULT; }
 
-template <> const float2* twiddle_table<float>() { return dev_state().tw32; }
-template <> const double2* twiddle_table<double>() { return dev_state().tw64; }
+template <> const float2* twiddle_table<float>() { DeviceState* s = dev_state(); return s ? s->tw32 : nullptr; }
+template <> const double2* twiddle_table<double>() { DeviceState* s = dev_state(); return s ? s->tw64 : nullptr; }
 
-// Workspaces are kept per (device, stream): work queued on different streams may run concurrently, so it must not
-// share scratch buffers.  The calling thread binds its stream with workspace_bind_stream (capi: bdsp_set_stream).
+// Workspaces are kept per host THREAD and (device, stream): threads that did not bind a stream all run on the legacy
+// default stream, where their multi-kernel operations may interleave, so scratch buffers are never shared between
+// threads (the reference is safe for concurrent use of distinct vectors).  The calling thread binds its stream with
+// workspace_bind_stream (capi: bdsp_set_stream).  Slots: 0..3 the transforms and reductions, 4..5 the full-length
+// convolution (its buffers stay live across nested fft_exec calls, which use 0..2).
 namespace {
 thread_local cudaStream_t tl_ws_stream = nullptr;
-struct WsSet { void* p[4] = {nullptr, nullptr, nullptr, nullptr}; size_t bytes[4] = {0, 0, 0, 0}; };
-std::map<std::pair<int, cudaStream_t>, WsSet> g_ws;
+constexpr int WS_SLOTS = 6;
+struct WsSet { void* p[WS_SLOTS] = {}; size_t bytes[WS_SLOTS] = {}; };
+struct WsMap {
+    std::map<std::pair<int, cudaStream_t>, WsSet> m;
+    ~WsMap() {   // thread exit: give the memory back (errors ignored: the context may already be gone at process exit)
+        for (auto& kv : m)
+            for (int i = 0; i < WS_SLOTS; i++) if (kv.second.p[i]) cudaFree(kv.second.p[i]);
+    }
+};
+thread_local WsMap tl_ws;
 }  // namespace
 
 void workspace_bind_stream(cudaStream_t st) { tl_ws_stream = st; }
 
 void workspace_release_stream(cudaStream_t st) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    for (auto it = g_ws.begin(); it != g_ws.end();) {
+    for (auto it = tl_ws.m.begin(); it != tl_ws.m.end();) {
         if (it->first.second == st) {
-            for (int i = 0; i < 4; i++) if (it->second.p[i]) cudaFree(it->second.p[i]);
-            it = g_ws.erase(it);
+            for (int i = 0; i < WS_SLOTS; i++) if (it->second.p[i]) cudaFree(it->second.p[i]);
+            it = tl_ws.m.erase(it);
         } else ++it;
     }
 }
 
 void* workspace(size_t bytes, int slot) {
     int d = 0;
-    BDSP_CUDA_ABORT(cudaGetDevice(&d));
-    std::lock_guard<std::mutex> lk(g_mu);
-    WsSet& s = g_ws[std::make_pair(d, tl_ws_stream)];
+    if (cudaGetDevice(&d) != cudaSuccess) { set_last_error("cudaGetDevice failed"); return nullptr; }
+    WsSet& s = tl_ws.m[std::make_pair(d, tl_ws_stream)];
     if (s.bytes[slot] < bytes) {
         if (s.p[slot]) {
-            BDSP_CUDA_ABORT(cudaStreamSynchronize(tl_ws_stream));
-            BDSP_CUDA_ABORT(cudaFree(s.p[slot]));
+            cudaStreamSynchronize(tl_ws_stream);
+            cudaFree(s.p[slot]);
+            s.p[slot] = nullptr; s.bytes[slot] = 0;
         }
         size_t want = bytes + bytes / 8;
-        BDSP_CUDA_ABORT(cudaMalloc(&s.p[slot], want));
+        if (cudaMalloc(&s.p[slot], want) != cudaSuccess) {
+            cudaGetLastError();
+            if (cudaMalloc(&s.p[slot], bytes) != cudaSuccess) {
+                cudaGetLastError();
+                s.p[slot] = nullptr;
+                set_last_error("workspace: out of device memory (%zu bytes)", bytes);
+                return nullptr;
+            }
+            want = bytes;
+        }
         s.bytes[slot] = want;
     }
     return s.p[slot];
@@ -516,6 +545,7 @@ int launch_block(const void* in, void* out, size_t n, size_t batch, bool real_in
     const size_t smem = spad_host(n * nfft) * sizeof(C);
     const long long grid = ((long long)batch + nfft - 1) / nfft;
     const C* tw = twiddle_table<T>();
+    if (!tw) return -1001;
 #define BDSP_LAUNCH_BLOCK(RI, MG)                                                                   \
     do {                                                                                            \
         int rc = set_smem(fft_block_kernel<T, INV, RI, MG>, smem);                                  \
@@ -542,7 +572,9 @@ int launch_tile(const TileParams& p, long long batch, T scale, cudaStream_t st) 
     const long long grid = batch * p.o1_count * (p.lanes / p.ct);
     int rc = set_smem(fft_tile_kernel<T, INV>, smem);
     if (rc) return rc;
-    fft_tile_kernel<T, INV><<<(unsigned)grid, threads, smem, st>>>(p, scale, twiddle_table<T>());
+    const typename CpxOf<T>::type* twt = twiddle_table<T>();
+    if (!twt) return -1001;
+    fft_tile_kernel<T, INV><<<(unsigned)grid, threads, smem, st>>>(p, scale, twt);
     BDSP_LAUNCHED();
     return 0;
 }
@@ -637,7 +669,78 @@ struct BluesteinKey {
         return dev < o.dev;
     }
 };
-std::map<BluesteinKey, void*> g_bluestein;
+// Cached chirp-filter spectra.  Entries are reference counted (a caller keeps its entry alive while its kernels are
+// queued; the deleter synchronises the device before freeing), published only after the stream that computed them has
+// been synchronised (any stream of the device may consume them), and evicted least-recently-used first once the cache
+// holds more than BLUESTEIN_CACHE_BYTES.
+struct BluesteinFilter {
+    void* spec = nullptr; size_t bytes = 0; int dev = 0;
+    ~BluesteinFilter() {
+        if (!spec) return;
+        int cur = 0;
+        cudaGetDevice(&cur);
+        if (cur != dev) cudaSetDevice(dev);
+        cudaDeviceSynchronize();
+        cudaFree(spec);
+        if (cur != dev) cudaSetDevice(cur);
+    }
+};
+struct BluesteinEntry { std::shared_ptr<BluesteinFilter> f; unsigned long long used = 0; };
+constexpr size_t BLUESTEIN_CACHE_BYTES = 1ull << 30;
+std::map<BluesteinKey, BluesteinEntry> g_bluestein;
+unsigned long long g_bluestein_clock = 0;
+
+template <typename T, bool INV>
+int fft_any(const void* in, void* out, size_t n, size_t batch, const FftOpts& o, void* work, size_t work_bytes,
+            cudaStream_t st);
+
+// spectrum of the chirp filter for length n (M = padded length), from the cache or computed on `st`
+template <typename T, bool INV>
+int bluestein_filter(size_t n, size_t M, void* w0, cudaStream_t st, std::shared_ptr<BluesteinFilter>* out) {
+    typedef typename CpxOf<T>::type C;
+    int d = 0;
+    BDSP_CUDA_OK(cudaGetDevice(&d));
+    const BluesteinKey key{n, INV ? 1 : 0, sizeof(T) == 8 ? 1 : 0, d};
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_bluestein.find(key);
+        if (it != g_bluestein.end()) { it->second.used = ++g_bluestein_clock; *out = it->second.f; return 0; }
+    }
+    auto f = std::make_shared<BluesteinFilter>();
+    f->dev = d; f->bytes = M * sizeof(C);
+    BDSP_CUDA_OK(cudaMalloc(&f->spec, f->bytes));
+    bluestein_filter_kernel<T, INV><<<(unsigned)((M + 255) / 256), 256, 0, st>>>(reinterpret_cast<C*>(f->spec), (long long)n, (long long)M);
+    BDSP_LAUNCHED();
+    OutMap plain; plain.seq_group = 1; plain.oes = 1; plain.group_stride = (long long)M; plain.rot = 0; plain.rot_n = (long long)M;
+    int rc = fft_pow2<T, false>(f->spec, f->spec, M, 1, false, false, 0, (T)1, plain, w0, st);
+    if (rc) return rc;
+    BDSP_CUDA_OK(cudaStreamSynchronize(st));
+    std::vector<std::shared_ptr<BluesteinFilter>> evicted;   // destroyed (device sync + free) outside the lock
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_bluestein.find(key);
+        if (it != g_bluestein.end()) {   // another thread computed the same filter meanwhile: use theirs, drop ours
+            it->second.used = ++g_bluestein_clock;
+            evicted.push_back(f);
+            f = it->second.f;
+        } else {
+            size_t total = f->bytes;
+            for (auto& kv : g_bluestein) total += kv.second.f->bytes;
+            while (total > BLUESTEIN_CACHE_BYTES && !g_bluestein.empty()) {
+                auto lru = g_bluestein.begin();
+                for (auto jt = g_bluestein.begin(); jt != g_bluestein.end(); ++jt)
+                    if (jt->second.used < lru->second.used) lru = jt;
+                total -= lru->second.f->bytes;
+                evicted.push_back(lru->second.f);
+                g_bluestein.erase(lru);
+            }
+            BluesteinEntry e; e.f = f; e.used = ++g_bluestein_clock;
+            g_bluestein[key] = e;
+        }
+    }
+    *out = f;
+    return 0;
+}
 
 template <typename T, bool INV>
 int fft_any(const void* in, void* out, size_t n, size_t batch, const FftOpts& o, void* work, size_t work_bytes,
@@ -657,7 +760,7 @@ int fft_any(const void* in, void* out, size_t n, size_t batch, const FftOpts& o,
             (n >= 4096 || batch % (4096 / n) == 0)) {
             // real f32 input in the throughput regime: one complexifying pass (4 B read + 8 B written per point) and the
             // packed complex passes beat the generic kernels that fuse the conversion into their first load
-            C* cx = reinterpret_cast<C*>(workspace(n * batch * sizeof(C), 1));
+            BDSP_WS(cx, C*, n * batch * sizeof(C), 1);
             int rc = ew_zero_interleave<T>(in, cx, n * batch, 2, 1, st);
             if (rc) return rc;
             FftOpts oc = o;
@@ -672,7 +775,7 @@ int fft_any(const void* in, void* out, size_t n, size_t batch, const FftOpts& o,
         void* w = work;
         if (n > fft_block_max_n<T>()) {
             size_t need = n * batch * sizeof(C);
-            if (!w || work_bytes < need) w = workspace(need, 0);
+            if (!w || work_bytes < need) { w = workspace(need, 0); if (!w) return -1001; }
         }
         if (sizeof(T) == 4 && n >= (1u << 15) && n <= (1u << 20)) {
             // packed two-pass path (fftp.cu): 16 B/point of traffic per pass
@@ -692,7 +795,7 @@ int fft_any(const void* in, void* out, size_t n, size_t batch, const FftOpts& o,
     const size_t q = n / P;
     if (q <= 31 && P >= 2) {
         size_t need = n * batch * sizeof(C);
-        C* w1 = reinterpret_cast<C*>(workspace(need, 1));
+        BDSP_WS(w1, C*, need, 1);
         const long long tot = (long long)(P * batch);
         const unsigned qgrid = (unsigned)((tot + 255) / 256);
         if (q == 3) dft_q_pass_kernel<T, INV, 3><<<qgrid, 256, 0, st>>>(in, w1, 3, (long long)P, (long long)batch, in_rot, o.real_input, scale);
@@ -711,7 +814,8 @@ int fft_any(const void* in, void* out, size_t n, size_t batch, const FftOpts& o,
         if (P > fft_block_max_n<T>() || packed_rows) {
             // row transforms into a second buffer (natural order), then one interleave pass
             void* w0 = P > fft_block_max_n<T>() ? workspace(need, 0) : nullptr;
-            C* w2 = reinterpret_cast<C*>(workspace(need, 2));
+            if (P > fft_block_max_n<T>() && !w0) return -1001;
+            BDSP_WS(w2, C*, need, 2);
             OutMap plainP; plainP.seq_group = 1; plainP.oes = 1; plainP.group_stride = (long long)P; plainP.rot = 0; plainP.rot_n = (long long)P;
             (void)plainP;
             FftOpts po;   // plain transform of the q*batch rows: takes the packed passes where they exist
@@ -727,28 +831,16 @@ int fft_any(const void* in, void* out, size_t n, size_t batch, const FftOpts& o,
     // Bluestein
     if (n >= (1ull << 31)) { set_last_error("fft: length %zu not supported", n); return -2; }
     const size_t M = next_pow2(2 * n - 1);
-    C* a = reinterpret_cast<C*>(workspace(M * batch * sizeof(C), 1));
-    C* bspec = nullptr;
-    {
-        int d = 0; BDSP_CUDA_OK(cudaGetDevice(&d));
-        BluesteinKey key{n, INV ? 1 : 0, sizeof(T) == 8 ? 1 : 0, d};
-        std::lock_guard<std::mutex> lk(g_mu);
-        auto it = g_bluestein.find(key);
-        if (it != g_bluestein.end()) bspec = reinterpret_cast<C*>(it->second);
-    }
+    BDSP_WS(a, C*, M * batch * sizeof(C), 1);
     OutMap plain; plain.seq_group = 1; plain.oes = 1; plain.group_stride = (long long)M; plain.rot = 0; plain.rot_n = (long long)M;
     void* w0 = M > fft_block_max_n<T>() ? workspace(M * (batch > 1 ? batch : 1) * sizeof(C), 0) : nullptr;
-    if (!bspec) {
-        BDSP_CUDA_OK(cudaMalloc(&bspec, M * sizeof(C)));
-        bluestein_filter_kernel<T, INV><<<(unsigned)((M + 255) / 256), 256, 0, st>>>(bspec, (long long)n, (long long)M);
-        BDSP_LAUNCHED();
-        int rc = fft_pow2<T, false>(bspec, bspec, M, 1, false, false, 0, (T)1, plain, w0, st);
-        if (rc) return rc;
-        int d = 0; BDSP_CUDA_OK(cudaGetDevice(&d));
-        BluesteinKey key{n, INV ? 1 : 0, sizeof(T) == 8 ? 1 : 0, d};
-        std::lock_guard<std::mutex> lk(g_mu);
-        g_bluestein[key] = bspec;
+    if (M > fft_block_max_n<T>() && !w0) return -1001;
+    std::shared_ptr<BluesteinFilter> filt;
+    {
+        const int rcf = bluestein_filter<T, INV>(n, M, w0, st, &filt);
+        if (rcf) return rcf;
     }
+    const C* bspec = reinterpret_cast<const C*>(filt->spec);
     const long long totM = (long long)(M * batch);
     bluestein_pre_kernel<T, INV><<<(unsigned)((totM + 255) / 256), 256, 0, st>>>(in, a, (long long)n, (long long)M, (long long)batch,
                                                                                  in_rot, o.real_input, scale);
@@ -759,7 +851,8 @@ int fft_any(const void* in, void* out, size_t n, size_t batch, const FftOpts& o,
     const size_t w0_bytes = w0 ? M * (batch > 1 ? batch : 1) * sizeof(C) : 0;
     int rc;
     const bool pingpong = !w0 && sizeof(T) == 4 && M >= 256 && M * batch >= (1u << 16);
-    C* b2 = pingpong ? reinterpret_cast<C*>(workspace(M * batch * sizeof(C), 2)) : a;
+    C* b2 = a;
+    if (pingpong) { b2 = reinterpret_cast<C*>(workspace(M * batch * sizeof(C), 2)); if (!b2) return -1001; }
     if (w0) rc = fft_any<T, false>(a, a, M, batch, fo, w0, w0_bytes, st);
     else if (pingpong) rc = fft_any<T, false>(a, b2, M, batch, fo, nullptr, 0, st);
     else rc = fft_pow2<T, false>(a, a, M, batch, false, false, 0, (T)1, plain, w0, st);

@@ -681,7 +681,7 @@ std::map<int, float*> g_fp_tw;
 
 const float* fftp_twiddles() {
     int d = 0;
-    BDSP_CUDA_ABORT(cudaGetDevice(&d));
+    if (cudaGetDevice(&d) != cudaSuccess) { set_last_error("cudaGetDevice failed"); return nullptr; }
     std::lock_guard<std::mutex> lk(g_fp_mu);
     auto it = g_fp_tw.find(d);
     if (it != g_fp_tw.end()) return it->second;
@@ -727,8 +727,13 @@ const float* fftp_twiddles() {
             e[2] = e[3] = (float)sinl(a);
         }
     float* dev = nullptr;
-    BDSP_CUDA_ABORT(cudaMalloc(&dev, FP_TW_FLOATS * sizeof(float)));
-    BDSP_CUDA_ABORT(cudaMemcpy(dev, h.data(), FP_TW_FLOATS * sizeof(float), cudaMemcpyHostToDevice));
+    if (cudaMalloc(&dev, FP_TW_FLOATS * sizeof(float)) != cudaSuccess ||
+        cudaMemcpy(dev, h.data(), FP_TW_FLOATS * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+        if (dev) cudaFree(dev);
+        cudaGetLastError();
+        set_last_error("fftp: twiddle table allocation failed");
+        return nullptr;
+    }
     g_fp_tw[d] = dev;
     return dev;
 }
@@ -744,6 +749,7 @@ int fftp_launch(const void* in, void* out, size_t rows, float scale, cudaStream_
         configured = true;
     }
     const float* tw = fftp_twiddles();
+    if (!tw) return -1001;
     cudaLaunchConfig_t cfg = {};
     // CL == 1 and n >= 8192: persistent CTAs (one per SM, 139/70 KB of shared memory each)
     size_t ctas = rows * CL;
@@ -825,6 +831,7 @@ int fftp_rows_pass(const void* tmp, void* out, size_t groups, bool inverse, bool
 template <bool INV, bool SI, bool RIN = false>
 int fftp_colpass(const void* in, void* tmp, int n1, int log2n2, size_t rows, cudaStream_t st) {
     const float* tw = fftp_twiddles();
+    if (!tw) return -1001;
     const float2* i2 = reinterpret_cast<const float2*>(in);
     float2* t2 = reinterpret_cast<float2*>(tmp);
     const float4* tws = reinterpret_cast<const float4*>(tw + FP_TW_SPLAT);

@@ -30,14 +30,17 @@ __device__ __forceinline__ void sts64(float* p, float2 v) {
 #ifndef OLS_H_TEX
 #define OLS_H_TEX 1   // measured: 0.3392 -> 0.3326 ms/step (LSU data pipe is the busiest unit, the texture pipe is idle)
 #endif
-#ifndef OLS_X_TEX
-#define OLS_X_TEX 0
-#endif
 #ifndef OLS_UNROLL_F3
 #define OLS_UNROLL_F3 0
 #endif
 #ifndef OLS_MIN_CTAS
-#define OLS_MIN_CTAS 4
+#define OLS_MIN_CTAS 5     // 96 registers, no spills.  With the warp-local middle section: 4 CTAs 0.3315 ms, 5 CTAs 0.3225 ms
+#endif                     // per step of the bench (64 x 2^20 points, 1023 taps); 6 CTAs (80 registers) spill
+#ifndef OLS_WARP_LOCAL
+#define OLS_WARP_LOCAL 1   // F3 takes the two halves of the 256-point row its quarter-warp owns in F2 / I2: the F2 -> F3 and
+#endif                     // I3 -> I2 exchanges then only need __syncwarp() (two CTA-wide barriers per block instead of four)
+#ifndef OLS_COMPUTE_TW2
+#define OLS_COMPUTE_TW2 0  // stride-16 stage twiddles as powers of one loaded root instead of 15 table loads
 #endif
 #ifndef OLS_TABLE_TW1
 #define OLS_TABLE_TW1 0  // measured on B200: the table variant (L1-bound) is 10% slower than computing the powers
@@ -72,12 +75,7 @@ ols4096_kernel(const float2* __restrict__ x, float2* __restrict__ y, int N, int 
 #pragma unroll
             for (int n2 = 0; n2 < 16; n2++) {
                 if (ALIGNED) {
-#if OLS_X_TEX
-                    const float4 ab = xtex ? tex1Dfetch<float4>(xtex, (int)(((size_t)vec * (size_t)N + p0 + c + 256 * n2) >> 1))
-                                           : __ldg(reinterpret_cast<const float4*>(px + 256 * n2));
-#else
-                    const float4 ab = __ldg(reinterpret_cast<const float4*>(px + 256 * n2));
-#endif
+                    const float4 ab = ldg_x4(reinterpret_cast<const float4*>(px + 256 * n2));
                     v[n2].re = make_float2(ab.x, ab.z);
                     v[n2].im = make_float2(ab.y, ab.w);
                 } else {
@@ -141,6 +139,15 @@ ols4096_kernel(const float2* __restrict__ x, float2* __restrict__ y, int N, int 
             v[n1].im = *reinterpret_cast<const float2*>(&sim[a]);
         }
         r16<false>(v);
+#if OLS_COMPUTE_TW2
+        {
+            const float4 f = __ldg(tw2 + 8);
+            cp w1;
+            w1.re = make_float2(f.x, f.y);
+            w1.im = make_float2(f.z, f.w);
+            apply_twiddles<true>(v, w1);
+        }
+#else
 #pragma unroll
         for (int s = 1; s < 16; s++) {
             const int k1 = r16_k(s);
@@ -150,6 +157,7 @@ ols4096_kernel(const float2* __restrict__ x, float2* __restrict__ y, int N, int 
             w.im = make_float2(f.z, f.w);
             v[s] = cmul(v[s], w);
         }
+#endif
 #pragma unroll
         for (int s = 0; s < 16; s++) {
             const int k1 = r16_k(s);
@@ -158,7 +166,11 @@ ols4096_kernel(const float2* __restrict__ x, float2* __restrict__ y, int N, int 
             *reinterpret_cast<float2*>(&sim[a]) = v[s].im;
         }
     }
+#if OLS_WARP_LOCAL
+    __syncwarp();
+#else
     __syncthreads();
+#endif
     // ------------------------------------------------------------------ F3 | *H | I3 on two groups of 16 contiguous points
 #if OLS_UNROLL_F3
 #pragma unroll
@@ -166,8 +178,13 @@ ols4096_kernel(const float2* __restrict__ x, float2* __restrict__ y, int N, int 
 #pragma unroll 1
 #endif
     for (int half = 0; half < 2; half++) {
+#if OLS_WARP_LOCAL
+        const int k0 = t >> 3, g = (t & 7) + 8 * half;
+#else
         const int gg = t + 128 * half;           // group index 0..255
-        const int k0 = gg >> 4, g = gg & 15, r = rot_of(g);
+        const int k0 = gg >> 4, g = gg & 15;
+#endif
+        const int r = rot_of(g);
         const int base = 272 * k0 + 16 * g;
         cp P[8];
 #pragma unroll
@@ -207,7 +224,11 @@ ols4096_kernel(const float2* __restrict__ x, float2* __restrict__ y, int N, int 
             sts64(&sim[a + 2], P[2 * q + 1].im);
         }
     }
+#if OLS_WARP_LOCAL
+    __syncwarp();
+#else
     __syncthreads();
+#endif
     // ------------------------------------------------------------------ I2: stride 16 (DIT: twiddle first)
     {
 #pragma unroll
@@ -216,6 +237,15 @@ ols4096_kernel(const float2* __restrict__ x, float2* __restrict__ y, int N, int 
             v[k1].re = *reinterpret_cast<const float2*>(&sre[a]);
             v[k1].im = *reinterpret_cast<const float2*>(&sim[a]);
         }
+#if OLS_COMPUTE_TW2
+        {
+            const float4 f = __ldg(tw2 + 8);
+            cp w1;
+            w1.re = make_float2(f.x, f.y);
+            w1.im = pneg(make_float2(f.z, f.w));
+            apply_twiddles<false>(v, w1);
+        }
+#else
 #pragma unroll
         for (int k1 = 1; k1 < 16; k1++) {
             const float4 f = __ldg(tw2 + 8 * k1);
@@ -224,6 +254,7 @@ ols4096_kernel(const float2* __restrict__ x, float2* __restrict__ y, int N, int 
             w.im = make_float2(f.z, f.w);
             v[k1] = cmul_conj(v[k1], w);
         }
+#endif
         r16<true>(v);
 #pragma unroll
         for (int s = 0; s < 16; s++) {
@@ -281,7 +312,8 @@ ols4096_kernel(const float2* __restrict__ x, float2* __restrict__ y, int N, int 
 
 // Hpos (planar, kernel layout) <- Hs (interleaved, natural order, already scaled by 1/M), delayed by d
 // samples: H_d[k] = H[k] * exp(-2 pi i k d / M).  Kernel layout: value of block position
-// p = 16*(t + 128*half) + 4*q + e is stored at ((half*4 + q)*128 + t)*4 + e.
+// p = 16*gg + 4*q + e (gg = 16*k0 + g, owned by thread t = 8*k0 + (g & 7) in iteration half = g >> 3) is stored at
+// ((half*4 + q)*128 + t)*4 + e.
 __global__ void ols4096_permute_h_kernel(const float2* __restrict__ Hs, float* __restrict__ Hre, float* __restrict__ Him, int d) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= OLS_M) return;
@@ -289,7 +321,11 @@ __global__ void ols4096_permute_h_kernel(const float2* __restrict__ Hs, float* _
     float2 h = Hs[k];
     if (d) h = cmul(h, unit_root<float>((unsigned long long)k * (unsigned long long)d, OLS_M, -1));
     const int gg = p >> 4, q = (p >> 2) & 3, e = p & 3;
+#if OLS_WARP_LOCAL
+    const int t = 8 * (gg >> 4) + (gg & 7), half = (gg >> 3) & 1;
+#else
     const int t = gg & 127, half = gg >> 7;
+#endif
     const int dst = ((half * 4 + q) * OLS_THREADS + t) * 4 + e;
     Hre[dst] = h.x;
     Him[dst] = h.y;
@@ -302,7 +338,7 @@ std::map<int, float*> g_tw;  // per device
 
 static const float* ols4096_twiddles() {
     int d = 0;
-    BDSP_CUDA_ABORT(cudaGetDevice(&d));
+    if (cudaGetDevice(&d) != cudaSuccess) { set_last_error("ols4096: cudaGetDevice failed"); return nullptr; }
     std::lock_guard<std::mutex> lk(g_tw_mu);
     auto it = g_tw.find(d);
     if (it != g_tw.end()) return it->second;
@@ -325,63 +361,15 @@ static const float* ols4096_twiddles() {
             h[OLS_TW1_IM + 256 * k + c] = (float)sinl(a);
         }
     float* dev = nullptr;
-    BDSP_CUDA_ABORT(cudaMalloc(&dev, OLS_TW_FLOATS * sizeof(float)));
-    BDSP_CUDA_ABORT(cudaMemcpy(dev, h.data(), OLS_TW_FLOATS * sizeof(float), cudaMemcpyHostToDevice));
+    if (cudaMalloc(&dev, OLS_TW_FLOATS * sizeof(float)) != cudaSuccess ||
+        cudaMemcpy(dev, h.data(), OLS_TW_FLOATS * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+        if (dev) cudaFree(dev);
+        set_last_error("ols4096: twiddle table allocation failed");
+        return nullptr;
+    }
     g_tw[d] = dev;
     return dev;
 }
-
-namespace {
-std::map<const void*, cudaTextureObject_t> g_htex;
-cudaTextureObject_t htex_for(const float* hp) {
-#if OLS_H_TEX
-    std::lock_guard<std::mutex> lk(g_tw_mu);
-    auto it = g_htex.find(hp);
-    if (it != g_htex.end()) return it->second;
-    cudaResourceDesc rd = {};
-    rd.resType = cudaResourceTypeLinear;
-    rd.res.linear.devPtr = const_cast<float*>(hp);
-    rd.res.linear.desc = cudaCreateChannelDesc<float4>();
-    rd.res.linear.sizeInBytes = 2 * OLS_M * sizeof(float);
-    cudaTextureDesc td = {};
-    td.readMode = cudaReadModeElementType;
-    cudaTextureObject_t tex = 0;
-    BDSP_CUDA_ABORT(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
-    g_htex[hp] = tex;
-    return tex;
-#else
-    (void)hp;
-    return 0;
-#endif
-}
-}  // namespace
-
-namespace {
-std::map<std::pair<const void*, size_t>, cudaTextureObject_t> g_xtex;
-cudaTextureObject_t xtex_for(const void* x, size_t bytes) {
-#if OLS_X_TEX
-    if (bytes / 16 > (1ull << 27)) return 0;   // linear texture limit: 2^27 texels
-    std::lock_guard<std::mutex> lk(g_tw_mu);
-    auto key = std::make_pair(x, bytes);
-    auto it = g_xtex.find(key);
-    if (it != g_xtex.end()) return it->second;
-    cudaResourceDesc rd = {};
-    rd.resType = cudaResourceTypeLinear;
-    rd.res.linear.devPtr = const_cast<void*>(x);
-    rd.res.linear.desc = cudaCreateChannelDesc<float4>();
-    rd.res.linear.sizeInBytes = bytes;
-    cudaTextureDesc td = {};
-    td.readMode = cudaReadModeElementType;
-    cudaTextureObject_t tex = 0;
-    if (cudaCreateTextureObject(&tex, &rd, &td, nullptr) != cudaSuccess) { cudaGetLastError(); return 0; }
-    g_xtex[key] = tex;
-    return tex;
-#else
-    (void)x; (void)bytes;
-    return 0;
-#endif
-}
-}  // namespace
 
 bool ols4096_applicable(size_t N, size_t L, size_t M) {
     // needs one wrap at most per strided load and 32-bit row indices
@@ -409,7 +397,7 @@ int ols4096_prepare(const void* Hs, void* Hpos, size_t L, cudaStream_t st) {
     return 0;
 }
 
-int ols4096_convolve(const void* x, void* y, size_t N, size_t batch, size_t L, const void* Hpos, cudaStream_t st) {
+int ols4096_convolve(const void* x, void* y, size_t N, size_t batch, size_t L, const void* Hpos, cudaTextureObject_t htex, cudaStream_t st) {
     if (x == y) { set_last_error("ols4096_convolve: in-place operation is not supported"); return -3; }
     int d, shift, m_first, step;
     ols4096_geometry(L, &d, &shift, &m_first, &step);
@@ -418,8 +406,8 @@ int ols4096_convolve(const void* x, void* y, size_t N, size_t batch, size_t L, c
     if (grid > 0x7fffffffll) { set_last_error("ols4096_convolve: grid too large"); return -2; }
     const float* hp = reinterpret_cast<const float*>(Hpos);
     const float* tw = ols4096_twiddles();
-    const cudaTextureObject_t htex = htex_for(hp);
-    const cudaTextureObject_t xtex = xtex_for(x, N * batch * sizeof(float2));
+    if (!tw) return -1;
+    const cudaTextureObject_t xtex = 0;
     const bool aligned = (N % 2 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     if (aligned)
         ols4096_kernel<true><<<(unsigned)grid, OLS_THREADS, 0, st>>>(reinterpret_cast<const float2*>(x), reinterpret_cast<float2*>(y), (int)N,

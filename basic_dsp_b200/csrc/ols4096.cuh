@@ -130,6 +130,21 @@ template <bool SLOTMAP> __device__ __forceinline__ void apply_twiddles(cp (&v)[1
     }
 }
 
+// 128-bit read-only global load that does not allocate in L1 (the block inputs are used once; a load that allocates
+// passes the L1 data RAM twice: fill + read)
+#ifndef OLS_X_NOALLOC
+#define OLS_X_NOALLOC 0
+#endif
+__device__ __forceinline__ float4 ldg_x4(const float4* p) {
+#if OLS_X_NOALLOC
+    float4 r;
+    asm("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+#else
+    return __ldg(p);
+#endif
+}
+
 // swizzled shared-memory layout, see header comment.  p = 256*k0 + 16*g + j
 __device__ __forceinline__ int rot_of(int g) { return (g >> 1) & 3; }
 __device__ __forceinline__ int phys(int k0, int g, int j) { return 272 * k0 + 16 * g + ((j + 4 * rot_of(g)) & 15); }

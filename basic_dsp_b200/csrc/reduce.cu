@@ -235,6 +235,7 @@ int run_reduce(const void* a, const void* b, size_t elems, int cplx, int parts, 
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     Rec* dev = reinterpret_cast<Rec*>(workspace(sizeof(Rec) * (size_t)(blocks * parts + parts), 3));
+    if (!dev) return -1001;
     Rec* dev_out = dev + blocks * parts;
     const size_t shm = sizeof(Rec) * RT;
     static bool configured = false;   // per instantiation

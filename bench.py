@@ -275,8 +275,11 @@ def run_gpu(args):
     chk = np.empty(row_floats, dtype=np.float32)
     L.bdsp_memcpy_d2h(chk.ctypes.data, d_out + (ROWS - 1) * row_floats * 4, row_floats * 4)
     L.bdsp_sync()
-    if not np.array_equal(chk, hout[(ROWS - 1) * row_floats:]):
-        raise SystemExit("e2e result differs from the device-resident result")
+    # (the per-vector call and the batched call may pick different block lengths, so equal up to rounding)
+    a64, b64 = chk.astype(np.float64), hout[(ROWS - 1) * row_floats:].astype(np.float64)
+    rel = float(np.linalg.norm(a64 - b64) / np.linalg.norm(a64))
+    if not rel <= 2e-5:
+        raise SystemExit("e2e result differs from the device-resident result (rel L2 %.3e)" % rel)
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -304,10 +307,10 @@ def run_gpu(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            rate, sec = cpu_port_rate(cores, cores, steps=1, warmup=0)
+            rate, sec = cpu_port_rate(cores, cores, steps=3, warmup=1)   # same protocol as --impl reference
             line["cpu_baseline"] = {"value": rate, "unit": "Msamples/s", "cores": cores, "kind": "port",
-                                    "sample": "%d x 2^20-point vectors (one per host thread), %.1f s; C port of the reference's "
-                                              "overlap_discard incl. scalar head/tail (oracle/ref_port.c)" % (cores, sec)}
+                                    "sample": "%d x 2^20-point vectors (one per host thread) per step, 1 warm-up + 3 timed steps of %.2f s; "
+                                              "C port of the reference's overlap_discard incl. scalar head/tail (oracle/ref_port.c)" % (cores, sec)}
         print(json.dumps(line))
     barrier()
     L.bdsp_conv_plan_destroy(plan)

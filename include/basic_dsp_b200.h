@@ -83,6 +83,13 @@ typedef BdspComplex64 (*BdspComplexFn64)(const void* data, double x);
  * 1. Reference C ABI, hot-path subset (interop/src/facade32.rs; f64 twins in facade64.rs)
  * =================================================================================================== */
 
+/* Threading (the reference: re-entrant per handle, interop/src/lib.rs): different threads may work on different
+ * vectors at the same time, with or without bdsp_set_stream - scratch workspaces are per host thread.  A vector that is
+ * only BORROWED by a call (`const BdspVec32*`, e.g. the impulse response of convolve_signal32) may be shared by several
+ * threads; its cached spectrum is built under a lock and reference counted.
+ * Errors: no entry point terminates the process.  Constructors return NULL when the device allocation fails
+ * (bdsp_last_error() says why); other calls report CUDA failures as result codes <= -1000. */
+
 /* ---- life cycle and meta data -------------------------------------------------------------------- */
 BdspVec32* new32(int32_t is_complex, int32_t domain, float init_value, size_t length, float delta);     /* facade32.rs:22 */
 BdspVec32* new_with_performance_options32(int32_t is_complex, int32_t domain, float init_value, size_t length,
@@ -471,7 +478,12 @@ int32_t bdsp_download_async32(const BdspVec32* vector, float* host, size_t len);
 int32_t bdsp_download_async64(const BdspVec64* vector, double* host, size_t len);
 int32_t bdsp_upload64(BdspVec64* vector, const double* host, size_t len);
 int32_t bdsp_download64(const BdspVec64* vector, double* host, size_t len);
-void* bdsp_device_ptr32(BdspVec32* vector);           /* device pointer of the vector's storage (interleaved) */
+/* Device pointer of the vector's storage (interleaved).  Valid until the next call that mutates the vector: most
+ * operations produce their result in the handle's scratch buffer and swap the two pointers, and growing a vector
+ * reallocates.  The pointer gives mutable access, so the call also drops every cache derived from the vector's contents
+ * (the impulse-response spectrum convolve_signal32 keeps inside its `impulse_response` argument): write through the
+ * pointer first, then call convolve_signal32. */
+void* bdsp_device_ptr32(BdspVec32* vector);
 void* bdsp_device_ptr64(BdspVec64* vector);
 /* fused chain of the sequential trait calls scale(c) -> mul(&w) -> get_mag_phase(&mut mag, &mut phase)
  * in ONE pass over memory; `vector` keeps scale(c)*w when write_back != 0 */
@@ -505,6 +517,7 @@ int32_t bdsp_convolve_signal_rows_c64(const void* in, void* out, size_t points, 
 /* raw memory helpers so that non-CUDA hosts (ctypes, cgo, JNI) can drive section 3 */
 void* bdsp_malloc(size_t bytes);
 void bdsp_free(void* device_ptr);
+size_t bdsp_mem_free(void);                           /* free device memory in bytes (cudaMemGetInfo), 0 on error */
 void* bdsp_malloc_host(size_t bytes);                 /* pinned host memory */
 void bdsp_free_host(void* host_ptr);
 int32_t bdsp_memcpy_h2d(void* device_dst, const void* host_src, size_t bytes);   /* async on the thread's stream */

@@ -1,16 +1,18 @@
 #!/bin/bash
 # usage: build_variant.sh <name> <extra nvcc -D flags...>   -> scratch/lib_<name>.so
+# (the flags go to the kernel files under study; everything else is taken from the regular build)
 set -e
 name=$1; shift
 cd /root/repo/basic_dsp_b200/csrc
 objs=""
-for f in common fft conv ols4096 fftp interp elementwise capi; do
-  if [ "$f" = "ols4096" ] || [ "$f" = "fftp" ]; then
-    nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden "$@" -c $f.cu -o /tmp/var_${name}_$f.o
+for f in common fft conv ols4096 ols8192 fftp interp elementwise mathops reduce capi; do
+  if [ "$f" = "ols4096" ] || [ "$f" = "ols8192" ] || [ "$f" = "fftp" ] || [ "$f" = "conv" ]; then
+    nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden "$@" -c $f.cu -o /tmp/var_${name}_$f.o &
     objs="$objs /tmp/var_${name}_$f.o"
   else
     objs="$objs ../build/$f.o"
   fi
 done
+wait
 nvcc -shared -o /root/repo/scratch/lib_$name.so $objs -cudart static -Xlinker --exclude-libs,ALL
 echo built scratch/lib_$name.so

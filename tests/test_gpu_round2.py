@@ -1,0 +1,195 @@
+"""Round-2 GPU tests: the fused 8192-point overlap-save kernel, the full-length convolution path with mixed-radix and
+chirp-z lengths (workspace slot clash), thread safety of shared impulse responses and of the per-thread
+workspaces, and the bounded chirp-filter cache.  Everything goes through the C ABI."""
+import math
+import threading
+
+import numpy as np
+import pytest
+
+import basic_dsp_b200 as bd
+from basic_dsp_b200 import DspVec
+from oracle import dsp_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+
+def tol(n, dtype):
+    return (1e-5 if dtype == np.float32 else 1e-12) * max(1.0, math.log2(max(n, 2)))
+
+
+def dptr(v):
+    return v._fn("bdsp_device_ptr")(v._h)
+
+
+def rand_c(rng, n, dtype):
+    ct = np.complex64 if dtype == np.float32 else np.complex128
+    return (rng.uniform(-10, 10, n) + 1j * rng.uniform(-10, 10, n)).astype(ct)
+
+
+# ---- fused 8192-point blocks (c32, 1450 <= L <= 4094 in the throughput regime; 2047 <= L <= 4094 always) ----------
+@pytest.mark.parametrize("n,l", [(8192, 2047), (8192, 4094), (8193, 3000), (20001, 2500), (1 << 16, 4093), (100000, 3333),
+                                 (1 << 22, 1500), (1 << 22, 2046), (3 * (1 << 20) + 2, 1451)])
+def test_convolve_signal_8192_point_blocks(n, l):
+    rng = np.random.default_rng(n + l)
+    x = rand_c(rng, n, np.float32)
+    h = (rand_c(rng, l, np.float32) / 10).astype(np.complex64)
+    got = DspVec(x).convolve_signal(DspVec(h)).to_numpy()
+    assert o.rel_l2(got, o.convolve_signal(x, h)) <= tol(8192, np.float32)
+
+
+@pytest.mark.parametrize("n,rows,l", [(100000, 40, 2000), (1 << 16, 64, 1450), (50001, 33, 4094), (1 << 20, 6, 1023)])
+def test_convolve_signal_rows_8192_point_blocks(n, rows, l):
+    L = bd.lib()
+    rng = np.random.default_rng(n + rows + l)
+    x = rand_c(rng, n * rows, np.float32)
+    h = (rand_c(rng, l, np.float32) / 10).astype(np.complex64)
+    xv, hv, out = DspVec(x), DspVec(h), DspVec.zeros(2 * n * rows, is_complex=True)
+    plan = L.bdsp_conv_plan_create_c32(dptr(hv), l)
+    assert plan
+    assert L.bdsp_convolve_signal_rows_c32(dptr(xv), dptr(out), n, rows, plan) == 0
+    got = out.to_numpy().reshape(rows, n)
+    xr = x.reshape(rows, n)
+    for r in range(rows):
+        assert o.rel_l2(got[r], o.convolve_signal(xr[r], h)) <= tol(8192, np.float32), r
+    L.bdsp_conv_plan_destroy(plan)
+
+
+def test_real_taps_on_complex_signal_fused_blocks():
+    rng = np.random.default_rng(77)
+    for n, l in [(30000, 1023), (70000, 3001)]:
+        x = rand_c(rng, n, np.float32)
+        h = rng.uniform(-1, 1, l).astype(np.float32)
+        got = DspVec(x).convolve_signal(DspVec(h.astype(np.complex64))).to_numpy()
+        assert o.rel_l2(got, o.convolve_signal(x, h.astype(np.complex128))) <= tol(8192, np.float32)
+
+
+# ---- full-length frequency-domain path: impulse responses too long for a block transform ---------------------------
+@pytest.mark.parametrize("dtype,n,l", [(np.float32, 3 * 32768, 9001), (np.float32, 31 * 16384, 8500), (np.float32, 1 << 17, 20000),
+                                       (np.float32, 40000, 9000), (np.float64, 3 * 32768, 4500), (np.float64, 31 * 16384, 5000),
+                                       (np.float64, 20001, 4099)])
+def test_convolve_signal_full_length_path(dtype, n, l):
+    rng = np.random.default_rng(n + l)
+    x = rand_c(rng, n, dtype)
+    h = (rand_c(rng, l, dtype) / 10).astype(x.dtype)
+    got = DspVec(x).convolve_signal(DspVec(h)).to_numpy()
+    assert o.rel_l2(got, o.convolve_signal(x, h)) <= tol(n, dtype)
+
+
+@pytest.mark.parametrize("dtype,n,rows,l", [(np.float32, 3 * 32768, 3, 9001), (np.float64, 3 * 16384, 4, 4500), (np.float32, 31 * 4096, 5, 10000)])
+def test_convolve_signal_rows_full_length_path(dtype, n, rows, l):
+    L = bd.lib()
+    sfx = "c32" if dtype == np.float32 else "c64"
+    rng = np.random.default_rng(n + l + rows)
+    x = rand_c(rng, n * rows, dtype)
+    h = (rand_c(rng, l, dtype) / 10).astype(x.dtype)
+    xv, hv = DspVec(x), DspVec(h)
+    out = DspVec.zeros(2 * n * rows, is_complex=True, dtype=dtype)
+    plan = getattr(L, "bdsp_conv_plan_create_" + sfx)(dptr(hv), l)
+    assert plan
+    for _ in range(2):   # the second call reuses (and must not have clobbered) every workspace
+        assert getattr(L, "bdsp_convolve_signal_rows_" + sfx)(dptr(xv), dptr(out), n, rows, plan) == 0
+        got = out.to_numpy().reshape(rows, n)
+        for r in range(rows):
+            assert o.rel_l2(got[r], o.convolve_signal(x.reshape(rows, n)[r], h)) <= tol(n, dtype), r
+    L.bdsp_conv_plan_destroy(plan)
+
+
+# ---- threads -----------------------------------------------------------------------------------------------------------
+def test_two_threads_share_one_impulse_response():
+    """`impulse_response` is a borrowed, read-only argument (facade32.rs:1171): two threads convolving different
+    vectors with ONE shared response, each on its own stream, while the response's spectrum cache is cold."""
+    L = bd.lib()
+    rng = np.random.default_rng(5)
+    n, l = 1 << 18, 1023
+    h = (rand_c(rng, l, np.float32) / 10).astype(np.complex64)
+    xs = [rand_c(rng, n, np.float32) for _ in range(2)]
+    refs = [o.convolve_signal(x, h) for x in xs]
+    errs = []
+
+    for attempt in range(4):
+        hv = DspVec(h)          # fresh response: the plan is built inside the racing calls
+        start = threading.Barrier(2)
+
+        def work(i):
+            try:
+                st = L.bdsp_stream_create()
+                L.bdsp_set_stream(st)
+                v = DspVec(xs[i])
+                start.wait()
+                for _ in range(3):
+                    v.upload(xs[i].view(np.float32))
+                    got = v.convolve_signal(hv).to_numpy()
+                    e = o.rel_l2(got, refs[i])
+                    if not e <= tol(4096, np.float32):
+                        errs.append((attempt, i, e))
+                del v
+                L.bdsp_set_stream(None)
+                L.bdsp_stream_destroy(st)
+            except Exception as exc:  # noqa: BLE001
+                errs.append((attempt, i, repr(exc)))
+
+        ts = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+    assert not errs, errs
+
+
+def test_threads_without_streams_do_not_share_workspaces():
+    """Two threads on the default stream running multi-kernel transforms (three-pass, mixed radix, chirp-z) on their
+    own vectors: scratch buffers are per thread."""
+    rng = np.random.default_rng(6)
+    sizes = [3 * (1 << 16), 1 << 21, 10007 * 3, 1 << 17]
+    data = {n: rand_c(rng, n, np.float32) for n in sizes}
+    refs = {n: o.plain_fft(data[n]) for n in sizes}
+    errs = []
+
+    def work(order):
+        try:
+            for _ in range(3):
+                for n in order:
+                    got = DspVec(data[n]).plain_fft().to_numpy()
+                    e = o.rel_l2(got, refs[n])
+                    if not e <= tol(n, np.float32):
+                        errs.append((n, e))
+        except Exception as exc:  # noqa: BLE001
+            errs.append(repr(exc))
+
+    ts = [threading.Thread(target=work, args=(sizes,)), threading.Thread(target=work, args=(sizes[::-1],))]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs
+
+
+def test_chirp_filter_cache_is_bounded():
+    """Many distinct non-smooth lengths: the chirp-z filter cache evicts instead of growing without bound
+    (1 GiB cap; each of these lengths needs a 2^22-point c64 filter = 64 MiB)."""
+    L = bd.lib()
+    rng = np.random.default_rng(8)
+    free0 = L.bdsp_mem_free() if hasattr(L, "bdsp_mem_free") else None
+    primes = [1000003, 1000033, 1000037, 1000039, 1000081, 1000099, 1000117, 1000121, 1000133, 1000151, 1000159, 1000171,
+              1000183, 1000187, 1000193, 1000199, 1000211, 1000213, 1000231, 1000249]
+    for n in primes:
+        x = rand_c(rng, n, np.float64)
+        got = DspVec(x).plain_fft().to_numpy()
+        if n in (primes[0], primes[-1]):
+            assert o.rel_l2(got, o.plain_fft(x)) <= tol(n, np.float64)
+    # the first length again (evicted by now: 20 x 64 MiB > 1 GiB) still gives the right answer
+    x = rand_c(rng, primes[0], np.float64)
+    assert o.rel_l2(DspVec(x).plain_fft().to_numpy(), o.plain_fft(x)) <= tol(primes[0], np.float64)
+    if free0 is not None:
+        assert free0 - L.bdsp_mem_free() < (3 << 30)
+
+
+def test_device_ptr_access_invalidates_cached_spectrum():
+    L = bd.lib()
+    rng = np.random.default_rng(9)
+    n, l = 20000, 500
+    x = rand_c(rng, n, np.float32)
+    h1 = (rand_c(rng, l, np.float32) / 10).astype(np.complex64)
+    h2 = (rand_c(rng, l, np.float32) / 10).astype(np.complex64)
+    hv = DspVec(h1)
+    assert o.rel_l2(DspVec(x).convolve_signal(hv).to_numpy(), o.convolve_signal(x, h1)) <= tol(4096, np.float32)
+    L.bdsp_memcpy_h2d(dptr(hv), h2.ctypes.data, l * 8)      # refresh the taps through the raw device pointer
+    L.bdsp_sync()
+    assert o.rel_l2(DspVec(x).convolve_signal(hv).to_numpy(), o.convolve_signal(x, h2)) <= tol(4096, np.float32)
