@@ -25,35 +25,12 @@
 #include <mutex>
 #include <vector>
 
-#include "fft.cuh"
-#include "ols4096.cuh"
+#include "fftp.cuh"
 
 namespace cg = cooperative_groups;
 
 namespace bdsp {
 using namespace ols16;
-
-// floats per sub-block plane: 16 rows of 272 plus a pad that spreads the sub-blocks over the 16-byte
-// bank windows, so that the 8 lanes of every quarter-warp of the 128-bit loads in F3 (lanes walk
-// sub-block, then row) hit 8 different windows: NSB = 2 -> +8 floats, NSB = 4 -> +4 floats
-#define FP_B_OF(NSB_) (4352 + ((NSB_) == 2 ? 8 : (NSB_) == 4 ? 4 : 0))
-
-// layout inside a sub-block: p = 256*row + 16*g + j  ->  272*row + 16*g + ((j + 4*(rot(g) + (row>>1))) & 15)
-__device__ __forceinline__ int fp_rot(int row, int g) { return (((g >> 1) + (row >> 1)) & 3); }
-
-// twiddle table (floats): [0,256) Re W4096^c, [256,512) Im W4096^c, [512,1024) stride-16 table (see ols4096.cu),
-// [1024 + 8192*i + c] Re W_{8192<<i}^c, [1024 + 8192*i + 4096 + c] Im, c in [0,4096), i in {0,1}
-// [1024 + 16384 + 4*(16*ka + b)] splat table {c, c, s, s} of W256^{ka*b} (first pass of the 2^20 transform)
-#define FP_TW_SPLAT (1024 + 2 * 8192)
-// [FP_TW_1K + c] Re W1024^c, [FP_TW_1K + 256 + c] Im, c in [0,256)
-#define FP_TW_1K (FP_TW_SPLAT + 1024)
-// same for W512^c and W2048^c
-#define FP_TW_512 (FP_TW_1K + 512)
-#define FP_TW_2K (FP_TW_512 + 512)
-// second-stage tables of the short-row mode: float4 index (8*kg + j/2) = {Re(j), Re(j+1), Im(j), Im(j+1)} of W_{16P}^{kg*j}
-#define FP_TW_S4 (FP_TW_2K + 512)
-#define FP_TW_S8 (FP_TW_S4 + 128)
-#define FP_TW_FLOATS (FP_TW_S8 + 256)
 
 // ROWS = true (R0 = 4, CL = 1): the CTA transforms FOUR independent, adjacent 4096-point rows (no F0) and
 // writes result k of row r to out[(r0 + r) + n1 * k]: the transposing last pass of a two-pass transform of
@@ -678,6 +655,7 @@ __global__ void __launch_bounds__(128, 5) fftp_col256_kernel(const float2* __res
 namespace {
 std::mutex g_fp_mu;
 std::map<int, float*> g_fp_tw;
+}  // namespace
 
 const float* fftp_twiddles() {
     int d = 0;
@@ -737,6 +715,8 @@ const float* fftp_twiddles() {
     g_fp_tw[d] = dev;
     return dev;
 }
+
+namespace {
 
 template <int R0, int CL, bool INV, bool SI, bool SO, bool MAG, bool ROWS = false, int TQ = 0, int NATQ = 0, bool RIN = false, int SQ = 0>
 int fftp_launch(const void* in, void* out, size_t rows, float scale, cudaStream_t st, int n1 = 1, int n2c = 1) {
@@ -994,6 +974,17 @@ static int fftp_cluster_mode() {
     return mode;
 }
 
+int fftp16k_try(const void* in, void* out, size_t rows, bool inverse, bool shift_in, bool shift_out, bool magnitude, float scale,
+                cudaStream_t st);
+// BDSP_FFTP16K=0 selects round 1's one-CTA-per-row kernel for 16384-point rows (A/B measurements)
+static int fftp16k_mode() {
+    static int mode = [] {
+        const char* e = getenv("BDSP_FFTP16K");
+        return (e && e[0] == '0') ? 0 : 1;
+    }();
+    return mode;
+}
+
 // returns 0 on success, 1 when this configuration is not covered (caller uses the generic kernel)
 int fftp_try(const void* in, void* out, size_t n, size_t rows, bool inverse, size_t in_rot, size_t out_rot, double scale,
              bool magnitude, cudaStream_t st) {
@@ -1020,6 +1011,11 @@ int fftp_try(const void* in, void* out, size_t n, size_t rows, bool inverse, siz
     const bool si = in_rot != 0, so = out_rot != 0;
     const float sc = (float)scale;
     if (n == 4096) return fftp_dispatch<1, 1>(in, out, rows, inverse, si, so, magnitude, sc, st);
+    if (n == 16384 && fftp16k_mode() && rows >= 2) {
+        // persistent CTAs with the rolling F3 || F0 pipeline (fftp16k.cu)
+        const int rc = fftp16k_try(in, out, rows, inverse, si, so, magnitude, sc, st);
+        if (rc <= 0) return rc;
+    }
     if (n == 8192) return fftp_cluster_mode() == 2 ? fftp_dispatch<2, 2>(in, out, rows, inverse, si, so, magnitude, sc, st)
                                               : fftp_dispatch<2, 1>(in, out, rows, inverse, si, so, magnitude, sc, st);
     return fftp_cluster_mode() == 2 ? fftp_dispatch<4, 2>(in, out, rows, inverse, si, so, magnitude, sc, st)

@@ -34,6 +34,26 @@ __device__ __forceinline__ pk psub(pk a, pk b) { return __fadd2_rn(a, pneg(b)); 
 __device__ __forceinline__ pk pmul(pk a, pk b) { return __fmul2_rn(a, b); }
 __device__ __forceinline__ pk pfma(pk a, pk b, pk c) { return __ffma2_rn(a, b, c); }
 __device__ __forceinline__ pk splat(float v) { return make_float2(v, v); }
+// sqrt with a maximum relative error of 2^-23 (MUFU.SQRT; the IEEE sqrtf costs ~10 instructions and a slow-path call):
+// used by the fused magnitude epilogues, whose tolerance is the transform's (1e-5 * log2 N relative L2)
+__device__ __forceinline__ float sqrt_fast(float v) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+// {re0, im0, re1, im1} (two adjacent interleaved points) -> planar pairs {re0, re1}, {im0, im1}; the explicit 64-bit packs
+// keep the compiler from materialising each pair twice (once per consumer)
+#ifndef OLS_PACK_ASM
+#define OLS_PACK_ASM 1
+#endif
+__device__ __forceinline__ void planar_of(const float4& ab, pk& re, pk& im) {
+#if OLS_PACK_ASM
+    unsigned long long r, i;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(ab.x), "f"(ab.z));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(i) : "f"(ab.y), "f"(ab.w));
+    re = *reinterpret_cast<pk*>(&r);
+    im = *reinterpret_cast<pk*>(&i);
+#else
+    re = make_float2(ab.x, ab.z);
+    im = make_float2(ab.y, ab.w);
+#endif
+}
 
 __device__ __forceinline__ cp cadd(cp a, cp b) { cp r; r.re = padd(a.re, b.re); r.im = padd(a.im, b.im); return r; }
 __device__ __forceinline__ cp csub(cp a, cp b) { cp r; r.re = psub(a.re, b.re); r.im = psub(a.im, b.im); return r; }
