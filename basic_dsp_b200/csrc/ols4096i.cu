@@ -22,7 +22,7 @@
 #include <vector>
 
 #include "conv.cuh"
-#include "cxmath.cuh"
+#include "olsi.cuh"
 
 namespace bdsp {
 
@@ -37,69 +37,6 @@ using namespace cx;
 // twiddle table (float2): [0,256) W4096^col; [256 + 16 k + c] W256^{k c}, k, c in [0,16)
 #define OI_TW_C2 (256 + 256)
 #define OI_TW2 256
-
-// block inputs are used once: OI_X_LOAD = 1 (L1::no_allocate) / 2 (ld.global.cg, L2 only) keep them from displacing the
-// spectrum and the twiddles in L1
-#ifndef OI_X_LOAD
-#define OI_X_LOAD 0
-#endif
-__device__ __forceinline__ float4 ld_x4(const float2* p) {
-#if OI_X_LOAD == 1
-    float4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-    return r;
-#elif OI_X_LOAD == 2
-    float4 r;
-    asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-    return r;
-#else
-    return __ldg(reinterpret_cast<const float4*>(p));
-#endif
-}
-// stride-16 stage twiddles W256^{k c}, k = 1..15: 0 = fifteen 128-bit table loads per stage (4-5 L1 wavefronts each:
-// 16 % of the kernel's L1 data-pipe traffic, which is its saturated unit), 1 = six loads (k = 1, 2, 3, 4, 8, 12) +
-// nine products, 2 = one load + the power scheme of the stride-256 stages
-// measurement only (results become wrong): bit 0 = no F3|H|I3 arithmetic, 1 = no stride-16 stages' arithmetic, 2 = no
-// stride-256 stages' arithmetic, 3 = no H fetch, 4 = no shared-memory traffic in the middle section
-#ifndef OI_ABLATE
-#define OI_ABLATE 0
-#endif
-#ifndef OI_TW2_MODE
-#define OI_TW2_MODE 1
-#endif
-// v[s] *= W^{k(s)} (CONJ: conjugated), k(s) = SLOTMAP ? r16_k(s) : s, for the two columns held in v / u
-template <bool SLOTMAP, bool CONJ>
-__device__ __forceinline__ void oi_tw2(c2 (&v)[16], c2 (&u)[16], const float4* __restrict__ tw2) {
-#if OI_TW2_MODE == 0
-#pragma unroll
-    for (int s = 1; s < 16; s++) {
-        const float4 f = __ldg(tw2 + 8 * (SLOTMAP ? r16_k(s) : s));
-        v[s] = CONJ ? mul_conj(v[s], make_float2(f.x, f.y)) : mul(v[s], make_float2(f.x, f.y));
-        u[s] = CONJ ? mul_conj(u[s], make_float2(f.z, f.w)) : mul(u[s], make_float2(f.z, f.w));
-    }
-#elif OI_TW2_MODE == 1
-    c2 Av[4], Bv[4], Au[4], Bu[4];
-#pragma unroll
-    for (int i = 1; i < 4; i++) {
-        const float4 fa = __ldg(tw2 + 8 * i), fb = __ldg(tw2 + 8 * 4 * i);
-        Av[i] = make_float2(fa.x, CONJ ? -fa.y : fa.y); Au[i] = make_float2(fa.z, CONJ ? -fa.w : fa.w);
-        Bv[i] = make_float2(fb.x, CONJ ? -fb.y : fb.y); Bu[i] = make_float2(fb.z, CONJ ? -fb.w : fb.w);
-    }
-#pragma unroll
-    for (int s = 1; s < 16; s++) {
-        const int k = SLOTMAP ? r16_k(s) : s;
-        const int a = k & 3, b = k >> 2;
-        const c2 wv = b == 0 ? Av[a] : a == 0 ? Bv[b] : mul(Av[a], Bv[b]);
-        const c2 wu = b == 0 ? Au[a] : a == 0 ? Bu[b] : mul(Au[a], Bu[b]);
-        v[s] = mul(v[s], wv);
-        u[s] = mul(u[s], wu);
-    }
-#else
-    const float4 f = __ldg(tw2 + 8);
-    apply_twiddles<SLOTMAP>(v, make_float2(f.x, CONJ ? -f.y : f.y));
-    apply_twiddles<SLOTMAP>(u, make_float2(f.z, CONJ ? -f.w : f.w));
-#endif
-}
 
 // ALIGNED: rows start on 16-byte boundaries (N even, 16-byte aligned base pointers); together with the even block
 // offsets chosen by the plan every thread then moves its two adjacent points with one 128-bit access.  `shift` =
@@ -174,7 +111,7 @@ ols4096i_kernel(const float2* __restrict__ x, float2* __restrict__ y, int N, int
         if (!(OI_ABLATE & 2)) {
         r16<false>(v);
         r16<false>(u);
-        oi_tw2<true, false>(v, u, tw2);
+        oi_tw2<true, false, 8>(v, u, tw2);
         }
 #pragma unroll
         for (int s = 0; s < 16; s++) {
@@ -217,7 +154,7 @@ ols4096i_kernel(const float2* __restrict__ x, float2* __restrict__ y, int N, int
             u[k1] = make_float2(f.z, f.w);
         }
         if (!(OI_ABLATE & 2)) {
-        oi_tw2<false, true>(v, u, tw2);
+        oi_tw2<false, true, 8>(v, u, tw2);
         r16<true>(v);
         r16<true>(u);
         }
@@ -324,21 +261,10 @@ bool ols4096_applicable(size_t N, size_t L, size_t M) {
     return M == OI_M && L >= 2 && L <= OI_M / 2 - 2 && N >= OI_M && N < (1ull << 30);
 }
 
-// plan geometry shared by prepare and convolve: delay d makes the input->output index distance even
-static inline void ols4096_geometry(size_t L, int* d, int* shift, int* m_first, int* step) {
-    const int cl = (int)(L - L / 2);
-    *d = (cl - 1) & 1;
-    *shift = cl - 1 + *d;
-    int mf = (int)L - 1 + *d;      // first block position whose circular convolution value is valid
-    if (mf & 1) mf++;
-    *m_first = mf;
-    *step = (OI_M - mf) & ~1;
-}
-
 // Hpos: 4096 float2 <- Hs from the plan (FFT_4096(pad(h)) / 4096, natural order)
 int ols4096_prepare(const void* Hs, void* Hpos, size_t L, cudaStream_t st) {
     int d, shift, m_first, step;
-    ols4096_geometry(L, &d, &shift, &m_first, &step);
+    olsi_geometry(OI_M, L, &d, &shift, &m_first, &step);
     ols4096i_permute_h_kernel<<<OI_M / 256, 256, 0, st>>>(reinterpret_cast<const float2*>(Hs), reinterpret_cast<float2*>(Hpos), d);
     BDSP_LAUNCHED();
     return 0;
@@ -348,7 +274,7 @@ int ols4096_convolve(const void* x, void* y, size_t N, size_t batch, size_t L, c
     (void)Hpos;
     if (x == y) { set_last_error("ols4096_convolve: in-place operation is not supported"); return -3; }
     int d, shift, m_first, step;
-    ols4096_geometry(L, &d, &shift, &m_first, &step);
+    olsi_geometry(OI_M, L, &d, &shift, &m_first, &step);
     const long long bpv = ((long long)N + step - 1) / step;
     const long long grid = bpv * (long long)batch;
     if (grid > 0x7fffffffll) { set_last_error("ols4096_convolve: grid too large"); return -2; }
