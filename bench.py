@@ -76,7 +76,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -85,23 +85,28 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([time.time()] + [c.strip() for c in line.split(",")])
+
+    def summary(self, t0=None, t1=None):
+        """Median SM clock / throttle reasons of the samples taken in [t0, t1] (all samples when None)."""
+        rows = [r[1:] for r in self.rows if (t0 is None or r[0] >= t0 - 0.05) and (t1 is None or r[0] <= t1 + 0.05)]
+        sm = [float(r[0]) for r in rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        return self.summary()
 
 
 def cpu_port_rate(rows, threads, steps=1, warmup=0):
@@ -205,6 +210,18 @@ def run_gpu(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        time.sleep(0.1)
+    # The K timed steps last only a few milliseconds, far less than nvidia-smi's sampling period: the same step is
+    # kept running (untimed) for ~0.25 s before and after them so that the clock record brackets the timed region
+    # with >= 10 samples taken under the same load.
+    def load_for(seconds):
+        t_end = time.perf_counter() + seconds
+        while time.perf_counter() < t_end:
+            for _ in range(20):
+                step()
+            L.bdsp_sync()
+    load_for(0.25)
+    t_load0 = time.time() - 0.25
     launches0 = bd.kernel_launch_count()
     evs = [L.bdsp_event_create() for _ in range(args.steps + 1)]
     barrier()
@@ -216,7 +233,9 @@ def run_gpu(args):
     total_ms = L.bdsp_event_elapsed_ms(evs[0], evs[args.steps])
     per_launch_ms = [L.bdsp_event_elapsed_ms(evs[i], evs[i + 1]) for i in range(args.steps)]
     launches = bd.kernel_launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    load_for(0.25)
+    t_load1 = time.time()
+    clocks = sampler.summary(t_load0, t_load1) if rank == 0 else None
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -270,6 +289,31 @@ def run_gpu(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * ROWS * N_POINTS * e2e_steps / float(t.item()) / 1e6
+
+    # ---- what the box's host <-> device path allows: the same pinned buffers copied up and down concurrently (two
+    # streams, all ranks at once, nothing else running), i.e. the ceiling of any end-to-end number on this machine
+    s_up, s_dn = streams[0], streams[1 % DEPTH]
+
+    def copy_step():
+        L.bdsp_set_stream(s_up)
+        L.bdsp_memcpy_h2d(d_in, host_in, nbytes)
+        L.bdsp_set_stream(s_dn)
+        L.bdsp_memcpy_d2h(host_out, d_out, nbytes)
+        L.bdsp_stream_sync(s_up)
+        L.bdsp_stream_sync(s_dn)
+        L.bdsp_set_stream(None)
+
+    copy_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        copy_step()
+    barrier()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    copy_ceiling_gbs = world * 2.0 * nbytes * 3 / float(t.item()) / 1e9          # aggregate, both directions
+    e2e_gbs = e2e_value * 1e6 * 16.0 / 1e9                                       # 8 B up + 8 B down per sample
     # the e2e result of the last row must equal the device-resident result (same kernel, same input)
     hout = np.ctypeslib.as_array((ctypes.c_float * (2 * ROWS * N_POINTS)).from_address(host_out))
     chk = np.empty(row_floats, dtype=np.float32)
@@ -296,15 +340,32 @@ def run_gpu(args):
                        "sharding": "rows, no collective"},
             "gflops_5nlog2n": flops * world / (total_ms_max / args.steps * 1e-3) / 1e9,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": 1032126464.0, "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/r1_ols4096_ncu.txt)",
-                         "kernel": "ols4096_kernel<true>", "peak_source": peak_src,
+                         "traffic": 1027147776.0, "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/r2_ols4096i_ncu.txt)",
+                         "kernel": "ols4096i_kernel<true>", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_ms,
                          "min_launch_ms": min(per_launch_ms)},
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
-                    "steps": e2e_steps, "path": "per row: bdsp_upload32 -> convolve_signal32 -> bdsp_download_async32, pinned host buffers, 3 streams in flight"},
+                    "steps": e2e_steps, "path": "per row: bdsp_upload32 -> convolve_signal32 -> bdsp_download_async32, pinned host buffers, 3 streams in flight",
+                    "host_link_GBps": e2e_gbs, "copy_ceiling_GBps": copy_ceiling_gbs, "frac_of_copy_ceiling": e2e_gbs / copy_ceiling_gbs,
+                    "copy_ceiling": "aggregate over all ranks of concurrent pinned H2D + D2H cudaMemcpyAsync of the same buffers, no kernels"},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if world == 1 and not args.no_configs:
+            # every other BASELINE config, device resident, CUDA events, with the clocks sampled while it ran
+            import bench_configs
+            lines = bench_configs.measure(set("C1,C2a,C2b,C3,C4a,C4b,C5a,C5b".split(",")), 10, emit=False)
+            cfgs = {}
+            prev_end = time.time()
+            for ln in lines:
+                key = ln["config"] + (" (L2 flushed)" if "flushed" in ln["what"] else " (L2 warm)" if "warm" in ln["what"] else "")
+                cfgs[key] = {"what": ln["what"], "ms": ln["ms_median"], "ms_best": ln["ms_best"], "Msamples_per_s": ln["Msamples_per_s"],
+                             "algorithmic_bytes": ln["algorithmic_bytes"], "achieved_GBps": ln["achieved_GBps"], "frac": ln["roofline_frac"]}
+            t_cfg1 = time.time()
+            ck = sampler.summary(t_load1, t_cfg1)
+            for k_ in cfgs:
+                cfgs[k_]["clocks"] = ck
+            line["configs"] = cfgs
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             rate, sec = cpu_port_rate(cores, cores, steps=3, warmup=1)   # same protocol as --impl reference
@@ -312,6 +373,7 @@ def run_gpu(args):
                                     "sample": "%d x 2^20-point vectors (one per host thread) per step, 1 warm-up + 3 timed steps of %.2f s; "
                                               "C port of the reference's overlap_discard incl. scalar head/tail (oracle/ref_port.c)" % (cores, sec)}
         print(json.dumps(line))
+        sampler.stop()
     barrier()
     L.bdsp_conv_plan_destroy(plan)
     for p in (d_in, d_out, d_h):
@@ -330,6 +392,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config measurements (C1 ... C5b) on the N=1 line")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -34,7 +34,9 @@ class Timer:
         self.flush_buf = L.bdsp_malloc(256 << 20)
 
     def run(self, fn, iters, setup=None, flush=False, warmup=3):
+        import time
         L = self.L
+        self.t_start = time.time()
         for _ in range(warmup):
             if setup:
                 setup()
@@ -56,15 +58,23 @@ class Timer:
         return statistics.median(times), min(times)
 
 
+RESULTS = []          # every report() line of this process, for callers that import the module (bench.py)
+EMIT = True           # print one JSON line per config
+
+
 def report(name, what, samples, alg_bytes, flops, med_ms, best_ms, extra=None):
+    import time
     pk = peak()
     gbs = alg_bytes / (med_ms * 1e-3) / 1e9
     line = {"config": name, "what": what, "ms_median": med_ms, "ms_best": best_ms,
             "Msamples_per_s": samples / (med_ms * 1e-3) / 1e6, "GFLOPs_5nlog2n": flops / (med_ms * 1e-3) / 1e9 if flops else None,
-            "algorithmic_bytes": alg_bytes, "achieved_GBps": gbs, "hbm_peak_GBps": pk, "roofline_frac": gbs / pk}
+            "algorithmic_bytes": alg_bytes, "achieved_GBps": gbs, "hbm_peak_GBps": pk, "roofline_frac": gbs / pk,
+            "t_end": time.time()}
     if extra:
         line.update(extra)
-    print(json.dumps(line), flush=True)
+    RESULTS.append(line)
+    if EMIT:
+        print(json.dumps(line), flush=True)
 
 
 def dptr(v):
@@ -84,7 +94,19 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--configs", default="C1,C2a,C2b,C3,C4a,C4b,C5a,C5b")
     args = ap.parse_args()
-    want = set(args.configs.split(","))
+    measure(set(args.configs.split(",")), args.iters)
+
+
+def measure(want, iters, emit=True):
+    """Runs the requested configs on the current device; returns the report lines (also kept in RESULTS)."""
+    global EMIT
+    EMIT = emit
+    del RESULTS[:]
+
+    class _A:
+        pass
+    args = _A()
+    args.iters = iters
     L = bd.lib()
     bd.require_device()
     T = Timer(L)
@@ -223,6 +245,8 @@ def main():
             mag, ph = DspVec.zeros(n, dtype=np.float64), DspVec.zeros(n, dtype=np.float64)
             med, best = T.run(lambda: v.scale_mul_mag_phase(complex(0.5, 0.25), w, mag, ph), max(4, args.iters // 4), warmup=2)
             report("C5b", "c64 3*2^26 fused scale -> mul -> (magnitude, phase)", n, 48 * n, None, med, best)
+    L.bdsp_free(T.flush_buf)
+    return list(RESULTS)
 
 
 if __name__ == "__main__":
