@@ -236,6 +236,14 @@ def _declare(lib):
     lib.bdsp_malloc.restype, lib.bdsp_malloc.argtypes = c_void_p, [c_size_t]
     lib.bdsp_free.restype, lib.bdsp_free.argtypes = None, [c_void_p]
     lib.bdsp_mem_free.restype, lib.bdsp_mem_free.argtypes = c_size_t, []
+    for sfx, T in (("32", c_float), ("64", c_double)):
+        for name in ("bdsp_magnitude_rows_c", "bdsp_magnitude_squared_rows_c", "bdsp_phase_rows_c"):
+            fn = getattr(lib, name + sfx)
+            fn.restype, fn.argtypes = c_int32, [c_void_p, c_void_p, c_size_t, c_size_t]
+        fn = getattr(lib, "bdsp_scale_mul_mag_phase_rows_c" + sfx)
+        fn.restype, fn.argtypes = c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, T, T, c_int32]
+        fn = getattr(lib, "bdsp_interpolatef_rows" + sfx)
+        fn.restype, fn.argtypes = c_int32, [c_void_p, c_void_p, c_size_t, c_size_t, c_int32, c_int32, T, T, T, c_size_t, POINTER(c_size_t)]
     lib.bdsp_malloc_host.restype, lib.bdsp_malloc_host.argtypes = c_void_p, [c_size_t]
     lib.bdsp_free_host.restype, lib.bdsp_free_host.argtypes = None, [c_void_p]
     lib.bdsp_memcpy_h2d.restype, lib.bdsp_memcpy_h2d.argtypes = c_int32, [c_void_p, c_void_p, c_size_t]

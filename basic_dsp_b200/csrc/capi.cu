@@ -733,6 +733,39 @@ template <typename T> Res<T> op_decimatei(Vec<T>* v, uint32_t factor, uint32_t d
 }
 
 // ---- interpolation ---------------------------------------------------------------------------------
+// Tap tables of the polyphase interpolatef path on the device: [2][F][2L+3] (interior, edge) over the window superset
+// n = r-L-1+jj, jj in [0, 2L+3).  Built-in responses are cached by parameter set; callbacks go through the staging buffer
+// (call table_consumed() after the consuming kernel).
+template <typename T> int interp_tap_tables(const RealFn<T>& f, T delay, int F, int L, const T** tab_dev) {
+    const int J = 2 * L + 3;
+    TableKey key = {};
+    key.what = 2; key.kind = f.kind; key.rolloff = (double)f.rolloff; key.a = (double)delay; key.n0 = (size_t)F; key.n1 = (size_t)L;
+    size_t cnt = 0;
+    const T* cached = f.kind != 2 ? table_cache_find<T>(key, &cnt) : nullptr;
+    if (cached) { *tab_dev = cached; return 0; }
+    // function_to_vectors (interpolation.rs:133-181): v_s[k] = f(j_k - s/F), j_0 = -(L-1) + delay
+    std::vector<T> vs((size_t)F * (2 * L + 1));
+    for (int s = 0; s < F; s++) {
+        T offset = (T)s / (T)F;
+        T j = -((T)L - (T)1) + delay;
+        for (int k = 0; k < 2 * L + 1; k++) { vs[(size_t)s * (2 * L + 1) + k] = f(j - offset); j = j + (T)1; }
+    }
+    std::vector<T> tab((size_t)2 * F * J, (T)0);
+    for (int s = 0; s < F; s++) {
+        T* ti = &tab[(size_t)s * J];                    // interior (interpolation.rs:244-275)
+        if (s == 0) { for (int jj = 0; jj <= 2 * L; jj++) ti[jj] = vs[2 * L - jj]; }
+        else { for (int jj = 1; jj <= 2 * L + 1; jj++) ti[jj] = vs[(size_t)(F - s) * (2 * L + 1) + (2 * L + 1 - jj)]; }
+        T* te = &tab[(size_t)(F + s) * J];              // edges (interpolation.rs:293-315)
+        for (int k = 0; k <= 2 * L; k++) te[k + 2] = vs[(size_t)s * (2 * L + 1) + k];
+    }
+    cached = f.kind != 2 ? table_cache_insert<T>(key, tab) : nullptr;
+    if (cached) { *tab_dev = cached; return 0; }
+    T* dev = nullptr;
+    const int rc = upload_table(tab, &dev);
+    *tab_dev = dev;
+    return rc;
+}
+
 template <typename T> Res<T> op_interpolatef(Vec<T>* v, const RealFn<T>& f, T factor, T delay, size_t conv_len) {
     // interpolation.rs:387-482
     delay = delay / v->delta;
@@ -751,42 +784,10 @@ template <typename T> Res<T> op_interpolatef(Vec<T>* v, const RealFn<T>& f, T fa
     if (conv_len <= 202 && new_len >= 2000 && integer) {
         const int F = (int)round(factor);
         const int L = (int)conv_len;
-        const int J = 2 * L + 3;
-        TableKey key = {};
-        key.what = 2; key.kind = f.kind; key.rolloff = (double)f.rolloff; key.a = (double)delay; key.n0 = (size_t)F; key.n1 = (size_t)L;
-        size_t cnt = 0;
-        const T* cached = f.kind != 2 ? table_cache_find<T>(key, &cnt) : nullptr;
-        if (cached) {
-            rc = interp_poly<T>(v->d, v->scratch, cached, N, new_points, F, L, v->is_complex, g_stream);
-            if (rc) return done(v, rc);
-            trade(v);
-            v->len = new_len;
-            return done(v, 0);
-        }
-        // function_to_vectors (interpolation.rs:133-181): v_s[k] = f(j_k - s/F), j_0 = -(L-1) + delay
-        std::vector<T> vs((size_t)F * (2 * L + 1));
-        for (int s = 0; s < F; s++) {
-            T offset = (T)s / (T)F;
-            T j = -((T)L - (T)1) + delay;
-            for (int k = 0; k < 2 * L + 1; k++) { vs[(size_t)s * (2 * L + 1) + k] = f(j - offset); j = j + (T)1; }
-        }
-        // tables over the window superset n = r-L-1+jj, jj in [0, J)
-        std::vector<T> tab((size_t)2 * F * J, (T)0);
-        for (int s = 0; s < F; s++) {
-            T* ti = &tab[(size_t)s * J];                    // interior (interpolation.rs:244-275)
-            if (s == 0) { for (int jj = 0; jj <= 2 * L; jj++) ti[jj] = vs[2 * L - jj]; }
-            else { for (int jj = 1; jj <= 2 * L + 1; jj++) ti[jj] = vs[(size_t)(F - s) * (2 * L + 1) + (2 * L + 1 - jj)]; }
-            T* te = &tab[(size_t)(F + s) * J];              // edges (interpolation.rs:293-315)
-            for (int k = 0; k <= 2 * L; k++) te[k + 2] = vs[(size_t)s * (2 * L + 1) + k];
-        }
-        cached = f.kind != 2 ? table_cache_insert<T>(key, tab) : nullptr;
-        if (cached) rc = interp_poly<T>(v->d, v->scratch, cached, N, new_points, F, L, v->is_complex, g_stream);
-        else {
-            T* dev = nullptr;
-            rc = upload_table(tab, &dev);
-            if (!rc) rc = interp_poly<T>(v->d, v->scratch, dev, N, new_points, F, L, v->is_complex, g_stream);
-            table_consumed();
-        }
+        const T* tab = nullptr;
+        rc = interp_tap_tables<T>(f, delay, F, L, &tab);
+        if (!rc) rc = interp_poly<T>(v->d, v->scratch, tab, N, new_points, F, L, v->is_complex, g_stream);
+        table_consumed();
     } else {
         if (f.kind == 2) return done(v, E_ARG_LEN);   // custom callback + per-output taps: not supported on the device
         rc = interp_frac<T>(v->d, v->scratch, N, new_points, (double)factor, (double)delay, (int)conv_len, f.kind,
@@ -1328,6 +1329,58 @@ template <typename T> int fft_rows(const void* in, void* out, size_t points, siz
     return fft_exec<T>(in, out, points, rows, o, nullptr, 0, g_stream);
 }
 
+// ---- batched (matrix-row) forms: the reference's MatrixMxN applies the vector operation to every row in turn
+// (matrix/src/time_freq.rs:52-74, matrix/src/complex.rs:18-26); rows sit back to back in device memory ----------------------
+// magnitude (hypot, complex_to_real.rs:376) / phase (atan2, :402) / magnitude_squared of `rows` rows: elementwise, so the
+// batch is one launch over rows * points points
+template <typename T> int c2r_rows(int op, const void* in, void* out, size_t points, size_t rows) {
+    if (!points || !rows) return 0;
+    return ew_complex_to_real<T>(op, in, out, points * rows, g_stream);
+}
+// fused scale(c) -> mul(&w) -> (magnitude, phase) over rows (elementwise as well; w has the same shape as v)
+template <typename T>
+int chain_rows(void* v, const void* w, void* mag, void* phase, size_t points, size_t rows, T cre, T cim, int write_back) {
+    if (!points || !rows) return 0;
+    return ew_scale_mul_mag_phase<T>(v, w, mag, phase, points * rows, (double)cre, (double)cim, cim != (T)0, write_back, g_stream);
+}
+// interpolatef (interpolation.rs:387-482) with a built-in impulse response on `rows` rows of `points` points (complex or
+// real), integer factor (the polyphase path): the tap tables are built once, every row is one kernel launch.
+// out: rows * new_points points, new_points as interpolatef32 computes it.  Returns the reference's error codes.
+template <typename T>
+int interp_rows(const void* in, void* out, size_t points, size_t rows, int is_complex, int kind, T rolloff, T factor, T delay,
+                size_t conv_len, size_t* new_points_out) {
+    typedef typename CpxOf<T>::type C;
+    const size_t len = is_complex ? 2 * points : points;
+    if (conv_len > points / 2) conv_len = points / 2;
+    const double nl = round((double)((T)len * factor));
+    if (!(nl >= 0)) return E_ARG_LEN;
+    size_t new_len = (size_t)nl;
+    new_len += new_len % 2;
+    const size_t new_points = is_complex ? new_len / 2 : new_len;
+    if (new_points_out) *new_points_out = new_points;
+    if (!points || !rows) return 0;
+    const bool integer = (T)fabs((T)round(factor) - factor) < (T)1e-6;
+    RealFn<T> f;
+    f.kind = kind == 0 ? 0 : 1;
+    f.rolloff = rolloff;
+    const size_t in_stride = (is_complex ? sizeof(C) : sizeof(T)) * points, out_stride = (is_complex ? sizeof(C) : sizeof(T)) * new_points;
+    if (conv_len <= 202 && new_len >= 2000 && integer) {
+        const int F = (int)round(factor), L = (int)conv_len;
+        const T* tab = nullptr;
+        int rc = interp_tap_tables<T>(f, delay, F, L, &tab);
+        for (size_t r = 0; r < rows && !rc; r++)
+            rc = interp_poly<T>(reinterpret_cast<const char*>(in) + r * in_stride, reinterpret_cast<char*>(out) + r * out_stride, tab, points,
+                                new_points, F, L, is_complex, g_stream);
+        table_consumed();
+        return rc;
+    }
+    int rc = 0;
+    for (size_t r = 0; r < rows && !rc; r++)
+        rc = interp_frac<T>(reinterpret_cast<const char*>(in) + r * in_stride, reinterpret_cast<char*>(out) + r * out_stride, points, new_points,
+                            (double)factor, (double)delay, (int)conv_len, f.kind, (double)rolloff, is_complex, g_stream);
+    return rc;
+}
+
 }  // namespace
 
 // =====================================================================================================
@@ -1679,6 +1732,30 @@ extern "C" int32_t bdsp_convolve_signal_rows_c32(const void* in, void* out, size
 extern "C" int32_t bdsp_convolve_signal_rows_c64(const void* in, void* out, size_t points, size_t rows, const BdspConvPlan* plan) {
     return conv_rows<double>(in, out, points, rows, reinterpret_cast<const ConvPlan*>(plan));
 }
+#define BDSP_ROWS(S, T)                                                                                                          \
+    extern "C" int32_t bdsp_magnitude_rows_c##S(const void* in, void* out, size_t points, size_t rows) {                              \
+        return c2r_rows<T>(C2R_MAG_HYPOT, in, out, points, rows);                                                                     \
+    }                                                                                                                                 \
+    extern "C" int32_t bdsp_magnitude_squared_rows_c##S(const void* in, void* out, size_t points, size_t rows) {                      \
+        return c2r_rows<T>(C2R_MAG_SQ, in, out, points, rows);                                                                        \
+    }                                                                                                                                 \
+    extern "C" int32_t bdsp_phase_rows_c##S(const void* in, void* out, size_t points, size_t rows) {                                  \
+        return c2r_rows<T>(C2R_PHASE, in, out, points, rows);                                                                         \
+    }                                                                                                                                 \
+    extern "C" int32_t bdsp_scale_mul_mag_phase_rows_c##S(void* v, const void* w, void* magnitude, void* phase, size_t points,        \
+                                                          size_t rows, T scale_re, T scale_im, int32_t write_back) {                  \
+        return chain_rows<T>(v, w, magnitude, phase, points, rows, scale_re, scale_im, write_back);                                   \
+    }                                                                                                                                 \
+    extern "C" int32_t bdsp_interpolatef_rows##S(const void* in, void* out, size_t points, size_t rows, int32_t is_complex,           \
+                                                 int32_t impulse_response, T rolloff, T interpolation_factor, T delay, size_t len,    \
+                                                 size_t* new_points) {                                                                \
+        return interp_rows<T>(in, out, points, rows, is_complex, impulse_response, rolloff, interpolation_factor, delay, len,         \
+                              new_points);                                                                                            \
+    }
+BDSP_ROWS(32, float)
+BDSP_ROWS(64, double)
+#undef BDSP_ROWS
+
 extern "C" void* bdsp_malloc(size_t bytes) {
     void* p = nullptr;
     if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) { set_last_error("bdsp_malloc(%zu) failed", bytes); return nullptr; }

@@ -514,6 +514,32 @@ BdspConvPlan* bdsp_conv_plan_create_c64(const void* h_device, size_t h_points);
 void bdsp_conv_plan_destroy(BdspConvPlan* plan);
 int32_t bdsp_convolve_signal_rows_c32(const void* in, void* out, size_t points, size_t rows, const BdspConvPlan* plan);
 int32_t bdsp_convolve_signal_rows_c64(const void* in, void* out, size_t points, size_t rows, const BdspConvPlan* plan);
+
+/* More batched (matrix-row) forms: the reference's MatrixMxN applies the vector operation to every row in turn
+ * (matrix/src/time_freq.rs:52-74 interpolatef ..., matrix/src/complex.rs:18-26 magnitude / phase ...).  Rows sit back to
+ * back in device memory; `in` / `out` are raw device pointers (bdsp_malloc or bdsp_device_ptr32), in != out.
+ * magnitude = hypot(re, im) as ComplexToRealTransformsOps::magnitude (complex_to_real.rs:374-379), phase = atan2(im, re).
+ * out: rows * points real scalars. */
+int32_t bdsp_magnitude_rows_c32(const void* in, void* out, size_t points, size_t rows);
+int32_t bdsp_magnitude_rows_c64(const void* in, void* out, size_t points, size_t rows);
+int32_t bdsp_magnitude_squared_rows_c32(const void* in, void* out, size_t points, size_t rows);
+int32_t bdsp_magnitude_squared_rows_c64(const void* in, void* out, size_t points, size_t rows);
+int32_t bdsp_phase_rows_c32(const void* in, void* out, size_t points, size_t rows);
+int32_t bdsp_phase_rows_c64(const void* in, void* out, size_t points, size_t rows);
+/* rows of the fused chain of bdsp_scale_mul_mag_phase32: v <- v * scale * w (written back iff write_back), magnitude and
+ * phase of the product; v, w: rows * points complex points, magnitude, phase: rows * points real scalars */
+int32_t bdsp_scale_mul_mag_phase_rows_c32(void* v, const void* w, void* magnitude, void* phase, size_t points, size_t rows,
+                                          float scale_re, float scale_im, int32_t write_back);
+int32_t bdsp_scale_mul_mag_phase_rows_c64(void* v, const void* w, void* magnitude, void* phase, size_t points, size_t rows,
+                                          double scale_re, double scale_im, int32_t write_back);
+/* interpolatef32 (facade32.rs:1334) on every one of `rows` rows of `points` points (is_complex: interleaved complex
+ * points, else real scalars) with a built-in impulse response (0 Sinc, else RaisedCosine(rolloff)); delay is in samples
+ * (delta = 1).  out must hold rows * new_points points, new_points = round(len * factor) rounded up to even in scalars
+ * (interpolation.rs:406-410), also returned through *new_points (may be NULL).  The tap tables are built once. */
+int32_t bdsp_interpolatef_rows32(const void* in, void* out, size_t points, size_t rows, int32_t is_complex, int32_t impulse_response,
+                                 float rolloff, float interpolation_factor, float delay, size_t len, size_t* new_points);
+int32_t bdsp_interpolatef_rows64(const void* in, void* out, size_t points, size_t rows, int32_t is_complex, int32_t impulse_response,
+                                 double rolloff, double interpolation_factor, double delay, size_t len, size_t* new_points);
 /* raw memory helpers so that non-CUDA hosts (ctypes, cgo, JNI) can drive section 3 */
 void* bdsp_malloc(size_t bytes);
 void bdsp_free(void* device_ptr);

@@ -193,3 +193,67 @@ def test_device_ptr_access_invalidates_cached_spectrum():
     L.bdsp_memcpy_h2d(dptr(hv), h2.ctypes.data, l * 8)      # refresh the taps through the raw device pointer
     L.bdsp_sync()
     assert o.rel_l2(DspVec(x).convolve_signal(hv).to_numpy(), o.convolve_signal(x, h2)) <= tol(4096, np.float32)
+
+
+# ---- batched (matrix-row) forms beyond fft / convolve_signal (matrix/src/time_freq.rs:52-74, matrix/src/complex.rs:18-26) ---------
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_magnitude_phase_rows(dtype):
+    L = bd.lib()
+    sfx = "32" if dtype == np.float32 else "64"
+    rng = np.random.default_rng(11)
+    points, rows = 3001, 7
+    x = rand_c(rng, points * rows, dtype)
+    xv = DspVec(x)
+    out = DspVec.zeros(points * rows, dtype=dtype)
+    assert getattr(L, "bdsp_magnitude_rows_c" + sfx)(dptr(xv), dptr(out), points, rows) == 0
+    assert o.ulp_diff(out.to_numpy(), o.magnitude(x, dtype), dtype).max() <= 4
+    # identical to the per-vector call on every row
+    for r in (0, rows - 1):
+        assert np.array_equal(out.to_numpy()[r * points:(r + 1) * points], DspVec(x[r * points:(r + 1) * points]).magnitude().to_numpy())
+    assert getattr(L, "bdsp_phase_rows_c" + sfx)(dptr(xv), dptr(out), points, rows) == 0
+    assert o.ulp_diff(out.to_numpy(), o.phase(x, dtype), dtype).max() <= 4
+    assert getattr(L, "bdsp_magnitude_squared_rows_c" + sfx)(dptr(xv), dptr(out), points, rows) == 0
+    assert o.ulp_diff(out.to_numpy(), o.magnitude_squared(x, dtype), dtype).max() <= 4
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_fused_chain_rows(dtype):
+    L = bd.lib()
+    sfx = "32" if dtype == np.float32 else "64"
+    rng = np.random.default_rng(12)
+    points, rows = 5000, 5
+    x, w = rand_c(rng, points * rows, dtype), rand_c(rng, points * rows, dtype)
+    c = complex(0.75, -1.5)
+    xv, wv = DspVec(x), DspVec(w)
+    mag, ph = DspVec.zeros(points * rows, dtype=dtype), DspVec.zeros(points * rows, dtype=dtype)
+    assert getattr(L, "bdsp_scale_mul_mag_phase_rows_c" + sfx)(dptr(xv), dptr(wv), dptr(mag), dptr(ph), points, rows, c.real, c.imag, 0) == 0
+    ref = o.mul(o.complex_scale(x, c, dtype), w, dtype)
+    assert o.ulp_diff(mag.to_numpy(), o.magnitude(ref, dtype), dtype).max() <= 4
+    assert o.ulp_diff(ph.to_numpy(), o.phase(ref, dtype), dtype).max() <= 4
+    # bit-identical to the per-vector fused call
+    m1, p1 = DspVec.zeros(0, dtype=dtype), DspVec.zeros(0, dtype=dtype)
+    DspVec(x[:points]).scale_mul_mag_phase(c, DspVec(w[:points]), m1, p1)
+    assert np.array_equal(m1.to_numpy(), mag.to_numpy()[:points]) and np.array_equal(p1.to_numpy(), ph.to_numpy()[:points])
+
+
+@pytest.mark.parametrize("dtype,cplx_", [(np.float32, False), (np.float32, True), (np.float64, False)])
+def test_interpolatef_rows(dtype, cplx_):
+    import ctypes
+    L = bd.lib()
+    sfx = "32" if dtype == np.float32 else "64"
+    rng = np.random.default_rng(13)
+    points, rows, F, conv_len = 3000, 4, 4, 12
+    x = rand_c(rng, points * rows, dtype) if cplx_ else rng.uniform(-10, 10, points * rows).astype(dtype)
+    xv = DspVec(x)
+    out = DspVec.zeros((2 if cplx_ else 1) * points * rows * F, is_complex=cplx_, dtype=dtype)
+    npts = ctypes.c_size_t(0)
+    rc = getattr(L, "bdsp_interpolatef_rows" + sfx)(dptr(xv), dptr(out), points, rows, 1 if cplx_ else 0, bd.SINC, 0.0, float(F), 0.0, conv_len,
+                                                    ctypes.byref(npts))
+    assert rc == 0 and npts.value == points * F
+    got = out.to_numpy().reshape(rows, points * F)
+    xr = x.reshape(rows, points)
+    for r in range(rows):
+        ref = o.interpolatef(xr[r], lambda t: o.sinc_impulse(t, dtype), float(F), 0.0, conv_len, dtype)
+        assert o.rel_l2(got[r], ref) <= tol(4096, dtype)
+        # identical to the per-vector trait call
+        assert np.array_equal(got[r], DspVec(xr[r].copy()).interpolatef(bd.SINC, 0.0, float(F), 0.0, conv_len).to_numpy())
