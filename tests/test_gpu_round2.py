@@ -207,9 +207,8 @@ def test_magnitude_phase_rows(dtype):
     out = DspVec.zeros(points * rows, dtype=dtype)
     assert getattr(L, "bdsp_magnitude_rows_c" + sfx)(dptr(xv), dptr(out), points, rows) == 0
     assert o.ulp_diff(out.to_numpy(), o.magnitude(x, dtype), dtype).max() <= 4
-    # identical to the per-vector call on every row
-    for r in (0, rows - 1):
-        assert np.array_equal(out.to_numpy()[r * points:(r + 1) * points], DspVec(x[r * points:(r + 1) * points]).magnitude().to_numpy())
+    # (the C ABI's per-vector magnitude32 is the reference's magnitude_b = sqrt(re^2 + im^2), facade32.rs:559; the rows form is the
+    # trait's magnitude = hypot, complex_to_real.rs:376: both within 4 ulp of the oracle, not bit-identical to each other)
     assert getattr(L, "bdsp_phase_rows_c" + sfx)(dptr(xv), dptr(out), points, rows) == 0
     assert o.ulp_diff(out.to_numpy(), o.phase(x, dtype), dtype).max() <= 4
     assert getattr(L, "bdsp_magnitude_squared_rows_c" + sfx)(dptr(xv), dptr(out), points, rows) == 0
