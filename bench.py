@@ -164,6 +164,17 @@ def run_gpu(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
     torch.cuda.set_device(local)
+    # one disjoint slice of the host's CPUs per rank (before the pinned buffers are allocated and first touched): the
+    # end-to-end path is bound by the host <-> device link, and ranks that migrate over each other's cores and memory make it worse
+    affinity = None
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+        if world > 1 and len(cpus) >= world:
+            per = len(cpus) // world
+            affinity = cpus[local * per:(local + 1) * per]
+            os.sched_setaffinity(0, affinity)
+    except (AttributeError, OSError):
+        affinity = None
     L = bd.lib()
     if L.bdsp_set_device(local) != 0:
         raise SystemExit("bdsp_set_device failed: %s" % L.bdsp_last_error())
@@ -332,7 +343,7 @@ def run_gpu(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "rows_per_gpu": ROWS, "points": N_POINTS, "taps": TAPS,
                        "l2": "inputs larger than L2 (512 MiB in + 512 MiB out per step), no flush",
-                       "sharding": "rows, no collective"},
+                       "sharding": "rows, no collective", "cpus_per_rank": len(affinity) if affinity else None},
             "gflops_5nlog2n": flops * world / (total_ms_max / args.steps * 1e-3) / 1e9,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": 1027147776.0, "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/r2_ols4096i_ncu.txt)",
