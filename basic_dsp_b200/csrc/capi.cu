@@ -483,6 +483,23 @@ template <typename T> Res<T> op_convolve_signal(Vec<T>* v, Vec<T>* h) {
     return done(v, convolve_taps<T>(v, h->d, L, h->is_complex, &cache));
 }
 
+// More taps than points: the tap window wraps around the vector (the reference's ReverseWrappingIterator,
+// time_freq/mod.rs:788-848).  Folds Lt taps of `width` scalars each into an N-tap kernel with the same circular result:
+// y[i] = sum_k x[(i + cl - 1 - k) mod N] t[k], cl = Lt - Lt/2, re-centred on cl' = N - N/2.
+template <typename T> void fold_taps(std::vector<T>& taps, size_t N, size_t width) {
+    const size_t Lt = taps.size() / width;
+    if (Lt <= N) return;
+    std::vector<T> folded(N * width, (T)0);
+    const size_t cl = Lt - Lt / 2, cl2 = N - N / 2;
+    for (size_t k = 0; k < Lt; k++) {
+        const long long off = (long long)cl - 1 - (long long)k;       // x index offset of tap k
+        long long k2 = ((long long)cl2 - 1 - off) % (long long)N;     // slot of the N-tap kernel with the same offset
+        if (k2 < 0) k2 += (long long)N;
+        for (size_t c = 0; c < width; c++) folded[(size_t)k2 * width + c] += taps[k * width + c];
+    }
+    taps.swap(folded);
+}
+
 template <typename T> Res<T> op_convolve_fn(Vec<T>* v, const RealFn<T>& f, T ratio, size_t len) {
     // convolution.rs:136-192 (real impulse response)
     if (v->domain != 0) { mark_invalid(v); return done(v, 0); }   // assert_time!
@@ -512,20 +529,7 @@ template <typename T> Res<T> op_convolve_fn(Vec<T>* v, const RealFn<T>& f, T rat
         for (size_t q = 0; q < 2 * L + 1; q++) { t[q] = f(-j * ratio); j = j + (T)1; }
         taps.assign(t.rbegin(), t.rend());
     }
-    if (taps.size() > N) {
-        // more taps than points: fold the taps modulo N (the window wraps around the vector)
-        std::vector<T> folded(N, (T)0);
-        const size_t Lt = taps.size(), cl = Lt - Lt / 2;
-        // y[i] = sum_k x[(i + cl - 1 - k) mod N] t[k]; re-centre on an N-tap kernel with cl' = N - N/2
-        const size_t cl2 = N - N / 2;
-        for (size_t k = 0; k < Lt; k++) {
-            long long off = (long long)cl - 1 - (long long)k;           // x index offset
-            long long k2 = ((long long)cl2 - 1 - off) % (long long)N;   // tap slot with the same offset
-            if (k2 < 0) k2 += (long long)N;
-            folded[(size_t)k2] += taps[k];
-        }
-        taps.swap(folded);
-    }
+    fold_taps(taps, N, 1);
     if (f.kind != 2) {
         const T* cached = table_cache_insert<T>(key, taps);
         if (cached) return done(v, convolve_taps<T>(v, cached, taps.size(), false, nullptr));
@@ -547,7 +551,6 @@ Res<T> op_convolve_cfn(Vec<T>* v, CT (*fn)(const void*, T), const void* data, T 
     const size_t N = points_of(v);
     if (N == 0) return done(v, 0);
     const size_t L = len > N ? N : len;
-    if (2 * L + 1 > N) return done(v, E_ARG_LEN);
     std::vector<T> t(2 * (2 * L + 1));
     T j = -(T)L;
     for (size_t q = 0; q < 2 * L + 1; q++) {
@@ -556,10 +559,11 @@ Res<T> op_convolve_cfn(Vec<T>* v, CT (*fn)(const void*, T), const void* data, T 
         t[2 * k] = c.re; t[2 * k + 1] = c.im;
         j = j + (T)1;
     }
+    fold_taps(t, N, 2);   // 2L + 1 > N: the window wraps around the vector, as in the reference
     T* h_dev = nullptr;
     int rc = upload_table(t, &h_dev);
     if (rc) return done(v, rc);
-    rc = convolve_taps<T>(v, h_dev, 2 * L + 1, true, nullptr);
+    rc = convolve_taps<T>(v, h_dev, t.size() / 2, true, nullptr);
     table_consumed();
     return done(v, rc);
 }

@@ -256,3 +256,19 @@ def test_interpolatef_rows(dtype, cplx_):
         assert o.rel_l2(got[r], ref) <= tol(4096, dtype)
         # identical to the per-vector trait call
         assert np.array_equal(got[r], DspVec(xr[r].copy()).interpolatef(bd.SINC, 0.0, float(F), 0.0, conv_len).to_numpy())
+
+
+def test_convolve_complex_callback_wraps_around_short_vectors():
+    """2 len + 1 > points: the tap window wraps around the vector (ReverseWrappingIterator, time_freq/mod.rs:788-848;
+    ADVICE r1: the complex-tap path used to return InvalidArgumentLength)."""
+    rng = np.random.default_rng(78)
+    for n, length in [(12, 10), (7, 7), (30, 20)]:
+        x = rand_c(rng, n, np.float32)
+        fn = lambda t: complex(o.sinc_impulse(t, np.float32), 0.5 * o.sinc_impulse(t * 0.5, np.float32))
+        got = DspVec(x).convolve_complex(fn, 0.5, length).to_numpy()
+        L_ = min(length, n)
+        idx = np.arange(n)
+        ref = np.zeros(n, dtype=np.complex128)
+        for m in range(-L_, L_ + 1):
+            ref += x[(idx + m) % n].astype(np.complex128) * fn(np.float32(-m * 0.5))
+        assert o.rel_l2(got, ref) <= tol(4096, np.float32), (n, length)
