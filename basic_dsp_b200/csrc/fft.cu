@@ -260,6 +260,8 @@ struct TileParams {
     int last;                  // last pass: out index goes through OutMap (batch = inner sequence)
     int magnitude;
     OutMap om;
+    int q = 1;                 // > 1 (first pass only): columns of q * m points; a radix-q DIF step over stride m runs in shared
+                               // memory in front of the m-point transforms, result index K = ka + q * kb
 };
 
 template <typename T, bool INV>
@@ -269,6 +271,7 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? 1024 : 512, (sizeof(T) == 8 &
     C* s = reinterpret_cast<C*>(smem_raw);
     const int m = 1 << p.log2m;
     const int ct = p.ct;
+    const int Q = p.q;           // sub-columns per lane (1: plain power-of-two columns)
     const int sstride = m + 16;  // sequence stride in shared memory (keeps lane-major accesses conflict free)
     const long long tiles_per_o1 = p.lanes / ct;
     long long t = blockIdx.x;
@@ -277,7 +280,7 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? 1024 : 512, (sizeof(T) == 8 &
     const long long b = t / p.o1_count;
     const long long lane0 = tile * ct;
     const long long in_base = b * p.in_batch_stride + o1 * p.in_o1_stride;
-    const int total = m * ct;
+    const int total = m * ct * Q;
     // ---- load ----  (UN independent global loads are issued before the first use: the loop is latency-bound otherwise)
     {
         constexpr int UN = 8;
@@ -310,13 +313,51 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? 1024 : 512, (sizeof(T) == 8 &
                     if (contiguous) { l = idx >> p.log2m; pt = idx & (m - 1); }
                     else { pt = idx >> lct; l = idx & (ct - 1); }
                     v[u].x *= scale; v[u].y *= scale;
-                    s[spad(l * sstride + pt)] = v[u];
+                    // Q > 1: point pt = a * m + b of lane l goes to sequence l * Q + a, element b
+                    s[spad(Q > 1 ? (l * Q + (pt >> p.log2m)) * sstride + (pt & (m - 1)) : l * sstride + pt)] = v[u];
                 }
             }
         }
     }
     (void)in_base;
     __syncthreads();
+    if (Q > 1) {
+        // radix-Q DIF step over stride m inside every lane: z_ka[b] = (sum_a y[a m + b] W_Q^{a ka}) W_{Q m}^{b ka}
+        // (time_freq/mod.rs:32-63: rustfft takes any length; this folds the odd factor of q * 2^k lengths into the first pass)
+        C* wq = s + spad_host_dev((m + 16) * ct * Q) + ct * (33 + (((Q * m + 31) >> 5) | 1));
+        if ((int)threadIdx.x < Q) wq[threadIdx.x] = unit_root<T>((unsigned long long)threadIdx.x, (unsigned long long)Q, INV ? 1 : -1);
+        __syncthreads();
+        for (int i = threadIdx.x; i < m * ct; i += blockDim.x) {
+            const int l = i >> p.log2m, b = i & (m - 1);
+            if (Q == 3) {   // registers only
+                C* p0 = &s[spad((l * 3 + 0) * sstride + b)];
+                C* p1 = &s[spad((l * 3 + 1) * sstride + b)];
+                C* p2 = &s[spad((l * 3 + 2) * sstride + b)];
+                const C y0 = *p0, y1 = *p1, y2 = *p2;
+                const C w1 = unit_root<T>((unsigned long long)b, (unsigned long long)(3 * m), INV ? 1 : -1);
+                const C t1 = cmul(y1, wq[1]), t2 = cmul(y2, wq[2]), u1 = cmul(y1, wq[2]), u2 = cmul(y2, wq[1]);
+                *p0 = cadd(y0, cadd(y1, y2));
+                *p1 = cmul(cadd(y0, cadd(t1, t2)), w1);
+                *p2 = cmul(cadd(y0, cadd(u1, u2)), cmul(w1, w1));
+                continue;
+            }
+            C y[31];
+            for (int a = 0; a < Q; a++) y[a] = s[spad((l * Q + a) * sstride + b)];
+            const C w1 = unit_root<T>((unsigned long long)b, (unsigned long long)(Q * m), INV ? 1 : -1);   // W_{Q m}^{b}
+            C wk = mk<T>(1, 0);
+            for (int ka = 0; ka < Q; ka++) {
+                C acc = y[0];
+                int e = 0;
+                for (int a = 1; a < Q; a++) {
+                    e += ka; if (e >= Q) e -= Q;
+                    acc = cadd(acc, cmul(y[a], wq[e]));
+                }
+                s[spad((l * Q + ka) * sstride + b)] = cmul(acc, wk);
+                wk = cmul(wk, w1);
+            }
+        }
+        __syncthreads();
+    }
     // ---- transform ----
     {
         const int n = m;
@@ -325,23 +366,23 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? 1024 : 512, (sizeof(T) == 8 &
         if constexpr (sizeof(T) == 8 && BDSP_TILE_F64_RADIX8) {
             // f64: radix-8 stages, 8 points per thread (half the registers of radix 16 -> twice the resident warps;
             // 2^9 = 8*8*8 needs the same three stages as 16*16*2)
-            while (rem >= 3) { stockham_stage_strided<T, 8, INV, 1>(s, n, ct, sstride, Ns, tw); Ns <<= 3; rem -= 3; }
-            if (rem == 2) stockham_stage_strided<T, 4, INV, 2>(s, n, ct, sstride, Ns, tw);
-            else if (rem == 1) stockham_stage_strided<T, 2, INV, 4>(s, n, ct, sstride, Ns, tw);
+            while (rem >= 3) { stockham_stage_strided<T, 8, INV, 1>(s, n, ct * Q, sstride, Ns, tw); Ns <<= 3; rem -= 3; }
+            if (rem == 2) stockham_stage_strided<T, 4, INV, 2>(s, n, ct * Q, sstride, Ns, tw);
+            else if (rem == 1) stockham_stage_strided<T, 2, INV, 4>(s, n, ct * Q, sstride, Ns, tw);
         } else {
-            while (rem >= 4) { stockham_stage_strided<T, 16, INV, 1>(s, n, ct, sstride, Ns, tw); Ns <<= 4; rem -= 4; }
-            if (rem == 3) stockham_stage_strided<T, 8, INV, 2>(s, n, ct, sstride, Ns, tw);
-            else if (rem == 2) stockham_stage_strided<T, 4, INV, 4>(s, n, ct, sstride, Ns, tw);
-            else if (rem == 1) stockham_stage_strided<T, 2, INV, 8>(s, n, ct, sstride, Ns, tw);
+            while (rem >= 4) { stockham_stage_strided<T, 16, INV, 1>(s, n, ct * Q, sstride, Ns, tw); Ns <<= 4; rem -= 4; }
+            if (rem == 3) stockham_stage_strided<T, 8, INV, 2>(s, n, ct * Q, sstride, Ns, tw);
+            else if (rem == 2) stockham_stage_strided<T, 4, INV, 4>(s, n, ct * Q, sstride, Ns, tw);
+            else if (rem == 1) stockham_stage_strided<T, 2, INV, 8>(s, n, ct * Q, sstride, Ns, tw);
         }
     }
     // ---- twiddle + store ----
     // W_{tw_n}^{lane*k} = A[l][k & 31] * B[l][k >> 5] with A[l][a] = W^{lane*a}, B[l][b] = W^{lane*32*b}:
     // ct*(32 + m/32) exactly reduced roots per tile (sincospi) instead of one per element.
     // rows are padded to an odd length: consecutive lanes (rows) must fall into different banks
-    C* twA = s + spad_host_dev((m + 16) * ct);
+    C* twA = s + spad_host_dev((m + 16) * ct * Q);
     C* twB = twA + ct * 33;
-    const int nb = (m + 31) >> 5;
+    const int nb = (Q * m + 31) >> 5;
     const int nbs = nb | 1;
     if (p.tw_n) {
         for (int i = threadIdx.x; i < ct * (32 + nb); i += blockDim.x) {
@@ -367,7 +408,8 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? 1024 : 512, (sizeof(T) == 8 &
         int l, k;
         if (lane_major) { k = idx >> lct; l = idx & (ct - 1); }
         else { l = idx >> p.log2m; k = idx & (m - 1); }
-        C v = s[spad(l * sstride + k)];
+        // Q > 1 (always lane-major): result K = ka + Q * kb of the column sits in sequence l * Q + ka, element kb
+        C v = Q > 1 ? s[spad((l * Q + k % Q) * sstride + k / Q)] : s[spad(l * sstride + k)];
         if (p.tw_n) {
             const C w = cmul(twA[l * 33 + (k & 31)], twB[l * nbs + (k >> 5)]);
             v = cmul(v, w);
@@ -566,9 +608,10 @@ template <typename T, bool INV>
 int launch_tile(const TileParams& p, long long batch, T scale, cudaStream_t st) {
     typedef typename CpxOf<T>::type C;
     const int m = 1 << p.log2m;
-    const size_t smem = (spad_host((size_t)(m + 16) * p.ct) + (size_t)p.ct * (33 + (((m + 31) >> 5) | 1))) * sizeof(C);
-    int threads = block_fft_threads(m, p.ct);
-    if (sizeof(T) == 8 && BDSP_TILE_F64_RADIX8) { threads = (m * p.ct / 8 + 31) / 32 * 32; if (threads < 32) threads = 32; }
+    const size_t smem = (spad_host((size_t)(m + 16) * p.ct * p.q) + (size_t)p.ct * (33 + (((p.q * m + 31) >> 5) | 1)) + (p.q > 1 ? 32 : 0)) * sizeof(C);
+    int threads = block_fft_threads(m, p.ct * p.q);
+    if (sizeof(T) == 8 && BDSP_TILE_F64_RADIX8) { threads = (m * p.ct * p.q / 8 + 31) / 32 * 32; if (threads < 32) threads = 32; }
+    if (threads > (sizeof(T) == 4 ? 1024 : 512)) { set_last_error("fft tile: %d threads", threads); return -2; }
     const long long grid = batch * p.o1_count * (p.lanes / p.ct);
     int rc = set_smem(fft_tile_kernel<T, INV>, smem);
     if (rc) return rc;
@@ -656,6 +699,59 @@ int fft_pow2(const void* in, void* out, size_t n, size_t batch, bool real_in, bo
     p.o1_count = npass == 3 ? n2 : 1;
     p.in_lane_stride = (long long)n / n1; p.in_point_stride = 1; p.in_o1_stride = npass == 3 ? nl : 0;
     p.out_lane_stride = 1; p.out_point_stride = npass == 3 ? n1 * n2 : n1; p.out_o1_stride = npass == 3 ? n1 : 0;
+    p.tw_n = 0; p.in_rot = 0; p.real_input = 0; p.last = 1; p.magnitude = mag;
+    return launch_tile<T, INV>(p, (long long)batch, (T)1, st);
+}
+
+// n = q * 2^k (q odd <= 31) too long for one CTA: n = N1 * N2 * N3 with N1 = q * 2^a, three passes of tiles
+//   A: columns of N1 points over stride n / N1 (radix-q step + 2^a-point transforms in shared memory), twiddle W_n^{l K1}
+//   B: inside every row K1: columns of N2 points over stride N3, in place, twiddle W_{N2 N3}^{l k2}
+//   C: rows of N3 points, lanes = K1, transposing store X[K1 + N1 (k2 + N2 k3)]
+// 96 bytes per point (c64) instead of the 160 of "radix-q pre-pass + three passes + interleave pass".
+template <typename T, bool INV>
+int fft_q_three_pass(const void* in, void* out, size_t n, size_t batch, size_t q, bool real_in, bool mag, long long in_rot, T scale,
+                     const OutMap& om, void* work, cudaStream_t st) {
+    typedef typename CpxOf<T>::type C;
+    size_t P = n / q;
+    const int k = ilog2(P);
+    const int mx = tile_log2m_max<T>();
+    int a = 8 - (q > 3 ? ilog2(q) - 1 : 0);          // N1 = q * 2^a <= ~1024 points per column
+    if (a < 4) a = 4;
+    int rest = k - a;
+    if (rest < 1 || rest > 2 * mx) return 1;
+    const bool two = rest <= mx;                       // short enough: no middle pass
+    const int b = two ? 0 : (rest + 1) / 2, c = rest - b;
+    const long long N1 = (long long)q << a, N2 = 1ll << b, N3 = 1ll << c;
+    const long long ct1 = 4;                           // lanes of the first pass: 64-byte (c64) row segments, q * 2^a * 4 points per tile
+    if ((long long)n / N1 % ct1) return 1;
+    C* tmp = reinterpret_cast<C*>(work);
+    TileParams p;
+    p.in = in; p.out = tmp; p.log2m = a; p.q = (int)q;
+    p.lanes = (long long)n / N1; p.ct = (int)ct1; p.o1_count = 1;
+    p.in_lane_stride = 1; p.in_point_stride = (long long)n / N1; p.in_o1_stride = 0; p.in_batch_stride = (long long)n;
+    p.out_lane_stride = 1; p.out_point_stride = (long long)n / N1; p.out_o1_stride = 0; p.out_batch_stride = (long long)n;
+    p.tw_n = (long long)n; p.in_rot = in_rot; p.in_n = (long long)n; p.real_input = real_in; p.last = 0; p.magnitude = 0;
+    p.om = om;
+    int rc = launch_tile<T, INV>(p, (long long)batch, scale, st);
+    if (rc) return rc;
+    p.q = 1;
+    if (!two) {
+        p.in = tmp; p.out = tmp; p.log2m = b;
+        p.lanes = N3; p.ct = (int)(N3 < tile_lanes<T>() ? N3 : tile_lanes<T>()); p.o1_count = N1;
+        p.in_lane_stride = 1; p.in_point_stride = N3; p.in_o1_stride = N2 * N3;
+        p.out_lane_stride = 1; p.out_point_stride = N3; p.out_o1_stride = N2 * N3;
+        p.tw_n = N2 * N3; p.in_rot = 0; p.real_input = 0;
+        rc = launch_tile<T, INV>(p, (long long)batch, (T)1, st);
+        if (rc) return rc;
+    }
+    p.in = tmp; p.out = out; p.log2m = c;
+    p.lanes = N1; p.ct = (int)tile_lanes<T>();
+    // short rows: more lanes per tile so that a CTA still holds >= 2048 points
+    while (p.ct < 64 && ((long long)p.ct << c) < 2048 && N1 % (2 * p.ct) == 0) p.ct *= 2;
+    if (N1 % p.ct) return -2;
+    p.o1_count = two ? 1 : N2;
+    p.in_lane_stride = (long long)n / N1; p.in_point_stride = 1; p.in_o1_stride = two ? 0 : N3;
+    p.out_lane_stride = 1; p.out_point_stride = two ? N1 : N1 * N2; p.out_o1_stride = two ? 0 : N1;
     p.tw_n = 0; p.in_rot = 0; p.real_input = 0; p.last = 1; p.magnitude = mag;
     return launch_tile<T, INV>(p, (long long)batch, (T)1, st);
 }
@@ -795,6 +891,13 @@ int fft_any(const void* in, void* out, size_t n, size_t batch, const FftOpts& o,
     const size_t q = n / P;
     if (q <= 31 && P >= 2) {
         size_t need = n * batch * sizeof(C);
+        if (sizeof(T) == 8 && P > fft_block_max_n<T>() && !o.magnitude) {
+            // f64, long q * 2^k: three passes with the radix-q step inside the first one (C5a: 3 * 2^26)
+            void* w = work;
+            if (!w || work_bytes < need || w == in || w == out) { w = workspace(need, 0); if (!w) return -1001; }
+            const int rc = fft_q_three_pass<T, INV>(in, out, n, batch, q, o.real_input != 0, false, in_rot, scale, om, w, st);
+            if (rc <= 0) return rc;
+        }
         BDSP_WS(w1, C*, need, 1);
         const long long tot = (long long)(P * batch);
         const unsigned qgrid = (unsigned)((tot + 255) / 256);
