@@ -190,9 +190,11 @@ int ols_plan_convolve(const OlsPlan* p, const void* x, void* y, size_t N, size_t
     const size_t L = p->L, M = p->M;
     if (sizeof(T) == 4 && !is_real) {
         const int force = ols_forced_block();
-        const bool want8 = force ? force == 8192
-                                 : (L >= BDSP_OLS8192_MIN_TAPS && ols8192_blocks(N, L) * (long long)batch >= BDSP_OLS8192_MIN_BLOCKS);
-        if (p->htex2 && ols8192_applicable(N, L) && want8)
+        // (ols8192_blocks divides by the block step, which is only positive for applicable lengths)
+        const bool can8 = ols8192_applicable(N, L);
+        const bool want8 = can8 && (force ? force == 8192
+                                          : (L >= BDSP_OLS8192_MIN_TAPS && ols8192_blocks(N, L) * (long long)batch >= BDSP_OLS8192_MIN_BLOCKS));
+        if (p->htex2 && want8)
             return ols8192_convolve(x, y, N, batch, L, reinterpret_cast<const C*>(p->Hs2) + p->M2, p->htex2, st);
         if (p->htex && M == 4096 && ols4096_applicable(N, L, M))
             return ols4096_convolve(x, y, N, batch, L, reinterpret_cast<const C*>(p->Hs) + M, p->htex, st);

@@ -425,6 +425,11 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? 1024 : 512, (sizeof(T) == 8 &
     }
 }
 
+#ifndef BDSP_F64_TILE_KERNELS
+#define BDSP_F64_TILE_KERNELS 1
+#endif
+#include "fft64t.cuh"   // namespace bdsp::f64t
+
 // ------------------------------------------------------------------------------------------
 // radix-q pass for n = q * P, q odd and small:  y[k1*P + n2] = W_n^{n2 k1} sum_{n1} x[n1*P + n2] W_q^{n1 k1}
 // ------------------------------------------------------------------------------------------
@@ -607,6 +612,13 @@ int launch_block(const void* in, void* out, size_t n, size_t batch, bool real_in
 template <typename T, bool INV>
 int launch_tile(const TileParams& p, long long batch, T scale, cudaStream_t st) {
     typedef typename CpxOf<T>::type C;
+    if constexpr (sizeof(T) == 8 && BDSP_F64_TILE_KERNELS) {
+        // c64: compile-time specialised passes for m = 64 .. 512 (fft64t.cuh); anything else runs the generic tile kernel
+        const double2* twt = twiddle_table<double>();
+        if (!twt) return -1001;
+        const int rc = f64t::launch<INV>(p, batch, (double)scale, twt, st);
+        if (rc <= 0) { if (!rc) BDSP_LAUNCHED(); return rc; }
+    }
     const int m = 1 << p.log2m;
     const size_t smem = (spad_host((size_t)(m + 16) * p.ct * p.q) + (size_t)p.ct * (33 + (((p.q * m + 31) >> 5) | 1)) + (p.q > 1 ? 32 : 0)) * sizeof(C);
     int threads = block_fft_threads(m, p.ct * p.q);

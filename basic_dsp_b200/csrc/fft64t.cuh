@@ -1,0 +1,263 @@
+// c64 tile passes of the multi-pass transforms (included by fft.cu after TileParams / OutMap).
+//
+// Same contract as fft_tile_kernel (one CTA = CT lanes x m points of one pass, strides and twiddle modulus in
+// TileParams), specialised at compile time for m = 64 .. 512 and written for the instruction budget of f64 on B200:
+// the generic kernel spends ~260 instructions per point (run-time index arithmetic, four shared-memory round trips,
+// per-tile root tables: profiles/r2_c5a_tile_generic_ncu.txt) and runs at 21-35 % DRAM utilisation.  Here
+//   * a thread owns the 8 points  j + i * m/8  (i < 8) of one lane: they are the inputs of its first radix-8 butterfly,
+//     loaded straight from global memory, AND the outputs of its last one, stored straight to global memory -
+//     two shared-memory exchanges per pass instead of four, no staging;
+//   * lanes are the fastest thread index: a warp touches (32 / CT) x 8 row segments of CT * 16 bytes on both sides,
+//     for column passes (lane stride 1) and for the transposing row pass alike;
+//   * the pass twiddle W_tw^{lane k} costs one exactly reduced sincospi per thread (k = j) and one per lane (k = m/8);
+//     the other seven are a product chain;
+//   * Q = 3: columns of 3 m points - a radix-3 decimation-in-frequency step (global -> shared) in front of three
+//     m-point transforms, results K = ka + 3 kb (time_freq/mod.rs:32-63: rustfft plans any length; BASELINE C5a).
+#pragma once
+
+namespace f64t {
+
+__device__ __forceinline__ double2 conj_if(double2 w, bool c) { return c ? make_double2(w.x, -w.y) : w; }
+
+// W_den^x (forward sign, INV: conjugate) for x < 2^53: x mod den through the reciprocal estimate, then sincospi
+template <bool INV>
+__device__ __forceinline__ double2 root_of(unsigned long long x, long long den, double inv_den) {
+    const long long q = (long long)((double)x * inv_den);
+    long long r = (long long)x - q * den;
+    if (r < 0) r += den;
+    else if (r >= den) r -= den;
+    double s, c;
+    sincospi(2.0 * (double)r / (double)den, &s, &c);
+    return make_double2(c, INV ? s : -s);
+}
+
+// v[r] *= w1^r, r = 1 .. R-1 (product tree of depth <= 3)
+template <int R>
+__device__ __forceinline__ void twiddle_powers(double2* v, int stride, double2 w1) {
+    if (R >= 2) v[stride] = cmul(v[stride], w1);
+    if (R >= 4) {
+        const double2 w2 = cmul(w1, w1), w3 = cmul(w2, w1);
+        v[2 * stride] = cmul(v[2 * stride], w2);
+        v[3 * stride] = cmul(v[3 * stride], w3);
+        if (R >= 8) {
+            const double2 w4 = cmul(w2, w2);
+            v[4 * stride] = cmul(v[4 * stride], w4);
+            v[5 * stride] = cmul(v[5 * stride], cmul(w4, w1));
+            v[6 * stride] = cmul(v[6 * stride], cmul(w3, w3));
+            v[7 * stride] = cmul(v[7 * stride], cmul(w4, w3));
+        }
+    }
+}
+
+template <int LOG2M, int LCT, int Q> struct Geo {
+    static constexpr int M = 1 << LOG2M, CT = 1 << LCT, J = M / 8;
+    static constexpr int NT = J * CT * Q;
+    static constexpr int UNITS = M * CT + (LCT < 3 ? M * CT / 8 : 0);   // padded complex words per sub-sequence region
+    static constexpr size_t SMEM = ((size_t)UNITS * Q + CT + (Q > 1 ? M : 0)) * sizeof(double2);
+};
+
+template <int LOG2M, int LCT, int Q, bool INV>
+__global__ void __launch_bounds__(Geo<LOG2M, LCT, Q>::NT, Q == 1 ? 3 : 2)
+f64_tile_kernel(TileParams p, double scale, const double2* __restrict__ tw) {
+    typedef Geo<LOG2M, LCT, Q> G;
+    constexpr int M = G::M, CT = G::CT, J = G::J, NT = G::NT;
+    constexpr int R3 = LOG2M == 6 ? 1 : M / 64;   // radix of the third stage (m = 8 * 8 * R3; 1: two stages)
+    constexpr int U3 = LOG2M == 6 ? 1 : 8 / R3;   // third-stage butterflies per thread
+    constexpr int TWL = 16384;                    // master table W_16384^i
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2* sbase = reinterpret_cast<double2*>(smem_raw);
+    double2* sstep = sbase + G::UNITS * Q;        // per-lane step root W_tw^{lane * stepk}
+    double2* sw3 = sstep + CT;                    // Q = 3: W_{3m}^b, b < m
+    const int tid = threadIdx.x;
+    const int l = tid & (CT - 1);
+    const int jq = tid >> LCT;
+    const int ka = Q > 1 ? jq >> (LOG2M - 3) : 0;
+    const int j = jq & (J - 1);
+    double2* s = sbase + ka * G::UNITS;
+    // word of sequence element idx of this thread's lane: lanes fastest; one lane-group of padding per 8 elements keeps the
+    // stride-8 writes of the first stage on distinct banks when a 128-byte phase spans several j (CT < 8)
+    auto at = [&](int idx) -> double2& {
+        const int u = (idx << LCT) + l;
+        return s[LCT < 3 ? u + ((u >> (3 + LCT)) << LCT) : u];
+    };
+    const long long tile = blockIdx.x, o1 = blockIdx.y, b = blockIdx.z;
+    const long long lane = tile * CT + l;
+    const long long inb = b * p.in_batch_stride + o1 * p.in_o1_stride;
+    const double inv_tw = p.tw_n ? 1.0 / (double)p.tw_n : 0.0;
+    constexpr int stepk = Q * J;                  // distance of a thread's consecutive results in the column
+    double2 v[8];
+
+    if (Q == 1) {
+        const long long g0 = lane * p.in_lane_stride + (long long)j * p.in_point_stride + p.in_rot;
+        const long long gs = (long long)J * p.in_point_stride;
+        if (p.real_input) {
+            const double* in = reinterpret_cast<const double*>(p.in) + inb;
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                long long g = g0 + r * gs;
+                if (g >= p.in_n) g -= p.in_n;
+                v[r] = make_double2(in[g], 0.0);
+            }
+        } else {
+            const double2* in = reinterpret_cast<const double2*>(p.in) + inb;
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                long long g = g0 + r * gs;
+                if (g >= p.in_n) g -= p.in_n;
+                v[r] = in[g];
+            }
+        }
+        if (p.tw_n && jq == 0) sstep[l] = root_of<INV>((unsigned long long)lane * stepk, p.tw_n, inv_tw);
+    } else {
+        // ---- radix-3 step over stride m: z_ka[b] = (sum_a y[a m + b] W_3^{a ka}) W_{3m}^{b ka} ----
+        constexpr int NB = M * CT;                    // butterflies per CTA
+        constexpr int IT = (NB + NT - 1) / NT;
+        double2 y[IT][3];
+#pragma unroll
+        for (int it = 0; it < IT; it++) {
+            const int bi = tid + it * NT;
+            if (bi < NB) {
+                const int l3 = bi & (CT - 1), b3 = bi >> LCT;
+                const long long g0 = (tile * CT + l3) * p.in_lane_stride + (long long)b3 * p.in_point_stride + p.in_rot;
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    long long g = g0 + (long long)a * M * p.in_point_stride;
+                    if (g >= p.in_n) g -= p.in_n;
+                    if (p.real_input) y[it][a] = make_double2(reinterpret_cast<const double*>(p.in)[inb + g], 0.0);
+                    else y[it][a] = reinterpret_cast<const double2*>(p.in)[inb + g];
+                }
+            }
+        }
+        for (int i = tid; i < M; i += NT) sw3[i] = root_of<INV>((unsigned long long)i, 3 * M, 1.0 / (3.0 * M));
+        if (p.tw_n && tid < CT) sstep[tid] = root_of<INV>((unsigned long long)(tile * CT + tid) * stepk, p.tw_n, inv_tw);
+        __syncthreads();
+        const double sn = INV ? 0.86602540378443864676 : -0.86602540378443864676;   // Im W_3
+#pragma unroll
+        for (int it = 0; it < IT; it++) {
+            const int bi = tid + it * NT;
+            if (bi < NB) {
+                const int l3 = bi & (CT - 1), b3 = bi >> LCT;
+                const double2 y0 = y[it][0], t = cadd(y[it][1], y[it][2]), d = csub(y[it][1], y[it][2]);
+                const double2 m0 = make_double2(y0.x - 0.5 * t.x, y0.y - 0.5 * t.y);
+                const double2 id = make_double2(-sn * d.y, sn * d.x);          // i * Im(W_3) * (y1 - y2)
+                const double2 w1 = sw3[b3];
+                const int u = (b3 << LCT) + l3;
+                const int word = LCT < 3 ? u + ((u >> (3 + LCT)) << LCT) : u;
+                sbase[word] = cadd(y0, t);
+                sbase[G::UNITS + word] = cmul(cadd(m0, id), w1);
+                sbase[2 * G::UNITS + word] = cmul(csub(m0, id), cmul(w1, w1));
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 8; r++) v[r] = at(j + r * J);
+        __syncthreads();
+    }
+
+    // ---- stage 1: radix 8 over stride m/8, no twiddles; results to 8 j + r ----
+    RegFFT<double, 8, INV>::run(v);
+#pragma unroll
+    for (int r = 0; r < 8; r++) at(8 * j + r) = v[r];
+    __syncthreads();
+    // ---- stage 2: Ns = 8, radix 8 ----
+#pragma unroll
+    for (int r = 0; r < 8; r++) v[r] = at(j + r * J);
+    {
+        const int k = j & 7;
+        twiddle_powers<8>(v, 1, conj_if(__ldg(&tw[k * (TWL / 64)]), INV));
+    }
+    RegFFT<double, 8, INV>::run(v);
+    if constexpr (LOG2M > 6) {
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 8; r++) at((j >> 3) * 64 + (j & 7) + 8 * r) = v[r];
+        __syncthreads();
+        // ---- stage 3: Ns = 64, radix R3; butterfly u of the thread: jb = j + u J, element r at jb + 64 r = j + (u + r U3) J ----
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = at(j + i * J);
+#pragma unroll
+        for (int u = 0; u < U3; u++) {
+            const int k = j + u * J;
+            twiddle_powers<R3>(v + u, U3, conj_if(__ldg(&tw[k * (TWL / M)]), INV));
+            double2 x[R3];
+#pragma unroll
+            for (int r = 0; r < R3; r++) x[r] = v[u + r * U3];
+            RegFFT<double, R3, INV>::run(x);
+#pragma unroll
+            for (int r = 0; r < R3; r++) v[u + r * U3] = x[r];
+        }
+    }
+    // ---- pass twiddle W_tw^{lane K}, K = kfirst + i * stepk, and store ----
+    const int kfirst = Q > 1 ? ka + Q * j : j;
+    if (p.tw_n) {
+        double2 c = root_of<INV>((unsigned long long)lane * kfirst, p.tw_n, inv_tw);
+        c.x *= scale; c.y *= scale;
+        const double2 st = sstep[l];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            v[i] = cmul(v[i], c);
+            if (i < 7) c = cmul(c, st);
+        }
+    } else if (scale != 1.0) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) { v[i].x *= scale; v[i].y *= scale; }
+    }
+    const long long local0 = o1 * p.out_o1_stride + lane * p.out_lane_stride + (long long)kfirst * p.out_point_stride;
+    const long long ls = (long long)stepk * p.out_point_stride;
+    if (p.last) {
+        const long long grp = p.om.seq_group == 1 ? b : b / p.om.seq_group;
+        const long long rb = b - grp * p.om.seq_group;
+        const long long base = grp * p.om.group_stride;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            long long loc = rb + (local0 + i * ls) * p.om.oes + p.om.rot;
+            if (loc >= p.om.rot_n) loc -= p.om.rot_n;
+            if (p.magnitude) reinterpret_cast<double*>(p.out)[base + loc] = sqrt(v[i].x * v[i].x + v[i].y * v[i].y);
+            else reinterpret_cast<double2*>(p.out)[base + loc] = v[i];
+        }
+    } else {
+        double2* out = reinterpret_cast<double2*>(p.out) + b * p.out_batch_stride;
+#pragma unroll
+        for (int i = 0; i < 8; i++) out[local0 + i * ls] = v[i];
+    }
+}
+
+template <int LOG2M, int LCT, int Q, bool INV>
+int launch_one(const TileParams& p, long long batch, double scale, const double2* tw, cudaStream_t st) {
+    typedef Geo<LOG2M, LCT, Q> G;
+    auto kernel = f64_tile_kernel<LOG2M, LCT, Q, INV>;
+    static bool configured[16] = {};
+    int dev = 0;
+    BDSP_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 16 && !configured[dev]) {
+        BDSP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
+        BDSP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        configured[dev] = true;
+    } else if (dev >= 16) {
+        BDSP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
+    }
+    const dim3 grid((unsigned)(p.lanes >> LCT), (unsigned)p.o1_count, (unsigned)batch);
+    kernel<<<grid, G::NT, G::SMEM, st>>>(p, scale, tw);
+    return 0;
+}
+
+// 1: not covered by these kernels (the caller falls back to fft_tile_kernel), 0: launched, < 0: error
+template <bool INV>
+int launch(const TileParams& p, long long batch, double scale, const double2* tw, cudaStream_t st) {
+    if (batch > 65535 || p.o1_count > 65535 || p.lanes >= (1ll << 36)) return 1;
+    if (p.q == 3) {
+        if (p.log2m == 8 && p.lanes % 4 == 0) return launch_one<8, 2, 3, INV>(p, batch, scale, tw, st);
+        return 1;
+    }
+    if (p.q != 1) return 1;
+    switch (p.log2m) {
+        case 6: if (p.lanes % 32 == 0) return launch_one<6, 5, 1, INV>(p, batch, scale, tw, st); break;
+        case 7: if (p.lanes % 16 == 0) return launch_one<7, 4, 1, INV>(p, batch, scale, tw, st); break;
+        case 8: if (p.lanes % 8 == 0) return launch_one<8, 3, 1, INV>(p, batch, scale, tw, st); break;
+        case 9: if (p.lanes % 4 == 0) return launch_one<9, 2, 1, INV>(p, batch, scale, tw, st); break;
+        default: break;
+    }
+    return 1;
+}
+
+}  // namespace f64t

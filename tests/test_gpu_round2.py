@@ -55,6 +55,29 @@ def test_convolve_signal_rows_8192_point_blocks(n, rows, l):
     L.bdsp_conv_plan_destroy(plan)
 
 
+@pytest.mark.parametrize("dtype,n,rows,l", [(np.float32, 1 << 16, 3, 4095), (np.float32, 1 << 16, 2, 8191), (np.float32, 1 << 16, 2, 8192),
+                                            (np.float32, 20000, 2, 4096), (np.float64, 1 << 15, 2, 4095), (np.float64, 1 << 15, 2, 4096)])
+def test_convolve_signal_rows_tap_counts_at_the_block_limits(dtype, n, rows, l):
+    """Impulse responses one short of / exactly at the longest block transform (regression: the 8192-point block step is 0
+    for 8191 taps and must not be divided by)."""
+    L = bd.lib()
+    sfx = "c32" if dtype == np.float32 else "c64"
+    rng = np.random.default_rng(n + l + rows)
+    x = rand_c(rng, n * rows, dtype)
+    h = (rand_c(rng, l, dtype) / 10).astype(x.dtype)
+    xv, hv = DspVec(x), DspVec(h)
+    out = DspVec.zeros(2 * n * rows, is_complex=True, dtype=dtype)
+    plan = getattr(L, "bdsp_conv_plan_create_" + sfx)(dptr(hv), l)
+    assert plan
+    assert getattr(L, "bdsp_convolve_signal_rows_" + sfx)(dptr(xv), dptr(out), n, rows, plan) == 0
+    got = out.to_numpy().reshape(rows, n)
+    for r in range(rows):
+        assert o.rel_l2(got[r], o.convolve_signal(x.reshape(rows, n)[r], h)) <= tol(n, dtype), r
+    L.bdsp_conv_plan_destroy(plan)
+    got1 = DspVec(x[:n]).convolve_signal(hv).to_numpy()
+    assert o.rel_l2(got1, o.convolve_signal(x[:n], h)) <= tol(n, dtype)
+
+
 def test_real_taps_on_complex_signal_fused_blocks():
     rng = np.random.default_rng(77)
     for n, l in [(30000, 1023), (70000, 3001)]:
