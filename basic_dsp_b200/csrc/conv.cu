@@ -103,6 +103,8 @@ bool ols8192_applicable(size_t N, size_t L);
 int ols8192_prepare(const void* Hs, void* Hpos, size_t L, cudaStream_t st);
 int ols8192_convolve(const void* x, void* y, size_t N, size_t batch, size_t L, const void* Hpos, cudaTextureObject_t htex, cudaStream_t st);
 long long ols8192_blocks(size_t N, size_t L);
+bool ols64_applicable(size_t N, size_t L, size_t M);
+int ols64_convolve(const void* x, void* y, size_t N, size_t batch, size_t L, const void* Hs, cudaStream_t st);
 
 namespace {
 // Hs (2*M complex) <- FFT_M(pad(h)) / M, then the fused kernel's layout behind it (c32, M = 4096 / 8192)
@@ -201,6 +203,7 @@ int ols_plan_convolve(const OlsPlan* p, const void* x, void* y, size_t N, size_t
         if (p->htex && M == 8192 && ols8192_applicable(N, L))
             return ols8192_convolve(x, y, N, batch, L, reinterpret_cast<const C*>(p->Hs) + M, p->htex, st);
     }
+    if (sizeof(T) == 8 && !is_real && ols64_applicable(N, L, M)) return ols64_convolve(x, y, N, batch, L, p->Hs, st);   // fused 4096-point c64 blocks
     const size_t step = M - L + 1;
     const long long bpv = (long long)((N + step - 1) / step);
     const int log2M = ilog2(M);

@@ -15,6 +15,12 @@
 //     m-point transforms, results K = ka + 3 kb (time_freq/mod.rs:32-63: rustfft plans any length; BASELINE C5a).
 #pragma once
 
+#ifndef F64T_MIN_CTAS
+#define F64T_MIN_CTAS 4
+#endif
+#ifndef F64T_POINTS_LOG2
+#define F64T_POINTS_LOG2 11
+#endif
 namespace f64t {
 
 __device__ __forceinline__ double2 conj_if(double2 w, bool c) { return c ? make_double2(w.x, -w.y) : w; }
@@ -57,7 +63,7 @@ template <int LOG2M, int LCT, int Q> struct Geo {
 };
 
 template <int LOG2M, int LCT, int Q, bool INV>
-__global__ void __launch_bounds__(Geo<LOG2M, LCT, Q>::NT, Q == 1 ? 3 : 2)
+__global__ void __launch_bounds__(Geo<LOG2M, LCT, Q>::NT, Q == 1 ? F64T_MIN_CTAS : 2)
 f64_tile_kernel(TileParams p, double scale, const double2* __restrict__ tw) {
     typedef Geo<LOG2M, LCT, Q> G;
     constexpr int M = G::M, CT = G::CT, J = G::J, NT = G::NT;
@@ -250,11 +256,12 @@ int launch(const TileParams& p, long long batch, double scale, const double2* tw
         return 1;
     }
     if (p.q != 1) return 1;
+    constexpr int PL = F64T_POINTS_LOG2;          // points per CTA
     switch (p.log2m) {
-        case 6: if (p.lanes % 32 == 0) return launch_one<6, 5, 1, INV>(p, batch, scale, tw, st); break;
-        case 7: if (p.lanes % 16 == 0) return launch_one<7, 4, 1, INV>(p, batch, scale, tw, st); break;
-        case 8: if (p.lanes % 8 == 0) return launch_one<8, 3, 1, INV>(p, batch, scale, tw, st); break;
-        case 9: if (p.lanes % 4 == 0) return launch_one<9, 2, 1, INV>(p, batch, scale, tw, st); break;
+        case 6: if (p.lanes % (1 << (PL - 6)) == 0) return launch_one<6, PL - 6, 1, INV>(p, batch, scale, tw, st); break;
+        case 7: if (p.lanes % (1 << (PL - 7)) == 0) return launch_one<7, PL - 7, 1, INV>(p, batch, scale, tw, st); break;
+        case 8: if (p.lanes % (1 << (PL - 8)) == 0) return launch_one<8, PL - 8, 1, INV>(p, batch, scale, tw, st); break;
+        case 9: if (p.lanes % (1 << (PL - 9)) == 0) return launch_one<9, PL - 9, 1, INV>(p, batch, scale, tw, st); break;
         default: break;
     }
     return 1;
