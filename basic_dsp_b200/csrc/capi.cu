@@ -122,7 +122,7 @@ template <typename T> bool meta_agrees(const Vec<T>* a, const Vec<T>* b) {
 }
 
 // ---- transforms ------------------------------------------------------------------------------------
-template <typename T> Res<T> op_fft(Vec<T>* v, bool inverse, bool shifted, bool magnitude) {
+template <typename T> Res<T> op_fft(Vec<T>* v, bool inverse, bool shifted, bool magnitude, const InMul* in_mul = nullptr) {
     // time_to_freq.rs:136-165, freq_to_time.rs:138-168, time_freq/mod.rs:32-63
     const int want_domain = inverse ? 1 : 0;
     if (v->domain != want_domain) {
@@ -136,6 +136,7 @@ template <typename T> Res<T> op_fft(Vec<T>* v, bool inverse, bool shifted, bool 
     o.inverse = inverse;
     o.real_input = !v->is_complex;
     o.magnitude = magnitude;
+    if (in_mul) o.in_mul = *in_mul;
     if (points) {
         if (shifted && !inverse) o.out_rot = points / 2;                       // fft_shift (freq.rs:85-87)
         if (shifted && inverse) {                                              // ifft: scale -> ifft_shift -> plain_ifft
@@ -659,9 +660,30 @@ template <typename T> Res<T> op_window(Vec<T>* v, int kind, bool unapply) {
 }
 
 template <typename T> Res<T> op_windowed_fft_fn(Vec<T>* v, const WinFn<T>& w) {
-    Res<T> r = op_window_fn(v, w, false);
-    if (r.result_code) return r;
-    return op_fft(v, false, true, false);
+    // time_to_freq.rs:167-175: apply_window, then fft.  The window rides on the first load of the transform
+    // (FftOpts::in_mul) instead of making its own pass over the vector: built-in windows are evaluated on the fly,
+    // callback windows come from the host-built table.
+    if (v->domain != 0) { mark_invalid(v); return op_fft(v, false, true, false); }
+    const size_t points = points_of(v);
+    if (!points) return op_fft(v, false, true, false);
+    InMul im;
+    if (!w.fn) {
+        im.kind = 3; im.arg = w.kind < 0 || w.kind > 2 ? 3 : w.kind;
+        if (im.arg == 3) im.kind = 0;   // rectangular
+        return op_fft(v, false, true, false, &im);
+    }
+    std::vector<T> tab(points);
+    for (size_t i = 0; i < points; i++) {
+        const size_t j = !w.symmetric || i < (points + 1) / 2 ? i : points - 1 - i;
+        tab[i] = w(j, points);
+    }
+    T* dev = nullptr;
+    int rc = upload_table(tab, &dev);
+    if (rc) return done(v, rc);
+    im.p = dev; im.kind = 1;
+    Res<T> r = op_fft(v, false, true, false, &im);
+    table_consumed();
+    return r;
 }
 template <typename T> Res<T> op_windowed_ifft_fn(Vec<T>* v, const WinFn<T>& w) {
     Res<T> r = op_fft(v, true, true, false);

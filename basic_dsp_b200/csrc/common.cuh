@@ -78,6 +78,35 @@ __device__ __forceinline__ double2 cmul_nofma(double2 a, double2 b) {
 __device__ __forceinline__ void sincospi_t(float x, float* s, float* c) { sincospif(x, s, c); }
 __device__ __forceinline__ void sincospi_t(double x, double* s, double* c) { sincospi(x, s, c); }
 
+// --- multiplier fused into the first load of a transform (FftOpts::in_mul) ------------------
+// kind 0: none; 1: table of n real scalars T; 2: table of n complex values; 3: built-in window `arg` (0 triangular,
+// 1 Hamming, 2 Blackman-Harris, else rectangular) of length n evaluated on the fly (window_functions.rs:25-129,
+// symmetric evaluation of vector_types/mod.rs:528-598).  The index is the element's position in its sequence.
+struct InMul {
+    const void* p = nullptr;
+    int kind = 0;
+    int arg = 0;
+};
+template <typename T> __device__ __forceinline__ T window_value_dev(int kind, long long n, long long length) {
+    const T one = (T)1, two = (T)2, pi = (T)3.14159265358979323846;
+    const T nn = (T)n, ln = (T)length;
+    if (kind == 0) return one - fabs((nn - (ln - one) / two) / (ln / two));
+    if (kind == 1) { const T alpha = (T)0.54; return alpha - (one - alpha) * cos(two * pi * nn / (ln - one)); }
+    if (kind == 2)
+        return (T)0.35875 - (T)0.48829 * cos(two * pi * nn / (ln - one)) + (T)0.14128 * cos((T)4 * pi * nn / (ln - one)) -
+               (T)0.01168 * cos((T)6 * pi * nn / (ln - one));
+    return one;
+}
+// v * multiplier[g], g = position inside a sequence of n elements
+template <typename T>
+__device__ __forceinline__ typename CpxOf<T>::type in_mul_apply(typename CpxOf<T>::type v, const void* p, int kind, int arg, long long g, long long n) {
+    typedef typename CpxOf<T>::type C;
+    if (kind == 1) { const T w = reinterpret_cast<const T*>(p)[g]; v.x *= w; v.y *= w; }
+    else if (kind == 2) v = cmul(v, reinterpret_cast<const C*>(p)[g]);
+    else if (kind == 3) { const T w = window_value_dev<T>(arg, g < (n + 1) / 2 ? g : n - 1 - g, n); v.x *= w; v.y *= w; }
+    return v;
+}
+
 // exp(sign * 2*pi*i * num/den), argument reduced exactly in integers first
 template <typename T>
 __device__ __forceinline__ typename CpxOf<T>::type unit_root(unsigned long long num, unsigned long long den, int sign) {

@@ -404,10 +404,18 @@ int fft_convolve_full(const void* x, void* y, const void* h, size_t N, size_t ba
     rc = fft_exec<T>(x, X, N, batch, fx, nullptr, 0, st);
     if (rc) return rc;
     const long long tot = (long long)(N * batch);
-    spectrum_mul_kernel<T><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(X, Hf, (long long)N, (long long)batch, (T)(1.0 / (double)N));
-    BDSP_LAUNCHED();
+    // spectrum multiply (convolution.rs:427-429,444-446) and the 1/N of the inverse: fused into the first load of the
+    // inverse transform (FftOpts::in_mul) wherever that transform carries a multiplier - every length except c32 powers of
+    // two up to 16384, whose packed single-pass kernels keep the separate pass
     FftOpts inv;
     inv.inverse = 1;
+    if (sizeof(T) == 4 && is_pow2(N) && N >= 64 && N <= 16384) {
+        spectrum_mul_kernel<T><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(X, Hf, (long long)N, (long long)batch, (T)(1.0 / (double)N));
+        BDSP_LAUNCHED();
+    } else {
+        inv.in_mul.p = Hf; inv.in_mul.kind = 2;
+        inv.scale = 1.0 / (double)N;
+    }
     if (!is_real) return fft_exec<T>(X, y, N, batch, inv, nullptr, 0, st);
     rc = fft_exec<T>(X, X, N, batch, inv, nullptr, 0, st);
     if (rc) return rc;

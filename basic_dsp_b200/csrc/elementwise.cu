@@ -256,16 +256,6 @@ __global__ void mul_freq_resp_kernel(T* __restrict__ data, long long points, int
 
 // apply_window / unapply_window for the built-in windows (window_functions.rs:25-129; time.rs:33-66; symmetric windows are
 // evaluated for the first half and mirrored, vector_types/mod.rs:528-598), evaluated on the device in precision T
-template <typename T> __device__ __forceinline__ T window_value_dev(int kind, long long n, long long length) {
-    const T one = (T)1, two = (T)2, pi = (T)3.14159265358979323846;
-    const T nn = (T)n, ln = (T)length;
-    if (kind == 0) return one - fabs((nn - (ln - one) / two) / (ln / two));
-    if (kind == 1) { const T alpha = (T)0.54; return alpha - (one - alpha) * cos(two * pi * nn / (ln - one)); }
-    if (kind == 2)
-        return (T)0.35875 - (T)0.48829 * cos(two * pi * nn / (ln - one)) + (T)0.14128 * cos((T)4 * pi * nn / (ln - one)) -
-               (T)0.01168 * cos((T)6 * pi * nn / (ln - one));
-    return one;
-}
 template <typename T>
 __global__ void window_kernel(T* __restrict__ data, long long points, int is_complex, int kind, int unapply) {
     typedef Arith<T> A;

@@ -27,9 +27,9 @@ namespace bdsp {
 int fftp_rows1k_try(const void* tmp, void* out, size_t n, size_t rows, bool inverse, size_t out_rot, double scale, bool magnitude,
                     cudaStream_t st);
 int fftp_three_pass_try(const void* in, void* out, void* tmp, size_t n, size_t rows, bool inverse, size_t in_rot, size_t out_rot,
-                        double scale, bool magnitude, cudaStream_t st, bool real_in);
+                        double scale, bool magnitude, cudaStream_t st, bool real_in, const InMul& im);
 int fftp_two_pass_try(const void* in, void* out, void* tmp, size_t n, size_t rows, bool inverse, size_t in_rot, size_t out_rot,
-                      double scale, bool magnitude, cudaStream_t st, bool real_in);
+                      double scale, bool magnitude, cudaStream_t st, bool real_in, const InMul& im);
 int fftp_try(const void* in, void* out, size_t n, size_t rows, bool inverse, size_t in_rot, size_t out_rot, double scale,
              bool magnitude, cudaStream_t st);
 int fftp_try_real(const void* in, void* out, size_t n, size_t rows, size_t out_rot, double scale, bool magnitude, cudaStream_t st);
@@ -184,7 +184,7 @@ __device__ __forceinline__ int spad_host_dev(int n) { return n + (n >> 4) + 1; }
 template <typename T, bool INV, bool REAL_IN, bool MAG>
 __global__ void __launch_bounds__(sizeof(T) == 4 ? 1024 : 1024, 1) fft_block_kernel(const void* __restrict__ in_, void* __restrict__ out_, int log2n, int nfft,
                                  long long batch, long long in_rot, T scale, OutMap om,
-                                 const typename CpxOf<T>::type* __restrict__ tw) {
+                                 const typename CpxOf<T>::type* __restrict__ tw, InMul im) {
     typedef typename CpxOf<T>::type C;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C* s = reinterpret_cast<C*>(smem_raw);
@@ -206,6 +206,7 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? 1024 : 1024, 1) fft_block_ker
                         const long long src = (p + in_rot) & (n - 1);
                         if (REAL_IN) v[u].x = reinterpret_cast<const T*>(in_)[seq * n + src];
                         else v[u] = reinterpret_cast<const C*>(in_)[seq * n + src];
+                        if (im.kind) v[u] = in_mul_apply<T>(v[u], im.p, im.kind, im.arg, src, n);
                     }
                 }
             }
@@ -260,6 +261,7 @@ struct TileParams {
     int last;                  // last pass: out index goes through OutMap (batch = inner sequence)
     int magnitude;
     OutMap om;
+    InMul im;                  // first pass only: multiplier fused into the load (index = element position in the sequence)
     int q = 1;                 // > 1 (first pass only): columns of q * m points; a radix-q DIF step over stride m runs in shared
                                // memory in front of the m-point transforms, result index K = ka + q * kb
 };
@@ -303,6 +305,7 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? 1024 : 512, (sizeof(T) == 8 &
                     if (g >= p.in_n) g -= p.in_n;
                     if (p.real_input) { v[u].x = reinterpret_cast<const T*>(p.in)[in_b0 + g]; v[u].y = 0; }
                     else v[u] = reinterpret_cast<const C*>(p.in)[in_b0 + g];
+                    if (p.im.kind) v[u] = in_mul_apply<T>(v[u], p.im.p, p.im.kind, p.im.arg, g, p.in_n);
                 }
             }
 #pragma unroll
@@ -437,7 +440,7 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? 1024 : 512, (sizeof(T) == 8 &
 // The q-th roots of unity are evaluated once per block into shared memory.
 template <typename T, bool INV, int Q>
 __global__ void dft_q_pass_kernel(const void* __restrict__ in_, typename CpxOf<T>::type* __restrict__ out, int q_rt,
-                                  long long P, long long batch, long long in_rot, int real_input, T scale) {
+                                  long long P, long long batch, long long in_rot, int real_input, T scale, InMul im) {
     typedef typename CpxOf<T>::type C;
     constexpr int QM = Q > 0 ? Q : 31;
     const int q = Q > 0 ? Q : q_rt;
@@ -458,6 +461,7 @@ __global__ void dft_q_pass_kernel(const void* __restrict__ in_, typename CpxOf<T
             C v;
             if (real_input) { v.x = reinterpret_cast<const T*>(in_)[b * n + g]; v.y = 0; }
             else v = reinterpret_cast<const C*>(in_)[b * n + g];
+            if (im.kind) v = in_mul_apply<T>(v, im.p, im.kind, im.arg, g, n);
             xin[n1] = v;
         }
     }
@@ -516,7 +520,7 @@ __device__ __forceinline__ typename CpxOf<T>::type chirp(long long i, long long 
 
 template <typename T, bool INV>
 __global__ void bluestein_pre_kernel(const void* __restrict__ in_, typename CpxOf<T>::type* __restrict__ a,
-                                     long long n, long long M, long long batch, long long in_rot, int real_input, T scale) {
+                                     long long n, long long M, long long batch, long long in_rot, int real_input, T scale, InMul im) {
     typedef typename CpxOf<T>::type C;
     long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= M * batch) return;
@@ -526,6 +530,7 @@ __global__ void bluestein_pre_kernel(const void* __restrict__ in_, typename CpxO
         long long g = i + in_rot; if (g >= n) g -= n;
         if (real_input) v.x = reinterpret_cast<const T*>(in_)[b * n + g];
         else v = reinterpret_cast<const C*>(in_)[b * n + g];
+        if (im.kind) v = in_mul_apply<T>(v, im.p, im.kind, im.arg, g, n);
         v.x *= scale; v.y *= scale;
         v = cmul(v, chirp<T>(i, n, INV ? 1 : -1));
     }
@@ -580,7 +585,7 @@ template <typename K> int set_smem(K kernel, size_t bytes) {
 
 template <typename T, bool INV>
 int launch_block(const void* in, void* out, size_t n, size_t batch, bool real_in, bool mag, long long in_rot,
-                 T scale, const OutMap& om, cudaStream_t st) {
+                 T scale, const OutMap& om, cudaStream_t st, const InMul& im = InMul()) {
     typedef typename CpxOf<T>::type C;
     const int log2n = ilog2(n);
     // points per CTA for short sequences (BDSP_BLOCK_POINTS): smaller CTAs overlap their load / compute / store phases better
@@ -598,7 +603,7 @@ int launch_block(const void* in, void* out, size_t n, size_t batch, bool real_in
         int rc = set_smem(fft_block_kernel<T, INV, RI, MG>, smem);                                  \
         if (rc) return rc;                                                                          \
         fft_block_kernel<T, INV, RI, MG><<<(unsigned)grid, threads, smem, st>>>(                    \
-            in, out, log2n, nfft, (long long)batch, in_rot, scale, om, tw);                         \
+            in, out, log2n, nfft, (long long)batch, in_rot, scale, om, tw, im);                     \
     } while (0)
     if (real_in && mag) BDSP_LAUNCH_BLOCK(true, true);
     else if (real_in) BDSP_LAUNCH_BLOCK(true, false);
@@ -646,8 +651,8 @@ template <typename T> long long tile_lanes() { return sizeof(T) == 8 ? BDSP_TILE
 // power-of-two transform of `batch` sequences; handles any supported size
 template <typename T, bool INV>
 int fft_pow2(const void* in, void* out, size_t n, size_t batch, bool real_in, bool mag, long long in_rot, T scale,
-             const OutMap& om, void* work, cudaStream_t st) {
-    if (n <= fft_block_max_n<T>()) return launch_block<T, INV>(in, out, n, batch, real_in, mag, in_rot, scale, om, st);
+             const OutMap& om, void* work, cudaStream_t st, const InMul& im = InMul()) {
+    if (n <= fft_block_max_n<T>()) return launch_block<T, INV>(in, out, n, batch, real_in, mag, in_rot, scale, om, st, im);
     const int L = ilog2(n);
     const int mx = tile_log2m_max<T>();
     if (sizeof(T) == 4 && L - 10 <= mx && om.seq_group == 1 && om.oes == 1 && om.group_stride == (long long)n && om.rot_n == (long long)n &&
@@ -665,6 +670,7 @@ int fft_pow2(const void* in, void* out, size_t n, size_t batch, bool real_in, bo
         p.out_lane_stride = 1; p.out_point_stride = 1024; p.out_o1_stride = 0; p.out_batch_stride = (long long)n;
         p.tw_n = (long long)n; p.in_rot = in_rot; p.in_n = (long long)n; p.real_input = real_in; p.last = 0; p.magnitude = 0;
         p.om = om;
+        p.im = im;
         (void)n1;
         if (work != out && work != in) {
             int rc = launch_tile<T, INV>(p, (long long)batch, scale, st);
@@ -692,8 +698,10 @@ int fft_pow2(const void* in, void* out, size_t n, size_t batch, bool real_in, bo
     p.out_lane_stride = 1; p.out_point_stride = (long long)n / n1; p.out_o1_stride = 0; p.out_batch_stride = (long long)n;
     p.tw_n = (long long)n; p.in_rot = in_rot; p.in_n = (long long)n; p.real_input = real_in; p.last = 0; p.magnitude = 0;
     p.om = om;
+    p.im = im;
     int rc = launch_tile<T, INV>(p, (long long)batch, scale, st);
     if (rc) return rc;
+    p.im = InMul();
     if (npass == 3) {
         // pass B: inside every row k1: columns of length n2, stride n3, in place
         p.in = tmp; p.out = tmp; p.log2m = l[1];
@@ -722,7 +730,7 @@ int fft_pow2(const void* in, void* out, size_t n, size_t batch, bool real_in, bo
 // 96 bytes per point (c64) instead of the 160 of "radix-q pre-pass + three passes + interleave pass".
 template <typename T, bool INV>
 int fft_q_three_pass(const void* in, void* out, size_t n, size_t batch, size_t q, bool real_in, bool mag, long long in_rot, T scale,
-                     const OutMap& om, void* work, cudaStream_t st) {
+                     const OutMap& om, void* work, cudaStream_t st, const InMul& im = InMul()) {
     typedef typename CpxOf<T>::type C;
     size_t P = n / q;
     const int k = ilog2(P);
@@ -744,9 +752,10 @@ int fft_q_three_pass(const void* in, void* out, size_t n, size_t batch, size_t q
     p.out_lane_stride = 1; p.out_point_stride = (long long)n / N1; p.out_o1_stride = 0; p.out_batch_stride = (long long)n;
     p.tw_n = (long long)n; p.in_rot = in_rot; p.in_n = (long long)n; p.real_input = real_in; p.last = 0; p.magnitude = 0;
     p.om = om;
+    p.im = im;
     int rc = launch_tile<T, INV>(p, (long long)batch, scale, st);
     if (rc) return rc;
-    p.q = 1;
+    p.q = 1; p.im = InMul();
     if (!two) {
         p.in = tmp; p.out = tmp; p.log2m = b;
         p.lanes = N3; p.ct = (int)(N3 < tile_lanes<T>() ? N3 : tile_lanes<T>()); p.o1_count = N1;
@@ -858,8 +867,11 @@ int fft_any(const void* in, void* out, size_t n, size_t batch, const FftOpts& o,
     om.seq_group = 1; om.oes = 1; om.group_stride = (long long)n; om.rot = (long long)(o.out_rot % n); om.rot_n = (long long)n;
     const long long in_rot = (long long)(o.in_rot % n);
     const T scale = (T)o.scale;
+    const InMul& im = o.in_mul;
+    // a first-load multiplier (window / spectrum) is carried by the generic kernels, the c64 tile passes and the packed
+    // column passes of the two- and three-pass c32 transforms; the packed single-pass c32 kernels do not take one
     if (is_pow2(n)) {
-        if (sizeof(T) == 4 && o.real_input && !INV && in_rot == 0 && n >= 64 && n <= 16384 && n * batch >= (1u << 16)) {
+        if (sizeof(T) == 4 && !im.kind && o.real_input && !INV && in_rot == 0 && n >= 64 && n <= 16384 && n * batch >= (1u << 16)) {
             // rows of real scalars, single pass: the packed kernel loads the reals directly (4 B read + 8 B written per point)
             const int rc = fftp_try_real(in, out, n, batch, (size_t)om.rot, o.scale, o.magnitude != 0, st);
             if (rc <= 0) return rc;
@@ -875,7 +887,7 @@ int fft_any(const void* in, void* out, size_t n, size_t batch, const FftOpts& o,
             oc.real_input = 0;
             return fft_any<T, INV>(cx, out, n, batch, oc, work, work_bytes, st);
         }
-        if (sizeof(T) == 4 && !o.real_input && n >= 64 && n <= 16384) {
+        if (sizeof(T) == 4 && !im.kind && !o.real_input && n >= 64 && n <= 16384) {
             // packed-FP32x2 kernel (fftp.cu); returns 1 when the configuration is not covered
             const int rc = fftp_try(in, out, n, batch, INV, (size_t)in_rot, (size_t)om.rot, o.scale, o.magnitude != 0, st);
             if (rc <= 0) return rc;
@@ -887,15 +899,15 @@ int fft_any(const void* in, void* out, size_t n, size_t batch, const FftOpts& o,
         }
         if (sizeof(T) == 4 && n >= (1u << 15) && n <= (1u << 20)) {
             // packed two-pass path (fftp.cu): 16 B/point of traffic per pass
-            const int rc = fftp_two_pass_try(in, out, w, n, batch, INV, (size_t)in_rot, (size_t)om.rot, o.scale, o.magnitude != 0, st, o.real_input != 0);
+            const int rc = fftp_two_pass_try(in, out, w, n, batch, INV, (size_t)in_rot, (size_t)om.rot, o.scale, o.magnitude != 0, st, o.real_input != 0, im);
             if (rc <= 0) return rc;
         }
         if (sizeof(T) == 4 && n >= (1u << 21) && n <= (1u << 24)) {
             // packed three-pass path (fftp.cu)
-            const int rc = fftp_three_pass_try(in, out, w, n, batch, INV, (size_t)in_rot, (size_t)om.rot, o.scale, o.magnitude != 0, st, o.real_input != 0);
+            const int rc = fftp_three_pass_try(in, out, w, n, batch, INV, (size_t)in_rot, (size_t)om.rot, o.scale, o.magnitude != 0, st, o.real_input != 0, im);
             if (rc <= 0) return rc;
         }
-        return fft_pow2<T, INV>(in, out, n, batch, o.real_input, o.magnitude, in_rot, scale, om, w, st);
+        return fft_pow2<T, INV>(in, out, n, batch, o.real_input, o.magnitude, in_rot, scale, om, w, st, im);
     }
     // n = q * P with q odd
     size_t P = 1;
@@ -907,16 +919,16 @@ int fft_any(const void* in, void* out, size_t n, size_t batch, const FftOpts& o,
             // f64, long q * 2^k: three passes with the radix-q step inside the first one (C5a: 3 * 2^26)
             void* w = work;
             if (!w || work_bytes < need || w == in || w == out) { w = workspace(need, 0); if (!w) return -1001; }
-            const int rc = fft_q_three_pass<T, INV>(in, out, n, batch, q, o.real_input != 0, false, in_rot, scale, om, w, st);
+            const int rc = fft_q_three_pass<T, INV>(in, out, n, batch, q, o.real_input != 0, false, in_rot, scale, om, w, st, im);
             if (rc <= 0) return rc;
         }
         BDSP_WS(w1, C*, need, 1);
         const long long tot = (long long)(P * batch);
         const unsigned qgrid = (unsigned)((tot + 255) / 256);
-        if (q == 3) dft_q_pass_kernel<T, INV, 3><<<qgrid, 256, 0, st>>>(in, w1, 3, (long long)P, (long long)batch, in_rot, o.real_input, scale);
-        else if (q == 5) dft_q_pass_kernel<T, INV, 5><<<qgrid, 256, 0, st>>>(in, w1, 5, (long long)P, (long long)batch, in_rot, o.real_input, scale);
-        else if (q == 7) dft_q_pass_kernel<T, INV, 7><<<qgrid, 256, 0, st>>>(in, w1, 7, (long long)P, (long long)batch, in_rot, o.real_input, scale);
-        else dft_q_pass_kernel<T, INV, 0><<<qgrid, 256, 0, st>>>(in, w1, (int)q, (long long)P, (long long)batch, in_rot, o.real_input, scale);
+        if (q == 3) dft_q_pass_kernel<T, INV, 3><<<qgrid, 256, 0, st>>>(in, w1, 3, (long long)P, (long long)batch, in_rot, o.real_input, scale, im);
+        else if (q == 5) dft_q_pass_kernel<T, INV, 5><<<qgrid, 256, 0, st>>>(in, w1, 5, (long long)P, (long long)batch, in_rot, o.real_input, scale, im);
+        else if (q == 7) dft_q_pass_kernel<T, INV, 7><<<qgrid, 256, 0, st>>>(in, w1, 7, (long long)P, (long long)batch, in_rot, o.real_input, scale, im);
+        else dft_q_pass_kernel<T, INV, 0><<<qgrid, 256, 0, st>>>(in, w1, (int)q, (long long)P, (long long)batch, in_rot, o.real_input, scale, im);
         BDSP_LAUNCHED();
         OutMap om2;
         om2.seq_group = (long long)q; om2.oes = (long long)q; om2.group_stride = (long long)n;
@@ -958,7 +970,7 @@ int fft_any(const void* in, void* out, size_t n, size_t batch, const FftOpts& o,
     const C* bspec = reinterpret_cast<const C*>(filt->spec);
     const long long totM = (long long)(M * batch);
     bluestein_pre_kernel<T, INV><<<(unsigned)((totM + 255) / 256), 256, 0, st>>>(in, a, (long long)n, (long long)M, (long long)batch,
-                                                                                 in_rot, o.real_input, scale);
+                                                                                 in_rot, o.real_input, scale, im);
     BDSP_LAUNCHED();
     // the two length-M transforms of the chirp-z convolution take the packed passes where they exist: in place with the
     // pass workspace for M > 16384, ping-pong between two buffers for the single-pass sizes (those kernels are out of place)
@@ -972,12 +984,20 @@ int fft_any(const void* in, void* out, size_t n, size_t batch, const FftOpts& o,
     else if (pingpong) rc = fft_any<T, false>(a, b2, M, batch, fo, nullptr, 0, st);
     else rc = fft_pow2<T, false>(a, a, M, batch, false, false, 0, (T)1, plain, w0, st);
     if (rc) return rc;
-    pointwise_mul_bcast_kernel<T><<<(unsigned)((totM + 255) / 256), 256, 0, st>>>(b2, bspec, (long long)M, (long long)batch, (T)(1.0 / (double)M));
-    BDSP_LAUNCHED();
+    // the product with the chirp filter's spectrum (and the 1/M of the inverse) rides on the inverse transform's first
+    // load where that transform takes a multiplier; the packed single-pass c32 kernels keep the separate pass
     fo.inverse = 1;
+    InMul fm; fm.p = bspec; fm.kind = 2;
+    const bool fused_filter = !(sizeof(T) == 4 && M >= 64 && M <= 16384);
+    if (!fused_filter) {
+        pointwise_mul_bcast_kernel<T><<<(unsigned)((totM + 255) / 256), 256, 0, st>>>(b2, bspec, (long long)M, (long long)batch, (T)(1.0 / (double)M));
+        BDSP_LAUNCHED();
+    } else {
+        fo.in_mul = fm; fo.scale = 1.0 / (double)M;
+    }
     if (w0) rc = fft_any<T, true>(a, a, M, batch, fo, w0, w0_bytes, st);
     else if (pingpong) rc = fft_any<T, true>(b2, a, M, batch, fo, nullptr, 0, st);
-    else rc = fft_pow2<T, true>(a, a, M, batch, false, false, 0, (T)1, plain, w0, st);
+    else rc = fft_pow2<T, true>(a, a, M, batch, false, false, 0, fused_filter ? (T)(1.0 / (double)M) : (T)1, plain, w0, st, fused_filter ? fm : InMul());
     if (rc) return rc;
     const long long totn = (long long)(n * batch);
     bluestein_post_kernel<T, INV><<<(unsigned)((totn + 255) / 256), 256, 0, st>>>(a, out, (long long)n, (long long)M, (long long)batch, om, o.magnitude);

@@ -11,6 +11,9 @@ struct FftOpts {
     size_t out_rot = 0;     // write result k to (k + out_rot) mod n      (fft_shift fused on store)
     double scale = 1.0;     // multiply input by scale while loading (ifft's 1/points)
     int magnitude = 0;      // epilogue: store hypot(re, im) as n real scalars per sequence
+    InMul in_mul;           // multiply input element g of every sequence by a table entry / window value while loading
+                            // (windowed_fft: time_to_freq.rs:167-175; spectrum multiply of the frequency-domain
+                            // convolution: convolution.rs:427-429,444-446) - no separate pass over memory
 };
 
 // Transforms `batch` sequences of n complex points (sequence b at element offset b*n; real input:

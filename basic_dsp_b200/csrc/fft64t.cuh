@@ -103,6 +103,7 @@ f64_tile_kernel(TileParams p, double scale, const double2* __restrict__ tw) {
                 long long g = g0 + r * gs;
                 if (g >= p.in_n) g -= p.in_n;
                 v[r] = make_double2(in[g], 0.0);
+                if (p.im.kind) v[r] = in_mul_apply<double>(v[r], p.im.p, p.im.kind, p.im.arg, g, p.in_n);
             }
         } else {
             const double2* in = reinterpret_cast<const double2*>(p.in) + inb;
@@ -111,6 +112,7 @@ f64_tile_kernel(TileParams p, double scale, const double2* __restrict__ tw) {
                 long long g = g0 + r * gs;
                 if (g >= p.in_n) g -= p.in_n;
                 v[r] = in[g];
+                if (p.im.kind) v[r] = in_mul_apply<double>(v[r], p.im.p, p.im.kind, p.im.arg, g, p.in_n);
             }
         }
         if (p.tw_n && jq == 0) sstep[l] = root_of<INV>((unsigned long long)lane * stepk, p.tw_n, inv_tw);
@@ -131,6 +133,7 @@ f64_tile_kernel(TileParams p, double scale, const double2* __restrict__ tw) {
                     if (g >= p.in_n) g -= p.in_n;
                     if (p.real_input) y[it][a] = make_double2(reinterpret_cast<const double*>(p.in)[inb + g], 0.0);
                     else y[it][a] = reinterpret_cast<const double2*>(p.in)[inb + g];
+                    if (p.im.kind) y[it][a] = in_mul_apply<double>(y[it][a], p.im.p, p.im.kind, p.im.arg, g, p.in_n);
                 }
             }
         }

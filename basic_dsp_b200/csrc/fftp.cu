@@ -497,23 +497,44 @@ __device__ __constant__ float FP_S32[16] = {0.f, 0.19509032201612826785f, 0.3826
 // NH = 2: 32-point columns as a radix-2 step in front of the 16-point transform (two sweeps over the inputs: the
 // second one is served by L2): y_h[a] = (x[a] + (-1)^h x[a + 16]) W_32^{a h}, X[2k' + h] = DFT16(y_h)[k'].
 // RIN: x holds real scalars (see fftp_kernel)
-template <bool RIN> __device__ __forceinline__ float4 col_ldpair(const float2* x, const float2* gp) {
+// two adjacent points {re0, im0, re1, im1} at complex element pointer gp; im: multiplier fused into the load, indexed by the
+// points' positions gp - xseq (even) inside their sequence of n points (FftOpts::in_mul: window / spectrum)
+template <bool RIN> __device__ __forceinline__ float4 col_ldpair(const float2* x, const float2* gp, const InMul& im, const float2* xseq, unsigned n) {
+    float4 v;
     if constexpr (RIN) {
         const float2 r = __ldg(reinterpret_cast<const float2*>(reinterpret_cast<const float*>(x) + (gp - x)));
-        return make_float4(r.x, 0.f, r.y, 0.f);
+        v = make_float4(r.x, 0.f, r.y, 0.f);
     } else {
-        return __ldg(reinterpret_cast<const float4*>(gp));
+        v = __ldg(reinterpret_cast<const float4*>(gp));
     }
+    if (im.kind) {
+        const long long g = (long long)(gp - xseq);
+        if (im.kind == 2) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float2*>(im.p) + g));
+            v = make_float4(v.x * w.x - v.y * w.y, v.x * w.y + v.y * w.x, v.z * w.z - v.w * w.w, v.z * w.w + v.w * w.z);
+        } else {
+            float2 w;
+            if (im.kind == 1) w = __ldg(reinterpret_cast<const float2*>(reinterpret_cast<const float*>(im.p) + g));
+            else {
+                const long long h = ((long long)n + 1) / 2;
+                w.x = window_value_dev<float>(im.arg, g < h ? g : (long long)n - 1 - g, (long long)n);
+                w.y = window_value_dev<float>(im.arg, g + 1 < h ? g + 1 : (long long)n - 2 - g, (long long)n);
+            }
+            v = make_float4(v.x * w.x, v.y * w.x, v.z * w.y, v.w * w.y);
+        }
+    }
+    return v;
 }
 
 template <bool INV, bool SHIFT_IN, int NH, bool RIN = false>
-__global__ void __launch_bounds__(128) fftp_col16_kernel(const float2* __restrict__ x, float2* __restrict__ tmp, int log2n2) {
+__global__ void __launch_bounds__(128) fftp_col16_kernel(const float2* __restrict__ x, float2* __restrict__ tmp, int log2n2, InMul im) {
     // n = 16 * NH * N2 points per sequence, N2 = 2^log2n2 = row length of the second pass
     const unsigned N2 = 1u << log2n2, N = 16u * NH * N2;
     const unsigned pi = blockIdx.x * 128u + threadIdx.x;   // column pair over all sequences
     const size_t seq = pi >> (log2n2 - 1);
     const unsigned c = 2u * (pi & (N2 / 2 - 1));
-    const float2* xs = x + seq * N + c;
+    const float2* xq = x + seq * N;
+    const float2* xs = xq + c;
     float2* o = tmp + seq * N + c;
     const float ton = 2.0f / (float)N;
 #pragma unroll 1
@@ -523,13 +544,13 @@ __global__ void __launch_bounds__(128) fftp_col16_kernel(const float2* __restric
         for (int a = 0; a < 16; a++) {
             if constexpr (NH == 1) {
                 const int src = SHIFT_IN ? (a ^ 8) : a;
-                const float4 ab = col_ldpair<RIN>(x, xs + (size_t)N2 * src);
+                const float4 ab = col_ldpair<RIN>(x, xs + (size_t)N2 * src, im, xq, N);
                 v[a].re = make_float2(ab.x, ab.z);
                 v[a].im = make_float2(ab.y, ab.w);
             } else {
                 // SHIFT_IN rotates the input by n/2 = 16 rows: the two halves swap
-                const float4 lo = col_ldpair<RIN>(x, xs + (size_t)N2 * (a + (SHIFT_IN ? 16 : 0)));
-                const float4 hi = col_ldpair<RIN>(x, xs + (size_t)N2 * (a + (SHIFT_IN ? 0 : 16)));
+                const float4 lo = col_ldpair<RIN>(x, xs + (size_t)N2 * (a + (SHIFT_IN ? 16 : 0)), im, xq, N);
+                const float4 hi = col_ldpair<RIN>(x, xs + (size_t)N2 * (a + (SHIFT_IN ? 0 : 16)), im, xq, N);
                 cp l, g;
                 l.re = make_float2(lo.x, lo.z); l.im = make_float2(lo.y, lo.w);
                 g.re = make_float2(hi.x, hi.z); g.im = make_float2(hi.y, hi.w);
@@ -558,7 +579,7 @@ __global__ void __launch_bounds__(128) fftp_col16_kernel(const float2* __restric
 // y_h[m] = (x[m] + (-1)^h x[m + 256]) W_512^{m h}, X[2k' + h] = DFT256(y_h)[k'].  Not usable in place.
 template <bool INV, bool SHIFT_IN, int NH, bool RIN = false>
 __global__ void __launch_bounds__(128, 5) fftp_col256_kernel(const float2* __restrict__ x, float2* __restrict__ tmp,
-                                                             const float4* __restrict__ tws, int log2n2) {
+                                                             const float4* __restrict__ tws, int log2n2, InMul im) {
     // n = 256 * NH * N2 points per sequence, N2 = 2^log2n2 = row length of the second pass
     const unsigned N2 = 1u << log2n2;
     const unsigned N = 256u * NH * N2;
@@ -574,20 +595,21 @@ __global__ void __launch_bounds__(128, 5) fftp_col256_kernel(const float2* __res
     for (int h = 0; h < NH; h++) {
     cp v[16];
     {   // stage 1: radix 16 over m = 16a + b, b = hi
-        const float2* xs = x + seq * N + c0 + j + (size_t)hi * N2;
+        const float2* xq = x + seq * N;
+        const float2* xs = xq + c0 + j + (size_t)hi * N2;
         cp wb;
         if constexpr (NH == 2) wb = unit_root_pair((unsigned)hi, (unsigned)hi, 2.0f / 512.0f, INV);   // W_512^b (both lanes)
 #pragma unroll
         for (int a = 0; a < 16; a++) {
             if constexpr (NH == 1) {
                 const int src = SHIFT_IN ? (a ^ 8) : a;
-                const float4 ab = col_ldpair<RIN>(x, xs + (size_t)src * (16 * (size_t)N2));
+                const float4 ab = col_ldpair<RIN>(x, xs + (size_t)src * (16 * (size_t)N2), im, xq, N);
                 v[a].re = make_float2(ab.x, ab.z);
                 v[a].im = make_float2(ab.y, ab.w);
             } else {
                 const size_t r0 = (size_t)a * (16 * (size_t)N2), half = (size_t)256 * N2;
-                const float4 lo = col_ldpair<RIN>(x, xs + r0 + (SHIFT_IN ? half : 0));
-                const float4 hh = col_ldpair<RIN>(x, xs + r0 + (SHIFT_IN ? 0 : half));
+                const float4 lo = col_ldpair<RIN>(x, xs + r0 + (SHIFT_IN ? half : 0), im, xq, N);
+                const float4 hh = col_ldpair<RIN>(x, xs + r0 + (SHIFT_IN ? 0 : half), im, xq, N);
                 cp l, g;
                 l.re = make_float2(lo.x, lo.z); l.im = make_float2(lo.y, lo.w);
                 g.re = make_float2(hh.x, hh.z); g.im = make_float2(hh.y, hh.w);
@@ -809,17 +831,17 @@ int fftp_rows_pass(const void* tmp, void* out, size_t groups, bool inverse, bool
 }
 
 template <bool INV, bool SI, bool RIN = false>
-int fftp_colpass(const void* in, void* tmp, int n1, int log2n2, size_t rows, cudaStream_t st) {
+int fftp_colpass(const void* in, void* tmp, int n1, int log2n2, size_t rows, cudaStream_t st, const InMul& im = InMul()) {
     const float* tw = fftp_twiddles();
     if (!tw) return -1001;
     const float2* i2 = reinterpret_cast<const float2*>(in);
     float2* t2 = reinterpret_cast<float2*>(tmp);
     const float4* tws = reinterpret_cast<const float4*>(tw + FP_TW_SPLAT);
     const unsigned g16 = (unsigned)(rows * ((size_t)1 << (log2n2 - 8))), g256 = (unsigned)(rows * ((size_t)1 << (log2n2 - 4)));
-    if (n1 == 16) fftp_col16_kernel<INV, SI, 1, RIN><<<g16, 128, 0, st>>>(i2, t2, log2n2);
-    else if (n1 == 32) fftp_col16_kernel<INV, SI, 2, RIN><<<g16, 128, 0, st>>>(i2, t2, log2n2);
-    else if (n1 == 256) fftp_col256_kernel<INV, SI, 1, RIN><<<g256, 128, 0, st>>>(i2, t2, tws, log2n2);
-    else fftp_col256_kernel<INV, SI, 2, RIN><<<g256, 128, 0, st>>>(i2, t2, tws, log2n2);
+    if (n1 == 16) fftp_col16_kernel<INV, SI, 1, RIN><<<g16, 128, 0, st>>>(i2, t2, log2n2, im);
+    else if (n1 == 32) fftp_col16_kernel<INV, SI, 2, RIN><<<g16, 128, 0, st>>>(i2, t2, log2n2, im);
+    else if (n1 == 256) fftp_col256_kernel<INV, SI, 1, RIN><<<g256, 128, 0, st>>>(i2, t2, tws, log2n2, im);
+    else fftp_col256_kernel<INV, SI, 2, RIN><<<g256, 128, 0, st>>>(i2, t2, tws, log2n2, im);
     BDSP_CUDA_OK(cudaGetLastError());
     BDSP_LAUNCHED();
     return 0;
@@ -840,7 +862,7 @@ int fftp_rowsq_pass(const void* tmp, void* out, size_t groups, bool inverse, boo
 // two-pass packed transform for n = 2^16 and 2^20 (tmp: n*rows complex values, distinct from in; may equal out only
 // if out != in).  Returns 1 when the configuration is not covered.
 int fftp_two_pass_try(const void* in, void* out, void* tmp, size_t n, size_t rows, bool inverse, size_t in_rot, size_t out_rot,
-                      double scale, bool magnitude, cudaStream_t st, bool real_in) {
+                      double scale, bool magnitude, cudaStream_t st, bool real_in, const InMul& im) {
     if (real_in && (inverse || in_rot != 0)) return 1;
     // n = n1 * N2:  2^15 = 32 x 1024, 2^16 = 256 x 256, 2^17 = 256 x 512, 2^18 = 256 x 1024, 2^19 = 512 x 1024, 2^20 = 256 x 4096.
     // (two adjacent 2048-point rows give only 16-byte store runs: 16 x 2048 took 0.46 ms and 256 x 2048 0.48 ms per 2^26 points)
@@ -893,9 +915,9 @@ int fftp_two_pass_try(const void* in, void* out, void* tmp, size_t n, size_t row
         void* cout = reinterpret_cast<char*>(out) + r0 * n * out_elem;
         const size_t groups_c = nr * (size_t)(n1 / rpc);
         int rc;
-        if (real_in) rc = fftp_colpass<false, false, true>(cin, tmp, n1, log2n2, nr, st);
-        else if (inverse) rc = si ? fftp_colpass<true, true>(cin, tmp, n1, log2n2, nr, st) : fftp_colpass<true, false>(cin, tmp, n1, log2n2, nr, st);
-        else rc = si ? fftp_colpass<false, true>(cin, tmp, n1, log2n2, nr, st) : fftp_colpass<false, false>(cin, tmp, n1, log2n2, nr, st);
+        if (real_in) rc = fftp_colpass<false, false, true>(cin, tmp, n1, log2n2, nr, st, im);
+        else if (inverse) rc = si ? fftp_colpass<true, true>(cin, tmp, n1, log2n2, nr, st, im) : fftp_colpass<true, false>(cin, tmp, n1, log2n2, nr, st, im);
+        else rc = si ? fftp_colpass<false, true>(cin, tmp, n1, log2n2, nr, st, im) : fftp_colpass<false, false>(cin, tmp, n1, log2n2, nr, st, im);
         if (rc) return rc;
         if (tq == 8) rc = fftp_rowsq_pass<8>(tmp, cout, groups_c, inverse, so, magnitude, sc, st, n1);
         else if (tq == 4) rc = fftp_rowsq_pass<4>(tmp, cout, groups_c, inverse, so, magnitude, sc, st, n1);
@@ -914,7 +936,7 @@ int fftp_two_pass_try(const void* in, void* out, void* tmp, size_t n, size_t row
 //   points (exactly the first pass of the two-pass transform of that length, in place), pass C: rows of N3 = 256*Q points,
 //   16/Q rows with consecutive k1 per CTA, stored at k1 + nA*k2 + nA*256*k3.
 int fftp_three_pass_try(const void* in, void* out, void* tmp, size_t n, size_t rows, bool inverse, size_t in_rot, size_t out_rot,
-                        double scale, bool magnitude, cudaStream_t st, bool real_in) {
+                        double scale, bool magnitude, cudaStream_t st, bool real_in, const InMul& im) {
     if (real_in && (inverse || in_rot != 0)) return 1;
     int nA, log2n3;
     switch (n) {
@@ -934,9 +956,9 @@ int fftp_three_pass_try(const void* in, void* out, void* tmp, size_t n, size_t r
     int rc;
     int l2 = 0;
     while (((size_t)nA << l2) < n) l2++;                 // n / nA = 2^l2
-    if (real_in) rc = fftp_colpass<false, false, true>(in, tmp, nA, l2, rows, st);
-    else if (inverse) rc = si ? fftp_colpass<true, true>(in, tmp, nA, l2, rows, st) : fftp_colpass<true, false>(in, tmp, nA, l2, rows, st);
-    else rc = si ? fftp_colpass<false, true>(in, tmp, nA, l2, rows, st) : fftp_colpass<false, false>(in, tmp, nA, l2, rows, st);
+    if (real_in) rc = fftp_colpass<false, false, true>(in, tmp, nA, l2, rows, st, im);
+    else if (inverse) rc = si ? fftp_colpass<true, true>(in, tmp, nA, l2, rows, st, im) : fftp_colpass<true, false>(in, tmp, nA, l2, rows, st, im);
+    else rc = si ? fftp_colpass<false, true>(in, tmp, nA, l2, rows, st, im) : fftp_colpass<false, false>(in, tmp, nA, l2, rows, st, im);
     if (rc) return rc;
     rc = inverse ? fftp_colpass<true, false>(tmp, tmp, 256, log2n3, rows * (size_t)nA, st) : fftp_colpass<false, false>(tmp, tmp, 256, log2n3, rows * (size_t)nA, st);
     if (rc) return rc;

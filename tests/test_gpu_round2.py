@@ -295,3 +295,41 @@ def test_convolve_complex_callback_wraps_around_short_vectors():
         for m in range(-L_, L_ + 1):
             ref += x[(idx + m) % n].astype(np.complex128) * fn(np.float32(-m * 0.5))
         assert o.rel_l2(got, ref) <= tol(4096, np.float32), (n, length)
+
+
+# ---- multipliers fused into the first load of a transform (FftOpts::in_mul) --------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [16, 1000, 1001, 4096, 3 * 4096, 1 << 14, 1 << 15, 1 << 16, 3 * (1 << 15), 40000, 1 << 19, 1 << 21, 3 * (1 << 18), 5 * (1 << 17)])
+def test_windowed_fft_every_transform_path(n, dtype):
+    """windowed_fft = apply_window + fft (time_to_freq.rs:167-175) with the window carried by the transform's first load:
+    single-CTA, two- and three-pass (generic, c64 tiles, packed c32 columns), mixed radix and chirp-z lengths; complex and
+    real vectors."""
+    rng = np.random.default_rng(n)
+    x = rand_c(rng, n, dtype)
+    for kind in (1, 2):
+        X = DspVec(x).windowed_fft(kind).to_numpy()
+        ref = o.windowed_fft(x, kind, dtype)
+        assert o.rel_l2(X, ref) <= tol(n, dtype), kind
+        # identical to the two separate calls up to summation order
+        X2 = DspVec(x).apply_window(kind).fft().to_numpy()
+        assert o.rel_l2(X, X2) <= tol(n, dtype), kind
+    r = rng.uniform(-10, 10, n).astype(dtype)
+    R = DspVec(r).windowed_fft(1).to_numpy()
+    assert o.rel_l2(R, o.windowed_fft(r.astype(x.dtype), 1, dtype)) <= tol(n, dtype)
+
+
+@pytest.mark.parametrize("dtype,n,l", [(np.float32, 1 << 15, 9000), (np.float32, 1 << 21, 8200), (np.float32, 5 * (1 << 13), 8500),
+                                       (np.float64, 1 << 14, 4100), (np.float64, 1 << 16, 5000), (np.float64, 3 * (1 << 14), 4100),
+                                       (np.float64, 30001, 4100)])
+def test_convolve_signal_full_length_fused_spectrum_multiply(dtype, n, l):
+    """Full-length frequency-domain convolution (impulse responses too long for a block transform): the spectrum multiply
+    (convolution.rs:427-429) rides on the inverse transform's first load."""
+    rng = np.random.default_rng(n + l)
+    x = rand_c(rng, n, dtype)
+    h = (rand_c(rng, l, dtype) / 10).astype(x.dtype)
+    got = DspVec(x).convolve_signal(DspVec(h)).to_numpy()
+    assert o.rel_l2(got, o.convolve_signal(x, h)) <= tol(n, dtype)
+    xr = rng.uniform(-10, 10, n).astype(dtype)
+    hr = (rng.uniform(-1, 1, l) / 10).astype(dtype)
+    gr = DspVec(xr).convolve_signal(DspVec(hr)).to_numpy()
+    assert o.rel_l2(gr, o.convolve_signal(xr.astype(x.dtype), hr.astype(x.dtype)).real) <= tol(n, dtype)
