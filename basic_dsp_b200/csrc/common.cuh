@@ -80,8 +80,8 @@ __device__ __forceinline__ void sincospi_t(double x, double* s, double* c) { sin
 
 // --- multiplier fused into the first load of a transform (FftOpts::in_mul) ------------------
 // kind 0: none; 1: table of n real scalars T; 2: table of n complex values; 3: built-in window `arg` (0 triangular,
-// 1 Hamming, 2 Blackman-Harris, else rectangular) of length n evaluated on the fly (window_functions.rs:25-129,
-// symmetric evaluation of vector_types/mod.rs:528-598).  The index is the element's position in its sequence.
+// 1 Hamming, 2 Blackman-Harris, else rectangular) of length n (window_functions.rs:25-129, symmetric evaluation of
+// vector_types/mod.rs:528-598), which fft_exec writes into a table (4 B/point, one small kernel) before the transform.  The index is the element's position in its sequence.
 struct InMul {
     const void* p = nullptr;
     int kind = 0;
@@ -103,7 +103,7 @@ __device__ __forceinline__ typename CpxOf<T>::type in_mul_apply(typename CpxOf<T
     typedef typename CpxOf<T>::type C;
     if (kind == 1) { const T w = reinterpret_cast<const T*>(p)[g]; v.x *= w; v.y *= w; }
     else if (kind == 2) v = cmul(v, reinterpret_cast<const C*>(p)[g]);
-    else if (kind == 3) { const T w = window_value_dev<T>(arg, g < (n + 1) / 2 ? g : n - 1 - g, n); v.x *= w; v.y *= w; }
+    (void)arg; (void)n;   // kind 3 (built-in window) is materialised as a kind-1 table by fft_exec: no cos() in transform kernels
     return v;
 }
 

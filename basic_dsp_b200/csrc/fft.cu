@@ -859,6 +859,13 @@ int bluestein_filter(size_t n, size_t M, void* w0, cudaStream_t st, std::shared_
     return 0;
 }
 
+// table of the built-in window `kind` (InMul kind 3 -> kind 1) for the kernels that take tables only
+template <typename T>
+__global__ void window_table_kernel(T* __restrict__ tab, long long n, int kind) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) tab[i] = window_value_dev<T>(kind, i < (n + 1) / 2 ? i : n - 1 - i, n);
+}
+
 template <typename T, bool INV>
 int fft_any(const void* in, void* out, size_t n, size_t batch, const FftOpts& o, void* work, size_t work_bytes,
             cudaStream_t st) {
@@ -867,7 +874,14 @@ int fft_any(const void* in, void* out, size_t n, size_t batch, const FftOpts& o,
     om.seq_group = 1; om.oes = 1; om.group_stride = (long long)n; om.rot = (long long)(o.out_rot % n); om.rot_n = (long long)n;
     const long long in_rot = (long long)(o.in_rot % n);
     const T scale = (T)o.scale;
-    const InMul& im = o.in_mul;
+    InMul im = o.in_mul;
+    if (im.kind == 3) {
+        // transform kernels take multiplier tables: one small kernel writes the window (n scalars, once per call)
+        BDSP_WS(tab, T*, n * sizeof(T), 3);
+        window_table_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(tab, (long long)n, im.arg);
+        BDSP_LAUNCHED();
+        im.p = tab; im.kind = 1;
+    }
     // a first-load multiplier (window / spectrum) is carried by the generic kernels, the c64 tile passes and the packed
     // column passes of the two- and three-pass c32 transforms; the packed single-pass c32 kernels do not take one
     if (is_pow2(n)) {
@@ -885,6 +899,7 @@ int fft_any(const void* in, void* out, size_t n, size_t batch, const FftOpts& o,
             if (rc) return rc;
             FftOpts oc = o;
             oc.real_input = 0;
+            oc.in_mul = im;
             return fft_any<T, INV>(cx, out, n, batch, oc, work, work_bytes, st);
         }
         if (sizeof(T) == 4 && !im.kind && !o.real_input && n >= 64 && n <= 16384) {

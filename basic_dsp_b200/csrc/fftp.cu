@@ -497,9 +497,10 @@ __device__ __constant__ float FP_S32[16] = {0.f, 0.19509032201612826785f, 0.3826
 // NH = 2: 32-point columns as a radix-2 step in front of the 16-point transform (two sweeps over the inputs: the
 // second one is served by L2): y_h[a] = (x[a] + (-1)^h x[a + 16]) W_32^{a h}, X[2k' + h] = DFT16(y_h)[k'].
 // RIN: x holds real scalars (see fftp_kernel)
-// two adjacent points {re0, im0, re1, im1} at complex element pointer gp; im: multiplier fused into the load, indexed by the
-// points' positions gp - xseq (even) inside their sequence of n points (FftOpts::in_mul: window / spectrum)
-template <bool RIN> __device__ __forceinline__ float4 col_ldpair(const float2* x, const float2* gp, const InMul& im, const float2* xseq, unsigned n) {
+// two adjacent points {re0, im0, re1, im1} at complex element pointer gp.  MUL: a multiplier table is fused into the load,
+// indexed by the points' positions gp - xseq (even) inside their sequence (FftOpts::in_mul kinds 1 and 2: real window
+// table / complex spectrum); MUL = false compiles to the plain load.
+template <bool RIN, bool MUL> __device__ __forceinline__ float4 col_ldpair(const float2* x, const float2* gp, const InMul& im, const float2* xseq) {
     float4 v;
     if constexpr (RIN) {
         const float2 r = __ldg(reinterpret_cast<const float2*>(reinterpret_cast<const float*>(x) + (gp - x)));
@@ -507,26 +508,20 @@ template <bool RIN> __device__ __forceinline__ float4 col_ldpair(const float2* x
     } else {
         v = __ldg(reinterpret_cast<const float4*>(gp));
     }
-    if (im.kind) {
+    if constexpr (MUL) {
         const long long g = (long long)(gp - xseq);
         if (im.kind == 2) {
             const float4 w = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float2*>(im.p) + g));
             v = make_float4(v.x * w.x - v.y * w.y, v.x * w.y + v.y * w.x, v.z * w.z - v.w * w.w, v.z * w.w + v.w * w.z);
         } else {
-            float2 w;
-            if (im.kind == 1) w = __ldg(reinterpret_cast<const float2*>(reinterpret_cast<const float*>(im.p) + g));
-            else {
-                const long long h = ((long long)n + 1) / 2;
-                w.x = window_value_dev<float>(im.arg, g < h ? g : (long long)n - 1 - g, (long long)n);
-                w.y = window_value_dev<float>(im.arg, g + 1 < h ? g + 1 : (long long)n - 2 - g, (long long)n);
-            }
+            const float2 w = __ldg(reinterpret_cast<const float2*>(reinterpret_cast<const float*>(im.p) + g));
             v = make_float4(v.x * w.x, v.y * w.x, v.z * w.y, v.w * w.y);
         }
     }
     return v;
 }
 
-template <bool INV, bool SHIFT_IN, int NH, bool RIN = false>
+template <bool INV, bool SHIFT_IN, int NH, bool RIN = false, bool MUL = false>
 __global__ void __launch_bounds__(128) fftp_col16_kernel(const float2* __restrict__ x, float2* __restrict__ tmp, int log2n2, InMul im) {
     // n = 16 * NH * N2 points per sequence, N2 = 2^log2n2 = row length of the second pass
     const unsigned N2 = 1u << log2n2, N = 16u * NH * N2;
@@ -544,13 +539,13 @@ __global__ void __launch_bounds__(128) fftp_col16_kernel(const float2* __restric
         for (int a = 0; a < 16; a++) {
             if constexpr (NH == 1) {
                 const int src = SHIFT_IN ? (a ^ 8) : a;
-                const float4 ab = col_ldpair<RIN>(x, xs + (size_t)N2 * src, im, xq, N);
+                const float4 ab = col_ldpair<RIN, MUL>(x, xs + (size_t)N2 * src, im, xq);
                 v[a].re = make_float2(ab.x, ab.z);
                 v[a].im = make_float2(ab.y, ab.w);
             } else {
                 // SHIFT_IN rotates the input by n/2 = 16 rows: the two halves swap
-                const float4 lo = col_ldpair<RIN>(x, xs + (size_t)N2 * (a + (SHIFT_IN ? 16 : 0)), im, xq, N);
-                const float4 hi = col_ldpair<RIN>(x, xs + (size_t)N2 * (a + (SHIFT_IN ? 0 : 16)), im, xq, N);
+                const float4 lo = col_ldpair<RIN, MUL>(x, xs + (size_t)N2 * (a + (SHIFT_IN ? 16 : 0)), im, xq);
+                const float4 hi = col_ldpair<RIN, MUL>(x, xs + (size_t)N2 * (a + (SHIFT_IN ? 0 : 16)), im, xq);
                 cp l, g;
                 l.re = make_float2(lo.x, lo.z); l.im = make_float2(lo.y, lo.w);
                 g.re = make_float2(hi.x, hi.z); g.im = make_float2(hi.y, hi.w);
@@ -577,7 +572,7 @@ __global__ void __launch_bounds__(128) fftp_col16_kernel(const float2* __restric
 
 // NH = 2: 512-point columns, radix-2 step in front of the 256-point transform (two sweeps, see fftp_col16_kernel):
 // y_h[m] = (x[m] + (-1)^h x[m + 256]) W_512^{m h}, X[2k' + h] = DFT256(y_h)[k'].  Not usable in place.
-template <bool INV, bool SHIFT_IN, int NH, bool RIN = false>
+template <bool INV, bool SHIFT_IN, int NH, bool RIN = false, bool MUL = false>
 __global__ void __launch_bounds__(128, 5) fftp_col256_kernel(const float2* __restrict__ x, float2* __restrict__ tmp,
                                                              const float4* __restrict__ tws, int log2n2, InMul im) {
     // n = 256 * NH * N2 points per sequence, N2 = 2^log2n2 = row length of the second pass
@@ -603,13 +598,13 @@ __global__ void __launch_bounds__(128, 5) fftp_col256_kernel(const float2* __res
         for (int a = 0; a < 16; a++) {
             if constexpr (NH == 1) {
                 const int src = SHIFT_IN ? (a ^ 8) : a;
-                const float4 ab = col_ldpair<RIN>(x, xs + (size_t)src * (16 * (size_t)N2), im, xq, N);
+                const float4 ab = col_ldpair<RIN, MUL>(x, xs + (size_t)src * (16 * (size_t)N2), im, xq);
                 v[a].re = make_float2(ab.x, ab.z);
                 v[a].im = make_float2(ab.y, ab.w);
             } else {
                 const size_t r0 = (size_t)a * (16 * (size_t)N2), half = (size_t)256 * N2;
-                const float4 lo = col_ldpair<RIN>(x, xs + r0 + (SHIFT_IN ? half : 0), im, xq, N);
-                const float4 hh = col_ldpair<RIN>(x, xs + r0 + (SHIFT_IN ? 0 : half), im, xq, N);
+                const float4 lo = col_ldpair<RIN, MUL>(x, xs + r0 + (SHIFT_IN ? half : 0), im, xq);
+                const float4 hh = col_ldpair<RIN, MUL>(x, xs + r0 + (SHIFT_IN ? 0 : half), im, xq);
                 cp l, g;
                 l.re = make_float2(lo.x, lo.z); l.im = make_float2(lo.y, lo.w);
                 g.re = make_float2(hh.x, hh.z); g.im = make_float2(hh.y, hh.w);
@@ -838,10 +833,20 @@ int fftp_colpass(const void* in, void* tmp, int n1, int log2n2, size_t rows, cud
     float2* t2 = reinterpret_cast<float2*>(tmp);
     const float4* tws = reinterpret_cast<const float4*>(tw + FP_TW_SPLAT);
     const unsigned g16 = (unsigned)(rows * ((size_t)1 << (log2n2 - 8))), g256 = (unsigned)(rows * ((size_t)1 << (log2n2 - 4)));
-    if (n1 == 16) fftp_col16_kernel<INV, SI, 1, RIN><<<g16, 128, 0, st>>>(i2, t2, log2n2, im);
-    else if (n1 == 32) fftp_col16_kernel<INV, SI, 2, RIN><<<g16, 128, 0, st>>>(i2, t2, log2n2, im);
-    else if (n1 == 256) fftp_col256_kernel<INV, SI, 1, RIN><<<g256, 128, 0, st>>>(i2, t2, tws, log2n2, im);
-    else fftp_col256_kernel<INV, SI, 2, RIN><<<g256, 128, 0, st>>>(i2, t2, tws, log2n2, im);
+    if (im.kind == 1 || im.kind == 2) {
+        if (n1 == 16) fftp_col16_kernel<INV, SI, 1, RIN, true><<<g16, 128, 0, st>>>(i2, t2, log2n2, im);
+        else if (n1 == 32) fftp_col16_kernel<INV, SI, 2, RIN, true><<<g16, 128, 0, st>>>(i2, t2, log2n2, im);
+        else if (n1 == 256) fftp_col256_kernel<INV, SI, 1, RIN, true><<<g256, 128, 0, st>>>(i2, t2, tws, log2n2, im);
+        else fftp_col256_kernel<INV, SI, 2, RIN, true><<<g256, 128, 0, st>>>(i2, t2, tws, log2n2, im);
+    } else if (im.kind) {
+        set_last_error("fftp_colpass: multiplier kind %d must be materialised as a table", im.kind);
+        return -2;
+    } else {
+        if (n1 == 16) fftp_col16_kernel<INV, SI, 1, RIN><<<g16, 128, 0, st>>>(i2, t2, log2n2, im);
+        else if (n1 == 32) fftp_col16_kernel<INV, SI, 2, RIN><<<g16, 128, 0, st>>>(i2, t2, log2n2, im);
+        else if (n1 == 256) fftp_col256_kernel<INV, SI, 1, RIN><<<g256, 128, 0, st>>>(i2, t2, tws, log2n2, im);
+        else fftp_col256_kernel<INV, SI, 2, RIN><<<g256, 128, 0, st>>>(i2, t2, tws, log2n2, im);
+    }
     BDSP_CUDA_OK(cudaGetLastError());
     BDSP_LAUNCHED();
     return 0;
