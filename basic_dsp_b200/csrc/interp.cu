@@ -164,12 +164,18 @@ interp_poly_tiled_kernel(const void* __restrict__ x_, void* __restrict__ y_, con
 #ifndef IPF_THREADS
 #define IPF_THREADS 64
 #endif
-#define IPF_RP 8
+// positions per thread (IPF_LRP = log2): 8 -> 64 registers, 1024 threads per SM; 16 -> half the shared loads and loop overhead
+// per FFMA2, but 127 registers and 512 threads per SM.  Measured on B200 (C4a): 8 positions 0.131 ms; 16 positions 0.162 ms
+// (64-thread CTAs), 0.160 (32), 0.185 (128): the FMA pipe needs the resident warps more than it needs fewer instructions
+#ifndef IPF_LRP
+#define IPF_LRP 3
+#endif
+#define IPF_RP (1 << IPF_LRP)
 #define IPF_POS (IPF_THREADS * IPF_RP)
-#define IPF_ROW 34   // staging row stride in floats (17 x 8 B: conflict-free 64-bit stores)
-__device__ __forceinline__ int ipf_skew(int i) { return i + (i >> 3); }
+#define IPF_ROW (4 * IPF_RP + 2)   // staging row stride in floats (odd number of 8-byte words: conflict-free 64-bit stores)
+__device__ __forceinline__ int ipf_skew(int i) { return i + (i >> IPF_LRP); }
 
-__global__ void __launch_bounds__(IPF_THREADS, 1024 / IPF_THREADS)
+__global__ void __launch_bounds__(IPF_THREADS, (IPF_LRP == 3 ? 1024 : 512) / IPF_THREADS)
 interp_poly_f32_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ tab, long long N,
                        long long new_points, int F, int L, long long scalar_len) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -274,7 +280,7 @@ interp_poly_f32_kernel(const float* __restrict__ x, float* __restrict__ y, const
 #pragma unroll
         for (int it = 0; it < IPF_RP; it++) {
             const int o = 4 * (threadIdx.x + IPF_THREADS * it);
-            const float* sp = so + (o >> 5) * IPF_ROW + (o & 31);
+            const float* sp = so + (o >> (IPF_LRP + 2)) * IPF_ROW + (o & (4 * IPF_RP - 1));
             const float2 a = *reinterpret_cast<const float2*>(sp), b = *reinterpret_cast<const float2*>(sp + 2);
             *reinterpret_cast<float4*>(yo + o) = make_float4(a.x, a.y, b.x, b.y);
         }
@@ -311,7 +317,7 @@ int interp_poly(const void* x, void* y, const T* tab_dev, size_t N, size_t new_p
         if (is_complex) { if (F <= 4) BDSP_IP2(true, 4, 2); else BDSP_IP2(true, 8, 1); }
         else if (F <= 4 && sizeof(T) == 4) {
             const size_t wlen = (size_t)IPF_POS + J + 2 * IPF_RP;
-            size_t smem = (size_t)J * 16 + (wlen + wlen / 8 + 2) * 8;
+            size_t smem = (size_t)J * 16 + (wlen + wlen / IPF_RP + 2) * 8;
             const size_t stage = (size_t)IPF_THREADS * IPF_ROW * 4;
             if (smem < stage) smem = stage;
             const long long grid = (rows + IPF_POS - 1) / IPF_POS;
