@@ -62,5 +62,28 @@ parts = [DspVec(np.zeros(2, dtype=np.float32)) for _ in range(3)]
 DspVec(r[:20001 - 20001 % 3]).split_into(parts)
 DspVec(np.zeros(2, dtype=np.float32)).merge(parts).to_numpy()
 DspVec(r).add_smaller(DspVec(r[:3])).to_numpy() if 20001 % 3 == 0 else None
+# ---- round 2 kernels ----
+# c64 tile passes (two / three passes, radix-3 first pass, real input, shifted, magnitude), generic fallbacks
+for n in (1 << 14, 1 << 15, 1 << 17, 1 << 19, 1 << 20, 3 * (1 << 14), 3 * (1 << 17), 5 * (1 << 14)):
+    DspVec(rc(n, np.complex128)).fft().ifft().to_numpy()
+DspVec(rng.uniform(-1, 1, 1 << 15)).fft().to_numpy()
+DspVec(rc(1 << 16, np.complex128)).fft_magnitude().to_numpy()
+# fused c64 overlap-save blocks, 8192-point c32 blocks, tap counts at the block limits
+for n, l in ((4096, 2), (20001, 1024), (70000, 513)):
+    DspVec(rc(n, np.complex128)).convolve_signal(DspVec(rc(l, np.complex128))).to_numpy()
+for n, l in ((8192, 4094), (100000, 3333), (1 << 16, 8191), (1 << 16, 4095)):
+    DspVec(rc(n)).convolve_signal(DspVec(rc(l))).to_numpy()
+# first-load multipliers: windows on every transform path, spectrum multiply of the full-length convolution, chirp filter
+for n in (1000, 1001, 4096, 1 << 15, 1 << 16, 3 * (1 << 15), 1 << 21):
+    DspVec(rc(n)).windowed_fft(bd.HAMMING).to_numpy()
+for n in (1001, 1 << 14, 3 * (1 << 14)):
+    DspVec(rc(n, np.complex128)).windowed_fft(bd.BLACKMAN_HARRIS).to_numpy()
+DspVec(rc(1 << 15)).convolve_signal(DspVec(rc(9000))).to_numpy()
+DspVec(rc(5 * (1 << 13))).convolve_signal(DspVec(rc(8500))).to_numpy()
+DspVec(rc(30001, np.complex128)).convolve_signal(DspVec(rc(4100, np.complex128))).to_numpy()
+# 16384-point rows (rolling pipeline), batched rows entry points
+x = DspVec(rc(16384 * 5)); out = DspVec.zeros(2 * 16384 * 5, is_complex=True, dtype=np.float32)
+for flags in (0, bd.F_SHIFT | bd.F_MAGNITUDE, bd.F_INVERSE):
+    assert L.bdsp_fft_rows_c32(dp(x), dp(out), 16384, 5, flags) == 0
 L.bdsp_sync()
 print("sanitize smoke done")
