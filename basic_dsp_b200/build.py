@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbasic_dsp_b200.so")
 STAMP = os.path.join(HERE, ".build_stamp")
-SOURCES = ["common.cu", "fft.cu", "conv.cu", "ols4096i.cu", "ols8192i.cu", "ols64.cu", "fftp.cu", "fftp16k.cu", "interp.cu", "elementwise.cu", "mathops.cu", "reduce.cu", "capi.cu"]
+SOURCES = ["common.cu", "fft.cu", "conv.cu", "ols4096i.cu", "ols8192i.cu", "ols64.cu", "fftp.cu", "fftp16k.cu", "fftc.cu", "interp.cu", "elementwise.cu", "mathops.cu", "reduce.cu", "capi.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--use_fast_math=false",

@@ -33,6 +33,7 @@ int fftp_two_pass_try(const void* in, void* out, void* tmp, size_t n, size_t row
 int fftp_try(const void* in, void* out, size_t n, size_t rows, bool inverse, size_t in_rot, size_t out_rot, double scale,
              bool magnitude, cudaStream_t st);
 int fftp_try_real(const void* in, void* out, size_t n, size_t rows, size_t out_rot, double scale, bool magnitude, cudaStream_t st);
+int fftc_try(const void* in, void* out, size_t n, size_t rows, bool inverse, size_t in_rot, size_t out_rot, double scale, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------
 // per-device state: twiddle tables, workspaces
@@ -911,6 +912,11 @@ int fft_any(const void* in, void* out, size_t n, size_t batch, const FftOpts& o,
         if (n > fft_block_max_n<T>()) {
             size_t need = n * batch * sizeof(C);
             if (!w || work_bytes < need) { w = workspace(need, 0); if (!w) return -1001; }
+        }
+        if (sizeof(T) == 4 && n == 65536 && !o.real_input && !im.kind && !o.magnitude) {
+            // few 2^16-point vectors: one launch on a 16-CTA cluster, transposition through distributed shared memory (fftc.cu)
+            const int rc = fftc_try(in, out, n, batch, INV, (size_t)in_rot, (size_t)om.rot, o.scale, st);
+            if (rc <= 0) return rc;
         }
         if (sizeof(T) == 4 && n >= (1u << 15) && n <= (1u << 20)) {
             // packed two-pass path (fftp.cu): 16 B/point of traffic per pass

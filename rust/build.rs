@@ -21,7 +21,7 @@ fn main() {
             .flag("-std=c++17")
             .include(root.join("include"));
         for f in &[
-            "common.cu", "fft.cu", "conv.cu", "ols4096i.cu", "ols8192i.cu", "ols64.cu", "fftp.cu", "fftp16k.cu", "interp.cu", "elementwise.cu",
+            "common.cu", "fft.cu", "conv.cu", "ols4096i.cu", "ols8192i.cu", "ols64.cu", "fftp.cu", "fftp16k.cu", "fftc.cu", "interp.cu", "elementwise.cu",
             "mathops.cu", "reduce.cu", "capi.cu",
         ] {
             b.file(csrc.join(f));

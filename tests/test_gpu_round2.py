@@ -333,3 +333,28 @@ def test_convolve_signal_full_length_fused_spectrum_multiply(dtype, n, l):
     hr = (rng.uniform(-1, 1, l) / 10).astype(dtype)
     gr = DspVec(xr).convolve_signal(DspVec(hr)).to_numpy()
     assert o.rel_l2(gr, o.convolve_signal(xr.astype(x.dtype), hr.astype(x.dtype)).real) <= tol(n, dtype)
+
+
+# ---- single-launch 2^16-point transform on a 16-CTA cluster (fftc.cu) ---------------------------------------------------
+@pytest.mark.parametrize("rows", [1, 3, 8])
+def test_cluster_fft_65536(rows):
+    """Few 2^16-point c32 vectors take one launch on a thread-block cluster (transposition through distributed shared
+    memory); every flag combination of the rows entry point and the vector methods against the oracle."""
+    L = bd.lib()
+    n = 1 << 16
+    rng = np.random.default_rng(rows)
+    x = rand_c(rng, n * rows, np.float32)
+    xv = DspVec(x)
+    out = DspVec.zeros(2 * n * rows, is_complex=True)
+    xr = x.reshape(rows, n)
+    for flags, ref in ((0, o.plain_fft), (bd.F_SHIFT, o.fft), (bd.F_INVERSE, lambda v: o.plain_ifft(v)),
+                       (bd.F_INVERSE | bd.F_SHIFT, lambda v: o.ifft(v))):
+        before = bd.kernel_launch_count()
+        assert L.bdsp_fft_rows_c32(dptr(xv), dptr(out), n, rows, flags) == 0
+        assert bd.kernel_launch_count() - before == 1
+        got = out.to_numpy().reshape(rows, n)
+        for r in range(rows):
+            want = np.asarray(ref(xr[r]))
+            assert o.rel_l2(got[r], want) <= tol(n, np.float32), (flags, r)
+    v = DspVec(xr[0])
+    assert o.rel_l2(v.fft().ifft().to_numpy(), xr[0]) <= 2 * tol(n, np.float32)
