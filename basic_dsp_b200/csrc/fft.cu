@@ -588,6 +588,16 @@ template <typename T, bool INV>
 int launch_block(const void* in, void* out, size_t n, size_t batch, bool real_in, bool mag, long long in_rot,
                  T scale, const OutMap& om, cudaStream_t st, const InMul& im = InMul()) {
     typedef typename CpxOf<T>::type C;
+    if constexpr (sizeof(T) == 8 && BDSP_F64_TILE_KERNELS) {
+        // c64 rows of 1024 / 2048 / 4096 points: the 8-points-per-thread row kernel of fft64t.cuh
+        // (in place only with the plain row layout: a row's loads all precede its stores, rows do not overlap)
+        if (n >= 1024 && n <= 4096 && (in != out || (om.seq_group == 1 && om.oes == 1 && om.group_stride == (long long)n && !real_in && !mag))) {
+            const double2* twt = twiddle_table<double>();
+            if (!twt) return -1001;
+            const int rc = f64t::launch_rows<INV>(in, out, n, batch, real_in, mag, in_rot, (double)scale, om, im, twt, st);
+            if (rc <= 0) { if (!rc) BDSP_LAUNCHED(); return rc; }
+        }
+    }
     const int log2n = ilog2(n);
     // points per CTA for short sequences (BDSP_BLOCK_POINTS): smaller CTAs overlap their load / compute / store phases better
     int nfft = (int)(BDSP_BLOCK_POINTS / n);
