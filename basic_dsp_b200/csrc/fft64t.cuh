@@ -18,6 +18,12 @@
 #ifndef F64T_MIN_CTAS
 #define F64T_MIN_CTAS 4
 #endif
+#ifndef F64T_Q3_LCT
+#define F64T_Q3_LCT 2   // lanes (log2) per tile of the radix-3 first pass: 3 x 256 x 4 points, 384 threads
+#endif
+#ifndef F64T_Q3_MIN_CTAS
+#define F64T_Q3_MIN_CTAS 2
+#endif
 #ifndef F64T_POINTS_LOG2
 #define F64T_POINTS_LOG2 11
 #endif
@@ -63,7 +69,7 @@ template <int LOG2M, int LCT, int Q> struct Geo {
 };
 
 template <int LOG2M, int LCT, int Q, bool INV>
-__global__ void __launch_bounds__(Geo<LOG2M, LCT, Q>::NT, Q == 1 ? F64T_MIN_CTAS : 2)
+__global__ void __launch_bounds__(Geo<LOG2M, LCT, Q>::NT, Q == 1 ? (F64T_MIN_CTAS * 256) / Geo<LOG2M, LCT, Q>::NT : F64T_Q3_MIN_CTAS)
 f64_tile_kernel(TileParams p, double scale, const double2* __restrict__ tw) {
     typedef Geo<LOG2M, LCT, Q> G;
     constexpr int M = G::M, CT = G::CT, J = G::J, NT = G::NT;
@@ -255,7 +261,7 @@ template <bool INV>
 int launch(const TileParams& p, long long batch, double scale, const double2* tw, cudaStream_t st) {
     if (batch > 65535 || p.o1_count > 65535 || p.lanes >= (1ll << 36)) return 1;
     if (p.q == 3) {
-        if (p.log2m == 8 && p.lanes % 4 == 0) return launch_one<8, 2, 3, INV>(p, batch, scale, tw, st);
+        if (p.log2m == 8 && p.lanes % (1 << F64T_Q3_LCT) == 0) return launch_one<8, F64T_Q3_LCT, 3, INV>(p, batch, scale, tw, st);
         return 1;
     }
     if (p.q != 1) return 1;
@@ -264,7 +270,12 @@ int launch(const TileParams& p, long long batch, double scale, const double2* tw
         case 6: if (p.lanes % (1 << (PL - 6)) == 0) return launch_one<6, PL - 6, 1, INV>(p, batch, scale, tw, st); break;
         case 7: if (p.lanes % (1 << (PL - 7)) == 0) return launch_one<7, PL - 7, 1, INV>(p, batch, scale, tw, st); break;
         case 8: if (p.lanes % (1 << (PL - 8)) == 0) return launch_one<8, PL - 8, 1, INV>(p, batch, scale, tw, st); break;
-        case 9: if (p.lanes % (1 << (PL - 9)) == 0) return launch_one<9, PL - 9, 1, INV>(p, batch, scale, tw, st); break;
+        case 9:
+            // 512-point passes: 8 lanes (128-byte segments, 4096 points, 512 threads) where the lane count allows - measured on
+            // B200 (C5a): 5.56 ms against 5.72 ms with 4 lanes; 32-byte segments (2 lanes): 7.2 ms
+            if (p.lanes % (2 << (PL - 9)) == 0) return launch_one<9, PL - 8, 1, INV>(p, batch, scale, tw, st);
+            if (p.lanes % (1 << (PL - 9)) == 0) return launch_one<9, PL - 9, 1, INV>(p, batch, scale, tw, st);
+            break;
         default: break;
     }
     return 1;
