@@ -30,6 +30,10 @@ using namespace cx;
 
 #define OI_M 4096
 #define OI_T 128
+// spectrum H through the texture path (0) or as plain 128-bit global loads (1)
+#ifndef OI_H_LDG
+#define OI_H_LDG 0
+#endif
 #ifndef OI_MIN_CTAS
 #define OI_MIN_CTAS 5
 #endif
@@ -44,7 +48,7 @@ using namespace cx;
 template <bool ALIGNED>
 __global__ void __launch_bounds__(OI_T, OI_MIN_CTAS)
 ols4096i_kernel(const float2* __restrict__ x, float2* __restrict__ y, int N, int m_first, int step, int shift,
-                int blocks_per_vec, const float2* __restrict__ tw, cudaTextureObject_t htex) {
+                int blocks_per_vec, const float2* __restrict__ tw, cudaTextureObject_t htex, const float4* __restrict__ hpos) {
     __shared__ __align__(16) float2 sm[OI_M];
     const int t = threadIdx.x;
     const int vec = blockIdx.x / blocks_per_vec;
@@ -135,7 +139,7 @@ ols4096i_kernel(const float2* __restrict__ x, float2* __restrict__ y, int N, int
 #pragma unroll
         for (int q = 0; q < 8; q++) {
             // plan layout: [half][q][thread] float4 = H of positions c = 2q, 2q + 1 -> a warp reads 512 contiguous bytes
-            const float4 h = (OI_ABLATE & 8) ? make_float4(1.f, 0.f, 1.f, 0.f) : tex1Dfetch<float4>(htex, (half * 8 + q) * OI_T + t);
+            const float4 h = (OI_ABLATE & 8) ? make_float4(1.f, 0.f, 1.f, 0.f) : OI_H_LDG ? __ldg(hpos + (half * 8 + q) * OI_T + t) : tex1Dfetch<float4>(htex, (half * 8 + q) * OI_T + t);
             P[2 * q] = mul(P[2 * q], make_float2(h.x, h.y));
             P[2 * q + 1] = mul(P[2 * q + 1], make_float2(h.z, h.w));
         }
@@ -271,7 +275,6 @@ int ols4096_prepare(const void* Hs, void* Hpos, size_t L, cudaStream_t st) {
 }
 
 int ols4096_convolve(const void* x, void* y, size_t N, size_t batch, size_t L, const void* Hpos, cudaTextureObject_t htex, cudaStream_t st) {
-    (void)Hpos;
     if (x == y) { set_last_error("ols4096_convolve: in-place operation is not supported"); return -3; }
     int d, shift, m_first, step;
     olsi_geometry(OI_M, L, &d, &shift, &m_first, &step);
@@ -283,10 +286,10 @@ int ols4096_convolve(const void* x, void* y, size_t N, size_t batch, size_t L, c
     const bool aligned = (N % 2 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     if (aligned)
         ols4096i_kernel<true><<<(unsigned)grid, OI_T, 0, st>>>(reinterpret_cast<const float2*>(x), reinterpret_cast<float2*>(y), (int)N,
-                                                               m_first, step, shift, (int)bpv, tw, htex);
+                                                               m_first, step, shift, (int)bpv, tw, htex, reinterpret_cast<const float4*>(Hpos));
     else
         ols4096i_kernel<false><<<(unsigned)grid, OI_T, 0, st>>>(reinterpret_cast<const float2*>(x), reinterpret_cast<float2*>(y), (int)N,
-                                                                m_first, step, shift, (int)bpv, tw, htex);
+                                                                m_first, step, shift, (int)bpv, tw, htex, reinterpret_cast<const float4*>(Hpos));
     BDSP_LAUNCHED();
     return 0;
 }
