@@ -78,6 +78,27 @@ __device__ __forceinline__ double2 cmul_nofma(double2 a, double2 b) {
 __device__ __forceinline__ void sincospi_t(float x, float* s, float* c) { sincospif(x, s, c); }
 __device__ __forceinline__ void sincospi_t(double x, double* s, double* c) { sincospi(x, s, c); }
 
+// --- programmatic dependent launch (sm_90+): a kernel launched with launch_pdl() may become resident while the previous
+// kernel of the stream is still draining; pdl_wait() (griddepcontrol.wait) blocks until that kernel has completed and its
+// memory is visible, and must precede the first global access.  pdl_trigger() lets the NEXT kernel start its launch early.
+// Hides the 2-3 us launch latency between the short kernels of single-vector operation chains.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+#ifndef BDSP_PDL
+#define BDSP_PDL 1
+#endif
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = BDSP_PDL ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // --- multiplier fused into the first load of a transform (FftOpts::in_mul) ------------------
 // kind 0: none; 1: table of n real scalars T; 2: table of n complex values; 3: built-in window `arg` (0 triangular,
 // 1 Hamming, 2 Blackman-Harris, else rectangular) of length n (window_functions.rs:25-129, symmetric evaluation of

@@ -57,6 +57,8 @@ ols4096i_kernel(const float2* __restrict__ x, float2* __restrict__ y, int N, int
     const float2* xr = x + (size_t)vec * (size_t)N;
     float2* yr = y + (size_t)vec * (size_t)N;
     const int hi = t >> 3, lo = t & 7;         // quarter-warp index / lane inside it
+    pdl_trigger();                             // the next kernel of the stream may start launching
+    pdl_wait();                                // ... and this one touches global memory only after its predecessor is complete
 
     c2 v[16], u[16];                           // the thread's two columns
     // ------------------------------------------------------------------ F1: over a, columns (2t, 2t+1) = (b = hi, c = 2 lo, 2 lo + 1)
@@ -285,11 +287,11 @@ int ols4096_convolve(const void* x, void* y, size_t N, size_t batch, size_t L, c
     if (!tw) return -1;
     const bool aligned = (N % 2 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     if (aligned)
-        ols4096i_kernel<true><<<(unsigned)grid, OI_T, 0, st>>>(reinterpret_cast<const float2*>(x), reinterpret_cast<float2*>(y), (int)N,
-                                                               m_first, step, shift, (int)bpv, tw, htex, reinterpret_cast<const float4*>(Hpos));
+        BDSP_CUDA_OK(launch_pdl(ols4096i_kernel<true>, dim3((unsigned)grid), dim3(OI_T), 0, st, reinterpret_cast<const float2*>(x),
+                                reinterpret_cast<float2*>(y), (int)N, m_first, step, shift, (int)bpv, tw, htex, reinterpret_cast<const float4*>(Hpos)));
     else
-        ols4096i_kernel<false><<<(unsigned)grid, OI_T, 0, st>>>(reinterpret_cast<const float2*>(x), reinterpret_cast<float2*>(y), (int)N,
-                                                                m_first, step, shift, (int)bpv, tw, htex, reinterpret_cast<const float4*>(Hpos));
+        BDSP_CUDA_OK(launch_pdl(ols4096i_kernel<false>, dim3((unsigned)grid), dim3(OI_T), 0, st, reinterpret_cast<const float2*>(x),
+                                reinterpret_cast<float2*>(y), (int)N, m_first, step, shift, (int)bpv, tw, htex, reinterpret_cast<const float4*>(Hpos)));
     BDSP_LAUNCHED();
     return 0;
 }
