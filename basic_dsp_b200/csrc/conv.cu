@@ -155,6 +155,15 @@ OlsPlan* ols_plan_create(const void* h, size_t L, int h_is_real, bool complex_si
         p->M2 = 8192;
         rc = ols_spectrum<T>(h, L, h_is_real, p->M2, true, &p->Hs2, &p->htex2, st);
     }
+    if (!rc && sizeof(T) == 4 && complex_signal && L > 4094) {
+        const size_t bytes = L * (h_is_real ? sizeof(T) : sizeof(typename CpxOf<T>::type));
+        if (cudaMalloc(&p->taps_dev, bytes) != cudaSuccess ||
+            cudaMemcpyAsync(p->taps_dev, h, bytes, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+            cudaGetLastError();
+            if (p->taps_dev) cudaFree(p->taps_dev);
+            p->taps_dev = nullptr;   // not fatal: such plans use the generic blocks
+        }
+    }
     if (rc) { ols_plan_destroy(p); return nullptr; }
     return p;
 }
@@ -169,6 +178,7 @@ void ols_plan_destroy(OlsPlan* p) {
     if (p->htex2) cudaDestroyTextureObject(p->htex2);
     if (p->Hs) cudaFree(p->Hs);
     if (p->Hs2) cudaFree(p->Hs2);
+    if (p->taps_dev) cudaFree(p->taps_dev);
     if (cur != p->device) cudaSetDevice(cur);
     delete p;
 }
@@ -193,6 +203,11 @@ int ols_plan_convolve(const OlsPlan* p, const void* x, void* y, size_t N, size_t
     if (!p || p->is64 != (sizeof(T) == 8)) { set_last_error("ols_convolve: plan precision mismatch"); return -2; }
     if (x == y) { set_last_error("ols_convolve: in-place operation is not supported"); return -3; }
     const size_t L = p->L, M = p->M;
+    // c32 responses beyond the fused blocks (4095 .. 8192 taps) on power-of-two vectors with packed multi-pass transforms:
+    // forward transform + inverse transform with the spectrum multiply on its first load (2 x 2 passes over HBM) beats the
+    // generic 16384-point overlap-save blocks (64 x 2^20, 8191 taps: 1.79 ms)
+    if (sizeof(T) == 4 && !is_real && L > 4094 && is_pow2(N) && N >= (1u << 15) && N <= (1u << 24) && p->taps_dev)
+        return fft_convolve_full<T>(x, y, p->taps_dev, N, batch, L, 0, p->h_is_real, st);
     if (sizeof(T) == 4 && !is_real) {
         const int force = ols_forced_block();
         // (ols8192_blocks divides by the block step, which is only positive for applicable lengths)

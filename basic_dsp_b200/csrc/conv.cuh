@@ -22,6 +22,9 @@ struct OlsPlan {
     size_t M2 = 0;
     void* Hs2 = nullptr;
     cudaTextureObject_t htex2 = 0;
+    // c32 responses longer than the fused blocks: the plan's own copy of the taps (L real or complex values) for the
+    // full-length frequency-domain path, which power-of-two vectors take instead of the generic blocks
+    void* taps_dev = nullptr;
 };
 // h: L complex (or real) taps on the device.  complex_signal: the vectors that will be convolved are complex.
 template <typename T> OlsPlan* ols_plan_create(const void* h, size_t L, int h_is_real, bool complex_signal, cudaStream_t st);
