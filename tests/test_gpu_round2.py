@@ -358,3 +358,70 @@ def test_cluster_fft_65536(rows):
             assert o.rel_l2(got[r], want) <= tol(n, np.float32), (flags, r)
     v = DspVec(xr[0])
     assert o.rel_l2(v.fft().ifft().to_numpy(), xr[0]) <= 2 * tol(n, np.float32)
+
+
+# ---- seeded sweep over lengths / rows / flags: every dispatch branch of the transforms ----------------------------------
+def _sweep_lengths():
+    rng = np.random.default_rng(20261017)
+    out = []
+    # powers of two, q * 2^k with odd q <= 31, and arbitrary lengths (chirp-z), small to multi-pass
+    for k in rng.integers(1, 21, 10):
+        out.append(1 << int(k))
+    for _ in range(12):
+        q = int(rng.choice([3, 5, 7, 9, 11, 13, 15, 17, 21, 25, 27, 31]))
+        out.append(q << int(rng.integers(1, 16)))
+    for _ in range(8):
+        out.append(int(rng.integers(3, 200000)) | 1)
+    return sorted(set(out))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("n", _sweep_lengths())
+def test_fft_rows_sweep(n, dtype):
+    """Rows entry point over a seeded sample of lengths with every flag combination, against pocketfft in c128."""
+    L = bd.lib()
+    sfx = "c32" if dtype == np.float32 else "c64"
+    rng = np.random.default_rng(n)
+    rows = int(max(1, min(5, (1 << 19) // n)))
+    x = rand_c(rng, n * rows, dtype)
+    xv = DspVec(x)
+    out = DspVec.zeros(2 * n * rows, is_complex=True, dtype=dtype)
+    xr = x.reshape(rows, n)
+    fn = getattr(L, "bdsp_fft_rows_" + sfx)
+    for flags, ref in ((0, o.plain_fft), (bd.F_SHIFT, o.fft), (bd.F_INVERSE, o.plain_ifft), (bd.F_INVERSE | bd.F_SHIFT, o.ifft)):
+        assert fn(dptr(xv), dptr(out), n, rows, flags) == 0
+        got = out.to_numpy().reshape(rows, n)
+        for r in range(rows):
+            assert o.rel_l2(got[r], np.asarray(ref(xr[r]))) <= 2 * tol(n, dtype), (flags, r)
+    # magnitude epilogue and real input
+    mag = DspVec.zeros(n * rows, is_complex=False, dtype=dtype)
+    assert fn(dptr(xv), dptr(mag), n, rows, bd.F_SHIFT | bd.F_MAGNITUDE) == 0
+    gm = mag.to_numpy().reshape(rows, n)
+    for r in range(rows):
+        assert o.rel_l2(gm[r], np.abs(o.fft(xr[r]))) <= 2 * tol(n, dtype), r
+    xre = DspVec(np.ascontiguousarray(x.real))
+    assert fn(dptr(xre), dptr(out), n, rows, bd.F_REAL_INPUT) == 0
+    gr = out.to_numpy().reshape(rows, n)
+    for r in range(rows):
+        assert o.rel_l2(gr[r], o.plain_fft(xr[r].real)) <= 2 * tol(n, dtype), r
+
+
+def _sweep_conv():
+    rng = np.random.default_rng(20261018)
+    out = []
+    for _ in range(14):
+        n = int(rng.integers(64, 300000))
+        l = int(rng.integers(1, min(n, 9000)))
+        out.append((n, l))
+    return out
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("n,l", _sweep_conv())
+def test_convolve_signal_sweep(n, l, dtype):
+    rng = np.random.default_rng(n * 31 + l)
+    x = rand_c(rng, n, dtype)
+    h = (rand_c(rng, l, dtype) / 10).astype(x.dtype)
+    got = DspVec(x).convolve_signal(DspVec(h)).to_numpy()
+    ref = o.convolve_signal_direct(x, h) if n * l < 3e7 else o.convolve_signal(x, h)
+    assert o.rel_l2(got, ref) <= tol(max(n, 4096), dtype)
