@@ -22,6 +22,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BASIC_DSP_B200_LIB", os.path.join(_HERE, "libbasic_dsp_b200.so"))
 
 F_INVERSE, F_SHIFT, F_MAGNITUDE, F_REAL_INPUT = 1, 2, 4, 8
+
+
+def F_WINDOW(kind):
+    """bdsp_fft_rows_* flag: multiply every row by the built-in window `kind` while loading it (windowed_fft per row)."""
+    return ((kind & 7) + 1) << 8
 TIME, FREQ = 0, 1
 SINC, RAISED_COSINE = 0, 1
 TRIANGULAR, HAMMING, BLACKMAN_HARRIS, RECTANGULAR = 0, 1, 2, 3   # translate_to_window_function (interop/src/lib.rs:153-164)

@@ -1352,6 +1352,12 @@ template <typename T> int fft_rows(const void* in, void* out, size_t points, siz
         if (o.inverse) { o.in_rot = points / 2; o.scale = (double)((T)1 / (T)points); }
         else o.out_rot = points / 2;
     }
+    const int wk = (flags >> 8) & 15;   // BDSP_F_WINDOW(kind): every row is multiplied by the window on the way in (windowed_fft per row)
+    if (wk) {
+        if (o.inverse) { set_last_error("fft rows: a window applies to forward transforms only"); return -2; }
+        const int kind = wk - 1;
+        if (kind >= 0 && kind <= 2) { o.in_mul.kind = 3; o.in_mul.arg = kind; }
+    }
     return fft_exec<T>(in, out, points, rows, o, nullptr, 0, g_stream);
 }
 

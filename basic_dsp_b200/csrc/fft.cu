@@ -877,6 +877,20 @@ __global__ void window_table_kernel(T* __restrict__ tab, long long n, int kind) 
     if (i < n) tab[i] = window_value_dev<T>(kind, i < (n + 1) / 2 ? i : n - 1 - i, n);
 }
 
+// out[b][g] = in[b][g] * multiplier[g]: the separate pass for transforms whose kernels take no first-load multiplier
+// (packed single-pass c32 rows).  Real rows stay real under a real table and become complex under a complex one.
+template <typename T>
+__global__ void in_mul_rows_kernel(const void* __restrict__ in_, void* __restrict__ out_, long long n, long long total, int real_input, InMul im) {
+    typedef typename CpxOf<T>::type C;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long g = i % n;
+    C v = real_input ? mk<T>(reinterpret_cast<const T*>(in_)[i], (T)0) : reinterpret_cast<const C*>(in_)[i];
+    v = in_mul_apply<T>(v, im.p, im.kind, im.arg, g, n);
+    if (real_input && im.kind != 2) reinterpret_cast<T*>(out_)[i] = v.x;
+    else reinterpret_cast<C*>(out_)[i] = v;
+}
+
 template <typename T, bool INV>
 int fft_any(const void* in, void* out, size_t n, size_t batch, const FftOpts& o, void* work, size_t work_bytes,
             cudaStream_t st) {
@@ -894,7 +908,20 @@ int fft_any(const void* in, void* out, size_t n, size_t batch, const FftOpts& o,
         im.p = tab; im.kind = 1;
     }
     // a first-load multiplier (window / spectrum) is carried by the generic kernels, the c64 tile passes and the packed
-    // column passes of the two- and three-pass c32 transforms; the packed single-pass c32 kernels do not take one
+    // column passes of the two- and three-pass c32 transforms; the packed single-pass c32 kernels do not take one: in
+    // their throughput regime one elementwise pass + the packed kernel beats the generic kernel with the multiplier fused
+    if (sizeof(T) == 4 && im.kind && is_pow2(n) && n >= 64 && n <= 16384 && n * batch >= (1u << 16)) {
+        const bool to_complex = o.real_input && im.kind == 2;
+        const bool real_rows = o.real_input && !to_complex;
+        BDSP_WS(mx, void*, n * batch * (real_rows ? sizeof(T) : sizeof(C)), 2);
+        const long long tot = (long long)(n * batch);
+        in_mul_rows_kernel<T><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(in, mx, (long long)n, tot, o.real_input, im);
+        BDSP_LAUNCHED();
+        FftOpts o2 = o;
+        o2.in_mul = InMul();
+        if (to_complex) o2.real_input = 0;
+        return fft_any<T, INV>(mx, out, n, batch, o2, work, work_bytes, st);
+    }
     if (is_pow2(n)) {
         if (sizeof(T) == 4 && !im.kind && o.real_input && !INV && in_rot == 0 && n >= 64 && n <= 16384 && n * batch >= (1u << 16)) {
             // rows of real scalars, single pass: the packed kernel loads the reals directly (4 B read + 8 B written per point)

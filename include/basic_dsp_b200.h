@@ -504,6 +504,10 @@ BdspVecResult64 bdsp_fft_magnitude64(BdspVec64* vector);
 #define BDSP_F_SHIFT 2        /* forward: fft_shift the result; inverse: scale(1/points) + ifft_shift the input (fft()/ifft() semantics) */
 #define BDSP_F_MAGNITUDE 4    /* store |X| (points real scalars per row) */
 #define BDSP_F_REAL_INPUT 8   /* rows hold `points` real scalars */
+#define BDSP_F_WINDOW(kind) ((((kind) & 7) + 1) << 8) /* forward only: multiply every row by the built-in window `kind` (0 triangular,
+                                                     * 1 Hamming, 2 Blackman-Harris, 3 rectangular; translate_to_window_function,
+                                                     * interop/src/lib.rs:153-164) while loading it = windowed_fft per row
+                                                     * (matrix/src/time_freq.rs:69-74, time_to_freq.rs:167-175) */
 int32_t bdsp_fft_rows_c32(const void* in, void* out, size_t points, size_t rows, int32_t flags);
 int32_t bdsp_fft_rows_c64(const void* in, void* out, size_t points, size_t rows, int32_t flags);
 /* convolve_signal for every row with one impulse response of h_points complex taps (device pointer);

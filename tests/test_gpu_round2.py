@@ -425,3 +425,32 @@ def test_convolve_signal_sweep(n, l, dtype):
     got = DspVec(x).convolve_signal(DspVec(h)).to_numpy()
     ref = o.convolve_signal_direct(x, h) if n * l < 3e7 else o.convolve_signal(x, h)
     assert o.rel_l2(got, ref) <= tol(max(n, 4096), dtype)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("n,rows", [(256, 512), (1024, 64), (4096, 32), (16384, 8), (1000, 70), (3 * 1024, 24), (1 << 15, 4), (1 << 17, 2), (64, 3)])
+def test_windowed_fft_rows(n, rows, dtype):
+    """BDSP_F_WINDOW: windowed_fft of every row (matrix/src/time_freq.rs:69-74) in one call; complex and real rows; equals the
+    per-vector windowed_fft."""
+    L = bd.lib()
+    sfx = "c32" if dtype == np.float32 else "c64"
+    fn = getattr(L, "bdsp_fft_rows_" + sfx)
+    rng = np.random.default_rng(n + rows)
+    x = rand_c(rng, n * rows, dtype)
+    xv = DspVec(x)
+    out = DspVec.zeros(2 * n * rows, is_complex=True, dtype=dtype)
+    xr = x.reshape(rows, n)
+    for kind in (bd.HAMMING, bd.BLACKMAN_HARRIS, bd.RECTANGULAR):
+        assert fn(dptr(xv), dptr(out), n, rows, bd.F_SHIFT | bd.F_WINDOW(kind)) == 0
+        got = out.to_numpy().reshape(rows, n)
+        for r in (0, rows // 2, rows - 1):
+            assert o.rel_l2(got[r], o.windowed_fft(xr[r], kind, dtype)) <= tol(n, dtype), (kind, r)
+    one = DspVec(xr[rows - 1]).windowed_fft(bd.BLACKMAN_HARRIS).to_numpy()
+    assert fn(dptr(xv), dptr(out), n, rows, bd.F_SHIFT | bd.F_WINDOW(bd.BLACKMAN_HARRIS)) == 0
+    assert o.rel_l2(out.to_numpy().reshape(rows, n)[rows - 1], one) <= tol(n, dtype)
+    xre = DspVec(np.ascontiguousarray(x.real))
+    assert fn(dptr(xre), dptr(out), n, rows, bd.F_REAL_INPUT | bd.F_SHIFT | bd.F_WINDOW(bd.HAMMING)) == 0
+    gr = out.to_numpy().reshape(rows, n)
+    for r in (0, rows - 1):
+        assert o.rel_l2(gr[r], o.windowed_fft(xr[r].real.astype(x.dtype), bd.HAMMING, dtype)) <= tol(n, dtype), r
+    assert fn(dptr(xv), dptr(out), n, rows, bd.F_INVERSE | bd.F_WINDOW(bd.HAMMING)) != 0   # forward transforms only
