@@ -721,14 +721,15 @@ template <typename T> Res<T> op_correlate(Vec<T>* v, const Vec<T>* other) {
     FftOpts f;
     int rc = ensure_scratch(v, v->len);
     if (!rc) rc = fft_exec<T>(v->d, v->scratch, points, 1, f, nullptr, 0, g_stream);
-    if (!rc) rc = ew_binary<T>(EW_MUL, v->scratch, other->d, v->scratch, 2 * points, 1, g_stream);
     if (rc) return done(v, rc);
-    // plain_ifft, then scale(1/points) and swap_halves fused into the transform's store
+    // mul(other), plain_ifft, scale(1/points), swap_halves (correlation.rs:151-160) as ONE transform: the product with the
+    // prepared spectrum and the scale ride on the inverse transform's first load, swap_halves on its store
     FftOpts inv;
     inv.inverse = 1;
     inv.out_rot = points / 2;
+    inv.in_mul.p = other->d; inv.in_mul.kind = 2;
+    inv.scale = (double)((T)1 / (T)points);
     rc = fft_exec<T>(v->scratch, v->d, points, 1, inv, nullptr, 0, g_stream);
-    if (!rc) rc = ew_scalar<T>(EW_SCALE, v->d, v->d, 2 * points, (double)((T)1 / (T)points), g_stream);
     v->delta = delta;
     return done(v, rc);
 }
