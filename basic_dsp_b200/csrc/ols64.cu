@@ -72,17 +72,18 @@ ols64_kernel(const double2* __restrict__ x, double2* __restrict__ y, long long N
     const int j = threadIdx.x;
     const unsigned vec = blockIdx.x / blocks_per_vec;
     const unsigned blk = blockIdx.x - vec * blocks_per_vec;
-    const long long i0 = (long long)blk * step;          // first output of this block
+    const int i0 = (int)blk * step;                      // first output of this block (N < 2^31)
     const int cl = L - L / 2;
-    const long long p0 = i0 - (L - cl);                   // first input: -N < p0 < N, block length <= N
+    const int n = (int)N;
+    int g = i0 - (L - cl) + j;                            // first input: -N < g < N, block length <= N
+    if (g < 0) g += n;
     const double2* xv = x + (long long)vec * N;
     double2 v[8];
 #pragma unroll
     for (int r = 0; r < 8; r++) {
-        long long g = p0 + j + 512 * r;
-        if (g < 0) g += N;
-        else if (g >= N) g -= N;
         v[r] = xv[g];
+        g += 512;
+        if (g >= n) g -= n;
     }
     o64_fft<false>(v, s, j, tw);
 #pragma unroll
@@ -93,14 +94,14 @@ ols64_kernel(const double2* __restrict__ x, double2* __restrict__ y, long long N
 #pragma unroll
     for (int r = 0; r < 8; r++) {
         const int m = j + 512 * r;
-        const long long i = i0 + m - (L - 1);
-        if (m >= L - 1 && i < N) yv[i] = v[r];
+        const int i = i0 + m - (L - 1);
+        if (m >= L - 1 && i < n) yv[i] = v[r];
     }
 }
 
 }  // namespace
 
-bool ols64_applicable(size_t N, size_t L, size_t M) { return M == (size_t)O64_M && L >= 1 && L <= (size_t)O64_M / 2 && N >= (size_t)O64_M; }
+bool ols64_applicable(size_t N, size_t L, size_t M) { return M == (size_t)O64_M && L >= 1 && L <= (size_t)O64_M / 2 && N >= (size_t)O64_M && N < (1ull << 30); }
 
 int ols64_convolve(const void* x, void* y, size_t N, size_t batch, size_t L, const void* Hs, cudaStream_t st) {
     const int step = O64_M - (int)L + 1;
