@@ -100,14 +100,16 @@ f64_tile_kernel(TileParams p, double scale, const double2* __restrict__ tw) {
     double2 v[8];
 
     if (Q == 1) {
-        const long long g0 = lane * p.in_lane_stride + (long long)j * p.in_point_stride + p.in_rot;
-        const long long gs = (long long)J * p.in_point_stride;
+        // positions inside a sequence fit 32 bits (sequences have fewer than 2^31 points)
+        const int n_in = (int)p.in_n;
+        const int g0 = (int)lane * (int)p.in_lane_stride + j * (int)p.in_point_stride + (int)p.in_rot;
+        const int gs = J * (int)p.in_point_stride;
         if (p.real_input) {
             const double* in = reinterpret_cast<const double*>(p.in) + inb;
 #pragma unroll
             for (int r = 0; r < 8; r++) {
-                long long g = g0 + r * gs;
-                if (g >= p.in_n) g -= p.in_n;
+                int g = g0 + r * gs;
+                if (g >= n_in) g -= n_in;
                 v[r] = make_double2(in[g], 0.0);
                 if (p.im.kind) v[r] = in_mul_apply<double>(v[r], p.im.p, p.im.kind, p.im.arg, g, p.in_n);
             }
@@ -115,8 +117,8 @@ f64_tile_kernel(TileParams p, double scale, const double2* __restrict__ tw) {
             const double2* in = reinterpret_cast<const double2*>(p.in) + inb;
 #pragma unroll
             for (int r = 0; r < 8; r++) {
-                long long g = g0 + r * gs;
-                if (g >= p.in_n) g -= p.in_n;
+                int g = g0 + r * gs;
+                if (g >= n_in) g -= n_in;
                 v[r] = in[g];
                 if (p.im.kind) v[r] = in_mul_apply<double>(v[r], p.im.p, p.im.kind, p.im.arg, g, p.in_n);
             }
@@ -232,8 +234,9 @@ f64_tile_kernel(TileParams p, double scale, const double2* __restrict__ tw) {
         }
     } else {
         double2* out = reinterpret_cast<double2*>(p.out) + b * p.out_batch_stride;
+        const int l0 = (int)local0, lsi = (int)ls;
 #pragma unroll
-        for (int i = 0; i < 8; i++) out[local0 + i * ls] = v[i];
+        for (int i = 0; i < 8; i++) out[l0 + i * lsi] = v[i];
     }
 }
 
@@ -259,7 +262,7 @@ int launch_one(const TileParams& p, long long batch, double scale, const double2
 // 1: not covered by these kernels (the caller falls back to fft_tile_kernel), 0: launched, < 0: error
 template <bool INV>
 int launch(const TileParams& p, long long batch, double scale, const double2* tw, cudaStream_t st) {
-    if (batch > 65535 || p.o1_count > 65535 || p.lanes >= (1ll << 36)) return 1;
+    if (batch > 65535 || p.o1_count > 65535 || p.in_n >= (1ll << 30)) return 1;   // (32-bit positions inside a sequence)
     if (p.q == 3) {
         if (p.log2m == 8 && p.lanes % (1 << F64T_Q3_LCT) == 0) return launch_one<8, F64T_Q3_LCT, 3, INV>(p, batch, scale, tw, st);
         return 1;

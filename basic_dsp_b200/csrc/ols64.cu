@@ -77,6 +77,7 @@ ols64_kernel(const double2* __restrict__ x, double2* __restrict__ y, long long N
     const int n = (int)N;
     int g = i0 - (L - cl) + j;                            // first input: -N < g < N, block length <= N
     if (g < 0) g += n;
+    else if (g >= n) g -= n;                              // (last block of a vector)
     const double2* xv = x + (long long)vec * N;
     double2 v[8];
 #pragma unroll
