@@ -85,5 +85,24 @@ DspVec(rc(30001, np.complex128)).convolve_signal(DspVec(rc(4100, np.complex128))
 x = DspVec(rc(16384 * 5)); out = DspVec.zeros(2 * 16384 * 5, is_complex=True, dtype=np.float32)
 for flags in (0, bd.F_SHIFT | bd.F_MAGNITUDE, bd.F_INVERSE):
     assert L.bdsp_fft_rows_c32(dp(x), dp(out), 16384, 5, flags) == 0
+# later round-2 additions: windowed rows (separate pass + packed kernel, fused paths), c64 rows of 1024..4096 points, cluster
+# transform for few 2^16-point rows, long c64 / c32 responses, correlation with the fused spectrum product
+for n, rows, dt in ((1024, 64, np.complex64), (16384, 4, np.complex64), (1000, 8, np.complex64), (4096, 8, np.complex128), (1 << 15, 2, np.complex64)):
+    xx = DspVec(rc(n * rows, dt)); oo = DspVec.zeros(2 * n * rows, is_complex=True, dtype=np.float32 if dt == np.complex64 else np.float64)
+    fn = L.bdsp_fft_rows_c32 if dt == np.complex64 else L.bdsp_fft_rows_c64
+    assert fn(dp(xx), dp(oo), n, rows, bd.F_SHIFT | bd.F_WINDOW(bd.HAMMING)) == 0
+for n in (1024, 2048, 4096):
+    xx = DspVec(rc(n * 6, np.complex128)); oo = DspVec.zeros(2 * n * 6, is_complex=True, dtype=np.float64)
+    for flags in (0, bd.F_SHIFT | bd.F_MAGNITUDE, bd.F_INVERSE | bd.F_SHIFT):
+        assert L.bdsp_fft_rows_c64(dp(xx), dp(oo), n, 6, flags) == 0
+xx = DspVec(rc(65536 * 3)); oo = DspVec.zeros(2 * 65536 * 3, is_complex=True, dtype=np.float32)
+for flags in (0, bd.F_SHIFT, bd.F_INVERSE | bd.F_SHIFT):
+    assert L.bdsp_fft_rows_c32(dp(xx), dp(oo), 65536, 3, flags) == 0
+DspVec(rc(259779, np.complex128)).convolve_signal(DspVec(rc(167, np.complex128))).to_numpy()
+DspVec(rc(50000, np.complex128)).convolve_signal(DspVec(rc(2047, np.complex128))).to_numpy()
+DspVec(rc(1 << 16)).convolve_signal(DspVec(rc(6000))).to_numpy()
+a, b = DspVec(rc(3001)), DspVec(rc(3001))
+a.correlate(b.prepare_argument_padded())
+a.to_numpy()
 L.bdsp_sync()
 print("sanitize smoke done")
