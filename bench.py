@@ -346,7 +346,7 @@ def run_gpu(args):
                        "sharding": "rows, no collective", "cpus_per_rank": len(affinity) if affinity else None},
             "gflops_5nlog2n": flops * world / (total_ms_max / args.steps * 1e-3) / 1e9,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": 1027147776.0, "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/r2_ols4096i_ncu.txt)",
+                         "traffic": 1030119424.0, "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/r2_ols4096i_ncu.txt)",
                          "kernel": "ols4096i_kernel<true>", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_ms,
                          "min_launch_ms": min(per_launch_ms)},
