@@ -34,6 +34,10 @@ using namespace cx;
 #ifndef OI_H_LDG
 #define OI_H_LDG 0
 #endif
+// 1: request the spectrum values of a half before its shared loads and transform (32 more live registers)
+#ifndef OI_H_EARLY
+#define OI_H_EARLY 0
+#endif
 #ifndef OI_MIN_CTAS
 #define OI_MIN_CTAS 5
 #endif
@@ -130,6 +134,11 @@ ols4096i_kernel(const float2* __restrict__ x, float2* __restrict__ y, int N, int
 #pragma unroll 1
     for (int half = 0; half < 2; half++) {
         float2* grp = row + 16 * (lo + 8 * half);
+#if OI_H_EARLY
+        float4 hq[8];      // spectrum values of this half, requested before the shared loads and the transform
+#pragma unroll
+        for (int q = 0; q < 8; q++) hq[q] = tex1Dfetch<float4>(htex, (half * 8 + q) * OI_T + t);
+#endif
         c2 P[16];
 #pragma unroll
         for (int q = 0; q < 8; q++) {
@@ -141,7 +150,11 @@ ols4096i_kernel(const float2* __restrict__ x, float2* __restrict__ y, int N, int
 #pragma unroll
         for (int q = 0; q < 8; q++) {
             // plan layout: [half][q][thread] float4 = H of positions c = 2q, 2q + 1 -> a warp reads 512 contiguous bytes
+#if OI_H_EARLY
+            const float4 h = hq[q];
+#else
             const float4 h = (OI_ABLATE & 8) ? make_float4(1.f, 0.f, 1.f, 0.f) : OI_H_LDG ? __ldg(hpos + (half * 8 + q) * OI_T + t) : tex1Dfetch<float4>(htex, (half * 8 + q) * OI_T + t);
+#endif
             P[2 * q] = mul(P[2 * q], make_float2(h.x, h.y));
             P[2 * q + 1] = mul(P[2 * q + 1], make_float2(h.z, h.w));
         }
