@@ -78,6 +78,15 @@ __device__ __forceinline__ double2 cmul_nofma(double2 a, double2 b) {
 __device__ __forceinline__ void sincospi_t(float x, float* s, float* c) { sincospif(x, s, c); }
 __device__ __forceinline__ void sincospi_t(double x, double* s, double* c) { sincospi(x, s, c); }
 
+// kernel attributes (dynamic shared memory size, carve-out) belong to the function IN ONE DEVICE'S context: launchers
+// configure once per device, not once per process (a process may drive several devices through bdsp_set_device)
+struct PerDeviceOnce {
+    bool done[64] = {};
+    int dev = 0;
+    bool need() { if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { dev = -1; return true; } return !done[dev]; }
+    void mark() { if (dev >= 0) done[dev] = true; }
+};
+
 // --- programmatic dependent launch (sm_90+): a kernel launched with launch_pdl() may become resident while the previous
 // kernel of the stream is still draining; pdl_wait() (griddepcontrol.wait) blocks until that kernel has completed and its
 // memory is visible, and must precede the first global access.  pdl_trigger() lets the NEXT kernel start its launch early.

@@ -740,10 +740,10 @@ int fftp_launch(const void* in, void* out, size_t rows, float scale, cudaStream_
     constexpr int NSB = R0 / CL;
     const size_t smem = (size_t)2 * NSB * FP_B_OF(NSB) * sizeof(float);
     auto kern = fftp_kernel<R0, CL, INV, SI, SO, MAG, ROWS, TQ, NATQ, RIN, SQ>;
-    static bool configured = false;   // per instantiation
-    if (!configured) {
+    static PerDeviceOnce configured;   // per instantiation and device
+    if (configured.need()) {
         BDSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured.mark();
     }
     const float* tw = fftp_twiddles();
     if (!tw) return -1001;

@@ -314,10 +314,10 @@ template <bool INV, bool SI, bool SO, bool MAG>
 int f16_launch(const void* in, void* out, size_t rows, float scale, cudaStream_t st) {
     const size_t smem = (size_t)2 * 4 * F16_B * sizeof(float) + (F16_TMA_STAGE ? F16_STG_BYTES + 16 : 0);
     auto kern = fftp16k_kernel<INV, SI, SO, MAG>;
-    static bool configured = false;   // per instantiation
-    if (!configured) {
+    static PerDeviceOnce configured;   // per instantiation and device
+    if (configured.need()) {
         BDSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured.mark();
     }
     const float* tw = fftp_twiddles();
     if (!tw) return -1001;

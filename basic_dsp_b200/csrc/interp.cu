@@ -321,11 +321,11 @@ int interp_poly(const void* x, void* y, const T* tab_dev, size_t N, size_t new_p
             const size_t stage = (size_t)IPF_THREADS * IPF_ROW * 4;
             if (smem < stage) smem = stage;
             const long long grid = (rows + IPF_POS - 1) / IPF_POS;
-            static bool configured = false;
-            if (!configured) {
+            static PerDeviceOnce configured;
+            if (configured.need()) {
                 BDSP_CUDA_OK(cudaFuncSetAttribute(interp_poly_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024)));
                 BDSP_CUDA_OK(cudaFuncSetAttribute(interp_poly_f32_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-                configured = true;
+                configured.mark();
             }
             interp_poly_f32_kernel<<<(unsigned)grid, IPF_THREADS, smem, st>>>(reinterpret_cast<const float*>(x), reinterpret_cast<float*>(y),
                                                                               reinterpret_cast<const float*>(tab_dev), (long long)N,

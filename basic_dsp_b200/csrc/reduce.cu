@@ -238,11 +238,11 @@ int run_reduce(const void* a, const void* b, size_t elems, int cplx, int parts, 
     if (!dev) return -1001;
     Rec* dev_out = dev + blocks * parts;
     const size_t shm = sizeof(Rec) * RT;
-    static bool configured = false;   // per instantiation
-    if (!configured) {
+    static PerDeviceOnce configured;   // per instantiation and device
+    if (configured.need()) {
         BDSP_CUDA_OK(cudaFuncSetAttribute(reduce_kernel<T, MODE, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
         BDSP_CUDA_OK(cudaFuncSetAttribute(fold_kernel<PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-        configured = true;
+        configured.mark();
     }
     reduce_kernel<T, MODE, PREC><<<dim3((unsigned)blocks, (unsigned)parts), RT, shm, st>>>(reinterpret_cast<const T*>(a), reinterpret_cast<const T*>(b),
                                                                                         (long long)elems, cplx, dev);
