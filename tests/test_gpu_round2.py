@@ -454,3 +454,34 @@ def test_windowed_fft_rows(n, rows, dtype):
     for r in (0, rows - 1):
         assert o.rel_l2(gr[r], o.windowed_fft(xr[r].real.astype(x.dtype), bd.HAMMING, dtype)) <= tol(n, dtype), r
     assert fn(dptr(xv), dptr(out), n, rows, bd.F_INVERSE | bd.F_WINDOW(bd.HAMMING)) != 0   # forward transforms only
+
+
+def test_two_devices_in_one_process():
+    """One process driving two devices (bdsp_set_device): kernels that need more than 48 KB of dynamic shared memory are
+    configured per device, plans / tables / workspaces are per device."""
+    if bd.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    L = bd.lib()
+    rng = np.random.default_rng(2)
+    try:
+        for dev in (0, 1, 0):
+            assert L.bdsp_set_device(dev) == 0
+            n, rows = 16384, 3
+            x = rand_c(rng, n * rows, np.float32)
+            xv = DspVec(x)
+            out = DspVec.zeros(2 * n * rows, is_complex=True)
+            assert L.bdsp_fft_rows_c32(dptr(xv), dptr(out), n, rows, 0) == 0
+            got = out.to_numpy().reshape(rows, n)
+            assert o.rel_l2(got[1], o.plain_fft(x.reshape(rows, n)[1])) <= tol(n, np.float32)
+            xs = rand_c(rng, 1 << 16, np.float32)
+            h = (rand_c(rng, 1023, np.float32) / 10).astype(np.complex64)
+            y = DspVec(xs).convolve_signal(DspVec(h)).to_numpy()
+            assert o.rel_l2(y, o.convolve_signal(xs, h)) <= tol(1 << 16, np.float32)
+            assert o.rel_l2(DspVec(xs).fft().ifft().to_numpy(), xs) <= 2 * tol(1 << 16, np.float32)
+            xd = rand_c(rng, 3 * (1 << 14), np.float64)
+            assert o.rel_l2(DspVec(xd).plain_fft().to_numpy(), o.plain_fft(xd)) <= tol(xd.size, np.float64)
+            r = rng.uniform(-1, 1, 20001).astype(np.float32)
+            DspVec(r).interpolatef(bd.SINC, 0.0, 4.0, 0.0, 12).to_numpy()
+            assert abs(DspVec(r).sum() - float(np.sum(r.astype(np.float64)))) < 1e-2
+    finally:
+        L.bdsp_set_device(0)
