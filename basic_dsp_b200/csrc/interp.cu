@@ -58,7 +58,10 @@ interp_poly_tiled_kernel(const void* __restrict__ x_, void* __restrict__ y_, con
     constexpr int POS = IP2_THREADS * RP;                     // input positions per CTA
     T* stab = reinterpret_cast<T*>(smem_raw);                 // interior taps, [J][FMAX]
     X* sx = reinterpret_cast<X*>(stab + ((J * FMAX + 3) & ~3));
-    const long long r0 = (long long)blockIdx.x * POS;
+    // the LAST tile of a vector takes the slow per-output path with wrap-around: it runs first (CTA 0), next to the first tile
+    // (CTA 1), so that its latency-bound loop overlaps the whole grid instead of forming the kernel's tail
+    const long long tile_ix = blockIdx.x == 0 ? (long long)gridDim.x - 1 : (long long)blockIdx.x - 1;
+    const long long r0 = tile_ix * POS;
     const bool interior = (r0 * F >= scalar_len) && ((r0 + POS) * F <= new_points - scalar_len);
     if (!interior) {
         // edge CTA: one output at a time, tap table chosen per output
@@ -191,23 +194,14 @@ interp_poly_f32_kernel(const float* __restrict__ x, float* __restrict__ y, const
     const int JI = 2 * L + 2;                                  // the last window slot has no interior tap
     float4* stab = reinterpret_cast<float4*>(smem_raw);        // interior taps, [J] x {s0, s1, s2, s3}
     float2* sxx = reinterpret_cast<float2*>(stab + J);         // duplicated window
-    const long long r0 = (long long)blockIdx.x * IPF_POS;
+    // Tiles that touch the ends of the vector run the same packed path over a window loaded with wrap-around (interior
+    // outputs never need wrapped samples; the read-ahead slots and the outputs of the edge regions merely have to stay in
+    // bounds) and then overwrite the (2 L + 1) F outputs of each edge region with the per-output form below.  They used to
+    // take the per-output form for all their 2048 outputs - 27 latency-bound loads per output on 64 threads - and the last
+    // tile, scheduled last, was the kernel's tail (ncu: SMs active for 70 % of the duration).  Edge tiles still go first.
+    const long long tile_ix = blockIdx.x == 0 ? (long long)gridDim.x - 1 : (long long)blockIdx.x - 1;
+    const long long r0 = tile_ix * IPF_POS;
     const bool interior = (r0 * F >= scalar_len) && ((r0 + IPF_POS) * F <= new_points - scalar_len);
-    if (!interior) {
-        for (long long i = r0 * F + threadIdx.x; i < (r0 + IPF_POS) * F && i < new_points; i += IPF_THREADS) {
-            const long long r = i / F; const int s = (int)(i - r * F);
-            const bool in = (i >= scalar_len) && (i < new_points - scalar_len);
-            const float* t = tab + (in ? 0 : F * J) + s * J;
-            long long g = (r - L - 1) % N; if (g < 0) g += N;
-            float acc = 0.f;
-            for (int j = 0; j < J; j++) {
-                acc += x[g] * t[j];
-                g++; if (g >= N) g -= N;
-            }
-            y[i] = acc;
-        }
-        return;
-    }
     for (int j = threadIdx.x; j < J; j += IPF_THREADS) {
         float4 t4;
         t4.x = tab[j];
@@ -218,11 +212,21 @@ interp_poly_f32_kernel(const float* __restrict__ x, float* __restrict__ y, const
     }
     const int W = IPF_POS + JI - 1 + IPF_RP;
     {
-        const float* xs = x + (r0 - L - 1);
-        const long long wmax = N - 1 - (r0 - L - 1);          // the last IPF_RP slots are read ahead of use: keep them inside the vector
-        for (int w = threadIdx.x; w < W; w += IPF_THREADS) {
-            const float v = xs[w <= wmax ? w : (int)wmax];
-            sxx[ipf_skew(w)] = make_float2(v, v);
+        if (interior) {
+            const float* xs = x + (r0 - L - 1);
+            const long long wmax = N - 1 - (r0 - L - 1);      // the last IPF_RP slots are read ahead of use: keep them inside the vector
+            for (int w = threadIdx.x; w < W; w += IPF_THREADS) {
+                const float v = xs[w <= wmax ? w : (int)wmax];
+                sxx[ipf_skew(w)] = make_float2(v, v);
+            }
+        } else {
+            long long g = (r0 - L - 1 + threadIdx.x) % N; if (g < 0) g += N;
+            const long long adv = IPF_THREADS % N;
+            for (int w = threadIdx.x; w < W; w += IPF_THREADS) {
+                const float v = x[g];
+                sxx[ipf_skew(w)] = make_float2(v, v);
+                g += adv; if (g >= N) g -= N;
+            }
         }
     }
     __syncthreads();
@@ -291,14 +295,40 @@ interp_poly_f32_kernel(const float* __restrict__ x, float* __restrict__ y, const
             const int o = 4 * (threadIdx.x + IPF_THREADS * it);
             const float* sp = so + (o >> (IPF_LRP + 2)) * IPF_ROW + (o & (4 * IPF_RP - 1));
             const float2 a = *reinterpret_cast<const float2*>(sp), b = *reinterpret_cast<const float2*>(sp + 2);
-            *reinterpret_cast<float4*>(yo + o) = make_float4(a.x, a.y, b.x, b.y);
+            if (interior || r0 * F + o + 3 < new_points) *reinterpret_cast<float4*>(yo + o) = make_float4(a.x, a.y, b.x, b.y);
+            else
+                for (int e = 0; e < 4; e++)
+                    if (r0 * F + o + e < new_points) yo[o + e] = sp[e];
         }
     } else {
         const int per_thread = IPF_RP * F;
         const int total = IPF_POS * F;
         for (int o = threadIdx.x; o < total; o += IPF_THREADS) {
             const int tt = o / per_thread, e = o - tt * per_thread;
-            yo[o] = so[tt * IPF_ROW + e];
+            if (interior || r0 * F + o < new_points) yo[o] = so[tt * IPF_ROW + e];
+        }
+    }
+    if (!interior) {
+        // outputs of the two edge regions inside this tile: taps chosen per output, circular window (interpolation.rs:191-290)
+        __syncthreads();
+        const long long lo = r0 * F, hi = (r0 + IPF_POS) * F < new_points ? (r0 + IPF_POS) * F : new_points;
+        const long long b0 = hi < scalar_len ? hi : scalar_len;                     // end of the leading edge region in this tile
+        long long a1 = lo > new_points - scalar_len ? lo : new_points - scalar_len;   // start of the trailing one
+        if (a1 < b0) a1 = b0;                                                        // (short vectors: the regions meet)
+        for (int pass = 0; pass < 2; pass++) {
+            const long long a = pass == 0 ? lo : a1;
+            const long long b = pass == 0 ? b0 : hi;
+            for (long long i = a + threadIdx.x; i < b; i += IPF_THREADS) {
+                const long long r = i / F; const int s = (int)(i - r * F);
+                const float* t = tab + F * J + s * J;
+                long long g = (r - L - 1) % N; if (g < 0) g += N;
+                float acc = 0.f;
+                for (int j = 0; j < J; j++) {
+                    acc += x[g] * t[j];
+                    g++; if (g >= N) g -= N;
+                }
+                y[i] = acc;
+            }
         }
     }
 }
