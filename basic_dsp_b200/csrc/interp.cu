@@ -355,11 +355,14 @@ interp_poly_f32p_kernel(const float* __restrict__ x, float* __restrict__ y, cons
     float2* bufs = reinterpret_cast<float2*>(stab + J);        // two window buffers of buf_f2 float2 each
     const int W = IPF_POS + JI - 1 + IPF_RP;
     const int t = threadIdx.x;
-    auto interior_of = [&](long long tile) {
-        const long long r0 = tile * IPF_POS;
+    // work item -> tile: the vector's last tile (slow per-output path) is item 0, so that it does not end up as the tail
+    auto tile_of = [&](long long item) { return item == 0 ? ntiles - 1 : item - 1; };
+    auto interior_of = [&](long long item) {
+        const long long r0 = tile_of(item) * IPF_POS;
         return (r0 * F >= scalar_len) && ((r0 + IPF_POS) * F <= new_points - scalar_len);
     };
-    auto prefetch = [&](long long tile, float2* dst) {
+    auto prefetch = [&](long long item, float2* dst) {
+        const long long tile = tile_of(item);
         const float* xs = x + (tile * IPF_POS - L - 1);
         const long long wmax = N - 1 - (tile * IPF_POS - L - 1);   // read-ahead slots stay inside the vector
         for (int w = t; w < W; w += IPF_THREADS) {
@@ -390,7 +393,7 @@ interp_poly_f32p_kernel(const float* __restrict__ x, float* __restrict__ y, cons
                                                                // everybody is done with the other buffer
         if (nxt < ntiles && interior_of(nxt)) prefetch(nxt, bufs + (b ^ 1) * buf_f2);
         asm volatile("cp.async.commit_group;" ::: "memory");
-        const long long r0 = tile * IPF_POS;
+        const long long r0 = tile_of(tile) * IPF_POS;
         if (!interior_of(tile)) {                              // first / last tiles of the vector: per-output taps with wrap-around
             for (long long i = r0 * F + t; i < (r0 + IPF_POS) * F && i < new_points; i += IPF_THREADS) {
                 const long long r = i / F; const int s = (int)(i - r * F);
