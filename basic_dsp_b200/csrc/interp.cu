@@ -163,7 +163,8 @@ interp_poly_tiled_kernel(const void* __restrict__ x_, void* __restrict__ y_, con
 // 16 FFMA2 for 32 outputs.
 // ------------------------------------------------------------------------------------------
 // threads per CTA: small CTAs keep the barrier-separated load / compute / store phases of different CTAs overlapping on
-// the SM.  Measured on B200 (C4a, 2^24 samples x4): 256 threads 0.160 ms, 128: 0.142, 64: 0.133, 32: 0.136.
+// the SM.  Measured on B200 (C4a, 2^24 samples x4): 256 threads 0.160 ms, 128: 0.142, 64: 0.133, 32: 0.136 while the vector's last
+// tile was the kernel's tail (+ ~25 us on every variant); with the end tiles first: 256: 0.117, 128: 0.109, 64: 0.111, 32: 0.118.
 #ifndef IPF_THREADS
 #define IPF_THREADS 64
 #endif
@@ -333,6 +334,7 @@ interp_poly_f32_kernel(const float* __restrict__ x, float* __restrict__ y, const
     }
 }
 
+#if IPF_PERSISTENT
 // ------------------------------------------------------------------------------------------
 // Persistent, double-buffered form of interp_poly_f32_kernel for F = 4 (BASELINE C4a): a CTA walks tiles of IPF_POS
 // positions; the window of the NEXT tile arrives through cp.async (two 4-byte copies per sample: the duplicated {x, x}
@@ -472,6 +474,8 @@ interp_poly_f32p_kernel(const float* __restrict__ x, float* __restrict__ y, cons
     }
 }
 
+#endif
+
 template <typename T>
 int interp_poly(const void* x, void* y, const T* tab_dev, size_t N, size_t new_points, int F, int L, int is_complex,
                 cudaStream_t st) {
@@ -493,7 +497,8 @@ int interp_poly(const void* x, void* y, const T* tab_dev, size_t N, size_t new_p
         interp_poly_tiled_kernel<T, CP, FM, RPV><<<(unsigned)grid, IP2_THREADS, smem, st>>>(x, y, tab_dev, (long long)N, (long long)new_points, F, L, scalar_len); \
     } while (0)
         if (is_complex) { if (F <= 4) BDSP_IP2(true, 4, 2); else BDSP_IP2(true, 8, 1); }
-        else if (F == 4 && sizeof(T) == 4 && IPF_PERSISTENT && rows >= 64 * IPF_POS) {
+#if IPF_PERSISTENT
+        else if (F == 4 && sizeof(T) == 4 && rows >= 64 * IPF_POS) {
             // long real f32 vectors, factor 4: persistent CTAs with the next tile's window in flight during the FFMA2 loop
             const size_t wlen = (size_t)IPF_POS + J + 2 * IPF_RP;
             size_t buf_f2 = wlen + wlen / IPF_RP + 2;
@@ -514,6 +519,7 @@ int interp_poly(const void* x, void* y, const T* tab_dev, size_t N, size_t new_p
                                                                                reinterpret_cast<const float*>(tab_dev), (long long)N,
                                                                                (long long)new_points, L, scalar_len, ntiles, (int)buf_f2, sm_count());
         }
+#endif
         else if (F <= 4 && sizeof(T) == 4) {
             const size_t wlen = (size_t)IPF_POS + J + 2 * IPF_RP;
             size_t smem = (size_t)J * 16 + (wlen + wlen / IPF_RP + 2) * 8;
