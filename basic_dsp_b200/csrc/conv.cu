@@ -270,13 +270,18 @@ fir_kernel(const void* __restrict__ x_, void* __restrict__ y_, const void* __res
     // layout: taps (L entries of C), then the window (FIR_TILE + L - 1 entries of C, +pad)
     C* sh = reinterpret_cast<C*>(smem_raw);
     C* sx = sh + L;
-    const long long vec = blockIdx.x / tiles_per_vec;
-    const long long tile = blockIdx.x - vec * tiles_per_vec;
+    const unsigned tpv = (unsigned)tiles_per_vec;            // (the grid has fewer than 2^31 tiles)
+    const unsigned vec_u = blockIdx.x / tpv;
+    const long long vec = vec_u;
+    const long long tile = blockIdx.x - vec_u * tpv;
     const long long i0 = tile * FIR_TILE;
     const int W = FIR_TILE + L - 1;
     // window element w corresponds to x[(i0 - (L - cl) + w) mod N]
-    long long p0 = (i0 - (L - cl)) % N;
-    if (p0 < 0) p0 += N;
+    // (64-bit remainders cost ~100 instructions each: vectors longer than a tile + taps need conditional corrections only)
+    const bool big = N >= (long long)FIR_TILE + L;
+    long long p0 = i0 - (L - cl);
+    if (big) { if (p0 < 0) p0 += N; }
+    else { p0 %= N; if (p0 < 0) p0 += N; }
     for (int k = threadIdx.x; k < L; k += FIR_THREADS) {
         C t;
         if (HC) t = reinterpret_cast<const C*>(h_)[k];
@@ -284,8 +289,9 @@ fir_kernel(const void* __restrict__ x_, void* __restrict__ y_, const void* __res
         sh[k] = t;
     }
     {
-        long long g = (p0 + threadIdx.x) % N;
-        const long long adv = FIR_THREADS % N;
+        long long g = p0 + threadIdx.x;
+        if (big) { if (g >= N) g -= N; } else g %= N;
+        const long long adv = big ? FIR_THREADS : FIR_THREADS % N;
         for (int w = threadIdx.x; w < W; w += FIR_THREADS) {
             C v;
             if (XC) v = reinterpret_cast<const C*>(x_)[vec * N + g];
