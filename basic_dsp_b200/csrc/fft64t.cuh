@@ -65,12 +65,12 @@ template <int LOG2M, int LCT, int Q> struct Geo {
     static constexpr int M = 1 << LOG2M, CT = 1 << LCT, J = M / 8;
     static constexpr int NT = J * CT * Q;
     static constexpr int UNITS = M * CT + (LCT < 3 ? M * CT / 8 : 0);   // padded complex words per sub-sequence region
-    static constexpr size_t SMEM = ((size_t)UNITS * Q + CT + (Q > 1 ? M : 0)) * sizeof(double2);
+    static constexpr size_t SMEM = ((size_t)UNITS * Q + CT) * sizeof(double2);
 };
 
 template <int LOG2M, int LCT, int Q, bool INV>
 __global__ void __launch_bounds__(Geo<LOG2M, LCT, Q>::NT, Q == 1 ? (F64T_MIN_CTAS * 256) / Geo<LOG2M, LCT, Q>::NT : F64T_Q3_MIN_CTAS)
-f64_tile_kernel(TileParams p, double scale, const double2* __restrict__ tw) {
+f64_tile_kernel(TileParams p, double scale, const double2* __restrict__ tw, const double2* __restrict__ w3tab) {
     typedef Geo<LOG2M, LCT, Q> G;
     constexpr int M = G::M, CT = G::CT, J = G::J, NT = G::NT;
     constexpr int R3 = LOG2M == 6 ? 1 : M / 64;   // radix of the third stage (m = 8 * 8 * R3; 1: two stages)
@@ -79,7 +79,6 @@ f64_tile_kernel(TileParams p, double scale, const double2* __restrict__ tw) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2* sbase = reinterpret_cast<double2*>(smem_raw);
     double2* sstep = sbase + G::UNITS * Q;        // per-lane step root W_tw^{lane * stepk}
-    double2* sw3 = sstep + CT;                    // Q = 3: W_{3m}^b, b < m
     const int tid = threadIdx.x;
     const int l = tid & (CT - 1);
     const int jq = tid >> LCT;
@@ -134,20 +133,19 @@ f64_tile_kernel(TileParams p, double scale, const double2* __restrict__ tw) {
             const int bi = tid + it * NT;
             if (bi < NB) {
                 const int l3 = bi & (CT - 1), b3 = bi >> LCT;
-                const long long g0 = (tile * CT + l3) * p.in_lane_stride + (long long)b3 * p.in_point_stride + p.in_rot;
+                const int n_in = (int)p.in_n;   // positions inside a sequence fit 32 bits
+                const int g0 = (int)(tile * CT + l3) * (int)p.in_lane_stride + b3 * (int)p.in_point_stride + (int)p.in_rot;
 #pragma unroll
                 for (int a = 0; a < 3; a++) {
-                    long long g = g0 + (long long)a * M * p.in_point_stride;
-                    if (g >= p.in_n) g -= p.in_n;
+                    int g = g0 + a * M * (int)p.in_point_stride;
+                    if (g >= n_in) g -= n_in;
                     if (p.real_input) y[it][a] = make_double2(reinterpret_cast<const double*>(p.in)[inb + g], 0.0);
                     else y[it][a] = reinterpret_cast<const double2*>(p.in)[inb + g];
                     if (p.im.kind) y[it][a] = in_mul_apply<double>(y[it][a], p.im.p, p.im.kind, p.im.arg, g, p.in_n);
                 }
             }
         }
-        for (int i = tid; i < M; i += NT) sw3[i] = root_of<INV>((unsigned long long)i, 3 * M, 1.0 / (3.0 * M));
-        if (p.tw_n && tid < CT) sstep[tid] = root_of<INV>((unsigned long long)(tile * CT + tid) * stepk, p.tw_n, inv_tw);
-        __syncthreads();
+        if (p.tw_n && tid < CT) sstep[tid] = root_of<INV>((unsigned long long)(tile * CT + tid) * stepk, p.tw_n, inv_tw);   // read after later barriers
         const double sn = INV ? 0.86602540378443864676 : -0.86602540378443864676;   // Im W_3
 #pragma unroll
         for (int it = 0; it < IT; it++) {
@@ -157,7 +155,7 @@ f64_tile_kernel(TileParams p, double scale, const double2* __restrict__ tw) {
                 const double2 y0 = y[it][0], t = cadd(y[it][1], y[it][2]), d = csub(y[it][1], y[it][2]);
                 const double2 m0 = make_double2(y0.x - 0.5 * t.x, y0.y - 0.5 * t.y);
                 const double2 id = make_double2(-sn * d.y, sn * d.x);          // i * Im(W_3) * (y1 - y2)
-                const double2 w1 = sw3[b3];
+                const double2 w1 = conj_if(__ldg(&w3tab[b3]), INV);     // W_{3m}^b from the per-device table (forward sign)
                 const int u = (b3 << LCT) + l3;
                 const int word = LCT < 3 ? u + ((u >> (3 + LCT)) << LCT) : u;
                 sbase[word] = cadd(y0, t);
@@ -254,8 +252,29 @@ int launch_one(const TileParams& p, long long batch, double scale, const double2
     } else if (dev >= 16) {
         BDSP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
     }
+    const double2* w3tab = nullptr;
+    if (Q == 3) {
+        // W_{3m}^b, b < m (forward sign), evaluated once per device on the host in long double
+        static double2* tabs[16] = {};
+        static std::mutex mu;
+        std::lock_guard<std::mutex> lk(mu);
+        if (dev >= 16) return 1;
+        if (!tabs[dev]) {
+            std::vector<double2> h(G::M);
+            const long double tau = 2.0L * 3.14159265358979323846264338327950288L;
+            for (int b = 0; b < G::M; b++) {
+                h[b].x = (double)cosl(tau * (long double)b / (long double)(3 * G::M));
+                h[b].y = (double)-sinl(tau * (long double)b / (long double)(3 * G::M));
+            }
+            double2* d = nullptr;
+            BDSP_CUDA_OK(cudaMalloc(&d, sizeof(double2) * G::M));
+            BDSP_CUDA_OK(cudaMemcpy(d, h.data(), sizeof(double2) * G::M, cudaMemcpyHostToDevice));
+            tabs[dev] = d;
+        }
+        w3tab = tabs[dev];
+    }
     const dim3 grid((unsigned)(p.lanes >> LCT), (unsigned)p.o1_count, (unsigned)batch);
-    kernel<<<grid, G::NT, G::SMEM, st>>>(p, scale, tw);
+    kernel<<<grid, G::NT, G::SMEM, st>>>(p, scale, tw, w3tab);
     return 0;
 }
 
