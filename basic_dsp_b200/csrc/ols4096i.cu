@@ -38,6 +38,9 @@ using namespace cx;
 #ifndef OI_H_EARLY
 #define OI_H_EARLY 0
 #endif
+#ifndef OLS_L2_AHEAD
+#define OLS_L2_AHEAD 0   // blocks ahead (740 = resident CTAs): measured 0.3194 vs 0.3183 ms without - off
+#endif
 #ifndef OI_MIN_CTAS
 #define OI_MIN_CTAS 5
 #endif
@@ -70,6 +73,22 @@ ols4096i_kernel(const float2* __restrict__ x, float2* __restrict__ y, int N, int
         const int col = 2 * t;
         // block position p holds x[(p0 + p) mod N], p0 = i0 + shift - m_first  (p0 > -4096, even)
         const int p0 = i0 + shift - m_first;
+#if OLS_L2_AHEAD > 0
+        // one thread asks L2 for the NEW inputs (step points) of the block that takes this CTA's slot next: blocks are
+        // scheduled in index order, so block index + (resident CTAs of the grid) starts about when this one ends
+        if (ALIGNED && t == 0) {
+            const long long nb = (long long)blockIdx.x + OLS_L2_AHEAD;
+            if (nb < (long long)gridDim.x) {
+                const long long nvec = nb / blocks_per_vec;
+                const int nblk = (int)(nb - nvec * blocks_per_vec);
+                const long long q0 = (long long)nblk * step + shift - m_first + (OI_M - step);   // first input not shared with its predecessor
+                if (q0 >= 0 && q0 + step <= N) {
+                    const float2* pf = x + (size_t)nvec * (size_t)N + q0;
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pf), "r"(step * 8) : "memory");
+                }
+            }
+        }
+#endif
         if (p0 >= 0 && p0 + OI_M <= N) {   // block-uniform: no wrap-around inside this block
             const float2* px = xr + p0 + col;
 #pragma unroll
